@@ -1,0 +1,342 @@
+"""ORACLE (test infrastructure, NOT product code) -- CLD SDE tables + DEIS sampler, numpy fp64.
+
+Parity status: **parity unpinned** by the reference (its tests assert nothing); this
+restatement is pinned by the analytic known-answer identities of SURVEY.md 8(c) in
+tests/test_oracle_cld.py.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this package.
+
+Follows (file:line relative to /root/reference):
+  cld_jax/sde_lib.py:17-43     inv_2x2, get_interp_fn
+  cld_jax/sde_lib.py:45-118    CLD.__init__, _get_s_R_fn (scan in oracle/cld_ode.c or the python loop here)
+  cld_jax/sde_lib.py:182-253   s_psi, s_eps_integrand, s_F, s_G, eps2score
+  cld_jax/sde_lib.py:289-319   prepare_order0_coef, get_deis_coef
+  cld_jax/deis.py:19-95        DEIS Adams-Bashforth coefficient tables
+  cld_jax/deis.py:141-151      multistep_ab_step
+  cld_jax/sampling.py:23-39    get_denoising_step
+  cld_jax/sampling.py:156-253  get_order0_sampler, _impl_deis_sampler, get_rev_ts, get_deis_sampler
+  cld_jax/models/utils.py:153-176  (d g)->(g d) relayout, labels = 999 t, mixed_score
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcld_ode.so")
+
+
+def build_c(force=False):
+  """gcc-compile the C scan (oracle/cld_ode.c).  Called by __graft_entry__.build() and lazily here."""
+  src = os.path.join(_HERE, "cld_ode.c")
+  if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    os.makedirs(os.path.dirname(_SO), exist_ok=True)
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", _SO, src, "-lm"])
+  return _SO
+
+
+_lib = None
+
+
+def _clib():
+  global _lib
+  if _lib is None:
+    _lib = ctypes.CDLL(build_c())
+    _lib.oracle_cld_scan_R.restype = None
+    _lib.oracle_cld_scan_R.argtypes = [ctypes.c_double] * 4 + [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
+  return _lib
+
+
+def inv_2x2(m):
+  """sde_lib.py:17-26 (batched over leading axes)."""
+  a, b, c, d = m[..., 0, 0], m[..., 0, 1], m[..., 1, 0], m[..., 1, 1]
+  coef = 1.0 / (a * d - b * c)
+  out = np.empty_like(m)
+  out[..., 0, 0] = d * coef
+  out[..., 0, 1] = -b * coef
+  out[..., 1, 0] = -c * coef
+  out[..., 1, 1] = a * coef
+  return out
+
+
+def get_rev_ts(T, sampling_eps, ts_order, num_step):
+  """sampling.py:241-249 (fp64 here; the reference evaluates it in fp32)."""
+  return np.power(np.linspace(np.power(T, 1.0 / ts_order), np.power(sampling_eps, 1.0 / ts_order), num_step + 1),
+                  ts_order)
+
+
+class CLD:
+  """cld_jax/sde_lib.py:45-319, fp64, no pickle cache."""
+
+  def __init__(self, m_inv=4.0, beta_0=4.0, beta_1=0.0, vv_gamma=0.04, numerical_eps=1e-6,
+               mixed_score=False, is_R_rk=False, R_dt=1e-5, use_c=True):
+    self.mixed_score = mixed_score
+    self.m_inv = float(m_inv)
+    self.Gamma = 2.0 / np.sqrt(m_inv)
+    self.beta_0 = float(beta_0)
+    self.beta_1 = float(beta_1)
+    self.R_0 = np.array([[np.sqrt(numerical_eps), 0.0], [0.0, np.sqrt(vv_gamma / m_inv + numerical_eps)]])
+    self.sampling_eps = 1e-3
+    self.T = 1.0
+    self.is_R_rk = bool(is_R_rk)
+    self.R_dt = float(R_dt)
+    self._build_R_table(use_c)
+
+  # ---- schedule -------------------------------------------------------------------------------
+  def beta(self, t):
+    return self.beta_0 + self.beta_1 * t
+
+  def beta_int(self, t):
+    return self.beta_0 * t + 0.5 * self.beta_1 * t ** 2
+
+  # ---- R(t) -----------------------------------------------------------------------------------
+  def _ode_rhs(self, R, t):
+    """sde_lib.py:94-97."""
+    F, G = self.s_F(t), self.s_G(t)
+    return F @ R + 0.5 * G @ G.T @ inv_2x2(R).T
+
+  def _scan_py(self, ts):
+    """Pure-python scan (slow; used to cross-check the C scan on short grids).  sde_lib.py:98-107."""
+    R = self.R_0.copy()
+    out = np.empty((len(ts), 2, 2))
+    dt = self.R_dt
+    for k, t in enumerate(ts):
+      out[k] = R
+      if self.is_R_rk:                                        # deis.py:5-17
+        g1 = self._ode_rhs(R, t)
+        g2 = self._ode_rhs(R + g1 * dt / 2, t + dt / 2)
+        g3 = self._ode_rhs(R + g2 * dt / 2, t + dt / 2)
+        g4 = self._ode_rhs(R + g3 * dt, t + dt)
+        R = R + dt / 6 * (g1 + 2 * g2 + 2 * g3 + g4)
+      else:                                                   # "mid point integral"
+        F = (self.s_F(t) + self.s_F(t + dt)) / 2.0
+        G = (self.s_G(t) + self.s_G(t + dt)) / 2.0
+        R = R + dt * (F @ R + 0.5 * G @ G @ np.linalg.inv(R).T)
+    return out
+
+  def _grid(self):
+    n = int(1.0 / self.R_dt)                                  # sde_lib.py:109 (99999 for 1e-5!)
+    return np.linspace(0, 1.0 + self.R_dt, n + 1, endpoint=False)
+
+  def _build_R_table(self, use_c):
+    ts = self._grid()
+    if use_c:
+      Rs = np.empty((len(ts), 2, 2))
+      R0 = np.ascontiguousarray(self.R_0)
+      tsc = np.ascontiguousarray(ts)
+      _clib().oracle_cld_scan_R(self.m_inv, self.beta_0, self.beta_1, self.Gamma,
+                                R0.ctypes.data, tsc.ctypes.data, len(tsc), self.R_dt, int(self.is_R_rk),
+                                Rs.ctypes.data)
+    else:
+      Rs = self._scan_py(ts)
+    idx = np.linspace(0, Rs.shape[0] - 1, 100_000).astype(np.int64)   # sde_lib.py:117 (dtype=int: floor)
+    self._xp, self._fp = ts[idx], Rs[idx]
+
+  def R(self, t):
+    """get_interp_fn, sde_lib.py:32-43: piecewise-linear table lookup; t scalar or array -> [...,2,2]."""
+    x = np.asarray(t, dtype=np.float64)
+    xp, fp = self._xp, self._fp
+    i = np.clip(np.searchsorted(xp, x, side="right"), 1, len(xp) - 1)
+    df = fp[i] - fp[i - 1]
+    dx = xp[i] - xp[i - 1]
+    delta = x - xp[i - 1]
+    return fp[i - 1] + (delta / dx)[..., None, None] * df
+
+  s_R = R
+
+  def invR(self, t):
+    return inv_2x2(self.R(t))
+
+  def cov(self, t):
+    R = self.R(t)
+    return R @ np.swapaxes(R, -1, -2)
+
+  # ---- closed forms -----------------------------------------------------------------------------
+  def psi(self, s, t):
+    """s_psi, sde_lib.py:182-205.  Broadcasts over s, t -> [...,2,2]."""
+    B = self.beta_int(np.asarray(t, dtype=np.float64)) - self.beta_int(np.asarray(s, dtype=np.float64))
+    a = 2.0 * np.sqrt(self.m_inv)
+    coef = np.exp(-a * B / 2)
+    out = np.empty(np.shape(B) + (2, 2))
+    out[..., 0, 0] = (1 + a * B / 2) * coef
+    out[..., 0, 1] = 0.25 * a * a * B * coef
+    out[..., 1, 0] = -B * coef
+    out[..., 1, 1] = (1 - a * B / 2) * coef
+    return out
+
+  def s_F(self, t):
+    b = self.beta(t)
+    return np.array([[0.0, b * self.m_inv], [-b, -self.Gamma * b * self.m_inv]])
+
+  def s_G(self, t):
+    b = self.beta(t)
+    return np.array([[0.0, 0.0], [0.0, np.sqrt(2 * self.Gamma * b)]])
+
+  def eps_integrand(self, t):
+    """s_eps_integrand, sde_lib.py:207-212, vectorised: 0.5 G G R^{-T}."""
+    t = np.asarray(t, dtype=np.float64)
+    g2 = 2 * self.Gamma * self.beta(t)                         # (G@G)[1,1]
+    iRT = np.swapaxes(self.invR(t), -1, -2)
+    out = np.zeros(np.shape(t) + (2, 2))
+    out[..., 1, :] = 0.5 * g2[..., None] * iRT[..., 1, :]
+    return out
+
+  def eps2score(self, eps, t):
+    """sde_lib.py:246-253 with a scalar t shared by the batch: score = -R^{-T} eps on the last axis."""
+    m = -self.invR(t).T
+    return np.einsum("ij,...j->...i", m, eps)
+
+  # ---- tables ---------------------------------------------------------------------------------
+  def prepare_order0_coef(self, rev_ts, num_item=1000):
+    """sde_lib.py:289-306."""
+    rev_ts = np.asarray(rev_ts, dtype=np.float64)
+    mean = self.psi(rev_ts[:-1], rev_ts[1:])
+    eps = np.stack([_riemann(self, s, e, None, 0, num_item) for s, e in zip(rev_ts[:-1], rev_ts[1:])])
+    return mean, eps
+
+  def get_deis_coef(self, order, rev_ts):
+    """sde_lib.py:308-319 -> [N, order+3, 2, 2]."""
+    rev_ts = np.asarray(rev_ts, dtype=np.float64)
+    x_coef = self.psi(rev_ts[:-1], rev_ts[1:])
+    eps_coef = get_ab_eps_coef(self, order + 1, rev_ts, order)
+    return np.concatenate([x_coef[:, None], eps_coef], axis=1)
+
+
+def from_config(config):
+  """sde_lib.py:321-331."""
+  m = config.model
+  return CLD(m_inv=m.m_inv, beta_0=m.beta_0, beta_1=m.beta_1, vv_gamma=m.vv_gamma,
+             mixed_score=m.mixed_score, is_R_rk=m.is_R_rk, R_dt=m.R_dt)
+
+
+# ---- DEIS coefficient tables (cld_jax/deis.py:19-95) ---------------------------------------------
+def _lagrange(t_val, ts_poly, coef_idx):
+  """single_poly_coef / vec_poly_coef, deis.py:30-38, vectorised over t_val."""
+  out = np.ones_like(t_val)
+  for k in range(len(ts_poly)):
+    if k != coef_idx:
+      out = out * (t_val - ts_poly[k]) / (ts_poly[coef_idx] - ts_poly[k])
+  return out
+
+
+def _riemann(sde, t_start, t_end, ts_poly, coef_idx, num_item=10000):
+  """get_eps_coef_worker_fn + get_eps_single_coef_fn, deis.py:19-47: left Riemann sum, num_item nodes."""
+  dt = (t_end - t_start) / num_item
+  t_inter = np.linspace(t_start, t_end, num_item, endpoint=False)
+  integrand = sde.psi(t_inter, t_end) @ sde.eps_integrand(t_inter)
+  w = np.ones(num_item) if ts_poly is None else _lagrange(t_inter, ts_poly, coef_idx)
+  return np.sum(integrand * w[:, None, None], axis=0) * dt
+
+
+def _coef_row(sde, highest_order, order, t_start, t_end, ts_poly):
+  """get_eps_coef_fn._worker, deis.py:49-59: rtn[j] uses node ts_poly[order-j] (the jnp.flip)."""
+  rtn = np.zeros((highest_order + 1, 2, 2))
+  ts_poly = ts_poly[:order + 1]
+  for j, coef_idx in enumerate(range(order, -1, -1)):
+    rtn[j] = _riemann(sde, t_start, t_end, ts_poly, coef_idx)
+  return rtn
+
+
+def get_ab_eps_coef(sde, highest_order, timesteps, order):
+  """deis.py:61-95 (recursion included)."""
+  timesteps = np.asarray(timesteps, dtype=np.float64)
+  if order == 0:
+    return np.stack([_coef_row(sde, highest_order, 0, timesteps[i], timesteps[i + 1], timesteps[i:i + 1])
+                     for i in range(len(timesteps) - 1)])
+  prev = get_ab_eps_coef(sde, highest_order, timesteps[:order + 1], order - 1)
+  rows = []
+  for k in range(len(timesteps) - order - 1):
+    ts_poly = timesteps[k:k + order + 1]
+    rows.append(_coef_row(sde, highest_order, order, timesteps[order + k], timesteps[order + k + 1], ts_poly))
+  cur = np.stack(rows) if rows else np.zeros((0, highest_order + 1, 2, 2))
+  return np.concatenate([prev, cur], axis=0)
+
+
+# ---- update ops -----------------------------------------------------------------------------------
+def multistep_ab_step(x, deis_coef, new_eps, eps_pred):
+  """deis.py:141-151."""
+  x_coef, eps_coef = deis_coef[0], deis_coef[1:]
+  full_eps = np.concatenate([new_eps[None], eps_pred])
+  linear_term = np.einsum("ij,b...j->b...i", x_coef, x)
+  eps_term = np.einsum("oij,o...j->...i", eps_coef, full_eps)
+  return linear_term + eps_term, full_eps[:-1]
+
+
+def relayout_in(u):
+  """'b ... d g -> b ... (g d)', models/utils.py:153."""
+  return np.concatenate([u[..., 0], u[..., 1]], axis=-1)
+
+
+def relayout_out(o):
+  """'b ... (g d) -> b ... d g', g=2, models/utils.py:158."""
+  c = o.shape[-1] // 2
+  return np.stack([o[..., :c], o[..., c:]], axis=-1)
+
+
+def make_eps_fn(sde, net_fn):
+  """get_eps_fn, models/utils.py:168-182.  net_fn(x[B,H,W,2C], labels scalar) -> [B,H,W,2C]."""
+  def eps_fn(u, t):
+    out = relayout_out(np.asarray(net_fn(relayout_in(u), 999.0 * t), dtype=u.dtype))
+    if sde.mixed_score:
+      u0 = u.copy()
+      u0[..., 0] = 0.0
+      out = out + np.einsum("ij,...j->...i", sde.invR(t), u0).astype(u.dtype)
+    return out
+  return eps_fn
+
+
+def denoise_step(sde, eps_fn, u):
+  """get_denoising_step, sampling.py:30-39, with t = denoising_eps = sde.sampling_eps."""
+  t = sde.sampling_eps
+  F, G = sde.s_F(t), sde.s_G(t)
+  dt = -t
+  eps = eps_fn(u, t)
+  score = sde.eps2score(eps, t)
+  return u + np.einsum("ij,...j->...i", F, u) * dt - np.einsum("ij,...j->...i", G @ G, score) * dt
+
+
+def deis_sampler(sde, eps_fn, u, nfe, deis_order, ts_order=2, denoising=True, centered=True,
+                 dtype=np.float64, trace=None):
+  """_impl_deis_sampler.sampler + get_deis_sampler, sampling.py:204-253 (single device, explicit u)."""
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = get_rev_ts(sde.T, sde.sampling_eps, ts_order, num_step)
+  coef = sde.get_deis_coef(deis_order, rev_ts).astype(dtype)
+  u = np.asarray(u, dtype=dtype)
+  eps_pred = np.stack([u] * (deis_order + 1))
+  for i in range(num_step):
+    eps = np.asarray(eps_fn(u, rev_ts[i]), dtype=dtype)
+    u, eps_pred = multistep_ab_step(u, coef[i], eps, eps_pred)
+    u = u.astype(dtype)
+    if trace is not None:
+      trace.append(u.copy())
+  if denoising:
+    u = denoise_step(sde, eps_fn, u).astype(dtype)
+  x, v = u[..., 0], u[..., 1]
+  if centered:
+    x = (x + 1.0) / 2.0
+  return x, v, nfe
+
+
+def order0_sampler(sde, eps_fn, u, nfe, denoising=True, centered=True, dtype=np.float64):
+  """get_order0_sampler (is_em=False), sampling.py:156-202; ts_order hard-coded 2 (162)."""
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = get_rev_ts(sde.T, sde.sampling_eps, 2, num_step)
+  mean, epsm = sde.prepare_order0_coef(rev_ts)
+  u = np.asarray(u, dtype=dtype)
+  for i in range(num_step):
+    eps = np.asarray(eps_fn(u, rev_ts[i]), dtype=dtype)
+    u = (np.einsum("ij,...j->...i", mean[i], u) + np.einsum("ij,...j->...i", epsm[i], eps)).astype(dtype)
+  if denoising:
+    u = denoise_step(sde, eps_fn, u).astype(dtype)
+  x, v = u[..., 0], u[..., 1]
+  if centered:
+    x = (x + 1.0) / 2.0
+  return x, v, nfe
+
+
+def prior_sampling(rng, shape, m_inv=4.0):
+  """CLD.prior_sampling, sde_lib.py:270-274, with a numpy Generator instead of jax threefry."""
+  xs = rng.standard_normal(shape)
+  vs = rng.standard_normal(shape) / np.sqrt(m_inv)
+  return np.stack([xs, vs], axis=-1)
