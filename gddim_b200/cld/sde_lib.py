@@ -1,0 +1,203 @@
+"""Stand-in for cld_jax/sde_lib.py: the CLD SDE (tables computed in fp64 by libgddim_b200.so on the host).
+
+Mirrors `CLD` (sde_lib.py:45-319) and `from_config` (321-331).  Returned arrays are numpy float32 unless
+x64=True (the reference runs with jax_enable_x64 = config.model.x64 = False).  The pickle cache of the
+reference (`used_cache`) is not reproduced: tables are recomputed (sub-second).
+`LambdaSDE` / `LSDE` (334-519) are SURVEY.md 8(f) "next" rows and raise NotImplementedError.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+
+
+def inv_2x2(matrix):
+  """sde_lib.py:17-26."""
+  m = np.asarray(matrix)
+  a, b, c, d = m[..., 0, 0], m[..., 0, 1], m[..., 1, 0], m[..., 1, 1]
+  coef = 1.0 / (a * d - b * c)
+  out = np.empty_like(m)
+  out[..., 0, 0], out[..., 0, 1], out[..., 1, 0], out[..., 1, 1] = d * coef, -b * coef, -c * coef, a * coef
+  return out
+
+
+inv_2x2s = inv_2x2
+
+
+def _d(a):
+  return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+class CLD:
+  def __init__(self, m_inv=4.0, beta_0=4.0, beta_1=0.0, vv_gamma=0.04, numerical_eps=1e-6, mixed_score=False,
+               used_cache=True, x64=False, is_R_rk=False, R_dt=1e-5):
+    self.mixed_score, self.used_cache, self.x64 = mixed_score, used_cache, x64
+    self.m_inv = m_inv
+    self.Gamma = 2. / np.sqrt(m_inv)
+    self.beta_0, self.beta_1 = beta_0, beta_1
+    self.vv_gamma, self.numerical_eps = vv_gamma, numerical_eps
+    self.is_R_rk, self.R_dt = bool(is_R_rk), float(R_dt)
+    self._dt = np.float64 if x64 else np.float32
+    self.R_0 = np.asarray([[np.sqrt(numerical_eps), 0], [0, np.sqrt(vv_gamma / m_inv + numerical_eps)]], self._dt)
+    h = C.c_void_p()
+    _lib.check(_lib.lib().gddim_cld_create(float(m_inv), float(beta_0), float(beta_1), float(vv_gamma),
+                                            float(numerical_eps), float(R_dt), int(bool(is_R_rk)), C.byref(h)),
+               "gddim_cld_create")
+    self._h = h
+    self.sampling_eps = 1e-3
+    self.T = 1.0
+
+  def __del__(self):
+    try:
+      if getattr(self, "_h", None):
+        _lib.lib().gddim_cld_destroy(self._h)
+        self._h = None
+    except Exception:
+      pass
+
+  # -- schedule ------------------------------------------------------------------------------------------
+  def beta(self, t):
+    return self.beta_0 + self.beta_1 * t
+
+  def beta_int(self, t):
+    return self.beta_0 * t + 0.5 * self.beta_1 * t ** 2
+
+  _beta, _beta_int = beta, beta_int
+
+  # -- matrices (fp64 inside; "64" variants return fp64) --------------------------------------------------------
+  def _R64(self, ts):
+    ts = _d(ts).ravel()
+    out = np.empty((ts.size, 2, 2))
+    _lib.check(_lib.lib().gddim_cld_R(self._h, ts.ctypes.data, ts.size, out.ctypes.data))
+    return out
+
+  def _psi64(self, s, t):
+    s, t = np.broadcast_arrays(_d(s), _d(t))
+    s, t = _d(s).ravel(), _d(t).ravel()
+    out = np.empty((s.size, 2, 2))
+    _lib.check(_lib.lib().gddim_cld_psi(self._h, s.ctypes.data, t.ctypes.data, s.size, out.ctypes.data))
+    return out
+
+  def s_R(self, t):
+    return self._R64([t])[0].astype(self._dt)
+
+  def v_R(self, ts):
+    return self._R64(ts).astype(self._dt)
+
+  def s_invR(self, t):
+    return inv_2x2(self._R64([t])[0]).astype(self._dt)
+
+  def v_invR(self, ts):
+    return inv_2x2(self._R64(ts)).astype(self._dt)
+
+  def s_cov(self, t):
+    r = self._R64([t])[0]
+    return (r @ r.T).astype(self._dt)
+
+  def v_cov(self, ts):
+    r = self._R64(ts)
+    return (r @ np.swapaxes(r, -1, -2)).astype(self._dt)
+
+  def s_psi(self, s, t):
+    return self._psi64(s, t)[0].astype(self._dt)
+
+  def vv_psi(self, s, t):
+    return self._psi64(s, t).astype(self._dt)
+
+  def vs_psi(self, s, t):
+    return self._psi64(s, t).astype(self._dt)
+
+  def s_F(self, t):
+    out = np.empty((2, 2))
+    _lib.check(_lib.lib().gddim_cld_F(self._h, float(t), out.ctypes.data))
+    return out.astype(self._dt)
+
+  def s_G(self, t):
+    out = np.empty((2, 2))
+    _lib.check(_lib.lib().gddim_cld_G(self._h, float(t), out.ctypes.data))
+    return out.astype(self._dt)
+
+  def s_eps_integrand(self, s_t):
+    return self.v_eps_integrand([s_t])[0]
+
+  def v_eps_integrand(self, ts):
+    ts = _d(ts).ravel()
+    out = np.empty((ts.size, 2, 2))
+    _lib.check(_lib.lib().gddim_cld_eps_integrand(self._h, ts.ctypes.data, ts.size, out.ctypes.data))
+    return out.astype(self._dt)
+
+  # -- batch helpers (host numpy; not on the per-step path) -------------------------------------------------------
+  def eps2score(self, eps, ts):
+    """sde_lib.py:246-253: score = -R^{-T} eps, eps (B, ..., c, 2), ts (B,)."""
+    inv_rs = inv_2x2(self._R64(ts))
+    return np.einsum("bji,b...dj->b...di", -inv_rs, np.asarray(eps, np.float64)).astype(self._dt)
+
+  def mean(self, batch, ts):
+    psis = self._psi64(np.zeros_like(_d(ts)), ts)
+    return np.einsum("bij,b...dj->b...di", psis, np.asarray(batch, np.float64)).astype(self._dt)
+
+  def perturb_data(self, batch, ts, rng):
+    mean = self.mean(batch, ts)
+    raw_noise = _np_rng(rng).standard_normal(mean.shape).astype(self._dt)
+    perb = np.einsum("bij,b...dj->b...di", self._R64(ts), raw_noise.astype(np.float64)).astype(self._dt)
+    return mean + perb, mean, raw_noise
+
+  def prior_sampling(self, rng, shape):
+    """sde_lib.py:270-274.  JAX's threefry stream is not reproduced: `rng` seeds numpy's default_rng; x and v
+    are drawn from two child streams (mirrors the key split)."""
+    g = _np_rng(rng)
+    seeds = g.integers(0, 2 ** 63 - 1, size=2)
+    xs = np.random.default_rng(int(seeds[0])).standard_normal(tuple(shape)).astype(self._dt)
+    vs = (np.random.default_rng(int(seeds[1])).standard_normal(tuple(shape)) / np.sqrt(self.m_inv)).astype(self._dt)
+    return np.stack([xs, vs], axis=-1)
+
+  # -- coefficient tables -----------------------------------------------------------------------------------------
+  def prepare_naive_coef(self, rev_ts):
+    """sde_lib.py:276-287 (Euler-Maruyama style coefficients)."""
+    rev_ts = _d(rev_ts)
+    mean, eps = [], []
+    for cur, nxt in zip(rev_ts[:-1], rev_ts[1:]):
+      mean.append(np.eye(2) + self.s_F(cur).astype(np.float64) * (nxt - cur))
+      eps.append(self.s_eps_integrand(cur).astype(np.float64) * (nxt - cur))
+    return np.stack(mean).astype(self._dt), np.stack(eps).astype(self._dt)
+
+  def prepare_order0_coef(self, rev_ts):
+    rev_ts = _d(rev_ts)
+    n = rev_ts.size
+    mean, eps = np.empty((n - 1, 2, 2)), np.empty((n - 1, 2, 2))
+    _lib.check(_lib.lib().gddim_cld_order0_coef(self._h, rev_ts.ctypes.data, n, mean.ctypes.data, eps.ctypes.data))
+    return mean.astype(self._dt), eps.astype(self._dt)
+
+  def get_deis_coef(self, order, rev_timesteps, used_cache=True):
+    """sde_lib.py:308-319 -> [N, order+3, 2, 2]."""
+    rev = _d(rev_timesteps)
+    out = np.empty((rev.size - 1, order + 3, 2, 2))
+    _lib.check(_lib.lib().gddim_cld_deis_coef(self._h, int(order), rev.ctypes.data, rev.size, out.ctypes.data),
+               "gddim_cld_deis_coef")
+    return out.astype(self._dt)
+
+
+def _np_rng(rng):
+  if isinstance(rng, np.random.Generator):
+    return rng
+  if rng is None:
+    return np.random.default_rng()
+  return np.random.default_rng(np.asarray(rng).astype(np.uint32).ravel().tolist())
+
+
+class LambdaSDE:
+  def __init__(self, *a, **k):
+    raise NotImplementedError("LambdaSDE (stochastic gDDIM) is outside the round-1 hot path (SURVEY.md 8f N1)")
+
+
+class LSDE:
+  def __init__(self, *a, **k):
+    raise NotImplementedError("LSDE (Cholesky L_t baseline) is outside the round-1 hot path (SURVEY.md 8f N3)")
+
+
+def from_config(config):
+  """sde_lib.py:321-331."""
+  m = config.model
+  return CLD(m_inv=m.m_inv, beta_0=m.beta_0, beta_1=m.beta_1, vv_gamma=m.vv_gamma, mixed_score=m.mixed_score,
+             is_R_rk=m.is_R_rk, used_cache=m.used_cache, R_dt=m.R_dt, x64=m.x64)

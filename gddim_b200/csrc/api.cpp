@@ -1,0 +1,513 @@
+// C ABI (include/gddim_b200.h): contexts, host tables, update operators and the samplers.
+//
+// Sampler loops restate (index-exact) cld_jax/sampling.py:204-253 (_impl_deis_sampler, get_deis_sampler),
+// :156-202 (get_order0_sampler), :30-39 (denoising step) and blur_jax/sampling.py:53-90.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/gddim_b200.h"
+#include "kernels.h"
+#include "tables.h"
+#include "unet.h"
+
+using namespace gddim;
+
+static thread_local std::string g_err;
+static int set_err(const std::string& m) { g_err = m; return -1; }
+
+struct gddim_ctx {
+  int device;
+  std::unique_ptr<UNet> net;
+};
+struct gddim_cld { std::unique_ptr<CldTables> t; };
+struct gddim_blur { std::unique_ptr<BlurTables> t; };
+
+struct gddim_sampler {
+  gddim_ctx* ctx = nullptr;
+  gddim_sampler_cfg cfg;
+  int n_steps = 0, order = 0, C = 0, S = 0;
+  bool is_blur = false;
+  std::vector<double> rev_ts;
+  std::vector<float> coef;            // CLD: [n_steps][order+3][4]
+  float den_A[4], den_C[4];
+  std::vector<float> mixm;            // [n_steps + 1][4]  R(t)^-1 [[0,0],[0,1]] when mixed_score
+  float* d_temb_all = nullptr;        // [n_steps (+1 denoise)][temb_total]
+  float* d_u = nullptr;               // state, net layout (CLD) / y (blur)
+  std::vector<float*> d_eps;          // ring of network outputs
+  float* d_xin = nullptr;             // blur: network input x = IDCT(y)
+  float* d_stage = nullptr;           // host-buffer staging / reference-layout scratch
+  float *d_x = nullptr, *d_v = nullptr;
+  float *d_blur_a = nullptr, *d_blur_b = nullptr;
+  std::vector<cudaGraphExec_t> graphs;   // per ring slot
+  int graph_batch = 0;
+  long long kernels_per_forward = 0;
+  long long launches = 0;
+};
+
+extern "C" {
+
+const char* gddim_last_error(void) { return g_err.c_str(); }
+int gddim_abi_version(void) { return GDDIM_ABI_VERSION; }
+int gddim_cuda_available(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n > 0 ? 1 : 0;
+}
+
+// ---- context ------------------------------------------------------------------------------------------------
+int gddim_ctx_create(int device, const gddim_model_cfg* cfg, int max_batch, gddim_ctx** out) {
+  if (!cfg || !out || max_batch < 1) return set_err("gddim_ctx_create: bad arguments");
+  std::unique_ptr<gddim_ctx> c(new gddim_ctx);
+  c->device = device;
+  c->net.reset(new UNet(*cfg, max_batch));
+  if (!c->net->error().empty()) return set_err("gddim_ctx_create: " + c->net->error());
+  *out = c.release();
+  return 0;
+}
+void gddim_ctx_destroy(gddim_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->net && ctx->net->finalized()) cudaSetDevice(ctx->device);
+  delete ctx;
+}
+int gddim_param_count(const gddim_ctx* ctx) { return ctx ? (int)ctx->net->specs().size() : -1; }
+int gddim_param_spec(const gddim_ctx* ctx, int index, char* name_buf, int name_buf_len, int shape[4], int* ndim,
+                     int* kind, float* scale) {
+  if (!ctx || index < 0 || index >= (int)ctx->net->specs().size()) return set_err("gddim_param_spec: bad index");
+  const ParamSpec& s = ctx->net->specs()[index];
+  if (name_buf && name_buf_len > 0) {
+    strncpy(name_buf, s.name.c_str(), name_buf_len - 1);
+    name_buf[name_buf_len - 1] = 0;
+  }
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = i < (int)s.shape.size() ? s.shape[i] : 1;
+  if (ndim) *ndim = (int)s.shape.size();
+  if (kind) *kind = s.kind;
+  if (scale) *scale = s.scale;
+  return 0;
+}
+int gddim_param_set(gddim_ctx* ctx, const char* name, const float* host_data, size_t n_elem) {
+  if (!ctx || !name || !host_data) return set_err("gddim_param_set: bad arguments");
+  if (ctx->net->finalized()) return set_err("gddim_param_set: context already finalized");
+  if (ctx->net->set_param(name, host_data, n_elem)) return set_err(ctx->net->error());
+  return 0;
+}
+int gddim_ctx_finalize(gddim_ctx* ctx) {
+  if (!ctx) return set_err("gddim_ctx_finalize: null ctx");
+  if (!gddim_cuda_available()) return set_err("gddim_ctx_finalize: no CUDA device available (the hot path has no CPU fallback)");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
+  if (ctx->net->finalize()) return set_err(ctx->net->error());
+  return 0;
+}
+int gddim_ctx_set_gemm_impl(gddim_ctx* ctx, int impl) {
+  if (!ctx || (impl != 0 && impl != 1)) return set_err("gddim_ctx_set_gemm_impl: bad arguments");
+  ctx->net->gemm_impl = impl;
+  return 0;
+}
+size_t gddim_ctx_workspace_bytes(const gddim_ctx* ctx) { return ctx ? ctx->net->workspace_bytes() : 0; }
+long long gddim_ctx_launch_count(const gddim_ctx* ctx) { return ctx ? ctx->net->launch_count() : -1; }
+
+int gddim_unet_forward(gddim_ctx* ctx, const float* x_dev, float t, float* out_dev, int batch, void* stream) {
+  if (!ctx || !x_dev || !out_dev) return set_err("gddim_unet_forward: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ctx->net->time_projections((double)t, ctx->net->temb_cur(), st)) return set_err(ctx->net->error());
+  if (ctx->net->forward(x_dev, out_dev, batch, st)) return set_err(ctx->net->error());
+  return 0;
+}
+
+// ---- CLD tables ---------------------------------------------------------------------------------------------
+int gddim_cld_create(double m_inv, double beta_0, double beta_1, double vv_gamma, double numerical_eps, double R_dt,
+                     int is_R_rk, gddim_cld** out) {
+  if (!out || !(R_dt > 0) || R_dt > 1e-2) return set_err("gddim_cld_create: bad arguments");
+  gddim_cld* c = new gddim_cld;
+  c->t.reset(new CldTables(m_inv, beta_0, beta_1, vv_gamma, numerical_eps, R_dt, is_R_rk != 0));
+  *out = c;
+  return 0;
+}
+void gddim_cld_destroy(gddim_cld* cld) { delete cld; }
+static void put(double* o, const Mat2& m) { o[0] = m.a; o[1] = m.b; o[2] = m.c; o[3] = m.d; }
+int gddim_cld_R(const gddim_cld* cld, const double* t, int n, double* out) {
+  if (!cld || !t || !out) return set_err("gddim_cld_R: bad arguments");
+  for (int i = 0; i < n; ++i) put(out + 4 * i, cld->t->R(t[i]));
+  return 0;
+}
+int gddim_cld_psi(const gddim_cld* cld, const double* s, const double* t, int n, double* out) {
+  if (!cld || !s || !t || !out) return set_err("gddim_cld_psi: bad arguments");
+  for (int i = 0; i < n; ++i) put(out + 4 * i, cld->t->psi(s[i], t[i]));
+  return 0;
+}
+int gddim_cld_F(const gddim_cld* cld, double t, double* out) {
+  if (!cld || !out) return set_err("gddim_cld_F: bad arguments");
+  put(out, cld->t->F(t));
+  return 0;
+}
+int gddim_cld_G(const gddim_cld* cld, double t, double* out) {
+  if (!cld || !out) return set_err("gddim_cld_G: bad arguments");
+  put(out, cld->t->G(t));
+  return 0;
+}
+int gddim_cld_eps_integrand(const gddim_cld* cld, const double* t, int n, double* out) {
+  if (!cld || !t || !out) return set_err("gddim_cld_eps_integrand: bad arguments");
+  for (int i = 0; i < n; ++i) put(out + 4 * i, cld->t->eps_integrand(t[i]));
+  return 0;
+}
+int gddim_cld_deis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out) {
+  if (!cld || !rev_ts || !out || order < 0 || order > 4 || n_ts < 2) return set_err("gddim_cld_deis_coef: bad arguments");
+  if (n_ts - 1 < order) return set_err("gddim_cld_deis_coef: fewer steps than the multistep order");
+  cld->t->deis_coef(order, rev_ts, n_ts, out);
+  return 0;
+}
+int gddim_cld_order0_coef(const gddim_cld* cld, const double* rev_ts, int n_ts, double* mean_out, double* eps_out) {
+  if (!cld || !rev_ts || !mean_out || !eps_out || n_ts < 2) return set_err("gddim_cld_order0_coef: bad arguments");
+  cld->t->order0_coef(rev_ts, n_ts, mean_out, eps_out);
+  return 0;
+}
+int gddim_rev_ts(double T, double eps, int ts_order, int num_step, double* out) {
+  if (!out || num_step < 1 || ts_order < 1) return set_err("gddim_rev_ts: bad arguments");
+  rev_timesteps(T, eps, ts_order, num_step, out);
+  return 0;
+}
+
+// ---- blur tables --------------------------------------------------------------------------------------------
+int gddim_blur_create(double sigma_blur_max, double sampling_eps, gddim_blur** out) {
+  if (!out) return set_err("gddim_blur_create: bad arguments");
+  gddim_blur* b = new gddim_blur;
+  b->t.reset(new BlurTables(sigma_blur_max, sampling_eps));
+  *out = b;
+  return 0;
+}
+void gddim_blur_destroy(gddim_blur* b) { delete b; }
+double gddim_blur_sampling_T(const gddim_blur* b) { return b->t->sampling_T(); }
+int gddim_blur_y_mean_coef(const gddim_blur* b, double t, double* out) {
+  if (!b || !out) return set_err("gddim_blur_y_mean_coef: bad arguments");
+  b->t->y_mean_coef(t, out);
+  return 0;
+}
+double gddim_blur_y_std_coef(const gddim_blur* b, double t) { return b->t->y_std_coef(t); }
+double gddim_blur_t2alpha(const gddim_blur* b, double t) { return b->t->t2alpha(t); }
+
+// ---- update operators -----------------------------------------------------------------------------------------
+static int need_cuda(const char* who) {
+  if (!gddim_cuda_available()) return set_err(std::string(who) + ": no CUDA device available (no CPU fallback)");
+  return 0;
+}
+
+int gddim_multistep_ab_step(const float* x_dev, const float* deis_coef_host, const float* new_eps_dev,
+                            const float* eps_pred_dev, float* x_out_dev, float* eps_pred_out_dev, int order,
+                            long long n_pairs, void* stream) {
+  if (need_cuda("gddim_multistep_ab_step")) return -1;
+  if (!x_dev || !deis_coef_host || !new_eps_dev || !eps_pred_dev || !x_out_dev || !eps_pred_out_dev || order < 0 ||
+      order > 5)
+    return set_err("gddim_multistep_ab_step: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* d_coef = nullptr;
+  const size_t nb = (size_t)(order + 3) * 4 * sizeof(float);
+  if (cudaMallocAsync(&d_coef, nb, st) != cudaSuccess) return set_err("cudaMallocAsync failed");
+  cudaMemcpyAsync(d_coef, deis_coef_host, nb, cudaMemcpyHostToDevice, st);
+  int rc = ab_step_ref_layout_launch(x_dev, d_coef, new_eps_dev, eps_pred_dev, x_out_dev, eps_pred_out_dev, order,
+                                     n_pairs, st);
+  cudaFreeAsync(d_coef, st);
+  if (rc) return set_err("gddim_multistep_ab_step: launch failed");
+  return 0;
+}
+
+int gddim_scalar_ab_step(const float* x_dev, const float* ei_coef_host, const float* new_eps_dev,
+                         const float* eps_pred_dev, float* x_out_dev, float* eps_pred_out_dev, int n_hist, long long n,
+                         void* stream) {
+  if (need_cuda("gddim_scalar_ab_step")) return -1;
+  if (!x_dev || !ei_coef_host || !new_eps_dev || !x_out_dev || n_hist < 0 || n_hist > 8)
+    return set_err("gddim_scalar_ab_step: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* d_coef = nullptr;
+  const size_t nb = (size_t)(n_hist + 2) * sizeof(float);
+  if (cudaMallocAsync(&d_coef, nb, st) != cudaSuccess) return set_err("cudaMallocAsync failed");
+  cudaMemcpyAsync(d_coef, ei_coef_host, nb, cudaMemcpyHostToDevice, st);
+  int rc = scalar_ab_step_launch(x_dev, d_coef, new_eps_dev, eps_pred_dev, x_out_dev, eps_pred_out_dev, n_hist, n, st);
+  cudaFreeAsync(d_coef, st);
+  if (rc) return set_err("gddim_scalar_ab_step: launch failed");
+  return 0;
+}
+
+int gddim_relayout(const float* src_dev, float* dst_dev, long long n_pix, int C, int to_net, void* stream) {
+  if (need_cuda("gddim_relayout")) return -1;
+  if (relayout_launch(src_dev, dst_dev, n_pix, C, to_net, (cudaStream_t)stream)) return set_err("gddim_relayout: launch failed");
+  return 0;
+}
+
+int gddim_dct2d_32(const float* in_dev, float* out_dev, int batch, int C, int forward, void* stream) {
+  if (need_cuda("gddim_dct2d_32")) return -1;
+  if (dct32_launch(in_dev, out_dev, batch, C, forward, (cudaStream_t)stream)) return set_err("gddim_dct2d_32: launch failed");
+  return 0;
+}
+
+// ---- samplers ---------------------------------------------------------------------------------------------------
+static void free_sampler_buffers(gddim_sampler* s) {
+  for (auto g : s->graphs) if (g) cudaGraphExecDestroy(g);
+  s->graphs.clear();
+  cudaFree(s->d_temb_all); cudaFree(s->d_u); cudaFree(s->d_xin); cudaFree(s->d_stage); cudaFree(s->d_x);
+  cudaFree(s->d_v); cudaFree(s->d_blur_a); cudaFree(s->d_blur_b);
+  for (auto p : s->d_eps) cudaFree(p);
+  s->d_eps.clear();
+}
+
+int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
+                         gddim_sampler** out) {
+  if (!ctx || !cfg || !out) return set_err("gddim_sampler_create: bad arguments");
+  if (!ctx->net->finalized()) return set_err("gddim_sampler_create: context not finalized");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
+  std::unique_ptr<gddim_sampler> s(new gddim_sampler);
+  s->ctx = ctx;
+  s->cfg = *cfg;
+  UNet& net = *ctx->net;
+  s->S = net.image_size();
+  s->C = net.cfg().data_channels;
+  const int B = net.max_batch();
+  const size_t state_elems = (size_t)B * s->S * s->S * net.net_channels();
+  std::vector<double> eval_ts;       // the time of every network evaluation, in order
+
+  if (cfg->kind == GDDIM_CLD_DEIS || cfg->kind == GDDIM_CLD_ORDER0) {
+    if (!cld) return set_err("gddim_sampler_create: CLD sampler needs a gddim_cld");
+    if (net.cfg().state_mult != 2) return set_err("gddim_sampler_create: CLD sampler needs a state_mult=2 network");
+    const CldTables& t = *cld->t;
+    const bool is_o0 = cfg->kind == GDDIM_CLD_ORDER0;
+    s->order = is_o0 ? 0 : cfg->deis_order;
+    if (s->order < 0 || s->order > 4) return set_err("gddim_sampler_create: deis_order must be in 0..4");
+    s->n_steps = cfg->denoising ? cfg->nfe - 1 : cfg->nfe;      // sampling.py:205 / :160
+    if (s->n_steps < 1 || s->n_steps < s->order) return set_err("gddim_sampler_create: nfe too small for this order");
+    const int ts_order = is_o0 ? 2 : cfg->ts_order;             // sampling.py:162 hard-codes 2 for order0
+    s->rev_ts.resize(s->n_steps + 1);
+    rev_timesteps(t.T, t.sampling_eps, ts_order, s->n_steps, s->rev_ts.data());
+    const int per = s->order + 3;
+    std::vector<double> c((size_t)s->n_steps * per * 4, 0.0);
+    if (is_o0) {
+      std::vector<double> mean((size_t)s->n_steps * 4), eps((size_t)s->n_steps * 4);
+      t.order0_coef(s->rev_ts.data(), s->n_steps + 1, mean.data(), eps.data());
+      for (int i = 0; i < s->n_steps; ++i) {
+        memcpy(&c[(size_t)i * per * 4], &mean[(size_t)i * 4], 4 * sizeof(double));
+        memcpy(&c[(size_t)i * per * 4 + 4], &eps[(size_t)i * 4], 4 * sizeof(double));
+      }
+    } else {
+      t.deis_coef(s->order, s->rev_ts.data(), s->n_steps + 1, c.data());
+    }
+    s->coef.resize(c.size());
+    for (size_t i = 0; i < c.size(); ++i) s->coef[i] = (float)c[i];
+    for (int i = 0; i < s->n_steps; ++i) eval_ts.push_back(s->rev_ts[i]);
+    if (cfg->denoising) {
+      Mat2 A, Cm;
+      t.denoise_coef(t.sampling_eps, &A, &Cm);
+      s->den_A[0] = (float)A.a; s->den_A[1] = (float)A.b; s->den_A[2] = (float)A.c; s->den_A[3] = (float)A.d;
+      s->den_C[0] = (float)Cm.a; s->den_C[1] = (float)Cm.b; s->den_C[2] = (float)Cm.c; s->den_C[3] = (float)Cm.d;
+      eval_ts.push_back(t.sampling_eps);
+    }
+    s->mixm.assign(eval_ts.size() * 4, 0.f);
+    if (cfg->mixed_score) {
+      for (size_t i = 0; i < eval_ts.size(); ++i) {
+        const Mat2 ri = inv(t.R(eval_ts[i]));      // eps += R^-1 [0, v]  (models/utils.py:174-176)
+        s->mixm[i * 4 + 0] = 0.f; s->mixm[i * 4 + 1] = (float)ri.b;
+        s->mixm[i * 4 + 2] = 0.f; s->mixm[i * 4 + 3] = (float)ri.d;
+      }
+    }
+    s->d_eps.resize(s->order + 1, nullptr);
+  } else if (cfg->kind == GDDIM_BLUR_ORDER0) {
+    if (!blur) return set_err("gddim_sampler_create: blur sampler needs a gddim_blur");
+    if (net.cfg().state_mult != 1 || s->S != 32) return set_err("gddim_sampler_create: blur sampler needs a 32x32 state_mult=1 network");
+    if (s->C > 5) return set_err("gddim_sampler_create: blur sampler supports up to 5 channels");
+    s->is_blur = true;
+    const BlurTables& t = *blur->t;
+    s->n_steps = cfg->nfe;
+    s->rev_ts.resize(s->n_steps + 1);
+    rev_timesteps(t.sampling_T(), t.sampling_eps, cfg->ts_order, s->n_steps, s->rev_ts.data());
+    std::vector<double> a((size_t)s->n_steps * 1024), b((size_t)s->n_steps * 1024);
+    t.order0_coef(s->rev_ts.data(), s->n_steps + 1, a.data(), b.data());
+    std::vector<float> af(a.size()), bf(b.size());
+    for (size_t i = 0; i < a.size(); ++i) { af[i] = (float)a[i]; bf[i] = (float)b[i]; }
+    if (cudaMalloc(&s->d_blur_a, af.size() * 4) != cudaSuccess || cudaMalloc(&s->d_blur_b, bf.size() * 4) != cudaSuccess)
+      return set_err("cudaMalloc failed");
+    cudaMemcpy(s->d_blur_a, af.data(), af.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(s->d_blur_b, bf.data(), bf.size() * 4, cudaMemcpyHostToDevice);
+    for (int i = 0; i < s->n_steps; ++i) eval_ts.push_back(s->rev_ts[i]);
+    s->d_eps.resize(1, nullptr);
+    if (cudaMalloc(&s->d_xin, state_elems * 4) != cudaSuccess) return set_err("cudaMalloc failed");
+  } else {
+    return set_err("gddim_sampler_create: unknown sampler kind");
+  }
+
+  bool ok = cudaMalloc(&s->d_u, state_elems * 4) == cudaSuccess;
+  for (auto& p : s->d_eps) ok = ok && cudaMalloc(&p, state_elems * 4) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->d_stage, state_elems * 4) == cudaSuccess;
+  const size_t img_elems = (size_t)B * s->S * s->S * s->C;
+  ok = ok && cudaMalloc(&s->d_x, img_elems * 4) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->d_v, img_elems * 4) == cudaSuccess;
+  const int tt = net.temb_total();
+  if (tt > 0) {
+    ok = ok && cudaMalloc(&s->d_temb_all, eval_ts.size() * (size_t)tt * 4) == cudaSuccess;
+    if (ok)
+      for (size_t i = 0; i < eval_ts.size(); ++i)
+        if (net.time_projections(eval_ts[i], s->d_temb_all + i * (size_t)tt, 0)) { free_sampler_buffers(s.get()); return set_err(net.error()); }
+  }
+  if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
+    free_sampler_buffers(s.get());
+    return set_err(std::string("gddim_sampler_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  *out = s.release();
+  return 0;
+}
+
+void gddim_sampler_destroy(gddim_sampler* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  free_sampler_buffers(s);
+  delete s;
+}
+
+long long gddim_sampler_coef(const gddim_sampler* s, float* out, long long cap) {
+  if (!s) return -1;
+  const long long n = (long long)s->coef.size();
+  if (out && cap >= n) memcpy(out, s->coef.data(), n * sizeof(float));
+  return n;
+}
+int gddim_sampler_num_steps(const gddim_sampler* s) { return s ? s->n_steps : -1; }
+int gddim_sampler_rev_ts(const gddim_sampler* s, double* out, int cap) {
+  if (!s) return -1;
+  const int n = (int)s->rev_ts.size();
+  if (out && cap >= n) memcpy(out, s->rev_ts.data(), n * sizeof(double));
+  return n;
+}
+
+// one network evaluation #e (time index e) reading s->d_u / d_xin and writing ring slot `slot`
+static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t st) {
+  UNet& net = *s->ctx->net;
+  const int tt = net.temb_total();
+  if (tt > 0)
+    cudaMemcpyAsync(net.temb_cur(), s->d_temb_all + (size_t)e * tt, (size_t)tt * 4, cudaMemcpyDeviceToDevice, st);
+  const float* in = s->is_blur ? s->d_xin : s->d_u;
+  if (s->cfg.use_graph) {
+    if (s->graph_batch != batch) {
+      for (auto g : s->graphs) if (g) cudaGraphExecDestroy(g);
+      s->graphs.assign(s->d_eps.size(), nullptr);
+      s->graph_batch = batch;
+    }
+    if (!s->graphs[slot]) {
+      // eager warm-up (sets function attributes), then capture
+      if (net.forward(in, s->d_eps[slot], batch, st)) return set_err(net.error());
+      cudaStreamSynchronize(st);
+      const long long before = net.launch_count();
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) return set_err("cudaStreamBeginCapture failed");
+      int rc = net.forward(in, s->d_eps[slot], batch, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (rc || ce != cudaSuccess) return set_err(rc ? net.error() : std::string("graph capture failed: ") + cudaGetErrorString(ce));
+      s->kernels_per_forward = net.launch_count() - before;
+      ce = cudaGraphInstantiate(&s->graphs[slot], g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) return set_err(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+    }
+    if (cudaGraphLaunch(s->graphs[slot], st) != cudaSuccess) return set_err("cudaGraphLaunch failed");
+    s->launches += s->kernels_per_forward;
+  } else {
+    const long long before = net.launch_count();
+    if (net.forward(in, s->d_eps[slot], batch, st)) return set_err(net.error());
+    s->launches += net.launch_count() - before;
+  }
+  return 0;
+}
+
+int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch, int host_buffers, float* trace_dev,
+                 void* stream) {
+  if (!s || !u || !x) return set_err("gddim_sample: bad arguments");
+  UNet& net = *s->ctx->net;
+  if (batch < 1 || batch > net.max_batch()) return set_err("gddim_sample: batch exceeds the context's max_batch");
+  if (cudaSetDevice(s->ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n_pix = (long long)batch * s->S * s->S;
+  const size_t state_elems = (size_t)n_pix * net.net_channels();
+  const size_t img_elems = (size_t)n_pix * s->C;
+
+  if (!s->is_blur) {
+    if (!v) return set_err("gddim_sample: CLD sampler needs a v output");
+    const float* u_dev = u;
+    if (host_buffers) {
+      if (cudaMemcpyAsync(s->d_stage, u, state_elems * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return set_err("H2D copy failed");
+      u_dev = s->d_stage;
+    }
+    if (relayout_launch(u_dev, s->d_u, n_pix, s->C, 1, st)) return set_err("relayout failed");
+    s->launches += 1;
+    const int ring = s->order + 1;
+    const int per = s->order + 3;
+    const int n_evals = s->n_steps + (s->cfg.denoising ? 1 : 0);
+    for (int e = 0; e < n_evals; ++e) {
+      const int slot = e % ring;
+      if (eval_net(s, e, slot, batch, st)) return -1;
+      CldStepArgs a;
+      memset(&a, 0, sizeof(a));
+      a.u = s->d_u; a.u_out = s->d_u;
+      a.n_pix = n_pix; a.C = s->C;
+      a.mixed = s->cfg.mixed_score; a.eps_store = s->d_eps[slot];
+      memcpy(a.mixm, &s->mixm[(size_t)e * 4], 16);
+      if (e < s->n_steps) {
+        const float* c = &s->coef[(size_t)e * per * 4];
+        const int r = e < s->order ? e : s->order;          // rows i < order run at order i (deis.py:75)
+        a.n_eps = r + 1;
+        memcpy(a.coef[0], c, 16);
+        for (int j = 0; j <= r; ++j) {
+          memcpy(a.coef[1 + j], c + (1 + j) * 4, 16);
+          a.eps[j] = s->d_eps[((e - j) % ring + ring) % ring];
+        }
+      } else {
+        a.n_eps = 1;
+        memcpy(a.coef[0], s->den_A, 16);
+        memcpy(a.coef[1], s->den_C, 16);
+        a.eps[0] = s->d_eps[slot];
+      }
+      if (cld_step_launch(&a, st)) return set_err("cld_step launch failed");
+      s->launches += 1;
+      if (trace_dev && e < s->n_steps) {
+        if (relayout_launch(s->d_u, trace_dev + (size_t)e * state_elems, n_pix, s->C, 0, st)) return set_err("trace relayout failed");
+        s->launches += 1;
+      }
+    }
+    float* xd = host_buffers ? s->d_x : x;
+    float* vd = host_buffers ? s->d_v : v;
+    if (cld_split_launch(s->d_u, xd, vd, n_pix, s->C, s->cfg.x_mul, s->cfg.x_add, st)) return set_err("split failed");
+    s->launches += 1;
+    if (host_buffers) {
+      cudaMemcpyAsync(x, s->d_x, img_elems * 4, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(v, s->d_v, img_elems * 4, cudaMemcpyDeviceToHost, st);
+    }
+  } else {
+    if (host_buffers) {
+      if (cudaMemcpyAsync(s->d_u, u, state_elems * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return set_err("H2D copy failed");
+    } else {
+      cudaMemcpyAsync(s->d_u, u, state_elems * 4, cudaMemcpyDeviceToDevice, st);
+    }
+    if (dct32_launch(s->d_u, s->d_xin, batch, s->C, 0, st)) return set_err("idct failed");
+    s->launches += 1;
+    for (int e = 0; e < s->n_steps; ++e) {
+      if (eval_net(s, e, 0, batch, st)) return -1;
+      if (blur_step_launch(s->d_u, s->d_eps[0], s->d_blur_a + (size_t)e * 1024, s->d_blur_b + (size_t)e * 1024, s->d_u,
+                           s->d_xin, batch, s->C, st))
+        return set_err("blur_step launch failed");
+      s->launches += 1;
+      if (trace_dev) cudaMemcpyAsync(trace_dev + (size_t)e * state_elems, s->d_u, state_elems * 4, cudaMemcpyDeviceToDevice, st);
+    }
+    float* xd = host_buffers ? s->d_x : x;
+    if (scale_shift_launch(s->d_xin, xd, (long long)img_elems, s->cfg.x_mul, s->cfg.x_add, st)) return set_err("final scale failed");
+    s->launches += 1;
+    if (host_buffers) cudaMemcpyAsync(x, s->d_x, img_elems * 4, cudaMemcpyDeviceToHost, st);
+  }
+  if (host_buffers) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return set_err(std::string("gddim_sample: ") + cudaGetErrorString(e));
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(std::string("gddim_sample: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+long long gddim_sampler_launch_count(const gddim_sampler* s) { return s ? s->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,613 @@
+// K1: implicit-GEMM convolution / GEMM on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces the XLA conv_general_dilated / dot_general calls that the reference issues from
+//   cld_jax/models/layers.py:66-107 (ddpm_conv1x1 / ddpm_conv3x3), layers.py:467-478 (NIN),
+//   cld_jax/models/layerspp.py:74-78 (attention einsums).
+//
+// Design: persistent CTAs (one per SM), 6 warps:
+//   warp 0   TMA producer  - one 4-D box load per (tap, 64-channel chunk) builds the im2col A tile
+//                            directly in shared memory (shifted box + hardware zero fill = SAME padding)
+//   warp 1   MMA issuer    - tcgen05.mma.kind::f16, 128 x BLOCK_N x 16, accumulators in TMEM (2 stages)
+//   warps 2-5 epilogue     - tcgen05.ld -> bias / temb / residual / scale (or row softmax) -> global
+// Operands are fp16 with fp32 accumulation; smem tiles use the 128-byte swizzle (K-major).
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace gddim {
+
+static thread_local char g_gemm_err[512] = "";
+const char* gemm_last_error() { return g_gemm_err; }
+#define GEMM_FAIL(...)                                          \
+  do {                                                          \
+    snprintf(g_gemm_err, sizeof(g_gemm_err), __VA_ARGS__);      \
+    return -1;                                                  \
+  } while (0)
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                       // 64 fp16 = 128 bytes = one swizzle row
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int NUM_THREADS = 192;
+
+struct GemmArgs {
+  int taps[2], kch[2], coff[2];
+  int nseg;
+  int H, W;
+  int M, N;
+  int m_tiles, n_tiles, tiles_per_batch;
+  int w_koff;
+  const float* bias;
+  const float* bias2;
+  const float* residual;
+  const float* rowscale;
+  float scale;
+  float* out32;
+  __half* out16;
+  float* row_out;
+  int ldo;
+};
+
+template <int BLOCK_N>
+struct SmemLayout {
+  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int STAGES = ((SMEM_BUDGET - BAR_BYTES - 1024) / STAGE_BYTES) > 8
+                                    ? 8
+                                    : ((SMEM_BUDGET - BAR_BYTES - 1024) / STAGE_BYTES);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                      const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  using L = SmemLayout<BLOCK_N>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);   // 2 accumulator stages
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + STAGES;            // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * STAGES;        // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA0);
+    if (p.nseg > 1) ptx::prefetch_tmap(&tmA1);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);
+      ptx::mbar_init(&tempty_bar[s], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int kblocks = p.taps[0] * p.kch[0] + (p.nseg > 1 ? p.taps[1] * p.kch[1] : 0);
+
+  if (threadIdx.x == 0) {
+    // ================= TMA producer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      const int p0 = mt * BLOCK_M;
+      const int w0 = p0 % p.W;
+      const int h0 = (p0 / p.W) % p.H;
+      const int b0 = p0 / (p.W * p.H);
+      const int bidx = p.tiles_per_batch > 0 ? mt / p.tiles_per_batch : 0;
+      int kb = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const CUtensorMap* tm = (s == 0) ? &tmA0 : &tmA1;
+        for (int tap = 0; tap < p.taps[s]; ++tap) {
+          const int dy = (p.taps[s] == 9) ? tap / 3 - 1 : 0;
+          const int dx = (p.taps[s] == 9) ? tap % 3 - 1 : 0;
+          for (int kc = 0; kc < p.kch[s]; ++kc, ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            ptx::tma_load_4d(tm, &full_bar[stage], sA + stage * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K, w0 + dx,
+                             h0 + dy, b0);
+            ptx::tma_load_4d(&tmB, &full_bar[stage], sB + stage * L::B_TILE_BYTES, p.w_koff + kb * BLOCK_K,
+                             nt * BLOCK_N, bidx, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = ptx::umma_idesc_f16(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sA + stage * A_TILE_BYTES));
+        const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sB + stage * L::B_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 fp16 = 32 bytes inside the swizzle row: +2 in the 16-byte-granular address field
+          ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        }
+        ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(&tfull_bar[acc]);              // accumulator ready for the epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ================= epilogue =================
+    const int quad = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+      const long long m = (long long)mt * BLOCK_M + row;
+      const bool valid = m < p.M;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N;
+      uint32_t r[32];
+      if (EPI == EPI_LINEAR) {
+        const float rs = (p.rowscale != nullptr && valid) ? p.rowscale[m] : 1.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          const int n0 = nt * BLOCK_N + c0;
+          if (valid) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs;
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (p.bias2 != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (p.residual != nullptr) {
+              const float4* rp = reinterpret_cast<const float4*>(p.residual + m * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(rp + (j >> 2));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= p.scale;
+            if (p.out32 != nullptr) {
+              float4* op = reinterpret_cast<float4*>(p.out32 + m * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.out16 != nullptr) {
+              uint4* op = reinterpret_cast<uint4*>(p.out16 + m * p.ldo + n0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]);
+                __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
+                __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                op[j >> 3] = pk;
+              }
+            }
+          }
+        }
+      } else {
+        // row softmax over the BLOCK_N columns of this tile (requires N == BLOCK_N)
+        const float sc = p.scale * 1.4426950408889634f;     // exp(x) = exp2(x * log2 e)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) * sc);
+        }
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            // round to fp16 first so that the row sum matches what the PV GEMM will actually consume
+            v[j] = __half2float(__float2half_rn(exp2f(__uint_as_float(r[j]) * sc - mx)));
+            sum += v[j];
+          }
+          if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(p.out16 + m * p.ldo + c0);
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __half2 h0 = __floats2half2_rn(v[j], v[j + 1]);
+              __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+              __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
+              __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              op[j >> 3] = pk;
+            }
+          }
+        }
+        if (valid) p.row_out[m] = 1.0f / sum;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CUDA-core reference with identical semantics (validation of the tcgen05 path on the GPU; never the
+// default).  64x64 output tile, 16-wide K slices, 256 threads x (4x4) outputs.
+// ---------------------------------------------------------------------------------------------------
+struct RefArgs {
+  const __half* a[2];
+  int ctot[2], coff[2], c[2], taps[2];
+  int nseg;
+  int B, H, W, M, N;
+  const __half* w;
+  int w_ld, w_koff;
+  long long w_batch_stride;
+  int tiles_per_batch_rows;      // rows of M per batch matrix (0 = shared)
+  const float* bias;
+  const float* bias2;
+  const float* residual;
+  const float* rowscale;
+  float scale;
+  float* out32;
+  __half* out16;
+  float* row_out;
+  int ldo;
+  int epi;
+  float* softmax_tmp;            // [M, N] scratch for the softmax epilogue
+};
+
+__global__ void __launch_bounds__(256) conv_gemm_ref_kernel(const RefArgs p) {
+  __shared__ float sA[16][64 + 1];
+  __shared__ float sW[16][64 + 1];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const long long m0 = (long long)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  int kglobal = 0;
+  for (int s = 0; s < p.nseg; ++s) {
+    for (int tap = 0; tap < p.taps[s]; ++tap) {
+      const int dy = (p.taps[s] == 9) ? tap / 3 - 1 : 0;
+      const int dx = (p.taps[s] == 9) ? tap % 3 - 1 : 0;
+      for (int c0 = 0; c0 < p.c[s]; c0 += 16, kglobal += 16) {
+        // load A slice: 64 rows x 16 k
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+          const int r = i / 16, kk = i % 16;
+          const long long m = m0 + r;
+          float v = 0.f;
+          if (m < p.M) {
+            const int x = int(m % p.W), y = int((m / p.W) % p.H);
+            const long long b = m / ((long long)p.W * p.H);
+            const int yy = y + dy, xx = x + dx;
+            if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+              v = __half2float(p.a[s][((b * p.H + yy) * p.W + xx) * p.ctot[s] + p.coff[s] + c0 + kk]);
+          }
+          sA[kk][r] = v;
+        }
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+          const int r = i / 16, kk = i % 16;
+          const int n = n0 + r;
+          float v = 0.f;
+          if (n < p.N) {
+            long long boff = 0;
+            if (p.w_batch_stride != 0) boff = (m0 / p.tiles_per_batch_rows) * p.w_batch_stride;
+            v = __half2float(p.w[boff + (long long)n * p.w_ld + p.w_koff + kglobal + kk]);
+          }
+          sW[kk][r] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          float a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = sW[kk][tx * 4 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.epi == EPI_SOFTMAX) {
+        p.softmax_tmp[m * p.N + n] = v * p.scale;
+        continue;
+      }
+      if (p.rowscale) v *= p.rowscale[m];
+      if (p.bias) v += p.bias[n];
+      if (p.bias2) v += p.bias2[n];
+      if (p.residual) v += p.residual[m * p.ldo + n];
+      v *= p.scale;
+      if (p.out32) p.out32[m * p.ldo + n] = v;
+      if (p.out16) p.out16[m * p.ldo + n] = __float2half_rn(v);
+    }
+  }
+}
+
+__global__ void softmax_ref_kernel(const float* s, __half* out16, float* row_out, int M, int N, int ldo) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float mx = -INFINITY;
+  for (int n = 0; n < N; ++n) mx = fmaxf(mx, s[m * N + n]);
+  float sum = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const __half e = __float2half_rn(expf(s[m * N + n] - mx));
+    sum += __half2float(e);
+    out16[m * ldo + n] = e;
+  }
+  row_out[m] = 1.0f / sum;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+static int encode_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], const uint32_t box[4]) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) GEMM_FAIL("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {dims[0] * 2, dims[0] * dims[1] * 2, dims[0] * dims[1] * dims[2] * 2};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    GEMM_FAIL("cuTensorMapEncodeTiled failed (%d) dims=%llu,%llu,%llu,%llu box=%u,%u,%u,%u", (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], box[0], box[1], box[2], box[3]);
+  return 0;
+}
+
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+int gemm_prepare(GemmOp* op, int force_block_n) {
+  op->prepared = 0;
+  const long long M = (long long)op->B * op->H * op->W;
+  if (!is_pow2(op->W) || !is_pow2(op->H)) GEMM_FAIL("conv_gemm: H and W must be powers of two (got %d x %d)", op->H, op->W);
+  if (op->nseg < 1 || op->nseg > 2) GEMM_FAIL("conv_gemm: 1 or 2 A segments");
+  int ktot = 0;
+  for (int s = 0; s < op->nseg; ++s) {
+    const GemmSeg& g = op->seg[s];
+    if (g.c % BLOCK_K != 0 || g.c_off % 8 != 0 || g.c_total % 8 != 0)
+      GEMM_FAIL("conv_gemm: segment %d channels (%d of %d at %d) must be a multiple of %d", s, g.c, g.c_total, g.c_off, BLOCK_K);
+    if (g.taps != 1 && g.taps != 9) GEMM_FAIL("conv_gemm: taps must be 1 or 9");
+    ktot += g.taps * g.c;
+  }
+  if (op->w_koff + ktot > op->w_ld) GEMM_FAIL("conv_gemm: K range exceeds weight row stride");
+  int bn = force_block_n;
+  if (bn == 0) {
+    if (op->epi == EPI_SOFTMAX) bn = op->N;
+    else if (op->N % 256 == 0) bn = 256;
+    else if (op->N % 128 == 0) bn = 128;
+    else if (op->N % 64 == 0) bn = 64;
+    else if (op->N % 32 == 0) bn = 32;
+    else GEMM_FAIL("conv_gemm: N=%d must be a multiple of 32", op->N);
+    // keep at least ~2 tiles per SM when the layer is small
+    const long long mt = (M + BLOCK_M - 1) / BLOCK_M;
+    while (bn > 64 && mt * (op->N / bn) < 2 * 148 && op->epi != EPI_SOFTMAX) bn >>= 1;
+  }
+  if (op->N % bn != 0) GEMM_FAIL("conv_gemm: N=%d not a multiple of block_n=%d", op->N, bn);
+  if (op->epi == EPI_SOFTMAX && (bn != op->N || bn != 256)) GEMM_FAIL("conv_gemm: softmax epilogue needs N == 256");
+  if (op->epi == EPI_SOFTMAX && (!op->out16 || !op->row_out)) GEMM_FAIL("conv_gemm: softmax needs out16 and row_out");
+  if (op->ldo % 8 != 0) GEMM_FAIL("conv_gemm: ldo must be a multiple of 8");
+  op->block_n = bn;
+  op->m_tiles = int((M + BLOCK_M - 1) / BLOCK_M);
+  op->n_tiles = op->N / bn;
+  op->tiles_per_batch = 0;
+  if (op->w_batch_stride != 0) {
+    const int hw = op->H * op->W;
+    if (hw % BLOCK_M != 0) GEMM_FAIL("conv_gemm: batched B operand needs H*W %% 128 == 0");
+    op->tiles_per_batch = hw / BLOCK_M;
+  }
+  // A boxes: 128 consecutive pixels in NHW order
+  const uint32_t bw = op->W < BLOCK_M ? op->W : BLOCK_M;
+  const uint32_t bh = (op->H < int(BLOCK_M / bw)) ? op->H : BLOCK_M / bw;
+  const uint32_t bb = BLOCK_M / (bw * bh);
+  for (int s = 0; s < op->nseg; ++s) {
+    const GemmSeg& g = op->seg[s];
+    const uint64_t dims[4] = {(uint64_t)g.c_total, (uint64_t)op->W, (uint64_t)op->H, (uint64_t)op->B};
+    const uint32_t box[4] = {BLOCK_K, bw, bh, bb};
+    if (encode_4d(&op->tmA[s], g.ptr, dims, box)) return -1;
+  }
+  if (op->nseg == 1) op->tmA[1] = op->tmA[0];
+  {
+    uint64_t nb = 1, rows = op->N;
+    if (op->w_batch_stride != 0) {
+      rows = op->w_rows_per_batch;
+      if ((long long)rows * op->w_ld != op->w_batch_stride) GEMM_FAIL("conv_gemm: batched B operand must be dense");
+      nb = op->B;
+    }
+    const uint64_t dims[4] = {(uint64_t)op->w_ld, rows, nb, 1};
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)bn, 1, 1};
+    if (encode_4d(&op->tmB, op->w, dims, box)) return -1;
+  }
+  op->prepared = 1;
+  return 0;
+}
+
+template <int BN, int EPI>
+static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  static bool attr_set = false;
+  auto kern = conv_gemm_umma_kernel<BN, EPI>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) GEMM_FAIL("cudaFuncSetAttribute(smem=%d): %s", L::TOTAL, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(op->tmA[0], op->tmA[1], op->tmB, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) GEMM_FAIL("conv_gemm_umma launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static float* g_softmax_tmp = nullptr;
+static size_t g_softmax_tmp_bytes = 0;
+
+int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
+  const long long M = (long long)op->B * op->H * op->W;
+  if (impl == 0) {
+    if (!op->prepared) GEMM_FAIL("conv_gemm: op not prepared");
+    GemmArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int s = 0; s < op->nseg; ++s) {
+      a.taps[s] = op->seg[s].taps;
+      a.kch[s] = op->seg[s].c / BLOCK_K;
+      a.coff[s] = op->seg[s].c_off;
+    }
+    a.nseg = op->nseg;
+    a.H = op->H; a.W = op->W;
+    a.M = (int)M; a.N = op->N;
+    a.m_tiles = op->m_tiles; a.n_tiles = op->n_tiles; a.tiles_per_batch = op->tiles_per_batch;
+    a.w_koff = op->w_koff;
+    a.bias = op->bias; a.bias2 = op->bias2; a.residual = op->residual; a.rowscale = op->rowscale;
+    a.scale = op->scale; a.out32 = op->out32; a.out16 = op->out16; a.row_out = op->row_out; a.ldo = op->ldo;
+    if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX>(op, a, st);
+    switch (op->block_n) {
+      case 256: return launch_umma<256, EPI_LINEAR>(op, a, st);
+      case 128: return launch_umma<128, EPI_LINEAR>(op, a, st);
+      case 64: return launch_umma<64, EPI_LINEAR>(op, a, st);
+      case 32: return launch_umma<32, EPI_LINEAR>(op, a, st);
+      default: GEMM_FAIL("conv_gemm: unsupported block_n %d", op->block_n);
+    }
+  }
+  // reference path
+  RefArgs r;
+  memset(&r, 0, sizeof(r));
+  for (int s = 0; s < op->nseg; ++s) {
+    r.a[s] = op->seg[s].ptr; r.ctot[s] = op->seg[s].c_total; r.coff[s] = op->seg[s].c_off;
+    r.c[s] = op->seg[s].c; r.taps[s] = op->seg[s].taps;
+  }
+  r.nseg = op->nseg; r.B = op->B; r.H = op->H; r.W = op->W; r.M = (int)M; r.N = op->N;
+  r.w = op->w; r.w_ld = op->w_ld; r.w_koff = op->w_koff; r.w_batch_stride = op->w_batch_stride;
+  r.tiles_per_batch_rows = op->H * op->W;
+  r.bias = op->bias; r.bias2 = op->bias2; r.residual = op->residual; r.rowscale = op->rowscale;
+  r.scale = op->scale; r.out32 = op->out32; r.out16 = op->out16; r.row_out = op->row_out; r.ldo = op->ldo;
+  r.epi = op->epi;
+  if (op->w_batch_stride != 0 && (op->H * op->W) % 64 != 0) GEMM_FAIL("conv_gemm ref: batched B needs H*W %% 64 == 0");
+  if (op->epi == EPI_SOFTMAX) {
+    const size_t need = (size_t)M * op->N * sizeof(float);
+    if (need > g_softmax_tmp_bytes) {
+      if (g_softmax_tmp) cudaFree(g_softmax_tmp);
+      if (cudaMalloc(&g_softmax_tmp, need) != cudaSuccess) GEMM_FAIL("conv_gemm ref: softmax scratch alloc failed");
+      g_softmax_tmp_bytes = need;
+    }
+    r.softmax_tmp = g_softmax_tmp;
+  }
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((op->N + 63) / 64));
+  conv_gemm_ref_kernel<<<grid, 256, 0, st>>>(r);
+  if (op->epi == EPI_SOFTMAX)
+    softmax_ref_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(g_softmax_tmp, op->out16, op->row_out, (int)M, op->N, op->ldo);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) GEMM_FAIL("conv_gemm_ref launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace gddim

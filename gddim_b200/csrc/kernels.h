@@ -1,0 +1,134 @@
+// Host-side declarations of every device op of the sampling hot path (sm_100a).
+// Tensors are NHWC; "T32" = fp32 trunk / conv outputs, "T16" = fp16 GEMM operands.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace gddim {
+
+// ---- implicit-GEMM convolution / GEMM (conv_gemm.cu) -------------------------------------------
+// out[m, n] = epilogue( sum_seg sum_tap sum_c A_seg[pixel(m)+tap, c] * Wt[n, k(seg,tap,c)] )
+//   m enumerates pixels of a [B,H,W] grid in NHW order; taps = 9 -> 3x3 SAME window, 1 -> pointwise.
+//   Wt is K-major: [N, Ktot] fp16 (optionally one matrix per batch item: attention QK^T / PV).
+// Linear epilogue: out = (acc * rowscale[m] + bias[n] + bias2[n] + residual[m,n]) * scale
+// Softmax epilogue (N == block_n == 256): out16 = exp(acc*scale - rowmax), row_out[m] = 1/rowsum.
+struct GemmSeg {
+  const __half* ptr;   // [B,H,W,c_total]
+  int c_total;         // channel count of the tensor
+  int c_off;           // first channel used
+  int c;               // channels used (multiple of 64)
+  int taps;            // 1 or 9
+};
+
+enum { EPI_LINEAR = 0, EPI_SOFTMAX = 1 };
+
+struct GemmOp {
+  GemmSeg seg[2];
+  int nseg;
+  int B, H, W;
+  const __half* w;          // weights / B operand, K-major
+  int N;                    // output columns
+  int w_ld;                 // row stride of w in elements (>= Ktot)
+  int w_koff;               // first K column used in w
+  long long w_batch_stride; // elements between per-image B matrices; 0 = shared weights
+  int w_rows_per_batch;     // rows (N) per batch matrix when batched
+  const float* bias;
+  const float* bias2;
+  const float* residual;    // [M, ldo] fp32
+  const float* rowscale;    // [M]
+  float scale;
+  float* out32;             // [M, ldo]
+  __half* out16;            // [M, ldo]
+  float* row_out;           // [M] (softmax)
+  int ldo;
+  int epi;
+  // GroupNorm partial statistics of the fp32 output (optional): per (image, group) sum / sumsq
+  // ---- filled by gemm_prepare ----
+  CUtensorMap tmA[2];
+  CUtensorMap tmB;
+  int block_n;
+  int m_tiles, n_tiles, tiles_per_batch;
+  int prepared;
+};
+
+// Encodes the TMA descriptors (needs the final device addresses). Returns 0 or a negative error.
+int gemm_prepare(GemmOp* op, int force_block_n);
+// impl: 0 = tcgen05/TMA kernel, 1 = CUDA-core reference kernel (validation only)
+int gemm_launch(const GemmOp* op, int impl, cudaStream_t st);
+const char* gemm_last_error();
+
+// ---- GroupNorm (+SiLU) (+FIR / naive resampling) (norm.cu) ---------------------------------------
+enum { RS_NONE = 0, RS_FIR_DOWN = 1, RS_FIR_UP = 2, RS_NAIVE_DOWN = 3, RS_NAIVE_UP = 4 };
+
+struct NormOp {
+  const float* src1; int c1;     // [B,H,W,c1]
+  const float* src2; int c2;     // optional second source, channel-concatenated after src1
+  int B, H, W;                   // input grid
+  int groups;
+  const float* gamma; const float* beta;   // [c1+c2]
+  float eps;
+  int silu;                      // apply x*sigmoid(x) after the affine
+  int resample;                  // RS_*
+  float* partial;                // [B, splits, groups, 2] scratch
+  int splits;
+  __half* dst16;                 // normalised (+act, +resample) output  [B,H',W',C]; may be null
+  __half* raw16;                 // raw (resampled) copy of the input in fp16; may be null
+};
+int norm_launch(const NormOp* op, cudaStream_t st);
+int norm_splits(int B, int H, int W);
+
+// ---- small direct convolutions and data movement (small.cu) ---------------------------------------
+// 3x3 SAME conv with few input channels (stem): in fp32 [B,H,W,cin] -> out32 [B,H,W,cout]
+int stem_conv_launch(const float* in, const float* w /*[3,3,cin,cout]*/, const float* bias, float* out32, int B,
+                     int H, int W, int cin, int cout, cudaStream_t st);
+// 3x3 SAME conv with few output channels (head): in fp16 [B,H,W,cin] -> out32 [B,H,W,cout]
+int head_conv_launch(const __half* in, const float* w /*[3,3,cin,cout]*/, const float* bias, float* out32, int B,
+                     int H, int W, int cin, int cout, cudaStream_t st);
+// FIR (pad 2, [1,3,3,1]x[1,3,3,1]/64) followed by the 3x3 stride-2 VALID window gather:
+// in fp32 [B,H,W,c] -> A16 [B,H/2,W/2,kpad] with k = tap*c + ch (zero padded to kpad)
+int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,
+                           cudaStream_t st);
+// V^T per image for the PV GEMM: qkv16 [B,T,ld] (V at channel voff) -> vT [B,C,T]
+int transpose_v_launch(const __half* qkv, __half* vT, int B, int T, int C, int ld, int voff, cudaStream_t st);
+// Full attention for very short sequences (T <= 64): qkv16 [B,T,3C] -> o16 [B,T,C]
+int small_attn_launch(const __half* qkv, __half* o16, int B, int T, int C, float scale, cudaStream_t st);
+// y[r, n] = bias[n] + sum_k act(x[r,k]) * w[k,n]  (time-embedding MLP and per-block projections; fp32)
+int dense_launch(const float* x, const float* w, const float* bias, float* y, int rows, int K, int N, int silu_in,
+                 cudaStream_t st);
+int add_vec_launch(const float* a, const float* b, float* y, int n, cudaStream_t st);
+
+// ---- sampler updates (update.cu) --------------------------------------------------------------------
+// State in "net layout" [B,H,W,2C]: channel d (< C) = x_d, channel C+d = v_d.
+// u' = A u + sum_j Cj e_j   with 2x2 matrices acting on (x_d, v_d); e_0 = eps_new (+ M u if mixed).
+struct CldStepArgs {
+  const float* u; float* u_out;
+  const float* eps[6];         // eps[0] newest
+  int n_eps;                   // number of eps terms with (possibly) non-zero coefficient
+  float coef[7][4];            // coef[0] = A, coef[1+j] = C_j (row-major 2x2)
+  int mixed; float mixm[4];    // eps_0 += M u, written back to eps_store
+  float* eps_store;
+  long long n_pix; int C;
+};
+int cld_step_launch(const CldStepArgs* a, cudaStream_t st);
+// x = u_x * mul + add, v = u_v : [B,H,W,2C] -> x[B,H,W,C], v[B,H,W,C]
+int cld_split_launch(const float* u, float* x, float* v, long long n_pix, int C, float mul, float add, cudaStream_t st);
+// reference layout [..., C, 2] <-> net layout [..., 2C]
+int relayout_launch(const float* src, float* dst, long long n_pix, int C, int to_net, cudaStream_t st);
+// Reference-API update on reference-layout arrays (deis.multistep_ab_step): x,new_eps [n,2]; hist [order+1,n,2]
+int ab_step_ref_layout_launch(const float* x, const float* coef /*[(order+3)*4]*/, const float* new_eps,
+                              const float* hist, float* x_out, float* hist_out, int order, long long n_pairs,
+                              cudaStream_t st);
+
+// 2-D orthonormal DCT-II (fwd=1) / DCT-III (fwd=0) on 32x32 NHWC planes
+int dct32_launch(const float* in, float* out, int B, int C, int fwd, cudaStream_t st);
+// Blur DDIM step: y' = a .* y + b .* DCT(eps_x);  x_next = IDCT(y')   (a, b: [32,32])
+int blur_step_launch(const float* y, const float* eps_x, const float* a, const float* b, float* y_out,
+                     float* x_next, int B, int C, cudaStream_t st);
+int scale_shift_launch(const float* in, float* out, long long n, float mul, float add, cudaStream_t st);
+// Scalar-coefficient AB step (blur multistep.ab_step): x' = c0 x + sum_j c_{1+j} e_j
+int scalar_ab_step_launch(const float* x, const float* coef, const float* new_eps, const float* hist, float* x_out,
+                          float* hist_out, int n_hist, long long n, cudaStream_t st);
+
+}  // namespace gddim

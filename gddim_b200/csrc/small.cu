@@ -1,0 +1,296 @@
+// Small CUDA-core kernels around the tensor-core GEMMs: stem / head convolutions (6 or 3 channels on one
+// side: < 0.1 % of the FLOPs, no tensor-core path), the FIR + stride-2 window gather of the input pyramid,
+// V transposition for the PV GEMM, 16-token attention of the 4x4 middle block, and the tiny dense layers of
+// the time embedding.
+//
+// Reference semantics: cld_jax/models/ncsnpp.py:146 (stem conv3x3), :237 (head conv3x3, init_scale),
+// layerspp.py:115-143 + up_or_down_sampling.py:168-209 (Downsample fir+with_conv = conv_downsample_2d),
+// layerspp.py:61-83 (AttnBlockpp), ncsnpp.py:87-89 + layerspp.py:216 (Dense).
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace gddim {
+
+static int ceil_div_ll(long long a, long long b) { return int((a + b - 1) / b); }
+
+// ---- stem: fp32 in [B,H,W,cin<=8] -> out32 [B,H,W,cout]; block = 4 image rows x all couts ------------------
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int H,
+                                                       int W, int cin, int cout) {
+  extern __shared__ float sm[];
+  float* sw = sm;                              // [9*cin][cout]
+  float* sin_ = sm + 9 * cin * cout;           // [(rows+2)][W+2][cin]
+  const int rows = 4;
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * rows;
+  for (int i = threadIdx.x; i < 9 * cin * cout; i += blockDim.x) sw[i] = w[i];
+  const int tw = W + 2;
+  for (int i = threadIdx.x; i < (rows + 2) * tw * cin; i += blockDim.x) {
+    const int ci = i % cin;
+    const int x = (i / cin) % tw - 1;
+    const int y = y0 + i / (cin * tw) - 1;
+    float v = 0.f;
+    if (x >= 0 && x < W && y >= 0 && y < H) v = in[(((long long)b * H + y) * W + x) * cin + ci];
+    sin_[i] = v;
+  }
+  __syncthreads();
+  const int total = rows * W * cout;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int co = i % cout;
+    const int x = (i / cout) % W;
+    const int r = i / (cout * W);
+    if (y0 + r >= H) continue;
+    float acc = bias ? bias[co] : 0.f;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* ip = sin_ + ((r + ky) * tw + (x + kx)) * cin;
+        const float* wp = sw + ((ky * 3 + kx) * cin) * cout + co;
+        for (int ci = 0; ci < cin; ++ci) acc += ip[ci] * wp[ci * cout];
+      }
+    out[(((long long)b * H + y0 + r) * W + x) * cout + co] = acc;
+  }
+}
+
+int stem_conv_launch(const float* in, const float* w, const float* bias, float* out32, int B, int H, int W, int cin,
+                     int cout, cudaStream_t st) {
+  const size_t smem = (size_t)(9 * cin * cout + 6 * (W + 2) * cin) * sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  dim3 grid((H + 3) / 4, B);
+  stem_conv_kernel<<<grid, 256, smem, st>>>(in, w, bias, out32, H, W, cin, cout);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---- head: fp16 in [B,H,W,cin] -> out32 [B,H,W,cout<=8]; one warp per output pixel ---------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256) head_conv_kernel(const __half* __restrict__ in, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                       int H, int W, int cin) {
+  extern __shared__ float sw[];                // [9*cin][COUT]
+  for (int i = threadIdx.x; i < 9 * cin * COUT; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long npix = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); pix < npix; pix += (long long)gridDim.x * 8) {
+    const int x = int(pix % W), y = int((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const __half* ip = in + ((b * H + yy) * W + xx) * cin;
+        const float* wp = sw + (ky * 3 + kx) * cin * COUT;
+        for (int ci = lane * 2; ci < cin; ci += 64) {
+          const float2 v = __half22float2(*reinterpret_cast<const __half2*>(ip + ci));
+#pragma unroll
+          for (int j = 0; j < COUT; ++j) acc[j] += v.x * wp[ci * COUT + j] + v.y * wp[(ci + 1) * COUT + j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (lane < COUT) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < COUT; ++j) if (lane == j) v = acc[j];
+      out[pix * COUT + lane] = v + (bias ? bias[lane] : 0.f);
+    }
+  }
+}
+
+int head_conv_launch(const __half* in, const float* w, const float* bias, float* out32, int B, int H, int W, int cin,
+                     int cout, cudaStream_t st) {
+  const size_t smem = (size_t)9 * cin * cout * sizeof(float);
+  if (smem > 48 * 1024 || cin % 2 != 0) return -1;
+  const long long npix = (long long)B * H * W;
+  int grid = ceil_div_ll(npix, 8);
+  if (grid > 148 * 16) grid = 148 * 16;
+  switch (cout) {
+    case 3: head_conv_kernel<3><<<grid, 256, smem, st>>>(in, w, bias, out32, B, H, W, cin); break;
+    case 6: head_conv_kernel<6><<<grid, 256, smem, st>>>(in, w, bias, out32, B, H, W, cin); break;
+    case 1: head_conv_kernel<1><<<grid, 256, smem, st>>>(in, w, bias, out32, B, H, W, cin); break;
+    case 2: head_conv_kernel<2><<<grid, 256, smem, st>>>(in, w, bias, out32, B, H, W, cin); break;
+    default: return -3;
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---- input pyramid: FIR (pad 2) then 3x3 stride-2 VALID window gather -> GEMM A operand ---------------------
+__global__ void __launch_bounds__(256) im2col_fir_down_kernel(const float* __restrict__ in, __half* __restrict__ a16,
+                                                             int B, int H, int W, int c, int kpad, int use_fir) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * kpad;
+  const float kf[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = int(idx % kpad);
+    const long long opix = idx / kpad;
+    float v = 0.f;
+    if (k < 9 * c) {
+      const int ch = k % c, tap = k / c;
+      const int ky = tap / 3, kx = tap % 3;
+      const int ox = int(opix % Wo), oy = int((opix / Wo) % Ho);
+      const long long b = opix / ((long long)Wo * Ho);
+      if (use_fir) {
+        // FIR output grid is (H+1)x(W+1): f[py][px] = sum_{i,j} k[i]k[j] in[py + i - 2][px + j - 2]
+        const int py = 2 * oy + ky, px = 2 * ox + kx;
+        for (int i = 0; i < 4; ++i) {
+          const int iy = py + i - 2;
+          if (iy < 0 || iy >= H) continue;
+          for (int j = 0; j < 4; ++j) {
+            const int ix = px + j - 2;
+            if (ix < 0 || ix >= W) continue;
+            v += kf[i] * kf[j] * in[((b * H + iy) * W + ix) * c + ch];
+          }
+        }
+      } else {
+        // plain stride-2 SAME 3x3 (pad (0,1)): used only when fir is off
+        const int iy = 2 * oy + ky, ix = 2 * ox + kx;
+        if (iy < H && ix < W) v = in[((b * H + iy) * W + ix) * c + ch];
+      }
+    }
+    a16[idx] = __float2half_rn(v);
+  }
+}
+
+int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,
+                           cudaStream_t st) {
+  const long long total = (long long)B * (H / 2) * (W / 2) * kpad;
+  int grid = ceil_div_ll(total, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  im2col_fir_down_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, kpad, use_fir);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---- V^T: qkv16 [B,T,ld] (V at voff) -> vT [B,C,T]; 32x32 tiles through shared memory ------------------------
+__global__ void __launch_bounds__(256) transpose_v_kernel(const __half* __restrict__ qkv, __half* __restrict__ vT, int T,
+                                                         int C, int ld, int voff) {
+  __shared__ __half tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, c = c0 + tx;
+    tile[r][tx] = (t < T && c < C) ? qkv[((long long)b * T + t) * ld + voff + c] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, t = t0 + tx;
+    if (c < C && t < T) vT[((long long)b * C + c) * T + t] = tile[tx][r];
+  }
+}
+
+int transpose_v_launch(const __half* qkv, __half* vT, int B, int T, int C, int ld, int voff, cudaStream_t st) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+  transpose_v_kernel<<<grid, 256, 0, st>>>(qkv, vT, T, C, ld, voff);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---- attention for very short sequences (the 4x4 middle block: T = 16) ---------------------------------------
+__global__ void __launch_bounds__(256) small_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o16, int T,
+                                                        int C, float scale) {
+  extern __shared__ float sm[];
+  float* sq = sm;                 // [T][C]
+  float* sk = sq + T * C;
+  float* sv = sk + T * C;
+  float* ss = sv + T * C;         // [T][T]
+  const int b = blockIdx.x;
+  const __half* base = qkv + (long long)b * T * 3 * C;
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    const int t = i / C, c = i % C;
+    sq[i] = __half2float(base[t * 3 * C + c]);
+    sk[i] = __half2float(base[t * 3 * C + C + c]);
+    sv[i] = __half2float(base[t * 3 * C + 2 * C + c]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int e = warp; e < T * T; e += nw) {
+    const int i = e / T, j = e % T;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc += sq[i * C + c] * sk[j * C + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) ss[e] = acc * scale;
+  }
+  __syncthreads();
+  if (threadIdx.x < T) {
+    const int i = threadIdx.x;
+    float mx = -INFINITY;
+    for (int j = 0; j < T; ++j) mx = fmaxf(mx, ss[i * T + j]);
+    float sum = 0.f;
+    for (int j = 0; j < T; ++j) { const float e = expf(ss[i * T + j] - mx); ss[i * T + j] = e; sum += e; }
+    const float inv = 1.0f / sum;
+    for (int j = 0; j < T; ++j) ss[i * T + j] *= inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * C; i += blockDim.x) {
+    const int t = i / C, c = i % C;
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc += ss[t * T + j] * sv[j * C + c];
+    o16[((long long)b * T + t) * C + c] = __float2half_rn(acc);
+  }
+}
+
+int small_attn_launch(const __half* qkv, __half* o16, int B, int T, int C, float scale, cudaStream_t st) {
+  const size_t smem = (size_t)(3 * T * C + T * T) * sizeof(float);
+  if (smem > 200 * 1024 || T > 256) return -1;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaFuncSetAttribute(small_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  small_attn_kernel<<<B, 256, smem, st>>>(qkv, o16, T, C, scale);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---- dense: y[r,n] = bias[n] + sum_k act(x[r,k]) w[k,n]  (w in flax (in,out) layout) ------------------------
+__global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, float* __restrict__ y, int rows, int K,
+                                                   int N, int silu_in) {
+  const long long total = (long long)rows * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int n = int(idx % N);
+    const long long r = idx / N;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float v = x[r * K + k];
+      if (silu_in) v = v / (1.0f + expf(-v));
+      acc += v * w[(long long)k * N + n];
+    }
+    y[idx] = acc + (bias ? bias[n] : 0.f);
+  }
+}
+
+int dense_launch(const float* x, const float* w, const float* bias, float* y, int rows, int K, int N, int silu_in,
+                 cudaStream_t st) {
+  const long long total = (long long)rows * N;
+  int grid = ceil_div_ll(total, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  dense_kernel<<<grid, 256, 0, st>>>(x, w, bias, y, rows, K, N, silu_in);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a[i] + b[i];
+}
+int add_vec_launch(const float* a, const float* b, float* y, int n, cudaStream_t st) {
+  add_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, y, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace gddim

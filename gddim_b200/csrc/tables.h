@@ -1,0 +1,72 @@
+// Host-side (fp64) coefficient tables of the CLD gDDIM / DEIS sampler and the blur-diffusion DDIM sampler.
+// Built once per sampler; nothing here runs per step.
+#pragma once
+#include <vector>
+
+namespace gddim {
+
+struct Mat2 {
+  double a, b, c, d;   // row-major [[a, b], [c, d]]
+};
+inline Mat2 mul(const Mat2& x, const Mat2& y) {
+  return {x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d};
+}
+inline Mat2 inv(const Mat2& m) {
+  const double k = 1.0 / (m.a * m.d - m.b * m.c);
+  return {m.d * k, -m.b * k, -m.c * k, m.a * k};
+}
+inline Mat2 tr(const Mat2& m) { return {m.a, m.c, m.b, m.d}; }
+
+// linspace(T^(1/p), eps^(1/p), n+1)^p
+void rev_timesteps(double T, double eps, int ts_order, int num_step, double* out);
+
+class CldTables {
+ public:
+  CldTables(double m_inv, double beta_0, double beta_1, double vv_gamma, double numerical_eps, double R_dt,
+            bool is_rk);
+  double m_inv, beta_0, beta_1, Gamma, R_dt;
+  bool is_rk;
+  Mat2 R0;
+  double sampling_eps = 1e-3, T = 1.0;
+
+  double beta(double t) const { return beta_0 + beta_1 * t; }
+  double beta_int(double t) const { return beta_0 * t + 0.5 * beta_1 * t * t; }
+  Mat2 F(double t) const;
+  Mat2 G(double t) const;
+  Mat2 R(double t) const;                    // piecewise-linear table lookup
+  Mat2 psi(double s, double t) const;        // closed-form transition matrix
+  Mat2 eps_integrand(double t) const;        // 0.5 G G R^{-T}
+  // [N, order+3, 2, 2]: [i,0] = Psi(t_i, t_{i+1}); [i,1+j] = DEIS Adams-Bashforth coefficient j; trailing zero
+  void deis_coef(int order, const double* rev_ts, int n_ts, double* out) const;
+  // [N,2,2] mean and eps matrices of the order-0 gDDIM sampler (1000-node quadrature)
+  void order0_coef(const double* rev_ts, int n_ts, double* mean_out, double* eps_out) const;
+  // denoising step as u' = A u + C eps
+  void denoise_coef(double t, Mat2* A, Mat2* C) const;
+
+ private:
+  std::vector<double> xp_;
+  std::vector<Mat2> fp_;
+  Mat2 ode_rhs(const Mat2& R, double t) const;
+  Mat2 quad(double t_start, double t_end, const double* ts_poly, int n_poly, int coef_idx, int num_item) const;
+  void coef_row(int highest_order, int order, double t_start, double t_end, const double* ts_poly, double* out) const;
+  void ab_eps_coef(int highest_order, const double* ts, int n_ts, int order, std::vector<double>& out) const;
+};
+
+class BlurTables {
+ public:
+  BlurTables(double sigma_blur_max, double sampling_eps, double min_scale = 0.001, int img_dim = 32);
+  double sigma_blur_max, sampling_eps, min_scale;
+  int img_dim;
+  double alpha_start;
+  double t2alpha(double t) const;
+  double alpha2t(double a) const;
+  double rho2t(double rho) const;
+  double sampling_T() const { return rho2t(80.0); }
+  void freq_scaling(double t, double* out /*[dim*dim]*/) const;
+  void y_mean_coef(double t, double* out /*[dim*dim]*/) const;
+  double y_std_coef(double t) const;
+  // per-step per-frequency DDIM coefficients: y' = a .* y + b .* eps_y
+  void order0_coef(const double* rev_ts, int n_ts, double* a_out, double* b_out) const;
+};
+
+}  // namespace gddim

@@ -1,0 +1,739 @@
+// NCSN++ / DDPM++ forward as a static launch plan over the kernels of kernels.h.
+//
+// Control flow follows cld_jax/models/ncsnpp.py:41-243; blocks follow layerspp.py:61-83 (AttnBlockpp),
+// :115-143 (Downsample), :180-227 (ResnetBlockBigGANpp); parameter names follow flax.linen compact-module
+// auto naming (<Class>_<k> per parent scope) so that a Flax checkpoint tree can be loaded by name.
+//
+// Fusions relative to the reference graph:
+//   * Dense_0(act(temb)) of every ResBlock depends only on t -> one [temb_dim x sum(C_out)] GEMV per time
+//     value, added as a second bias in the conv1 epilogue (conv1's own bias is folded into it).
+//   * the 1x1 shortcut conv (Conv_2) is appended to conv2's K loop as a second A segment; (x + h)/sqrt(2)
+//     is the epilogue scale.  Identity shortcuts are a residual read in the epilogue.
+//   * channel concat [h, skip] is never materialised: GroupNorm reads two sources.
+//   * FIR / naive resampling is fused into the GroupNorm+swish apply pass (both branches).
+//   * q, k, v projections are one GEMM (N = 3C); softmax is the epilogue of the QK^T GEMM.
+#include "unet.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace gddim {
+
+struct UNet::Scope {
+  std::string prefix;
+  std::map<std::string, int> counts;
+  Scope child(const std::string& cls) {
+    int k = counts[cls]++;
+    Scope s;
+    s.prefix = prefix + cls + "_" + std::to_string(k) + "/";
+    return s;
+  }
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+UNet::UNet(const gddim_model_cfg& cfg, int max_batch) : cfg_(cfg), max_batch_(max_batch) {
+  dry_ = true;
+  arena_ = reinterpret_cast<char*>(uintptr_t(1) << 20);   // fake non-null base for the dry planning pass
+  wts_ = reinterpret_cast<char*>(uintptr_t(1) << 20);
+  if (walk() != 0) return;
+  arena_peak_ = arena_top_;
+}
+
+UNet::~UNet() {
+  if (finalized_ || !dry_) {
+    if (arena_) cudaFree(arena_);
+    if (wts_) cudaFree(wts_);
+  }
+}
+
+// ---- arenas -------------------------------------------------------------------------------------------
+void* UNet::a_alloc(size_t bytes) {
+  bytes = align_up(bytes, 1024);
+  for (size_t i = 0; i < free_.size(); ++i) {
+    if (free_[i].second >= bytes) {
+      const size_t off = free_[i].first;
+      if (free_[i].second == bytes) free_.erase(free_.begin() + i);
+      else { free_[i].first += bytes; free_[i].second -= bytes; }
+      return arena_ + off;
+    }
+  }
+  const size_t off = arena_top_;
+  arena_top_ += bytes;
+  return arena_ + off;
+}
+
+void UNet::a_free(void* p, size_t bytes) {
+  bytes = align_up(bytes, 1024);
+  size_t off = (char*)p - arena_;
+  size_t i = 0;
+  while (i < free_.size() && free_[i].first < off) ++i;
+  free_.insert(free_.begin() + i, {off, bytes});
+  if (i + 1 < free_.size() && free_[i].first + free_[i].second == free_[i + 1].first) {
+    free_[i].second += free_[i + 1].second;
+    free_.erase(free_.begin() + i + 1);
+  }
+  if (i > 0 && free_[i - 1].first + free_[i - 1].second == free_[i].first) {
+    free_[i - 1].second += free_[i].second;
+    free_.erase(free_.begin() + i);
+  }
+}
+
+void* UNet::w_alloc(size_t bytes) {
+  bytes = align_up(bytes, 256);
+  const size_t off = weight_top_;
+  weight_top_ += bytes;
+  return wts_ + off;
+}
+
+float* UNet::upload_f32(const std::vector<float>& v) {
+  float* d = (float*)w_alloc(v.size() * sizeof(float));
+  if (!dry_) cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+  return d;
+}
+__half* UNet::upload_f16(const std::vector<__half>& v) {
+  __half* d = (__half*)w_alloc(v.size() * sizeof(__half));
+  if (!dry_) cudaMemcpy(d, v.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  return d;
+}
+
+UNet::T32 UNet::new32(int C, int H, int W) {
+  T32 t;
+  t.C = C; t.H = H; t.W = W;
+  t.bytes = (size_t)max_batch_ * H * W * C * sizeof(float);
+  t.p = (float*)a_alloc(t.bytes);
+  return t;
+}
+UNet::T16 UNet::new16(int C, int H, int W) {
+  T16 t;
+  t.C = C; t.H = H; t.W = W;
+  t.bytes = (size_t)max_batch_ * H * W * C * sizeof(__half);
+  t.p = (__half*)a_alloc(t.bytes);
+  return t;
+}
+void UNet::rel(T32& t) { if (t.p) a_free(t.p, t.bytes); t.p = nullptr; }
+void UNet::rel(T16& t) { if (t.p) a_free(t.p, t.bytes); t.p = nullptr; }
+
+// ---- parameters -----------------------------------------------------------------------------------------
+const std::vector<float>* UNet::param(Scope& s, const std::string& name, std::vector<int> shape, int kind, float scale) {
+  const std::string full = s.prefix + name;
+  if (dry_) {
+    specs_.push_back({full, shape, kind, scale});
+    return nullptr;
+  }
+  auto it = host_params_.find(full);
+  if (it == host_params_.end()) { err_ = "parameter not loaded: " + full; return nullptr; }
+  size_t n = 1;
+  for (int d : shape) n *= d;
+  if (it->second.size() != n) { err_ = "parameter size mismatch: " + full; return nullptr; }
+  return &it->second;
+}
+
+int UNet::set_param(const std::string& name, const float* host, size_t n) {
+  for (const auto& sp : specs_)
+    if (sp.name == name) {
+      size_t need = 1;
+      for (int d : sp.shape) need *= d;
+      if (need != n) return fail("gddim_param_set: size mismatch for " + name);
+      host_params_[name].assign(host, host + n);
+      return 0;
+    }
+  return fail("gddim_param_set: unknown parameter " + name);
+}
+
+static float scale0(float s) { return s == 0.f ? 1e-10f : s; }   // layers.py:62
+
+// conv kernel HWIO (kh,kw,cin,cout) -> K-major [cout][koff + tap*cin + ci] inside rows of length ld
+static void pack_conv(const std::vector<float>& k, int taps, int cin, int cout, std::vector<__half>& dst, int ld,
+                      int koff) {
+  for (int tap = 0; tap < taps; ++tap)
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* src = k.data() + ((size_t)tap * cin + ci) * cout;
+      for (int co = 0; co < cout; ++co) dst[(size_t)co * ld + koff + tap * cin + ci] = __float2half_rn(src[co]);
+    }
+}
+
+std::pair<const float*, const float*> UNet::gn_params(Scope& s, int C) {
+  Scope g = s.child("GroupNorm");
+  const auto* sc = param(g, "scale", {C}, 2, 1.f);
+  const auto* bi = param(g, "bias", {C}, 1, 1.f);
+  if (dry_) { w_alloc(C * 4); w_alloc(C * 4); return {nullptr, nullptr}; }
+  if (!sc || !bi) return {nullptr, nullptr};
+  return {upload_f32(*sc), upload_f32(*bi)};
+}
+
+void UNet::add_norm(const T32& in1, const T32* in2, const float* gamma, const float* beta, bool silu, int resample,
+                    T16* dst, T16* raw, const std::string& tag) {
+  Op op;
+  op.kind = OP_NORM;
+  op.tag = tag;
+  NormOp& n = op.norm;
+  memset(&n, 0, sizeof(n));
+  n.src1 = in1.p; n.c1 = in1.C;
+  n.src2 = in2 ? in2->p : nullptr; n.c2 = in2 ? in2->C : 0;
+  n.B = max_batch_; n.H = in1.H; n.W = in1.W;
+  const int C = n.c1 + n.c2;
+  n.groups = std::min(C / 4, 32);
+  n.gamma = gamma; n.beta = beta;
+  n.eps = 1e-6f;
+  n.silu = silu ? 1 : 0;
+  n.resample = resample;
+  n.partial = gn_partial_;
+  n.splits = norm_splits(max_batch_, in1.H, in1.W);
+  n.dst16 = dst ? dst->p : nullptr;
+  n.raw16 = raw ? raw->p : nullptr;
+  ops_.push_back(op);
+}
+
+int UNet::add_temb_proj(const std::vector<float>* w, const std::vector<float>* b, const std::vector<float>* conv_b,
+                        int out_ch) {
+  const int off = temb_total_;
+  temb_total_ += out_ch;
+  if (!dry_) {
+    // proj_w_host_ is [temb_dim][total] assembled column-block by column-block; total known from the dry pass
+    const int total = (int)proj_b_host_.size();
+    for (int k = 0; k < temb_dim_; ++k)
+      for (int n = 0; n < out_ch; ++n) proj_w_host_[(size_t)k * total + off + n] = (*w)[(size_t)k * out_ch + n];
+    for (int n = 0; n < out_ch; ++n) proj_b_host_[off + n] = (*b)[n] + (*conv_b)[n];
+  }
+  return off;
+}
+
+static GemmOp make_gemm(int B, int H, int W) {
+  GemmOp g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.H = H; g.W = W;
+  g.scale = 1.f;
+  g.epi = EPI_LINEAR;
+  return g;
+}
+
+// ---- ResnetBlockBigGANpp (layerspp.py:180-227) ------------------------------------------------------------
+UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch, bool up, bool down) {
+  Scope s = top.child("ResnetBlockBigGANpp");
+  const int Cin = in1.C + (in2 ? in2->C : 0);
+  if (out_ch == 0) out_ch = Cin;
+  const int H = in1.H, W = in1.W;
+  const int Ho = up ? H * 2 : (down ? H / 2 : H), Wo = up ? W * 2 : (down ? W / 2 : W);
+  const bool need_sc = (Cin != out_ch) || up || down;
+  int rs = RS_NONE;
+  if (up) rs = cfg_.fir ? RS_FIR_UP : RS_NAIVE_UP;
+  if (down) rs = cfg_.fir ? RS_FIR_DOWN : RS_NAIVE_DOWN;
+  const float out_scale = cfg_.skip_rescale ? (float)(1.0 / std::sqrt(2.0)) : 1.f;
+
+  auto gn0 = gn_params(s, Cin);
+  T16 a1 = new16(Cin, Ho, Wo);
+  T16 x16; x16.p = nullptr;
+  if (need_sc) x16 = new16(Cin, Ho, Wo);
+  add_norm(in1, in2, gn0.first, gn0.second, true, rs, &a1, need_sc ? &x16 : nullptr, s.prefix + "gn0");
+
+  // conv1 (Conv_0) + Dense_0(act(temb))
+  Scope c0 = s.child("Conv");
+  const auto* k0 = param(c0, "kernel", {3, 3, Cin, out_ch}, 0, 1.f);
+  const auto* b0 = param(c0, "bias", {out_ch}, 1, 1.f);
+  const float* bias1 = nullptr;
+  int temb_off = -1;
+  if (cfg_.conditional) {
+    Scope d0 = s.child("Dense");
+    const auto* dw = param(d0, "kernel", {temb_dim_, out_ch}, 0, 1.f);
+    const auto* db = param(d0, "bias", {out_ch}, 1, 1.f);
+    if (!dry_ && (!dw || !db || !b0)) return T32{nullptr, 0, 0, 0, 0};
+    temb_off = add_temb_proj(dw, db, b0, out_ch);
+  } else {
+    if (dry_) w_alloc(out_ch * 4);
+    else { if (!b0) return T32{nullptr, 0, 0, 0, 0}; bias1 = upload_f32(*b0); }
+  }
+  __half* w1 = nullptr;
+  {
+    const size_t n = (size_t)out_ch * 9 * Cin;
+    if (dry_) w1 = (__half*)w_alloc(n * 2);
+    else {
+      if (!k0) return T32{nullptr, 0, 0, 0, 0};
+      std::vector<__half> pk(n);
+      pack_conv(*k0, 9, Cin, out_ch, pk, 9 * Cin, 0);
+      w1 = upload_f16(pk);
+    }
+  }
+  T32 h2 = new32(out_ch, Ho, Wo);
+  {
+    Op op; op.kind = OP_GEMM; op.tag = s.prefix + "conv1";
+    op.gemm = make_gemm(max_batch_, Ho, Wo);
+    GemmOp& g = op.gemm;
+    g.nseg = 1;
+    g.seg[0] = {a1.p, Cin, 0, Cin, 9};
+    g.w = w1; g.N = out_ch; g.w_ld = 9 * Cin;
+    g.bias = bias1;
+    g.bias2 = temb_off >= 0 ? temb_cur_ + temb_off : nullptr;
+    g.out32 = h2.p; g.ldo = out_ch;
+    ops_.push_back(op);
+  }
+  rel(a1);
+
+  auto gn1 = gn_params(s, out_ch);
+  T16 a2 = new16(out_ch, Ho, Wo);
+  add_norm(h2, nullptr, gn1.first, gn1.second, true, RS_NONE, &a2, nullptr, s.prefix + "gn1");
+  rel(h2);
+
+  Scope c1 = s.child("Conv");
+  const auto* k1 = param(c1, "kernel", {3, 3, out_ch, out_ch}, 0, scale0(0.f));   // init_scale = config.model.init_scale
+  const auto* b1 = param(c1, "bias", {out_ch}, 1, 1.f);
+  const std::vector<float>* k2 = nullptr;
+  const std::vector<float>* b2 = nullptr;
+  if (need_sc) {
+    Scope c2 = s.child("Conv");
+    k2 = param(c2, "kernel", {1, 1, Cin, out_ch}, 0, 1.f);
+    b2 = param(c2, "bias", {out_ch}, 1, 1.f);
+  }
+  const int ktot = 9 * out_ch + (need_sc ? Cin : 0);
+  __half* w2 = nullptr;
+  const float* bias2v = nullptr;
+  if (dry_) { w2 = (__half*)w_alloc((size_t)out_ch * ktot * 2); w_alloc(out_ch * 4); }
+  else {
+    if (!k1 || !b1 || (need_sc && (!k2 || !b2))) return T32{nullptr, 0, 0, 0, 0};
+    std::vector<__half> pk((size_t)out_ch * ktot);
+    pack_conv(*k1, 9, out_ch, out_ch, pk, ktot, 0);
+    std::vector<float> bsum(*b1);
+    if (need_sc) {
+      pack_conv(*k2, 1, Cin, out_ch, pk, ktot, 9 * out_ch);
+      for (int i = 0; i < out_ch; ++i) bsum[i] += (*b2)[i];
+    }
+    w2 = upload_f16(pk);
+    bias2v = upload_f32(bsum);
+  }
+  T32 out = new32(out_ch, Ho, Wo);
+  {
+    Op op; op.kind = OP_GEMM; op.tag = s.prefix + "conv2";
+    op.gemm = make_gemm(max_batch_, Ho, Wo);
+    GemmOp& g = op.gemm;
+    g.nseg = need_sc ? 2 : 1;
+    g.seg[0] = {a2.p, out_ch, 0, out_ch, 9};
+    if (need_sc) g.seg[1] = {x16.p, Cin, 0, Cin, 1};
+    g.w = w2; g.N = out_ch; g.w_ld = ktot;
+    g.bias = bias2v;
+    g.residual = need_sc ? nullptr : in1.p;
+    g.scale = out_scale;
+    g.out32 = out.p; g.ldo = out_ch;
+    ops_.push_back(op);
+  }
+  rel(a2);
+  if (need_sc) rel(x16);
+  return out;
+}
+
+// ---- AttnBlockpp (layerspp.py:61-83) ------------------------------------------------------------------------
+UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
+  Scope s = top.child("AttnBlockpp");
+  const int C = x.C, H = x.H, W = x.W, T = H * W;
+  const float out_scale = cfg_.skip_rescale ? (float)(1.0 / std::sqrt(2.0)) : 1.f;
+  auto gn = gn_params(s, C);
+  T16 h16 = new16(C, H, W);
+  add_norm(x, nullptr, gn.first, gn.second, false, RS_NONE, &h16, nullptr, s.prefix + "gn");
+
+  const std::vector<float>* nw[4];
+  const std::vector<float>* nb[4];
+  for (int i = 0; i < 4; ++i) {
+    Scope n = s.child("NIN");
+    nw[i] = param(n, "W", {C, C}, 0, i == 3 ? scale0(0.f) : 0.1f);
+    nb[i] = param(n, "b", {C}, 1, 1.f);
+  }
+  __half *wqkv = nullptr, *w3 = nullptr;
+  const float *bqkv = nullptr, *b3 = nullptr;
+  if (dry_) {
+    wqkv = (__half*)w_alloc((size_t)3 * C * C * 2); w_alloc(3 * C * 4);
+    w3 = (__half*)w_alloc((size_t)C * C * 2); w_alloc(C * 4);
+  } else {
+    for (int i = 0; i < 4; ++i) if (!nw[i] || !nb[i]) return T32{nullptr, 0, 0, 0, 0};
+    std::vector<__half> pk((size_t)3 * C * C);
+    std::vector<float> bb(3 * C);
+    for (int i = 0; i < 3; ++i) {
+      for (int k = 0; k < C; ++k)
+        for (int n = 0; n < C; ++n) pk[((size_t)i * C + n) * C + k] = __float2half_rn((*nw[i])[(size_t)k * C + n]);
+      for (int n = 0; n < C; ++n) bb[i * C + n] = (*nb[i])[n];
+    }
+    wqkv = upload_f16(pk);
+    bqkv = upload_f32(bb);
+    std::vector<__half> p3((size_t)C * C);
+    for (int k = 0; k < C; ++k)
+      for (int n = 0; n < C; ++n) p3[(size_t)n * C + k] = __float2half_rn((*nw[3])[(size_t)k * C + n]);
+    w3 = upload_f16(p3);
+    b3 = upload_f32(*nb[3]);
+  }
+  T16 qkv = new16(3 * C, H, W);
+  {
+    Op op; op.kind = OP_GEMM; op.tag = s.prefix + "qkv";
+    op.gemm = make_gemm(max_batch_, H, W);
+    GemmOp& g = op.gemm;
+    g.nseg = 1; g.seg[0] = {h16.p, C, 0, C, 1};
+    g.w = wqkv; g.N = 3 * C; g.w_ld = C; g.bias = bqkv;
+    g.out16 = qkv.p; g.ldo = 3 * C;
+    ops_.push_back(op);
+  }
+  rel(h16);
+  T16 o16 = new16(C, H, W);
+  const float sm_scale = 1.0f / std::sqrt((float)C);
+  if (T == 256 && C % 64 == 0) {
+    T16 p16 = new16(T, H, W);
+    T16 vT; vT.C = T; vT.H = C; vT.W = 1; vT.bytes = (size_t)max_batch_ * C * T * 2; vT.p = (__half*)a_alloc(vT.bytes);
+    float* rowinv = (float*)a_alloc((size_t)max_batch_ * T * 4);
+    {
+      Op op; op.kind = OP_GEMM; op.tag = s.prefix + "qk_softmax";
+      op.gemm = make_gemm(max_batch_, H, W);
+      GemmOp& g = op.gemm;
+      g.nseg = 1; g.seg[0] = {qkv.p, 3 * C, 0, C, 1};
+      g.w = qkv.p; g.N = T; g.w_ld = 3 * C; g.w_koff = C;
+      g.w_batch_stride = (long long)T * 3 * C; g.w_rows_per_batch = T;
+      g.scale = sm_scale; g.epi = EPI_SOFTMAX;
+      g.out16 = p16.p; g.row_out = rowinv; g.ldo = T;
+      ops_.push_back(op);
+    }
+    {
+      Op op; op.kind = OP_TRANSPOSE_V; op.tag = s.prefix + "vT";
+      op.h_in = qkv.p; op.h_out = vT.p; op.T = T; op.cin = C; op.ld = 3 * C; op.voff = 2 * C;
+      ops_.push_back(op);
+    }
+    {
+      Op op; op.kind = OP_GEMM; op.tag = s.prefix + "pv";
+      op.gemm = make_gemm(max_batch_, H, W);
+      GemmOp& g = op.gemm;
+      g.nseg = 1; g.seg[0] = {p16.p, T, 0, T, 1};
+      g.w = vT.p; g.N = C; g.w_ld = T;
+      g.w_batch_stride = (long long)C * T; g.w_rows_per_batch = C;
+      g.rowscale = rowinv;
+      g.out16 = o16.p; g.ldo = C;
+      ops_.push_back(op);
+    }
+    rel(p16); rel(vT);
+    a_free(rowinv, (size_t)max_batch_ * T * 4);
+  } else if (T <= 64) {
+    Op op; op.kind = OP_SMALL_ATTN; op.tag = s.prefix + "attn_small";
+    op.h_in = qkv.p; op.h_out = o16.p; op.T = T; op.cin = C; op.scale = sm_scale;
+    ops_.push_back(op);
+  } else {
+    err_ = "attention over " + std::to_string(T) + " tokens is not supported (16..64 or 256)";
+    return T32{nullptr, 0, 0, 0, 0};
+  }
+  rel(qkv);
+  T32 out = new32(C, H, W);
+  {
+    Op op; op.kind = OP_GEMM; op.tag = s.prefix + "proj";
+    op.gemm = make_gemm(max_batch_, H, W);
+    GemmOp& g = op.gemm;
+    g.nseg = 1; g.seg[0] = {o16.p, C, 0, C, 1};
+    g.w = w3; g.N = C; g.w_ld = C; g.bias = b3;
+    g.residual = x.p; g.scale = out_scale;
+    g.out32 = out.p; g.ldo = C;
+    ops_.push_back(op);
+  }
+  rel(o16);
+  return out;
+}
+
+// ---- NCSNpp.__call__ (ncsnpp.py:41-243) ------------------------------------------------------------------------
+int UNet::walk() {
+  ops_.clear();
+  free_.clear();
+  arena_top_ = 0;
+  weight_top_ = 0;
+  temb_total_ = 0;
+  const gddim_model_cfg& m = cfg_;
+  if (m.n_levels < 1 || m.n_levels > 8) return fail("n_levels out of range");
+  if (!m.centered) return fail("config.data.centered = False is not supported");
+  if (m.nf % 64 != 0) return fail("nf must be a multiple of 64 for the tcgen05 GEMM path (got " + std::to_string(m.nf) + ")");
+  const int nf = m.nf, S = m.image_size, Cnet = net_channels();
+  Scope top;
+  temb_dim_ = nf * 4;
+
+  // time embedding parameters (ncsnpp.py:68-91)
+  if (m.embedding_type == 0) {
+    Scope f = top.child("GaussianFourierProjection");
+    const auto* w = param(f, "W", {nf}, 3, 16.f);
+    emb_in_dim_ = 2 * nf;
+    if (!dry_) { if (!w) return -1; fourier_w_ = *w; }
+  } else {
+    emb_in_dim_ = nf;
+  }
+  if (m.conditional) {
+    Scope d0 = top.child("Dense");
+    const auto* w0 = param(d0, "kernel", {emb_in_dim_, temb_dim_}, 0, 1.f);
+    const auto* b0 = param(d0, "bias", {temb_dim_}, 1, 1.f);
+    Scope d1 = top.child("Dense");
+    const auto* w1 = param(d1, "kernel", {temb_dim_, temb_dim_}, 0, 1.f);
+    const auto* b1 = param(d1, "bias", {temb_dim_}, 1, 1.f);
+    if (dry_) {
+      w_alloc((size_t)emb_in_dim_ * temb_dim_ * 4); w_alloc(temb_dim_ * 4);
+      w_alloc((size_t)temb_dim_ * temb_dim_ * 4); w_alloc(temb_dim_ * 4);
+    } else {
+      if (!w0 || !b0 || !w1 || !b1) return -1;
+      d_dense0_w_ = upload_f32(*w0); d_dense0_b_ = upload_f32(*b0);
+      d_dense1_w_ = upload_f32(*w1); d_dense1_b_ = upload_f32(*b1);
+    }
+  }
+  // small persistent buffers live at the bottom of the weight arena
+  d_temb0_ = (float*)w_alloc(emb_in_dim_ * 4);
+  d_temb1_ = (float*)w_alloc(temb_dim_ * 4);
+  d_temb2_ = (float*)w_alloc(temb_dim_ * 4);
+  gn_partial_ = (float*)w_alloc((size_t)max_batch_ * 32 * 32 * 2 * 4);
+  // temb_cur_: capacity known from the dry pass (first pass: generous upper bound is unnecessary -- the
+  // pointer is only used as an address; its size is fixed in finalize()).
+  temb_cur_ = (float*)w_alloc((size_t)(dry_ ? 1 : proj_b_host_.size()) * 4 + 16);
+
+  // stem (ncsnpp.py:146)
+  Scope stem = top.child("Conv");
+  const auto* sk = param(stem, "kernel", {3, 3, Cnet, nf}, 0, 1.f);
+  const auto* sb = param(stem, "bias", {nf}, 1, 1.f);
+  std::vector<T32> hs;
+  {
+    T32 h0 = new32(nf, S, S);
+    Op op; op.kind = OP_STEM; op.tag = "stem";
+    op.in_is_external = true; op.f_out = h0.p; op.H = S; op.W = S; op.cin = Cnet; op.cout = nf;
+    if (dry_) { w_alloc((size_t)9 * Cnet * nf * 4); w_alloc(nf * 4); }
+    else { if (!sk || !sb) return -1; op.w = upload_f32(*sk); op.bias = upload_f32(*sb); }
+    ops_.push_back(op);
+    hs.push_back(h0);
+  }
+  bool has_pyr = m.progressive_input == 1;
+  T32 pyr; pyr.p = nullptr; pyr.C = Cnet; pyr.H = S; pyr.W = S;     // p == nullptr & first: external x
+  bool pyr_external = true;
+
+  auto in_attn = [&](int res) { for (int i = 0; i < m.n_attn; ++i) if (m.attn_resolutions[i] == res) return true; return false; };
+
+  for (int lvl = 0; lvl < m.n_levels; ++lvl) {
+    for (int blk = 0; blk < m.num_res_blocks; ++blk) {
+      T32 h = resblock(top, hs.back(), nullptr, nf * m.ch_mult[lvl], false, false);
+      if (!err_.empty()) return -1;
+      if (in_attn(h.H)) {
+        T32 h2 = attnblock(top, h);
+        if (!err_.empty()) return -1;
+        rel(h);
+        h = h2;
+      }
+      hs.push_back(h);
+    }
+    if (lvl != m.n_levels - 1) {
+      T32 h = resblock(top, hs.back(), nullptr, 0, false, true);
+      if (!err_.empty()) return -1;
+      if (has_pyr) {
+        if (!m.fir) return fail("progressive_input='residual' without FIR is used by no shipped config");
+        // Downsample(fir, with_conv) = conv_downsample_2d (layerspp.py:115-143; up_or_down_sampling.py:168-209)
+        Scope ds = top.child("Downsample");
+        Scope c2d = ds.child("Conv2d");
+        const int cin = pyr.C, cout = h.C;
+        const auto* pw = param(c2d, "weight", {3, 3, cin, cout}, 0, 1.f);
+        const auto* pb = param(c2d, "bias", {cout}, 1, 1.f);
+        const int kpad = (int)align_up(9 * cin, 64);
+        T16 a16 = new16(kpad, pyr.H / 2, pyr.W / 2);
+        {
+          Op op; op.kind = OP_IM2COL; op.tag = ds.prefix + "im2col";
+          op.in_is_external = pyr_external; op.f_in = pyr.p; op.h_out = a16.p;
+          op.H = pyr.H; op.W = pyr.W; op.cin = cin; op.kpad = kpad; op.use_fir = 1;
+          ops_.push_back(op);
+        }
+        __half* wp = nullptr; const float* bp = nullptr;
+        if (dry_) { wp = (__half*)w_alloc((size_t)cout * kpad * 2); w_alloc(cout * 4); }
+        else {
+          if (!pw || !pb) return -1;
+          std::vector<__half> pk((size_t)cout * kpad, __float2half(0.f));
+          pack_conv(*pw, 9, cin, cout, pk, kpad, 0);
+          wp = upload_f16(pk); bp = upload_f32(*pb);
+        }
+        T32 np = new32(cout, h.H, h.W);
+        {
+          Op op; op.kind = OP_GEMM; op.tag = ds.prefix + "conv";
+          op.gemm = make_gemm(max_batch_, h.H, h.W);
+          GemmOp& g = op.gemm;
+          g.nseg = 1; g.seg[0] = {a16.p, kpad, 0, kpad, 1};
+          g.w = wp; g.N = cout; g.w_ld = kpad; g.bias = bp;
+          g.residual = h.p; g.scale = m.skip_rescale ? (float)(1.0 / std::sqrt(2.0)) : 1.f;
+          g.out32 = np.p; g.ldo = cout;
+          ops_.push_back(op);
+        }
+        rel(a16);
+        rel(h);
+        h = np;
+        pyr = np;            // owned by hs from now on
+        pyr_external = false;
+      }
+      hs.push_back(h);
+    }
+  }
+
+  // middle (ncsnpp.py:175-178)
+  T32 h;
+  {
+    T32 h1 = resblock(top, hs.back(), nullptr, 0, false, false);
+    if (!err_.empty()) return -1;
+    T32 h2 = attnblock(top, h1);
+    if (!err_.empty()) return -1;
+    rel(h1);
+    h = resblock(top, h2, nullptr, 0, false, false);
+    if (!err_.empty()) return -1;
+    rel(h2);
+  }
+
+  // up path (ncsnpp.py:183-229)
+  for (int lvl = m.n_levels - 1; lvl >= 0; --lvl) {
+    for (int blk = 0; blk < m.num_res_blocks + 1; ++blk) {
+      T32 skip = hs.back();
+      hs.pop_back();
+      T32 hn = resblock(top, h, &skip, nf * m.ch_mult[lvl], false, false);
+      if (!err_.empty()) return -1;
+      rel(h);
+      rel(skip);
+      h = hn;
+    }
+    if (in_attn(h.H)) {
+      T32 h2 = attnblock(top, h);
+      if (!err_.empty()) return -1;
+      rel(h);
+      h = h2;
+    }
+    if (lvl != 0) {
+      T32 hu = resblock(top, h, nullptr, 0, true, false);
+      if (!err_.empty()) return -1;
+      rel(h);
+      h = hu;
+    }
+  }
+  if (!hs.empty()) return fail("internal: skip stack not empty");
+
+  // head (ncsnpp.py:236-237)
+  {
+    auto gn = gn_params(top, h.C);
+    T16 a = new16(h.C, h.H, h.W);
+    add_norm(h, nullptr, gn.first, gn.second, true, RS_NONE, &a, nullptr, "head_gn");
+    rel(h);
+    Scope hc = top.child("Conv");
+    const auto* hk = param(hc, "kernel", {3, 3, a.C, Cnet}, 0, scale0(0.f));
+    const auto* hb = param(hc, "bias", {Cnet}, 1, 1.f);
+    Op op; op.kind = OP_HEAD; op.tag = "head";
+    op.h_in = a.p; op.out_is_external = true; op.H = a.H; op.W = a.W; op.cin = a.C; op.cout = Cnet;
+    if (dry_) { w_alloc((size_t)9 * a.C * Cnet * 4); w_alloc(Cnet * 4); }
+    else { if (!hk || !hb) return -1; op.w = upload_f32(*hk); op.bias = upload_f32(*hb); }
+    ops_.push_back(op);
+    rel(a);
+  }
+  if (m.conditional) {
+    if (dry_) { w_alloc((size_t)temb_dim_ * temb_total_ * 4); w_alloc((size_t)temb_total_ * 4); }
+    else { d_proj_w_ = upload_f32(proj_w_host_); d_proj_b_ = upload_f32(proj_b_host_); }
+  }
+  return 0;
+}
+
+int UNet::finalize() {
+  if (!err_.empty()) return -1;
+  if (finalized_) return 0;
+  for (const auto& sp : specs_)
+    if (!host_params_.count(sp.name)) return fail("gddim_ctx_finalize: parameter not set: " + sp.name);
+  const size_t wbytes = weight_top_ + (size_t)temb_total_ * 4 + 4096;
+  const size_t abytes = arena_peak_ + 4096;
+  const int total = temb_total_;
+  wts_ = nullptr; arena_ = nullptr;
+  dry_ = false;
+  if (cudaMalloc(&wts_, wbytes) != cudaSuccess) { wts_ = nullptr; return fail("cudaMalloc(weights) failed"); }
+  if (cudaMalloc(&arena_, abytes) != cudaSuccess) { arena_ = nullptr; return fail("cudaMalloc(workspace) failed"); }
+  cudaMemset(wts_, 0, wbytes);
+  weight_bytes_ = wbytes;
+  arena_bytes_ = abytes;
+  proj_w_host_.assign((size_t)temb_dim_ * total, 0.f);
+  proj_b_host_.assign(total, 0.f);
+  dry_ = false;
+  if (walk() != 0) return -1;
+  if (arena_top_ > arena_peak_) return fail("internal: workspace plan mismatch");
+  host_params_.clear();
+  proj_w_host_.clear(); proj_w_host_.shrink_to_fit();
+  for (auto& op : ops_) {
+    if (op.kind == OP_GEMM) {
+      if (gemm_prepare(&op.gemm, 0) != 0) return fail(std::string("gemm_prepare(") + op.tag + "): " + gemm_last_error());
+    }
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail("device error during finalize");
+  finalized_ = true;
+  return 0;
+}
+
+int UNet::time_projections(double t, float* dst_dev, cudaStream_t st) {
+  if (!finalized_) return fail("context not finalized");
+  if (!cfg_.conditional) return 0;
+  const int nf = cfg_.nf;
+  std::vector<float> e(emb_in_dim_);
+  const float labels = (float)(999.0 * t);     // models/utils.py:172 (fp32 in the reference)
+  if (cfg_.embedding_type == 0) {
+    // layerspp.py:33-43 on log(labels) (ncsnpp.py:71-77): fp32 argument, then sin/cos
+    const float lg = (float)std::log((double)labels);
+    for (int i = 0; i < nf; ++i) {
+      const float arg = lg * fourier_w_[i] * 2.0f * (float)M_PI;
+      e[i] = (float)std::sin((double)arg);
+      e[nf + i] = (float)std::cos((double)arg);
+    }
+  } else {
+    // layers.py:450-464 get_timestep_embedding(labels, nf)
+    const int half = nf / 2;
+    const float k = (float)(std::log(10000.0) / (double)(half - 1));
+    for (int i = 0; i < half; ++i) {
+      const float f = (float)std::exp((double)((float)i * -k));
+      const float arg = labels * f;
+      e[i] = (float)std::sin((double)arg);
+      e[half + i] = (float)std::cos((double)arg);
+    }
+  }
+  if (cudaMemcpyAsync(d_temb0_, e.data(), e.size() * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return fail("temb upload failed");
+  if (dense_launch(d_temb0_, d_dense0_w_, d_dense0_b_, d_temb1_, 1, emb_in_dim_, temb_dim_, 0, st)) return fail("dense0");
+  if (dense_launch(d_temb1_, d_dense1_w_, d_dense1_b_, d_temb2_, 1, temb_dim_, temb_dim_, 1, st)) return fail("dense1");
+  if (dense_launch(d_temb2_, d_proj_w_, d_proj_b_, dst_dev, 1, temb_dim_, temb_total_, 1, st)) return fail("dense proj");
+  launches_ += 3;
+  return 0;
+}
+
+int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st) {
+  if (!finalized_) return fail("context not finalized");
+  if (batch < 1 || batch > max_batch_) return fail("batch exceeds max_batch");
+  for (auto& op : ops_) {
+    int rc = 0;
+    switch (op.kind) {
+      case OP_STEM:
+        rc = stem_conv_launch(x_dev, op.w, op.bias, op.f_out, batch, op.H, op.W, op.cin, op.cout, st);
+        launches_ += 1;
+        break;
+      case OP_NORM: {
+        NormOp n = op.norm;
+        n.B = batch;
+        rc = norm_launch(&n, st);
+        launches_ += n.dst16 ? 2 : 1;
+        break;
+      }
+      case OP_GEMM: {
+        GemmOp g = op.gemm;
+        g.B = batch;
+        g.m_tiles = (int)(((long long)batch * g.H * g.W + 127) / 128);
+        rc = gemm_launch(&g, gemm_impl, st);
+        if (rc) return fail(std::string("gemm_launch(") + op.tag + "): " + gemm_last_error());
+        launches_ += (gemm_impl == 1 && g.epi == EPI_SOFTMAX) ? 2 : 1;
+        break;
+      }
+      case OP_HEAD:
+        rc = head_conv_launch(op.h_in, op.w, op.bias, out_dev, batch, op.H, op.W, op.cin, op.cout, st);
+        launches_ += 1;
+        break;
+      case OP_IM2COL:
+        rc = im2col_fir_down_launch(op.in_is_external ? x_dev : op.f_in, op.h_out, batch, op.H, op.W, op.cin, op.kpad,
+                                    op.use_fir, st);
+        launches_ += 1;
+        break;
+      case OP_TRANSPOSE_V:
+        rc = transpose_v_launch(op.h_in, op.h_out, batch, op.T, op.cin, op.ld, op.voff, st);
+        launches_ += 1;
+        break;
+      case OP_SMALL_ATTN:
+        rc = small_attn_launch(op.h_in, op.h_out, batch, op.T, op.cin, op.scale, st);
+        launches_ += 1;
+        break;
+    }
+    if (rc) return fail("launch failed in op " + op.tag + " (rc=" + std::to_string(rc) + ")");
+  }
+  return 0;
+}
+
+}  // namespace gddim

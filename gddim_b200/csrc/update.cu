@@ -1,0 +1,344 @@
+// K5 / K6: the gDDIM / DEIS linear-algebra update and the blur-diffusion DCT-space update.
+// HBM-bound elementwise work, no tensor-core path: coalesced float4 traffic, one pass.
+//
+// Reference semantics:
+//   cld_jax/deis.py:141-151           multistep_ab_step   u' = Psi u + sum_j C_j eps_j  (2x2 on the (x,v) pair)
+//   cld_jax/sampling.py:30-39         denoising step (same algebraic form with A = I - eps F, C = -eps GG R^-T)
+//   cld_jax/models/utils.py:153,158   '(d g) <-> (g d)' relayout, :174-176 mixed_score
+//   blur_jax/sampling.py:60-75        order-0 DDIM update in DCT space
+//   blur_jax/blur.py:11-107           orthonormal DCT-II / DCT-III (here: dense 32x32 transforms in smem)
+//   blur_jax/multistep.py:94-98       scalar-coefficient ab_step
+#include <cmath>
+#include <cstdio>
+
+#include "kernels.h"
+
+namespace gddim {
+
+static int grid_for(long long n, int per_block, int cap = 148 * 16) {
+  long long g = (n + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+// ---- CLD step in net layout --------------------------------------------------------------------------
+struct CldStepDev {
+  const float* u; float* u_out;
+  const float* eps[6];
+  int n_eps;
+  float coef[7][4];
+  int mixed; float mixm[4];
+  float* eps_store;
+  long long n_pix; int C;
+};
+
+// Specialisation for C = 3 (pixel = 6 floats): a thread owns 2 pixels = 3 float4 per array.
+__global__ void __launch_bounds__(256) cld_step_c3_kernel(const CldStepDev p) {
+  const long long npair = p.n_pix / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair;
+       i += (long long)gridDim.x * blockDim.x) {
+    float u[12], acc[12];
+    {
+      const float4* q = reinterpret_cast<const float4*>(p.u) + i * 3;
+      const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+      u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = b.x; u[5] = b.y; u[6] = b.z; u[7] = b.w;
+      u[8] = c.x; u[9] = c.y; u[10] = c.z; u[11] = c.w;
+    }
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float x = u[px * 6 + d], v = u[px * 6 + 3 + d];
+        acc[px * 6 + d] = p.coef[0][0] * x + p.coef[0][1] * v;
+        acc[px * 6 + 3 + d] = p.coef[0][2] * x + p.coef[0][3] * v;
+      }
+    for (int j = 0; j < p.n_eps; ++j) {
+      float e[12];
+      const float4* q = reinterpret_cast<const float4*>(p.eps[j]) + i * 3;
+      const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+      e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
+      e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w;
+      if (j == 0 && p.mixed) {
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const float x = u[px * 6 + d], v = u[px * 6 + 3 + d];
+            e[px * 6 + d] += p.mixm[0] * x + p.mixm[1] * v;
+            e[px * 6 + 3 + d] += p.mixm[2] * x + p.mixm[3] * v;
+          }
+        float4* s = reinterpret_cast<float4*>(p.eps_store) + i * 3;
+        s[0] = make_float4(e[0], e[1], e[2], e[3]);
+        s[1] = make_float4(e[4], e[5], e[6], e[7]);
+        s[2] = make_float4(e[8], e[9], e[10], e[11]);
+      }
+      const float c00 = p.coef[1 + j][0], c01 = p.coef[1 + j][1], c10 = p.coef[1 + j][2], c11 = p.coef[1 + j][3];
+#pragma unroll
+      for (int px = 0; px < 2; ++px)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float ex = e[px * 6 + d], ev = e[px * 6 + 3 + d];
+          acc[px * 6 + d] += c00 * ex + c01 * ev;
+          acc[px * 6 + 3 + d] += c10 * ex + c11 * ev;
+        }
+    }
+    float4* o = reinterpret_cast<float4*>(p.u_out) + i * 3;
+    o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    o[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+  }
+}
+
+// Generic channel count: one thread per (pixel, d) pair.
+__global__ void __launch_bounds__(256) cld_step_generic_kernel(const CldStepDev p) {
+  const long long n = p.n_pix * p.C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / p.C;
+    const int d = int(i % p.C);
+    const long long ix = pix * 2 * p.C + d, iv = ix + p.C;
+    const float x = p.u[ix], v = p.u[iv];
+    float ax = p.coef[0][0] * x + p.coef[0][1] * v;
+    float av = p.coef[0][2] * x + p.coef[0][3] * v;
+    for (int j = 0; j < p.n_eps; ++j) {
+      float ex = p.eps[j][ix], ev = p.eps[j][iv];
+      if (j == 0 && p.mixed) {
+        ex += p.mixm[0] * x + p.mixm[1] * v;
+        ev += p.mixm[2] * x + p.mixm[3] * v;
+        p.eps_store[ix] = ex;
+        p.eps_store[iv] = ev;
+      }
+      ax += p.coef[1 + j][0] * ex + p.coef[1 + j][1] * ev;
+      av += p.coef[1 + j][2] * ex + p.coef[1 + j][3] * ev;
+    }
+    p.u_out[ix] = ax;
+    p.u_out[iv] = av;
+  }
+}
+
+int cld_step_launch(const CldStepArgs* a, cudaStream_t st) {
+  CldStepDev d;
+  d.u = a->u; d.u_out = a->u_out;
+  for (int j = 0; j < 6; ++j) d.eps[j] = a->eps[j];
+  d.n_eps = a->n_eps;
+  for (int j = 0; j < 7; ++j) for (int k = 0; k < 4; ++k) d.coef[j][k] = a->coef[j][k];
+  d.mixed = a->mixed;
+  for (int k = 0; k < 4; ++k) d.mixm[k] = a->mixm[k];
+  d.eps_store = a->eps_store; d.n_pix = a->n_pix; d.C = a->C;
+  if (a->n_eps < 0 || a->n_eps > 6) return -1;
+  if (a->C == 3 && a->n_pix % 2 == 0) {
+    cld_step_c3_kernel<<<grid_for(a->n_pix / 2, 256), 256, 0, st>>>(d);
+  } else {
+    cld_step_generic_kernel<<<grid_for(a->n_pix * a->C, 256), 256, 0, st>>>(d);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+__global__ void cld_split_kernel(const float* __restrict__ u, float* __restrict__ x, float* __restrict__ v,
+                                 long long n_pix, int C, float mul, float add) {
+  const long long n = n_pix * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / C;
+    const int d = int(i % C);
+    const float xv = u[pix * 2 * C + d], vv = u[pix * 2 * C + C + d];
+    x[i] = xv * mul + add;
+    v[i] = vv;
+  }
+}
+int cld_split_launch(const float* u, float* x, float* v, long long n_pix, int C, float mul, float add, cudaStream_t st) {
+  cld_split_kernel<<<grid_for(n_pix * C, 256), 256, 0, st>>>(u, x, v, n_pix, C, mul, add);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// reference layout [pix, d, g] <-> net layout [pix, g*C + d]
+__global__ void relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n_pix, int C,
+                                int to_net) {
+  const long long n = n_pix * 2 * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / (2 * C);
+    const int k = int(i % (2 * C));
+    if (to_net) {
+      const int g = k / C, d = k % C;                 // destination index k = g*C + d
+      dst[i] = src[pix * 2 * C + d * 2 + g];
+    } else {
+      const int d = k / 2, g = k % 2;                 // destination index k = d*2 + g
+      dst[i] = src[pix * 2 * C + g * C + d];
+    }
+  }
+}
+int relayout_launch(const float* src, float* dst, long long n_pix, int C, int to_net, cudaStream_t st) {
+  relayout_kernel<<<grid_for(n_pix * 2 * C, 256), 256, 0, st>>>(src, dst, n_pix, C, to_net);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// deis.multistep_ab_step on reference-layout arrays: pairs (x, v) are adjacent (last axis of size 2).
+__global__ void __launch_bounds__(256) ab_step_ref_kernel(const float* __restrict__ x, const float* __restrict__ coef,
+                                                         const float* __restrict__ new_eps,
+                                                         const float* __restrict__ hist, float* __restrict__ x_out,
+                                                         float* __restrict__ hist_out, int order, long long n_pairs) {
+  __shared__ float sc[8 * 4];
+  if (threadIdx.x < (order + 3) * 4) sc[threadIdx.x] = coef[threadIdx.x];
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float2 u = reinterpret_cast<const float2*>(x)[i];
+    float ax = sc[0] * u.x + sc[1] * u.y, av = sc[2] * u.x + sc[3] * u.y;
+    const float2 e0 = reinterpret_cast<const float2*>(new_eps)[i];
+    ax += sc[4] * e0.x + sc[5] * e0.y;
+    av += sc[6] * e0.x + sc[7] * e0.y;
+    reinterpret_cast<float2*>(hist_out)[i] = e0;                       // full[:-1][0] = new_eps
+    for (int j = 0; j <= order; ++j) {
+      const float2 e = reinterpret_cast<const float2*>(hist)[(long long)j * n_pairs + i];
+      const float* c = sc + (2 + j) * 4;
+      ax += c[0] * e.x + c[1] * e.y;
+      av += c[2] * e.x + c[3] * e.y;
+      if (j < order) reinterpret_cast<float2*>(hist_out)[(long long)(j + 1) * n_pairs + i] = e;
+    }
+    reinterpret_cast<float2*>(x_out)[i] = make_float2(ax, av);
+  }
+}
+int ab_step_ref_layout_launch(const float* x, const float* coef, const float* new_eps, const float* hist, float* x_out,
+                              float* hist_out, int order, long long n_pairs, cudaStream_t st) {
+  if (order < 0 || order > 5) return -1;
+  ab_step_ref_kernel<<<grid_for(n_pairs, 256), 256, 0, st>>>(x, coef, new_eps, hist, x_out, hist_out, order, n_pairs);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// ---- DCT on 32x32 planes -------------------------------------------------------------------------------
+__constant__ float c_dct[32 * 32];   // D[k][n] = s_k cos(pi (2n+1) k / 64), orthonormal DCT-II matrix
+static bool g_dct_ready = false;
+
+static int ensure_dct_matrix() {
+  if (g_dct_ready) return 0;
+  float h[32 * 32];
+  for (int k = 0; k < 32; ++k)
+    for (int n = 0; n < 32; ++n) {
+      const double s = (k == 0) ? std::sqrt(1.0 / 32.0) : std::sqrt(2.0 / 32.0);
+      h[k * 32 + n] = (float)(s * std::cos(M_PI * (2.0 * n + 1.0) * k / 64.0));
+    }
+  if (cudaMemcpyToSymbol(c_dct, h, sizeof(h)) != cudaSuccess) return -1;
+  g_dct_ready = true;
+  return 0;
+}
+
+// in-place separable transform of a [32][32][C] image held in shared memory.
+// fwd:  Y = D X D^T   (over h then w);  inverse: X = D^T Y D
+__device__ void dct_planes(float* img, float* tmp, const float* sD, int C, int fwd) {
+  const int n = 32 * 32 * C;
+  // pass over H: tmp[k][w][c] = sum_h M[k][h] img[h][w][c]
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % C, w = (i / C) % 32, k = i / (C * 32);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int h = 0; h < 32; ++h) {
+      const float m = fwd ? sD[k * 32 + h] : sD[h * 32 + k];
+      acc += m * img[(h * 32 + w) * C + c];
+    }
+    tmp[i] = acc;
+  }
+  __syncthreads();
+  // pass over W: img[k][l][c] = sum_w M[l][w] tmp[k][w][c]
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % C, l = (i / C) % 32, k = i / (C * 32);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) {
+      const float m = fwd ? sD[l * 32 + w] : sD[w * 32 + l];
+      acc += m * tmp[(k * 32 + w) * C + c];
+    }
+    img[i] = acc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) dct32_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int fwd) {
+  extern __shared__ float sm[];
+  float* sD = sm;
+  float* img = sm + 1024;
+  float* tmp = img + 1024 * C;
+  const int n = 1024 * C;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sD[i] = c_dct[i];
+  const float* src = in + (long long)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) img[i] = src[i];
+  __syncthreads();
+  dct_planes(img, tmp, sD, C, fwd);
+  float* dst = out + (long long)blockIdx.x * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = img[i];
+}
+
+int dct32_launch(const float* in, float* out, int B, int C, int fwd, cudaStream_t st) {
+  if (ensure_dct_matrix()) return -1;
+  const size_t smem = (size_t)(1024 + 2 * 1024 * C) * sizeof(float);
+  if (smem > 48 * 1024) return -3;
+  dct32_kernel<<<B, 256, smem, st>>>(in, out, C, fwd);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+// y' = a .* y + b .* DCT(eps_x);  x_next = IDCT(y').  One CTA per image; eps, y read once, y', x written once.
+__global__ void __launch_bounds__(256) blur_step_kernel(const float* __restrict__ y, const float* __restrict__ eps_x,
+                                                       const float* __restrict__ a, const float* __restrict__ bcoef,
+                                                       float* __restrict__ y_out, float* __restrict__ x_next, int C) {
+  extern __shared__ float sm[];
+  float* sD = sm;
+  float* img = sm + 1024;
+  float* tmp = img + 1024 * C;
+  const int n = 1024 * C;
+  const long long off = (long long)blockIdx.x * n;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) sD[i] = c_dct[i];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) img[i] = eps_x[off + i];
+  __syncthreads();
+  dct_planes(img, tmp, sD, C, 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int f = i / C;                            // frequency index h*32 + w
+    const float v = a[f] * y[off + i] + bcoef[f] * img[i];
+    y_out[off + i] = v;
+    img[i] = v;
+  }
+  __syncthreads();
+  if (x_next != nullptr) {
+    dct_planes(img, tmp, sD, C, 0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) x_next[off + i] = img[i];
+  }
+}
+
+int blur_step_launch(const float* y, const float* eps_x, const float* a, const float* b, float* y_out, float* x_next,
+                     int B, int C, cudaStream_t st) {
+  if (ensure_dct_matrix()) return -1;
+  const size_t smem = (size_t)(1024 + 2 * 1024 * C) * sizeof(float);
+  if (smem > 48 * 1024) return -3;
+  blur_step_kernel<<<B, 256, smem, st>>>(y, eps_x, a, b, y_out, x_next, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+__global__ void scale_shift_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float mul,
+                                   float add) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = in[i] * mul + add;
+}
+int scale_shift_launch(const float* in, float* out, long long n, float mul, float add, cudaStream_t st) {
+  scale_shift_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, out, n, mul, add);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+__global__ void scalar_ab_step_kernel(const float* __restrict__ x, const float* __restrict__ coef,
+                                      const float* __restrict__ new_eps, const float* __restrict__ hist,
+                                      float* __restrict__ x_out, float* __restrict__ hist_out, int n_hist, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float e0 = new_eps[i];
+    float acc = coef[0] * x[i] + coef[1] * e0;
+    if (n_hist > 0) hist_out[i] = e0;
+    for (int j = 0; j < n_hist; ++j) {
+      const float e = hist[(long long)j * n + i];
+      acc += coef[2 + j] * e;
+      if (j + 1 < n_hist) hist_out[(long long)(j + 1) * n + i] = e;
+    }
+    x_out[i] = acc;
+  }
+}
+int scalar_ab_step_launch(const float* x, const float* coef, const float* new_eps, const float* hist, float* x_out,
+                          float* hist_out, int n_hist, long long n, cudaStream_t st) {
+  scalar_ab_step_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, coef, new_eps, hist, x_out, hist_out, n_hist, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace gddim

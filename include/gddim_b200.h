@@ -1,0 +1,158 @@
+/*
+ * gddim_b200 -- C ABI of the B200-native gDDIM sampling hot path.
+ *
+ * The reference (qsh-zh/gDDIM) has no FFI layer: its boundary is plain Python calls
+ * (SURVEY.md 8b).  Each entry point below names the reference function it stands in for
+ * (paths relative to the reference repository root).  All pointers are caller-owned; the library never
+ * frees caller memory.  Functions return 0 on success and a negative value on error;
+ * gddim_last_error() returns a message for the calling thread.
+ *
+ * Layouts: images are NHWC.  The CLD state in *reference layout* is [B,H,W,C,2] (last axis = (x, v),
+ * cld_jax/sde_lib.py:270-274); in *net layout* it is [B,H,W,2C] with channel g*C+d
+ * (cld_jax/models/utils.py:153).  "dev" pointers are CUDA device pointers on the context's device;
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ */
+#ifndef GDDIM_B200_H
+#define GDDIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDDIM_ABI_VERSION 1
+
+typedef struct gddim_ctx gddim_ctx;         /* one per GPU: weights, workspace, CUDA graphs */
+typedef struct gddim_cld gddim_cld;         /* host-side CLD SDE tables (fp64) */
+typedef struct gddim_blur gddim_blur;       /* host-side blur SDE tables (fp64) */
+typedef struct gddim_sampler gddim_sampler; /* a configured sampler bound to a ctx */
+
+/* config.model.* / config.data.* fields read by cld_jax/models/ncsnpp.py:43-67 */
+typedef struct {
+  int image_size;          /* config.data.image_size */
+  int data_channels;       /* config.data.num_channels */
+  int state_mult;          /* 2 for CLD (x and v stacked on channels), 1 for blur */
+  int nf;
+  int n_levels;            /* len(ch_mult) */
+  int ch_mult[8];
+  int num_res_blocks;
+  int n_attn;
+  int attn_resolutions[8];
+  int fir;                 /* FIR [1,3,3,1] resampling (1) or naive repeat / mean (0) */
+  int skip_rescale;
+  int progressive_input;   /* 0 = none, 1 = residual */
+  int embedding_type;      /* 0 = fourier, 1 = positional */
+  int conditional;
+  int centered;            /* config.data.centered (if 0 the net maps x -> 2x-1 first, ncsnpp.py:136-138) */
+} gddim_model_cfg;
+
+const char* gddim_last_error(void);
+int gddim_abi_version(void);
+/* 1 if a CUDA device is usable from this process, else 0 (never throws) */
+int gddim_cuda_available(void);
+
+/* ---- context / parameters: models/utils.py:109-125 init_model, run_lib.py:707-711 restore + replicate ---- */
+int gddim_ctx_create(int device, const gddim_model_cfg* cfg, int max_batch, gddim_ctx** out);
+void gddim_ctx_destroy(gddim_ctx* ctx);
+/* parameter inventory in Flax naming (e.g. "ResnetBlockBigGANpp_3/Conv_0/kernel"), Flax layouts
+ * (conv HWIO, dense (in,out)).  kind: 0 variance_scaling(fan_avg, uniform), 1 zeros, 2 ones, 3 normal */
+int gddim_param_count(const gddim_ctx* ctx);
+int gddim_param_spec(const gddim_ctx* ctx, int index, char* name_buf, int name_buf_len, int shape[4], int* ndim,
+                     int* kind, float* scale);
+int gddim_param_set(gddim_ctx* ctx, const char* name, const float* host_data, size_t n_elem);
+/* packs the loaded parameters into device layouts (fp16 K-major GEMM operands) and builds the launch plan */
+int gddim_ctx_finalize(gddim_ctx* ctx);
+/* 0 = tcgen05/TMA kernels (default), 1 = CUDA-core reference kernels (on-GPU validation only) */
+int gddim_ctx_set_gemm_impl(gddim_ctx* ctx, int impl);
+size_t gddim_ctx_workspace_bytes(const gddim_ctx* ctx);
+long long gddim_ctx_launch_count(const gddim_ctx* ctx);   /* kernels launched by this ctx so far */
+
+/* ---- score network: NCSNpp.apply / get_eps_fn's model call (models/utils.py:128-166; ncsnpp.py:41-243) ----
+ * x_dev, out_dev: fp32 [batch, S, S, data_channels*state_mult] in net layout; t = diffusion time (labels = 999 t
+ * are formed inside, models/utils.py:172).  One t for the whole batch (as on the sampling path). */
+int gddim_unet_forward(gddim_ctx* ctx, const float* x_dev, float t, float* out_dev, int batch, void* stream);
+
+/* ---- CLD SDE tables: cld_jax/sde_lib.py:45-118 (CLD.__init__), :182-253, :289-319 ---- */
+int gddim_cld_create(double m_inv, double beta_0, double beta_1, double vv_gamma, double numerical_eps, double R_dt,
+                     int is_R_rk, gddim_cld** out);
+void gddim_cld_destroy(gddim_cld* cld);
+int gddim_cld_R(const gddim_cld* cld, const double* t, int n, double* out /*[n,2,2]*/);
+int gddim_cld_psi(const gddim_cld* cld, const double* s, const double* t, int n, double* out /*[n,2,2]*/);
+int gddim_cld_F(const gddim_cld* cld, double t, double* out /*[2,2]*/);
+int gddim_cld_G(const gddim_cld* cld, double t, double* out /*[2,2]*/);
+int gddim_cld_eps_integrand(const gddim_cld* cld, const double* t, int n, double* out /*[n,2,2]*/);
+/* CLD.get_deis_coef(order, rev_ts): out [n_ts-1, order+3, 2, 2] */
+int gddim_cld_deis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out);
+/* CLD.prepare_order0_coef(rev_ts): mean_out, eps_out [n_ts-1, 2, 2] */
+int gddim_cld_order0_coef(const gddim_cld* cld, const double* rev_ts, int n_ts, double* mean_out, double* eps_out);
+/* sampling.get_rev_ts (cld_jax/sampling.py:241-249; blur_jax/sampling.py:42-51): out [num_step+1] */
+int gddim_rev_ts(double T, double eps, int ts_order, int num_step, double* out);
+
+/* ---- blur SDE tables: blur_jax/sde_lib.py:18-163 ---- */
+int gddim_blur_create(double sigma_blur_max, double sampling_eps, gddim_blur** out);
+void gddim_blur_destroy(gddim_blur* b);
+double gddim_blur_sampling_T(const gddim_blur* b);
+int gddim_blur_y_mean_coef(const gddim_blur* b, double t, double* out /*[32,32]*/);
+double gddim_blur_y_std_coef(const gddim_blur* b, double t);
+double gddim_blur_t2alpha(const gddim_blur* b, double t);
+
+/* ---- update operators on device arrays ---- */
+/* deis.multistep_ab_step (cld_jax/deis.py:141-151), reference layout: x, new_eps, x_out [n_pairs,2];
+ * eps_pred, eps_pred_out [order+1, n_pairs, 2]; deis_coef host [order+3,2,2] fp32 */
+int gddim_multistep_ab_step(const float* x_dev, const float* deis_coef_host, const float* new_eps_dev,
+                            const float* eps_pred_dev, float* x_out_dev, float* eps_pred_out_dev, int order,
+                            long long n_pairs, void* stream);
+/* blur_jax/multistep.py:94-98 ab_step: ei_coef host [n_hist+2] */
+int gddim_scalar_ab_step(const float* x_dev, const float* ei_coef_host, const float* new_eps_dev,
+                         const float* eps_pred_dev, float* x_out_dev, float* eps_pred_out_dev, int n_hist, long long n,
+                         void* stream);
+/* '(b ... d g) <-> b ... (g d)' (models/utils.py:153,158) */
+int gddim_relayout(const float* src_dev, float* dst_dev, long long n_pix, int C, int to_net, void* stream);
+/* blur.batch_img_dct / batch_img_idct (blur_jax/blur.py:99-107) on [B,32,32,C] */
+int gddim_dct2d_32(const float* in_dev, float* out_dev, int batch, int C, int forward, void* stream);
+
+/* ---- samplers ----
+ * kind 0: CLD deis (sampling.py:204-253 _impl_deis_sampler / get_deis_sampler)
+ * kind 1: CLD order0 (sampling.py:156-202 get_order0_sampler, is_em = 0)
+ * kind 2: blur order0 (blur_jax/sampling.py:53-90) */
+#define GDDIM_CLD_DEIS 0
+#define GDDIM_CLD_ORDER0 1
+#define GDDIM_BLUR_ORDER0 2
+typedef struct {
+  int kind;
+  int nfe;
+  int deis_order;
+  int ts_order;
+  int denoising;     /* config.sampling.noise_removal */
+  int mixed_score;   /* config.model.mixed_score (CLD) */
+  int use_graph;     /* capture the network evaluation in a CUDA graph */
+  float x_mul, x_add; /* inverse_scaler as an affine map: x_out = x * x_mul + x_add  ((x+1)/2 -> 0.5, 0.5) */
+} gddim_sampler_cfg;
+
+/* exactly one of cld / blur is used, according to kind */
+int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
+                         gddim_sampler** out);
+void gddim_sampler_destroy(gddim_sampler* s);
+/* The table the sampler steps through (for index-exact parity checks): fp32 [n_steps, order+3, 2, 2] for CLD
+ * deis.  Returns the number of floats written (or needed when out == NULL). */
+long long gddim_sampler_coef(const gddim_sampler* s, float* out, long long cap);
+int gddim_sampler_num_steps(const gddim_sampler* s);
+int gddim_sampler_rev_ts(const gddim_sampler* s, double* out, int cap);
+/* One call = the reference's sampler(rng, state, u) body.
+ *  CLD:  u [batch,S,S,C,2] reference layout -> x [batch,S,S,C] (after the affine inverse scaler),
+ *        v [batch,S,S,C];  blur: u = y [batch,32,32,C] -> x; v may be NULL.
+ *  host_buffers = 1: u/x/v are host pointers (pinned or pageable); copies are issued on `stream` and the
+ *  call returns after synchronising it.  host_buffers = 0: device pointers, asynchronous on `stream`.
+ *  trace_dev (optional, device): receives the state after every multistep update, [n_steps, batch, ...]
+ *  in reference layout. */
+int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch, int host_buffers, float* trace_dev,
+                 void* stream);
+/* kernels launched (or replayed through CUDA graphs) by this sampler so far */
+long long gddim_sampler_launch_count(const gddim_sampler* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDDIM_B200_H */
