@@ -25,6 +25,24 @@ class SamplerCfg(C.Structure):
               ("x_mul", C.c_float), ("x_add", C.c_float)]
 
 
+class GemmDesc(C.Structure):
+  _fields_ = [("a0", C.c_void_p), ("a0_ctot", C.c_int), ("a0_coff", C.c_int), ("a0_c", C.c_int), ("a0_taps", C.c_int),
+              ("a1", C.c_void_p), ("a1_ctot", C.c_int), ("a1_coff", C.c_int), ("a1_c", C.c_int), ("a1_taps", C.c_int),
+              ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+              ("w", C.c_void_p), ("N", C.c_int), ("w_ld", C.c_int), ("w_koff", C.c_int),
+              ("w_batch_stride", C.c_longlong), ("w_rows_per_batch", C.c_int),
+              ("bias", C.c_void_p), ("bias2", C.c_void_p), ("residual", C.c_void_p), ("rowscale", C.c_void_p),
+              ("scale", C.c_float), ("out32", C.c_void_p), ("out16", C.c_void_p), ("row_out", C.c_void_p),
+              ("ldo", C.c_int), ("epi", C.c_int), ("impl", C.c_int), ("force_block_n", C.c_int)]
+
+
+class NormDesc(C.Structure):
+  _fields_ = [("src1", C.c_void_p), ("c1", C.c_int), ("src2", C.c_void_p), ("c2", C.c_int),
+              ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int),
+              ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+              ("silu", C.c_int), ("resample", C.c_int), ("dst16", C.c_void_p), ("raw16", C.c_void_p)]
+
+
 CLD_DEIS, CLD_ORDER0, BLUR_ORDER0 = 0, 1, 2
 
 _P = C.c_void_p
@@ -45,6 +63,9 @@ SIGNATURES = {
     "gddim_ctx_set_gemm_impl": (C.c_int, [_P, C.c_int]),
     "gddim_ctx_workspace_bytes": (C.c_size_t, [_P]),
     "gddim_ctx_launch_count": (C.c_longlong, [_P]),
+    "gddim_ctx_set_profile": (C.c_int, [_P, C.c_int]),
+    "gddim_ctx_get_profile": (C.c_int, [_P, _P, _P, _P]),
+    "gddim_ctx_dump_profile": (C.c_int, [_P, C.c_char_p]),
     "gddim_unet_forward": (C.c_int, [_P, _P, C.c_float, _P, C.c_int, _P]),
     "gddim_cld_create": (C.c_int, [C.c_double] * 6 + [C.c_int, C.POINTER(_P)]),
     "gddim_cld_destroy": (None, [_P]),
@@ -66,6 +87,8 @@ SIGNATURES = {
     "gddim_scalar_ab_step": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_longlong, _P]),
     "gddim_relayout": (C.c_int, [_P, _P, C.c_longlong, C.c_int, C.c_int, _P]),
     "gddim_dct2d_32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "gddim_conv_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
+    "gddim_group_norm": (C.c_int, [C.POINTER(NormDesc), _P]),
     "gddim_sampler_create": (C.c_int, [_P, C.POINTER(SamplerCfg), _P, _P, C.POINTER(_P)]),
     "gddim_sampler_destroy": (None, [_P]),
     "gddim_sampler_coef": (C.c_longlong, [_P, _P, C.c_longlong]),

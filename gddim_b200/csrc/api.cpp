@@ -111,6 +111,22 @@ int gddim_ctx_set_gemm_impl(gddim_ctx* ctx, int impl) {
 size_t gddim_ctx_workspace_bytes(const gddim_ctx* ctx) { return ctx ? ctx->net->workspace_bytes() : 0; }
 long long gddim_ctx_launch_count(const gddim_ctx* ctx) { return ctx ? ctx->net->launch_count() : -1; }
 
+int gddim_ctx_set_profile(gddim_ctx* ctx, int on) {
+  if (!ctx) return set_err("gddim_ctx_set_profile: null ctx");
+  ctx->net->set_profile(on != 0);
+  return 0;
+}
+int gddim_ctx_get_profile(const gddim_ctx* ctx, double* ms_by_kind, double* gemm_flops, long long* gemm_launches) {
+  if (!ctx || !ms_by_kind) return set_err("gddim_ctx_get_profile: bad arguments");
+  ctx->net->get_profile(ms_by_kind, gemm_flops, gemm_launches);
+  return 0;
+}
+int gddim_ctx_dump_profile(const gddim_ctx* ctx, const char* path) {
+  if (!ctx || !path) return set_err("gddim_ctx_dump_profile: bad arguments");
+  if (ctx->net->dump_profile(path)) return set_err("gddim_ctx_dump_profile: cannot write file");
+  return 0;
+}
+
 int gddim_unet_forward(gddim_ctx* ctx, const float* x_dev, float t, float* out_dev, int batch, void* stream) {
   if (!ctx || !x_dev || !out_dev) return set_err("gddim_unet_forward: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -241,6 +257,45 @@ int gddim_relayout(const float* src_dev, float* dst_dev, long long n_pix, int C,
 int gddim_dct2d_32(const float* in_dev, float* out_dev, int batch, int C, int forward, void* stream) {
   if (need_cuda("gddim_dct2d_32")) return -1;
   if (dct32_launch(in_dev, out_dev, batch, C, forward, (cudaStream_t)stream)) return set_err("gddim_dct2d_32: launch failed");
+  return 0;
+}
+
+// ---- operator level ---------------------------------------------------------------------------------------------
+int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream) {
+  if (need_cuda("gddim_conv_gemm")) return -1;
+  if (!d || !d->a0 || !d->w) return set_err("gddim_conv_gemm: bad arguments");
+  GemmOp g;
+  memset(&g, 0, sizeof(g));
+  g.nseg = d->a1 ? 2 : 1;
+  g.seg[0] = {(const __half*)d->a0, d->a0_ctot, d->a0_coff, d->a0_c, d->a0_taps};
+  if (d->a1) g.seg[1] = {(const __half*)d->a1, d->a1_ctot, d->a1_coff, d->a1_c, d->a1_taps};
+  g.B = d->B; g.H = d->H; g.W = d->W;
+  g.w = (const __half*)d->w; g.N = d->N; g.w_ld = d->w_ld; g.w_koff = d->w_koff;
+  g.w_batch_stride = d->w_batch_stride; g.w_rows_per_batch = d->w_rows_per_batch;
+  g.bias = d->bias; g.bias2 = d->bias2; g.residual = d->residual; g.rowscale = d->rowscale; g.scale = d->scale;
+  g.out32 = d->out32; g.out16 = (__half*)d->out16; g.row_out = d->row_out; g.ldo = d->ldo; g.epi = d->epi;
+  if (d->impl == 0 && gemm_prepare(&g, d->force_block_n)) return set_err(std::string("gddim_conv_gemm: ") + gemm_last_error());
+  if (gemm_launch(&g, d->impl, (cudaStream_t)stream)) return set_err(std::string("gddim_conv_gemm: ") + gemm_last_error());
+  return 0;
+}
+
+int gddim_group_norm(const gddim_norm_desc* d, void* stream) {
+  if (need_cuda("gddim_group_norm")) return -1;
+  if (!d || !d->src1) return set_err("gddim_group_norm: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  NormOp n;
+  memset(&n, 0, sizeof(n));
+  n.src1 = d->src1; n.c1 = d->c1; n.src2 = d->src2; n.c2 = d->c2;
+  n.B = d->B; n.H = d->H; n.W = d->W; n.groups = d->groups; n.gamma = d->gamma; n.beta = d->beta; n.eps = d->eps;
+  n.silu = d->silu; n.resample = d->resample; n.dst16 = (__half*)d->dst16; n.raw16 = (__half*)d->raw16;
+  n.splits = norm_splits(d->B, d->H, d->W);
+  float* part = nullptr;
+  const size_t nb = (size_t)d->B * n.splits * (d->groups > 0 ? d->groups : 1) * 2 * sizeof(float);
+  if (cudaMallocAsync(&part, nb, st) != cudaSuccess) return set_err("gddim_group_norm: scratch allocation failed");
+  n.partial = part;
+  const int rc = norm_launch(&n, st);
+  cudaFreeAsync(part, st);
+  if (rc) return set_err("gddim_group_norm: unsupported shape or launch failure (rc=" + std::to_string(rc) + ")");
   return 0;
 }
 
@@ -385,7 +440,7 @@ static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t s
   if (tt > 0)
     cudaMemcpyAsync(net.temb_cur(), s->d_temb_all + (size_t)e * tt, (size_t)tt * 4, cudaMemcpyDeviceToDevice, st);
   const float* in = s->is_blur ? s->d_xin : s->d_u;
-  if (s->cfg.use_graph) {
+  if (s->cfg.use_graph && !net.profiling()) {
     if (s->graph_batch != batch) {
       for (auto g : s->graphs) if (g) cudaGraphExecDestroy(g);
       s->graphs.assign(s->d_eps.size(), nullptr);

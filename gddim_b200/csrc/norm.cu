@@ -26,7 +26,7 @@ int norm_splits(int B, int H, int W) {
 
 __global__ void gn_partial_kernel(const float* __restrict__ src1, int c1, const float* __restrict__ src2, int c2,
                                   int P, int groups, int splits, int rows, float* __restrict__ partial) {
-  extern __shared__ float sm[];   // [threads][2]
+  extern __shared__ float sm[];   // [threads][8]: per-channel sum[4], sumsq[4]
   const int C = c1 + c2;
   const int nv = C / 4;
   const int b = blockIdx.y, split = blockIdx.x;
@@ -38,25 +38,30 @@ __global__ void gn_partial_kernel(const float* __restrict__ src1, int c1, const 
   int cs, cc;
   if (c < c1) { base = src1 + (long long)b * P * c1; cs = c1; cc = c; }
   else { base = src2 + (long long)b * P * c2; cs = c2; cc = c - c1; }
-  float s = 0.f, ss = 0.f;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
   for (int pix = pbeg + row; pix < pbeg + pp; pix += rows) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)pix * cs + cc));
-    s += (v.x + v.y) + (v.z + v.w);
-    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
   }
-  sm[threadIdx.x * 2] = s;
-  sm[threadIdx.x * 2 + 1] = ss;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sm[threadIdx.x * 8 + j] = s[j];
+    sm[threadIdx.x * 8 + 4 + j] = ss[j];
+  }
   __syncthreads();
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x;
-    const int vpg = (C / groups) / 4;     // float4 vectors per group
+  // fixed-order (deterministic) reduction: one thread per group walks its channels and pixel rows
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const int cpg = C / groups;
     float ts = 0.f, tss = 0.f;
-    for (int r = 0; r < rows; ++r)
-      for (int v = 0; v < vpg; ++v) {
-        const int t = r * nv + g * vpg + v;
-        ts += sm[t * 2];
-        tss += sm[t * 2 + 1];
+    for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) {
+      const int v = ch >> 2, j = ch & 3;
+      for (int r = 0; r < rows; ++r) {
+        const int t = r * nv + v;
+        ts += sm[t * 8 + j];
+        tss += sm[t * 8 + 4 + j];
       }
+    }
     float* o = partial + (((long long)b * splits + split) * groups + g) * 2;
     o[0] = ts;
     o[1] = tss;
@@ -193,7 +198,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
   const int do_norm = op->dst16 != nullptr;
   if (C % 8 != 0 || op->c1 % 8 != 0) return -1;
   if (do_norm) {
-    if (C % op->groups != 0 || (C / op->groups) % 4 != 0) return -2;
+    if (C % op->groups != 0 || C % 4 != 0) return -2;
     const int nv = C / 4;
     int rows = 256 / nv;
     if (rows < 1) rows = 1;
@@ -203,7 +208,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     if (nv * rows > 1024 || P % op->splits != 0) return -3;
     const int threads = nv * rows;
     dim3 grid(op->splits, op->B);
-    gn_partial_kernel<<<grid, threads, threads * 2 * sizeof(float), st>>>(op->src1, op->c1, op->src2, op->c2, P,
+    gn_partial_kernel<<<grid, threads, threads * 8 * sizeof(float), st>>>(op->src1, op->c1, op->src2, op->c2, P,
                                                                           op->groups, op->splits, rows, op->partial);
   }
   ApplyArgs a;

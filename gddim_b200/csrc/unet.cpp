@@ -690,6 +690,17 @@ int UNet::time_projections(double t, float* dst_dev, cudaStream_t st) {
 int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st) {
   if (!finalized_) return fail("context not finalized");
   if (batch < 1 || batch > max_batch_) return fail("batch exceeds max_batch");
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  const bool prof = profile_ && cap == cudaStreamCaptureStatusNone;
+  if (prof && prof_ev_.size() != ops_.size() + 1) {
+    prof_ev_.resize(ops_.size() + 1);
+    for (auto& e : prof_ev_) cudaEventCreate(&e);
+    prof_op_ms_.assign(ops_.size(), 0.0);
+    prof_op_flops_.assign(ops_.size(), 0.0);
+  }
+  size_t op_idx = 0;
+  if (prof) cudaEventRecord(prof_ev_[0], st);
   for (auto& op : ops_) {
     int rc = 0;
     switch (op.kind) {
@@ -732,7 +743,64 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         break;
     }
     if (rc) return fail("launch failed in op " + op.tag + " (rc=" + std::to_string(rc) + ")");
+    ++op_idx;
+    if (prof) cudaEventRecord(prof_ev_[op_idx], st);
   }
+  if (prof) {
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail("device error during profiled forward");
+    for (size_t i = 0; i < ops_.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, prof_ev_[i], prof_ev_[i + 1]);
+      prof_op_ms_[i] += ms;
+      if (ops_[i].kind == OP_GEMM) {
+        const GemmOp& g = ops_[i].gemm;
+        double k = 0;
+        for (int s2 = 0; s2 < g.nseg; ++s2) k += (double)g.seg[s2].taps * g.seg[s2].c;
+        prof_op_flops_[i] = 2.0 * batch * g.H * g.W * (double)g.N * k;
+      }
+    }
+    ++prof_forwards_;
+  }
+  return 0;
+}
+
+void UNet::set_profile(bool on) {
+  profile_ = on;
+  std::fill(prof_op_ms_.begin(), prof_op_ms_.end(), 0.0);
+  prof_forwards_ = 0;
+}
+
+void UNet::get_profile(double ms_by_kind[8], double* gemm_flops, long long* gemm_launches) const {
+  for (int i = 0; i < 8; ++i) ms_by_kind[i] = 0;
+  double fl = 0;
+  long long nl = 0;
+  for (size_t i = 0; i < prof_op_ms_.size(); ++i) {
+    ms_by_kind[(int)ops_[i].kind] += prof_op_ms_[i];
+    if (ops_[i].kind == OP_GEMM) { fl += prof_op_flops_[i] * prof_forwards_; nl += prof_forwards_; }
+  }
+  if (gemm_flops) *gemm_flops = fl;
+  if (gemm_launches) *gemm_launches = nl;
+}
+
+int UNet::dump_profile(const char* path) const {
+  FILE* f = fopen(path, "w");
+  if (!f) return -1;
+  fprintf(f, "op,kind,H,W,N,K,block_n,ms_per_forward,gflop,tflops\n");
+  for (size_t i = 0; i < prof_op_ms_.size(); ++i) {
+    const Op& op = ops_[i];
+    const double ms = prof_forwards_ ? prof_op_ms_[i] / prof_forwards_ : 0.0;
+    double k = 0;
+    int H = op.H, W = op.W, N = op.cout, bn = 0;
+    if (op.kind == OP_GEMM) {
+      for (int s2 = 0; s2 < op.gemm.nseg; ++s2) k += (double)op.gemm.seg[s2].taps * op.gemm.seg[s2].c;
+      H = op.gemm.H; W = op.gemm.W; N = op.gemm.N; bn = op.gemm.block_n;
+    } else if (op.kind == OP_NORM) {
+      H = op.norm.H; W = op.norm.W; N = op.norm.c1 + op.norm.c2;
+    }
+    fprintf(f, "%s,%d,%d,%d,%d,%.0f,%d,%.5f,%.4f,%.2f\n", op.tag.c_str(), (int)op.kind, H, W, N, k, bn, ms,
+            prof_op_flops_[i] * 1e-9, ms > 0 ? prof_op_flops_[i] / (ms * 1e-3) * 1e-12 : 0.0);
+  }
+  fclose(f);
   return 0;
 }
 

@@ -57,12 +57,17 @@ class UNet {
   int net_channels() const { return cfg_.data_channels * cfg_.state_mult; }
   int image_size() const { return cfg_.image_size; }
   int max_batch() const { return max_batch_; }
-  size_t workspace_bytes() const { return arena_bytes_ + weight_bytes_; }
+  size_t workspace_bytes() const { return finalized_ ? arena_bytes_ + weight_bytes_ : arena_peak_ + weight_top_; }
   long long launch_count() const { return launches_; }
   int gemm_impl = 0;
   const std::string& error() const { return err_; }
   const gddim_model_cfg& cfg() const { return cfg_; }
   int num_ops() const { return (int)ops_.size(); }
+  // per-op CUDA-event timing of forward() (eager launches only); accumulates until reset
+  void set_profile(bool on);
+  bool profiling() const { return profile_; }
+  void get_profile(double ms_by_kind[8], double* gemm_flops, long long* gemm_launches) const;
+  int dump_profile(const char* path) const;
 
  private:
   struct T32 { float* p; int C, H, W; size_t bytes; };
@@ -77,6 +82,11 @@ class UNet {
   std::map<std::string, std::vector<float>> host_params_;
   std::vector<Op> ops_;
   long long launches_ = 0;
+  bool profile_ = false;
+  std::vector<cudaEvent_t> prof_ev_;
+  std::vector<double> prof_op_ms_;        // per op, accumulated
+  std::vector<double> prof_op_flops_;     // per op per forward (GEMMs)
+  long long prof_forwards_ = 0;
 
   // workspace arena (activations) with a first-fit free list, offsets assigned during the walk
   char* arena_ = nullptr;

@@ -159,6 +159,21 @@ class ScoreNet:
   def workspace_bytes(self):
     return int(_lib.lib().gddim_ctx_workspace_bytes(self._ctx)) if self._ctx is not None else 0
 
+  # -- per-op timing (bench.py's roofline leg) ----------------------------------------------------------
+  def set_profile(self, on):
+    _lib.check(_lib.lib().gddim_ctx_set_profile(self._ctx, int(bool(on))))
+
+  def get_profile(self):
+    """-> (ms_by_kind dict, gemm_flops, gemm_launches) accumulated since set_profile(True)."""
+    ms = (C.c_double * 8)()
+    fl, nl = C.c_double(), C.c_longlong()
+    _lib.check(_lib.lib().gddim_ctx_get_profile(self._ctx, ms, C.byref(fl), C.byref(nl)))
+    names = ["stem", "groupnorm", "conv_gemm", "head", "im2col", "transpose_v", "small_attn"]
+    return {n: ms[i] for i, n in enumerate(names)}, fl.value, nl.value
+
+  def dump_profile(self, path):
+    _lib.check(_lib.lib().gddim_ctx_dump_profile(self._ctx, str(path).encode()))
+
   # -- forward --------------------------------------------------------------------------------------------
   def forward(self, x, t):
     """x: [B,H,W,Cnet] (numpy or torch.cuda float32), t: diffusion time shared by the batch

@@ -1,0 +1,81 @@
+"""Operator-level wrappers over libgddim_b200.so (torch.cuda tensors in, torch.cuda tensors out).
+
+These are the building blocks the launch plan in csrc/unet.cpp is made of, exposed so that each kernel can
+be checked against the oracle on its own:
+  conv2d / nin   <-> cld_jax/models/layers.py:66-107 (ddpm_conv1x1 / ddpm_conv3x3), :467-478 (NIN)
+  group_norm     <-> flax nn.GroupNorm (+ swish, + up_or_down_sampling resamplers), layerspp.py:196-213
+  attention      <-> layerspp.py:74-78
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(t):
+  return None if t is None else t.data_ptr()
+
+
+def pack_conv_weight(kernel_hwio, extra_1x1=None):
+  """Flax HWIO kernel (kh,kw,cin,cout) [+ optional 1x1 shortcut kernel (1,1,cin2,cout)] -> K-major fp16
+  [cout, kh*kw*cin (+ cin2)] with k = tap*cin + ci  (the layout csrc/unet.cpp packs)."""
+  import torch
+  k = torch.as_tensor(np.asarray(kernel_hwio, np.float32))
+  kh, kw, cin, cout = k.shape
+  w = k.reshape(kh * kw * cin, cout).t().contiguous()
+  if extra_1x1 is not None:
+    e = torch.as_tensor(np.asarray(extra_1x1, np.float32))
+    w = torch.cat([w, e.reshape(-1, cout).t().contiguous()], dim=1)
+  return w.to(torch.float16).contiguous().cuda()
+
+
+def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residual=None, rowscale=None, scale=1.0,
+              out_fp32=True, out_fp16=False, impl=0, force_block_n=0, epi=0, a0_coff=0, a0_c=None, w_ld=None,
+              w_koff=0, w_batch_stride=0, w_rows_per_batch=0):
+  """a0 (and a1): fp16 [B,H,W,C]; w: fp16 K-major.  Returns (out32 or None, out16 or None[, row_out])."""
+  import torch
+  _lib.require_cuda("conv_gemm")
+  B, H, W, C0 = a0.shape
+  d = _lib.GemmDesc()
+  d.a0, d.a0_ctot, d.a0_coff, d.a0_c, d.a0_taps = a0.data_ptr(), C0, a0_coff, (a0_c or C0), taps0
+  if a1 is not None:
+    d.a1, d.a1_ctot, d.a1_coff, d.a1_c, d.a1_taps = a1.data_ptr(), a1.shape[3], 0, a1.shape[3], taps1
+  d.B, d.H, d.W = B, H, W
+  d.w, d.N, d.w_ld, d.w_koff = w.data_ptr(), N, (w_ld or w.shape[-1]), w_koff
+  d.w_batch_stride, d.w_rows_per_batch = w_batch_stride, w_rows_per_batch
+  d.bias, d.bias2, d.residual, d.rowscale = _ptr(bias), _ptr(bias2), _ptr(residual), _ptr(rowscale)
+  d.scale = scale
+  o32 = torch.empty((B, H, W, N), dtype=torch.float32, device="cuda") if (out_fp32 and epi == 0) else None
+  o16 = torch.empty((B, H, W, N), dtype=torch.float16, device="cuda") if (out_fp16 or epi == 1) else None
+  row = torch.empty((B, H, W), dtype=torch.float32, device="cuda") if epi == 1 else None
+  d.out32, d.out16, d.row_out, d.ldo = _ptr(o32), _ptr(o16), _ptr(row), N
+  d.epi, d.impl, d.force_block_n = epi, impl, force_block_n
+  st = torch.cuda.current_stream().cuda_stream
+  _lib.check(_lib.lib().gddim_conv_gemm(C.byref(d), st), "gddim_conv_gemm")
+  if epi == 1:
+    return o32, o16, row
+  return o32, o16
+
+
+def group_norm(x, gamma, beta, groups=None, silu=True, resample=0, x2=None, want_raw=False, want_norm=True,
+               eps=1e-6):
+  """x (and x2): fp32 [B,H,W,C].  Returns (dst16 or None, raw16 or None)."""
+  import torch
+  _lib.require_cuda("group_norm")
+  B, H, W, C1 = x.shape
+  C2 = 0 if x2 is None else x2.shape[3]
+  Ct = C1 + C2
+  Ho, Wo = (H // 2, W // 2) if resample in (1, 3) else ((H * 2, W * 2) if resample in (2, 4) else (H, W))
+  d = _lib.NormDesc()
+  d.src1, d.c1, d.src2, d.c2 = x.data_ptr(), C1, _ptr(x2), C2
+  d.B, d.H, d.W = B, H, W
+  d.groups = groups or min(Ct // 4, 32)
+  d.gamma, d.beta, d.eps = _ptr(gamma), _ptr(beta), eps
+  d.silu, d.resample = int(silu), resample
+  dst = torch.empty((B, Ho, Wo, Ct), dtype=torch.float16, device="cuda") if want_norm else None
+  raw = torch.empty((B, Ho, Wo, Ct), dtype=torch.float16, device="cuda") if want_raw else None
+  d.dst16, d.raw16 = _ptr(dst), _ptr(raw)
+  st = torch.cuda.current_stream().cuda_stream
+  _lib.check(_lib.lib().gddim_group_norm(C.byref(d), st), "gddim_group_norm")
+  return dst, raw

@@ -69,6 +69,13 @@ int gddim_ctx_set_gemm_impl(gddim_ctx* ctx, int impl);
 size_t gddim_ctx_workspace_bytes(const gddim_ctx* ctx);
 long long gddim_ctx_launch_count(const gddim_ctx* ctx);   /* kernels launched by this ctx so far */
 
+/* per-op CUDA-event timing of the network evaluation (eager launches; CUDA graphs are bypassed while on).
+ * ms_by_kind[8]: accumulated ms per op kind {0 stem, 1 groupnorm, 2 conv/gemm (tcgen05), 3 head, 4 im2col,
+ * 5 transpose, 6 small attention}; gemm_flops: algorithmic FLOPs (2 M N K) of the GEMM launches timed. */
+int gddim_ctx_set_profile(gddim_ctx* ctx, int on);
+int gddim_ctx_get_profile(const gddim_ctx* ctx, double* ms_by_kind, double* gemm_flops, long long* gemm_launches);
+int gddim_ctx_dump_profile(const gddim_ctx* ctx, const char* path);   /* per-op CSV */
+
 /* ---- score network: NCSNpp.apply / get_eps_fn's model call (models/utils.py:128-166; ncsnpp.py:41-243) ----
  * x_dev, out_dev: fp32 [batch, S, S, data_channels*state_mult] in net layout; t = diffusion time (labels = 999 t
  * are formed inside, models/utils.py:172).  One t for the whole batch (as on the sampling path). */
@@ -112,6 +119,37 @@ int gddim_scalar_ab_step(const float* x_dev, const float* ei_coef_host, const fl
 int gddim_relayout(const float* src_dev, float* dst_dev, long long n_pix, int C, int to_net, void* stream);
 /* blur.batch_img_dct / batch_img_idct (blur_jax/blur.py:99-107) on [B,32,32,C] */
 int gddim_dct2d_32(const float* in_dev, float* out_dev, int batch, int C, int forward, void* stream);
+
+/* ---- operator level (layers.py:66-107 ddpm_conv1x1/3x3, :467-478 NIN; layerspp.py:74-78 attention einsums;
+ *      flax nn.GroupNorm + swish + up_or_down_sampling resamplers, layerspp.py:196-213) ----
+ * out[m,n] = (sum_seg sum_tap sum_c A_seg[pixel(m)+tap, c] Wt[n, k] * rowscale[m] + bias[n] + bias2[n]
+ *             + residual[m,n]) * scale, m over the [B,H,W] pixel grid.  A*, w, out16: fp16; K-major weights
+ * Wt [N, w_ld] with k = w_koff + seg-major, tap-major, channel-minor.  epi = 1: row softmax (N == 256). */
+typedef struct {
+  const void* a0; int a0_ctot, a0_coff, a0_c, a0_taps;
+  const void* a1; int a1_ctot, a1_coff, a1_c, a1_taps;      /* a1 = NULL: single segment */
+  int B, H, W;
+  const void* w; int N, w_ld, w_koff;
+  long long w_batch_stride; int w_rows_per_batch;           /* per-image B operand (attention); 0 = shared */
+  const float* bias; const float* bias2; const float* residual; const float* rowscale;
+  float scale;
+  float* out32; void* out16; float* row_out; int ldo;
+  int epi;                                                  /* 0 linear, 1 softmax */
+  int impl;                                                 /* 0 tcgen05, 1 CUDA-core reference */
+  int force_block_n;                                        /* 0 = heuristic */
+} gddim_gemm_desc;
+int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream);
+
+/* resample: 0 none, 1 FIR down, 2 FIR up, 3 naive (mean) down, 4 naive (repeat) up.  dst16 = act(GN(x)) resampled,
+ * raw16 = x resampled (either may be NULL).  Sources are fp32 NHWC, channel-concatenated (src2 optional). */
+typedef struct {
+  const float* src1; int c1; const float* src2; int c2;
+  int B, H, W; int groups;
+  const float* gamma; const float* beta; float eps;
+  int silu; int resample;
+  void* dst16; void* raw16;
+} gddim_norm_desc;
+int gddim_group_norm(const gddim_norm_desc* d, void* stream);
 
 /* ---- samplers ----
  * kind 0: CLD deis (sampling.py:204-253 _impl_deis_sampler / get_deis_sampler)

@@ -1,0 +1,169 @@
+"""Kernel-level parity on the GPU, through the C ABI (gddim_b200.ops / deis / blur wrappers): the tcgen05
+implicit-GEMM convolution (impl 0) and its CUDA-core twin (impl 1) against torch conv2d on the same
+fp16-rounded operands; GroupNorm(+swish)(+FIR) against the oracle's literal upfirdn restatement; the
+update / relayout / DCT kernels against the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+from gddim_b200 import ops
+from gddim_b200.blur import blur as gblur
+from gddim_b200.blur import multistep as gms
+from gddim_b200.cld import deis as gdeis
+from oracle import blur as ob
+from oracle import cld as oc
+from oracle import ncsnpp as on
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_ref(a16, k_hwio, taps):
+  """fp64 conv on the fp16-rounded operands; a16 [B,H,W,C] fp16 (cpu), k_hwio fp32."""
+  x = a16.double().permute(0, 3, 1, 2)
+  w = torch.as_tensor(k_hwio).to(torch.float16).double().permute(3, 2, 0, 1)
+  return F.conv2d(x, w, padding=1 if taps == 9 else 0).permute(0, 2, 3, 1)
+
+
+CASES = [  # B, H, W, Cin, Cout, two_seg
+    (2, 32, 32, 128, 128, False),
+    (3, 16, 16, 256, 256, False),
+    (4, 8, 8, 256, 256, True),
+    (16, 4, 4, 512, 256, True),
+    (3, 4, 4, 256, 256, False),        # M = 48 < one tile: tail rows masked
+    (1, 32, 32, 384, 128, True),
+    (5, 16, 16, 64, 64, False),
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
+@pytest.mark.parametrize("case", CASES, ids=[f"b{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}{'_sc' if c[5] else ''}" for c in CASES])
+def test_conv3x3_bias_residual_scale(impl, case):
+  B, H, W, Cin, Cout, two = case
+  g = torch.Generator().manual_seed(B * 1000 + Cin)
+  a = (torch.randn(B, H, W, Cout if two else Cin, generator=g)).to(torch.float16)
+  k = (torch.randn(3, 3, a.shape[3], Cout, generator=g) / np.sqrt(9 * a.shape[3])).numpy()
+  bias = torch.randn(Cout, generator=g)
+  bias2 = torch.randn(Cout, generator=g)
+  want = _conv_ref(a, k, 9) + (bias + bias2).double()
+  a1 = k1 = res = None
+  if two:
+    a1 = torch.randn(B, H, W, Cin, generator=g).to(torch.float16)
+    k1 = (torch.randn(1, 1, Cin, Cout, generator=g) / np.sqrt(Cin)).numpy()
+    want = want + _conv_ref(a1, k1, 1)
+  else:
+    res = torch.randn(B, H, W, Cout, generator=g)
+    want = want + res.double()
+  want = want / np.sqrt(2.0)
+  w = ops.pack_conv_weight(k, k1)
+  o32, o16 = ops.conv_gemm(a.cuda(), w, Cout, taps0=9, a1=None if a1 is None else a1.cuda(), bias=bias.cuda(),
+                           bias2=bias2.cuda(), residual=None if res is None else res.cuda(),
+                           scale=float(1 / np.sqrt(2.0)), out_fp32=True, out_fp16=True, impl=impl)
+  torch.cuda.synchronize()
+  assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
+  assert rel_l2(o16.float().cpu().numpy(), want.numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 256])
+def test_gemm_block_n_variants(impl, bn):
+  if impl == 1 and bn != 0:
+    pytest.skip("block_n only exists on the tcgen05 path")
+  g = torch.Generator().manual_seed(7 + bn)
+  a = torch.randn(2, 16, 16, 128, generator=g).to(torch.float16)
+  k = (torch.randn(1, 1, 128, 256, generator=g) / np.sqrt(128)).numpy()
+  want = _conv_ref(a, k, 1)
+  o32, _ = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k), 256, taps0=1, impl=impl, force_block_n=bn)
+  assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
+def test_attention_chain(impl):
+  """qk^T -> row softmax epilogue -> P V with per-image B operands == softmax(q k^T / sqrt(C)) v."""
+  B, H, W, Cc = 3, 16, 16, 256
+  T = H * W
+  g = torch.Generator().manual_seed(11)
+  qkv = (torch.randn(B, H, W, 3 * Cc, generator=g) * 0.5).to(torch.float16)
+  qd = qkv.cuda()
+  scale = float(Cc) ** -0.5
+  _, p16, rowinv = ops.conv_gemm(qd, qd, T, taps0=1, a0_coff=0, a0_c=Cc, w_ld=3 * Cc, w_koff=Cc,
+                                 w_batch_stride=T * 3 * Cc, w_rows_per_batch=T, scale=scale, epi=1, impl=impl)
+  q, k, v = qkv[..., :Cc].double().reshape(B, T, Cc), qkv[..., Cc:2 * Cc].double().reshape(B, T, Cc), \
+      qkv[..., 2 * Cc:].double().reshape(B, T, Cc)
+  s = torch.einsum("btc,bsc->bts", q, k) * scale
+  p_want = torch.softmax(s, dim=-1)
+  p_got = p16.float().reshape(B, T, T).cpu().double() * rowinv.reshape(B, T, 1).cpu().double()
+  assert rel_l2(p_got.numpy(), p_want.numpy()) < 2e-3
+  vT = v.transpose(1, 2).contiguous().to(torch.float16).cuda()             # [B, C, T]
+  _, o16 = ops.conv_gemm(p16, vT, Cc, taps0=1, w_ld=T, w_batch_stride=Cc * T, w_rows_per_batch=Cc,
+                         rowscale=rowinv, out_fp32=False, out_fp16=True, impl=impl)
+  o_want = torch.einsum("bts,bsc->btc", p_want, v)
+  assert rel_l2(o16.float().reshape(B, T, Cc).cpu().numpy(), o_want.numpy()) < 3e-3
+
+
+NORM_CASES = [(2, 32, 32, 128, 0, 0), (2, 16, 16, 256, 128, 0), (2, 16, 16, 128, 64, 0), (3, 8, 8, 256, 0, 1),
+              (3, 8, 8, 256, 0, 2), (2, 16, 16, 128, 0, 3), (2, 4, 4, 256, 0, 4), (5, 4, 4, 256, 256, 0),
+              (2, 32, 32, 64, 0, 1)]
+
+
+@pytest.mark.parametrize("case", NORM_CASES, ids=[f"b{c[0]}_{c[1]}_{c[3]}+{c[4]}_rs{c[5]}" for c in NORM_CASES])
+@pytest.mark.parametrize("silu", [True, False])
+def test_group_norm_swish_resample(case, silu):
+  B, H, W, C1, C2, rs = case
+  g = torch.Generator().manual_seed(H * C1 + rs)
+  x1 = torch.randn(B, H, W, C1, generator=g) * 2 + 0.3
+  x2 = torch.randn(B, H, W, C2, generator=g) if C2 else None
+  Ct = C1 + C2
+  gamma, beta = 1 + 0.1 * torch.randn(Ct, generator=g), 0.1 * torch.randn(Ct, generator=g)
+  dst, raw = ops.group_norm(x1.cuda(), gamma.cuda(), beta.cuda(), silu=silu, resample=rs,
+                            x2=None if x2 is None else x2.cuda(), want_raw=True)
+  x = (x1 if x2 is None else torch.cat([x1, x2], -1)).double().permute(0, 3, 1, 2)
+  h = F.group_norm(x, min(Ct // 4, 32), gamma.double(), beta.double(), eps=1e-6)
+  if silu:
+    h = on.swish(h)
+  fn = {0: lambda t: t, 1: lambda t: on.downsample_2d(t, (1, 3, 3, 1)), 2: lambda t: on.upsample_2d(t, (1, 3, 3, 1)),
+        3: on.naive_downsample_2d, 4: on.naive_upsample_2d}[rs]
+  want_n, want_r = fn(h).permute(0, 2, 3, 1), fn(x).permute(0, 2, 3, 1)
+  assert dst.shape == want_n.shape
+  assert rel_l2(dst.float().cpu().numpy(), want_n.numpy()) < 6e-4       # fp16 output rounding ~ 2^-11 / sqrt(3)
+  assert rel_l2(raw.float().cpu().numpy(), want_r.numpy()) < 6e-4
+
+
+@pytest.mark.parametrize("order", [0, 1, 2, 3])
+@pytest.mark.parametrize("as_numpy", [True, False])
+def test_multistep_ab_step(order, as_numpy):
+  rng = np.random.default_rng(order)
+  x = rng.standard_normal((3, 8, 8, 3, 2)).astype(np.float32)
+  e = rng.standard_normal(x.shape).astype(np.float32)
+  hist = rng.standard_normal((order + 1,) + x.shape).astype(np.float32)
+  coef = rng.standard_normal((order + 3, 2, 2)).astype(np.float32)
+  wx, wh = oc.multistep_ab_step(x.astype(np.float64), coef.astype(np.float64), e.astype(np.float64), hist.astype(np.float64))
+  if as_numpy:
+    gx, gh = gdeis.multistep_ab_step(x, coef, e, hist)
+  else:
+    gx, gh = gdeis.multistep_ab_step(torch.as_tensor(x).cuda(), coef, torch.as_tensor(e).cuda(), torch.as_tensor(hist).cuda())
+    gx, gh = gx.cpu().numpy(), gh.cpu().numpy()
+  np.testing.assert_allclose(gx, wx, rtol=0, atol=2e-5)
+  np.testing.assert_array_equal(gh, wh.astype(np.float32))           # history shift is a pure copy: bit exact
+
+
+def test_scalar_ab_step():
+  rng = np.random.default_rng(5)
+  x = rng.standard_normal((4, 32, 32, 3)).astype(np.float32)
+  e = rng.standard_normal(x.shape).astype(np.float32)
+  h = rng.standard_normal((2,) + x.shape).astype(np.float32)
+  c = rng.standard_normal(4).astype(np.float32)
+  wx, wh = ob.ab_step(x.astype(np.float64), c.astype(np.float64), e.astype(np.float64), h.astype(np.float64))
+  gx, gh = gms.ab_step(x, c, e, h)
+  np.testing.assert_allclose(gx, wx, atol=1e-5)
+  np.testing.assert_array_equal(gh, wh.astype(np.float32))
+
+
+@pytest.mark.parametrize("C", [1, 3])
+def test_dct_matches_oracle_and_roundtrips(C):
+  x = np.random.default_rng(C).standard_normal((5, 32, 32, C)).astype(np.float32)
+  y = gblur.batch_img_dct(x)
+  np.testing.assert_allclose(y, ob.batch_img_dct(x.astype(np.float64)), atol=2e-5)
+  np.testing.assert_allclose(gblur.batch_img_idct(y), x, atol=2e-5)
+  np.testing.assert_allclose(gblur.batch_img_idct(x), ob.batch_img_idct(x.astype(np.float64)), atol=2e-5)

@@ -1,0 +1,112 @@
+"""End-to-end sampler parity on the GPU through the reference-shaped Python API (get_sampling_fn /
+get_deis_sampler / get_order0_sampler) against the CPU oracle, on identical prior noise and parameters.
+Tolerance from BASELINE.json north_star: 1e-3 relative L2 on the samples."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from helpers import build, oracle_blur_sample, oracle_cld_sample, prior_u
+from gddim_b200 import net
+from gddim_b200.blur import sampling as bsampling
+from gddim_b200.blur import sde_lib as bsde
+from gddim_b200.cld import sampling, sde_lib
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+inv = lambda x: (x + 1.) / 2.
+
+
+@pytest.mark.parametrize("kind,order,nfe,denoise", [("cld_deep", 0, 6, True), ("cld_deep", 2, 8, True),
+                                                    ("cld_deep", 3, 8, False), ("cld_ddpmpp", 1, 6, True),
+                                                    ("cld_mixed", 2, 7, True)])
+def test_cld_deis_matches_oracle(kind, order, nfe, denoise):
+  cfg, model, net_fn = build(kind)
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_deis_sampler(sde, model, (32, 32, 3), nfe, inv, order, ts_order=2, denoising=denoise, is_p=False)
+  u = prior_u(2, seed=order)
+  x, v, n, tr = fn(0, net.State(model.params), 2, u=u, trace=True)
+  otr = []
+  ox, ov, on_ = oracle_cld_sample(cfg, net_fn, u, nfe, order, denoising=denoise, trace=otr)
+  assert n == on_ == nfe
+  assert tr.shape[0] == len(otr) == (nfe - 1 if denoise else nfe)
+  errs = [rel_l2(tr[i], otr[i]) for i in range(len(otr))]
+  print(f"{kind} order={order} nfe={nfe}: per-step rel_l2 {['%.1e' % e for e in errs]}; "
+        f"x {rel_l2(x, ox):.2e} v {rel_l2(v, ov):.2e}")
+  assert max(errs) < TOL
+  assert rel_l2(x, ox) < TOL and rel_l2(v, ov) < TOL
+  # index-exact coefficient table
+  tab = fn.core.coef_table(model, 2)
+  from oracle import cld as oc
+  o = oc.from_config(cfg)
+  want = o.get_deis_coef(order, oc.get_rev_ts(1.0, 1e-3, 2, nfe - 1 if denoise else nfe))
+  np.testing.assert_allclose(tab, want, rtol=2e-6, atol=1e-9)
+
+
+def test_cld_order0_sampler_matches_oracle():
+  cfg, model, net_fn = build("cld_deep")
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_order0_sampler(sde, model, (32, 32, 3), 6, inv, denoising=True, is_p=False)
+  u = prior_u(2, seed=9)
+  x, v, n = fn(0, model, 2, u=u)
+  ox, ov, _ = oracle_cld_sample(cfg, net_fn, u, 6, 0, denoising=True, method="order0")
+  assert rel_l2(x, ox) < TOL and rel_l2(v, ov) < TOL and n == 6
+
+
+def test_get_sampling_fn_psampler_contract():
+  """config-driven factory, pmapped signature: u (n_dev=1, B, H, W, C, 2) -> xs (1, B, H, W, C)."""
+  cfg, model, net_fn = build("cld_deep")
+  cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "deis", 5, 1
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_sampling_fn(cfg, sde, model, None, inv)
+  u = prior_u(2, seed=4)
+  xs, vs, nfe = fn(np.array([[0, 1]], np.uint32), net.State(model.params), 2, u=u[None])
+  assert xs.shape == (1, 2, 32, 32, 3) and vs.shape == xs.shape and nfe == 5
+  ox, ov, _ = oracle_cld_sample(cfg, net_fn, u, 5, 1)
+  assert rel_l2(xs[0], ox) < TOL
+  # device-resident call returns device tensors with the same values (host path = H2D + same kernels + D2H)
+  xd, vd, _ = fn(None, model, 2, u=torch.as_tensor(u[None]).cuda())
+  assert xd.is_cuda and np.array_equal(xd.cpu().numpy(), xs)
+  # prior drawn inside when u is None
+  x2, _, _ = fn(np.array([[0, 7]], np.uint32), model, 2)
+  assert x2.shape == (1, 2, 32, 32, 3) and np.isfinite(x2).all()
+
+
+def test_graph_replay_equals_eager_launches():
+  cfg, model, _ = build("cld_deep")
+  sde = sde_lib.from_config(cfg)
+  u = prior_u(2, seed=5)
+  a = sampling.get_deis_sampler(sde, model, (32, 32, 3), 6, inv, 2, denoising=True)
+  b = sampling.get_deis_sampler(sde, model, (32, 32, 3), 6, inv, 2, denoising=True)
+  b.core.use_graph = False
+  xa, va, _ = a(0, model, 2, u=u)
+  xb, vb, _ = b(0, model, 2, u=u)
+  assert np.array_equal(xa, xb) and np.array_equal(va, vb)
+  assert a.core.launch_count() == b.core.launch_count() > 0
+  xa2, _, _ = a(0, model, 2, u=u)            # second call replays the captured graphs
+  assert np.array_equal(xa, xa2)
+
+
+def test_blur_order0_matches_oracle():
+  cfg, model, net_fn = build("blur_deep")
+  sde = bsde.from_config(cfg)
+  cfg.sampling.nfe = 6
+  fn = bsampling.get_sampling_fn(cfg, sde, model, None, inv, is_p=False)
+  y = prior_u(2, seed=2, cld=False)
+  x, n, tr = fn(0, model, 2, u=y, trace=True)
+  otr = []
+  ox, on_ = oracle_blur_sample(cfg, net_fn, y, 6, trace=otr)
+  errs = [rel_l2(tr[i], otr[i]) for i in range(6)]
+  print(f"blur per-step rel_l2 {['%.1e' % e for e in errs]}; x {rel_l2(x, ox):.2e}")
+  assert n == on_ == 6 and max(errs) < TOL and rel_l2(x, ox) < TOL
+
+
+def test_non_affine_inverse_scaler_is_applied_in_python():
+  cfg, model, _ = build("cld_deep")
+  sde = sde_lib.from_config(cfg)
+  u = prior_u(2, seed=6)
+  a = sampling.get_deis_sampler(sde, model, (32, 32, 3), 4, lambda x: x, 1, denoising=False)
+  b = sampling.get_deis_sampler(sde, model, (32, 32, 3), 4, lambda x: np.tanh(x), 1, denoising=False)
+  xa, _, _ = a(0, model, 2, u=u)
+  xb, _, _ = b(0, model, 2, u=u)
+  np.testing.assert_allclose(xb, np.tanh(xa), atol=1e-6)
