@@ -40,7 +40,8 @@ class NormDesc(C.Structure):
   _fields_ = [("src1", C.c_void_p), ("c1", C.c_int), ("src2", C.c_void_p), ("c2", C.c_int),
               ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int),
               ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
-              ("silu", C.c_int), ("resample", C.c_int), ("dst16", C.c_void_p), ("raw16", C.c_void_p)]
+              ("silu", C.c_int), ("resample", C.c_int), ("dst16", C.c_void_p), ("raw16", C.c_void_p),
+              ("raw_scale", C.c_float)]
 
 
 CLD_DEIS, CLD_ORDER0, BLUR_ORDER0 = 0, 1, 2

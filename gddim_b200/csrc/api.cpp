@@ -48,6 +48,8 @@ struct gddim_sampler {
   int graph_batch = 0;
   long long kernels_per_forward = 0;
   long long launches = 0;
+  cudaStream_t own_stream = nullptr;   // used when the caller passes the legacy default stream (not capturable)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 extern "C" {
@@ -288,6 +290,7 @@ int gddim_group_norm(const gddim_norm_desc* d, void* stream) {
   n.src1 = d->src1; n.c1 = d->c1; n.src2 = d->src2; n.c2 = d->c2;
   n.B = d->B; n.H = d->H; n.W = d->W; n.groups = d->groups; n.gamma = d->gamma; n.beta = d->beta; n.eps = d->eps;
   n.silu = d->silu; n.resample = d->resample; n.dst16 = (__half*)d->dst16; n.raw16 = (__half*)d->raw16;
+  n.raw_scale = d->raw_scale;
   n.splits = norm_splits(d->B, d->H, d->W);
   float* part = nullptr;
   const size_t nb = (size_t)d->B * n.splits * (d->groups > 0 ? d->groups : 1) * 2 * sizeof(float);
@@ -307,6 +310,10 @@ static void free_sampler_buffers(gddim_sampler* s) {
   cudaFree(s->d_v); cudaFree(s->d_blur_a); cudaFree(s->d_blur_b);
   for (auto p : s->d_eps) cudaFree(p);
   s->d_eps.clear();
+  if (s->own_stream) cudaStreamDestroy(s->own_stream);
+  if (s->ev_in) cudaEventDestroy(s->ev_in);
+  if (s->ev_out) cudaEventDestroy(s->ev_out);
+  s->own_stream = nullptr; s->ev_in = s->ev_out = nullptr;
 }
 
 int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
@@ -477,7 +484,20 @@ int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch
   UNet& net = *s->ctx->net;
   if (batch < 1 || batch > net.max_batch()) return set_err("gddim_sample: batch exceeds the context's max_batch");
   if (cudaSetDevice(s->ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t caller = (cudaStream_t)stream;
+  cudaStream_t st = caller;
+  const bool legacy = (caller == nullptr || caller == cudaStreamLegacy);
+  if (legacy) {
+    if (!s->own_stream) {
+      if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming) != cudaSuccess)
+        return set_err("gddim_sample: stream creation failed");
+    }
+    st = s->own_stream;
+    cudaEventRecord(s->ev_in, caller);          // order after the caller's pending work ...
+    cudaStreamWaitEvent(st, s->ev_in, 0);
+  }
   const long long n_pix = (long long)batch * s->S * s->S;
   const size_t state_elems = (size_t)n_pix * net.net_channels();
   const size_t img_elems = (size_t)n_pix * s->C;
@@ -557,6 +577,10 @@ int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch
   if (host_buffers) {
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return set_err(std::string("gddim_sample: ") + cudaGetErrorString(e));
+  }
+  if (legacy) {                                   // ... and make the caller's stream wait for the results
+    cudaEventRecord(s->ev_out, st);
+    cudaStreamWaitEvent(caller, s->ev_out, 0);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(std::string("gddim_sample: ") + cudaGetErrorString(e));

@@ -75,6 +75,7 @@ struct NormOp {
   int splits;
   __half* dst16;                 // normalised (+act, +resample) output  [B,H',W',C]; may be null
   __half* raw16;                 // raw (resampled) copy of the input in fp16; may be null
+  float raw_scale;               // raw16 = x * raw_scale (power of two: headroom against fp16 overflow)
 };
 int norm_launch(const NormOp* op, cudaStream_t st);
 int norm_splits(int B, int H, int W);
@@ -89,7 +90,7 @@ int head_conv_launch(const __half* in, const float* w /*[3,3,cin,cout]*/, const 
 // FIR (pad 2, [1,3,3,1]x[1,3,3,1]/64) followed by the 3x3 stride-2 VALID window gather:
 // in fp32 [B,H,W,c] -> A16 [B,H/2,W/2,kpad] with k = tap*c + ch (zero padded to kpad)
 int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,
-                           cudaStream_t st);
+                           float out_scale, cudaStream_t st);
 // V^T per image for the PV GEMM: qkv16 [B,T,ld] (V at channel voff) -> vT [B,C,T]
 int transpose_v_launch(const __half* qkv, __half* vT, int B, int T, int C, int ld, int voff, cudaStream_t st);
 // Full attention for very short sequences (T <= 64): qkv16 [B,T,3C] -> o16 [B,T,C]

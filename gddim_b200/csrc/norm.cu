@@ -79,6 +79,7 @@ struct ApplyArgs {
   const float* partial;
   float eps;
   int silu, resample, do_norm;
+  float raw_scale;
   __half* dst16; __half* raw16;
 };
 
@@ -189,7 +190,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
     }
     const long long o = (((long long)b * p.Ho + oy) * p.Wo + ox) * C + c;
     if (p.dst16) store8(p.dst16 + o, accn);
-    if (p.raw16) store8(p.raw16 + o, accr);
+    if (p.raw16) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) accr[k] *= p.raw_scale;
+      store8(p.raw16 + o, accr);
+    }
   }
 }
 
@@ -222,6 +227,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
   a.groups = op->groups; a.splits = op->splits; a.gamma = op->gamma; a.beta = op->beta; a.partial = op->partial;
   a.eps = op->eps; a.silu = op->silu; a.resample = op->resample; a.do_norm = do_norm;
   a.dst16 = op->dst16; a.raw16 = op->raw16;
+  a.raw_scale = op->raw_scale;
   const long long total = (long long)a.Ho * a.Wo * (C / 8);
   int gx = ceil_div(total, 256 * 2);
   if (gx < 1) gx = 1;

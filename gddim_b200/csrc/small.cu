@@ -130,7 +130,8 @@ int head_conv_launch(const __half* in, const float* w, const float* bias, float*
 
 // ---- input pyramid: FIR (pad 2) then 3x3 stride-2 VALID window gather -> GEMM A operand ---------------------
 __global__ void __launch_bounds__(256) im2col_fir_down_kernel(const float* __restrict__ in, __half* __restrict__ a16,
-                                                             int B, int H, int W, int c, int kpad, int use_fir) {
+                                                             int B, int H, int W, int c, int kpad, int use_fir,
+                                                             float out_scale) {
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * Wo * kpad;
   const float kf[4] = {0.125f, 0.375f, 0.375f, 0.125f};
@@ -162,16 +163,16 @@ __global__ void __launch_bounds__(256) im2col_fir_down_kernel(const float* __res
         if (iy < H && ix < W) v = in[((b * H + iy) * W + ix) * c + ch];
       }
     }
-    a16[idx] = __float2half_rn(v);
+    a16[idx] = __float2half_rn(v * out_scale);
   }
 }
 
 int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,
-                           cudaStream_t st) {
+                           float out_scale, cudaStream_t st) {
   const long long total = (long long)B * (H / 2) * (W / 2) * kpad;
   int grid = ceil_div_ll(total, 256);
   if (grid > 148 * 32) grid = 148 * 32;
-  im2col_fir_down_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, kpad, use_fir);
+  im2col_fir_down_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, kpad, use_fir, out_scale);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

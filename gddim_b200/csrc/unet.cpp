@@ -145,13 +145,18 @@ int UNet::set_param(const std::string& name, const float* host, size_t n) {
 
 static float scale0(float s) { return s == 0.f ? 1e-10f : s; }   // layers.py:62
 
+// Raw (un-normalised) activations that feed a GEMM in fp16 -- the shortcut branch and the input pyramid -- are
+// stored divided by 64 and their weights multiplied by 64 (exact power-of-two rescaling): headroom up to
+// |x| ~ 4e6 before fp16 overflows, which matters when a random-weight network lets the reverse-time state grow.
+constexpr float kRawScale = 1.0f / 64.0f;
+
 // conv kernel HWIO (kh,kw,cin,cout) -> K-major [cout][koff + tap*cin + ci] inside rows of length ld
 static void pack_conv(const std::vector<float>& k, int taps, int cin, int cout, std::vector<__half>& dst, int ld,
-                      int koff) {
+                      int koff, float mul = 1.f) {
   for (int tap = 0; tap < taps; ++tap)
     for (int ci = 0; ci < cin; ++ci) {
       const float* src = k.data() + ((size_t)tap * cin + ci) * cout;
-      for (int co = 0; co < cout; ++co) dst[(size_t)co * ld + koff + tap * cin + ci] = __float2half_rn(src[co]);
+      for (int co = 0; co < cout; ++co) dst[(size_t)co * ld + koff + tap * cin + ci] = __float2half_rn(src[co] * mul);
     }
 }
 
@@ -184,6 +189,7 @@ void UNet::add_norm(const T32& in1, const T32* in2, const float* gamma, const fl
   n.splits = norm_splits(max_batch_, in1.H, in1.W);
   n.dst16 = dst ? dst->p : nullptr;
   n.raw16 = raw ? raw->p : nullptr;
+  n.raw_scale = kRawScale;
   ops_.push_back(op);
 }
 
@@ -296,7 +302,7 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     pack_conv(*k1, 9, out_ch, out_ch, pk, ktot, 0);
     std::vector<float> bsum(*b1);
     if (need_sc) {
-      pack_conv(*k2, 1, Cin, out_ch, pk, ktot, 9 * out_ch);
+      pack_conv(*k2, 1, Cin, out_ch, pk, ktot, 9 * out_ch, 1.0f / kRawScale);
       for (int i = 0; i < out_ch; ++i) bsum[i] += (*b2)[i];
     }
     w2 = upload_f16(pk);
@@ -535,7 +541,7 @@ int UNet::walk() {
         else {
           if (!pw || !pb) return -1;
           std::vector<__half> pk((size_t)cout * kpad, __float2half(0.f));
-          pack_conv(*pw, 9, cin, cout, pk, kpad, 0);
+          pack_conv(*pw, 9, cin, cout, pk, kpad, 0, 1.0f / kRawScale);
           wp = upload_f16(pk); bp = upload_f32(*pb);
         }
         T32 np = new32(cout, h.H, h.W);
@@ -730,7 +736,7 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         break;
       case OP_IM2COL:
         rc = im2col_fir_down_launch(op.in_is_external ? x_dev : op.f_in, op.h_out, batch, op.H, op.W, op.cin, op.kpad,
-                                    op.use_fir, st);
+                                    op.use_fir, kRawScale, st);
         launches_ += 1;
         break;
       case OP_TRANSPOSE_V:

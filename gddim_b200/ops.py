@@ -59,7 +59,7 @@ def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residu
 
 
 def group_norm(x, gamma, beta, groups=None, silu=True, resample=0, x2=None, want_raw=False, want_norm=True,
-               eps=1e-6):
+               eps=1e-6, raw_scale=1.0):
   """x (and x2): fp32 [B,H,W,C].  Returns (dst16 or None, raw16 or None)."""
   import torch
   _lib.require_cuda("group_norm")
@@ -76,6 +76,7 @@ def group_norm(x, gamma, beta, groups=None, silu=True, resample=0, x2=None, want
   dst = torch.empty((B, Ho, Wo, Ct), dtype=torch.float16, device="cuda") if want_norm else None
   raw = torch.empty((B, Ho, Wo, Ct), dtype=torch.float16, device="cuda") if want_raw else None
   d.dst16, d.raw16 = _ptr(dst), _ptr(raw)
+  d.raw_scale = raw_scale
   st = torch.cuda.current_stream().cuda_stream
   _lib.check(_lib.lib().gddim_group_norm(C.byref(d), st), "gddim_group_norm")
   return dst, raw

@@ -148,6 +148,7 @@ typedef struct {
   const float* gamma; const float* beta; float eps;
   int silu; int resample;
   void* dst16; void* raw16;
+  float raw_scale;            /* raw16 = x * raw_scale */
 } gddim_norm_desc;
 int gddim_group_norm(const gddim_norm_desc* d, void* stream);
 

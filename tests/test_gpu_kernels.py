@@ -61,7 +61,9 @@ def test_conv3x3_bias_residual_scale(impl, case):
                            bias2=bias2.cuda(), residual=None if res is None else res.cuda(),
                            scale=float(1 / np.sqrt(2.0)), out_fp32=True, out_fp16=True, impl=impl)
   torch.cuda.synchronize()
-  assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
+  e32 = rel_l2(o32.cpu().numpy(), want.numpy())
+  print(f"conv {case} impl={impl}: fp32-out rel_l2={e32:.2e}")
+  assert e32 < 2e-5
   assert rel_l2(o16.float().cpu().numpy(), want.numpy()) < 1e-3
 
 
