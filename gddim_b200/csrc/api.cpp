@@ -292,12 +292,18 @@ int gddim_group_norm(const gddim_norm_desc* d, void* stream) {
   n.silu = d->silu; n.resample = d->resample; n.dst16 = (__half*)d->dst16; n.raw16 = (__half*)d->raw16;
   n.raw_scale = d->raw_scale;
   n.splits = norm_splits(d->B, d->H, d->W);
-  float* part = nullptr;
-  const size_t nb = (size_t)d->B * n.splits * (d->groups > 0 ? d->groups : 1) * 2 * sizeof(float);
-  if (cudaMallocAsync(&part, nb, st) != cudaSuccess) return set_err("gddim_group_norm: scratch allocation failed");
-  n.partial = part;
+  char* scratch = nullptr;
+  const size_t nb_part = (size_t)d->B * n.splits * (d->groups > 0 ? d->groups : 1) * 2 * sizeof(float);
+  const size_t nb_coef = (size_t)d->B * 2 * (d->c1 + d->c2) * sizeof(float);
+  const size_t nb_tick = (size_t)d->B * sizeof(unsigned int);
+  if (cudaMallocAsync(&scratch, nb_part + nb_coef + nb_tick, st) != cudaSuccess)
+    return set_err("gddim_group_norm: scratch allocation failed");
+  n.partial = (float*)scratch;
+  n.coef = (float*)(scratch + nb_part);
+  n.ticket = (unsigned int*)(scratch + nb_part + nb_coef);
+  cudaMemsetAsync(n.ticket, 0, nb_tick, st);
   const int rc = norm_launch(&n, st);
-  cudaFreeAsync(part, st);
+  cudaFreeAsync(scratch, st);
   if (rc) return set_err("gddim_group_norm: unsupported shape or launch failure (rc=" + std::to_string(rc) + ")");
   return 0;
 }

@@ -56,10 +56,12 @@ struct SmemLayout {
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int STAGES = ((SMEM_BUDGET - BAR_BYTES - 1024) / STAGE_BYTES) > 8
-                                    ? 8
-                                    : ((SMEM_BUDGET - BAR_BYTES - 1024) / STAGE_BYTES);
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+  // epilogue staging: 4 warps x 32 rows x (32 + 4 pad) fp32 -- conflict-free 128-bit transposition
+  static constexpr int EPI_ROW_FLOATS = 36;
+  static constexpr int EPI_BYTES = 4 * 32 * EPI_ROW_FLOATS * 4;
+  static constexpr int AVAIL = SMEM_BUDGET - BAR_BYTES - EPI_BYTES - 1024;
+  static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;   // +1024: alignment slack
 };
 
 template <int BLOCK_N, int EPI>
@@ -81,6 +83,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   uint64_t* tfull_bar = bars + 2 * STAGES;        // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -182,62 +185,65 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N;
       uint32_t r[32];
       if (EPI == EPI_LINEAR) {
-        const float rs = (p.rowscale != nullptr && valid) ? p.rowscale[m] : 1.0f;
+        // TMEM -> registers (thread = row) -> padded smem -> registers (8 lanes = one 32-column row segment),
+        // so that every global access of the epilogue is a full 128-byte line.
+        constexpr int RS = L::EPI_ROW_FLOATS;
+        float* stg = epi_stage + (warp - 2) * 32 * RS;
+        const int rsub = lane >> 3;                    // row within a group of 4
+        const int c4 = (lane & 7) * 4;                 // first of this lane's 4 columns
+        const long long m_base = (long long)mt * BLOCK_M + quad * 32;
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
           ptx::tmem_ld_32x32b_x32(taddr + c0, r);
           ptx::tmem_ld_wait();
-          const int n0 = nt * BLOCK_N + c0;
-          if (valid) {
-            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs;
-            if (p.bias != nullptr) {
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(stg + lane * RS + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          __syncwarp();
+          const int n0 = nt * BLOCK_N + c0 + c4;
+          float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+            bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
+          }
+          if (p.bias2 != nullptr) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0));
+            bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
+          }
+          float4 res[8];
+          if (p.residual != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
+            for (int i = 0; i < 8; ++i) {
+              const long long mm = m_base + i * 4 + rsub;
+              res[i] = (mm < p.M) ? __ldg(reinterpret_cast<const float4*>(p.residual + mm * p.ldo + n0))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (p.bias2 != nullptr) {
+          }
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            const long long mm = m_base + rr;
+            float4 v = *reinterpret_cast<const float4*>(stg + rr * RS + c4);
+            if (p.rowscale != nullptr) {
+              const float rs = (mm < p.M) ? __ldg(p.rowscale + mm) : 1.0f;
+              v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
             }
-            if (p.residual != nullptr) {
-              const float4* rp = reinterpret_cast<const float4*>(p.residual + m * p.ldo + n0);
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(rp + (j >> 2));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= p.scale;
-            if (p.out32 != nullptr) {
-              float4* op = reinterpret_cast<float4*>(p.out32 + m * p.ldo + n0);
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) op[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (p.out16 != nullptr) {
-              uint4* op = reinterpret_cast<uint4*>(p.out16 + m * p.ldo + n0);
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                __half2 h0 = __floats2half2_rn(v[j], v[j + 1]);
-                __half2 h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
-                __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]);
-                __half2 h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
-                uint4 pk;
+            v.x += bsum.x; v.y += bsum.y; v.z += bsum.z; v.w += bsum.w;
+            if (p.residual != nullptr) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+            v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
+            if (mm < p.M) {
+              if (p.out32 != nullptr) *reinterpret_cast<float4*>(p.out32 + mm * p.ldo + n0) = v;
+              if (p.out16 != nullptr) {
+                __half2 h0 = __floats2half2_rn(v.x, v.y);
+                __half2 h1 = __floats2half2_rn(v.z, v.w);
+                uint2 pk;
                 pk.x = *reinterpret_cast<uint32_t*>(&h0);
                 pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                op[j >> 3] = pk;
+                *reinterpret_cast<uint2*>(p.out16 + mm * p.ldo + n0) = pk;
               }
             }
           }
+          __syncwarp();
         }
       } else {
         // row softmax over the BLOCK_N columns of this tile (requires N == BLOCK_N)
@@ -481,9 +487,24 @@ int gemm_prepare(GemmOp* op, int force_block_n) {
     else if (op->N % 64 == 0) bn = 64;
     else if (op->N % 32 == 0) bn = 32;
     else GEMM_FAIL("conv_gemm: N=%d must be a multiple of 32", op->N);
-    // keep at least ~2 tiles per SM when the layer is small
-    const long long mt = (M + BLOCK_M - 1) / BLOCK_M;
-    while (bn > 64 && mt * (op->N / bn) < 2 * 148 && op->epi != EPI_SOFTMAX) bn >>= 1;
+    // Pick the widest tile the layer can feed: wide tiles halve the L2->smem traffic per FLOP (the A tile is
+    // re-read once per N tile) and are MMA-issue efficient; narrow tiles only win when the layer has too few
+    // tiles to occupy the 148 SMs.  Cost model in tensor-pipe cycles per CTA: waves x (mainloop + epilogue).
+    if (op->epi != EPI_SOFTMAX) {
+      const long long mt = (M + BLOCK_M - 1) / BLOCK_M;
+      const int kb = ktot / BLOCK_K;
+      double best = 1e30;
+      int best_bn = bn;
+      for (int cand = bn; cand >= 32; cand >>= 1) {
+        if (op->N % cand != 0) continue;
+        const long long tiles = mt * (op->N / cand);
+        const long long waves = (tiles + 147) / 148;
+        const double mma = (double)kb * 4.0 * (cand >= 64 ? cand / 2.0 : 32.0) * (cand >= 256 ? 1.0 : 1.25);
+        const double cost = (double)waves * (mma + 6.0 * cand + 1500.0);
+        if (cost < best * 0.97) { best = cost; best_bn = cand; }
+      }
+      bn = best_bn;
+    }
   }
   if (op->N % bn != 0) GEMM_FAIL("conv_gemm: N=%d not a multiple of block_n=%d", op->N, bn);
   if (op->epi == EPI_SOFTMAX && (bn != op->N || bn != 256)) GEMM_FAIL("conv_gemm: softmax epilogue needs N == 256");

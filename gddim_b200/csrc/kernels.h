@@ -72,6 +72,8 @@ struct NormOp {
   int silu;                      // apply x*sigmoid(x) after the affine
   int resample;                  // RS_*
   float* partial;                // [B, splits, groups, 2] scratch
+  float* coef;                   // [B, 2, C] scratch: per-channel scale / shift
+  unsigned int* ticket;          // [B] zero-initialised slab counters (self-resetting)
   int splits;
   __half* dst16;                 // normalised (+act, +resample) output  [B,H',W',C]; may be null
   __half* raw16;                 // raw (resampled) copy of the input in fp16; may be null

@@ -5,42 +5,68 @@
 // ncsnpp.py:236.  Statistics: per (image, group) over (H, W, C/G), variance = E[x^2] - E[x]^2,
 // eps = 1e-6 (flax default), groups are contiguous channel blocks.
 //
-// Memory-bound, no tensor-core path: pass 1 reads the fp32 source once (float4, coalesced) and writes
-// deterministic per-slab partial sums; pass 2 reads it again, applies scale/shift/swish in registers,
-// optionally gathers the 4x4 (down) or 2x2 (up) FIR footprint, and writes 16-byte fp16 vectors.
+// Memory-bound, no tensor-core path.
+//   pass 1  gn_stats_kernel   reads the fp32 source once (float4, 4 loads in flight per thread), writes
+//                             per-slab partial sums; the last slab of an image (atomic ticket) folds them in a
+//                             fixed order into per-channel scale/shift  a = rstd*gamma, b = beta - mean*a
+//   pass 2  gn_apply_kernel   reads the source again, y = act(a*x + b) in registers (8 channels per thread,
+//                             coefficients held in registers across pixels), optional 4x4 / 2x2 FIR gather,
+//                             16-byte fp16 stores.  Also emits the raw (resampled) fp16 copy for shortcut convs.
 #include <cstdio>
 
 #include "kernels.h"
 
 namespace gddim {
 
-static int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
-
 int norm_splits(int B, int H, int W) {
   const int P = H * W;
   int s = 1;
-  // aim for >= 2 waves of 148 SMs, keep >= 16 pixels per slab
-  while (s < 32 && (long long)B * s < 592 && P / (s * 2) >= 16) s *= 2;
+  // aim for >= 4 CTAs per SM (148 SMs), keep >= 32 pixels per slab
+  while (s < 32 && (long long)B * s < 148 * 4 && P / (s * 2) >= 32) s *= 2;
   return s;
 }
 
-__global__ void gn_partial_kernel(const float* __restrict__ src1, int c1, const float* __restrict__ src2, int c2,
-                                  int P, int groups, int splits, int rows, float* __restrict__ partial) {
+struct StatsArgs {
+  const float* src1; int c1;
+  const float* src2; int c2;
+  int P, groups, splits, rows;
+  float inv_n, eps;
+  const float* gamma; const float* beta;
+  float* partial;          // [B, splits, groups, 2]
+  float* coef;             // [B, 2, C]  (a then b)
+  unsigned int* ticket;    // [B], zero between launches
+};
+
+__global__ void __launch_bounds__(1024) gn_stats_kernel(const StatsArgs p) {
   extern __shared__ float sm[];   // [threads][8]: per-channel sum[4], sumsq[4]
-  const int C = c1 + c2;
+  __shared__ int s_last;
+  const int C = p.c1 + p.c2;
   const int nv = C / 4;
   const int b = blockIdx.y, split = blockIdx.x;
   const int vi = threadIdx.x % nv, row = threadIdx.x / nv;
-  const int pp = P / splits;
+  const int pp = p.P / p.splits;
   const int pbeg = split * pp;
   const int c = vi * 4;
   const float* base;
-  int cs, cc;
-  if (c < c1) { base = src1 + (long long)b * P * c1; cs = c1; cc = c; }
-  else { base = src2 + (long long)b * P * c2; cs = c2; cc = c - c1; }
+  int cs;
+  if (c < p.c1) { base = p.src1 + (long long)b * p.P * p.c1 + c; cs = p.c1; }
+  else { base = p.src2 + (long long)b * p.P * p.c2 + (c - p.c1); cs = p.c2; }
   float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int pix = pbeg + row; pix < pbeg + pp; pix += rows) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)pix * cs + cc));
+  int pix = pbeg + row;
+  const int pend = pbeg + pp;
+  const int rows = p.rows;
+  for (; pix + 3 * rows < pend; pix += 4 * rows) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(base + (long long)(pix + k * rows) * cs));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[0] += v[k].x; s[1] += v[k].y; s[2] += v[k].z; s[3] += v[k].w;
+      ss[0] += v[k].x * v[k].x; ss[1] += v[k].y * v[k].y; ss[2] += v[k].z * v[k].z; ss[3] += v[k].w * v[k].w;
+    }
+  }
+  for (; pix < pend; pix += rows) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(base + (long long)pix * cs));
     s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
     ss[0] += v.x * v.x; ss[1] += v.y * v.y; ss[2] += v.z * v.z; ss[3] += v.w * v.w;
   }
@@ -51,8 +77,8 @@ __global__ void gn_partial_kernel(const float* __restrict__ src1, int c1, const 
   }
   __syncthreads();
   // fixed-order (deterministic) reduction: one thread per group walks its channels and pixel rows
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    const int cpg = C / groups;
+  const int cpg = C / p.groups;
+  for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
     float ts = 0.f, tss = 0.f;
     for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) {
       const int v = ch >> 2, j = ch & 3;
@@ -62,9 +88,34 @@ __global__ void gn_partial_kernel(const float* __restrict__ src1, int c1, const 
         tss += sm[t * 8 + 4 + j];
       }
     }
-    float* o = partial + (((long long)b * splits + split) * groups + g) * 2;
+    float* o = p.partial + (((long long)b * p.splits + split) * p.groups + g) * 2;
     o[0] = ts;
     o[1] = tss;
+  }
+  // the last slab of this image turns the partial sums into per-channel scale / shift
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&p.ticket[b], 1u);
+    s_last = (t == (unsigned int)(p.splits - 1));
+    if (s_last) p.ticket[b] = 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const int g = ch / cpg;
+    float ts = 0.f, tss = 0.f;
+    for (int k = 0; k < p.splits; ++k) {
+      const float* q = p.partial + (((long long)b * p.splits + k) * p.groups + g) * 2;
+      ts += __ldcg(q);
+      tss += __ldcg(q + 1);
+    }
+    const float mean = ts * p.inv_n;
+    const float var = fmaxf(tss * p.inv_n - mean * mean, 0.f);
+    const float a = rsqrtf(var + p.eps) * p.gamma[ch];
+    p.coef[((long long)b * 2) * C + ch] = a;
+    p.coef[((long long)b * 2 + 1) * C + ch] = p.beta[ch] - mean * a;
   }
 }
 
@@ -74,12 +125,11 @@ struct ApplyArgs {
   const float* src1; int c1;
   const float* src2; int c2;
   int H, W, Ho, Wo;
-  int groups, splits;
-  const float* gamma; const float* beta;
-  const float* partial;
-  float eps;
-  int silu, resample, do_norm;
+  const float* coef;       // [B, 2, C]
+  int silu, do_norm;
   float raw_scale;
+  int rows;                // pixel rows handled concurrently by a CTA (blockDim.x = rows * C/8)
+  int pix_per_cta;
   __half* dst16; __half* raw16;
 };
 
@@ -96,76 +146,107 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = pk;
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
-  extern __shared__ float sm[];   // a[C], b[C]
-  const int C = p.c1 + p.c2;
-  float* sa = sm;
-  float* sb = sm + C;
-  const int b = blockIdx.y;
-  if (p.do_norm) {
-    const int cpg = C / p.groups;
-    const float inv_n = 1.0f / (float(p.H) * float(p.W) * float(cpg));
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int g = c / cpg;
-      float s = 0.f, ss = 0.f;
-      for (int k = 0; k < p.splits; ++k) {
-        const float* q = p.partial + (((long long)b * p.splits + k) * p.groups + g) * 2;
-        s += q[0];
-        ss += q[1];
-      }
-      const float mean = s * inv_n;
-      const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.eps);
-      const float a = rstd * p.gamma[c];
-      sa[c] = a;
-      sb[c] = p.beta[c] - mean * a;
-    }
-    __syncthreads();
+template <int RS>
+__device__ __forceinline__ void tap_table(int oy, int ox, int& ny, int& nx, int& y0, int& x0, float (&wy)[4],
+                                          float (&wx)[4]) {
+  if (RS == RS_FIR_DOWN) {
+    ny = nx = 4; y0 = 2 * oy - 1; x0 = 2 * ox - 1;
+    wy[0] = wx[0] = 0.125f; wy[1] = wx[1] = 0.375f; wy[2] = wx[2] = 0.375f; wy[3] = wx[3] = 0.125f;
+  } else if (RS == RS_FIR_UP) {
+    ny = nx = 2;
+    if (oy & 1) { y0 = oy >> 1; wy[0] = 0.75f; wy[1] = 0.25f; } else { y0 = (oy >> 1) - 1; wy[0] = 0.25f; wy[1] = 0.75f; }
+    if (ox & 1) { x0 = ox >> 1; wx[0] = 0.75f; wx[1] = 0.25f; } else { x0 = (ox >> 1) - 1; wx[0] = 0.25f; wx[1] = 0.75f; }
+  } else if (RS == RS_NAIVE_DOWN) {
+    ny = nx = 2; y0 = 2 * oy; x0 = 2 * ox; wy[0] = wy[1] = wx[0] = wx[1] = 0.5f;
+  } else if (RS == RS_NAIVE_UP) {
+    ny = nx = 1; y0 = oy >> 1; x0 = ox >> 1; wy[0] = wx[0] = 1.f;
+  } else {
+    ny = nx = 1; y0 = oy; x0 = ox; wy[0] = wx[0] = 1.f;
   }
+}
+
+template <int RS>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
+  const int C = p.c1 + p.c2;
   const int nv = C / 8;
-  const long long total = (long long)p.Ho * p.Wo * nv;
-  const float* base1 = p.src1 + (long long)b * p.H * p.W * p.c1;
-  const float* base2 = p.src2 ? p.src2 + (long long)b * p.H * p.W * p.c2 : nullptr;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int vi = int(idx % nv);
-    const int opix = int(idx / nv);
-    const int ox = opix % p.Wo, oy = opix / p.Wo;
-    const int c = vi * 8;
-    const float* base; int cs, cc;
-    if (c < p.c1) { base = base1; cs = p.c1; cc = c; } else { base = base2; cs = p.c2; cc = c - p.c1; }
-    float a[8], bb[8];
-    if (p.do_norm) {
+  const int b = blockIdx.y;
+  const int vi = threadIdx.x % nv, row = threadIdx.x / nv;
+  const int c = vi * 8;
+  const float* base; int cs;
+  if (c < p.c1) { base = p.src1 + (long long)b * p.H * p.W * p.c1 + c; cs = p.c1; }
+  else { base = p.src2 + (long long)b * p.H * p.W * p.c2 + (c - p.c1); cs = p.c2; }
+  float a[8], bb[8];
+  if (p.do_norm) {
+    const float4* ca = reinterpret_cast<const float4*>(p.coef + ((long long)b * 2) * C + c);
+    const float4* cb = reinterpret_cast<const float4*>(p.coef + ((long long)b * 2 + 1) * C + c);
+    const float4 a0 = ca[0], a1 = ca[1], b0 = cb[0], b1 = cb[1];
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+  }
+  const int Pout = p.Ho * p.Wo;
+  const int pbeg = blockIdx.x * p.pix_per_cta;
+  const int pend = min(pbeg + p.pix_per_cta, Pout);
+  __half* dst = p.dst16 ? p.dst16 + (long long)b * Pout * C + c : nullptr;
+  __half* raw = p.raw16 ? p.raw16 + (long long)b * Pout * C + c : nullptr;
+
+  if (RS == RS_NONE) {
+    // straight path: 4 pixels in flight per thread
+    int pix = pbeg + row;
+    for (; pix + 3 * p.rows < pend; pix += 4 * p.rows) {
+      float4 v[4][2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a[j] = sa[c + j]; bb[j] = sb[c + j]; }
+      for (int k = 0; k < 4; ++k) {
+        const float* q = base + (long long)(pix + k * p.rows) * cs;
+        v[k][0] = __ldg(reinterpret_cast<const float4*>(q));
+        v[k][1] = __ldg(reinterpret_cast<const float4*>(q + 4));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x[8] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w, v[k][1].x, v[k][1].y, v[k][1].z, v[k][1].w};
+        const long long o = (long long)(pix + k * p.rows) * C;
+        if (dst) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { y[j] = x[j] * a[j] + bb[j]; if (p.silu) y[j] = silu_f(y[j]); }
+          store8(dst + o, y);
+        }
+        if (raw) {
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[j] = x[j] * p.raw_scale;
+          store8(raw + o, y);
+        }
+      }
     }
+    for (; pix < pend; pix += p.rows) {
+      const float* q = base + (long long)pix * cs;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(q)), v1 = __ldg(reinterpret_cast<const float4*>(q + 4));
+      const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      const long long o = (long long)pix * C;
+      if (dst) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { y[j] = x[j] * a[j] + bb[j]; if (p.silu) y[j] = silu_f(y[j]); }
+        store8(dst + o, y);
+      }
+      if (raw) {
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = x[j] * p.raw_scale;
+        store8(raw + o, y);
+      }
+    }
+    return;
+  }
+
+  for (int pix = pbeg + row; pix < pend; pix += p.rows) {
+    const int ox = pix % p.Wo, oy = pix / p.Wo;
+    int ny, nx, y0, x0;
+    float wy[4], wx[4];
+    tap_table<RS>(oy, ox, ny, nx, y0, x0, wy, wx);
     float accn[8], accr[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { accn[j] = 0.f; accr[j] = 0.f; }
-
-    // tap enumeration
-    int ny, nx, y0, x0;
-    float wy[4], wx[4];
-    switch (p.resample) {
-      case RS_FIR_DOWN:
-        ny = nx = 4; y0 = 2 * oy - 1; x0 = 2 * ox - 1;
-        wy[0] = wx[0] = 0.125f; wy[1] = wx[1] = 0.375f; wy[2] = wx[2] = 0.375f; wy[3] = wx[3] = 0.125f;
-        break;
-      case RS_FIR_UP:
-        ny = nx = 2;
-        if (oy & 1) { y0 = oy >> 1; wy[0] = 0.75f; wy[1] = 0.25f; } else { y0 = (oy >> 1) - 1; wy[0] = 0.25f; wy[1] = 0.75f; }
-        if (ox & 1) { x0 = ox >> 1; wx[0] = 0.75f; wx[1] = 0.25f; } else { x0 = (ox >> 1) - 1; wx[0] = 0.25f; wx[1] = 0.75f; }
-        break;
-      case RS_NAIVE_DOWN:
-        ny = nx = 2; y0 = 2 * oy; x0 = 2 * ox; wy[0] = wy[1] = wx[0] = wx[1] = 0.5f;
-        break;
-      case RS_NAIVE_UP:
-        ny = nx = 1; y0 = oy >> 1; x0 = ox >> 1; wy[0] = wx[0] = 1.f;
-        break;
-      default:
-        ny = nx = 1; y0 = oy; x0 = ox; wy[0] = wx[0] = 1.f;
-        break;
-    }
     for (int i = 0; i < ny; ++i) {
       const int iy = y0 + i;
       if (iy < 0 || iy >= p.H) continue;
@@ -173,7 +254,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
         const int ix = x0 + j;
         if (ix < 0 || ix >= p.W) continue;
         const float w = wy[i] * wx[j];
-        const float* q = base + ((long long)iy * p.W + ix) * cs + cc;
+        const float* q = base + ((long long)iy * p.W + ix) * cs;
         const float4 v0 = __ldg(reinterpret_cast<const float4*>(q));
         const float4 v1 = __ldg(reinterpret_cast<const float4*>(q + 4));
         const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -188,12 +269,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
         }
       }
     }
-    const long long o = (((long long)b * p.Ho + oy) * p.Wo + ox) * C + c;
-    if (p.dst16) store8(p.dst16 + o, accn);
-    if (p.raw16) {
+    const long long o = (long long)pix * C;
+    if (dst) store8(dst + o, accn);
+    if (raw) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) accr[k] *= p.raw_scale;
-      store8(p.raw16 + o, accr);
+      store8(raw + o, accr);
     }
   }
 }
@@ -201,20 +282,26 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
 int norm_launch(const NormOp* op, cudaStream_t st) {
   const int C = op->c1 + op->c2;
   const int do_norm = op->dst16 != nullptr;
-  if (C % 8 != 0 || op->c1 % 8 != 0) return -1;
+  if (C % 8 != 0 || op->c1 % 8 != 0 || C > 2048) return -1;
+  const int P = op->H * op->W;
   if (do_norm) {
-    if (C % op->groups != 0 || C % 4 != 0) return -2;
+    if (C % op->groups != 0) return -2;
+    if (!op->partial || !op->coef || !op->ticket) return -5;
     const int nv = C / 4;
     int rows = 256 / nv;
     if (rows < 1) rows = 1;
-    const int P = op->H * op->W;
     const int pp = P / op->splits;
     if (rows > pp) rows = pp;
     if (nv * rows > 1024 || P % op->splits != 0) return -3;
     const int threads = nv * rows;
+    StatsArgs s;
+    s.src1 = op->src1; s.c1 = op->c1; s.src2 = op->src2; s.c2 = op->c2;
+    s.P = P; s.groups = op->groups; s.splits = op->splits; s.rows = rows;
+    s.inv_n = 1.0f / ((float)P * (float)(C / op->groups));
+    s.eps = op->eps; s.gamma = op->gamma; s.beta = op->beta;
+    s.partial = op->partial; s.coef = op->coef; s.ticket = op->ticket;
     dim3 grid(op->splits, op->B);
-    gn_partial_kernel<<<grid, threads, threads * 8 * sizeof(float), st>>>(op->src1, op->c1, op->src2, op->c2, P,
-                                                                          op->groups, op->splits, rows, op->partial);
+    gn_stats_kernel<<<grid, threads, threads * 8 * sizeof(float), st>>>(s);
   }
   ApplyArgs a;
   a.src1 = op->src1; a.c1 = op->c1; a.src2 = op->src2; a.c2 = op->c2;
@@ -224,15 +311,28 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     case RS_FIR_UP: case RS_NAIVE_UP: a.Ho = op->H * 2; a.Wo = op->W * 2; break;
     default: a.Ho = op->H; a.Wo = op->W; break;
   }
-  a.groups = op->groups; a.splits = op->splits; a.gamma = op->gamma; a.beta = op->beta; a.partial = op->partial;
-  a.eps = op->eps; a.silu = op->silu; a.resample = op->resample; a.do_norm = do_norm;
+  a.coef = op->coef; a.silu = op->silu; a.do_norm = do_norm; a.raw_scale = op->raw_scale;
   a.dst16 = op->dst16; a.raw16 = op->raw16;
-  a.raw_scale = op->raw_scale;
-  const long long total = (long long)a.Ho * a.Wo * (C / 8);
-  int gx = ceil_div(total, 256 * 2);
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, op->B);
-  gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>(a);
+  const int nv8 = C / 8;
+  int rows = 256 / nv8;
+  if (rows < 1) rows = 1;
+  const int Pout = a.Ho * a.Wo;
+  if (rows > Pout) rows = Pout;
+  a.rows = rows;
+  // 8 pixels per thread (2 unrolled rounds), but never fewer than ~2 CTAs per SM overall
+  int ppc = rows * 8;
+  while (ppc > rows && (long long)op->B * ((Pout + ppc - 1) / ppc) < 148 * 2) ppc >>= 1;
+  a.pix_per_cta = ppc;
+  dim3 grid((Pout + ppc - 1) / ppc, op->B);
+  const int threads = rows * nv8;
+  switch (op->resample) {
+    case RS_NONE: gn_apply_kernel<RS_NONE><<<grid, threads, 0, st>>>(a); break;
+    case RS_FIR_DOWN: gn_apply_kernel<RS_FIR_DOWN><<<grid, threads, 0, st>>>(a); break;
+    case RS_FIR_UP: gn_apply_kernel<RS_FIR_UP><<<grid, threads, 0, st>>>(a); break;
+    case RS_NAIVE_DOWN: gn_apply_kernel<RS_NAIVE_DOWN><<<grid, threads, 0, st>>>(a); break;
+    case RS_NAIVE_UP: gn_apply_kernel<RS_NAIVE_UP><<<grid, threads, 0, st>>>(a); break;
+    default: return -6;
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 

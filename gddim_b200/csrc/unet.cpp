@@ -186,6 +186,8 @@ void UNet::add_norm(const T32& in1, const T32* in2, const float* gamma, const fl
   n.silu = silu ? 1 : 0;
   n.resample = resample;
   n.partial = gn_partial_;
+  n.coef = gn_coef_;
+  n.ticket = gn_ticket_;
   n.splits = norm_splits(max_batch_, in1.H, in1.W);
   n.dst16 = dst ? dst->p : nullptr;
   n.raw16 = raw ? raw->p : nullptr;
@@ -481,6 +483,8 @@ int UNet::walk() {
   d_temb1_ = (float*)w_alloc(temb_dim_ * 4);
   d_temb2_ = (float*)w_alloc(temb_dim_ * 4);
   gn_partial_ = (float*)w_alloc((size_t)max_batch_ * 32 * 32 * 2 * 4);
+  gn_coef_ = (float*)w_alloc((size_t)max_batch_ * 2 * 2048 * 4);
+  gn_ticket_ = (unsigned int*)w_alloc((size_t)max_batch_ * 4);
   // temb_cur_: capacity known from the dry pass (first pass: generous upper bound is unnecessary -- the
   // pointer is only used as an address; its size is fixed in finalize()).
   temb_cur_ = (float*)w_alloc((size_t)(dry_ ? 1 : proj_b_host_.size()) * 4 + 16);

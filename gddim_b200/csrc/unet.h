@@ -113,6 +113,8 @@ class UNet {
   float *d_temb0_ = nullptr, *d_temb1_ = nullptr, *d_temb2_ = nullptr;
   float* temb_cur_ = nullptr;
   float* gn_partial_ = nullptr;
+  float* gn_coef_ = nullptr;
+  unsigned int* gn_ticket_ = nullptr;
 
   // walk
   const std::vector<float>* param(Scope& s, const std::string& name, std::vector<int> shape, int kind, float scale);

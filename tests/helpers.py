@@ -43,6 +43,12 @@ def build(kind, nondegenerate=True, seed=1234):
   return _cache[key]
 
 
+def build_oracle_only(kind, nondegenerate=True, seed=1234):
+  """-> (cfg, oracle net_fn) without touching the CUDA library's context (specs still come from its walk)."""
+  cfg, _, net_fn = build(kind, nondegenerate, seed)
+  return cfg, net_fn
+
+
 def oracle_cld_sample(cfg, net_fn, u, nfe, order, denoising=True, method="deis", trace=None):
   sde = oc.from_config(cfg)
   eps_fn = oc.make_eps_fn(sde, net_fn)

@@ -8,7 +8,7 @@ timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "ref or grou
 echo "== stage B: tcgen05 kernels ==" | tee -a gpurun_out/ci.log
 timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "umma" 2>&1 | tail -40 | tee -a gpurun_out/ci.log
 echo "== stage C: network + samplers ==" | tee -a gpurun_out/ci.log
-timeout 900 python -m pytest tests/test_gpu_net.py tests/test_gpu_sampler.py -m gpu -q -s > gpurun_out/stageC.log 2>&1; tail -30 gpurun_out/stageC.log | tee -a gpurun_out/ci.log
+timeout 900 python -m pytest tests/test_gpu_net.py tests/test_gpu_sampler.py tests/test_golden.py -m gpu -q -s > gpurun_out/stageC.log 2>&1; tail -30 gpurun_out/stageC.log | tee -a gpurun_out/ci.log
 echo "== done ==" | tee -a gpurun_out/ci.log
 if [ "$1" = "bench" ]; then
   echo "== bench ==" | tee -a gpurun_out/ci.log
