@@ -49,34 +49,38 @@ struct GemmArgs {
   __half* out16;
   float* row_out;
   int ldo;
+  float* colstats;
 };
 
-template <int BLOCK_N>
+// MT = number of 128-row M sub-tiles a CTA tile covers (2 for narrow N: the weight tile is then shared by 256
+// output rows, which halves the L2->smem operand traffic per FLOP of the N <= 128 layers)
+template <int BLOCK_N, int MT>
 struct SmemLayout {
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGE_BYTES = MT * A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_BYTES = 1024;
   // epilogue staging: 4 warps x 32 rows x (32 + 4 pad) fp32 -- conflict-free 128-bit transposition
   static constexpr int EPI_ROW_FLOATS = 36;
-  static constexpr int EPI_BYTES = 4 * 32 * EPI_ROW_FLOATS * 4;
+  static constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_ROW_FLOATS * 4;
+  static constexpr int EPI_BYTES = EPI_STAGE_BYTES + 4 * BLOCK_N * 4;   // + per-warp (bias + bias2) row
   static constexpr int AVAIL = SMEM_BUDGET - BAR_BYTES - EPI_BYTES - 1024;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;   // +1024: alignment slack
 };
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
-  using L = SmemLayout<BLOCK_N>;
+  using L = SmemLayout<BLOCK_N, MT>;
   constexpr int STAGES = L::STAGES;
-  constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);   // 2 accumulator stages
+  constexpr uint32_t TMEM_COLS = (2 * MT * BLOCK_N) < 32 ? 32 : (2 * MT * BLOCK_N);   // 2 accumulator stages
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_TILE_BYTES;
+  uint8_t* sB = smem + STAGES * MT * A_TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
   uint64_t* full_bar = bars;                      // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;            // [STAGES]  MMA -> TMA
@@ -84,6 +88,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES);
+  float* epi_bias = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES + L::EPI_STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -120,10 +125,14 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-      const int p0 = mt * BLOCK_M;
-      const int w0 = p0 % p.W;
-      const int h0 = (p0 / p.W) % p.H;
-      const int b0 = p0 / (p.W * p.H);
+      int w0[MT], h0[MT], b0[MT];
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) {
+        const int p0 = (mt * MT + mi) * BLOCK_M;
+        w0[mi] = p0 % p.W;
+        h0[mi] = (p0 / p.W) % p.H;
+        b0[mi] = p0 / (p.W * p.H);
+      }
       const int bidx = p.tiles_per_batch > 0 ? mt / p.tiles_per_batch : 0;
       int kb = 0;
       for (int s = 0; s < p.nseg; ++s) {
@@ -134,8 +143,10 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           for (int kc = 0; kc < p.kch[s]; ++kc, ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-            ptx::tma_load_4d(tm, &full_bar[stage], sA + stage * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K, w0 + dx,
-                             h0 + dy, b0);
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi)
+              ptx::tma_load_4d(tm, &full_bar[stage], sA + (stage * MT + mi) * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K,
+                               w0[mi] + dx, h0[mi] + dy, b0[mi]);
             ptx::tma_load_4d(&tmB, &full_bar[stage], sB + stage * L::B_TILE_BYTES, p.w_koff + kb * BLOCK_K,
                              nt * BLOCK_N, bidx, 0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -153,16 +164,19 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      const uint32_t d_tmem = tmem_base + acc * MT * BLOCK_N;
       for (int kb = 0; kb < kblocks; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sA + stage * A_TILE_BYTES));
         const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sB + stage * L::B_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 fp16 = 32 bytes inside the swizzle row: +2 in the 16-byte-granular address field
-          ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        for (int mi = 0; mi < MT; ++mi) {
+          const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sA + (stage * MT + mi) * A_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 fp16 = 32 bytes inside the swizzle row: +2 in the 16-byte-granular address field
+            ptx::umma_f16(d_tmem + mi * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
         }
         ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -178,47 +192,64 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
-      const long long m = (long long)mt * BLOCK_M + row;
+      const long long m = (long long)mt * MT * BLOCK_M + row;
       const bool valid = m < p.M;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N;
       uint32_t r[32];
       if (EPI == EPI_LINEAR) {
         // TMEM -> registers (thread = row) -> padded smem -> registers (8 lanes = one 32-column row segment),
-        // so that every global access of the epilogue is a full 128-byte line.
+        // so that every global access of the epilogue is a full 128-byte line.  Everything that does not depend
+        // on the accumulator (bias row, first residual chunk) is fetched before waiting for the MMAs, and the
+        // residual of chunk q+1 is in flight while chunk q is processed: the epilogue warps have no peers to
+        // hide latency behind (one warp per scheduler), so the overlap has to be explicit.
         constexpr int RS = L::EPI_ROW_FLOATS;
+        constexpr int NCH = BLOCK_N / 32;
+        constexpr int NQ = MT * NCH;
         float* stg = epi_stage + (warp - 2) * 32 * RS;
+        float* bias_s = epi_bias + (warp - 2) * BLOCK_N;
         const int rsub = lane >> 3;                    // row within a group of 4
         const int c4 = (lane & 7) * 4;                 // first of this lane's 4 columns
-        const long long m_base = (long long)mt * BLOCK_M + quad * 32;
+        for (int j = lane * 4; j < BLOCK_N; j += 128) {
+          float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + j));
+            bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
+          }
+          if (p.bias2 != nullptr) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias2 + nt * BLOCK_N + j));
+            bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
+          }
+          *reinterpret_cast<float4*>(bias_s + j) = bsum;
+        }
+        auto load_res = [&](int q, float4 (&res)[8]) {
+          const long long mb = ((long long)mt * MT + q / NCH) * BLOCK_M + quad * 32;
+          const int n0 = nt * BLOCK_N + (q % NCH) * 32 + c4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long mm = mb + i * 4 + rsub;
+            res[i] = (mm < p.M) ? __ldg(reinterpret_cast<const float4*>(p.residual + mm * p.ldo + n0))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        float4 res[8], res_next[8];
+        if (p.residual != nullptr) load_res(0, res);
+        __syncwarp();
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+        for (int q = 0; q < NQ; ++q) {
+          const int mi = q / NCH, c0 = (q % NCH) * 32;
+          const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + (acc * MT + mi) * BLOCK_N + c0;
+          const long long m_base = ((long long)mt * MT + mi) * BLOCK_M + quad * 32;
+          ptx::tmem_ld_32x32b_x32(taddr, r);
+          if (p.residual != nullptr && q + 1 < NQ) load_res(q + 1, res_next);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<uint4*>(stg + lane * RS + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
           __syncwarp();
           const int n0 = nt * BLOCK_N + c0 + c4;
-          float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
-            bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
-          }
-          if (p.bias2 != nullptr) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0));
-            bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
-          }
-          float4 res[8];
-          if (p.residual != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const long long mm = m_base + i * 4 + rsub;
-              res[i] = (mm < p.M) ? __ldg(reinterpret_cast<const float4*>(p.residual + mm * p.ldo + n0))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
+          const float4 bsum = *reinterpret_cast<const float4*>(bias_s + c0 + c4);
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + rsub;
@@ -232,6 +263,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             if (p.residual != nullptr) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
             v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
             if (mm < p.M) {
+              cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+              cq.x += v.x * v.x; cq.y += v.y * v.y; cq.z += v.z * v.z; cq.w += v.w * v.w;
               if (p.out32 != nullptr) *reinterpret_cast<float4*>(p.out32 + mm * p.ldo + n0) = v;
               if (p.out16 != nullptr) {
                 __half2 h0 = __floats2half2_rn(v.x, v.y);
@@ -243,10 +276,32 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
               }
             }
           }
+          if (p.colstats != nullptr) {
+            // fold the 4 row sub-groups (lanes l, l+8, l+16, l+24): lanes 0..7 then own 32 rows x 4 columns
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+              cq.x += __shfl_xor_sync(0xffffffffu, cq.x, o); cq.y += __shfl_xor_sync(0xffffffffu, cq.y, o);
+              cq.z += __shfl_xor_sync(0xffffffffu, cq.z, o); cq.w += __shfl_xor_sync(0xffffffffu, cq.w, o);
+            }
+            if (lane < 8 && m_base < p.M) {
+              const long long slab = m_base >> 5;
+              *reinterpret_cast<float4*>(p.colstats + (slab * 2) * p.ldo + n0) = cs;
+              *reinterpret_cast<float4*>(p.colstats + (slab * 2 + 1) * p.ldo + n0) = cq;
+            }
+          }
           __syncwarp();
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = res_next[i];
+          }
         }
       } else {
-        // row softmax over the BLOCK_N columns of this tile (requires N == BLOCK_N)
+        // row softmax over the BLOCK_N columns of this tile (requires N == BLOCK_N, MT == 1)
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N;
         const float sc = p.scale * 1.4426950408889634f;     // exp(x) = exp2(x * log2 e)
         float mx = -INFINITY;
 #pragma unroll 1
@@ -326,6 +381,7 @@ struct RefArgs {
   int ldo;
   int epi;
   float* softmax_tmp;            // [M, N] scratch for the softmax epilogue
+  float* colstats;
 };
 
 __global__ void __launch_bounds__(256) conv_gemm_ref_kernel(const RefArgs p) {
@@ -412,6 +468,22 @@ __global__ void __launch_bounds__(256) conv_gemm_ref_kernel(const RefArgs p) {
   }
 }
 
+// column statistics of the reference path's fp32 output (same layout as the fused epilogue's)
+__global__ void colstats_ref_kernel(const float* out32, float* colstats, int M, int N, int ldo) {
+  const int n = blockIdx.y * blockDim.x + threadIdx.x;
+  const long long slab = blockIdx.x;
+  if (n >= N) return;
+  float s = 0.f, q = 0.f;
+  for (int r = 0; r < 32; ++r) {
+    const long long m = slab * 32 + r;
+    if (m >= M) break;
+    const float v = out32[m * ldo + n];
+    s += v; q += v * v;
+  }
+  colstats[(slab * 2) * ldo + n] = s;
+  colstats[(slab * 2 + 1) * ldo + n] = q;
+}
+
 __global__ void softmax_ref_kernel(const float* s, __half* out16, float* row_out, int M, int N, int ldo) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
@@ -465,8 +537,9 @@ static int encode_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], 
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-int gemm_prepare(GemmOp* op, int force_block_n) {
+int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub) {
   op->prepared = 0;
+  op->m_sub = 1;
   const long long M = (long long)op->B * op->H * op->W;
   if (!is_pow2(op->W) || !is_pow2(op->H)) GEMM_FAIL("conv_gemm: H and W must be powers of two (got %d x %d)", op->H, op->W);
   if (op->nseg < 1 || op->nseg > 2) GEMM_FAIL("conv_gemm: 1 or 2 A segments");
@@ -494,15 +567,21 @@ int gemm_prepare(GemmOp* op, int force_block_n) {
       const long long mt = (M + BLOCK_M - 1) / BLOCK_M;
       const int kb = ktot / BLOCK_K;
       double best = 1e30;
-      int best_bn = bn;
+      int best_bn = bn, best_ms = 1;
       for (int cand = bn; cand >= 32; cand >>= 1) {
         if (op->N % cand != 0) continue;
-        const long long tiles = mt * (op->N / cand);
-        const long long waves = (tiles + 147) / 148;
-        const double mma = (double)kb * 4.0 * (cand >= 64 ? cand / 2.0 : 32.0) * (cand >= 256 ? 1.0 : 1.25);
-        const double cost = (double)waves * (mma + 6.0 * cand + 1500.0);
-        if (cost < best * 0.97) { best = cost; best_bn = cand; }
+        for (int ms = 1; ms <= 2; ++ms) {
+          if (ms == 2 && (cand > 128 || cand < 64 || op->w_batch_stride != 0)) continue;
+          const long long tiles = ((mt + ms - 1) / ms) * (op->N / cand);
+          const long long waves = (tiles + 147) / 148;
+          const double width = (double)cand * ms;         // output columns x row-tiles sharing one operand load
+          const double ineff = width >= 256 ? 1.0 : (width >= 128 ? 1.25 : 1.5);
+          const double mma = (double)kb * 4.0 * ms * (cand >= 64 ? cand / 2.0 : 32.0) * ineff;
+          const double cost = (double)waves * (mma + 6.0 * cand * ms + 1500.0);
+          if (cost < best * 0.97) { best = cost; best_bn = cand; best_ms = ms; }
+        }
       }
+      op->m_sub = best_ms;
       bn = best_bn;
     }
   }
@@ -511,7 +590,10 @@ int gemm_prepare(GemmOp* op, int force_block_n) {
   if (op->epi == EPI_SOFTMAX && (!op->out16 || !op->row_out)) GEMM_FAIL("conv_gemm: softmax needs out16 and row_out");
   if (op->ldo % 8 != 0) GEMM_FAIL("conv_gemm: ldo must be a multiple of 8");
   op->block_n = bn;
-  op->m_tiles = int((M + BLOCK_M - 1) / BLOCK_M);
+  if (force_block_n != 0) op->m_sub = (force_m_sub == 2) ? 2 : 1;
+  if (op->m_sub == 2 && ((bn != 128 && bn != 64) || op->w_batch_stride != 0 || op->epi != EPI_LINEAR))
+    GEMM_FAIL("conv_gemm: 256-row tiles need block_n 64/128, shared weights and the linear epilogue");
+  op->m_tiles = int((M + (long long)BLOCK_M * op->m_sub - 1) / ((long long)BLOCK_M * op->m_sub));
   op->n_tiles = op->N / bn;
   op->tiles_per_batch = 0;
   if (op->w_batch_stride != 0) {
@@ -545,11 +627,11 @@ int gemm_prepare(GemmOp* op, int force_block_n) {
   return 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int MT>
 static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, MT>;
   static bool attr_set = false;
-  auto kern = conv_gemm_umma_kernel<BN, EPI>;
+  auto kern = conv_gemm_umma_kernel<BN, EPI, MT>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) GEMM_FAIL("cudaFuncSetAttribute(smem=%d): %s", L::TOTAL, cudaGetErrorString(e));
@@ -590,12 +672,20 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     a.w_koff = op->w_koff;
     a.bias = op->bias; a.bias2 = op->bias2; a.residual = op->residual; a.rowscale = op->rowscale;
     a.scale = op->scale; a.out32 = op->out32; a.out16 = op->out16; a.row_out = op->row_out; a.ldo = op->ldo;
-    if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX>(op, a, st);
+    a.colstats = op->colstats;
+    if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX, 1>(op, a, st);
+    if (op->m_sub == 2) {
+      switch (op->block_n) {
+        case 128: return launch_umma<128, EPI_LINEAR, 2>(op, a, st);
+        case 64: return launch_umma<64, EPI_LINEAR, 2>(op, a, st);
+        default: GEMM_FAIL("conv_gemm: m_sub=2 needs block_n 64 or 128 (got %d)", op->block_n);
+      }
+    }
     switch (op->block_n) {
-      case 256: return launch_umma<256, EPI_LINEAR>(op, a, st);
-      case 128: return launch_umma<128, EPI_LINEAR>(op, a, st);
-      case 64: return launch_umma<64, EPI_LINEAR>(op, a, st);
-      case 32: return launch_umma<32, EPI_LINEAR>(op, a, st);
+      case 256: return launch_umma<256, EPI_LINEAR, 1>(op, a, st);
+      case 128: return launch_umma<128, EPI_LINEAR, 1>(op, a, st);
+      case 64: return launch_umma<64, EPI_LINEAR, 1>(op, a, st);
+      case 32: return launch_umma<32, EPI_LINEAR, 1>(op, a, st);
       default: GEMM_FAIL("conv_gemm: unsupported block_n %d", op->block_n);
     }
   }
@@ -624,6 +714,10 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
   }
   dim3 grid((unsigned)((M + 63) / 64), (unsigned)((op->N + 63) / 64));
   conv_gemm_ref_kernel<<<grid, 256, 0, st>>>(r);
+  if (op->colstats != nullptr && op->out32 != nullptr) {
+    dim3 g2((unsigned)((M + 31) / 32), (unsigned)((op->N + 127) / 128));
+    colstats_ref_kernel<<<g2, 128, 0, st>>>(op->out32, op->colstats, (int)M, op->N, op->ldo);
+  }
   if (op->epi == EPI_SOFTMAX)
     softmax_ref_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(g_softmax_tmp, op->out16, op->row_out, (int)M, op->N, op->ldo);
   cudaError_t e = cudaGetLastError();

@@ -44,17 +44,20 @@ struct GemmOp {
   float* row_out;           // [M] (softmax)
   int ldo;
   int epi;
-  // GroupNorm partial statistics of the fp32 output (optional): per (image, group) sum / sumsq
+  // optional GroupNorm statistics of the output, fused into the epilogue: per 32-row slab and column,
+  // colstats[slab][0][n] = sum, colstats[slab][1][n] = sum of squares (slab = m / 32; rows >= M excluded)
+  float* colstats;
   // ---- filled by gemm_prepare ----
   CUtensorMap tmA[2];
   CUtensorMap tmB;
   int block_n;
+  int m_sub;                // 128-row sub-tiles per CTA tile (1 or 2)
   int m_tiles, n_tiles, tiles_per_batch;
   int prepared;
 };
 
 // Encodes the TMA descriptors (needs the final device addresses). Returns 0 or a negative error.
-int gemm_prepare(GemmOp* op, int force_block_n);
+int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub = 0);
 // impl: 0 = tcgen05/TMA kernel, 1 = CUDA-core reference kernel (validation only)
 int gemm_launch(const GemmOp* op, int impl, cudaStream_t st);
 const char* gemm_last_error();
@@ -71,6 +74,8 @@ struct NormOp {
   float eps;
   int silu;                      // apply x*sigmoid(x) after the affine
   int resample;                  // RS_*
+  const float* colstats1;        // producer-written column statistics of src1 / src2 (see GemmOp); when both
+  const float* colstats2;        // present (src2 optional) the stats pass over the tensor is skipped
   float* partial;                // [B, splits, groups, 2] scratch
   float* coef;                   // [B, 2, C] scratch: per-channel scale / shift
   unsigned int* ticket;          // [B] zero-initialised slab counters (self-resetting)
@@ -93,6 +98,9 @@ int head_conv_launch(const __half* in, const float* w /*[3,3,cin,cout]*/, const 
 // in fp32 [B,H,W,c] -> A16 [B,H/2,W/2,kpad] with k = tap*c + ch (zero padded to kpad)
 int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,
                            float out_scale, cudaStream_t st);
+// 3x3 SAME window gather of a few-channel fp32 image (the stem): in [B,H,W,c] -> A16 [B,H,W,kpad], k = tap*c + ch
+int im2col_same3x3_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, float out_scale,
+                          cudaStream_t st);
 // V^T per image for the PV GEMM: qkv16 [B,T,ld] (V at channel voff) -> vT [B,C,T]
 int transpose_v_launch(const __half* qkv, __half* vT, int B, int T, int C, int ld, int voff, cudaStream_t st);
 // Full attention for very short sequences (T <= 64): qkv16 [B,T,3C] -> o16 [B,T,C]

@@ -119,7 +119,48 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const StatsArgs p) {
   }
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// Scale / shift from column statistics that the producing GEMM wrote in its epilogue (no pass over the tensor).
+struct CoefArgs {
+  const float* cs1; int c1;
+  const float* cs2; int c2;
+  int P, groups;
+  float inv_n, eps;
+  const float* gamma; const float* beta;
+  float* coef;
+};
+
+__global__ void __launch_bounds__(256) gn_coef_kernel(const CoefArgs p) {
+  extern __shared__ float sm[];   // [C][2] per-channel sum, sumsq over the image
+  const int C = p.c1 + p.c2;
+  const int b = blockIdx.x;
+  const int slabs = p.P / 32;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const float* cs; int cc, cw;
+    if (ch < p.c1) { cs = p.cs1; cc = ch; cw = p.c1; } else { cs = p.cs2; cc = ch - p.c1; cw = p.c2; }
+    float s = 0.f, q = 0.f;
+    for (int k = 0; k < slabs; ++k) {
+      const long long slab = (long long)b * slabs + k;
+      s += __ldg(cs + (slab * 2) * cw + cc);
+      q += __ldg(cs + (slab * 2 + 1) * cw + cc);
+    }
+    sm[ch * 2] = s;
+    sm[ch * 2 + 1] = q;
+  }
+  __syncthreads();
+  const int cpg = C / p.groups;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const int g = ch / cpg;
+    float ts = 0.f, tss = 0.f;
+    for (int k = g * cpg; k < (g + 1) * cpg; ++k) { ts += sm[k * 2]; tss += sm[k * 2 + 1]; }
+    const float mean = ts * p.inv_n;
+    const float var = fmaxf(tss * p.inv_n - mean * mean, 0.f);
+    const float a = rsqrtf(var + p.eps) * p.gamma[ch];
+    p.coef[((long long)b * 2) * C + ch] = a;
+    p.coef[((long long)b * 2 + 1) * C + ch] = p.beta[ch] - mean * a;
+  }
+}
+
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 struct ApplyArgs {
   const float* src1; int c1;
@@ -284,7 +325,18 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
   const int do_norm = op->dst16 != nullptr;
   if (C % 8 != 0 || op->c1 % 8 != 0 || C > 2048) return -1;
   const int P = op->H * op->W;
-  if (do_norm) {
+  const bool fused_stats = do_norm && op->colstats1 != nullptr && (op->src2 == nullptr || op->colstats2 != nullptr) &&
+                           P % 32 == 0;
+  if (fused_stats) {
+    if (C % op->groups != 0) return -2;
+    if (!op->coef) return -5;
+    CoefArgs c;
+    c.cs1 = op->colstats1; c.c1 = op->c1; c.cs2 = op->colstats2; c.c2 = op->c2;
+    c.P = P; c.groups = op->groups;
+    c.inv_n = 1.0f / ((float)P * (float)(C / op->groups));
+    c.eps = op->eps; c.gamma = op->gamma; c.beta = op->beta; c.coef = op->coef;
+    gn_coef_kernel<<<op->B, 256, 2 * C * sizeof(float), st>>>(c);
+  } else if (do_norm) {
     if (C % op->groups != 0) return -2;
     if (!op->partial || !op->coef || !op->ticket) return -5;
     const int nv = C / 4;

@@ -176,6 +176,44 @@ int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, in
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// ---- stem: 3x3 SAME window gather so that the 6 -> nf convolution runs as one K=64 GEMM k-block ---------------
+__global__ void __launch_bounds__(256) im2col_same3x3_kernel(const float* __restrict__ in, __half* __restrict__ a16,
+                                                            int B, int H, int W, int c, int kpad, float out_scale) {
+  // one thread per (pixel, 8 consecutive k): 16-byte stores
+  const int kv = kpad / 8;
+  const long long total = (long long)B * H * W * kv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k0 = int(idx % kv) * 8;
+    const long long pix = idx / kv;
+    const int x = int(pix % W), y = int((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    __half h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      float v = 0.f;
+      if (k < 9 * c) {
+        const int ch = k % c, tap = k / c;
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(in + ((b * H + yy) * W + xx) * c + ch) * out_scale;
+      }
+      h[j] = __float2half_rn(v);
+    }
+    *reinterpret_cast<uint4*>(a16 + pix * kpad + k0) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+int im2col_same3x3_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, float out_scale,
+                          cudaStream_t st) {
+  if (kpad % 8 != 0) return -1;
+  const long long total = (long long)B * H * W * (kpad / 8);
+  int grid = ceil_div_ll(total, 256);
+  if (grid > 148 * 32) grid = 148 * 32;
+  im2col_same3x3_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, kpad, out_scale);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 // ---- V^T: qkv16 [B,T,ld] (V at voff) -> vT [B,C,T]; 32x32 tiles through shared memory ------------------------
 __global__ void __launch_bounds__(256) transpose_v_kernel(const __half* __restrict__ qkv, __half* __restrict__ vT, int T,
                                                          int C, int ld, int voff) {

@@ -104,6 +104,14 @@ UNet::T32 UNet::new32(int C, int H, int W) {
   t.C = C; t.H = H; t.W = W;
   t.bytes = (size_t)max_batch_ * H * W * C * sizeof(float);
   t.p = (float*)a_alloc(t.bytes);
+  // column statistics written by the producing GEMM's epilogue (one (sum, sumsq) pair per 32-row slab and channel)
+  t.stats = nullptr;
+  t.stats_bytes = 0;
+  t.stats_valid = false;
+  if ((H * W) % 32 == 0) {
+    t.stats_bytes = (size_t)max_batch_ * H * W / 32 * 2 * C * sizeof(float);
+    t.stats = (float*)a_alloc(t.stats_bytes);
+  }
   return t;
 }
 UNet::T16 UNet::new16(int C, int H, int W) {
@@ -113,7 +121,12 @@ UNet::T16 UNet::new16(int C, int H, int W) {
   t.p = (__half*)a_alloc(t.bytes);
   return t;
 }
-void UNet::rel(T32& t) { if (t.p) a_free(t.p, t.bytes); t.p = nullptr; }
+void UNet::rel(T32& t) {
+  if (t.p) a_free(t.p, t.bytes);
+  if (t.stats) a_free(t.stats, t.stats_bytes);
+  t.p = nullptr;
+  t.stats = nullptr;
+}
 void UNet::rel(T16& t) { if (t.p) a_free(t.p, t.bytes); t.p = nullptr; }
 
 // ---- parameters -----------------------------------------------------------------------------------------
@@ -185,6 +198,8 @@ void UNet::add_norm(const T32& in1, const T32* in2, const float* gamma, const fl
   n.eps = 1e-6f;
   n.silu = silu ? 1 : 0;
   n.resample = resample;
+  n.colstats1 = in1.stats_valid ? in1.stats : nullptr;
+  n.colstats2 = (in2 && in2->stats_valid) ? in2->stats : nullptr;
   n.partial = gn_partial_;
   n.coef = gn_coef_;
   n.ticket = gn_ticket_;
@@ -275,6 +290,7 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     g.bias = bias1;
     g.bias2 = temb_off >= 0 ? temb_cur_ + temb_off : nullptr;
     g.out32 = h2.p; g.ldo = out_ch;
+    g.colstats = h2.stats; h2.stats_valid = h2.stats != nullptr;
     ops_.push_back(op);
   }
   rel(a1);
@@ -323,6 +339,7 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     g.residual = need_sc ? nullptr : in1.p;
     g.scale = out_scale;
     g.out32 = out.p; g.ldo = out_ch;
+    g.colstats = out.stats; out.stats_valid = out.stats != nullptr;
     ops_.push_back(op);
   }
   rel(a2);
@@ -432,6 +449,7 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
     g.w = w3; g.N = C; g.w_ld = C; g.bias = b3;
     g.residual = x.p; g.scale = out_scale;
     g.out32 = out.p; g.ldo = C;
+    g.colstats = out.stats; out.stats_valid = out.stats != nullptr;
     ops_.push_back(op);
   }
   rel(o16);
@@ -495,12 +513,34 @@ int UNet::walk() {
   const auto* sb = param(stem, "bias", {nf}, 1, 1.f);
   std::vector<T32> hs;
   {
+    // 9*Cnet (= 54 or 27) input taps padded to one 64-wide k-block: window gather + one tcgen05 GEMM
     T32 h0 = new32(nf, S, S);
-    Op op; op.kind = OP_STEM; op.tag = "stem";
-    op.in_is_external = true; op.f_out = h0.p; op.H = S; op.W = S; op.cin = Cnet; op.cout = nf;
-    if (dry_) { w_alloc((size_t)9 * Cnet * nf * 4); w_alloc(nf * 4); }
-    else { if (!sk || !sb) return -1; op.w = upload_f32(*sk); op.bias = upload_f32(*sb); }
-    ops_.push_back(op);
+    const int kpad = (int)align_up(9 * Cnet, 64);
+    T16 a16 = new16(kpad, S, S);
+    {
+      Op op; op.kind = OP_IM2COL; op.tag = "stem_im2col";
+      op.in_is_external = true; op.h_out = a16.p; op.H = S; op.W = S; op.cin = Cnet; op.kpad = kpad; op.use_fir = 2;
+      ops_.push_back(op);
+    }
+    __half* wp = nullptr; const float* bp = nullptr;
+    if (dry_) { wp = (__half*)w_alloc((size_t)nf * kpad * 2); w_alloc(nf * 4); }
+    else {
+      if (!sk || !sb) return -1;
+      std::vector<__half> pk((size_t)nf * kpad, __float2half(0.f));
+      pack_conv(*sk, 9, Cnet, nf, pk, kpad, 0, 1.0f / kRawScale);
+      wp = upload_f16(pk); bp = upload_f32(*sb);
+    }
+    {
+      Op op; op.kind = OP_GEMM; op.tag = "stem";
+      op.gemm = make_gemm(max_batch_, S, S);
+      GemmOp& g = op.gemm;
+      g.nseg = 1; g.seg[0] = {a16.p, kpad, 0, kpad, 1};
+      g.w = wp; g.N = nf; g.w_ld = kpad; g.bias = bp;
+      g.out32 = h0.p; g.ldo = nf;
+      g.colstats = h0.stats; h0.stats_valid = h0.stats != nullptr;
+      ops_.push_back(op);
+    }
+    rel(a16);
     hs.push_back(h0);
   }
   bool has_pyr = m.progressive_input == 1;
@@ -557,6 +597,7 @@ int UNet::walk() {
           g.w = wp; g.N = cout; g.w_ld = kpad; g.bias = bp;
           g.residual = h.p; g.scale = m.skip_rescale ? (float)(1.0 / std::sqrt(2.0)) : 1.f;
           g.out32 = np.p; g.ldo = cout;
+          g.colstats = np.stats; np.stats_valid = np.stats != nullptr;
           ops_.push_back(op);
         }
         rel(a16);
@@ -728,7 +769,7 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
       case OP_GEMM: {
         GemmOp g = op.gemm;
         g.B = batch;
-        g.m_tiles = (int)(((long long)batch * g.H * g.W + 127) / 128);
+        g.m_tiles = (int)(((long long)batch * g.H * g.W + 128 * g.m_sub - 1) / (128 * g.m_sub));
         rc = gemm_launch(&g, gemm_impl, st);
         if (rc) return fail(std::string("gemm_launch(") + op.tag + "): " + gemm_last_error());
         launches_ += (gemm_impl == 1 && g.epi == EPI_SOFTMAX) ? 2 : 1;
@@ -739,8 +780,11 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         launches_ += 1;
         break;
       case OP_IM2COL:
-        rc = im2col_fir_down_launch(op.in_is_external ? x_dev : op.f_in, op.h_out, batch, op.H, op.W, op.cin, op.kpad,
-                                    op.use_fir, kRawScale, st);
+        if (op.use_fir == 2)
+          rc = im2col_same3x3_launch(x_dev, op.h_out, batch, op.H, op.W, op.cin, op.kpad, kRawScale, st);
+        else
+          rc = im2col_fir_down_launch(op.in_is_external ? x_dev : op.f_in, op.h_out, batch, op.H, op.W, op.cin, op.kpad,
+                                      op.use_fir, kRawScale, st);
         launches_ += 1;
         break;
       case OP_TRANSPOSE_V:

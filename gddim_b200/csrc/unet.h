@@ -70,7 +70,7 @@ class UNet {
   int dump_profile(const char* path) const;
 
  private:
-  struct T32 { float* p; int C, H, W; size_t bytes; };
+  struct T32 { float* p; int C, H, W; size_t bytes; float* stats; size_t stats_bytes; bool stats_valid; };
   struct T16 { __half* p; int C, H, W; size_t bytes; };
   struct Scope;
   gddim_model_cfg cfg_;

@@ -80,6 +80,20 @@ def test_gemm_block_n_variants(impl, bn):
   assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("bn", [64, 128])
+@pytest.mark.parametrize("B", [2, 3, 5])
+def test_umma_256_row_tiles(bn, B):
+  """m_sub = 2: one weight tile feeds two 128-row accumulators (odd B: the last CTA tile is half out of range)."""
+  g = torch.Generator().manual_seed(40 + bn + B)
+  a = torch.randn(B, 8, 16, 128, generator=g).to(torch.float16)       # M = B*128
+  k = (torch.randn(3, 3, 128, 128, generator=g) / np.sqrt(9 * 128)).numpy()
+  res = torch.randn(B, 8, 16, 128, generator=g)
+  want = (_conv_ref(a, k, 9) + res.double()) * 0.5
+  o32, _ = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k), 128, taps0=9, residual=res.cuda(), scale=0.5, impl=0,
+                         force_block_n=bn, force_m_sub=2)
+  assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
+
+
 @pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
 def test_attention_chain(impl):
   """qk^T -> row softmax epilogue -> P V with per-image B operands == softmax(q k^T / sqrt(C)) v."""
