@@ -99,8 +99,9 @@ int head_conv_launch(const __half* in, const float* w /*[3,3,cin,cout]*/, const 
 int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,
                            float out_scale, cudaStream_t st);
 // 3x3 SAME window gather of a few-channel fp32 image (the stem): in [B,H,W,c] -> A16 [B,H,W,kpad], k = tap*c + ch
+// split = 1: kpad = 3 segments (hi(x), lo(x), hi(x)) for an fp32-accurate product with (hi(w), hi(w), lo(w)) rows
 int im2col_same3x3_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, float out_scale,
-                          cudaStream_t st);
+                          int split, cudaStream_t st);
 // V^T per image for the PV GEMM: qkv16 [B,T,ld] (V at channel voff) -> vT [B,C,T]
 int transpose_v_launch(const __half* qkv, __half* vT, int B, int T, int C, int ld, int voff, cudaStream_t st);
 // Full attention for very short sequences (T <= 64): qkv16 [B,T,3C] -> o16 [B,T,C]

@@ -178,7 +178,8 @@ int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, in
 
 // ---- stem: 3x3 SAME window gather so that the 6 -> nf convolution runs as one K=64 GEMM k-block ---------------
 __global__ void __launch_bounds__(256) im2col_same3x3_kernel(const float* __restrict__ in, __half* __restrict__ a16,
-                                                            int B, int H, int W, int c, int kpad, float out_scale) {
+                                                            int B, int H, int W, int c, int kpad, float out_scale,
+                                                            int split, int kseg) {
   // one thread per (pixel, 8 consecutive k): 16-byte stores
   const int kv = kpad / 8;
   const long long total = (long long)B * H * W * kv;
@@ -188,29 +189,34 @@ __global__ void __launch_bounds__(256) im2col_same3x3_kernel(const float* __rest
     const long long pix = idx / kv;
     const int x = int(pix % W), y = int((pix / W) % H);
     const long long b = pix / ((long long)W * H);
+    // split mode (kpad == 3*kseg): columns [0,kseg) = hi(x), [kseg,2kseg) = lo(x) = x - hi(x), [2kseg,3kseg) = hi(x)
+    // again; with weight rows (hi(w), hi(w), lo(w)) the GEMM evaluates x*w to ~2^-22 relative with fp16 operands.
+    const int seg = split ? k0 / kseg : 0;
     __half h[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = k0 + j;
+      const int k = k0 + j - seg * kseg;
       float v = 0.f;
       if (k < 9 * c) {
         const int ch = k % c, tap = k / c;
         const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
         if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(in + ((b * H + yy) * W + xx) * c + ch) * out_scale;
       }
-      h[j] = __float2half_rn(v);
+      const __half hi = __float2half_rn(v);
+      h[j] = (seg == 1) ? __float2half_rn(v - __half2float(hi)) : hi;
     }
     *reinterpret_cast<uint4*>(a16 + pix * kpad + k0) = *reinterpret_cast<const uint4*>(h);
   }
 }
 
 int im2col_same3x3_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, float out_scale,
-                          cudaStream_t st) {
-  if (kpad % 8 != 0) return -1;
+                          int split, cudaStream_t st) {
+  if (kpad % 8 != 0 || (split && kpad % 24 != 0)) return -1;
+  const int kseg = split ? kpad / 3 : kpad;
   const long long total = (long long)B * H * W * (kpad / 8);
   int grid = ceil_div_ll(total, 256);
   if (grid > 148 * 32) grid = 148 * 32;
-  im2col_same3x3_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, kpad, out_scale);
+  im2col_same3x3_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, kpad, out_scale, split, kseg);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -513,9 +513,12 @@ int UNet::walk() {
   const auto* sb = param(stem, "bias", {nf}, 1, 1.f);
   std::vector<T32> hs;
   {
-    // 9*Cnet (= 54 or 27) input taps padded to one 64-wide k-block: window gather + one tcgen05 GEMM
+    // 9*Cnet (= 54 or 27) input taps padded to a 64-wide k-block: window gather + one tcgen05 GEMM.  The raw
+    // state is the one operand that is not normalised, so it is fed as a hi/lo fp16 pair against hi/lo weights
+    // (3 k-blocks: hi*hi + lo*hi + hi*lo): the stem stays fp32-accurate at negligible cost.
     T32 h0 = new32(nf, S, S);
-    const int kpad = (int)align_up(9 * Cnet, 64);
+    const int kseg = (int)align_up(9 * Cnet, 64);
+    const int kpad = 3 * kseg;
     T16 a16 = new16(kpad, S, S);
     {
       Op op; op.kind = OP_IM2COL; op.tag = "stem_im2col";
@@ -528,6 +531,14 @@ int UNet::walk() {
       if (!sk || !sb) return -1;
       std::vector<__half> pk((size_t)nf * kpad, __float2half(0.f));
       pack_conv(*sk, 9, Cnet, nf, pk, kpad, 0, 1.0f / kRawScale);
+      for (int co = 0; co < nf; ++co)
+        for (int k = 0; k < 9 * Cnet; ++k) {
+          const int tap = k / Cnet, ci = k % Cnet;
+          const float w = (*sk)[((size_t)tap * Cnet + ci) * nf + co] / kRawScale;
+          const __half hi = pk[(size_t)co * kpad + k];
+          pk[(size_t)co * kpad + kseg + k] = hi;
+          pk[(size_t)co * kpad + 2 * kseg + k] = __float2half_rn(w - __half2float(hi));
+        }
       wp = upload_f16(pk); bp = upload_f32(*sb);
     }
     {
@@ -781,7 +792,7 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         break;
       case OP_IM2COL:
         if (op.use_fir == 2)
-          rc = im2col_same3x3_launch(x_dev, op.h_out, batch, op.H, op.W, op.cin, op.kpad, kRawScale, st);
+          rc = im2col_same3x3_launch(x_dev, op.h_out, batch, op.H, op.W, op.cin, op.kpad, kRawScale, 1, st);
         else
           rc = im2col_fir_down_launch(op.in_is_external ? x_dev : op.f_in, op.h_out, batch, op.H, op.W, op.cin, op.kpad,
                                       op.use_fir, kRawScale, st);
