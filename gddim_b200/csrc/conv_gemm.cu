@@ -11,6 +11,7 @@
 //   warps 2-5 epilogue     - tcgen05.ld -> bias / temb / residual / scale (or row softmax) -> global
 // Operands are fp16 with fp32 accumulation; smem tiles use the 128-byte swizzle (K-major).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -56,6 +57,7 @@ struct GemmArgs {
   float* row_out;
   int ldo;
   float* colstats;
+  int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };
 
 // MT = number of 128-row M sub-tiles a CTA tile covers (2 for narrow N: the weight tile is then shared by 256
@@ -139,12 +141,14 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
   ptx::mbar_wait(cx.tfull, cx.tfull_phase);
   ptx::tc_fence_after();
   uint32_t r[32];
+  if (p.dbg == 3) return;
 #pragma unroll 1
   for (int q = 0; q < NQ; ++q) {
     const int mi = q / NCH, c0 = (q % NCH) * 32;
     ptx::tmem_ld_32x32b_x32(cx.taddr + mi * BLOCK_N + c0, r);
     if (RES && q + 1 < NQ) load_res(q + 1, res_next);
     ptx::tmem_ld_wait();
+    if (p.dbg == 1) continue;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) sts128(stg_w + j * 4, r[j], r[j + 1], r[j + 2], r[j + 3]);
     __syncwarp();
@@ -166,7 +170,7 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
       if (RES) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
       v.x = fmaf(v.x, scale, bsum.x); v.y = fmaf(v.y, scale, bsum.y);
       v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
-      if (ok) {
+      if (ok && p.dbg != 2) {
         if (STATS) {
           cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
           cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y); cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
@@ -741,6 +745,11 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     a.bias = op->bias; a.bias2 = op->bias2; a.residual = op->residual; a.rowscale = op->rowscale;
     a.scale = op->scale; a.out32 = op->out32; a.out16 = op->out16; a.row_out = op->row_out; a.ldo = op->ldo;
     a.colstats = op->colstats;
+    {
+      static int dbg = -1;
+      if (dbg < 0) { const char* e = getenv("GDDIM_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+      a.dbg = dbg;
+    }
     if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX, 1>(op, a, st);
     if (op->m_sub == 2) {
       switch (op->block_n) {
