@@ -56,6 +56,7 @@ struct GemmArgs {
   __half* out16;
   float* row_out;
   int ldo;
+  int n_store;
   float* colstats;
   int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };
@@ -105,7 +106,8 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
-template <int BLOCK_N, int MT, bool RES_, bool O32_, bool O16_, bool STATS_, bool RSCALE_, bool FULL, bool GENERIC>
+template <int BLOCK_N, int MT, bool RES_, bool O32_, bool O16_, bool STATS_, bool RSCALE_, bool FULL, bool GENERIC,
+          bool NARROW = false>
 __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
   constexpr int RS = SmemLayout<BLOCK_N, MT>::EPI_ROW_FLOATS;
   constexpr int NCH = BLOCK_N / 32;
@@ -175,7 +177,13 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
           cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
           cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y); cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
         }
-        if (O32) *reinterpret_cast<float4*>(o32 + (long long)(i * 4) * ldo) = v;
+        if (NARROW) {
+          float* q = o32 + (long long)(i * 4) * ldo;
+          if (n0 + 0 < p.n_store) q[0] = v.x;
+          if (n0 + 1 < p.n_store) q[1] = v.y;
+          if (n0 + 2 < p.n_store) q[2] = v.z;
+          if (n0 + 3 < p.n_store) q[3] = v.w;
+        } else if (O32) *reinterpret_cast<float4*>(o32 + (long long)(i * 4) * ldo) = v;
         if (O16) {
           __half2 h0 = __floats2half2_rn(v.x, v.y);
           __half2 h1 = __floats2half2_rn(v.z, v.w);
@@ -363,7 +371,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
                               (p.colstats ? 8u : 0u) | (p.rowscale ? 16u : 0u);
         EpiCtx<BLOCK_N, MT> cx{p, stg, bias_s, &tfull_bar[acc], acc_phase, tmem_base + (uint32_t(quad * 32) << 16) + acc * MT * BLOCK_N,
                                (long long)mt * MT * BLOCK_M + quad * 32, nt * BLOCK_N, lane};
-        if (!full) epi_tile<BLOCK_N, MT, true, true, true, true, true, false, true>(cx);     // ragged last tile: generic path
+        if (p.n_store > 0) epi_tile<BLOCK_N, MT, false, true, false, false, false, false, false, true>(cx);   // few-channel output
+        else if (!full) epi_tile<BLOCK_N, MT, true, true, true, true, true, false, true>(cx);     // ragged last tile: generic path
         else if (mode == (2u | 8u)) epi_tile<BLOCK_N, MT, false, true, false, true, false, true, false>(cx);           // conv1, shortcut conv2, stem
         else if (mode == (1u | 2u | 8u)) epi_tile<BLOCK_N, MT, true, true, false, true, false, true, false>(cx);       // conv2 / proj / pyramid
         else if (mode == 4u) epi_tile<BLOCK_N, MT, false, false, true, false, false, true, false>(cx);                  // qkv
@@ -454,6 +463,7 @@ struct RefArgs {
   int epi;
   float* softmax_tmp;            // [M, N] scratch for the softmax epilogue
   float* colstats;
+  int n_store;
 };
 
 __global__ void __launch_bounds__(256) conv_gemm_ref_kernel(const RefArgs p) {
@@ -523,7 +533,7 @@ __global__ void __launch_bounds__(256) conv_gemm_ref_kernel(const RefArgs p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n >= p.N) continue;
+      if (n >= p.N || (p.n_store > 0 && n >= p.n_store)) continue;
       float v = acc[i][j];
       if (p.epi == EPI_SOFTMAX) {
         p.softmax_tmp[m * p.N + n] = v * p.scale;
@@ -660,7 +670,9 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub) {
   if (op->N % bn != 0) GEMM_FAIL("conv_gemm: N=%d not a multiple of block_n=%d", op->N, bn);
   if (op->epi == EPI_SOFTMAX && (bn != op->N || bn != 256)) GEMM_FAIL("conv_gemm: softmax epilogue needs N == 256");
   if (op->epi == EPI_SOFTMAX && (!op->out16 || !op->row_out)) GEMM_FAIL("conv_gemm: softmax needs out16 and row_out");
-  if (op->ldo % 8 != 0) GEMM_FAIL("conv_gemm: ldo must be a multiple of 8");
+  if (op->n_store == 0 && op->ldo % 8 != 0) GEMM_FAIL("conv_gemm: ldo must be a multiple of 8");
+  if (op->n_store != 0 && (op->residual || op->out16 || op->colstats || op->rowscale || !op->out32 || op->epi != EPI_LINEAR))
+    GEMM_FAIL("conv_gemm: n_store supports bias + scale + fp32 output only");
   op->block_n = bn;
   if (force_block_n != 0) op->m_sub = (force_m_sub == 2) ? 2 : 1;
   if (op->m_sub == 2 && ((bn != 128 && bn != 64) || op->w_batch_stride != 0 || op->epi != EPI_LINEAR))
@@ -745,6 +757,7 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     a.bias = op->bias; a.bias2 = op->bias2; a.residual = op->residual; a.rowscale = op->rowscale;
     a.scale = op->scale; a.out32 = op->out32; a.out16 = op->out16; a.row_out = op->row_out; a.ldo = op->ldo;
     a.colstats = op->colstats;
+    a.n_store = op->n_store;
     {
       static int dbg = -1;
       if (dbg < 0) { const char* e = getenv("GDDIM_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
@@ -779,6 +792,7 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
   r.bias = op->bias; r.bias2 = op->bias2; r.residual = op->residual; r.rowscale = op->rowscale;
   r.scale = op->scale; r.out32 = op->out32; r.out16 = op->out16; r.row_out = op->row_out; r.ldo = op->ldo;
   r.epi = op->epi;
+  r.n_store = op->n_store;
   if (op->w_batch_stride != 0 && (op->H * op->W) % 64 != 0) GEMM_FAIL("conv_gemm ref: batched B needs H*W %% 64 == 0");
   if (op->epi == EPI_SOFTMAX) {
     const size_t need = (size_t)M * op->N * sizeof(float);

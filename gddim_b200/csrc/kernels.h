@@ -43,6 +43,8 @@ struct GemmOp {
   __half* out16;            // [M, ldo]
   float* row_out;           // [M] (softmax)
   int ldo;
+  int n_store;              // 0 = all N columns; else only columns < n_store are written (fp32, scalar stores,
+                            // ldo may then be any value): few-channel outputs such as the 6-channel head conv
   int epi;
   // optional GroupNorm statistics of the output, fused into the epilogue: per 32-row slab and column,
   // colstats[slab][0][n] = sum, colstats[slab][1][n] = sum of squares (slab = m / 32; rows >= M excluded)

@@ -167,8 +167,54 @@ __global__ void __launch_bounds__(256) im2col_fir_down_kernel(const float* __res
   }
 }
 
+// 8 channels per thread (c % 8 == 0, kpad == 9*c): float4 loads, one 16-byte store
+__global__ void __launch_bounds__(256) im2col_fir_down_vec8_kernel(const float* __restrict__ in, __half* __restrict__ a16,
+                                                                  int B, int H, int W, int c, float out_scale) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int cv = c / 8;
+  const long long total = (long long)B * Ho * Wo * 9 * cv;
+  const float kf[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int ch = int(idx % cv) * 8;
+    const int tap = int((idx / cv) % 9);
+    const long long opix = idx / (9 * cv);
+    const int ky = tap / 3, kx = tap % 3;
+    const int ox = int(opix % Wo), oy = int((opix / Wo) % Ho);
+    const long long b = opix / ((long long)Wo * Ho);
+    const int py = 2 * oy + ky, px = 2 * ox + kx;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int iy = py + i - 2;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ix = px + j - 2;
+        if (ix < 0 || ix >= W) continue;
+        const float w = kf[i] * kf[j];
+        const float* q = in + ((b * H + iy) * W + ix) * c + ch;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(q)), v1 = __ldg(reinterpret_cast<const float4*>(q + 4));
+        acc[0] += w * v0.x; acc[1] += w * v0.y; acc[2] += w * v0.z; acc[3] += w * v0.w;
+        acc[4] += w * v1.x; acc[5] += w * v1.y; acc[6] += w * v1.z; acc[7] += w * v1.w;
+      }
+    }
+    __half h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(acc[j] * out_scale);
+    *reinterpret_cast<uint4*>(a16 + opix * (9 * c) + tap * c + ch) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
 int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,
                            float out_scale, cudaStream_t st) {
+  if (use_fir && c % 8 == 0 && kpad == 9 * c) {
+    const long long total = (long long)B * (H / 2) * (W / 2) * 9 * (c / 8);
+    int grid = ceil_div_ll(total, 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    im2col_fir_down_vec8_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, out_scale);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   const long long total = (long long)B * (H / 2) * (W / 2) * kpad;
   int grid = ceil_div_ll(total, 256);
   if (grid > 148 * 32) grid = 148 * 32;
@@ -209,9 +255,49 @@ __global__ void __launch_bounds__(256) im2col_same3x3_kernel(const float* __rest
   }
 }
 
+// split layout, 9*c <= 64: one thread per pixel builds the 64-wide hi and lo rows in registers and writes the three
+// 128-byte segments (hi, lo, hi) with 16-byte stores
+template <int C>
+__global__ void __launch_bounds__(128) im2col_stem_split_kernel(const float* __restrict__ in, __half* __restrict__ a16,
+                                                               int B, int H, int W, float out_scale) {
+  const long long npix = (long long)B * H * W;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int x = int(pix % W), y = int((pix / W) % H);
+  const long long b = pix / ((long long)W * H);
+  __half hi[64], lo[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) { hi[k] = __float2half(0.f); lo[k] = __float2half(0.f); }
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const float* q = in + ((b * H + yy) * W + xx) * C;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+      const float v = __ldg(q + ch) * out_scale;
+      const __half h = __float2half_rn(v);
+      hi[tap * C + ch] = h;
+      lo[tap * C + ch] = __float2half_rn(v - __half2float(h));
+    }
+  }
+  uint4* dst = reinterpret_cast<uint4*>(a16 + pix * 192);
+  const uint4* ph = reinterpret_cast<const uint4*>(hi);
+  const uint4* pl = reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { dst[j] = ph[j]; dst[8 + j] = pl[j]; dst[16 + j] = ph[j]; }
+}
+
 int im2col_same3x3_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, float out_scale,
                           int split, cudaStream_t st) {
   if (kpad % 8 != 0 || (split && kpad % 24 != 0)) return -1;
+  if (split && kpad == 192 && (c == 6 || c == 3)) {
+    const long long npix = (long long)B * H * W;
+    const int grid = ceil_div_ll(npix, 128);
+    if (c == 6) im2col_stem_split_kernel<6><<<grid, 128, 0, st>>>(in, a16, B, H, W, out_scale);
+    else im2col_stem_split_kernel<3><<<grid, 128, 0, st>>>(in, a16, B, H, W, out_scale);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   const int kseg = split ? kpad / 3 : kpad;
   const long long total = (long long)B * H * W * (kpad / 8);
   int grid = ceil_div_ll(total, 256);
@@ -238,7 +324,37 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const __half* __restri
   }
 }
 
+// 64x64 tiles, 16-byte global accesses on both sides (T, C, ld, voff multiples of 8; T, C multiples of 64)
+__global__ void __launch_bounds__(256) transpose_v64_kernel(const __half* __restrict__ qkv, __half* __restrict__ vT, int T,
+                                                           int C, int ld, int voff) {
+  __shared__ __align__(16) __half tile[64][72];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int v = threadIdx.x + k * 256;          // 512 vectors: row = v / 8, 8-channel group = v % 8
+    const int r = v >> 3, g = v & 7;
+    *reinterpret_cast<uint4*>(&tile[r][g * 8]) =
+        *reinterpret_cast<const uint4*>(qkv + ((long long)b * T + t0 + r) * ld + voff + c0 + g * 8);
+  }
+  __syncthreads();
+  const int c = threadIdx.x & 63;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int tv = (threadIdx.x >> 6) + k * 4;    // 8-token group 0..7
+    __half h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = tile[tv * 8 + j][c];
+    *reinterpret_cast<uint4*>(vT + ((long long)b * C + c0 + c) * T + t0 + tv * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
 int transpose_v_launch(const __half* qkv, __half* vT, int B, int T, int C, int ld, int voff, cudaStream_t st) {
+  if (T % 64 == 0 && C % 64 == 0 && ld % 8 == 0 && voff % 8 == 0) {
+    dim3 grid(T / 64, C / 64, B);
+    transpose_v64_kernel<<<grid, 256, 0, st>>>(qkv, vT, T, C, ld, voff);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+  }
   dim3 grid((T + 31) / 32, (C + 31) / 32, B);
   transpose_v_kernel<<<grid, 256, 0, st>>>(qkv, vT, T, C, ld, voff);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;

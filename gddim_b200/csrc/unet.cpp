@@ -669,10 +669,39 @@ int UNet::walk() {
     Scope hc = top.child("Conv");
     const auto* hk = param(hc, "kernel", {3, 3, a.C, Cnet}, 0, scale0(0.f));
     const auto* hb = param(hc, "bias", {Cnet}, 1, 1.f);
-    Op op; op.kind = OP_HEAD; op.tag = "head";
-    op.h_in = a.p; op.out_is_external = true; op.H = a.H; op.W = a.W; op.cin = a.C; op.cout = Cnet;
-    if (dry_) { w_alloc((size_t)9 * a.C * Cnet * 4); w_alloc(Cnet * 4); }
-    else { if (!hk || !hb) return -1; op.w = upload_f32(*hk); op.bias = upload_f32(*hb); }
+    // C_out = 6 (or 3) is padded to one 32-wide N tile; only the real columns are stored (n_store)
+    const int npad = 32;
+    float head_wscale = 1.f;
+    __half* wp = nullptr; const float* bp = nullptr;
+    if (dry_) { wp = (__half*)w_alloc((size_t)npad * 9 * a.C * 2); w_alloc(npad * 4); }
+    else {
+      if (!hk || !hb) return -1;
+      // The reference initialises this layer with scale 1e-10 (init_scale = 0): bring the weights into fp16's
+      // normal range with an exact power-of-two factor and undo it in the epilogue scale.
+      float wmax = 0.f;
+      for (float v : *hk) wmax = std::max(wmax, std::fabs(v));
+      int e = 0;
+      if (wmax > 0.f) std::frexp(wmax, &e);
+      head_wscale = std::ldexp(1.0f, -e);                         // wmax * head_wscale in [0.5, 1)
+      std::vector<__half> pk((size_t)npad * 9 * a.C, __float2half(0.f));
+      for (int tap = 0; tap < 9; ++tap)
+        for (int ci = 0; ci < a.C; ++ci)
+          for (int co = 0; co < Cnet; ++co)
+            pk[(size_t)co * 9 * a.C + tap * a.C + ci] =
+                __float2half_rn((*hk)[((size_t)tap * a.C + ci) * Cnet + co] * head_wscale);
+      std::vector<float> bb(npad, 0.f);
+      for (int co = 0; co < Cnet; ++co) bb[co] = (*hb)[co] * head_wscale;
+      wp = upload_f16(pk); bp = upload_f32(bb);
+    }
+    Op op; op.kind = OP_GEMM; op.tag = "head";
+    op.out_is_external = true;
+    op.gemm = make_gemm(max_batch_, a.H, a.W);
+    GemmOp& g = op.gemm;
+    g.nseg = 1; g.seg[0] = {a.p, a.C, 0, a.C, 9};
+    g.w = wp; g.N = npad; g.w_ld = 9 * a.C; g.bias = bp;
+    g.out32 = reinterpret_cast<float*>(uintptr_t(16));   // patched with the caller's output at launch
+    g.ldo = Cnet; g.n_store = Cnet;
+    g.scale = 1.0f / head_wscale;
     ops_.push_back(op);
     rel(a);
   }
@@ -780,6 +809,7 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
       case OP_GEMM: {
         GemmOp g = op.gemm;
         g.B = batch;
+        if (op.out_is_external) g.out32 = out_dev;
         g.m_tiles = (int)(((long long)batch * g.H * g.W + 128 * g.m_sub - 1) / (128 * g.m_sub));
         rc = gemm_launch(&g, gemm_impl, st);
         if (rc) return fail(std::string("gemm_launch(") + op.tag + "): " + gemm_last_error());

@@ -31,7 +31,7 @@ def pack_conv_weight(kernel_hwio, extra_1x1=None):
 
 
 def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residual=None, rowscale=None, scale=1.0,
-              out_fp32=True, out_fp16=False, impl=0, force_block_n=0, force_m_sub=0, epi=0, a0_coff=0, a0_c=None, w_ld=None,
+              out_fp32=True, out_fp16=False, impl=0, force_block_n=0, force_m_sub=0, epi=0, n_store=0, a0_coff=0, a0_c=None, w_ld=None,
               w_koff=0, w_batch_stride=0, w_rows_per_batch=0):
   """a0 (and a1): fp16 [B,H,W,C]; w: fp16 K-major.  Returns (out32 or None, out16 or None[, row_out])."""
   import torch
@@ -46,10 +46,12 @@ def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residu
   d.w_batch_stride, d.w_rows_per_batch = w_batch_stride, w_rows_per_batch
   d.bias, d.bias2, d.residual, d.rowscale = _ptr(bias), _ptr(bias2), _ptr(residual), _ptr(rowscale)
   d.scale = scale
-  o32 = torch.empty((B, H, W, N), dtype=torch.float32, device="cuda") if (out_fp32 and epi == 0) else None
+  No = n_store or N
+  o32 = torch.empty((B, H, W, No), dtype=torch.float32, device="cuda") if (out_fp32 and epi == 0) else None
   o16 = torch.empty((B, H, W, N), dtype=torch.float16, device="cuda") if (out_fp16 or epi == 1) else None
   row = torch.empty((B, H, W), dtype=torch.float32, device="cuda") if epi == 1 else None
-  d.out32, d.out16, d.row_out, d.ldo = _ptr(o32), _ptr(o16), _ptr(row), N
+  d.out32, d.out16, d.row_out, d.ldo = _ptr(o32), _ptr(o16), _ptr(row), No
+  d.n_store = n_store
   d.epi, d.impl, d.force_block_n, d.force_m_sub = epi, impl, force_block_n, force_m_sub
   st = torch.cuda.current_stream().cuda_stream
   _lib.check(_lib.lib().gddim_conv_gemm(C.byref(d), st), "gddim_conv_gemm")

@@ -138,6 +138,7 @@ typedef struct {
   int impl;                                                 /* 0 tcgen05, 1 CUDA-core reference */
   int force_block_n;                                        /* 0 = heuristic */
   int force_m_sub;                                          /* with force_block_n: 2 = 256-row CTA tiles */
+  int n_store;                                              /* 0 = all N; else store only columns < n_store (fp32) */
 } gddim_gemm_desc;
 int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream);
 

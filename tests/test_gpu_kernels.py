@@ -183,3 +183,18 @@ def test_dct_matches_oracle_and_roundtrips(C):
   np.testing.assert_allclose(y, ob.batch_img_dct(x.astype(np.float64)), atol=2e-5)
   np.testing.assert_allclose(gblur.batch_img_idct(y), x, atol=2e-5)
   np.testing.assert_allclose(gblur.batch_img_idct(x), ob.batch_img_idct(x.astype(np.float64)), atol=2e-5)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
+def test_few_channel_output_umma_or_ref(impl):
+  """Head conv: C_out = 6 padded to a 32-wide N tile, only 6 columns stored densely ([.., 6] fp32)."""
+  g = torch.Generator().manual_seed(77)
+  a = torch.randn(3, 32, 32, 128, generator=g).to(torch.float16)
+  k = (torch.randn(3, 3, 128, 6, generator=g) / np.sqrt(9 * 128)).numpy()
+  bias = torch.randn(6, generator=g)
+  want = _conv_ref(a, k, 9) + bias.double()
+  kp = np.zeros((3, 3, 128, 32), np.float32); kp[..., :6] = k
+  bp = torch.zeros(32); bp[:6] = bias
+  o32, _ = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(kp), 32, taps0=9, bias=bp.cuda(), impl=impl, n_store=6)
+  assert o32.shape == (3, 32, 32, 6)
+  assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
