@@ -118,7 +118,7 @@ def run_reference(args):
   model = net.ScoreNet(cfg, cld=True)
   params = model.init_params(seed=1234, nondegenerate=True)
   threads = os.cpu_count() or 1
-  batch = args.cpu_batch or 1
+  batch = args.cpu_batch or 2
   for _ in range(max(args.warmup, 0)):
     cpu_port_sample(cfg, params, batch, min(args.nfe, 4), args.order, threads)     # short warm-up (thread pools, caches)
   t = 0.0
@@ -144,7 +144,6 @@ def run_ours(args):
   from gddim_b200 import dist as gdist
   from gddim_b200 import net
   from gddim_b200.cld import sampling, sde_lib
-  from oracle import cld as oc      # prior noise generator only (numpy); nothing under oracle/ is timed here
 
   rank, local_rank, world = gdist.init_process_group()
   assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -167,7 +166,10 @@ def run_ours(args):
   core = psampler.core
 
   # one global prior draw, sliced per rank (sampling.py:235)
-  u_glob = oc.prior_sampling(np.random.default_rng(0), (world * B, 32, 32, 3)).astype(np.float32)
+  rng = np.random.default_rng(0)
+  shape = (world * B, 32, 32, 3)
+  u_glob = np.stack([rng.standard_normal(shape), rng.standard_normal(shape) / np.sqrt(cfg.model.m_inv)],
+                    axis=-1).astype(np.float32)          # x ~ N(0,1), v ~ N(0, 1/m_inv)  (sde_lib.py:270-274)
   u_host = np.ascontiguousarray(gdist.shard(u_glob, rank, world))
   u_pin = torch.from_numpy(u_host).pin_memory()
   u_dev = u_pin.cuda()
@@ -237,10 +239,17 @@ def run_ours(args):
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     ach = gemm_flops / (ms_kind["conv_gemm"] * 1e-3) * 1e-12 if ms_kind["conv_gemm"] > 0 else 0.0
     tot = sum(ms_kind.values())
+    # DRAM bytes per launch of the same kernel family from the committed ncu pass (profiles/, tools/profile.sh)
+    traffic = None
+    try:
+      traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+      pass
     roof = {"bound": "tensor", "kernel": "conv_gemm_umma_kernel (all conv3x3 / 1x1 / attention GEMM launches)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
-            "traffic": None, "launches": gemm_launches, "avg_launch_ms": ms_kind["conv_gemm"] / max(gemm_launches, 1),
+            "flop_per_launch": gemm_flops / max(gemm_launches, 1),
+            "traffic": traffic, "launches": gemm_launches, "avg_launch_ms": ms_kind["conv_gemm"] / max(gemm_launches, 1),
             "share_of_step": ms_kind["conv_gemm"] / tot if tot else None,
             "ms_by_kernel_family": {k: round(v_, 3) for k, v_ in ms_kind.items()}}
 
@@ -251,7 +260,7 @@ def run_ours(args):
   cpu = None
   if world == 1 and not args.no_cpu_baseline:
     threads = os.cpu_count() or 1
-    cb = args.cpu_batch or 1
+    cb = args.cpu_batch or 2
     v_cpu, dt = cpu_port_sample(cfg, model.params, cb, nfe, order, threads)
     cpu = {"value": v_cpu, "unit": "images/s", "cores": threads, "kind": "port",
            "sample": f"{cb} image(s) x {nfe} NFE, same net/sampler, torch-CPU fp32 restatement of the reference "
@@ -279,6 +288,12 @@ def main():
     run_reference(args)
   else:
     run_ours(args)
+    try:
+      import torch.distributed as dist
+      if dist.is_initialized():
+        dist.destroy_process_group()
+    except Exception:
+      pass
 
 
 if __name__ == "__main__":

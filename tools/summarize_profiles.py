@@ -61,7 +61,34 @@ def main():
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
       lines.append(f"| {k} | {v[0]} | {v[1]:.0f} | {100*v[1]/tot:.1f}% |")
     lines.append("")
-  for rep, title in (("prof_gemm.ncu-rep", "conv_gemm_umma_kernel (ncu --set full)"), ("prof_gn.ncu-rep", "GroupNorm kernels (ncu --set full)")):
+  p = os.path.join(SRC, "gemm_traffic.csv")
+  if os.path.exists(p):
+    rows = [r for r in csv.reader(open(p)) if len(r) > 5 and r[0].strip('"').isdigit()]
+    per = collections.defaultdict(dict)
+    for r in rows:
+      val = float(r[-1].replace(",", ""))
+      unit = r[-2]
+      if r[-3] == "gpu__time_duration.sum":
+        val = val / 1000.0 if unit == "ns" else (val if unit in ("us", "usecond") else val * 1000.0)
+      else:
+        val = val * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+      per[r[0]][r[-3]] = val
+      per[r[0]]["name"] = r[4].split("(")[0]
+    n = len(per)
+    rd = sum(v.get("dram__bytes_read.sum", 0.0) for v in per.values())
+    wr = sum(v.get("dram__bytes_write.sum", 0.0) for v in per.values())
+    us = sum(v.get("gpu__time_duration.sum", 0.0) for v in per.values())
+    json.dump({"kernel": "conv_gemm_umma_kernel (all launches of one network evaluation, deep NCSN++, batch 256)",
+               "launches": n, "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": (rd + wr) / max(n, 1),
+               "sum_duration_us": us, "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum (tools/profile.sh)"},
+              open(os.path.join(OUT, f"{TAG}_gemm_traffic.json"), "w"), indent=1)
+    lines.append(f"## DRAM traffic of the {n} conv_gemm_umma launches of one evaluation: read {rd/1e9:.2f} GB, write {wr/1e9:.2f} GB, "
+                 f"{(rd+wr)/max(n,1)/1e6:.1f} MB per launch; algorithmic minimum = operands + outputs (see DESIGN.md)\n")
+    import shutil
+    shutil.copy(p, os.path.join(OUT, f"{TAG}_gemm_traffic.csv"))
+  for rep, title in (("prof_gemm256.ncu-rep", "conv_gemm_umma_kernel<256,0,1> (3x3 conv 256->256 @16x16; ncu --set full)"),
+                     ("prof_gemm128.ncu-rep", "conv_gemm_umma_kernel<128,0,2> (3x3 conv 128->128 @32x32, 256-row tiles; ncu --set full)"),
+                     ("prof_gn.ncu-rep", "gn_apply_kernel (ncu --set full)")):
     p = os.path.join(SRC, rep)
     if os.path.exists(p):
       lines.append(f"## {title}\n")
