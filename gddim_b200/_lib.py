@@ -92,6 +92,7 @@ SIGNATURES = {
     "gddim_conv_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "gddim_group_norm": (C.c_int, [C.POINTER(NormDesc), _P]),
     "gddim_sampler_create": (C.c_int, [_P, C.POINTER(SamplerCfg), _P, _P, C.POINTER(_P)]),
+    "gddim_sampler_create_ts": (C.c_int, [_P, C.POINTER(SamplerCfg), _P, _P, _P, C.c_int, C.POINTER(_P)]),
     "gddim_sampler_destroy": (None, [_P]),
     "gddim_sampler_coef": (C.c_longlong, [_P, _P, C.c_longlong]),
     "gddim_sampler_num_steps": (C.c_int, [_P]),

@@ -16,7 +16,7 @@ import numpy as np
 from .. import _lib
 from .. import net as _net
 
-_NEXT = ("sdeis", "ldeis", "hybdeis", "mldeis", "ode", "sscs", "em")
+_NEXT = ("sdeis", "ldeis", "mldeis", "ode", "sscs", "em")
 
 
 def get_data_shape(config):
@@ -28,9 +28,13 @@ def get_data_shape(config):
 
 def get_rev_ts(sde, ts_order, num_step):
   """sampling.py:241-249 (fp64 table from the library, returned as fp32 like the reference)."""
-  out = np.empty(num_step + 1)
-  _lib.check(_lib.lib().gddim_rev_ts(float(sde.T), float(sde.sampling_eps), int(ts_order), int(num_step),
-                                      out.ctypes.data))
+  if float(ts_order) != int(ts_order):
+    out = np.power(np.linspace(np.power(sde.T, 1.0 / ts_order), np.power(sde.sampling_eps, 1.0 / ts_order),
+                               num_step + 1), ts_order)
+  else:
+    out = np.empty(num_step + 1)
+    _lib.check(_lib.lib().gddim_rev_ts(float(sde.T), float(sde.sampling_eps), int(ts_order), int(num_step),
+                                        out.ctypes.data))
   return out.astype(np.float64 if getattr(sde, "x64", False) else np.float32)
 
 
@@ -56,6 +60,12 @@ def get_sampling_fn(config, sde, model, shape, inverse_scaler):
     return get_deis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
                             inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
                             ts_order=config.sampling.ts_order, denoising=config.sampling.noise_removal, is_p=True)
+  if name == "hybdeis":
+    return get_hyd_deis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
+                                inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
+                                noise_nfe_ratio=config.sampling.noise_nfe_ratio,
+                                img_t_ratio=config.sampling.img_t_ratio, ts_order=config.sampling.ts_order,
+                                denoising=config.sampling.noise_removal, is_p=True)
   if name in _NEXT:
     raise NotImplementedError(f"sampler '{name}' is not part of the round-1 hot path (SURVEY.md 8f)")
   raise RuntimeError
@@ -65,13 +75,14 @@ class _Sampler:
   """Owns the C sampler object for one (network context, batch) pair."""
 
   def __init__(self, kind, sde, model, data_shape, nfe, inverse_scaler, deis_order, ts_order, denoising, is_p,
-               use_graph=True):
+               use_graph=True, rev_ts=None):
     self.kind, self.sde, self.model, self.data_shape = kind, sde, model, tuple(data_shape)
     self.nfe, self.order, self.ts_order, self.denoising, self.is_p = int(nfe), int(deis_order), int(ts_order), \
         bool(denoising), is_p
     self.inverse_scaler = inverse_scaler
     self.mul, self.add, self.affine = _affine_of(inverse_scaler)
     self.use_graph = use_graph
+    self.rev_ts = None if rev_ts is None else np.ascontiguousarray(np.asarray(rev_ts, np.float64))
     self._h, self._ctx_id, self._net = None, None, None
 
   def _destroy(self):
@@ -95,8 +106,12 @@ class _Sampler:
                           use_graph=int(self.use_graph), x_mul=self.mul if self.affine else 1.0,
                           x_add=self.add if self.affine else 0.0)
     h = C.c_void_p()
-    _lib.check(_lib.lib().gddim_sampler_create(ctx, C.byref(cfg), self.sde._h, None, C.byref(h)),
-               "gddim_sampler_create")
+    if self.rev_ts is None:
+      rc = _lib.lib().gddim_sampler_create(ctx, C.byref(cfg), self.sde._h, None, C.byref(h))
+    else:
+      rc = _lib.lib().gddim_sampler_create_ts(ctx, C.byref(cfg), self.sde._h, None, self.rev_ts.ctypes.data,
+                                               self.rev_ts.size, C.byref(h))
+    _lib.check(rc, "gddim_sampler_create")
     self._h, self._ctx_id, self._net = h, ctx.value, net
     return h
 
@@ -180,7 +195,11 @@ def get_order0_sampler(sde, model, data_shape, nfe, inverse_scaler, is_em=False,
 def get_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, ts_order=2, denoising=False,
                      is_p=False):
   """sampling.py:251-253 -> _impl_deis_sampler (204-239)."""
-  core = _Sampler(_lib.CLD_DEIS, sde, model, data_shape, nfe, inverse_scaler, deis_order, ts_order, denoising, is_p)
+  if float(ts_order) != int(ts_order):          # non-integer exponent (jnp.power accepts floats): explicit grid
+    grid = get_rev_ts(sde, ts_order, nfe - 1 if denoising else nfe)
+    return _impl_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, grid, denoising, is_p)
+  core = _Sampler(_lib.CLD_DEIS, sde, model, data_shape, nfe, inverse_scaler, deis_order, int(ts_order), denoising,
+                  is_p)
   return _wrap(core, sde, data_shape, is_p)
 
 
@@ -191,9 +210,33 @@ def _next(name):
   return f
 
 
+def _impl_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, rev_ts, denoising=False, is_p=False):
+  """sampling.py:204-239: the DEIS sampler on an explicit time grid rev_ts[num_step + 1]."""
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = np.asarray(rev_ts, np.float64)
+  assert rev_ts.shape[0] == num_step + 1
+  core = _Sampler(_lib.CLD_DEIS, sde, model, data_shape, nfe, inverse_scaler, deis_order, 2, denoising, is_p,
+                  rev_ts=rev_ts)
+  return _wrap(core, sde, data_shape, is_p)
+
+
+def get_hyd_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, noise_nfe_ratio=0.3, img_t_ratio=0.3,
+                         ts_order=2.0, denoising=False, is_p=False):
+  """sampling.py:255-269: uniform steps from T to img_t_ratio*T, then the polynomial grid (restated literally,
+  including that the second grid restarts at sde.T)."""
+  num_step = nfe - 1 if denoising else nfe
+  mid_t = sde.T * img_t_ratio
+  noise_nfe = int(num_step * noise_nfe_ratio)
+  img_nfe = num_step - noise_nfe
+  noise_ts = np.linspace(sde.T, mid_t, noise_nfe, endpoint=False)
+  img_ts = np.asarray(get_rev_ts(sde, ts_order, img_nfe), np.float64)
+  rev_ts = np.concatenate([noise_ts, img_ts])
+  assert rev_ts.shape[0] == num_step + 1
+  return _impl_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, rev_ts, denoising, is_p)
+
+
 get_sdeis_sampler = _next("get_sdeis_sampler")
 get_L_deis_sampler = _next("get_L_deis_sampler")
-get_hyd_deis_sampler = _next("get_hyd_deis_sampler")
 get_mldeis_sampler = _next("get_mldeis_sampler")
 get_ode_sampler = _next("get_ode_sampler")
 get_sscs_sampler = _next("get_sscs_sampler")

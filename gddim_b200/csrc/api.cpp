@@ -324,6 +324,11 @@ static void free_sampler_buffers(gddim_sampler* s) {
 
 int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
                          gddim_sampler** out) {
+  return gddim_sampler_create_ts(ctx, cfg, cld, blur, nullptr, 0, out);
+}
+
+int gddim_sampler_create_ts(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
+                            const double* rev_ts_in, int n_ts, gddim_sampler** out) {
   if (!ctx || !cfg || !out) return set_err("gddim_sampler_create: bad arguments");
   if (!ctx->net->finalized()) return set_err("gddim_sampler_create: context not finalized");
   if (cudaSetDevice(ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
@@ -348,7 +353,12 @@ int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gdd
     if (s->n_steps < 1 || s->n_steps < s->order) return set_err("gddim_sampler_create: nfe too small for this order");
     const int ts_order = is_o0 ? 2 : cfg->ts_order;             // sampling.py:162 hard-codes 2 for order0
     s->rev_ts.resize(s->n_steps + 1);
-    rev_timesteps(t.T, t.sampling_eps, ts_order, s->n_steps, s->rev_ts.data());
+    if (rev_ts_in != nullptr) {
+      if (is_o0 || n_ts != s->n_steps + 1) return set_err("gddim_sampler_create_ts: rev_ts must have num_step + 1 entries (deis sampler only)");
+      for (int i = 0; i <= s->n_steps; ++i) s->rev_ts[i] = rev_ts_in[i];
+    } else {
+      rev_timesteps(t.T, t.sampling_eps, ts_order, s->n_steps, s->rev_ts.data());
+    }
     const int per = s->order + 3;
     std::vector<double> c((size_t)s->n_steps * per * 4, 0.0);
     if (is_o0) {
@@ -382,6 +392,7 @@ int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gdd
     s->d_eps.resize(s->order + 1, nullptr);
   } else if (cfg->kind == GDDIM_BLUR_ORDER0) {
     if (!blur) return set_err("gddim_sampler_create: blur sampler needs a gddim_blur");
+    if (rev_ts_in != nullptr) return set_err("gddim_sampler_create_ts: custom time grids are supported by the CLD deis sampler only");
     if (net.cfg().state_mult != 1 || s->S != 32) return set_err("gddim_sampler_create: blur sampler needs a 32x32 state_mult=1 network");
     if (s->C > 5) return set_err("gddim_sampler_create: blur sampler supports up to 5 channels");
     s->is_blur = true;

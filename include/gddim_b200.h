@@ -175,6 +175,9 @@ typedef struct {
 /* exactly one of cld / blur is used, according to kind */
 int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
                          gddim_sampler** out);
+/* same with an explicit time grid rev_ts[num_step+1] (cld_jax/sampling.py:204 _impl_deis_sampler, :255 hybdeis) */
+int gddim_sampler_create_ts(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
+                            const double* rev_ts, int n_ts, gddim_sampler** out);
 void gddim_sampler_destroy(gddim_sampler* s);
 /* The table the sampler steps through (for index-exact parity checks): fp32 [n_steps, order+3, 2, 2] for CLD
  * deis.  Returns the number of floats written (or needed when out == NULL). */

@@ -297,10 +297,12 @@ def denoise_step(sde, eps_fn, u):
 
 
 def deis_sampler(sde, eps_fn, u, nfe, deis_order, ts_order=2, denoising=True, centered=True,
-                 dtype=np.float64, trace=None):
+                 dtype=np.float64, trace=None, rev_ts=None):
   """_impl_deis_sampler.sampler + get_deis_sampler, sampling.py:204-253 (single device, explicit u)."""
   num_step = nfe - 1 if denoising else nfe
-  rev_ts = get_rev_ts(sde.T, sde.sampling_eps, ts_order, num_step)
+  if rev_ts is None:
+    rev_ts = get_rev_ts(sde.T, sde.sampling_eps, ts_order, num_step)
+  assert len(rev_ts) == num_step + 1                         # sampling.py:268
   coef = sde.get_deis_coef(deis_order, rev_ts).astype(dtype)
   u = np.asarray(u, dtype=dtype)
   eps_pred = np.stack([u] * (deis_order + 1))
@@ -316,6 +318,16 @@ def deis_sampler(sde, eps_fn, u, nfe, deis_order, ts_order=2, denoising=True, ce
   if centered:
     x = (x + 1.0) / 2.0
   return x, v, nfe
+
+
+def hyd_rev_ts(sde, nfe, noise_nfe_ratio=0.3, img_t_ratio=0.3, ts_order=2.0, denoising=True):
+  """get_hyd_deis_sampler's grid, sampling.py:255-268 (the polynomial part restarts at sde.T, as written there)."""
+  num_step = nfe - 1 if denoising else nfe
+  mid_t = sde.T * img_t_ratio
+  noise_nfe = int(num_step * noise_nfe_ratio)
+  img_nfe = num_step - noise_nfe
+  noise_ts = np.linspace(sde.T, mid_t, noise_nfe, endpoint=False)
+  return np.concatenate([noise_ts, get_rev_ts(sde.T, sde.sampling_eps, ts_order, img_nfe)])
 
 
 def order0_sampler(sde, eps_fn, u, nfe, denoising=True, centered=True, dtype=np.float64):

@@ -175,3 +175,85 @@ def test_full_batch_properties_config2(deep):
   x2, v2, _ = fn(0, model, 2, u=ud[100:102].contiguous())
   assert rel_l2(x[100:102].cpu().numpy(), x2.cpu().numpy()) < 1e-4
   assert rel_l2(v[100:102].cpu().numpy(), v2.cpu().numpy()) < 1e-4
+
+
+def test_config4_sampler_deep_order3(deep):
+  """BASELINE config 4's sampler (deis_order=3: table [49,6,2,2], 4 history buffers) on the deep network, per-GPU
+  shard semantics: two ranks' shards sampled separately equal the same rows of one global batch."""
+  cfg, model, net_fn = deep
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_deis_sampler(sde, model, (32, 32, 3), 50, inv, 3, ts_order=2, denoising=True)
+  u = prior_u(4, seed=8)
+  x, v, n = fn(0, model, 4, u=u)
+  ox, ov, _ = oracle_cld_sample(cfg, net_fn, u[:2], 50, 3, denoising=True)
+  print(f"config4 deep nfe50 o3: x {rel_l2(x[:2], ox):.2e} v {rel_l2(v[:2], ov):.2e}")
+  assert n == 50 and rel_l2(x[:2], ox) < TOL and rel_l2(v[:2], ov) < TOL
+  from gddim_b200 import dist as gdist
+  xa, _, _ = fn(0, model, 2, u=gdist.shard(u, 0, 2))
+  xb, _, _ = fn(0, model, 2, u=gdist.shard(u, 1, 2))
+  assert rel_l2(np.concatenate([xa, xb]), x) < 1e-4
+
+
+def test_config3_blur_deep_small_batch():
+  """BASELINE config 3: blur diffusion, sigma_blur_max=1.0, NFE=50, deep network (C_in = 3), at batch 2."""
+  from gddim_b200 import configs
+  from oracle import ncsnpp as on
+  cfg = configs.blur_ddpm_deep_cifar10(1.0)
+  model = net.ScoreNet(cfg, cld=False)
+  p = model.init_params(seed=1234, nondegenerate=True)
+  net_fn = on.make_net_fn(p, cfg)
+  cfg.sampling.nfe = 50
+  fn = bsampling.get_sampling_fn(cfg, bsde.from_config(cfg), model, None, inv, is_p=False)
+  y = prior_u(2, seed=12, cld=False)
+  x, n = fn(0, model, 2, u=y)
+  ox, _ = oracle_blur_sample(cfg, net_fn, y, 50)
+  print(f"config3 blur deep nfe50: x {rel_l2(x, ox):.2e}")
+  assert n == 50 and rel_l2(x, ox) < TOL
+
+
+@pytest.mark.parametrize("batch", [1, 3, 5])
+def test_ragged_batches(batch):
+  """Batches that do not fill a 128-row tile at the low-resolution levels (4x4: 16 rows per image)."""
+  cfg, model, net_fn = build("cld_deep")
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_deis_sampler(sde, model, (32, 32, 3), 4, inv, 1, ts_order=2, denoising=True)
+  u = prior_u(batch, seed=20 + batch)
+  x, v, _ = fn(0, model, batch, u=u)
+  ox, ov, _ = oracle_cld_sample(cfg, net_fn, u, 4, 1, denoising=True)
+  assert rel_l2(x, ox) < TOL and rel_l2(v, ov) < TOL
+
+
+def test_image_size_64_celeba_like():
+  """ddpmpp_celeba-like geometry (64x64, attention at 16x16, 4 levels: 64/32/16/8) on a narrow network."""
+  from gddim_b200 import configs
+  from oracle import cld as oc
+  from oracle import ncsnpp as on
+  cfg = configs.cld_ddpmpp_cifar10()
+  cfg.data.image_size, cfg.model.nf, cfg.model.num_res_blocks = 64, 64, 1
+  model = net.ScoreNet(cfg, cld=True)
+  p = model.init_params(seed=5, nondegenerate=True)
+  net_fn = on.make_net_fn(p, cfg)
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_deis_sampler(sde, model, (64, 64, 3), 4, inv, 1, ts_order=2, denoising=True)
+  u = oc.prior_sampling(np.random.default_rng(3), (2, 64, 64, 3)).astype(np.float32)
+  x, v, _ = fn(0, model, 2, u=u)
+  o = oc.from_config(cfg)
+  ox, ov, _ = oc.deis_sampler(o, oc.make_eps_fn(o, net_fn), u, 4, 1, denoising=True, dtype=np.float32)
+  print(f"64x64: x {rel_l2(x, ox):.2e}")
+  assert rel_l2(x, ox) < TOL and rel_l2(v, ov) < TOL
+
+
+def test_hybdeis_custom_time_grid_matches_oracle():
+  """'hybdeis' (sampling.py:255-269) = the DEIS sampler on a two-part time grid, through get_sampling_fn."""
+  from oracle import cld as oc
+  cfg, model, net_fn = build("cld_deep")
+  cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "hybdeis", 9, 2
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_sampling_fn(cfg, sde, model, None, inv)
+  u = prior_u(2, seed=31)
+  xs, vs, nfe = fn(None, model, 2, u=u[None])
+  o = oc.from_config(cfg)
+  grid = oc.hyd_rev_ts(o, 9, cfg.sampling.noise_nfe_ratio, cfg.sampling.img_t_ratio, cfg.sampling.ts_order, True)
+  ox, ov, _ = oc.deis_sampler(o, oc.make_eps_fn(o, net_fn), u, 9, 2, denoising=True, dtype=np.float32, rev_ts=grid)
+  cfg.sampling.method = "deis"
+  assert nfe == 9 and rel_l2(xs[0], ox) < TOL and rel_l2(vs[0], ov) < TOL
