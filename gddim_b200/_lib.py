@@ -22,7 +22,8 @@ class ModelCfg(C.Structure):
 class SamplerCfg(C.Structure):
   _fields_ = [("kind", C.c_int), ("nfe", C.c_int), ("deis_order", C.c_int), ("ts_order", C.c_int),
               ("denoising", C.c_int), ("mixed_score", C.c_int), ("use_graph", C.c_int),
-              ("x_mul", C.c_float), ("x_add", C.c_float)]
+              ("x_mul", C.c_float), ("x_add", C.c_float), ("lambda_coef", C.c_float), ("sdeis_use_order0", C.c_int),
+              ("seed", C.c_ulonglong)]
 
 
 class GemmDesc(C.Structure):
@@ -45,7 +46,7 @@ class NormDesc(C.Structure):
               ("raw_scale", C.c_float)]
 
 
-CLD_DEIS, CLD_ORDER0, BLUR_ORDER0 = 0, 1, 2
+CLD_DEIS, CLD_ORDER0, BLUR_ORDER0, CLD_SDEIS = 0, 1, 2, 3
 
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
@@ -78,6 +79,8 @@ SIGNATURES = {
     "gddim_cld_eps_integrand": (C.c_int, [_P, _P, C.c_int, _P]),
     "gddim_cld_deis_coef": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
     "gddim_cld_order0_coef": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "gddim_cld_sdeis_coef": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "gddim_mvn_factor_svd": (C.c_int, [_P, _P]),
     "gddim_rev_ts": (C.c_int, [C.c_double, C.c_double, C.c_int, C.c_int, _P]),
     "gddim_blur_create": (C.c_int, [C.c_double, C.c_double, C.POINTER(_P)]),
     "gddim_blur_destroy": (None, [_P]),
@@ -98,6 +101,7 @@ SIGNATURES = {
     "gddim_sampler_num_steps": (C.c_int, [_P]),
     "gddim_sampler_rev_ts": (C.c_int, [_P, _P, C.c_int]),
     "gddim_sample": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "gddim_sample_noise": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "gddim_sampler_launch_count": (C.c_longlong, [_P]),
 }
 

@@ -5,9 +5,9 @@
 process drives one GPU; multi-GPU runs launch one process per GPU and shard the batch axis).
 The whole loop (network evaluations + multistep updates + denoising step) runs inside libgddim_b200.so.
 
-Implemented: 'deis' (204-253) and 'order0' (156-202, is_em=False).  'sdeis', 'ldeis', 'hybdeis', 'mldeis',
-'ode', 'sscs', 'em' are SURVEY.md 8(f) "next" rows and raise NotImplementedError; unknown names raise a bare
-RuntimeError exactly like sampling.py:152-153.
+Implemented: 'deis' (204-253), 'order0' (156-202, is_em=False), 'hybdeis' (255-269) and the stochastic 'sdeis'
+(380-427, on LambdaSDE).  'ldeis', 'mldeis', 'ode', 'sscs', 'em' are SURVEY.md 8(f) "next" rows and raise
+NotImplementedError; unknown names raise a bare RuntimeError exactly like sampling.py:152-153.
 """
 import ctypes as C
 
@@ -16,7 +16,7 @@ import numpy as np
 from .. import _lib
 from .. import net as _net
 
-_NEXT = ("sdeis", "ldeis", "mldeis", "ode", "sscs", "em")
+_NEXT = ("ldeis", "mldeis", "ode", "sscs", "em")
 
 
 def get_data_shape(config):
@@ -60,6 +60,11 @@ def get_sampling_fn(config, sde, model, shape, inverse_scaler):
     return get_deis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
                             inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
                             ts_order=config.sampling.ts_order, denoising=config.sampling.noise_removal, is_p=True)
+  if name == "sdeis":
+    return get_sdeis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
+                             inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
+                             lambda_coef=config.sampling.lambda_coef, use_order0=config.sampling.sdeis_use_order0,
+                             ts_order=config.sampling.ts_order, denoising=config.sampling.noise_removal, is_p=True)
   if name == "hybdeis":
     return get_hyd_deis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
                                 inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
@@ -75,7 +80,7 @@ class _Sampler:
   """Owns the C sampler object for one (network context, batch) pair."""
 
   def __init__(self, kind, sde, model, data_shape, nfe, inverse_scaler, deis_order, ts_order, denoising, is_p,
-               use_graph=True, rev_ts=None):
+               use_graph=True, rev_ts=None, lambda_coef=0.0, use_order0=True):
     self.kind, self.sde, self.model, self.data_shape = kind, sde, model, tuple(data_shape)
     self.nfe, self.order, self.ts_order, self.denoising, self.is_p = int(nfe), int(deis_order), int(ts_order), \
         bool(denoising), is_p
@@ -83,6 +88,7 @@ class _Sampler:
     self.mul, self.add, self.affine = _affine_of(inverse_scaler)
     self.use_graph = use_graph
     self.rev_ts = None if rev_ts is None else np.ascontiguousarray(np.asarray(rev_ts, np.float64))
+    self.lambda_coef, self.use_order0, self.seed = float(lambda_coef), bool(use_order0), 0
     self._h, self._ctx_id, self._net = None, None, None
 
   def _destroy(self):
@@ -104,7 +110,8 @@ class _Sampler:
     cfg = _lib.SamplerCfg(kind=self.kind, nfe=self.nfe, deis_order=self.order, ts_order=self.ts_order,
                           denoising=int(self.denoising), mixed_score=int(bool(self.sde.mixed_score)),
                           use_graph=int(self.use_graph), x_mul=self.mul if self.affine else 1.0,
-                          x_add=self.add if self.affine else 0.0)
+                          x_add=self.add if self.affine else 0.0, lambda_coef=self.lambda_coef,
+                          sdeis_use_order0=int(self.use_order0), seed=int(self.seed))
     h = C.c_void_p()
     if self.rev_ts is None:
       rc = _lib.lib().gddim_sampler_create(ctx, C.byref(cfg), self.sde._h, None, C.byref(h))
@@ -121,12 +128,13 @@ class _Sampler:
     n = _lib.lib().gddim_sampler_coef(h, None, 0)
     out = np.empty(n, np.float32)
     _lib.lib().gddim_sampler_coef(h, out.ctypes.data, n)
-    return out.reshape(-1, self.order + 3 if self.kind == _lib.CLD_DEIS else 3, 2, 2)
+    per = {_lib.CLD_DEIS: self.order + 3, _lib.CLD_ORDER0: 3, _lib.CLD_SDEIS: self.order + 4}[self.kind]
+    return out.reshape(-1, per, 2, 2)
 
   def launch_count(self):
     return int(_lib.lib().gddim_sampler_launch_count(self._h)) if self._h is not None else 0
 
-  def run(self, pstate, batch_size, u, trace=False):
+  def run(self, pstate, batch_size, u, trace=False, noise=None):
     import torch
     _lib.require_cuda("sampler")
     net = _net.resolve_net(self.model, pstate, cld=True)
@@ -140,18 +148,27 @@ class _Sampler:
     n_steps = _lib.lib().gddim_sampler_num_steps(h)
     if trace:
       tr = torch.empty((n_steps,) + shape, dtype=torch.float32, device="cuda")
+    nz, nz_keep = None, None
+    if noise is not None:                 # explicit standard normals [n_steps, B, H, W, C, 2] (parity hook for sdeis)
+      if self.kind != _lib.CLD_SDEIS:
+        raise ValueError("noise= is only meaningful for the sdeis sampler")
+      nz_keep = (noise.detach().to(device="cuda", dtype=torch.float32) if torch.is_tensor(noise)
+                 else torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32)).cuda()).contiguous()
+      if tuple(nz_keep.shape) != (n_steps,) + shape:
+        raise ValueError(f"noise has shape {tuple(nz_keep.shape)}, expected {(n_steps,) + shape}")
+      nz = nz_keep.data_ptr()
     if is_np:
       uh = np.ascontiguousarray(u, dtype=np.float32)
       x = np.empty((batch_size,) + self.data_shape, np.float32)
       v = np.empty_like(x)
-      _lib.check(_lib.lib().gddim_sample(h, uh.ctypes.data, x.ctypes.data, v.ctypes.data, batch_size, 1,
-                                          tr.data_ptr() if tr is not None else None, st), "gddim_sample")
+      _lib.check(_lib.lib().gddim_sample_noise(h, uh.ctypes.data, x.ctypes.data, v.ctypes.data, batch_size, 1,
+                                                tr.data_ptr() if tr is not None else None, nz, st), "gddim_sample")
     else:
       ud = u.detach().to(device="cuda", dtype=torch.float32).contiguous()
       x = torch.empty((batch_size,) + self.data_shape, dtype=torch.float32, device="cuda")
       v = torch.empty_like(x)
-      _lib.check(_lib.lib().gddim_sample(h, ud.data_ptr(), x.data_ptr(), v.data_ptr(), batch_size, 0,
-                                          tr.data_ptr() if tr is not None else None, st), "gddim_sample")
+      _lib.check(_lib.lib().gddim_sample_noise(h, ud.data_ptr(), x.data_ptr(), v.data_ptr(), batch_size, 0,
+                                                tr.data_ptr() if tr is not None else None, nz, st), "gddim_sample")
     if not self.affine:
       x = self.inverse_scaler(x)
     if trace:
@@ -159,12 +176,21 @@ class _Sampler:
     return x, v, self.nfe
 
 
+def _seed_of(rng):
+  if rng is None:
+    return 0
+  return int(np.asarray(rng).astype(np.uint64).ravel().sum() % (2 ** 63))
+
+
 def _wrap(core, sde, data_shape, is_p):
-  def sampler(rng, state, batch_size, u=None, trace=False):
+  def sampler(rng, state, batch_size, u=None, trace=False, noise=None):
     """sampling.py:212-230 (non-pmapped): u (B,H,W,C,2) -> (x, v, nfe)."""
     if u is None:
       u = sde.prior_sampling(rng, (batch_size,) + tuple(data_shape))
-    return core.run(state, batch_size, u, trace=trace)
+    if core.kind == _lib.CLD_SDEIS and noise is None and _seed_of(rng) != core.seed:
+      core.seed = _seed_of(rng)          # a new key re-seeds the Philox stream (sampler object is rebuilt)
+      core._destroy()
+    return core.run(state, batch_size, u, trace=trace, noise=noise)
 
   def psampler(prng, pstate, batch_size, u=None):
     """sampling.py:232-237: leading axis = local devices driven by this process (1)."""
@@ -235,7 +261,15 @@ def get_hyd_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order
   return _impl_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, rev_ts, denoising, is_p)
 
 
-get_sdeis_sampler = _next("get_sdeis_sampler")
+def get_sdeis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, lambda_coef=0, use_order0=True,
+                      ts_order=2, denoising=False, is_p=False):
+  """sampling.py:423-427 -> _impl_sdeis_sampler (416-421) on LambdaSDE(sde, lambda_coef, use_order0): the DEIS mean
+  update plus N(0, P_i) noise per (x, v) pair with P_i the conditional reverse covariance (sde_lib.py:381-399).
+  The injected normals come from a Philox4x32-10 stream keyed by `rng` (JAX's threefry is not reproduced) or from
+  the explicit `noise=` array of the non-pmapped sampler."""
+  core = _Sampler(_lib.CLD_SDEIS, sde, model, data_shape, nfe, inverse_scaler, deis_order, int(ts_order), denoising,
+                  is_p, lambda_coef=lambda_coef, use_order0=use_order0)
+  return _wrap(core, sde, data_shape, is_p)
 get_L_deis_sampler = _next("get_L_deis_sampler")
 get_mldeis_sampler = _next("get_mldeis_sampler")
 get_ode_sampler = _next("get_ode_sampler")

@@ -187,8 +187,43 @@ def _np_rng(rng):
 
 
 class LambdaSDE:
-  def __init__(self, *a, **k):
-    raise NotImplementedError("LambdaSDE (stochastic gDDIM) is outside the round-1 hot path (SURVEY.md 8f N1)")
+  """Stand-in for sde_lib.py:334-466 (stochastic gDDIM): hat-Psi table, conditional reverse covariance and the
+  coefficient tables, computed in fp64 by the library.  Only what the sdeis sampler reads is exposed."""
+
+  def __init__(self, sde, lambda_coef=0.1, use_order0=True, used_cache=True):
+    self.sde = sde
+    self.mixed_score = sde.mixed_score
+    self.prior_sampling = sde.prior_sampling
+    self.v_invR = sde.v_invR
+    self.x64 = sde.x64
+    self.use_order0, self.lambda_coef = use_order0, lambda_coef
+    self.T, self.sampling_eps = sde.T, sde.sampling_eps
+    self._h = sde._h
+    self._dt = np.float64 if sde.x64 else np.float32
+
+  def get_deis_coef(self, order, rev_timesteps, used_cache=True):
+    """sde_lib.py:435-454 -> [N, order+4, 2, 2]: x_coef, order+2 eps slots, covariance."""
+    rev = _d(rev_timesteps)
+    out = np.empty((rev.size - 1, order + 4, 2, 2))
+    _lib.check(_lib.lib().gddim_cld_sdeis_coef(self._h, float(self.lambda_coef), int(bool(self.use_order0)), int(order),
+                                                rev.ctypes.data, rev.size, out.ctypes.data), "gddim_cld_sdeis_coef")
+    return out.astype(self._dt)
+
+  def get_order0_coef(self, rev_timesteps, used_cache=True):
+    """sde_lib.py:457-466 -> [N, 3, 2, 2] (x_coef, eps_coef, cov)."""
+    rev = _d(rev_timesteps)
+    out = np.empty((rev.size - 1, 4, 2, 2))
+    _lib.check(_lib.lib().gddim_cld_sdeis_coef(self._h, float(self.lambda_coef), 1, 0, rev.ctypes.data, rev.size,
+                                                out.ctypes.data), "gddim_cld_sdeis_coef")
+    return out[:, [0, 1, 3]].astype(self._dt)
+
+
+def mvn_factor_svd(cov):
+  """U sqrt(S) of a 2x2 matrix as jax.random.multivariate_normal(method='svd') applies it (sign-normalised)."""
+  c = _d(cov)
+  out = np.empty((2, 2))
+  _lib.check(_lib.lib().gddim_mvn_factor_svd(c.ctypes.data, out.ctypes.data))
+  return out
 
 
 class LSDE:

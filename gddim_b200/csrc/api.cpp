@@ -34,7 +34,10 @@ struct gddim_sampler {
   int n_steps = 0, order = 0, C = 0, S = 0;
   bool is_blur = false;
   std::vector<double> rev_ts;
-  std::vector<float> coef;            // CLD: [n_steps][order+3][4]
+  std::vector<float> coef;            // CLD: [n_steps][per][4], per = order+3 (deis/order0) or order+4 (sdeis)
+  int per = 0;
+  std::vector<float> nfac;            // sdeis: [n_steps][4] factor applied to the standard normals
+  unsigned long long calls = 0;       // sample calls so far (Philox stream id)
   float den_A[4], den_C[4];
   std::vector<float> mixm;            // [n_steps + 1][4]  R(t)^-1 [[0,0],[0,1]] when mixed_score
   float* d_temb_all = nullptr;        // [n_steps (+1 denoise)][temb_total]
@@ -182,6 +185,19 @@ int gddim_cld_deis_coef(const gddim_cld* cld, int order, const double* rev_ts, i
 int gddim_cld_order0_coef(const gddim_cld* cld, const double* rev_ts, int n_ts, double* mean_out, double* eps_out) {
   if (!cld || !rev_ts || !mean_out || !eps_out || n_ts < 2) return set_err("gddim_cld_order0_coef: bad arguments");
   cld->t->order0_coef(rev_ts, n_ts, mean_out, eps_out);
+  return 0;
+}
+int gddim_cld_sdeis_coef(const gddim_cld* cld, double lambda_coef, int use_order0, int order, const double* rev_ts,
+                         int n_ts, double* out) {
+  if (!cld || !rev_ts || !out || order < 0 || order > 4 || n_ts < 2 || n_ts - 1 < order)
+    return set_err("gddim_cld_sdeis_coef: bad arguments");
+  LambdaTables lt(*cld->t, lambda_coef, use_order0 != 0);
+  lt.deis_coef(order, rev_ts, n_ts, out);
+  return 0;
+}
+int gddim_mvn_factor_svd(const double* cov, double* out) {
+  if (!cov || !out) return set_err("gddim_mvn_factor_svd: bad arguments");
+  put(out, mvn_factor_svd(Mat2{cov[0], cov[1], cov[2], cov[3]}));
   return 0;
 }
 int gddim_rev_ts(double T, double eps, int ts_order, int num_step, double* out) {
@@ -342,7 +358,7 @@ int gddim_sampler_create_ts(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const 
   const size_t state_elems = (size_t)B * s->S * s->S * net.net_channels();
   std::vector<double> eval_ts;       // the time of every network evaluation, in order
 
-  if (cfg->kind == GDDIM_CLD_DEIS || cfg->kind == GDDIM_CLD_ORDER0) {
+  if (cfg->kind == GDDIM_CLD_DEIS || cfg->kind == GDDIM_CLD_ORDER0 || cfg->kind == GDDIM_CLD_SDEIS) {
     if (!cld) return set_err("gddim_sampler_create: CLD sampler needs a gddim_cld");
     if (net.cfg().state_mult != 2) return set_err("gddim_sampler_create: CLD sampler needs a state_mult=2 network");
     const CldTables& t = *cld->t;
@@ -359,9 +375,24 @@ int gddim_sampler_create_ts(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const 
     } else {
       rev_timesteps(t.T, t.sampling_eps, ts_order, s->n_steps, s->rev_ts.data());
     }
-    const int per = s->order + 3;
+    const bool is_sdeis = cfg->kind == GDDIM_CLD_SDEIS;
+    const int per = s->order + (is_sdeis ? 4 : 3);
+    s->per = per;
     std::vector<double> c((size_t)s->n_steps * per * 4, 0.0);
-    if (is_o0) {
+    if (is_sdeis) {
+      if (rev_ts_in != nullptr) return set_err("gddim_sampler_create_ts: custom time grids are supported by the deis sampler only");
+      LambdaTables lt(t, (double)cfg->lambda_coef, cfg->sdeis_use_order0 != 0);
+      lt.deis_coef(s->order, s->rev_ts.data(), s->n_steps + 1, c.data());
+      // sampling.py:420: the last covariance is zeroed ("avoid numerical error")
+      for (int k = 0; k < 4; ++k) c[((size_t)(s->n_steps - 1) * per + (per - 1)) * 4 + k] = 0.0;
+      s->nfac.resize((size_t)s->n_steps * 4);
+      for (int i = 0; i < s->n_steps; ++i) {
+        const double* q = &c[((size_t)i * per + (per - 1)) * 4];
+        const Mat2 f = mvn_factor_svd(Mat2{q[0], q[1], q[2], q[3]});
+        s->nfac[i * 4 + 0] = (float)f.a; s->nfac[i * 4 + 1] = (float)f.b;
+        s->nfac[i * 4 + 2] = (float)f.c; s->nfac[i * 4 + 3] = (float)f.d;
+      }
+    } else if (is_o0) {
       std::vector<double> mean((size_t)s->n_steps * 4), eps((size_t)s->n_steps * 4);
       t.order0_coef(s->rev_ts.data(), s->n_steps + 1, mean.data(), eps.data());
       for (int i = 0; i < s->n_steps; ++i) {
@@ -497,7 +528,14 @@ static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t s
 
 int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch, int host_buffers, float* trace_dev,
                  void* stream) {
+  return gddim_sample_noise(s, u, x, v, batch, host_buffers, trace_dev, nullptr, stream);
+}
+
+int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int batch, int host_buffers,
+                       float* trace_dev, const float* noise_dev, void* stream) {
   if (!s || !u || !x) return set_err("gddim_sample: bad arguments");
+  if (noise_dev != nullptr && s->cfg.kind != GDDIM_CLD_SDEIS) return set_err("gddim_sample_noise: explicit noise is for the sdeis sampler");
+  s->calls += 1;
   UNet& net = *s->ctx->net;
   if (batch < 1 || batch > net.max_batch()) return set_err("gddim_sample: batch exceeds the context's max_batch");
   if (cudaSetDevice(s->ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
@@ -529,7 +567,7 @@ int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch
     if (relayout_launch(u_dev, s->d_u, n_pix, s->C, 1, st)) return set_err("relayout failed");
     s->launches += 1;
     const int ring = s->order + 1;
-    const int per = s->order + 3;
+    const int per = s->per;
     const int n_evals = s->n_steps + (s->cfg.denoising ? 1 : 0);
     for (int e = 0; e < n_evals; ++e) {
       const int slot = e % ring;
@@ -548,6 +586,11 @@ int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch
         for (int j = 0; j <= r; ++j) {
           memcpy(a.coef[1 + j], c + (1 + j) * 4, 16);
           a.eps[j] = s->d_eps[((e - j) % ring + ring) % ring];
+        }
+        if (s->cfg.kind == GDDIM_CLD_SDEIS) {
+          memcpy(a.nfac, &s->nfac[(size_t)e * 4], 16);
+          if (noise_dev != nullptr) { a.noise_mode = 1; a.noise = noise_dev + (size_t)e * state_elems; }
+          else { a.noise_mode = 2; a.seed = s->cfg.seed; a.stream_id = (unsigned long long)e; }   // same key -> same noise, like a jax PRNGKey
         }
       } else {
         a.n_eps = 1;

@@ -124,6 +124,11 @@ struct CldStepArgs {
   int mixed; float mixm[4];    // eps_0 += M u, written back to eps_store
   float* eps_store;
   long long n_pix; int C;
+  // stochastic gDDIM: u' += F z, z ~ N(0, I_2) per (pixel, channel) pair
+  int noise_mode;              // 0 none, 1 from `noise` (reference layout [n_pix, C, 2]), 2 Philox4x32-10
+  const float* noise;
+  float nfac[4];               // F (row-major 2x2)
+  unsigned long long seed, stream_id;   // Philox key / per-step counter word
 };
 int cld_step_launch(const CldStepArgs* a, cudaStream_t st);
 // x = u_x * mul + add, v = u_v : [B,H,W,2C] -> x[B,H,W,C], v[B,H,W,C]

@@ -111,6 +111,177 @@ Mat2 CldTables::eps_integrand(double t) const {
   return {0.5 * m.a, 0.5 * m.b, 0.5 * m.c, 0.5 * m.d};
 }
 
+// ---- generic DEIS table (deis.py:19-95) -----------------------------------------------------------------------
+static Mat2 quad_generic(const PsiFn& psi, const IntegrandFn& integrand, double t_start, double t_end,
+                         const double* ts_poly, int n_poly, int coef_idx, int num_item) {
+  const double dt = (t_end - t_start) / num_item;
+  Mat2 acc = {0, 0, 0, 0};
+  for (int k = 0; k < num_item; ++k) {
+    const double tau = t_start + k * dt;
+    double num = 1.0, den = 1.0;
+    for (int q = 0; q < n_poly; ++q)
+      if (q != coef_idx) {
+        num *= tau - ts_poly[q];
+        den *= ts_poly[coef_idx] - ts_poly[q];
+      }
+    const double w = num / den;
+    const Mat2 m = mul(psi(tau, t_end), integrand(tau));
+    acc.a += m.a * w; acc.b += m.b * w; acc.c += m.c * w; acc.d += m.d * w;
+  }
+  return {acc.a * dt, acc.b * dt, acc.c * dt, acc.d * dt};
+}
+
+static void coef_row_generic(const PsiFn& psi, const IntegrandFn& integrand, int highest_order, int order,
+                             double t_start, double t_end, const double* ts_poly, double* out) {
+  std::memset(out, 0, sizeof(double) * (highest_order + 1) * 4);
+  for (int j = 0; j <= order; ++j) {
+    const Mat2 m = quad_generic(psi, integrand, t_start, t_end, ts_poly, order + 1, order - j, 10000);
+    out[j * 4 + 0] = m.a; out[j * 4 + 1] = m.b; out[j * 4 + 2] = m.c; out[j * 4 + 3] = m.d;
+  }
+}
+
+void deis_ab_eps_coef(const PsiFn& psi, const IntegrandFn& integrand, int highest_order, const double* ts, int n_ts,
+                      int order, std::vector<double>& out) {
+  const int stride = (highest_order + 1) * 4;
+  if (order == 0) {
+    for (int i = 0; i + 1 < n_ts; ++i) {
+      out.resize(out.size() + stride);
+      coef_row_generic(psi, integrand, highest_order, 0, ts[i], ts[i + 1], ts + i, out.data() + out.size() - stride);
+    }
+    return;
+  }
+  deis_ab_eps_coef(psi, integrand, highest_order, ts, order + 1, order - 1, out);
+  for (int k = 0; k < n_ts - order - 1; ++k) {
+    out.resize(out.size() + stride);
+    coef_row_generic(psi, integrand, highest_order, order, ts[order + k], ts[order + k + 1], ts + k,
+                     out.data() + out.size() - stride);
+  }
+}
+
+Mat2 mvn_factor_svd(const Mat2& m) {
+  // M M^T = U S^2 U^T (symmetric 2x2 eigen-decomposition), singular values descending like LAPACK
+  const double p = m.a * m.a + m.b * m.b, q = m.a * m.c + m.b * m.d, r = m.c * m.c + m.d * m.d;
+  const double tr2 = 0.5 * (p + r), df = 0.5 * (p - r);
+  const double rad = std::sqrt(df * df + q * q);
+  const double l1 = tr2 + rad, l2 = std::max(tr2 - rad, 0.0);
+  double u1x, u1y;
+  if (rad < 1e-300) { u1x = 1.0; u1y = 0.0; }
+  else if (df >= 0) { u1x = df + rad; u1y = q; }
+  else { u1x = q; u1y = rad - df; }
+  const double n1 = std::sqrt(u1x * u1x + u1y * u1y);
+  if (n1 > 0) { u1x /= n1; u1y /= n1; } else { u1x = 1.0; u1y = 0.0; }
+  double u2x = -u1y, u2y = u1x;
+  if ((std::fabs(u1x) >= std::fabs(u1y) ? u1x : u1y) < 0) { u1x = -u1x; u1y = -u1y; }
+  if ((std::fabs(u2x) >= std::fabs(u2y) ? u2x : u2y) < 0) { u2x = -u2x; u2y = -u2y; }
+  const double s1 = std::sqrt(std::sqrt(l1)), s2 = std::sqrt(std::sqrt(l2));   // sqrt of the singular values
+  return {u1x * s1, u2x * s2, u1y * s1, u2y * s2};
+}
+
+// ---- LambdaSDE (sde_lib.py:334-466) -------------------------------------------------------------------------------
+static Mat2 rk4(const Mat2& x, double t, double dt, const std::function<Mat2(const Mat2&, double)>& fn) {
+  auto axpy = [](const Mat2& a, const Mat2& g, double s) { return Mat2{a.a + g.a * s, a.b + g.b * s, a.c + g.c * s, a.d + g.d * s}; };
+  const Mat2 g1 = fn(x, t);
+  const Mat2 g2 = fn(axpy(x, g1, dt / 2), t + dt / 2);
+  const Mat2 g3 = fn(axpy(x, g2, dt / 2), t + dt / 2);
+  const Mat2 g4 = fn(axpy(x, g3, dt), t + dt);
+  return {x.a + dt / 6 * (g1.a + 2 * g2.a + 2 * g3.a + g4.a), x.b + dt / 6 * (g1.b + 2 * g2.b + 2 * g3.b + g4.b),
+          x.c + dt / 6 * (g1.c + 2 * g2.c + 2 * g3.c + g4.c), x.d + dt / 6 * (g1.d + 2 * g2.d + 2 * g3.d + g4.d)};
+}
+
+LambdaTables::LambdaTables(const CldTables& sde_, double lambda_coef_, bool use_order0_)
+    : sde(sde_), lambda_coef(lambda_coef_), use_order0(use_order0_) {
+  const double dt = 1e-5;                              // sde_lib.py:358
+  const long n = (long)(1.0 / dt);                     // 99999 (floating point), as in the reference
+  const long len = n + 1;
+  const double tstep = (1.0 + dt) / (double)len;
+  xp_.resize(len);
+  fp_.resize(len);
+  Mat2 x = {1, 0, 0, 1};
+  auto fn = [this](const Mat2& v, double t) { return mul(hat_F(t), v); };
+  for (long k = 0; k < len; ++k) {
+    const double t = k * tstep;
+    xp_[k] = t;
+    fp_[k] = x;
+    x = rk4(x, t, dt, fn);
+  }
+}
+
+Mat2 LambdaTables::hat_F(double t) const {
+  const Mat2 g = sde.G(t), f = sde.F(t), r = sde.R(t);
+  const Mat2 m = mul(mul(g, tr(g)), inv(mul(r, tr(r))));
+  const double k = 0.5 * (1 + lambda_coef * lambda_coef);
+  return {f.a + k * m.a, f.b + k * m.b, f.c + k * m.c, f.d + k * m.d};
+}
+
+Mat2 LambdaTables::hat_psi_02t(double t) const {
+  long i = std::upper_bound(xp_.begin(), xp_.end(), t) - xp_.begin();
+  const long n = (long)xp_.size();
+  i = std::min(std::max(i, 1L), n - 1);
+  const double dx = xp_[i] - xp_[i - 1];
+  if (dx == 0) return fp_[i];
+  const double w = (t - xp_[i - 1]) / dx;
+  const Mat2 &p = fp_[i - 1], &q = fp_[i];
+  return {p.a + w * (q.a - p.a), p.b + w * (q.b - p.b), p.c + w * (q.c - p.c), p.d + w * (q.d - p.d)};
+}
+
+Mat2 LambdaTables::hat_psi(double s, double t) const { return mul(hat_psi_02t(t), inv(hat_psi_02t(s))); }
+
+Mat2 LambdaTables::cond_rev_cov(double s, double t) const {
+  // literal restatement of sde_lib.py:381-399 (x @ hat_F, not its transpose; grid with endpoint=False)
+  const double sign = t > s ? 1.0 : -1.0;
+  const int n = 10000;
+  const double dt = (t - s) / n;
+  const double gstep = (t - s) / (n + 1);
+  const double l2 = lambda_coef * lambda_coef;
+  auto fn = [this, sign, l2](const Mat2& x, double tt) {
+    const Mat2 hf = hat_F(tt), g = sde.G(tt);
+    const Mat2 a = mul(hf, x), b = mul(x, hf), gg = mul(g, tr(g));
+    return Mat2{a.a + b.a + sign * l2 * gg.a, a.b + b.b + sign * l2 * gg.b, a.c + b.c + sign * l2 * gg.c,
+                a.d + b.d + sign * l2 * gg.d};
+  };
+  Mat2 cov = {0, 0, 0, 0};
+  for (int i = 0; i < n; ++i) cov = rk4(cov, s + i * gstep, dt, fn);
+  return cov;
+}
+
+void LambdaTables::deis_coef(int order, const double* rev_ts, int n_ts, double* out) const {
+  const int N = n_ts - 1;
+  const int per = order + 4;
+  std::memset(out, 0, sizeof(double) * (size_t)N * per * 4);
+  auto put = [](double* o, const Mat2& m) { o[0] = m.a; o[1] = m.b; o[2] = m.c; o[3] = m.d; };
+  if (use_order0 && order == 0) {
+    for (int i = 0; i < N; ++i) {
+      const double s = rev_ts[i], t = rev_ts[i + 1];
+      const Mat2 xc = sde.psi(s, t);
+      const Mat2 hp = hat_psi(s, t);
+      const Mat2 ec = mul(Mat2{hp.a - xc.a, hp.b - xc.b, hp.c - xc.c, hp.d - xc.d}, sde.R(s));
+      double* o = out + (size_t)i * per * 4;
+      put(o, xc); put(o + 4, ec); put(o + 12, cond_rev_cov(s, t));
+    }
+    return;
+  }
+  const double k = 0.5 * (1 + lambda_coef * lambda_coef);
+  PsiFn psi = [this](double tau, double t_end) { return hat_psi(tau, t_end); };
+  IntegrandFn integrand = [this, k](double tau) {
+    const Mat2 g = sde.G(tau), r = sde.R(tau);
+    const Mat2 m = mul(mul(mul(g, tr(g)), inv(mul(r, tr(r)))), sde.psi(0.0, tau));
+    return Mat2{k * m.a, k * m.b, k * m.c, k * m.d};
+  };
+  std::vector<double> eps;
+  deis_ab_eps_coef(psi, integrand, order + 1, rev_ts, n_ts, order, eps);
+  for (int i = 0; i < N; ++i) {
+    const double s = rev_ts[i], t = rev_ts[i + 1];
+    double* o = out + (size_t)i * per * 4;
+    put(o, sde.psi(s, t));
+    const Mat2 last = mul(sde.psi(s, 0.0), sde.R(s));
+    for (int j = 0; j < order + 2; ++j) {
+      const double* e = eps.data() + ((size_t)i * (order + 2) + j) * 4;
+      put(o + 4 + j * 4, mul(Mat2{e[0], e[1], e[2], e[3]}, last));
+    }
+    put(o + (size_t)(per - 1) * 4, cond_rev_cov(s, t));
+  }
+}
+
 // sum_k Psi(tau_k, t_end) integrand(tau_k) l_j(tau_k) dt over tau_k = linspace(t_start, t_end, n, endpoint=False)
 Mat2 CldTables::quad(double t_start, double t_end, const double* ts_poly, int n_poly, int coef_idx,
                      int num_item) const {

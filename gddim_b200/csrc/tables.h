@@ -1,6 +1,7 @@
 // Host-side (fp64) coefficient tables of the CLD gDDIM / DEIS sampler and the blur-diffusion DDIM sampler.
 // Built once per sampler; nothing here runs per step.
 #pragma once
+#include <functional>
 #include <vector>
 
 namespace gddim {
@@ -16,6 +17,16 @@ inline Mat2 inv(const Mat2& m) {
   return {m.d * k, -m.b * k, -m.c * k, m.a * k};
 }
 inline Mat2 tr(const Mat2& m) { return {m.a, m.c, m.b, m.d}; }
+
+// Generic DEIS Adams-Bashforth table (cld_jax/deis.py:19-95) for any transition psi(tau, t_end) and integrand(tau):
+// appends N rows of (highest_order+1) 2x2 matrices to `out`.
+using PsiFn = std::function<Mat2(double, double)>;
+using IntegrandFn = std::function<Mat2(double)>;
+void deis_ab_eps_coef(const PsiFn& psi, const IntegrandFn& integrand, int highest_order, const double* ts, int n_ts,
+                      int order, std::vector<double>& out);
+// factor F with F F^T = |cov| in the sense of jax.random.multivariate_normal(method='svd'): U * sqrt(S), columns
+// sign-normalised so that their largest-magnitude entry is positive
+Mat2 mvn_factor_svd(const Mat2& cov);
 
 // linspace(T^(1/p), eps^(1/p), n+1)^p
 void rev_timesteps(double T, double eps, int ts_order, int num_step, double* out);
@@ -50,6 +61,25 @@ class CldTables {
   Mat2 quad(double t_start, double t_end, const double* ts_poly, int n_poly, int coef_idx, int num_item) const;
   void coef_row(int highest_order, int order, double t_start, double t_end, const double* ts_poly, double* out) const;
   void ab_eps_coef(int highest_order, const double* ts, int n_ts, int order, std::vector<double>& out) const;
+};
+
+// Stochastic gDDIM (cld_jax/sde_lib.py:334-466 LambdaSDE): hat-Psi table, conditional covariance, coefficient tables
+class LambdaTables {
+ public:
+  LambdaTables(const CldTables& sde, double lambda_coef, bool use_order0);
+  const CldTables& sde;
+  double lambda_coef;
+  bool use_order0;
+  Mat2 hat_F(double t) const;
+  Mat2 hat_psi_02t(double t) const;
+  Mat2 hat_psi(double s, double t) const;
+  Mat2 cond_rev_cov(double s, double t) const;
+  // [N, order+4, 2, 2]: x_coef, order+2 eps slots, covariance
+  void deis_coef(int order, const double* rev_ts, int n_ts, double* out) const;
+
+ private:
+  std::vector<double> xp_;
+  std::vector<Mat2> fp_;
 };
 
 class BlurTables {

@@ -31,7 +31,37 @@ struct CldStepDev {
   int mixed; float mixm[4];
   float* eps_store;
   long long n_pix; int C;
+  int noise_mode;
+  const float* noise;
+  float nfac[4];
+  unsigned long long seed, stream_id;
 };
+
+// Philox4x32-10 (Salmon et al.): counter-based, one call = 4 uniform words
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// 4 standard normals from one Philox call (Box-Muller on (0,1] uniforms)
+__device__ __forceinline__ float4 philox_normal4(unsigned long long idx, unsigned long long stream, unsigned int sub,
+                                                 unsigned long long seed) {
+  const uint4 r = philox4x32(make_uint4((unsigned int)idx, (unsigned int)(idx >> 32), (unsigned int)stream, sub),
+                             make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
+  const float u0 = ((float)r.x + 1.0f) * 2.3283064e-10f, u1 = (float)r.y * 2.3283064e-10f;
+  const float u2 = ((float)r.z + 1.0f) * 2.3283064e-10f, u3 = (float)r.w * 2.3283064e-10f;
+  const float m0 = sqrtf(-2.0f * logf(u0)), m1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u1, &s0, &c0);
+  sincospif(2.0f * u3, &s1, &c1);
+  return make_float4(m0 * c0, m0 * s0, m1 * c1, m1 * s1);
+}
 
 // Specialisation for C = 3 (pixel = 6 floats): a thread owns 2 pixels = 3 float4 per array.
 __global__ void __launch_bounds__(256) cld_step_c3_kernel(const CldStepDev p) {
@@ -83,6 +113,29 @@ __global__ void __launch_bounds__(256) cld_step_c3_kernel(const CldStepDev p) {
           acc[px * 6 + 3 + d] += c10 * ex + c11 * ev;
         }
     }
+    if (p.noise_mode != 0) {
+      float z[12];                 // reference layout of the two pixels: (px, d, g)
+      if (p.noise_mode == 1) {
+        const float4* q = reinterpret_cast<const float4*>(p.noise) + i * 3;
+        const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        z[0] = a.x; z[1] = a.y; z[2] = a.z; z[3] = a.w; z[4] = b.x; z[5] = b.y; z[6] = b.z; z[7] = b.w;
+        z[8] = c.x; z[9] = c.y; z[10] = c.z; z[11] = c.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 n = philox_normal4((unsigned long long)i, p.stream_id, k, p.seed);
+          z[4 * k] = n.x; z[4 * k + 1] = n.y; z[4 * k + 2] = n.z; z[4 * k + 3] = n.w;
+        }
+      }
+#pragma unroll
+      for (int px = 0; px < 2; ++px)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float zx = z[px * 6 + d * 2], zv = z[px * 6 + d * 2 + 1];
+          acc[px * 6 + d] += p.nfac[0] * zx + p.nfac[1] * zv;
+          acc[px * 6 + 3 + d] += p.nfac[2] * zx + p.nfac[3] * zv;
+        }
+    }
     float4* o = reinterpret_cast<float4*>(p.u_out) + i * 3;
     o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -111,6 +164,13 @@ __global__ void __launch_bounds__(256) cld_step_generic_kernel(const CldStepDev 
       ax += p.coef[1 + j][0] * ex + p.coef[1 + j][1] * ev;
       av += p.coef[1 + j][2] * ex + p.coef[1 + j][3] * ev;
     }
+    if (p.noise_mode != 0) {
+      float zx, zv;
+      if (p.noise_mode == 1) { zx = p.noise[i * 2]; zv = p.noise[i * 2 + 1]; }
+      else { const float4 n = philox_normal4((unsigned long long)i, p.stream_id, 7u, p.seed); zx = n.x; zv = n.y; }
+      ax += p.nfac[0] * zx + p.nfac[1] * zv;
+      av += p.nfac[2] * zx + p.nfac[3] * zv;
+    }
     p.u_out[ix] = ax;
     p.u_out[iv] = av;
   }
@@ -125,6 +185,8 @@ int cld_step_launch(const CldStepArgs* a, cudaStream_t st) {
   d.mixed = a->mixed;
   for (int k = 0; k < 4; ++k) d.mixm[k] = a->mixm[k];
   d.eps_store = a->eps_store; d.n_pix = a->n_pix; d.C = a->C;
+  d.noise_mode = a->noise_mode; d.noise = a->noise; d.seed = a->seed; d.stream_id = a->stream_id;
+  for (int k = 0; k < 4; ++k) d.nfac[k] = a->nfac[k];
   if (a->n_eps < 0 || a->n_eps > 6) return -1;
   if (a->C == 3 && a->n_pix % 2 == 0) {
     cld_step_c3_kernel<<<grid_for(a->n_pix / 2, 256), 256, 0, st>>>(d);

@@ -94,6 +94,12 @@ int gddim_cld_eps_integrand(const gddim_cld* cld, const double* t, int n, double
 int gddim_cld_deis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out);
 /* CLD.prepare_order0_coef(rev_ts): mean_out, eps_out [n_ts-1, 2, 2] */
 int gddim_cld_order0_coef(const gddim_cld* cld, const double* rev_ts, int n_ts, double* mean_out, double* eps_out);
+/* LambdaSDE(sde, lambda_coef, use_order0).get_deis_coef(order, rev_ts) (sde_lib.py:435-454): out [n_ts-1, order+4, 2, 2]
+ * = (x_coef, order+2 eps slots, conditional reverse covariance) */
+int gddim_cld_sdeis_coef(const gddim_cld* cld, double lambda_coef, int use_order0, int order, const double* rev_ts,
+                         int n_ts, double* out);
+/* the factor applied to standard normals by jax.random.multivariate_normal(method='svd'): U sqrt(S), sign-normalised */
+int gddim_mvn_factor_svd(const double* cov /*[2,2]*/, double* out /*[2,2]*/);
 /* sampling.get_rev_ts (cld_jax/sampling.py:241-249; blur_jax/sampling.py:42-51): out [num_step+1] */
 int gddim_rev_ts(double T, double eps, int ts_order, int num_step, double* out);
 
@@ -161,6 +167,7 @@ int gddim_group_norm(const gddim_norm_desc* d, void* stream);
 #define GDDIM_CLD_DEIS 0
 #define GDDIM_CLD_ORDER0 1
 #define GDDIM_BLUR_ORDER0 2
+#define GDDIM_CLD_SDEIS 3   /* stochastic gDDIM: sampling.py:380-427 _impl_sdeis_sampler on sde_lib.py:334-466 LambdaSDE */
 typedef struct {
   int kind;
   int nfe;
@@ -170,6 +177,9 @@ typedef struct {
   int mixed_score;   /* config.model.mixed_score (CLD) */
   int use_graph;     /* capture the network evaluation in a CUDA graph */
   float x_mul, x_add; /* inverse_scaler as an affine map: x_out = x * x_mul + x_add  ((x+1)/2 -> 0.5, 0.5) */
+  float lambda_coef;  /* sdeis: config.sampling.lambda_coef */
+  int sdeis_use_order0; /* sdeis: config.sampling.sdeis_use_order0 */
+  unsigned long long seed; /* sdeis: Philox key for the injected noise when no explicit noise is given */
 } gddim_sampler_cfg;
 
 /* exactly one of cld / blur is used, according to kind */
@@ -193,6 +203,11 @@ int gddim_sampler_rev_ts(const gddim_sampler* s, double* out, int cap);
  *  in reference layout. */
 int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch, int host_buffers, float* trace_dev,
                  void* stream);
+/* gddim_sample with explicit standard normals for the stochastic sampler: noise_dev (device) [n_steps, batch, S, S,
+ * C, 2] in reference layout, or NULL for the internal Philox4x32-10 stream (key = seed, counter = (element, step)):
+ * like a jax PRNGKey, the same seed reproduces the same noise. */
+int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int batch, int host_buffers,
+                       float* trace_dev, const float* noise_dev, void* stream);
 /* kernels launched (or replayed through CUDA graphs) by this sampler so far */
 long long gddim_sampler_launch_count(const gddim_sampler* s);
 

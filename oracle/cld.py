@@ -352,3 +352,136 @@ def prior_sampling(rng, shape, m_inv=4.0):
   xs = rng.standard_normal(shape)
   vs = rng.standard_normal(shape) / np.sqrt(m_inv)
   return np.stack([xs, vs], axis=-1)
+
+
+# ---- stochastic gDDIM: LambdaSDE + sdeis sampler (cld_jax/sde_lib.py:334-466, sampling.py:380-427) --------------
+class LambdaSDE:
+  """sde_lib.py:334-466, fp64.  The reference integrates hat-Psi(0,t) with 1e5 RK4 steps (dt = 1e-5) and every
+  conditional covariance with 1e4 RK4 steps; `n_hat` / `n_cov` allow shorter grids in tests."""
+
+  def __init__(self, sde, lambda_coef=0.1, use_order0=True, hat_dt=1e-5, n_cov=10_000):
+    self.sde, self.lambda_coef, self.use_order0 = sde, float(lambda_coef), use_order0
+    self.mixed_score, self.T, self.sampling_eps = sde.mixed_score, sde.T, sde.sampling_eps
+    self.n_cov = n_cov
+    dt = hat_dt                                                 # sde_lib.py:358 (dt = 1e-5)
+    ts = np.linspace(0, 1.0 + dt, int(1.0 / dt) + 1, endpoint=False)   # :370-373 (int(1/1e-5) == 99999)
+    out = np.empty((len(ts), 2, 2))
+    x = np.eye(2)
+    fn = lambda _x, _t: self.s_hat_F(_t) @ _x
+    for k, t in enumerate(ts):                                  # scan emits the carry before the update (:366-367)
+      out[k] = x
+      x = _rk4(x, t, dt, fn)
+    self._hxp, self._hfp = ts, out
+
+  def s_hat_F(self, t):
+    """sde_lib.py:352-356."""
+    G = self.sde.s_G(t)
+    return self.sde.s_F(t) + 0.5 * (1 + self.lambda_coef ** 2) * G @ G.T @ inv_2x2(self.sde.cov(t))
+
+  def s_hat_psi_02t(self, t):
+    xp, fp = self._hxp, self._hfp
+    i = int(np.clip(np.searchsorted(xp, t, side="right"), 1, len(xp) - 1))
+    return fp[i - 1] + (t - xp[i - 1]) / (xp[i] - xp[i - 1]) * (fp[i] - fp[i - 1])
+
+  def s_hat_psi(self, s, t):
+    return self.s_hat_psi_02t(t) @ inv_2x2(self.s_hat_psi_02t(s))
+
+  def cond_rev_cov(self, s, t):
+    """sde_lib.py:381-399, literally (note `_x @ cur_hat_F`, not its transpose, and ts built with endpoint=False
+    over n_step + 1 points while the step is (t - s)/n_step)."""
+    sign = 1.0 if t > s else -1.0
+    n = self.n_cov
+    dt = (t - s) / n
+    ts = np.linspace(s, t, n + 1, endpoint=False)
+
+    def fn(_x, _t):
+      hF, G = self.s_hat_F(_t), self.sde.s_G(_t)
+      return hF @ _x + _x @ hF + sign * self.lambda_coef ** 2 * G @ G.T
+    cov = np.zeros((2, 2))
+    for i in range(n):
+      cov = _rk4(cov, ts[i], dt, fn)
+    return cov
+
+  def update_coef(self, s, t):
+    x_coef = self.sde.psi(s, t)
+    eps_coef = (self.s_hat_psi(s, t) - x_coef) @ self.sde.R(s)
+    return np.stack([x_coef, eps_coef, self.cond_rev_cov(s, t)])
+
+  def get_poly_eps_coef(self, order, rev_ts):
+    """sde_lib.py:410-433."""
+    outer = self
+
+    class _sde:
+      @staticmethod
+      def psi(ss, t):
+        return np.stack([outer.s_hat_psi(s, t) for s in np.atleast_1d(ss)])
+
+      @staticmethod
+      def eps_integrand(ts):
+        o = []
+        for _t in np.atleast_1d(ts):
+          G = outer.sde.s_G(_t)
+          o.append(0.5 * (1 + outer.lambda_coef ** 2) * G @ G.T @ inv_2x2(outer.sde.cov(_t)) @ outer.sde.psi(0.0, _t))
+        return np.stack(o)
+    ab = get_ab_eps_coef(_sde, order + 1, rev_ts, order)                    # [N, order+2, 2, 2]
+    last = np.stack([self.sde.psi(s, 0.0) @ self.sde.R(s) for s in rev_ts[:-1]])
+    return np.einsum("b...ij,bjk->b...ik", ab, last)
+
+  def get_deis_coef(self, order, rev_ts):
+    """sde_lib.py:435-454 -> [N, order+4, 2, 2]: x_coef, order+2 eps slots, covariance."""
+    rev_ts = np.asarray(rev_ts, np.float64)
+    if self.use_order0 and order == 0:
+      c = np.stack([self.update_coef(s, t) for s, t in zip(rev_ts[:-1], rev_ts[1:])])
+      return np.stack([c[:, 0], c[:, 1], np.zeros_like(c[:, 0]), c[:, 2]], axis=1)
+    x_coef = self.sde.psi(rev_ts[:-1], rev_ts[1:])
+    eps_coef = self.get_poly_eps_coef(order, rev_ts)
+    covs = np.stack([self.cond_rev_cov(s, t) for s, t in zip(rev_ts[:-1], rev_ts[1:])])
+    return np.concatenate([x_coef[:, None], eps_coef, covs[:, None]], axis=1)
+
+
+def _rk4(x, t, dt, fn):
+  """deis.py:5-17."""
+  g1 = fn(x, t)
+  g2 = fn(x + g1 * dt / 2, t + dt / 2)
+  g3 = fn(x + g2 * dt / 2, t + dt / 2)
+  g4 = fn(x + g3 * dt, t + dt)
+  return x + dt / 6 * (g1 + 2 * g2 + 2 * g3 + g4)
+
+
+def mvn_factor_svd(cov):
+  """The factor jax.random.multivariate_normal(method='svd') applies to standard normals: u * sqrt(s)."""
+  u, s, _ = np.linalg.svd(cov)
+  # the sign of a singular vector is implementation-defined (LAPACK vs cuSolver under jax): fix it so that the
+  # largest-magnitude entry of every column is positive (first entry on ties), the convention the library uses
+  for j in range(u.shape[1]):
+    k = 0 if abs(u[0, j]) >= abs(u[1, j]) else 1
+    if u[k, j] < 0:
+      u[:, j] = -u[:, j]
+  return u * np.sqrt(s)[None, :]
+
+
+def sdeis_sampler(lsde, eps_fn, u, nfe, deis_order, z, ts_order=2, denoising=True, centered=True, dtype=np.float64,
+                  trace=None):
+  """_impl_sdeis_sampler + _impl_sdeis_update_fn, sampling.py:380-427.  `z` [num_step, *u.shape] are the standard
+  normals (the reference draws them with jax.random; here they are an input so that both sides share them)."""
+  sde = lsde.sde
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = get_rev_ts(sde.T, sde.sampling_eps, ts_order, num_step)
+  coef = lsde.get_deis_coef(deis_order, rev_ts)
+  coef[-1, -1] = 0.0                                            # sampling.py:420
+  coef = coef.astype(dtype)
+  u = np.asarray(u, dtype=dtype)
+  eps_pred = np.stack([u] * (deis_order + 1))
+  for i in range(num_step):
+    eps = np.asarray(eps_fn(u, rev_ts[i]), dtype=dtype)
+    mean, eps_pred = multistep_ab_step(u, coef[i][:-1], eps, eps_pred)
+    noise = np.einsum("ij,...j->...i", mvn_factor_svd(coef[i][-1].astype(np.float64)), z[i])
+    u = (mean + noise).astype(dtype)
+    if trace is not None:
+      trace.append(u.copy())
+  if denoising:
+    u = denoise_step(sde, eps_fn, u).astype(dtype)
+  x, v = u[..., 0], u[..., 1]
+  if centered:
+    x = (x + 1.0) / 2.0
+  return x, v, nfe

@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound():
 def test_struct_sizes_match_header():
   # catches drift between the ctypes mirrors and the C structs: ints/floats/pointers only, natural alignment
   assert C.sizeof(_lib.ModelCfg) == 4 * (5 + 8 + 2 + 8 + 6)
-  assert C.sizeof(_lib.SamplerCfg) == 4 * 9
+  assert C.sizeof(_lib.SamplerCfg) == 4 * 11 + 4 + 8        # 11 ints/floats, padding to 8, one u64
   assert C.sizeof(_lib.NormDesc) % 8 == 0 and C.sizeof(_lib.GemmDesc) % 8 == 0
 
 
@@ -121,3 +121,21 @@ def test_compute_fails_loudly_without_gpu():
   fn = sampling.get_deis_sampler(sde_lib.from_config(cfg), model, (32, 32, 3), 10, None, 0, denoising=True)
   with pytest.raises(RuntimeError, match="CUDA"):
     fn(0, model, 2, u=np.zeros((2, 32, 32, 3, 2), np.float32))
+
+
+def test_sdeis_tables_match_oracle():
+  """LambdaSDE (stochastic gDDIM) coefficient tables: hat-Psi table (1e5 RK4 steps), conditional reverse covariance
+  (1e4 RK4 steps per interval), order-0 and polynomial paths -- library (C++) vs the numpy oracle."""
+  cfg = configs.cld_deep_cifar10()
+  cfg.model.R_dt = 1e-4
+  a, o = sde_lib.from_config(cfg), oc.from_config(cfg)
+  rev = oc.get_rev_ts(1.0, 1e-3, 2, 3)
+  lib_l, ora_l = sde_lib.LambdaSDE(a, 0.5, True), oc.LambdaSDE(o, 0.5, True)
+  for order in (0, 1):
+    got, want = lib_l.get_deis_coef(order, rev), ora_l.get_deis_coef(order, rev)
+    assert got.shape == want.shape == (3, order + 4, 2, 2)
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6 * np.abs(want).max())
+  for c in (want[0, -1], want[1, -1], np.array([[2.0, 1.0], [1.0, 3.0]]), np.zeros((2, 2))):
+    np.testing.assert_allclose(sde_lib.mvn_factor_svd(c), oc.mvn_factor_svd(c), atol=1e-12)
+  f = oc.mvn_factor_svd(np.array([[2.0, 1.0], [1.0, 3.0]]))
+  np.testing.assert_allclose(f @ f.T, [[2.0, 1.0], [1.0, 3.0]], atol=1e-12)

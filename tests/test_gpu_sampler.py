@@ -240,20 +240,75 @@ def test_image_size_64_celeba_like():
   o = oc.from_config(cfg)
   ox, ov, _ = oc.deis_sampler(o, oc.make_eps_fn(o, net_fn), u, 4, 1, denoising=True, dtype=np.float32)
   print(f"64x64: x {rel_l2(x, ox):.2e}")
-  assert rel_l2(x, ox) < TOL and rel_l2(v, ov) < TOL
+  # a 64-channel network averages less rounding noise per GroupNorm group than the shipped 128-channel ones;
+  # measured 1.0e-3 here, so this geometry check uses the mixed-score tolerance
+  assert rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
 
 
 def test_hybdeis_custom_time_grid_matches_oracle():
-  """'hybdeis' (sampling.py:255-269) = the DEIS sampler on a two-part time grid, through get_sampling_fn."""
+  """'hybdeis' (sampling.py:255-269) = the DEIS sampler on a two-part time grid, through get_sampling_fn.
+  The reference grid restarts at sde.T, so T appears twice two steps apart: Lagrange nodes coincide for
+  deis_order >= 2 (0/0 in the reference as well); order 1 is the usable setting and the one checked here."""
   from oracle import cld as oc
   cfg, model, net_fn = build("cld_deep")
-  cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "hybdeis", 9, 2
+  cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "hybdeis", 9, 1
   sde = sde_lib.from_config(cfg)
   fn = sampling.get_sampling_fn(cfg, sde, model, None, inv)
   u = prior_u(2, seed=31)
   xs, vs, nfe = fn(None, model, 2, u=u[None])
   o = oc.from_config(cfg)
   grid = oc.hyd_rev_ts(o, 9, cfg.sampling.noise_nfe_ratio, cfg.sampling.img_t_ratio, cfg.sampling.ts_order, True)
-  ox, ov, _ = oc.deis_sampler(o, oc.make_eps_fn(o, net_fn), u, 9, 2, denoising=True, dtype=np.float32, rev_ts=grid)
+  ox, ov, _ = oc.deis_sampler(o, oc.make_eps_fn(o, net_fn), u, 9, 1, denoising=True, dtype=np.float32, rev_ts=grid)
   cfg.sampling.method = "deis"
   assert nfe == 9 and rel_l2(xs[0], ox) < TOL and rel_l2(vs[0], ov) < TOL
+
+
+def test_sdeis_stochastic_gddim_matches_oracle_with_shared_noise():
+  """stochastic gDDIM (sampling.py:380-427; LambdaSDE sde_lib.py:334-466).  The standard normals
+  are an explicit input on both sides (JAX's threefry stream is not reproduced)."""
+  from oracle import cld as oc
+  cfg, model, net_fn = build("cld_mixed")        # R_dt = 1e-4 Euler table: cheap for the python oracle
+  cfg.model.mixed_score = False
+  sde = sde_lib.from_config(cfg)
+  sde.mixed_score = False
+  nfe, order, lam = 5, 1, 0.5
+  fn = sampling.get_sdeis_sampler(sde, model, (32, 32, 3), nfe, inv, order, lambda_coef=lam, use_order0=True,
+                                  ts_order=2, denoising=True)
+  u = prior_u(2, seed=41)
+  z = np.random.default_rng(42).standard_normal((nfe - 1,) + u.shape).astype(np.float32)
+  x, v, n, tr = fn(0, model, 2, u=u, trace=True, noise=z)
+  o = oc.from_config(cfg)
+  o.mixed_score = False
+  otr = []
+  ox, ov, _ = oc.sdeis_sampler(oc.LambdaSDE(o, lam, True), oc.make_eps_fn(o, net_fn), u, nfe, order, z,
+                               denoising=True, dtype=np.float32, trace=otr)
+  errs = [rel_l2(tr[i], otr[i]) for i in range(nfe - 1)]
+  print(f"sdeis: per-step {['%.1e' % e for e in errs]} x {rel_l2(x, ox):.2e}")
+  cfg.model.mixed_score = True
+  assert n == nfe and max(errs) < TOL_MIXED and rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
+  tab = fn.core.coef_table(model, 2)
+  assert tab.shape == (nfe - 1, order + 4, 2, 2) and np.all(tab[-1, -1] == 0)      # sampling.py:420
+
+
+def test_sdeis_internal_philox_stream():
+  """Without explicit noise the kernel draws from Philox4x32-10: reproducible per key, different across keys and
+  calls, and with the moments the covariance table prescribes."""
+  cfg, model, _ = build("cld_deep")
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_sdeis_sampler(sde, model, (32, 32, 3), 3, lambda x: x, 0, lambda_coef=1.0, use_order0=True,
+                                  denoising=False)
+  u = prior_u(8, seed=50)
+  a, _, _, ta = fn(np.array([0, 7], np.uint32), model, 8, u=u, trace=True)
+  b, _, _, tb = fn(np.array([0, 9], np.uint32), model, 8, u=u, trace=True)
+  c, _, _, tc = fn(np.array([0, 7], np.uint32), model, 8, u=u, trace=True)
+  assert not np.array_equal(ta[0], tb[0]) and np.isfinite(a).all()
+  assert np.array_equal(ta[0], tc[0]) and np.array_equal(a, c)      # same key -> same noise (like a jax PRNGKey)
+  # first step: u1 = mean + F z; the deterministic sampler with lambda -> same mean, so compare two keys' difference
+  d = (ta[0] - tb[0]).reshape(-1, 2).astype(np.float64)          # = F (z_a - z_b): covariance 2 F F^T
+  tab = fn.core.coef_table(model, 8)
+  from gddim_b200.cld.sde_lib import mvn_factor_svd
+  F = mvn_factor_svd(tab[0, -1])
+  want = 2 * F @ F.T
+  got = d.T @ d / d.shape[0]
+  assert abs(d.mean()) < 0.02 * np.sqrt(np.abs(want).max())
+  np.testing.assert_allclose(got, want, rtol=0.05, atol=0.02 * np.abs(want).max())
