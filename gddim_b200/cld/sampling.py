@@ -16,7 +16,7 @@ import numpy as np
 from .. import _lib
 from .. import net as _net
 
-_NEXT = ("ldeis", "mldeis", "ode", "sscs", "em")
+_NEXT = ("mldeis", "ode")
 
 
 def get_data_shape(config):
@@ -65,6 +65,18 @@ def get_sampling_fn(config, sde, model, shape, inverse_scaler):
                              inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
                              lambda_coef=config.sampling.lambda_coef, use_order0=config.sampling.sdeis_use_order0,
                              ts_order=config.sampling.ts_order, denoising=config.sampling.noise_removal, is_p=True)
+  if name == "ldeis":
+    return get_L_deis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
+                              inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
+                              ts_order=config.sampling.ts_order, denoising=config.sampling.noise_removal, is_p=True)
+  if name == "sscs":
+    return get_sscs_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
+                            inverse_scaler=inverse_scaler, ts_order=config.sampling.ts_order,
+                            denoising=config.sampling.noise_removal, is_p=True)
+  if name == "em":
+    return get_em_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
+                          inverse_scaler=inverse_scaler, lambda_coef=config.sampling.lambda_coef,
+                          ts_order=config.sampling.ts_order, denoising=config.sampling.noise_removal, is_p=True)
   if name == "hybdeis":
     return get_hyd_deis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
                                 inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
@@ -154,8 +166,9 @@ class _Sampler:
         raise ValueError("noise= is only meaningful for the sdeis sampler")
       nz_keep = (noise.detach().to(device="cuda", dtype=torch.float32) if torch.is_tensor(noise)
                  else torch.as_tensor(np.ascontiguousarray(noise, dtype=np.float32)).cuda()).contiguous()
-      if tuple(nz_keep.shape) != (n_steps,) + shape:
-        raise ValueError(f"noise has shape {tuple(nz_keep.shape)}, expected {(n_steps,) + shape}")
+      n_noise = getattr(self, "n_noise", n_steps)
+      if tuple(nz_keep.shape) != (n_noise,) + shape:
+        raise ValueError(f"noise has shape {tuple(nz_keep.shape)}, expected {(n_noise,) + shape}")
       nz = nz_keep.data_ptr()
     if is_np:
       uh = np.ascontiguousarray(u, dtype=np.float32)
@@ -270,8 +283,142 @@ def get_sdeis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, l
   core = _Sampler(_lib.CLD_SDEIS, sde, model, data_shape, nfe, inverse_scaler, deis_order, int(ts_order), denoising,
                   is_p, lambda_coef=lambda_coef, use_order0=use_order0)
   return _wrap(core, sde, data_shape, is_p)
-get_L_deis_sampler = _next("get_L_deis_sampler")
 get_mldeis_sampler = _next("get_mldeis_sampler")
 get_ode_sampler = _next("get_ode_sampler")
-get_sscs_sampler = _next("get_sscs_sampler")
-get_em_sampler = _next("get_em_sampler")
+
+
+# ---- samplers expressed as explicit step programs (gddim_sampler_create_program) ---------------------------------
+class _ProgramSampler(_Sampler):
+  """Every remaining CLD sampler of the reference is a sequence of affine steps u <- A u + sum_j C_j eps_j + F z;
+  the tables are assembled here (fp64 numpy on top of the library's host functions) and executed by the library."""
+
+  def __init__(self, sde, model, data_shape, nfe, inverse_scaler, denoising, is_p, steps, history):
+    super().__init__(_lib.CLD_PROGRAM, sde, model, data_shape, nfe, inverse_scaler, 0, 2, denoising, is_p)
+    self.steps, self.history = steps, int(history)
+    self.kind = _lib.CLD_SDEIS if any(any(st.F) for st in steps) else _lib.CLD_PROGRAM   # noise= allowed iff stochastic
+    self.n_noise = sum(1 for st in steps if any(st.F))
+
+  def handle(self, net, batch):
+    ctx = net.ensure(batch)
+    if self._h is not None and self._ctx_id == ctx.value and self._net is net:
+      return self._h
+    self._destroy()
+    cfg = _lib.SamplerCfg(kind=_lib.CLD_PROGRAM, nfe=self.nfe, deis_order=0, ts_order=2, denoising=int(self.denoising),
+                          mixed_score=int(bool(self.sde.mixed_score)), use_graph=int(self.use_graph),
+                          x_mul=self.mul if self.affine else 1.0, x_add=self.add if self.affine else 0.0,
+                          lambda_coef=0.0, sdeis_use_order0=0, seed=int(self.seed))
+    arr = (_lib.Step * len(self.steps))(*self.steps)
+    h = C.c_void_p()
+    _lib.check(_lib.lib().gddim_sampler_create_program(ctx, C.byref(cfg), arr, len(self.steps), self.history, C.byref(h)),
+               "gddim_sampler_create_program")
+    self._h, self._ctx_id, self._net = h, ctx.value, net
+    return h
+
+
+def _step(t=-1.0, A=None, Cs=(), F=None, M=None, first_eps=0, trace=0):
+  st = _lib.Step()
+  st.t, st.n_eps, st.first_eps, st.trace = float(t), len(Cs), int(first_eps), int(trace)
+  A = np.eye(2) if A is None else np.asarray(A, np.float64)
+  for k in range(4):
+    st.A[k] = float(A.ravel()[k])
+    st.F[k] = 0.0 if F is None else float(np.asarray(F, np.float64).ravel()[k])
+    st.M[k] = 0.0 if M is None else float(np.asarray(M, np.float64).ravel()[k])
+  for j, c in enumerate(Cs):
+    for k in range(4):
+      st.C[j][k] = float(np.asarray(c, np.float64).ravel()[k])
+  return st
+
+
+def _base(sde):
+  return getattr(sde, "sde", sde)
+
+
+def _mix_matrix(sde, t):
+  """models/utils.py:174-176: eps += R(t)^-1 [0, v]."""
+  if not sde.mixed_score:
+    return None
+  ri = np.linalg.inv(_base(sde)._R64([t])[0])
+  return np.array([[0.0, ri[0, 1]], [0.0, ri[1, 1]]])
+
+
+def _denoise_step(sde):
+  """get_denoising_step (sampling.py:30-39) at t = dt = sampling_eps as one affine step."""
+  b = _base(sde)
+  t = b.sampling_eps
+  F, G, R = b._F64(t), b._G64(t), b._R64([t])[0]
+  return _step(t=t, A=np.eye(2) - t * F, Cs=[-t * (G @ G) @ np.linalg.inv(R).T], M=_mix_matrix(sde, t))
+
+
+def get_L_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, ts_order=2, denoising=False,
+                       is_p=False):
+  """sampling.py:536-540 -> _impl_Ldeis_sampler (497-534): DEIS in the L_t parameterisation; the network output is
+  mapped by L^T R^-T (sde_lib.py:493-499) before it enters the history, which is folded into the coefficients here.
+  (The reference's denoising branch calls LSDE.s_F, which does not exist; here it uses the base SDE's step.)"""
+  from . import sde_lib as _sl
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = np.asarray(get_rev_ts(sde, ts_order, num_step), np.float64)
+  lsde = _sl.LSDE(sde)
+  coef = np.asarray(lsde.get_deis_coef(deis_order, rev_ts), np.float64)
+  conv = [lsde._epsR2epsL_matrix64(t) for t in rev_ts[:-1]]
+  steps = []
+  for i in range(num_step):
+    r = min(i, deis_order)
+    steps.append(_step(t=rev_ts[i], A=coef[i, 0], Cs=[coef[i, 1 + j] @ conv[i - j] for j in range(r + 1)],
+                       M=_mix_matrix(sde, rev_ts[i]), trace=1))
+  if denoising:
+    steps.append(_denoise_step(sde))
+  core = _ProgramSampler(sde, model, data_shape, nfe, inverse_scaler, denoising, is_p, steps, deis_order + 1)
+  return _wrap(core, sde, data_shape, is_p)
+
+
+def get_em_sampler(sde, model, data_shape, nfe, inverse_scaler, lambda_coef=0, ts_order=2, denoising=False, is_p=False):
+  """sampling.py:624-669: Euler-Maruyama on the lambda-family reverse SDE (score = -R^-T eps, sde_lib.py:246-253)."""
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = np.asarray(get_rev_ts(sde, ts_order, num_step), np.float64)
+  steps = []
+  for i in range(num_step):
+    cur_t, dt = rev_ts[i], rev_ts[i + 1] - rev_ts[i]
+    F, G, R = sde._F64(cur_t), sde._G64(cur_t), sde._R64([cur_t])[0]
+    steps.append(_step(t=cur_t, A=np.eye(2) + F * dt, Cs=[(1.0 + lambda_coef) / 2.0 * dt * (G @ G.T) @ np.linalg.inv(R).T],
+                       F=(lambda_coef * np.sqrt(abs(dt)) * G) if lambda_coef != 0 else None,
+                       M=_mix_matrix(sde, cur_t), trace=1))
+  if denoising:
+    steps.append(_denoise_step(sde))
+  core = _ProgramSampler(sde, model, data_shape, nfe, inverse_scaler, denoising, is_p, steps, 1)
+  return _wrap(core, sde, data_shape, is_p)
+
+
+def _sscs_ou(sde, s_t, s_t_next):
+  """get_sscs_ou_fn (sampling.py:542-566): mean matrix and covariance of the analytic OU half step."""
+  bi = -1 * (sde.beta_int(1 - s_t_next) - sde.beta_int(1 - s_t))
+  Gm = sde.Gamma
+  mean = np.array([[1 + 2 * bi / Gm, -4 * bi / Gm / Gm], [bi, 1 - 2 * bi / Gm]]) * np.exp(-2.0 * bi / Gm)
+  cov_xx = np.exp(4 * bi / Gm) - 1 - 4 * bi / Gm - 8 * bi ** 2 / Gm / Gm
+  cov_xv = -4 * bi ** 2 / Gm
+  cov_vv = (Gm / 2) ** 2 * (np.exp(4 * bi / Gm) - 1) + bi * Gm - 2 * bi ** 2
+  return mean, np.array([[cov_xx, cov_xv], [cov_xv, cov_vv]]) * np.exp(-4 * bi / Gm)
+
+
+def get_sscs_sampler(sde, model, data_shape, nfe, inverse_scaler, ts_order=2, denoising=False, is_p=False):
+  """sampling.py:568-622: symmetric splitting (OU half step, score kick on v, OU half step) per step."""
+  from . import sde_lib as _sl
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = np.asarray(get_rev_ts(sde, ts_order, num_step), np.float64)
+  ts = 1 - rev_ts
+  steps = []
+  for i in range(num_step):
+    cur_t, next_t = ts[i], ts[i + 1]
+    mid = (cur_t + next_t) / 2.0
+    m, c = _sscs_ou(sde, cur_t, mid)
+    steps.append(_step(A=m, F=_sl.mvn_factor_svd(c)))
+    te = sde.T - cur_t                                            # evaluation time of the score (sampling.py:572)
+    rit = np.linalg.inv(sde._R64([te])[0]).T
+    k = 2 * sde.beta(cur_t) * sde.Gamma * (next_t - cur_t)
+    steps.append(_step(t=te, A=np.array([[1.0, 0.0], [0.0, 1.0 + k * sde.m_inv]]),
+                       Cs=[k * np.array([[0.0, 0.0], [-rit[1, 0], -rit[1, 1]]])], M=_mix_matrix(sde, te)))
+    m, c = _sscs_ou(sde, mid, next_t)
+    steps.append(_step(A=m, F=_sl.mvn_factor_svd(c), trace=1))
+  if denoising:
+    steps.append(_denoise_step(sde))
+  core = _ProgramSampler(sde, model, data_shape, nfe, inverse_scaler, denoising, is_p, steps, 1)
+  return _wrap(core, sde, data_shape, is_p)

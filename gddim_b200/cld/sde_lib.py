@@ -108,6 +108,16 @@ class CLD:
   def vs_psi(self, s, t):
     return self._psi64(s, t).astype(self._dt)
 
+  def _F64(self, t):
+    out = np.empty((2, 2))
+    _lib.check(_lib.lib().gddim_cld_F(self._h, float(t), out.ctypes.data))
+    return out
+
+  def _G64(self, t):
+    out = np.empty((2, 2))
+    _lib.check(_lib.lib().gddim_cld_G(self._h, float(t), out.ctypes.data))
+    return out
+
   def s_F(self, t):
     out = np.empty((2, 2))
     _lib.check(_lib.lib().gddim_cld_F(self._h, float(t), out.ctypes.data))
@@ -227,8 +237,43 @@ def mvn_factor_svd(cov):
 
 
 class LSDE:
-  def __init__(self, *a, **k):
-    raise NotImplementedError("LSDE (Cholesky L_t baseline) is outside the round-1 hot path (SURVEY.md 8f N3)")
+  """Stand-in for sde_lib.py:469-519: the L_t (Cholesky of Sigma_t) parameterisation of the 'ldeis' baseline."""
+
+  def __init__(self, sde, used_cache=True):
+    self.sde = sde
+    self.mixed_score = sde.mixed_score
+    self.prior_sampling = sde.prior_sampling
+    self.v_invR, self.s_G = sde.v_invR, sde.s_G
+    self.vs_psi, self.vv_psi = sde.vs_psi, sde.vv_psi
+    self.x64 = sde.x64
+    self.T, self.sampling_eps = sde.T, sde.sampling_eps
+    self._h = sde._h
+    self._dt = np.float64 if sde.x64 else np.float32
+
+  def _L64(self, t):
+    r = self.sde._R64([t])[0]
+    return np.linalg.cholesky(r @ r.T)
+
+  def s_L(self, s_t):
+    return self._L64(s_t).astype(self._dt)
+
+  def _epsR2epsL_matrix64(self, t):
+    return self._L64(t).T @ inv_2x2(self.sde._R64([t])[0].T)
+
+  def epsR2epsL(self, s_t, eps):
+    """sde_lib.py:493-499: (L^T R^-T) eps on the last axis."""
+    return np.einsum("ij,b...dj->b...di", self._epsR2epsL_matrix64(s_t), np.asarray(eps, np.float64)).astype(self._dt)
+
+  def s_eps_integrand(self, s_t):
+    g = self.sde.s_G(s_t).astype(np.float64)
+    return (0.5 * g @ g @ inv_2x2(self._L64(s_t)).T).astype(self._dt)
+
+  def get_deis_coef(self, order, rev_timesteps, used_cache=True):
+    rev = _d(rev_timesteps)
+    out = np.empty((rev.size - 1, order + 3, 2, 2))
+    _lib.check(_lib.lib().gddim_cld_ldeis_coef(self._h, int(order), rev.ctypes.data, rev.size, out.ctypes.data),
+               "gddim_cld_ldeis_coef")
+    return out.astype(self._dt)
 
 
 def from_config(config):

@@ -37,7 +37,9 @@ struct gddim_sampler {
   std::vector<float> coef;            // CLD: [n_steps][per][4], per = order+3 (deis/order0) or order+4 (sdeis)
   int per = 0;
   std::vector<float> nfac;            // sdeis: [n_steps][4] factor applied to the standard normals
-  unsigned long long calls = 0;       // sample calls so far (Philox stream id)
+  unsigned long long calls = 0;       // sample calls so far
+  std::vector<gddim_step> program;    // GDDIM_CLD_PROGRAM: explicit step list
+  int history = 1;
   float den_A[4], den_C[4];
   std::vector<float> mixm;            // [n_steps + 1][4]  R(t)^-1 [[0,0],[0,1]] when mixed_score
   float* d_temb_all = nullptr;        // [n_steps (+1 denoise)][temb_total]
@@ -198,6 +200,12 @@ int gddim_cld_sdeis_coef(const gddim_cld* cld, double lambda_coef, int use_order
 int gddim_mvn_factor_svd(const double* cov, double* out) {
   if (!cov || !out) return set_err("gddim_mvn_factor_svd: bad arguments");
   put(out, mvn_factor_svd(Mat2{cov[0], cov[1], cov[2], cov[3]}));
+  return 0;
+}
+int gddim_cld_ldeis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out) {
+  if (!cld || !rev_ts || !out || order < 0 || order > 4 || n_ts < 2 || n_ts - 1 < order)
+    return set_err("gddim_cld_ldeis_coef: bad arguments");
+  cld->t->ldeis_coef(order, rev_ts, n_ts, out);
   return 0;
 }
 int gddim_rev_ts(double T, double eps, int ts_order, int num_step, double* out) {
@@ -467,6 +475,59 @@ int gddim_sampler_create_ts(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const 
   return 0;
 }
 
+int gddim_sampler_create_program(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_step* steps, int n_steps,
+                                 int history, gddim_sampler** out) {
+  if (!ctx || !cfg || !steps || !out || n_steps < 1 || history < 1 || history > 6)
+    return set_err("gddim_sampler_create_program: bad arguments");
+  if (!ctx->net->finalized()) return set_err("gddim_sampler_create_program: context not finalized");
+  if (ctx->net->cfg().state_mult != 2) return set_err("gddim_sampler_create_program: needs a state_mult=2 (CLD) network");
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
+  std::unique_ptr<gddim_sampler> s(new gddim_sampler);
+  s->ctx = ctx;
+  s->cfg = *cfg;
+  s->cfg.kind = GDDIM_CLD_PROGRAM;
+  UNet& net = *ctx->net;
+  s->S = net.image_size();
+  s->C = net.cfg().data_channels;
+  s->program.assign(steps, steps + n_steps);
+  s->history = history;
+  s->n_steps = 0;
+  std::vector<double> eval_ts;
+  int n_evals = 0;
+  for (int i = 0; i < n_steps; ++i) {
+    const gddim_step& st = steps[i];
+    if (st.n_eps < 0 || st.n_eps > 6) return set_err("gddim_sampler_create_program: n_eps out of range");
+    if (st.t >= 0) { eval_ts.push_back(st.t); ++n_evals; }
+    if (st.n_eps > 0 && !st.first_eps && st.t < 0) return set_err("gddim_sampler_create_program: eps_0 used by a step without evaluation");
+    if (st.n_eps > 0) {
+      const int back_max = st.n_eps - 1 + ((st.t >= 0 && st.first_eps) ? 1 : 0);   // oldest evaluation referenced
+      if (back_max >= history) return set_err("gddim_sampler_create_program: eps term older than the history ring");
+      if (back_max > n_evals - 1) return set_err("gddim_sampler_create_program: eps term refers to an evaluation not made yet");
+    }
+    if (st.trace) s->n_steps += 1;
+  }
+  const size_t state_elems = (size_t)net.max_batch() * s->S * s->S * net.net_channels();
+  const size_t img_elems = (size_t)net.max_batch() * s->S * s->S * s->C;
+  s->d_eps.resize(history, nullptr);
+  bool ok = cudaMalloc(&s->d_u, state_elems * 4) == cudaSuccess;
+  for (auto& p : s->d_eps) ok = ok && cudaMalloc(&p, state_elems * 4) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->d_stage, state_elems * 4) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->d_x, img_elems * 4) == cudaSuccess && cudaMalloc(&s->d_v, img_elems * 4) == cudaSuccess;
+  const int tt = net.temb_total();
+  if (tt > 0 && !eval_ts.empty()) {
+    ok = ok && cudaMalloc(&s->d_temb_all, eval_ts.size() * (size_t)tt * 4) == cudaSuccess;
+    if (ok)
+      for (size_t i = 0; i < eval_ts.size(); ++i)
+        if (net.time_projections(eval_ts[i], s->d_temb_all + i * (size_t)tt, 0)) { free_sampler_buffers(s.get()); return set_err(net.error()); }
+  }
+  if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
+    free_sampler_buffers(s.get());
+    return set_err("gddim_sampler_create_program: device allocation failed");
+  }
+  *out = s.release();
+  return 0;
+}
+
 void gddim_sampler_destroy(gddim_sampler* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
@@ -534,7 +595,8 @@ int gddim_sample(gddim_sampler* s, const float* u, float* x, float* v, int batch
 int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int batch, int host_buffers,
                        float* trace_dev, const float* noise_dev, void* stream) {
   if (!s || !u || !x) return set_err("gddim_sample: bad arguments");
-  if (noise_dev != nullptr && s->cfg.kind != GDDIM_CLD_SDEIS) return set_err("gddim_sample_noise: explicit noise is for the sdeis sampler");
+  if (noise_dev != nullptr && s->cfg.kind != GDDIM_CLD_SDEIS && s->cfg.kind != GDDIM_CLD_PROGRAM)
+    return set_err("gddim_sample_noise: explicit noise is for the stochastic samplers");
   s->calls += 1;
   UNet& net = *s->ctx->net;
   if (batch < 1 || batch > net.max_batch()) return set_err("gddim_sample: batch exceeds the context's max_batch");
@@ -566,9 +628,55 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
     }
     if (relayout_launch(u_dev, s->d_u, n_pix, s->C, 1, st)) return set_err("relayout failed");
     s->launches += 1;
+    if (s->cfg.kind == GDDIM_CLD_PROGRAM) {
+      const int ring = s->history;
+      int ne = -1;            // index of the latest evaluation
+      int nn = 0, ntr = 0;    // noise draws / traced states so far
+      for (size_t i = 0; i < s->program.size(); ++i) {
+        const gddim_step& ps = s->program[i];
+        int slot = ne >= 0 ? ne % ring : 0;
+        if (ps.t >= 0) {
+          ++ne;
+          slot = ne % ring;
+          if (eval_net(s, ne, slot, batch, st)) return -1;
+        }
+        CldStepArgs a;
+        memset(&a, 0, sizeof(a));
+        a.u = s->d_u; a.u_out = s->d_u;
+        a.n_pix = n_pix; a.C = s->C;
+        a.mixed = (s->cfg.mixed_score && ps.t >= 0) ? 1 : 0;
+        a.eps_store = s->d_eps[slot];
+        memcpy(a.mixm, ps.M, 16);
+        memcpy(a.coef[0], ps.A, 16);
+        a.n_eps = ps.n_eps;
+        for (int j = 0; j < ps.n_eps; ++j) {
+          memcpy(a.coef[1 + j], ps.C[j], 16);
+          const int back = j + (ps.first_eps ? 1 : 0) - ((ps.t >= 0) ? 0 : (ps.first_eps ? 1 : 0));
+          if (ne - back < 0) return set_err("gddim_sample: program refers to an evaluation that was not made yet");
+          a.eps[j] = s->d_eps[(ne - back) % ring];
+        }
+        if (a.mixed && (ps.n_eps == 0 || ps.first_eps)) {
+          // the mixed-score term must be folded into this evaluation even if the step does not use it directly
+          return set_err("gddim_sample: mixed_score steps must consume their own evaluation as eps_0");
+        }
+        if (ps.F[0] != 0.f || ps.F[1] != 0.f || ps.F[2] != 0.f || ps.F[3] != 0.f) {
+          memcpy(a.nfac, ps.F, 16);
+          if (noise_dev != nullptr) { a.noise_mode = 1; a.noise = noise_dev + (size_t)nn * state_elems; }
+          else { a.noise_mode = 2; a.seed = s->cfg.seed; a.stream_id = (unsigned long long)nn; }
+          ++nn;
+        }
+        if (cld_step_launch(&a, st)) return set_err("cld_step launch failed");
+        s->launches += 1;
+        if (trace_dev && ps.trace) {
+          if (relayout_launch(s->d_u, trace_dev + (size_t)ntr * state_elems, n_pix, s->C, 0, st)) return set_err("trace relayout failed");
+          s->launches += 1;
+          ++ntr;
+        }
+      }
+    }
     const int ring = s->order + 1;
     const int per = s->per;
-    const int n_evals = s->n_steps + (s->cfg.denoising ? 1 : 0);
+    const int n_evals = s->cfg.kind == GDDIM_CLD_PROGRAM ? 0 : s->n_steps + (s->cfg.denoising ? 1 : 0);
     for (int e = 0; e < n_evals; ++e) {
       const int slot = e % ring;
       if (eval_net(s, e, slot, batch, st)) return -1;

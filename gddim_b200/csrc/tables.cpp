@@ -355,6 +355,31 @@ void CldTables::order0_coef(const double* rev_ts, int n_ts, double* mean_out, do
   }
 }
 
+Mat2 CldTables::chol_cov(double t) const {
+  const Mat2 r = R(t);
+  const Mat2 s = mul(r, tr(r));                       // Sigma_t
+  const double l00 = std::sqrt(s.a), l10 = s.c / l00;
+  return {l00, 0.0, l10, std::sqrt(s.d - l10 * l10)};
+}
+
+void CldTables::ldeis_coef(int order, const double* rev_ts, int n_ts, double* out) const {
+  const int N = n_ts - 1, highest = order + 1, per = order + 3;
+  PsiFn p = [this](double tau, double t_end) { return psi(tau, t_end); };
+  IntegrandFn f = [this](double tau) {
+    const Mat2 g = G(tau);
+    const Mat2 m = mul(mul(g, g), tr(inv(chol_cov(tau))));
+    return Mat2{0.5 * m.a, 0.5 * m.b, 0.5 * m.c, 0.5 * m.d};
+  };
+  std::vector<double> eps;
+  deis_ab_eps_coef(p, f, highest, rev_ts, n_ts, order, eps);
+  for (int i = 0; i < N; ++i) {
+    const Mat2 x = psi(rev_ts[i], rev_ts[i + 1]);
+    double* o = out + (size_t)i * per * 4;
+    o[0] = x.a; o[1] = x.b; o[2] = x.c; o[3] = x.d;
+    std::memcpy(o + 4, eps.data() + (size_t)i * (highest + 1) * 4, sizeof(double) * (highest + 1) * 4);
+  }
+}
+
 void CldTables::denoise_coef(double t, Mat2* A, Mat2* C) const {
   // u' = u + (F u)(-t) - (G G score)(-t),  score = -R^{-T} eps   =>   A = I - t F,  C = -t G G R^{-T}
   const Mat2 f = F(t), g = G(t);

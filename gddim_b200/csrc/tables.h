@@ -53,6 +53,9 @@ class CldTables {
   void order0_coef(const double* rev_ts, int n_ts, double* mean_out, double* eps_out) const;
   // denoising step as u' = A u + C eps
   void denoise_coef(double t, Mat2* A, Mat2* C) const;
+  // LSDE (sde_lib.py:469-519): same table with the Cholesky factor L_t of Sigma_t in the integrand
+  Mat2 chol_cov(double t) const;
+  void ldeis_coef(int order, const double* rev_ts, int n_ts, double* out) const;
 
  private:
   std::vector<double> xp_;

@@ -167,6 +167,7 @@ int gddim_group_norm(const gddim_norm_desc* d, void* stream);
 #define GDDIM_CLD_DEIS 0
 #define GDDIM_CLD_ORDER0 1
 #define GDDIM_BLUR_ORDER0 2
+#define GDDIM_CLD_PROGRAM 4 /* explicit step list (gddim_sampler_create_program) */
 #define GDDIM_CLD_SDEIS 3   /* stochastic gDDIM: sampling.py:380-427 _impl_sdeis_sampler on sde_lib.py:334-466 LambdaSDE */
 typedef struct {
   int kind;
@@ -188,6 +189,25 @@ int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gdd
 /* same with an explicit time grid rev_ts[num_step+1] (cld_jax/sampling.py:204 _impl_deis_sampler, :255 hybdeis) */
 int gddim_sampler_create_ts(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
                             const double* rev_ts, int n_ts, gddim_sampler** out);
+/* A sampler as an explicit list of affine steps on the (x, v) pairs -- the form every CLD sampler of
+ * cld_jax/sampling.py reduces to:  u <- A u + sum_j C_j eps_j + F z,  z ~ N(0, I_2).
+ * eps_0 is this step's network evaluation at diffusion time t (t < 0: no evaluation; then n_eps must be 0 or refer
+ * only to earlier evaluations through `first_eps` = 1), eps_j the j-th most recent earlier evaluation.
+ * Used for 'ldeis' (sampling.py:497-540), 'em' (624-669), 'sscs' (542-622); tables come from the gddim_cld_* calls. */
+typedef struct {
+  double t;          /* time of the network evaluation made by this step, or < 0 for none */
+  int n_eps;         /* number of eps terms (<= 6) */
+  int first_eps;     /* 0: eps_0 is this step's evaluation; 1: terms start at the most recent earlier evaluation */
+  float A[4];
+  float C[6][4];
+  float F[4];        /* noise factor, all zero = deterministic step */
+  float M[4];        /* mixed score: eps_0 += M u (applied when cfg.mixed_score) */
+  int trace;         /* 1: the state after this step is written to trace_dev (in order) */
+} gddim_step;
+int gddim_sampler_create_program(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_step* steps, int n_steps,
+                                 int history, gddim_sampler** out);
+/* LSDE(sde).get_deis_coef(order, rev_ts) (sde_lib.py:469-519: Cholesky L_t in place of R_t): out [n_ts-1, order+3, 2, 2] */
+int gddim_cld_ldeis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out);
 void gddim_sampler_destroy(gddim_sampler* s);
 /* The table the sampler steps through (for index-exact parity checks): fp32 [n_steps, order+3, 2, 2] for CLD
  * deis.  Returns the number of floats written (or needed when out == NULL). */

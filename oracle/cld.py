@@ -485,3 +485,103 @@ def sdeis_sampler(lsde, eps_fn, u, nfe, deis_order, z, ts_order=2, denoising=Tru
   if centered:
     x = (x + 1.0) / 2.0
   return x, v, nfe
+
+
+# ---- remaining CLD samplers (cld_jax/sampling.py:497-669; sde_lib.py:469-519) ----------------------------------------
+class LSDE:
+  """sde_lib.py:469-519: the L_t (Cholesky) parameterisation used by the 'ldeis' baseline."""
+
+  def __init__(self, sde):
+    self.sde, self.mixed_score, self.T, self.sampling_eps = sde, sde.mixed_score, sde.T, sde.sampling_eps
+
+  def s_L(self, t):
+    return np.linalg.cholesky(self.sde.cov(t))
+
+  def epsR2epsL_matrix(self, t):
+    """coef of epsR2epsL (sde_lib.py:494-499): L^T R^-T."""
+    return self.s_L(t).T @ inv_2x2(self.sde.R(t).T)
+
+  def psi(self, s, t):
+    return self.sde.psi(s, t)
+
+  def eps_integrand(self, ts):
+    out = []
+    for t in np.atleast_1d(ts):
+      G = self.sde.s_G(t)
+      out.append(0.5 * G @ G @ inv_2x2(self.s_L(t)).T)
+    return np.stack(out)
+
+  def get_deis_coef(self, order, rev_ts):
+    rev_ts = np.asarray(rev_ts, np.float64)
+    x_coef = self.sde.psi(rev_ts[:-1], rev_ts[1:])
+    return np.concatenate([x_coef[:, None], get_ab_eps_coef(self, order + 1, rev_ts, order)], axis=1)
+
+
+def ldeis_sampler(sde, eps_fn, u, nfe, deis_order, ts_order=2, denoising=False, centered=True, dtype=np.float64):
+  """_impl_Ldeis_sampler + get_L_deis_sampler, sampling.py:497-540 (the reference's denoising branch needs
+  LSDE.s_F, which does not exist; denoising here falls back to the base SDE's step)."""
+  lsde = LSDE(sde)
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = get_rev_ts(sde.T, sde.sampling_eps, ts_order, num_step)
+  coef = lsde.get_deis_coef(deis_order, rev_ts).astype(dtype)
+  u = np.asarray(u, dtype=dtype)
+  eps_pred = np.stack([u] * (deis_order + 1))
+  for i in range(num_step):
+    eps = np.asarray(eps_fn(u, rev_ts[i]), dtype=np.float64)
+    eps = np.einsum("ij,...j->...i", lsde.epsR2epsL_matrix(rev_ts[i]), eps).astype(dtype)
+    u, eps_pred = multistep_ab_step(u, coef[i], eps, eps_pred)
+    u = u.astype(dtype)
+  if denoising:
+    u = denoise_step(sde, eps_fn, u).astype(dtype)
+  x, v = u[..., 0], u[..., 1]
+  return ((x + 1.0) / 2.0 if centered else x), v, nfe
+
+
+def em_sampler(sde, eps_fn, u, nfe, z, lambda_coef=0.0, ts_order=2, denoising=False, centered=True, dtype=np.float64):
+  """get_em_sampler, sampling.py:624-669; z [num_step, *u.shape] standard normals."""
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = get_rev_ts(sde.T, sde.sampling_eps, ts_order, num_step)
+  u = np.asarray(u, dtype=dtype)
+  for i in range(num_step):
+    cur_t, next_t = rev_ts[i], rev_ts[i + 1]
+    dt = next_t - cur_t
+    G = sde.s_G(cur_t)
+    score = sde.eps2score(np.asarray(eps_fn(u, cur_t), np.float64), cur_t)
+    grad = np.einsum("ij,...j->...i", sde.s_F(cur_t), u) - (1.0 + lambda_coef) / 2.0 * np.einsum("ij,...j->...i", G @ G.T, score)
+    noise = z[i] * np.sqrt(np.abs(dt))
+    u = (u + grad * dt + np.einsum("ij,...j->...i", G, noise) * lambda_coef).astype(dtype)
+  if denoising:
+    u = denoise_step(sde, eps_fn, u).astype(dtype)
+  x, v = u[..., 0], u[..., 1]
+  return ((x + 1.0) / 2.0 if centered else x), v, nfe
+
+
+def _sscs_ou(sde, u, s_t, s_t_next, z):
+  """get_sscs_ou_fn, sampling.py:542-566."""
+  bi = -1 * (sde.beta_int(1 - s_t_next) - sde.beta_int(1 - s_t))
+  Gm = sde.Gamma
+  mean_matrix = np.array([[1 + 2 * bi / Gm, -4 * bi / Gm / Gm], [bi, 1 - 2 * bi / Gm]]) * np.exp(-2.0 * bi / Gm)
+  cov_xx = np.exp(4 * bi / Gm) - 1 - 4 * bi / Gm - 8 * bi ** 2 / Gm / Gm
+  cov_xv = -4 * bi ** 2 / Gm
+  cov_vv = (Gm / 2) ** 2 * (np.exp(4 * bi / Gm) - 1) + bi * Gm - 2 * bi ** 2
+  cov = np.array([[cov_xx, cov_xv], [cov_xv, cov_vv]]) * np.exp(-4 * bi / Gm)
+  return np.einsum("ij,...j->...i", mean_matrix, u) + np.einsum("ij,...j->...i", mvn_factor_svd(cov), z)
+
+
+def sscs_sampler(sde, eps_fn, u, nfe, z, ts_order=2, denoising=False, centered=True, dtype=np.float64):
+  """get_sscs_sampler, sampling.py:568-622; z [num_step, 2, *u.shape]: the two OU half-step draws of every step."""
+  num_step = nfe - 1 if denoising else nfe
+  ts = 1 - get_rev_ts(sde.T, sde.sampling_eps, ts_order, num_step)
+  u = np.asarray(u, dtype=dtype)
+  for i in range(num_step):
+    cur_t, next_t = ts[i], ts[i + 1]
+    mid = (cur_t + next_t) / 2.0
+    u = _sscs_ou(sde, u, cur_t, mid, z[i, 0]).astype(dtype)
+    score = sde.eps2score(np.asarray(eps_fn(u, sde.T - cur_t), np.float64), sde.T - cur_t)
+    v = u[..., 1] + 2 * sde.beta(cur_t) * sde.Gamma * (score[..., 1] + sde.m_inv * u[..., 1]) * (next_t - cur_t)
+    u = np.stack([u[..., 0], v], axis=-1).astype(dtype)
+    u = _sscs_ou(sde, u, mid, next_t, z[i, 1]).astype(dtype)
+  if denoising:
+    u = denoise_step(sde, eps_fn, u).astype(dtype)
+  x, v = u[..., 0], u[..., 1]
+  return ((x + 1.0) / 2.0 if centered else x), v, nfe

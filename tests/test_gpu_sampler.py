@@ -312,3 +312,51 @@ def test_sdeis_internal_philox_stream():
   got = d.T @ d / d.shape[0]
   assert abs(d.mean()) < 0.02 * np.sqrt(np.abs(want).max())
   np.testing.assert_allclose(got, want, rtol=0.05, atol=0.02 * np.abs(want).max())
+
+
+def _mixed_off_pair():
+  """small CLD net on the cheap Euler R table (R_dt = 1e-4) with mixed_score off, library SDE + oracle SDE."""
+  from oracle import cld as oc
+  cfg, model, net_fn = build("cld_mixed")
+  cfg.model.mixed_score = False
+  sde, o = sde_lib.from_config(cfg), oc.from_config(cfg)
+  cfg.model.mixed_score = True
+  return cfg, model, net_fn, sde, o
+
+
+def test_ldeis_matches_oracle():
+  """'ldeis' (sampling.py:497-540), the L_t-parameterised DEIS baseline."""
+  from oracle import cld as oc
+  cfg, model, net_fn, sde, o = _mixed_off_pair()
+  fn = sampling.get_L_deis_sampler(sde, model, (32, 32, 3), 6, inv, 2, ts_order=2, denoising=False)
+  u = prior_u(2, seed=61)
+  x, v, n = fn(0, model, 2, u=u)
+  ox, ov, _ = oc.ldeis_sampler(o, oc.make_eps_fn(o, net_fn), u, 6, 2, denoising=False, dtype=np.float32)
+  print(f"ldeis: x {rel_l2(x, ox):.2e}")
+  assert n == 6 and rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
+
+
+def test_em_matches_oracle_with_shared_noise():
+  """'em' (sampling.py:624-669): Euler-Maruyama with lambda-scaled noise."""
+  from oracle import cld as oc
+  cfg, model, net_fn, sde, o = _mixed_off_pair()
+  fn = sampling.get_em_sampler(sde, model, (32, 32, 3), 6, inv, lambda_coef=0.7, ts_order=2, denoising=True)
+  u = prior_u(2, seed=62)
+  z = np.random.default_rng(63).standard_normal((5,) + u.shape).astype(np.float32)
+  x, v, n = fn(0, model, 2, u=u, noise=z)
+  ox, ov, _ = oc.em_sampler(o, oc.make_eps_fn(o, net_fn), u, 6, z, lambda_coef=0.7, denoising=True, dtype=np.float32)
+  print(f"em: x {rel_l2(x, ox):.2e}")
+  assert n == 6 and rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
+
+
+def test_sscs_matches_oracle_with_shared_noise():
+  """'sscs' (sampling.py:542-622): OU half step / score kick / OU half step; two noise draws per step."""
+  from oracle import cld as oc
+  cfg, model, net_fn, sde, o = _mixed_off_pair()
+  fn = sampling.get_sscs_sampler(sde, model, (32, 32, 3), 5, inv, ts_order=2, denoising=False)
+  u = prior_u(2, seed=64)
+  z = np.random.default_rng(65).standard_normal((5, 2) + u.shape).astype(np.float32)
+  x, v, n = fn(0, model, 2, u=u, noise=z.reshape((10,) + u.shape))
+  ox, ov, _ = oc.sscs_sampler(o, oc.make_eps_fn(o, net_fn), u, 5, z, denoising=False, dtype=np.float32)
+  print(f"sscs: x {rel_l2(x, ox):.2e}")
+  assert n == 5 and rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
