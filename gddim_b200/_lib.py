@@ -48,7 +48,8 @@ class NormDesc(C.Structure):
 
 class Step(C.Structure):
   _fields_ = [("t", C.c_double), ("n_eps", C.c_int), ("first_eps", C.c_int), ("A", C.c_float * 4),
-              ("C", (C.c_float * 4) * 6), ("F", C.c_float * 4), ("M", C.c_float * 4), ("trace", C.c_int)]
+              ("C", (C.c_float * 4) * 6), ("F", C.c_float * 4), ("M", C.c_float * 4), ("trace", C.c_int),
+              ("has_P", C.c_int), ("P", C.c_float * 4)]
 
 
 CLD_DEIS, CLD_ORDER0, BLUR_ORDER0, CLD_SDEIS, CLD_PROGRAM = 0, 1, 2, 3, 4
@@ -103,6 +104,8 @@ SIGNATURES = {
     "gddim_sampler_create_ts": (C.c_int, [_P, C.POINTER(SamplerCfg), _P, _P, _P, C.c_int, C.POINTER(_P)]),
     "gddim_sampler_create_program": (C.c_int, [_P, C.POINTER(SamplerCfg), _P, C.c_int, C.c_int, C.POINTER(_P)]),
     "gddim_cld_ldeis_coef": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
+    "gddim_cld_mldeis_coef": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
+    "gddim_cld_psi1": (C.c_int, [_P, C.c_double, C.c_int, _P]),
     "gddim_sampler_destroy": (None, [_P]),
     "gddim_sampler_coef": (C.c_longlong, [_P, _P, C.c_longlong]),
     "gddim_sampler_num_steps": (C.c_int, [_P]),

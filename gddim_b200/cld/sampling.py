@@ -16,7 +16,7 @@ import numpy as np
 from .. import _lib
 from .. import net as _net
 
-_NEXT = ("mldeis", "ode")
+_NEXT = ()
 
 
 def get_data_shape(config):
@@ -77,6 +77,14 @@ def get_sampling_fn(config, sde, model, shape, inverse_scaler):
     return get_em_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
                           inverse_scaler=inverse_scaler, lambda_coef=config.sampling.lambda_coef,
                           ts_order=config.sampling.ts_order, denoising=config.sampling.noise_removal, is_p=True)
+  if name == "mldeis":
+    return get_mldeis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
+                              inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
+                              ts_order=config.sampling.ts_order, denoising=config.sampling.noise_removal, is_p=True)
+  if name == "ode":
+    return get_ode_sampler(sde=sde, model=model, data_shape=data_shape, inverse_scaler=inverse_scaler,
+                           denoising=config.sampling.noise_removal, atol=config.sampling.atol,
+                           rtol=config.sampling.rtol, method=config.sampling.ode_method, is_p=True)
   if name == "hybdeis":
     return get_hyd_deis_sampler(sde=sde, model=model, data_shape=data_shape, nfe=config.sampling.nfe,
                                 inverse_scaler=inverse_scaler, deis_order=config.sampling.deis_order,
@@ -283,8 +291,6 @@ def get_sdeis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, l
   core = _Sampler(_lib.CLD_SDEIS, sde, model, data_shape, nfe, inverse_scaler, deis_order, int(ts_order), denoising,
                   is_p, lambda_coef=lambda_coef, use_order0=use_order0)
   return _wrap(core, sde, data_shape, is_p)
-get_mldeis_sampler = _next("get_mldeis_sampler")
-get_ode_sampler = _next("get_ode_sampler")
 
 
 # ---- samplers expressed as explicit step programs (gddim_sampler_create_program) ---------------------------------
@@ -315,8 +321,11 @@ class _ProgramSampler(_Sampler):
     return h
 
 
-def _step(t=-1.0, A=None, Cs=(), F=None, M=None, first_eps=0, trace=0):
+def _step(t=-1.0, A=None, Cs=(), F=None, M=None, first_eps=0, trace=0, P=None):
   st = _lib.Step()
+  st.has_P = int(P is not None)
+  for k in range(4):
+    st.P[k] = float(np.eye(2).ravel()[k]) if P is None else float(np.asarray(P, np.float64).ravel()[k])
   st.t, st.n_eps, st.first_eps, st.trace = float(t), len(Cs), int(first_eps), int(trace)
   A = np.eye(2) if A is None else np.asarray(A, np.float64)
   for k in range(4):
@@ -421,4 +430,106 @@ def get_sscs_sampler(sde, model, data_shape, nfe, inverse_scaler, ts_order=2, de
   if denoising:
     steps.append(_denoise_step(sde))
   core = _ProgramSampler(sde, model, data_shape, nfe, inverse_scaler, denoising, is_p, steps, 1)
+  return _wrap(core, sde, data_shape, is_p)
+
+
+def get_ode_sampler(sde, model, data_shape, inverse_scaler, denoising=False, rtol=1e-5, atol=1e-5, method="RK45",
+                    is_p=False):
+  """sampling.py:432-495: probability-flow ODE integrated by scipy's black-box solver on the host; every drift
+  evaluation is one network evaluation on the GPU (gddim_unet_forward) followed by 2x2 algebra in torch.
+  Like the reference, the pmapped variant skips the denoising step (sampling.py:489) and takes the *global* batch."""
+  import torch
+  from scipy import integrate
+
+  def _run(pstate, batch_size, u, apply_denoise):
+    _lib.require_cuda("ode sampler")
+    net = _net.resolve_net(model, pstate, cld=True)
+    is_np = not torch.is_tensor(u)
+    ud = torch.as_tensor(np.ascontiguousarray(u, dtype=np.float32)).cuda() if is_np else u.float().cuda()
+    d_shape = tuple(ud.shape)
+    Cc = d_shape[-2]
+    mats = {}
+
+    def eps_of(x, t):
+      net_in = torch.cat([x[..., 0], x[..., 1]], dim=-1).contiguous()
+      out = net.forward(net_in, float(t))
+      eps = torch.stack([out[..., :Cc], out[..., Cc:]], dim=-1)
+      if sde.mixed_score:
+        inv_r = torch.as_tensor(np.linalg.inv(sde._R64([t])[0]), dtype=torch.float32, device=x.device)
+        x0 = x.clone()
+        x0[..., 0] = 0.0
+        eps = eps + torch.einsum("ij,...j->...i", inv_r, x0)
+      return eps
+
+    def drift(x, t):
+      F, G, R = sde._F64(t), sde._G64(t), sde._R64([t])[0]
+      f = torch.as_tensor(F, dtype=torch.float32, device=x.device)
+      # grad = F x - 0.5 G G score, score = -R^-T eps  =>  F x + 0.5 G G R^-T eps
+      c = torch.as_tensor(0.5 * (G @ G) @ np.linalg.inv(R).T, dtype=torch.float32, device=x.device)
+      return torch.einsum("ij,...j->...i", f, x) + torch.einsum("ij,...j->...i", c, eps_of(x, t))
+
+    def ode_func(t, xf):
+      x = torch.as_tensor(xf.reshape(d_shape), dtype=torch.float32).cuda()
+      return drift(x, t).cpu().numpy().reshape(-1).astype(np.float64)
+
+    sol = integrate.solve_ivp(ode_func, (sde.T, sde.sampling_eps), ud.cpu().numpy().reshape(-1).astype(np.float64),
+                              rtol=rtol, atol=atol, method=method)
+    nfe = sol.nfev
+    uo = torch.as_tensor(sol.y[:, -1].reshape(d_shape), dtype=torch.float32).cuda()
+    if apply_denoise and denoising:
+      t = sde.sampling_eps
+      F, G, R = sde._F64(t), sde._G64(t), sde._R64([t])[0]
+      a = torch.as_tensor(np.eye(2) - t * F, dtype=torch.float32, device=uo.device)
+      c = torch.as_tensor(-t * (G @ G) @ np.linalg.inv(R).T, dtype=torch.float32, device=uo.device)
+      uo = torch.einsum("ij,...j->...i", a, uo) + torch.einsum("ij,...j->...i", c, eps_of(uo, t))
+    x, v = uo[..., 0], uo[..., 1]
+    x = inverse_scaler(x) if inverse_scaler is not None else x
+    if is_np:
+      return np.asarray(x.cpu()), np.asarray(v.cpu()), nfe
+    return x, v, nfe
+
+  def sampler(rng, state, batch_size, u=None):
+    if u is None:
+      u = sde.prior_sampling(rng, (batch_size,) + tuple(data_shape))
+    return _run(state, batch_size, u, True)
+
+  def psampler(prng, pstate, batch_size, u=None):
+    if u is None:
+      u = sde.prior_sampling(prng, (1, batch_size) + tuple(data_shape))
+    if u.shape[0] != 1:
+      raise ValueError("this process drives one GPU: the leading device axis of u must be 1")
+    x, v, nfe = _run(pstate, batch_size, u[0], False)
+    return x[None], v[None], nfe
+
+  return psampler if is_p else sampler
+
+
+def _psi1(sde, t, inverse=False):
+  out = np.empty((2, 2))
+  _lib.check(_lib.lib().gddim_cld_psi1(sde._h, float(t), int(inverse), out.ctypes.data))
+  return out
+
+
+def get_mldeis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, ts_order=2, denoising=False, is_p=False):
+  """sampling.py:328-378 on MLCLD (272-325): DEIS in the frame rotated by psi1 = expm(int F_1).  The state is
+  y = psi1(T)^-1 u; the network sees psi1(t_i) y; the result is mapped back with psi1(sampling_eps / 2).  As in the
+  reference, the denoising step is applied to the rotated variable as if it were u (sampling.py:366)."""
+  if sde.beta_1 != 0:
+    raise AssertionError("MLCLD requires beta_1 == 0 (sampling.py:289)")
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = np.asarray(get_rev_ts(sde, ts_order, num_step), np.float64)
+  coef = np.empty((num_step, deis_order + 3, 2, 2))
+  _lib.check(_lib.lib().gddim_cld_mldeis_coef(sde._h, int(deis_order), rev_ts.ctypes.data, rev_ts.size, coef.ctypes.data),
+             "gddim_cld_mldeis_coef")
+  steps = [_step(A=_psi1(sde, sde.T, inverse=True))]                              # x2y at T
+  for i in range(num_step):
+    r = min(i, deis_order)
+    P = _psi1(sde, rev_ts[i])
+    M = _mix_matrix(sde, rev_ts[i])
+    steps.append(_step(t=rev_ts[i], A=coef[i, 0], Cs=[coef[i, 1 + j] for j in range(r + 1)], P=P,
+                       M=None if M is None else M @ P, trace=1))
+  if denoising:
+    steps.append(_denoise_step(sde))
+  steps.append(_step(A=_psi1(sde, sde.sampling_eps / 2)))                          # y2x at sampling_eps / 2
+  core = _ProgramSampler(sde, model, data_shape, nfe, inverse_scaler, denoising, is_p, steps, deis_order + 1)
   return _wrap(core, sde, data_shape, is_p)

@@ -208,6 +208,18 @@ int gddim_cld_ldeis_coef(const gddim_cld* cld, int order, const double* rev_ts, 
   cld->t->ldeis_coef(order, rev_ts, n_ts, out);
   return 0;
 }
+int gddim_cld_mldeis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out) {
+  if (!cld || !rev_ts || !out || order < 0 || order > 4 || n_ts < 2 || n_ts - 1 < order)
+    return set_err("gddim_cld_mldeis_coef: bad arguments");
+  if (cld->t->beta_1 != 0.0) return set_err("gddim_cld_mldeis_coef: MLCLD requires beta_1 == 0 (sampling.py:289)");
+  cld->t->mldeis_coef(order, rev_ts, n_ts, out);
+  return 0;
+}
+int gddim_cld_psi1(const gddim_cld* cld, double t, int inverse, double* out) {
+  if (!cld || !out) return set_err("gddim_cld_psi1: bad arguments");
+  put(out, inverse ? cld->t->f1_psi(t, 0.0) : cld->t->f1_psi(0.0, t));
+  return 0;
+}
 int gddim_rev_ts(double T, double eps, int ts_order, int num_step, double* out) {
   if (!out || num_step < 1 || ts_order < 1) return set_err("gddim_rev_ts: bad arguments");
   rev_timesteps(T, eps, ts_order, num_step, out);
@@ -510,6 +522,7 @@ int gddim_sampler_create_program(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, c
   const size_t img_elems = (size_t)net.max_batch() * s->S * s->S * s->C;
   s->d_eps.resize(history, nullptr);
   bool ok = cudaMalloc(&s->d_u, state_elems * 4) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->d_xin, state_elems * 4) == cudaSuccess;
   for (auto& p : s->d_eps) ok = ok && cudaMalloc(&p, state_elems * 4) == cudaSuccess;
   ok = ok && cudaMalloc(&s->d_stage, state_elems * 4) == cudaSuccess;
   ok = ok && cudaMalloc(&s->d_x, img_elems * 4) == cudaSuccess && cudaMalloc(&s->d_v, img_elems * 4) == cudaSuccess;
@@ -555,7 +568,7 @@ static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t s
   const int tt = net.temb_total();
   if (tt > 0)
     cudaMemcpyAsync(net.temb_cur(), s->d_temb_all + (size_t)e * tt, (size_t)tt * 4, cudaMemcpyDeviceToDevice, st);
-  const float* in = s->is_blur ? s->d_xin : s->d_u;
+  const float* in = (s->is_blur || s->cfg.kind == GDDIM_CLD_PROGRAM) ? s->d_xin : s->d_u;
   if (s->cfg.use_graph && !net.profiling()) {
     if (s->graph_batch != batch) {
       for (auto g : s->graphs) if (g) cudaGraphExecDestroy(g);
@@ -638,6 +651,14 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
         if (ps.t >= 0) {
           ++ne;
           slot = ne % ring;
+          // network input: the state, or P * state for rotating-frame samplers
+          CldStepArgs pin;
+          memset(&pin, 0, sizeof(pin));
+          pin.u = s->d_u; pin.u_out = s->d_xin; pin.n_pix = n_pix; pin.C = s->C;
+          const float ident[4] = {1.f, 0.f, 0.f, 1.f};
+          memcpy(pin.coef[0], ps.has_P ? ps.P : ident, 16);
+          if (cld_step_launch(&pin, st)) return set_err("cld_step launch failed");
+          s->launches += 1;
           if (eval_net(s, ne, slot, batch, st)) return -1;
         }
         CldStepArgs a;

@@ -15,6 +15,8 @@
 
 namespace gddim {
 
+static Mat2 rk4(const Mat2& x, double t, double dt, const std::function<Mat2(const Mat2&, double)>& fn);
+
 void rev_timesteps(double T, double eps, int ts_order, int num_step, double* out) {
   const double a = std::pow(T, 1.0 / ts_order), b = std::pow(eps, 1.0 / ts_order);
   // numpy.linspace(a, b, n+1): a + k*step, last element set to b
@@ -374,6 +376,62 @@ void CldTables::ldeis_coef(int order, const double* rev_ts, int n_ts, double* ou
   deis_ab_eps_coef(p, f, highest, rev_ts, n_ts, order, eps);
   for (int i = 0; i < N; ++i) {
     const Mat2 x = psi(rev_ts[i], rev_ts[i + 1]);
+    double* o = out + (size_t)i * per * 4;
+    o[0] = x.a; o[1] = x.b; o[2] = x.c; o[3] = x.d;
+    std::memcpy(o + 4, eps.data() + (size_t)i * (highest + 1) * 4, sizeof(double) * (highest + 1) * 4);
+  }
+}
+
+Mat2 CldTables::f1_psi(double s, double t) const {
+  const double bi = beta_int(t) - beta_int(s);
+  const double sm = std::sqrt(1.0 / m_inv), ism = std::sqrt(m_inv);
+  return {std::cos(bi * ism), ism * std::sin(bi * ism), -sm * std::sin(bi * ism), std::cos(bi * ism)};
+}
+
+void CldTables::build_psi2() const {
+  if (!p2x_.empty()) return;
+  const long N = 100000;                         // sampling.py:273
+  const double dt = 1.0 / N;
+  p2x_.resize(N + 1);
+  p2f_.resize(N + 1);
+  Mat2 x = {1, 0, 0, 1};
+  double t = 0.0;
+  auto fn = [this](const Mat2& v, double tt) {
+    const Mat2 f2 = {0.0, 0.0, 0.0, -Gamma * beta(tt) * m_inv};
+    return mul(mul(mul(f1_psi(tt, 0.0), f2), f1_psi(0.0, tt)), v);
+  };
+  for (long k = 0; k <= N; ++k) {                // scan emits (prev_psi2, cur_t) before the update
+    p2x_[k] = t;
+    p2f_[k] = x;
+    x = rk4(x, t, dt, fn);
+    t += dt;
+  }
+}
+
+Mat2 CldTables::psi2(double t) const {
+  build_psi2();
+  long i = std::upper_bound(p2x_.begin(), p2x_.end(), t) - p2x_.begin();
+  const long n = (long)p2x_.size();
+  i = std::min(std::max(i, 1L), n - 1);
+  const double dx = p2x_[i] - p2x_[i - 1];
+  if (dx == 0) return p2f_[i];
+  const double w = (t - p2x_[i - 1]) / dx;
+  const Mat2 &p = p2f_[i - 1], &q = p2f_[i];
+  return {p.a + w * (q.a - p.a), p.b + w * (q.b - p.b), p.c + w * (q.c - p.c), p.d + w * (q.d - p.d)};
+}
+
+void CldTables::mldeis_coef(int order, const double* rev_ts, int n_ts, double* out) const {
+  const int N = n_ts - 1, highest = order + 1, per = order + 3;
+  PsiFn p = [this](double s, double t) { return mul(psi2(t), inv(psi2(s))); };
+  IntegrandFn f = [this](double tau) {
+    const Mat2 g = G(tau);
+    const Mat2 m = mul(mul(mul(f1_psi(tau, 0.0), g), tr(g)), tr(inv(R(tau))));
+    return Mat2{0.5 * m.a, 0.5 * m.b, 0.5 * m.c, 0.5 * m.d};
+  };
+  std::vector<double> eps;
+  deis_ab_eps_coef(p, f, highest, rev_ts, n_ts, order, eps);
+  for (int i = 0; i < N; ++i) {
+    const Mat2 x = p(rev_ts[i], rev_ts[i + 1]);
     double* o = out + (size_t)i * per * 4;
     o[0] = x.a; o[1] = x.b; o[2] = x.c; o[3] = x.d;
     std::memcpy(o + 4, eps.data() + (size_t)i * (highest + 1) * 4, sizeof(double) * (highest + 1) * 4);

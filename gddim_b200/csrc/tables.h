@@ -55,11 +55,18 @@ class CldTables {
   void denoise_coef(double t, Mat2* A, Mat2* C) const;
   // LSDE (sde_lib.py:469-519): same table with the Cholesky factor L_t of Sigma_t in the integrand
   Mat2 chol_cov(double t) const;
+  // MLCLD (cld_jax/sampling.py:272-325, sde_lib.py:120-181): rotating frame psi1 = expm(int F1), psi2 table
+  Mat2 f1_psi(double s, double t) const;
+  Mat2 psi2(double t) const;
+  void mldeis_coef(int order, const double* rev_ts, int n_ts, double* out) const;
   void ldeis_coef(int order, const double* rev_ts, int n_ts, double* out) const;
 
  private:
   std::vector<double> xp_;
   std::vector<Mat2> fp_;
+  mutable std::vector<double> p2x_;      // psi2 table, built on first use
+  mutable std::vector<Mat2> p2f_;
+  void build_psi2() const;
   Mat2 ode_rhs(const Mat2& R, double t) const;
   Mat2 quad(double t_start, double t_end, const double* ts_poly, int n_poly, int coef_idx, int num_item) const;
   void coef_row(int highest_order, int order, double t_start, double t_end, const double* ts_poly, double* out) const;

@@ -203,11 +203,17 @@ typedef struct {
   float F[4];        /* noise factor, all zero = deterministic step */
   float M[4];        /* mixed score: eps_0 += M u (applied when cfg.mixed_score) */
   int trace;         /* 1: the state after this step is written to trace_dev (in order) */
+  int has_P;         /* 1: the network is evaluated on P u instead of u (rotating-frame samplers: mldeis) */
+  float P[4];
 } gddim_step;
 int gddim_sampler_create_program(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_step* steps, int n_steps,
                                  int history, gddim_sampler** out);
 /* LSDE(sde).get_deis_coef(order, rev_ts) (sde_lib.py:469-519: Cholesky L_t in place of R_t): out [n_ts-1, order+3, 2, 2] */
 int gddim_cld_ldeis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out);
+/* MLCLD(sde).get_deis_coef(order, rev_ts) (sampling.py:286-325): out [n_ts-1, order+3, 2, 2]; psi1: expm(int_0^t F_1)
+ * (inverse = 1: expm(int_t^0 F_1)), sde_lib.py:120-156 */
+int gddim_cld_mldeis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out);
+int gddim_cld_psi1(const gddim_cld* cld, double t, int inverse, double* out /*[2,2]*/);
 void gddim_sampler_destroy(gddim_sampler* s);
 /* The table the sampler steps through (for index-exact parity checks): fp32 [n_steps, order+3, 2, 2] for CLD
  * deis.  Returns the number of floats written (or needed when out == NULL). */

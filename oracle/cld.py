@@ -585,3 +585,97 @@ def sscs_sampler(sde, eps_fn, u, nfe, z, ts_order=2, denoising=False, centered=T
     u = denoise_step(sde, eps_fn, u).astype(dtype)
   x, v = u[..., 0], u[..., 1]
   return ((x + 1.0) / 2.0 if centered else x), v, nfe
+
+
+def ode_sampler(sde, eps_fn, u, denoising=False, rtol=1e-5, atol=1e-5, method="RK45", centered=True):
+  """get_ode_sampler.sampler, sampling.py:432-464: scipy RK45 on the probability-flow ODE."""
+  from scipy import integrate
+  shape = u.shape
+
+  def ode_func(t, xf):
+    x = xf.reshape(shape)
+    score = sde.eps2score(np.asarray(eps_fn(x.astype(np.float32), t), np.float64), t)
+    F, G = sde.s_F(t), sde.s_G(t)
+    return (np.einsum("ij,...j->...i", F, x) - 0.5 * np.einsum("ij,...j->...i", G @ G, score)).reshape(-1)
+  sol = integrate.solve_ivp(ode_func, (sde.T, sde.sampling_eps), np.asarray(u, np.float64).reshape(-1), rtol=rtol,
+                            atol=atol, method=method)
+  uo = sol.y[:, -1].reshape(shape)
+  if denoising:
+    uo = denoise_step(sde, eps_fn, uo)
+  x, v = uo[..., 0], uo[..., 1]
+  return ((x + 1.0) / 2.0 if centered else x), v, sol.nfev
+
+
+class MLCLD:
+  """cld_jax/sampling.py:272-325 on the CLD helpers sde_lib.py:120-181 (rotating frame psi1 = expm(int F_1))."""
+
+  def __init__(self, sde, n=100_000):
+    assert sde.beta_1 == 0
+    self.sde, self.T, self.sampling_eps, self.mixed_score = sde, sde.T, sde.sampling_eps, sde.mixed_score
+    dt = 1.0 / n
+    fn = lambda p2, t: self.inv_psi1(t) @ self.F2(t) @ self.psi1(t) @ p2
+    xs, ts = np.empty((n + 1, 2, 2)), np.empty(n + 1)
+    x, t = np.eye(2), 0.0
+    for k in range(n + 1):                                     # scan emits (prev_psi2, cur_t), sampling.py:276-283
+      xs[k], ts[k] = x, t
+      x = _rk4(x, t, dt, fn)
+      t = t + dt
+    self._xp, self._fp = ts, xs
+
+  def f1_psi(self, s, t):
+    bi = self.sde.beta_int(t) - self.sde.beta_int(s)
+    sm, ism = np.sqrt(1.0 / self.sde.m_inv), np.sqrt(self.sde.m_inv)
+    return np.array([[np.cos(bi * ism), ism * np.sin(bi * ism)], [-sm * np.sin(bi * ism), np.cos(bi * ism)]])
+
+  def psi1(self, t):
+    return self.f1_psi(0.0, t)
+
+  def inv_psi1(self, t):
+    return self.f1_psi(t, 0.0)
+
+  def F2(self, t):
+    return np.array([[0.0, 0.0], [0.0, -self.sde.Gamma * self.sde.beta(t) * self.sde.m_inv]])
+
+  def psi2(self, t):
+    xp, fp = self._xp, self._fp
+    i = int(np.clip(np.searchsorted(xp, t, side="right"), 1, len(xp) - 1))
+    return fp[i - 1] + (t - xp[i - 1]) / (xp[i] - xp[i - 1]) * (fp[i] - fp[i - 1])
+
+  def psi(self, ss, t):
+    p2t = self.psi2(t)
+    if np.ndim(ss) == 0:
+      return p2t @ np.linalg.inv(self.psi2(ss))
+    return np.stack([p2t @ np.linalg.inv(self.psi2(s)) for s in ss])
+
+  def eps_integrand(self, ts):
+    out = []
+    for t in np.atleast_1d(ts):
+      G = self.sde.s_G(t)
+      out.append(0.5 * self.inv_psi1(t) @ G @ G.T @ self.sde.invR(t).T)
+    return np.stack(out)
+
+  def get_deis_coef(self, order, rev_ts):
+    rev_ts = np.asarray(rev_ts, np.float64)
+    x_coef = np.stack([self.psi(s, t) for s, t in zip(rev_ts[:-1], rev_ts[1:])])
+    return np.concatenate([x_coef[:, None], get_ab_eps_coef(self, order + 1, rev_ts, order)], axis=1)
+
+
+def mldeis_sampler(sde, eps_fn, u, nfe, deis_order, ts_order=2, denoising=False, centered=True, dtype=np.float64,
+                   ml=None):
+  """get_mldeis_sampler, sampling.py:328-378 (the denoising step acts on the rotated variable, as written there)."""
+  ml = ml or MLCLD(sde)
+  num_step = nfe - 1 if denoising else nfe
+  rev_ts = get_rev_ts(sde.T, sde.sampling_eps, ts_order, num_step)
+  coef = ml.get_deis_coef(deis_order, rev_ts).astype(dtype)
+  y = np.einsum("ij,...j->...i", ml.inv_psi1(sde.T), np.asarray(u, np.float64)).astype(dtype)
+  eps_pred = np.stack([y] * (deis_order + 1))
+  for i in range(num_step):
+    x_u = np.einsum("ij,...j->...i", ml.psi1(rev_ts[i]), y.astype(np.float64)).astype(dtype)
+    eps = np.asarray(eps_fn(x_u, rev_ts[i]), dtype=dtype)
+    y, eps_pred = multistep_ab_step(y, coef[i], eps, eps_pred)
+    y = y.astype(dtype)
+  if denoising:
+    y = denoise_step(sde, eps_fn, y).astype(dtype)
+  uo = np.einsum("ij,...j->...i", ml.psi1(sde.sampling_eps / 2), y.astype(np.float64)).astype(dtype)
+  x, v = uo[..., 0], uo[..., 1]
+  return ((x + 1.0) / 2.0 if centered else x), v, nfe

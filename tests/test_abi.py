@@ -139,3 +139,19 @@ def test_sdeis_tables_match_oracle():
     np.testing.assert_allclose(sde_lib.mvn_factor_svd(c), oc.mvn_factor_svd(c), atol=1e-12)
   f = oc.mvn_factor_svd(np.array([[2.0, 1.0], [1.0, 3.0]]))
   np.testing.assert_allclose(f @ f.T, [[2.0, 1.0], [1.0, 3.0]], atol=1e-12)
+
+
+def test_ldeis_and_mldeis_tables_match_oracle():
+  cfg = configs.cld_deep_cifar10()
+  cfg.model.R_dt = 1e-4
+  a, o = sde_lib.from_config(cfg), oc.from_config(cfg)
+  rev = oc.get_rev_ts(1.0, 1e-3, 2, 4)
+  np.testing.assert_allclose(sde_lib.LSDE(a).get_deis_coef(2, rev), oc.LSDE(o).get_deis_coef(2, rev), rtol=3e-6, atol=1e-8)
+  got = np.empty((4, 4, 2, 2))
+  _lib.check(_lib.lib().gddim_cld_mldeis_coef(a._h, 1, rev.ctypes.data, 5, got.ctypes.data))
+  want = oc.MLCLD(o, n=100_000).get_deis_coef(1, rev)
+  np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12)
+  # every sampler name of cld_jax/sampling.py:57-153 dispatches
+  for name in ("order0", "deis", "sdeis", "ldeis", "hybdeis", "mldeis", "ode", "sscs", "em"):
+    cfg.sampling.method = name
+    assert callable(sampling.get_sampling_fn(cfg, a, None, None, lambda x: (x + 1) / 2))

@@ -360,3 +360,30 @@ def test_sscs_matches_oracle_with_shared_noise():
   ox, ov, _ = oc.sscs_sampler(o, oc.make_eps_fn(o, net_fn), u, 5, z, denoising=False, dtype=np.float32)
   print(f"sscs: x {rel_l2(x, ox):.2e}")
   assert n == 5 and rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
+
+
+def test_ode_sampler_matches_oracle():
+  """'ode' (sampling.py:432-495): scipy RK45 on the host, drift = one GPU network evaluation per call.  Adaptive
+  step control reacts to the ~1e-3 network rounding noise, so the two runs may take different step sequences:
+  loose tolerance on purpose (the solver tolerance itself is 1e-3 here to keep the oracle at a few seconds)."""
+  from oracle import cld as oc
+  cfg, model, net_fn, sde, o = _mixed_off_pair()
+  fn = sampling.get_ode_sampler(sde, model, (32, 32, 3), inv, denoising=True, rtol=1e-3, atol=1e-3)
+  u = prior_u(1, seed=66)
+  x, v, nfe = fn(0, model, 1, u=u)
+  ox, ov, onfe = oc.ode_sampler(o, oc.make_eps_fn(o, net_fn), u, denoising=True, rtol=1e-3, atol=1e-3)
+  print(f"ode: nfe {nfe} vs {onfe}; x {rel_l2(x, ox):.2e}")
+  assert np.isfinite(x).all() and rel_l2(x, ox) < 2e-2 and rel_l2(v, ov) < 2e-2
+
+
+def test_mldeis_matches_oracle():
+  """'mldeis' (sampling.py:272-378): DEIS in the frame rotated by expm(int F_1); psi2 table of 1e5 RK4 steps."""
+  from oracle import cld as oc
+  cfg, model, net_fn, sde, o = _mixed_off_pair()
+  fn = sampling.get_mldeis_sampler(sde, model, (32, 32, 3), 6, inv, 1, ts_order=2, denoising=True)
+  u = prior_u(2, seed=67)
+  x, v, n = fn(0, model, 2, u=u)
+  ml = oc.MLCLD(o, n=100_000)
+  ox, ov, _ = oc.mldeis_sampler(o, oc.make_eps_fn(o, net_fn), u, 6, 1, denoising=True, dtype=np.float32, ml=ml)
+  print(f"mldeis: x {rel_l2(x, ox):.2e}")
+  assert n == 6 and rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
