@@ -207,6 +207,10 @@ def _wrap(core, sde, data_shape, is_p):
   def sampler(rng, state, batch_size, u=None, trace=False, noise=None):
     """sampling.py:212-230 (non-pmapped): u (B,H,W,C,2) -> (x, v, nfe)."""
     if u is None:
+      from . import sde_lib as _sl
+      if _sl._is_jax_key(rng):                         # rng, step_rng = random.split(rng)   (sampling.py:213)
+        from .. import jax_random
+        rng = jax_random.split(rng)[1]
       u = sde.prior_sampling(rng, (batch_size,) + tuple(data_shape))
     if core.kind == _lib.CLD_SDEIS and noise is None and _seed_of(rng) != core.seed:
       core.seed = _seed_of(rng)          # a new key re-seeds the Philox stream (sampler object is rebuilt)
@@ -217,7 +221,10 @@ def _wrap(core, sde, data_shape, is_p):
     """sampling.py:232-237: leading axis = local devices driven by this process (1)."""
     import torch
     if u is None:
-      u = sde.prior_sampling(prng, (1, batch_size) + tuple(data_shape))
+      rng = prng                                        # flax.jax_utils.unreplicate(prng)   (sampling.py:233)
+      if isinstance(prng, np.ndarray) and prng.dtype == np.uint32 and prng.ndim == 2 and prng.shape[1] == 2:
+        rng = prng[0]
+      u = sde.prior_sampling(rng, (1, batch_size) + tuple(data_shape))
     if u.shape[0] != 1:
       raise ValueError("this process drives one GPU: the leading device axis of u must be 1 "
                        "(launch one process per GPU and shard the batch, see bench.py)")
@@ -232,9 +239,20 @@ def _wrap(core, sde, data_shape, is_p):
 
 
 def get_order0_sampler(sde, model, data_shape, nfe, inverse_scaler, is_em=False, denoising=False, is_p=False):
-  """sampling.py:156-202.  is_em=True (prepare_naive_coef) is the 'em'-flavoured variant: not in round 1."""
-  if is_em:
-    raise NotImplementedError("order0 with is_em=True (Euler coefficients) is a SURVEY.md 8(f) 'next' row")
+  """sampling.py:156-202 (is_em=True uses prepare_naive_coef, sde_lib.py:276-287)."""
+  if is_em:                                   # sampling.py:171-172: Euler coefficients (sde_lib.py:276-287)
+    num_step = nfe - 1 if denoising else nfe
+    rev_ts = np.asarray(get_rev_ts(sde, 2, num_step), np.float64)
+    steps = []
+    for i in range(num_step):
+      cur_t, dt = rev_ts[i], rev_ts[i + 1] - rev_ts[i]
+      G, R = sde._G64(cur_t), sde._R64([cur_t])[0]
+      steps.append(_step(t=cur_t, A=np.eye(2) + sde._F64(cur_t) * dt, Cs=[0.5 * (G @ G) @ np.linalg.inv(R).T * dt],
+                         M=_mix_matrix(sde, cur_t), trace=1))
+    if denoising:
+      steps.append(_denoise_step(sde))
+    core = _ProgramSampler(sde, model, data_shape, nfe, inverse_scaler, denoising, is_p, steps, 1)
+    return _wrap(core, sde, data_shape, is_p)
   core = _Sampler(_lib.CLD_ORDER0, sde, model, data_shape, nfe, inverse_scaler, 0, 2, denoising, is_p)
   return _wrap(core, sde, data_shape, is_p)
 

@@ -154,8 +154,12 @@ class CLD:
     return mean + perb, mean, raw_noise
 
   def prior_sampling(self, rng, shape):
-    """sde_lib.py:270-274.  JAX's threefry stream is not reproduced: `rng` seeds numpy's default_rng; x and v
-    are drawn from two child streams (mirrors the key split)."""
+    """sde_lib.py:270-274.  A jax PRNGKey (uint32[2]) reproduces jax.random's threefry stream
+    (gddim_b200/jax_random.py: split into x / v keys, normal = sqrt(2) erfinv(uniform)); anything else (int seed,
+    numpy Generator, None) seeds numpy's default_rng with two child streams."""
+    if _is_jax_key(rng):
+      from .. import jax_random
+      return jax_random.cld_prior(np.asarray(rng, np.uint32), shape, self.m_inv).astype(self._dt)
     g = _np_rng(rng)
     seeds = g.integers(0, 2 ** 63 - 1, size=2)
     xs = np.random.default_rng(int(seeds[0])).standard_normal(tuple(shape)).astype(self._dt)
@@ -186,6 +190,10 @@ class CLD:
     _lib.check(_lib.lib().gddim_cld_deis_coef(self._h, int(order), rev.ctypes.data, rev.size, out.ctypes.data),
                "gddim_cld_deis_coef")
     return out.astype(self._dt)
+
+
+def _is_jax_key(rng):
+  return isinstance(rng, np.ndarray) and rng.dtype == np.uint32 and rng.shape == (2,)
 
 
 def _np_rng(rng):

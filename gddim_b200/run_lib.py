@@ -1,0 +1,60 @@
+"""`sample_data` of cld_jax/run_lib.py:674-731 on top of the B200 sampler: seed -> prior ->
+sampler -> uint8 npz files, with the reference's key handling (PRNGKey(seed + 1), split per round), file naming and
+resume-by-skipping.  Everything else of run_lib.py (training, FID) stays out of scope."""
+import gc
+import io
+import logging
+import os
+
+import numpy as np
+
+from . import checkpoint, jax_random, net
+from .cld import sampling, sde_lib
+
+
+def get_data_inverse_scaler(config):
+  """cld_jax/datasets.py:34-40."""
+  if config.data.centered:
+    return lambda x: (x + 1.) / 2.
+  return lambda x: x
+
+
+def sample_data(config, ckpt_file, result_folder, is_continue=False, params=None, max_rounds=None):
+  """Mirrors run_lib.sample_data.  `ckpt_file` is a Flax msgpack checkpoint of the training `State` (its
+  `params_ema` is used, run_lib.py:707); alternatively pass `params` (Flax-named dict) directly."""
+  logging.critical(f"sample data for {result_folder}")
+  os.makedirs(result_folder, exist_ok=True)
+  rng = jax_random.PRNGKey(config.seed + 1)                                    # run_lib.py:682
+  inverse_scaler = get_data_inverse_scaler(config)
+  rng, model_rng = jax_random.split(rng)                                       # :688
+  score_model = net.ScoreNet(config, cld=True)
+  if params is None:
+    if not os.path.exists(ckpt_file):
+      raise RuntimeError(f"{ckpt_file} not exist")                             # :708-709
+    params = checkpoint.params_ema_from_checkpoint(ckpt_file)
+  score_model.set_params(params)
+  sde = sde_lib.from_config(config)
+  sampling_fn = sampling.get_sampling_fn(config, sde, score_model, None, inverse_scaler)
+  num_sampling_rounds = config.eval.num_samples // config.eval.batch_size + 1  # :704
+  n_dev = 1                                                                    # one process drives one GPU
+  written = []
+  for r in range(num_sampling_rounds):
+    keys = jax_random.split(rng, n_dev + 1)                                    # :715
+    rng, sample_rng = keys[0], keys[1:]
+    f_sample = os.path.join(result_folder, f"samples_{r}.npz")
+    if os.path.exists(f_sample) and is_continue:
+      logging.critical(f"SKIP!!! Already exists {f_sample}")
+      continue
+    if max_rounds is not None and len(written) >= max_rounds:
+      break
+    samples_org_x, samples_v, nfe_cnt = sampling_fn(sample_rng, score_model, config.eval.batch_size // n_dev)
+    samples_org_x, samples_v = np.asarray(samples_org_x), np.asarray(samples_v)
+    samples_x = np.clip(samples_org_x * 255., 0, 255).astype(np.uint8)         # :723
+    samples_x = samples_x.reshape((-1, config.data.image_size, config.data.image_size, config.data.num_channels))
+    io_buffer = io.BytesIO()
+    np.savez_compressed(io_buffer, samples=samples_x, nfe_cnt=nfe_cnt, samples_v=samples_v, samples_x=samples_org_x)
+    with open(f_sample, "wb") as fout:
+      fout.write(io_buffer.getvalue())
+    written.append(f_sample)
+    gc.collect()
+  return written

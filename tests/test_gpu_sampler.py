@@ -1,6 +1,8 @@
 """End-to-end sampler parity on the GPU through the reference-shaped Python API (get_sampling_fn /
 get_deis_sampler / get_order0_sampler) against the CPU oracle, on identical prior noise and parameters.
 Tolerance from BASELINE.json north_star: 1e-3 relative L2 on the samples."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -387,3 +389,46 @@ def test_mldeis_matches_oracle():
   ox, ov, _ = oc.mldeis_sampler(o, oc.make_eps_fn(o, net_fn), u, 6, 1, denoising=True, dtype=np.float32, ml=ml)
   print(f"mldeis: x {rel_l2(x, ox):.2e}")
   assert n == 6 and rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
+
+
+def test_sample_data_seed_to_npz(tmp_path):
+  """run_lib.sample_data (cld_jax/run_lib.py:674-731): Flax checkpoint -> jax-keyed prior -> sampler -> uint8 npz,
+  deterministic in config.seed, resumable by skipping existing files."""
+  from gddim_b200 import checkpoint, run_lib
+  cfg, model, _ = build("cld_deep")
+  cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "deis", 4, 1
+  cfg.eval.batch_size, cfg.eval.num_samples = 4, 4                      # 2 rounds (num_samples // batch + 1)
+  ck = tmp_path / "checkpoint_1"
+  checkpoint.save_flax_checkpoint(ck, model.params)
+  out = tmp_path / "res"
+  files = run_lib.sample_data(cfg, str(ck), str(out))
+  assert [os.path.basename(f) for f in files] == ["samples_0.npz", "samples_1.npz"]
+  a = np.load(files[0])
+  assert a["samples"].shape == (4, 32, 32, 3) and a["samples"].dtype == np.uint8 and int(a["nfe_cnt"]) == 4
+  assert a["samples_x"].shape == (1, 4, 32, 32, 3) and a["samples_v"].shape == (1, 4, 32, 32, 3)
+  out2 = tmp_path / "res2"
+  b = np.load(run_lib.sample_data(cfg, str(ck), str(out2), max_rounds=1)[0])
+  np.testing.assert_array_equal(a["samples"], b["samples"])              # same seed -> same images
+  assert run_lib.sample_data(cfg, str(ck), str(out), is_continue=True) == []   # everything already there
+  with pytest.raises(RuntimeError):
+    run_lib.sample_data(cfg, str(tmp_path / "missing"), str(out))
+
+
+def test_order0_is_em_matches_oracle():
+  """order0 with is_em=True (sampling.py:171-172, prepare_naive_coef)."""
+  from oracle import cld as oc
+  cfg, model, net_fn, sde, o = _mixed_off_pair()
+  fn = sampling.get_order0_sampler(sde, model, (32, 32, 3), 6, inv, is_em=True, denoising=True)
+  u = prior_u(2, seed=68)
+  x, v, n = fn(0, model, 2, u=u)
+  eps_fn = oc.make_eps_fn(o, net_fn)
+  rev = oc.get_rev_ts(1.0, 1e-3, 2, 5)
+  w = u.astype(np.float32)
+  for i in range(5):
+    cur, dt = rev[i], rev[i + 1] - rev[i]
+    G = o.s_G(cur)
+    mean = np.eye(2) + o.s_F(cur) * dt
+    em = 0.5 * G @ G @ oc.inv_2x2(o.R(cur)).T * dt
+    w = (np.einsum("ij,...j->...i", mean, w) + np.einsum("ij,...j->...i", em, eps_fn(w, cur))).astype(np.float32)
+  w = oc.denoise_step(o, eps_fn, w).astype(np.float32)
+  assert n == 6 and rel_l2(x, (w[..., 0] + 1) / 2) < TOL_MIXED and rel_l2(v, w[..., 1]) < TOL_MIXED
