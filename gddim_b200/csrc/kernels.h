@@ -107,6 +107,8 @@ int im2col_same3x3_launch(const float* in, __half* a16, int B, int H, int W, int
 // V^T per image for the PV GEMM: qkv16 [B,T,ld] (V at channel voff) -> vT [B,C,T]
 int transpose_v_launch(const __half* qkv, __half* vT, int B, int T, int C, int ld, int voff, cudaStream_t st);
 // Full attention for very short sequences (T <= 64): qkv16 [B,T,3C] -> o16 [B,T,C]
+// row softmax over T keys (long-sequence attention): p16 = exp(s - rowmax), rowinv = 1 / sum
+int softmax_rows_launch(const float* s32, __half* p16, float* rowinv, long long rows, int T, cudaStream_t st);
 int small_attn_launch(const __half* qkv, __half* o16, int B, int T, int C, float scale, cudaStream_t st);
 // y[r, n] = bias[n] + sum_k act(x[r,k]) * w[k,n]  (time-embedding MLP and per-block projections; fp32)
 int dense_launch(const float* x, const float* w, const float* bias, float* y, int rows, int K, int N, int silu_in,

@@ -417,6 +417,47 @@ int small_attn_launch(const __half* qkv, __half* o16, int B, int T, int C, float
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
+// ---- row softmax for long sequences (T > 256 keys: the 32x32-token middle attention of the 256x256 config) ------
+// One warp per query row: p16 = exp(s - max) in fp16, rowinv = 1 / sum of the ROUNDED numerators (what the P.V GEMM
+// will actually add up), same convention as the fused N = 256 epilogue.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s32, __half* __restrict__ p16,
+                                                          float* __restrict__ rowinv, long long rows, int T) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(s32 + row * T);
+  float mx = -INFINITY;
+  for (int j = lane; j < T / 4; j += 32) {
+    const float4 v = __ldg(src + j);
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  uint2* dst = reinterpret_cast<uint2*>(p16 + row * T);
+  for (int j = lane; j < T / 4; j += 32) {
+    const float4 v = __ldg(src + j);
+    const __half2 a = __floats2half2_rn(__expf(v.x - mx), __expf(v.y - mx));
+    const __half2 b = __floats2half2_rn(__expf(v.z - mx), __expf(v.w - mx));
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    sum += (fa.x + fa.y) + (fb.x + fb.y);
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned*>(&a);
+    o.y = *reinterpret_cast<const unsigned*>(&b);
+    dst[j] = o;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) rowinv[row] = 1.f / sum;
+}
+
+int softmax_rows_launch(const float* s32, __half* p16, float* rowinv, long long rows, int T, cudaStream_t st) {
+  if (T % 4 != 0 || rows <= 0) return -1;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  softmax_rows_kernel<<<grid, 256, 0, st>>>(s32, p16, rowinv, rows, T);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
 // ---- dense: y[r,n] = bias[n] + sum_k act(x[r,k]) w[k,n]  (w in flax (in,out) layout) ------------------------
 __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ y, int rows, int K,

@@ -431,12 +431,54 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
     }
     rel(p16); rel(vT);
     a_free(rowinv, (size_t)max_batch_ * T * 4);
+  } else if (T > 256 && T % 256 == 0 && C % 64 == 0) {
+    // long sequences (32x32 tokens of the 256x256 configuration): scores in fp32 through HBM, row softmax, P.V
+    T16 p16 = new16(T, H, W);
+    T16 vT; vT.C = T; vT.H = C; vT.W = 1; vT.bytes = (size_t)max_batch_ * C * T * 2; vT.p = (__half*)a_alloc(vT.bytes);
+    float* rowinv = (float*)a_alloc((size_t)max_batch_ * T * 4);
+    const size_t s_bytes = (size_t)max_batch_ * T * T * 4;
+    float* s32 = (float*)a_alloc(s_bytes);
+    {
+      Op op; op.kind = OP_GEMM; op.tag = s.prefix + "qk";
+      op.gemm = make_gemm(max_batch_, H, W);
+      GemmOp& g = op.gemm;
+      g.nseg = 1; g.seg[0] = {qkv.p, 3 * C, 0, C, 1};
+      g.w = qkv.p; g.N = T; g.w_ld = 3 * C; g.w_koff = C;
+      g.w_batch_stride = (long long)T * 3 * C; g.w_rows_per_batch = T;
+      g.scale = sm_scale;
+      g.out32 = s32; g.ldo = T;
+      ops_.push_back(op);
+    }
+    {
+      Op op; op.kind = OP_SOFTMAX_ROWS; op.tag = s.prefix + "softmax";
+      op.f_in = s32; op.h_out = p16.p; op.f_out = rowinv; op.T = T;
+      ops_.push_back(op);
+    }
+    a_free(s32, s_bytes);
+    {
+      Op op; op.kind = OP_TRANSPOSE_V; op.tag = s.prefix + "vT";
+      op.h_in = qkv.p; op.h_out = vT.p; op.T = T; op.cin = C; op.ld = 3 * C; op.voff = 2 * C;
+      ops_.push_back(op);
+    }
+    {
+      Op op; op.kind = OP_GEMM; op.tag = s.prefix + "pv";
+      op.gemm = make_gemm(max_batch_, H, W);
+      GemmOp& g = op.gemm;
+      g.nseg = 1; g.seg[0] = {p16.p, T, 0, T, 1};
+      g.w = vT.p; g.N = C; g.w_ld = T;
+      g.w_batch_stride = (long long)C * T; g.w_rows_per_batch = C;
+      g.rowscale = rowinv;
+      g.out16 = o16.p; g.ldo = C;
+      ops_.push_back(op);
+    }
+    rel(p16); rel(vT);
+    a_free(rowinv, (size_t)max_batch_ * T * 4);
   } else if (T <= 64) {
     Op op; op.kind = OP_SMALL_ATTN; op.tag = s.prefix + "attn_small";
     op.h_in = qkv.p; op.h_out = o16.p; op.T = T; op.cin = C; op.scale = sm_scale;
     ops_.push_back(op);
   } else {
-    err_ = "attention over " + std::to_string(T) + " tokens is not supported (16..64 or 256)";
+    err_ = "attention over " + std::to_string(T) + " tokens is not supported (16..64, 256 or a multiple of 256)";
     return T32{nullptr, 0, 0, 0, 0};
   }
   rel(qkv);
@@ -830,6 +872,10 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         break;
       case OP_TRANSPOSE_V:
         rc = transpose_v_launch(op.h_in, op.h_out, batch, op.T, op.cin, op.ld, op.voff, st);
+        launches_ += 1;
+        break;
+      case OP_SOFTMAX_ROWS:
+        rc = softmax_rows_launch(op.f_in, op.h_out, op.f_out, (long long)batch * op.T, op.T, st);
         launches_ += 1;
         break;
       case OP_SMALL_ATTN:

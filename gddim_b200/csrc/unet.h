@@ -19,7 +19,7 @@ struct ParamSpec {
   float scale;
 };
 
-enum OpKind { OP_STEM, OP_NORM, OP_GEMM, OP_HEAD, OP_IM2COL, OP_TRANSPOSE_V, OP_SMALL_ATTN };
+enum OpKind { OP_STEM, OP_NORM, OP_GEMM, OP_HEAD, OP_IM2COL, OP_TRANSPOSE_V, OP_SMALL_ATTN, OP_SOFTMAX_ROWS };
 
 struct Op {
   OpKind kind;

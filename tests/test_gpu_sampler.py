@@ -247,6 +247,29 @@ def test_image_size_64_celeba_like():
   assert rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
 
 
+def test_config5_256x256_sampler_narrow():
+  """BASELINE config 5 geometry (accr_dcifar10 with data.image_size=256, SURVEY 8d: 256/128/64/32 pyramid, one
+  1024-token attention) with deis_order=2, on a narrowed network (nf=64, 1 res-block) and NFE=4 so that the CPU
+  oracle finishes in well under a minute."""
+  from gddim_b200 import configs
+  from oracle import cld as oc
+  from oracle import ncsnpp as on
+  cfg = configs.cld_accr_dcifar10()
+  cfg.data.image_size, cfg.model.nf, cfg.model.num_res_blocks = 256, 64, 1
+  model = net.ScoreNet(cfg, cld=True)
+  p = model.init_params(seed=9, nondegenerate=True)
+  net_fn = on.make_net_fn(p, cfg)
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_deis_sampler(sde, model, (256, 256, 3), 4, inv, 2, ts_order=2, denoising=True)
+  u = oc.prior_sampling(np.random.default_rng(4), (1, 256, 256, 3)).astype(np.float32)
+  x, v, nfe = fn(0, model, 1, u=u)
+  assert nfe == 4 and x.shape == (1, 256, 256, 3)
+  o = oc.from_config(cfg)
+  ox, ov, _ = oc.deis_sampler(o, oc.make_eps_fn(o, net_fn), u, 4, 2, denoising=True, dtype=np.float32)
+  print(f"256x256: x {rel_l2(x, ox):.2e} v {rel_l2(v, ov):.2e}")
+  assert rel_l2(x, ox) < TOL_MIXED and rel_l2(v, ov) < TOL_MIXED
+
+
 def test_hybdeis_custom_time_grid_matches_oracle():
   """'hybdeis' (sampling.py:255-269) = the DEIS sampler on a two-part time grid, through get_sampling_fn.
   The reference grid restarts at sde.T, so T appears twice two steps apart: Lagrange nodes coincide for
