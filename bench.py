@@ -41,13 +41,20 @@ def parse():
   ap.add_argument("--order", type=int, default=2)
   ap.add_argument("--cpu-batch", type=int, default=0, help="images per CPU baseline sample (0 = auto)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--workload", default="cld", choices=["cld", "blur"],
+                  help="cld = BASELINE configs 2/4/5 (default: config 2); blur = config 3 (order-0 DDIM in DCT space)")
+  ap.add_argument("--image-size", type=int, default=32, help="256 = BASELINE config 5 geometry (use --batch 8)")
   ap.add_argument("--profile-csv", default="", help="write the per-op timing table of one profiled step here")
   return ap.parse_args()
 
 
-def make_cfg(name):
+def make_cfg(name, workload="cld", image_size=32):
   from gddim_b200 import configs
-  return configs.cld_accr_dcifar10() if name == "deep" else configs.cld_ddpmpp_cifar10()
+  if workload == "blur":
+    return configs.blur_ddpm_deep_cifar10(1.0)
+  cfg = configs.cld_accr_dcifar10() if name == "deep" else configs.cld_ddpmpp_cifar10()
+  cfg.data.image_size = image_size
+  return cfg
 
 
 class ClockSampler:
@@ -149,9 +156,15 @@ def run_ours(args):
   assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
   torch.cuda.set_device(local_rank)
   B, nfe, order = args.batch, args.nfe, args.order
-  cfg = make_cfg(args.net)
-  cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "deis", nfe, order
-  model = net.ScoreNet(cfg, cld=True)
+  blur, S = args.workload == "blur", args.image_size
+  default_workload = (not blur) and S == 32
+  cfg = make_cfg(args.net, args.workload, S)
+  if blur:
+    from gddim_b200.blur import sampling, sde_lib
+    cfg.sampling.method, cfg.sampling.nfe = "order0", nfe
+  else:
+    cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "deis", nfe, order
+  model = net.ScoreNet(cfg, cld=not blur)
   # parameters: generated on rank 0, one NCCL broadcast (run_lib.py:711 replicate)
   if rank == 0:
     params = model.init_params(seed=1234, nondegenerate=True)
@@ -167,9 +180,12 @@ def run_ours(args):
 
   # one global prior draw, sliced per rank (sampling.py:235)
   rng = np.random.default_rng(0)
-  shape = (world * B, 32, 32, 3)
-  u_glob = np.stack([rng.standard_normal(shape), rng.standard_normal(shape) / np.sqrt(cfg.model.m_inv)],
-                    axis=-1).astype(np.float32)          # x ~ N(0,1), v ~ N(0, 1/m_inv)  (sde_lib.py:270-274)
+  shape = (world * B, S, S, 3)
+  if blur:
+    u_glob = rng.standard_normal(shape).astype(np.float32)      # y ~ N(0, 1) in DCT space (blur sde_lib.py:128-130)
+  else:
+    u_glob = np.stack([rng.standard_normal(shape), rng.standard_normal(shape) / np.sqrt(cfg.model.m_inv)],
+                      axis=-1).astype(np.float32)        # x ~ N(0,1), v ~ N(0, 1/m_inv)  (sde_lib.py:270-274)
   u_host = np.ascontiguousarray(gdist.shard(u_glob, rank, world))
   u_pin = torch.from_numpy(u_host).pin_memory()
   u_dev = u_pin.cuda()
@@ -179,7 +195,7 @@ def run_ours(args):
     return core.run(model, B, u_dev)
 
   for _ in range(max(args.warmup, 3)):
-    x, v, _ = step_dev()
+    x = step_dev()[0]
   torch.cuda.synchronize()
 
   # ---- timed region: device-resident inputs -------------------------------------------------------------
@@ -192,7 +208,7 @@ def run_ours(args):
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record(stream)
   for _ in range(args.steps):
-    x, v, _ = step_dev()
+    x = step_dev()[0]
   e1.record(stream)
   torch.cuda.synchronize()
   gdist.barrier()
@@ -204,13 +220,13 @@ def run_ours(args):
 
   # ---- e2e: public API, host buffers (pinned), copies inside the timed region --------------------------------
   u_np = u_pin.numpy()[None]                       # (n_dev=1, B, 32, 32, 3, 2) view of pinned memory
-  xs, vs, _ = psampler(None, model, B, u=u_np)     # warm-up of the host path
+  outs = psampler(None, model, B, u=u_np)          # warm-up of the host path
   gdist.barrier()
   torch.cuda.synchronize()
   t0 = time.perf_counter()
   e0.record(stream)
   for _ in range(args.steps):
-    xs, vs, _ = psampler(None, model, B, u=u_np)
+    outs = psampler(None, model, B, u=u_np)
   e1.record(stream)
   torch.cuda.synchronize()
   wall = time.perf_counter() - t0
@@ -218,7 +234,7 @@ def run_ours(args):
   ms_e2e = gdist.max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
   e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
   h2d = u_host.nbytes
-  d2h = xs.nbytes + vs.nbytes
+  d2h = sum(o.nbytes for o in outs[:-1])           # (xs, vs) for CLD, (xs,) for blur; the last item is nfe
 
   # ---- roofline of the dominant kernel (conv_gemm_umma) from one profiled step ------------------------------
   roof = None
@@ -258,20 +274,31 @@ def run_ours(args):
     return
   # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ------------------------------
   cpu = None
-  if world == 1 and not args.no_cpu_baseline:
+  if world == 1 and not args.no_cpu_baseline and default_workload:
     threads = os.cpu_count() or 1
     cb = args.cpu_batch or 2
     v_cpu, dt = cpu_port_sample(cfg, model.params, cb, nfe, order, threads)
     cpu = {"value": v_cpu, "unit": "images/s", "cores": threads, "kind": "port",
            "sample": f"{cb} image(s) x {nfe} NFE, same net/sampler, torch-CPU fp32 restatement of the reference "
                      f"sampler ({dt:.1f} s); JAX/XLA itself is not installable offline"}
-  flop_img = GFLOP_PER_IMG_EVAL[args.net] * 1e9 * nfe
-  line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+  if default_workload or (blur and args.net == "deep"):
+    flop_img = (37.152 if blur else GFLOP_PER_IMG_EVAL[args.net]) * 1e9 * nfe
+  else:
+    # other geometries: 2*M*N*K of every GEMM launch of the profiled step (includes the 6-channel stem/head padding)
+    flop_img = (roof["flop_per_launch"] * roof["launches"] / B) if roof else 0.0
+  if blur:
+    wl = (f"Blur-diffusion CIFAR10 32x32, sigma_blur_max=1.0, batch={B}/GPU, NFE={nfe}, order0 (DDIM in DCT space), "
+          "net=ddpm_deep_cifar10 (deep NCSN++, 107.6M params)")
+    metric = f"CIFAR10 32x32 images/sec @ {nfe} NFE order0 (blur diffusion, deep NCSN++)"
+  else:
+    wl = (f"CLD {'CIFAR10 ' if S == 32 else ''}{S}x{S}, batch={B}/GPU, NFE={nfe}, deis_order={order}, "
+          f"net={'accr_dcifar10 (deep NCSN++, 107.6M params)' if args.net == 'deep' else 'ddpmpp_cifar10'}")
+    metric = METRIC if (S == 32 and order == 2 and nfe == 50 and args.net == "deep") else \
+        f"{S}x{S} images/sec @ {nfe} NFE deis_order={order} (CLD, {args.net})"
+  line = {"metric": metric, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
           "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
           "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/trunk", "data": "synthetic",
-          "config": {"workload": f"CLD CIFAR10 32x32, batch={B}/GPU, NFE={nfe}, deis_order={order}, "
-                                 f"net={'accr_dcifar10 (deep NCSN++, 107.6M params)' if args.net == 'deep' else 'ddpmpp_cifar10'}"
-                                 ", random-init (non-degenerate) weights, Gaussian prior",
+          "config": {"workload": wl + ", random-init (non-degenerate) weights, Gaussian prior",
                      "global_batch": world * B, "parallelism": f"dp{world} (batch-sharded, no per-step collective)",
                      "l2": f"working set >> L2: {model.workspace_bytes() / 2**30:.2f} GiB of activations+weights per evaluation"},
           "tensor_frac_end_to_end": value * flop_img / (world * 1e12 * (roof["peak"] if roof else 1400.0)),

@@ -123,35 +123,50 @@ __global__ void __launch_bounds__(1024) gn_stats_kernel(const StatsArgs p) {
 struct CoefArgs {
   const float* cs1; int c1;
   const float* cs2; int c2;
-  int P, groups;
+  int P, groups, gpc;      // gpc = groups handled by one CTA
   float inv_n, eps;
   const float* gamma; const float* beta;
   float* coef;
 };
 
-__global__ void __launch_bounds__(256) gn_coef_kernel(const CoefArgs p) {
-  extern __shared__ float sm[];   // [C][2] per-channel sum, sumsq over the image
+// grid (B, groups / gpc); block = lanes x nch threads (nch = gpc * channels-per-group).  Thread (lane, channel) adds
+// up every lanes-th 32-row slab of its channel, the lanes are folded in a fixed order: deterministic, and the
+// dependent chain is slabs / lanes long (2048 slabs per image at 256x256, hence up to 1024 threads).
+__global__ void __launch_bounds__(1024) gn_coef_kernel(const CoefArgs p) {
+  __shared__ float sm_s[1024], sm_q[1024];
   const int C = p.c1 + p.c2;
+  const int cpg = C / p.groups;
+  const int nch = p.gpc * cpg;
+  const int lanes = blockDim.x / nch;        // power of two
   const int b = blockIdx.x;
+  const int cl = threadIdx.x % nch, l = threadIdx.x / nch;
+  const int ch = blockIdx.y * nch + cl;
   const int slabs = p.P / 32;
-  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+  {
     const float* cs; int cc, cw;
     if (ch < p.c1) { cs = p.cs1; cc = ch; cw = p.c1; } else { cs = p.cs2; cc = ch - p.c1; cw = p.c2; }
+    const float* ps = cs + ((long long)b * slabs * 2) * cw + cc;
     float s = 0.f, q = 0.f;
-    for (int k = 0; k < slabs; ++k) {
-      const long long slab = (long long)b * slabs + k;
-      s += __ldg(cs + (slab * 2) * cw + cc);
-      q += __ldg(cs + (slab * 2 + 1) * cw + cc);
+#pragma unroll 4
+    for (int k = l; k < slabs; k += lanes) {
+      s += __ldg(ps + (long long)(2 * k) * cw);
+      q += __ldg(ps + (long long)(2 * k + 1) * cw);
     }
-    sm[ch * 2] = s;
-    sm[ch * 2 + 1] = q;
+    sm_s[threadIdx.x] = s;
+    sm_q[threadIdx.x] = q;
   }
   __syncthreads();
-  const int cpg = C / p.groups;
-  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
-    const int g = ch / cpg;
+  for (int off = lanes >> 1; off >= 1; off >>= 1) {       // fixed-shape tree: deterministic
+    if (l < off) {
+      sm_s[threadIdx.x] += sm_s[threadIdx.x + off * nch];
+      sm_q[threadIdx.x] += sm_q[threadIdx.x + off * nch];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < nch) {
+    const int g0 = (cl / cpg) * cpg;
     float ts = 0.f, tss = 0.f;
-    for (int k = g * cpg; k < (g + 1) * cpg; ++k) { ts += sm[k * 2]; tss += sm[k * 2 + 1]; }
+    for (int k = g0; k < g0 + cpg; ++k) { ts += sm_s[k]; tss += sm_q[k]; }
     const float mean = ts * p.inv_n;
     const float var = fmaxf(tss * p.inv_n - mean * mean, 0.f);
     const float a = rsqrtf(var + p.eps) * p.gamma[ch];
@@ -335,7 +350,18 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     c.P = P; c.groups = op->groups;
     c.inv_n = 1.0f / ((float)P * (float)(C / op->groups));
     c.eps = op->eps; c.gamma = op->gamma; c.beta = op->beta; c.coef = op->coef;
-    gn_coef_kernel<<<op->B, 256, 2 * C * sizeof(float), st>>>(c);
+    const int cpg = C / op->groups;
+    if (cpg > 256) return -2;
+    int gpc = 1;
+    while (gpc * 2 * cpg <= 32 && op->groups % (gpc * 2) == 0) gpc *= 2;
+    while (gpc > 1 && (long long)op->B * (op->groups / gpc) < 148 * 2) gpc >>= 1;     // small batches: more CTAs
+    c.gpc = gpc;
+    const int nch = gpc * cpg;
+    const int slabs = P / 32;
+    int lanes = 1;                                      // ~4 slabs per thread, at most 1024 threads
+    while (lanes * 2 * nch <= 1024 && lanes * 2 * 4 <= slabs) lanes *= 2;
+    dim3 cgrid(op->B, op->groups / gpc);
+    gn_coef_kernel<<<cgrid, lanes * nch, 0, st>>>(c);
   } else if (do_norm) {
     if (C % op->groups != 0) return -2;
     if (!op->partial || !op->coef || !op->ticket) return -5;
