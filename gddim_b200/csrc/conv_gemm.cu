@@ -32,13 +32,17 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                       // 64 fp16 = 128 bytes = one swizzle row
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;
 // Warp roles.  The scheduler prefers the highest warp id among eligible warps of a sub-partition, so the two
-// single-thread roles that must never wait for an issue slot get the highest ids: warps 0-3 epilogue (TMEM lane
-// quadrant = warp id), warp 4 TMA producer, warp 5 MMA issuer + TMEM owner.
-constexpr int PRODUCER_THREAD = 128;
-constexpr int MMA_WARP = 5;
-constexpr int MMA_THREAD = 160;
+// single-thread roles that must never wait for an issue slot get the highest ids: warps 0-7 epilogue (TMEM lane
+// quadrant = warp id & 3; the two groups of four take alternate 32-column chunks of every tile, so each scheduler
+// has two epilogue warps to hide TMEM / smem / store latency behind each other and a tile drains in half the
+// time), warp 8 TMA producer, warp 9 MMA issuer + TMEM owner.
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_GROUPS = 2;
+constexpr int PRODUCER_THREAD = 256;
+constexpr int MMA_WARP = 9;
+constexpr int MMA_THREAD = 288;
 
 struct GemmArgs {
   int taps[2], kch[2], coff[2];
@@ -67,20 +71,21 @@ template <int BLOCK_N, int MT>
 struct SmemLayout {
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = MT * A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int BAR_BYTES = 1024;
-  // epilogue staging: 4 warps x 32 rows x (32 + 4 pad) fp32 -- conflict-free 128-bit transposition
-  static constexpr int EPI_ROW_FLOATS = 36;
-  static constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_ROW_FLOATS * 4;
-  static constexpr int EPI_BYTES = EPI_STAGE_BYTES + 4 * BLOCK_N * 4;   // + per-warp (bias + bias2) row
-  static constexpr int AVAIL = SMEM_BUDGET - BAR_BYTES - EPI_BYTES - 1024;
+  static constexpr int BAR_BYTES = 256;
+  // epilogue staging: 8 warps x 32 rows x 32 fp32, XOR-swizzled in 16-byte units -- conflict-free 128-bit
+  // transposition without padding (the BLOCK_N = 256 layout has < 1 KB to spare next to four 48 KB stages)
+  static constexpr int EPI_ROW_FLOATS = 32;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_ROW_FLOATS * 4;
+  static constexpr int EPI_BYTES = EPI_STAGE_BYTES + 2 * BLOCK_N * 4;   // + double-buffered (bias + bias2) row
+  static constexpr int AVAIL = SMEM_BUDGET - BAR_BYTES - EPI_BYTES;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;   // +1024: alignment slack
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES;   // dynamic smem is declared 1024-aligned
 };
 
 
 // ---- linear epilogue --------------------------------------------------------------------------------------------
-// TMEM -> registers (thread = row) -> padded smem -> registers (8 lanes = one 32-column row segment), so that every
-// global access is a full 128-byte line.  One warp per scheduler runs this, so it is written for a low
+// TMEM -> registers (thread = row) -> swizzled smem -> registers (8 lanes = one 32-column row segment), so that
+// every global access is a full 128-byte line.  Two warps per scheduler run this, so it is written for a low
 // instruction count: the variant (residual / fp32 out / fp16 out / column statistics / row scale / full tile) is a
 // template parameter, and everything that does not depend on the accumulator (bias row, first residual chunk) is
 // fetched before waiting for the MMAs; the residual of chunk q+1 is in flight while chunk q is processed.
@@ -95,6 +100,7 @@ struct EpiCtx {
   long long m0;            // first row of this warp in sub-tile 0
   int n_tile0;             // first output column of the tile
   int lane;
+  int group;               // epilogue group: takes the 32-column chunks q = group, group + 2, ...
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
@@ -122,8 +128,12 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
   const int lane = cx.lane;
   const int rsub = lane >> 3;
   const int c4 = (lane & 7) * 4;
+  // staging rows are 128 bytes; the 16-byte unit u of row r lives at unit (u ^ (r & 7))
   const uint32_t stg_w = ptx::smem_u32(cx.stg) + lane * RS * 4;                 // this thread's row (write side)
-  const uint32_t stg_r = ptx::smem_u32(cx.stg) + (rsub * RS + c4) * 4;         // read side: row rsub (+4i), cols c4..
+  const uint32_t wx = lane & 7;
+  // read side: rows rsub + 4 i, unit lane & 7; (row & 7) alternates between rsub and rsub + 4 with the parity of i
+  const uint32_t stg_r0 = ptx::smem_u32(cx.stg) + rsub * RS * 4 + (((lane & 7) ^ rsub) << 4);
+  const uint32_t stg_r1 = ptx::smem_u32(cx.stg) + (rsub + 4) * RS * 4 + (((lane & 7) ^ (rsub + 4)) << 4);
   const uint32_t bias_a = ptx::smem_u32(cx.bias_s) + c4 * 4;
   const long long ldo = p.ldo;
   const float scale = p.scale;
@@ -137,22 +147,30 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
       else res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  float4 res[8], res_next[8];
-  if (RES) load_res(0, res);
+  float4 res[8];
+  if (RES && cx.group < NQ) load_res(cx.group, res);
   __syncwarp();
   ptx::mbar_wait(cx.tfull, cx.tfull_phase);
   ptx::tc_fence_after();
   uint32_t r[32];
   if (p.dbg == 3) return;
 #pragma unroll 1
-  for (int q = 0; q < NQ; ++q) {
+  for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
     const int mi = q / NCH, c0 = (q % NCH) * 32;
     ptx::tmem_ld_32x32b_x32(cx.taddr + mi * BLOCK_N + c0, r);
-    if (RES && q + 1 < NQ) load_res(q + 1, res_next);
+    // residual of this group's next chunk: each float4 is re-loaded in place right after it has been consumed
+    const bool res_more = RES && (q + EPI_GROUPS < NQ);
+    const float* res_nbase = nullptr;
+    long long res_nmb = 0;
+    if (res_more) {
+      const int qn = q + EPI_GROUPS;
+      res_nmb = cx.m0 + (long long)(qn / NCH) * BLOCK_M + rsub;
+      res_nbase = p.residual + res_nmb * ldo + cx.n_tile0 + (qn % NCH) * 32 + c4;
+    }
     ptx::tmem_ld_wait();
     if (p.dbg == 1) continue;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) sts128(stg_w + j * 4, r[j], r[j + 1], r[j + 2], r[j + 3]);
+    for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ wx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
     __syncwarp();
     const long long mb = cx.m0 + (long long)mi * BLOCK_M + rsub;                 // this lane's first row
     const int n0 = cx.n_tile0 + c0 + c4;
@@ -163,13 +181,19 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
     __half* o16 = O16 ? p.out16 + mb * ldo + n0 : nullptr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 v = lds128(stg_r + i * 4 * RS * 4);
+      float4 v = lds128(((i & 1) ? stg_r1 : stg_r0) + (i >> 1) * 8 * RS * 4);
       const bool ok = FULL || (mb + i * 4 < p.M);
       if (RSCALE) {
         const float rsc = ok ? __ldg(p.rowscale + mb + i * 4) : 1.0f;
         v.x *= rsc; v.y *= rsc; v.z *= rsc; v.w *= rsc;
       }
-      if (RES) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+      if (RES) {
+        v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
+        if (res_more) {
+          if (FULL || res_nmb + i * 4 < p.M) res[i] = __ldg(reinterpret_cast<const float4*>(res_nbase + (long long)(i * 4) * ldo));
+          else res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       v.x = fmaf(v.x, scale, bsum.x); v.y = fmaf(v.y, scale, bsum.y);
       v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
       if (ok && p.dbg != 2) {
@@ -211,10 +235,6 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
       }
     }
     __syncwarp();
-    if (RES) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) res[i] = res_next[i];
-    }
   }
 }
 
@@ -227,8 +247,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   constexpr uint32_t TMEM_COLS = (2 * MT * BLOCK_N) < 32 ? 32 : (2 * MT * BLOCK_N);   // 2 accumulator stages
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
+  if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * MT * A_TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
@@ -253,7 +273,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
-      ptx::mbar_init(&tempty_bar[s], 4);
+      ptx::mbar_init(&tempty_bar[s], EPI == EPI_SOFTMAX ? 4 : EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
@@ -334,13 +354,15 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       ptx::umma_commit(&tfull_bar[acc]);              // accumulator ready for the epilogue
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (warp < 4) {
+  } else if (warp < (EPI == EPI_SOFTMAX ? 4 : EPI_WARPS)) {
     // ================= epilogue =================
-    const int quad = warp;                        // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int group = warp >> 2;
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int bias_buf = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, bias_buf ^= 1) {
       const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
       const long long m = (long long)mt * MT * BLOCK_M + row;
       const bool valid = m < p.M;
@@ -353,8 +375,11 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         // hide latency behind (one warp per scheduler), so the overlap has to be explicit.
         constexpr int RS = L::EPI_ROW_FLOATS;
         float* stg = epi_stage + warp * 32 * RS;
-        float* bias_s = epi_bias + warp * BLOCK_N;
-        for (int j = lane * 4; j < BLOCK_N; j += 128) {
+        // one (bias + bias2) row per tile, filled by the 256 epilogue threads together; double-buffered so that a
+        // warp already on the next tile never overwrites the row a slower warp still reads (the barrier below keeps
+        // them within one tile of each other)
+        float* bias_s = epi_bias + bias_buf * BLOCK_N;
+        for (int j = threadIdx.x * 4; j < BLOCK_N; j += EPI_WARPS * 32 * 4) {
           float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias != nullptr) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + j));
@@ -366,11 +391,12 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           }
           *reinterpret_cast<float4*>(bias_s + j) = bsum;
         }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         const bool full = ((long long)(mt + 1) * MT * BLOCK_M <= (long long)p.M);
         const unsigned mode = (p.residual ? 1u : 0u) | (p.out32 ? 2u : 0u) | (p.out16 ? 4u : 0u) |
                               (p.colstats ? 8u : 0u) | (p.rowscale ? 16u : 0u);
         EpiCtx<BLOCK_N, MT> cx{p, stg, bias_s, &tfull_bar[acc], acc_phase, tmem_base + (uint32_t(quad * 32) << 16) + acc * MT * BLOCK_N,
-                               (long long)mt * MT * BLOCK_M + quad * 32, nt * BLOCK_N, lane};
+                               (long long)mt * MT * BLOCK_M + quad * 32, nt * BLOCK_N, lane, group};
         if (p.n_store > 0) epi_tile<BLOCK_N, MT, false, true, false, false, false, false, false, true>(cx);   // few-channel output
         else if (!full) epi_tile<BLOCK_N, MT, true, true, true, true, true, false, true>(cx);     // ragged last tile: generic path
         else if (mode == (2u | 8u)) epi_tile<BLOCK_N, MT, false, true, false, true, false, true, false>(cx);           // conv1, shortcut conv2, stem
