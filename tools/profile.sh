@@ -14,9 +14,9 @@ NG=$(grep -c conv_gemm_umma gpurun_out/launches.csv)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:conv_gemm_umma \
     -s $NG -c $NG --csv --log-file gpurun_out/gemm_traffic.csv python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:conv_gemm_umma_kernelILi256ELi0ELi1 \
-    -s $((NG + 40)) -c 3 -f -o gpurun_out/prof_gemm256 python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
+    -s 120 -c 6 -f -o gpurun_out/prof_gemm256 python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:conv_gemm_umma_kernelILi128ELi0ELi2 \
-    -s 40 -c 3 -f -o gpurun_out/prof_gemm128 python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
+    -s 45 -c 3 -f -o gpurun_out/prof_gemm128 python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:gn_apply_kernelILi0E \
     -s 160 -c 3 -f -o gpurun_out/prof_gn python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
 tail -3 gpurun_out/prof.log

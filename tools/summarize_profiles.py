@@ -20,7 +20,10 @@ KEEP = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "launch__waves_per_multiprocessor",
-        "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__ops_path_tensor_src_fp16_dst_fp32.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active"]
 
 
 def ncu_raw(rep):
@@ -31,7 +34,7 @@ def ncu_raw(rep):
   for r in rows[2:]:
     d = {}
     for i, h in enumerate(hdr):
-      if h in KEEP or ("tensor" in h and "pct" in h and ".avg." in h and "sparsity" not in h):
+      if h in KEEP:
         d[h] = f"{r[i]} {units[i]}".strip()
     out.append(d)
   return out
@@ -86,7 +89,7 @@ def main():
                  f"{(rd+wr)/max(n,1)/1e6:.1f} MB per launch; algorithmic minimum = operands + outputs (see DESIGN.md)\n")
     import shutil
     shutil.copy(p, os.path.join(OUT, f"{TAG}_gemm_traffic.csv"))
-  for rep, title in (("prof_gemm256.ncu-rep", "conv_gemm_umma_kernel<256,0,1> (3x3 conv 256->256 @16x16; ncu --set full)"),
+  for rep, title in (("prof_gemm256.ncu-rep", "conv_gemm_umma_kernel<256,0,1> (six consecutive N=256 launches of the 16x16 level: 3x3 convs and the K=256 attention GEMMs; ncu --set full)"),
                      ("prof_gemm128.ncu-rep", "conv_gemm_umma_kernel<128,0,2> (3x3 conv 128->128 @32x32, 256-row tiles; ncu --set full)"),
                      ("prof_gn.ncu-rep", "gn_apply_kernel (ncu --set full)")):
     p = os.path.join(SRC, rep)
