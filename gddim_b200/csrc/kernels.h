@@ -87,6 +87,7 @@ struct NormOp {
   float raw_scale;               // raw16 = x * raw_scale (power of two: headroom against fp16 overflow)
 };
 int norm_launch(const NormOp* op, cudaStream_t st);
+int norm_num_launches(const NormOp* op);   // kernels norm_launch issues for this op (1 or 2)
 int norm_splits(int B, int H, int W);
 
 // ---- small direct convolutions and data movement (small.cu) ---------------------------------------

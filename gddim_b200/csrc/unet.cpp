@@ -845,7 +845,7 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         NormOp n = op.norm;
         n.B = batch;
         rc = norm_launch(&n, st);
-        launches_ += n.dst16 ? 2 : 1;
+        launches_ += norm_num_launches(&n);
         break;
       }
       case OP_GEMM: {

@@ -120,7 +120,10 @@ def test_attention_chain(impl):
 
 NORM_CASES = [(2, 32, 32, 128, 0, 0), (2, 16, 16, 256, 128, 0), (2, 16, 16, 128, 64, 0), (3, 8, 8, 256, 0, 1),
               (3, 8, 8, 256, 0, 2), (2, 16, 16, 128, 0, 3), (2, 4, 4, 256, 0, 4), (5, 4, 4, 256, 256, 0),
-              (2, 32, 32, 64, 0, 1)]
+              (2, 32, 32, 64, 0, 1),
+              # single-kernel path for images of <= 64 pixels (8x8 / 4x4 levels), incl. concatenated sources
+              (3, 8, 8, 256, 0, 0), (2, 8, 8, 256, 256, 0), (3, 4, 4, 256, 0, 0), (2, 8, 8, 128, 0, 0), (2, 4, 4, 64, 64, 0),
+              (2, 8, 8, 192, 64, 0), (2, 2, 2, 256, 0, 0)]
 
 
 @pytest.mark.parametrize("case", NORM_CASES, ids=[f"b{c[0]}_{c[1]}_{c[3]}+{c[4]}_rs{c[5]}" for c in NORM_CASES])
