@@ -67,9 +67,11 @@ struct GemmArgs {
 
 // MT = number of 128-row M sub-tiles a CTA tile covers (2 for narrow N: the weight tile is then shared by 256
 // output rows, which halves the L2->smem operand traffic per FLOP of the N <= 128 layers)
-template <int BLOCK_N, int MT>
+// CG = CTAs cooperating on one MMA (cta_group): with CG = 2 a cluster of two CTAs computes 256 x BLOCK_N per MMA, each
+// CTA staging its own 128 A rows and HALF of the weight tile -- a third less L2->smem traffic on the N = 256 layers
+template <int BLOCK_N, int MT, int CG = 1>
 struct SmemLayout {
-  static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_TILE_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = MT * A_TILE_BYTES + B_TILE_BYTES;
   static constexpr int BAR_BYTES = 256;
   // epilogue staging: 8 warps x 32 rows x 32 fp32, XOR-swizzled in 16-byte units -- conflict-free 128-bit
@@ -238,11 +240,13 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
   }
 }
 
-template <int BLOCK_N, int EPI, int MT>
+template <int BLOCK_N, int EPI, int MT, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
-  using L = SmemLayout<BLOCK_N, MT>;
+  using L = SmemLayout<BLOCK_N, MT, CG>;
+  static_assert(CG == 1 || (EPI == EPI_LINEAR && (BLOCK_N / CG) % 16 == 0), "CTA pairs: linear epilogue only");
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // rank 0 = leader: issues the MMAs
   constexpr int STAGES = L::STAGES;
   constexpr uint32_t TMEM_COLS = (2 * MT * BLOCK_N) < 32 ? 32 : (2 * MT * BLOCK_N);   // 2 accumulator stages
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
@@ -268,33 +272,36 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     if (p.nseg > 1) ptx::prefetch_tmap(&tmA1);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&full_bar[s], CG);             // one arrive per producer of the pair (on the leader's barrier)
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
-      ptx::mbar_init(&tempty_bar[s], EPI == EPI_SOFTMAX ? 4 : EPI_WARPS);
+      ptx::mbar_init(&tempty_bar[s], (EPI == EPI_SOFTMAX ? 4 : EPI_WARPS) * CG);   // both CTAs' epilogues (leader's barrier)
     }
     ptx::fence_mbar_init();
   }
   if (warp == MMA_WARP) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (CG == 2) { ptx::tmem_alloc_2cta(tmem_slot, TMEM_COLS); ptx::tmem_relinquish_2cta(); }
+    else { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // work unit = CG vertically adjacent CTA tiles x one N tile; CTA `cta_rank` of the pair owns M tile unit_m * CG + rank
+  const int unit_m = (p.m_tiles + CG - 1) / CG;
+  const int num_tiles = unit_m * p.n_tiles;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   const int kblocks = p.taps[0] * p.kch[0] + (p.nseg > 1 ? p.taps[1] * p.kch[1] : 0);
 
   if (threadIdx.x == PRODUCER_THREAD) {
     // ================= TMA producer =================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
       int w0[MT], h0[MT], b0[MT];
 #pragma unroll
       for (int mi = 0; mi < MT; ++mi) {
@@ -312,26 +319,39 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           const int dx = (p.taps[s] == 9) ? tap % 3 - 1 : 0;
           for (int kc = 0; kc < p.kch[s]; ++kc, ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            if (CG == 1) {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
 #pragma unroll
-            for (int mi = 0; mi < MT; ++mi)
-              ptx::tma_load_4d(tm, &full_bar[stage], sA + (stage * MT + mi) * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K,
-                               w0[mi] + dx, h0[mi] + dy, b0[mi]);
-            ptx::tma_load_4d(&tmB, &full_bar[stage], sB + stage * L::B_TILE_BYTES, p.w_koff + kb * BLOCK_K,
-                             nt * BLOCK_N, bidx, 0);
+              for (int mi = 0; mi < MT; ++mi)
+                ptx::tma_load_4d(tm, &full_bar[stage], sA + (stage * MT + mi) * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K,
+                                 w0[mi] + dx, h0[mi] + dy, b0[mi]);
+              ptx::tma_load_4d(&tmB, &full_bar[stage], sB + stage * L::B_TILE_BYTES, p.w_koff + kb * BLOCK_K,
+                               nt * BLOCK_N, bidx, 0);
+            } else {
+              // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
+              const uint32_t fb = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+#pragma unroll
+              for (int mi = 0; mi < MT; ++mi)
+                ptx::tma_load_4d_2cta(tm, fb, sA + (stage * MT + mi) * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K,
+                                      w0[mi] + dx, h0[mi] + dy, b0[mi]);
+              ptx::tma_load_4d_2cta(&tmB, fb, sB + stage * L::B_TILE_BYTES, p.w_koff + kb * BLOCK_K,
+                                    nt * BLOCK_N + cta_rank * (BLOCK_N / CG), bidx, 0);
+              if (cta_rank != 0) ptx::mbar_arrive_cluster(fb);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (threadIdx.x == MMA_THREAD) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = ptx::umma_idesc_f16(BLOCK_M, BLOCK_N);
+  } else if (threadIdx.x == MMA_THREAD && cta_rank == 0) {
+    // ================= MMA issuer (leader CTA of a pair) =================
+    constexpr uint32_t idesc = ptx::umma_idesc_f16(BLOCK_M * CG, BLOCK_N);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * MT * BLOCK_N;
@@ -345,13 +365,16 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 fp16 = 32 bytes inside the swizzle row: +2 in the 16-byte-granular address field
-            ptx::umma_f16(d_tmem + mi * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 2) ptx::umma_f16_2cta(d_tmem + mi * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            else ptx::umma_f16(d_tmem + mi * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
         }
-        ptx::umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+        if (CG == 2) ptx::umma_commit_2cta(&empty_bar[stage], 3); else ptx::umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(&tfull_bar[acc]);              // accumulator ready for the epilogue
+      // accumulator ready for the epilogue (of both CTAs)
+      if (CG == 2) ptx::umma_commit_2cta(&tfull_bar[acc], 3); else ptx::umma_commit(&tfull_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp < (EPI == EPI_SOFTMAX ? 4 : EPI_WARPS)) {
@@ -362,8 +385,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     int bias_buf = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, bias_buf ^= 1) {
-      const int mt = tile / p.n_tiles, nt = tile % p.n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, bias_buf ^= 1) {
+      const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
       const long long m = (long long)mt * MT * BLOCK_M + row;
       const bool valid = m < p.M;
       uint32_t r[32];
@@ -451,16 +474,19 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty_bar[acc]), 0));   // the leader's barrier
+        else ptx::mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (CG == 2) ptx::cluster_sync(); else __syncthreads();     // pair: neither CTA may retire while its peer still works
   if (warp == MMA_WARP) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2) ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -645,7 +671,7 @@ static int encode_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], 
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub) {
+int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
   op->prepared = 0;
   op->m_sub = 1;
   const long long M = (long long)op->B * op->H * op->W;
@@ -705,6 +731,22 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub) {
     GEMM_FAIL("conv_gemm: 256-row tiles need block_n 64/128, shared weights and the linear epilogue");
   op->m_tiles = int((M + (long long)BLOCK_M * op->m_sub - 1) / ((long long)BLOCK_M * op->m_sub));
   op->n_tiles = op->N / bn;
+  // CTA pairs (cta_group::2) for the two work-horse shapes: shared weights, linear epilogue, enough tiles for 74 pairs
+  {
+    static int no_pairs = -1;               // GDDIM_NO_CTA_PAIRS=1: A/B timing switch, not a product option
+    if (no_pairs < 0) { const char* e = getenv("GDDIM_NO_CTA_PAIRS"); no_pairs = (e && e[0] == '1') ? 1 : 0; }
+    // measured (profiles/): +8..11 % on the K >= 1152, N = 256 layers with at least two waves of tiles; nothing on the
+    // 256-row N = 128 tiles (the weight tile is a third of their traffic) and a loss on K = 256 GEMMs and single-wave
+    // layers, which therefore stay on single-CTA MMAs
+    const bool shape_ok = bn == 256 && op->m_sub == 1 && ktot / BLOCK_K >= 16 && op->m_tiles >= 256;
+    const bool can_pair = bn == 256 && op->m_sub == 1 && op->epi == EPI_LINEAR && op->w_batch_stride == 0 && op->n_store == 0;
+    op->cg = (!no_pairs && shape_ok && can_pair) ? 2 : 1;
+    if (force_cg == 1) op->cg = 1;
+    if (force_cg == 2) {
+      if (!can_pair) GEMM_FAIL("conv_gemm: CTA pairs need block_n 256, 128-row tiles, shared weights and the linear epilogue");
+      op->cg = 2;
+    }
+  }
   op->tiles_per_batch = 0;
   if (op->w_batch_stride != 0) {
     const int hw = op->H * op->W;
@@ -730,18 +772,18 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub) {
       nb = op->B;
     }
     const uint64_t dims[4] = {(uint64_t)op->w_ld, rows, nb, 1};
-    const uint32_t box[4] = {BLOCK_K, (uint32_t)bn, 1, 1};
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)(bn / op->cg), 1, 1};      // a CTA of a pair stages half the weight tile
     if (encode_4d(&op->tmB, op->w, dims, box)) return -1;
   }
   op->prepared = 1;
   return 0;
 }
 
-template <int BN, int EPI, int MT>
+template <int BN, int EPI, int MT, int CG = 1>
 static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
-  using L = SmemLayout<BN, MT>;
+  using L = SmemLayout<BN, MT, CG>;
   static bool attr_set = false;
-  auto kern = conv_gemm_umma_kernel<BN, EPI, MT>;
+  auto kern = conv_gemm_umma_kernel<BN, EPI, MT, CG>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) GEMM_FAIL("cudaFuncSetAttribute(smem=%d): %s", L::TOTAL, cudaGetErrorString(e));
@@ -752,6 +794,19 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (CG == 2) {
+    const int units = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    const int pairs = units < num_sms / 2 ? units : num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, op->tmA[0], op->tmA[1], op->tmB, a);
+    if (e != cudaSuccess) GEMM_FAIL("conv_gemm_umma pair launch: %s", cudaGetErrorString(e));
+    return 0;
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
@@ -790,6 +845,10 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
       a.dbg = dbg;
     }
     if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX, 1>(op, a, st);
+    if (op->cg == 2) {
+      if (op->block_n == 256 && op->m_sub == 1) return launch_umma<256, EPI_LINEAR, 1, 2>(op, a, st);
+      GEMM_FAIL("conv_gemm: CTA pairs need block_n 256");
+    }
     if (op->m_sub == 2) {
       switch (op->block_n) {
         case 128: return launch_umma<128, EPI_LINEAR, 2>(op, a, st);

@@ -54,12 +54,13 @@ struct GemmOp {
   CUtensorMap tmB;
   int block_n;
   int m_sub;                // 128-row sub-tiles per CTA tile (1 or 2)
+  int cg;                   // CTAs per MMA (cta_group): 2 = cluster of two CTAs, each staging half the weight tile
   int m_tiles, n_tiles, tiles_per_batch;
   int prepared;
 };
 
 // Encodes the TMA descriptors (needs the final device addresses). Returns 0 or a negative error.
-int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub = 0);
+int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub = 0, int force_cg = 0);
 // impl: 0 = tcgen05/TMA kernel, 1 = CUDA-core reference kernel (validation only)
 int gemm_launch(const GemmOp* op, int impl, cudaStream_t st);
 const char* gemm_last_error();

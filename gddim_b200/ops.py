@@ -31,7 +31,7 @@ def pack_conv_weight(kernel_hwio, extra_1x1=None):
 
 
 def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residual=None, rowscale=None, scale=1.0,
-              out_fp32=True, out_fp16=False, impl=0, force_block_n=0, force_m_sub=0, epi=0, n_store=0, a0_coff=0, a0_c=None, w_ld=None,
+              out_fp32=True, out_fp16=False, impl=0, force_block_n=0, force_m_sub=0, force_cta_pairs=0, epi=0, n_store=0, a0_coff=0, a0_c=None, w_ld=None,
               w_koff=0, w_batch_stride=0, w_rows_per_batch=0):
   """a0 (and a1): fp16 [B,H,W,C]; w: fp16 K-major.  Returns (out32 or None, out16 or None[, row_out])."""
   import torch
@@ -53,6 +53,7 @@ def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residu
   d.out32, d.out16, d.row_out, d.ldo = _ptr(o32), _ptr(o16), _ptr(row), No
   d.n_store = n_store
   d.epi, d.impl, d.force_block_n, d.force_m_sub = epi, impl, force_block_n, force_m_sub
+  d.force_cta_pairs = force_cta_pairs
   st = torch.cuda.current_stream().cuda_stream
   _lib.check(_lib.lib().gddim_conv_gemm(C.byref(d), st), "gddim_conv_gemm")
   if epi == 1:

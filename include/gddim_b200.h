@@ -145,6 +145,7 @@ typedef struct {
   int force_block_n;                                        /* 0 = heuristic */
   int force_m_sub;                                          /* with force_block_n: 2 = 256-row CTA tiles */
   int n_store;                                              /* 0 = all N; else store only columns < n_store (fp32) */
+  int force_cta_pairs;                                      /* 0 = heuristic, 1 = single-CTA MMA, 2 = cta_group::2 pairs (block_n 256) */
 } gddim_gemm_desc;
 int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream);
 

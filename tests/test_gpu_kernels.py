@@ -94,6 +94,34 @@ def test_umma_256_row_tiles(bn, B):
   assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("B", [2, 3, 9])
+@pytest.mark.parametrize("two_seg", [False, True])
+def test_umma_cta_pairs(B, two_seg):
+  """cta_group::2: a cluster of two CTAs issues M = 256 MMAs, each CTA staging its own 128 rows and half of the
+  weight tile.  Odd B leaves the follower CTA of the last pair without rows (fully out-of-range tile); B = 9 gives
+  more pair tiles than one wave on small grids.  The heuristic only picks pairs for large layers, so force them."""
+  g = torch.Generator().manual_seed(90 + B + int(two_seg))
+  a = torch.randn(B, 8, 16, 128, generator=g).to(torch.float16)       # M = B*128 -> B CTA tiles
+  k = (torch.randn(3, 3, 128, 256, generator=g) / np.sqrt(9 * 128)).numpy()
+  a1 = torch.randn(B, 8, 16, 64, generator=g).to(torch.float16) if two_seg else None
+  k1 = (torch.randn(1, 1, 64, 256, generator=g) / 8).numpy() if two_seg else None
+  res = torch.randn(B, 8, 16, 256, generator=g)
+  bias = torch.randn(256, generator=g)
+  want = _conv_ref(a, k, 9)
+  if two_seg:
+    want = want + _conv_ref(a1, k1, 1)
+  want = (want + bias.double() + res.double()) * 0.5
+  o32, o16 = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k, k1), 256, taps0=9, a1=None if a1 is None else a1.cuda(),
+                           bias=bias.cuda(), residual=res.cuda(), scale=0.5, out_fp16=True, impl=0, force_block_n=256,
+                           force_cta_pairs=2)
+  assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
+  assert rel_l2(o16.float().cpu().numpy(), want.numpy()) < 1e-3
+  single, _ = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k, k1), 256, taps0=9, a1=None if a1 is None else a1.cuda(),
+                            bias=bias.cuda(), residual=res.cuda(), scale=0.5, impl=0, force_block_n=256,
+                            force_cta_pairs=1)
+  assert torch.equal(single, o32)          # same MMA order per output element: bit-identical to the single-CTA path
+
+
 @pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
 def test_attention_chain(impl):
   """qk^T -> row softmax epilogue -> P V with per-image B operands == softmax(q k^T / sqrt(C)) v."""
