@@ -795,9 +795,15 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  int num_sms_eff = num_sms;
+  {
+    static int cap = -1;                      // GDDIM_GEMM_MAX_CTAS: SM-partitioning experiments only
+    if (cap < 0) { const char* e = getenv("GDDIM_GEMM_MAX_CTAS"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && cap < num_sms) num_sms_eff = cap & ~1;
+  }
   if (CG == 2) {
     const int units = ((a.m_tiles + 1) / 2) * a.n_tiles;
-    const int pairs = units < num_sms / 2 ? units : num_sms / 2;
+    const int pairs = units < num_sms_eff / 2 ? units : num_sms_eff / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -809,7 +815,7 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
     return 0;
   }
   const int tiles = a.m_tiles * a.n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int grid = tiles < num_sms_eff ? tiles : num_sms_eff;
   kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(op->tmA[0], op->tmA[1], op->tmB, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) GEMM_FAIL("conv_gemm_umma launch: %s", cudaGetErrorString(e));

@@ -4,7 +4,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 from gddim_b200 import configs, net
 from gddim_b200.cld import sampling, sde_lib
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256  # total images over all streams
 NS = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 cfg = configs.cld_accr_dcifar10(); cfg.sampling.nfe, cfg.sampling.deis_order = 50, 2
 sde = sde_lib.from_config(cfg)
