@@ -62,6 +62,7 @@ struct GemmArgs {
   int ldo;
   int n_store;
   float* colstats;
+  int stages, stage_bytes, a_bytes;   // HALO kernels: smem ring geometry (depends on W)
   int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };
 
@@ -240,29 +241,35 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
   }
 }
 
-template <int BLOCK_N, int EPI, int MT, int CG>
+// HALO (3x3 convolutions whose CTA tile is a block of whole image rows): one TMA box of (tile rows + 2) image rows is
+// loaded per x-shift and channel block, and the three y-shifted operands are just descriptor start addresses W rows
+// apart inside it -- the A operand crosses L2->smem three times per tile instead of nine.
+template <int BLOCK_N, int EPI, int MT, int CG, bool HALO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                      const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmH, const GemmArgs p) {
   using L = SmemLayout<BLOCK_N, MT, CG>;
   static_assert(CG == 1 || (EPI == EPI_LINEAR && (BLOCK_N / CG) % 16 == 0), "CTA pairs: linear epilogue only");
+  static_assert(!HALO || EPI == EPI_LINEAR, "halo tiles: linear epilogue only");
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // rank 0 = leader: issues the MMAs
-  constexpr int STAGES = L::STAGES;
+  constexpr int MAX_STAGES = 8;
+  const int STAGES = HALO ? p.stages : L::STAGES;
+  const int stage_bytes = HALO ? p.stage_bytes : L::STAGE_BYTES;
+  const int a_bytes = HALO ? p.a_bytes : MT * A_TILE_BYTES;            // then up to three weight tiles
   constexpr uint32_t TMEM_COLS = (2 * MT * BLOCK_N) < 32 ? 32 : (2 * MT * BLOCK_N);   // 2 accumulator stages
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns must be a power of two <= 512");
 
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
   if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * MT * A_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
-  uint64_t* full_bar = bars;                      // [STAGES]  TMA -> MMA
-  uint64_t* empty_bar = bars + STAGES;            // [STAGES]  MMA -> TMA
-  uint64_t* tfull_bar = bars + 2 * STAGES;        // [2]       MMA -> epilogue
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;   // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES);
-  float* epi_bias = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES + L::EPI_STAGE_BYTES);
+  // ring slot s: [A operand (a_bytes)] [weight tile(s)]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* full_bar = bars;                          // [STAGES]  TMA -> MMA
+  uint64_t* empty_bar = bars + MAX_STAGES;            // [STAGES]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;        // [2]       MMA -> epilogue
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;   // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * stage_bytes + L::BAR_BYTES);
+  float* epi_bias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + L::BAR_BYTES + L::EPI_STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -271,6 +278,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     ptx::prefetch_tmap(&tmA0);
     if (p.nseg > 1) ptx::prefetch_tmap(&tmA1);
     ptx::prefetch_tmap(&tmB);
+    if (HALO) ptx::prefetch_tmap(&tmH);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], CG);             // one arrive per producer of the pair (on the leader's barrier)
       ptx::mbar_init(&empty_bar[s], 1);
@@ -294,12 +302,22 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   const int unit_m = (p.m_tiles + CG - 1) / CG;
   const int num_tiles = unit_m * p.n_tiles;
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
-  const int kblocks = p.taps[0] * p.kch[0] + (p.nseg > 1 ? p.taps[1] * p.kch[1] : 0);
 
   if (threadIdx.x == PRODUCER_THREAD) {
     // ================= TMA producer =================
     int stage = 0;
     uint32_t phase = 0;
+    // both CTAs of a pair complete their loads on the LEADER's barrier, which expects the bytes of the whole pair
+    auto arm = [&](int st, uint32_t bytes) -> uint32_t {
+      if (CG == 1) { ptx::mbar_arrive_expect_tx(&full_bar[st], bytes); return ptx::smem_u32(&full_bar[st]); }
+      const uint32_t fb = ptx::mapa(ptx::smem_u32(&full_bar[st]), 0);
+      if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[st], 2 * bytes);
+      return fb;
+    };
+    auto load = [&](const CUtensorMap* tm, uint32_t fb, uint64_t* own_bar, void* dst, int c0, int c1, int c2, int c3) {
+      if (CG == 1) ptx::tma_load_4d(tm, own_bar, dst, c0, c1, c2, c3);
+      else ptx::tma_load_4d_2cta(tm, fb, dst, c0, c1, c2, c3);
+    };
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
       int w0[MT], h0[MT], b0[MT];
@@ -311,34 +329,43 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         b0[mi] = p0 / (p.W * p.H);
       }
       const int bidx = p.tiles_per_batch > 0 ? mt / p.tiles_per_batch : 0;
+      const int nrow0 = nt * BLOCK_N + cta_rank * (BLOCK_N / CG);
       int kb = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const CUtensorMap* tm = (s == 0) ? &tmA0 : &tmA1;
+        if (HALO && p.taps[s] == 9) {
+          // ring slot = one x-shift of one 64-channel block: halo box + the three weight tiles of its y-shifts
+          const int cseg = p.kch[s] * BLOCK_K;
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            for (int kc = 0; kc < p.kch[s]; ++kc) {
+              uint8_t* slot = smem + stage * stage_bytes;
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              const uint32_t fb = arm(stage, (uint32_t)(a_bytes + 3 * L::B_TILE_BYTES));
+              load(&tmH, fb, &full_bar[stage], slot, p.coff[s] + kc * BLOCK_K, dxi - 1, h0[0] - 1, b0[0]);
+#pragma unroll
+              for (int dyi = 0; dyi < 3; ++dyi)
+                load(&tmB, fb, &full_bar[stage], slot + a_bytes + dyi * L::B_TILE_BYTES,
+                     p.w_koff + kb * BLOCK_K + (dyi * 3 + dxi) * cseg + kc * BLOCK_K, nrow0, bidx, 0);
+              if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_cluster(fb);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          kb += 9 * p.kch[s];
+          continue;
+        }
         for (int tap = 0; tap < p.taps[s]; ++tap) {
           const int dy = (p.taps[s] == 9) ? tap / 3 - 1 : 0;
           const int dx = (p.taps[s] == 9) ? tap % 3 - 1 : 0;
           for (int kc = 0; kc < p.kch[s]; ++kc, ++kb) {
+            uint8_t* slot = smem + stage * stage_bytes;
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (CG == 1) {
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            const uint32_t fb = arm(stage, (uint32_t)(MT * A_TILE_BYTES + L::B_TILE_BYTES));
 #pragma unroll
-              for (int mi = 0; mi < MT; ++mi)
-                ptx::tma_load_4d(tm, &full_bar[stage], sA + (stage * MT + mi) * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K,
-                                 w0[mi] + dx, h0[mi] + dy, b0[mi]);
-              ptx::tma_load_4d(&tmB, &full_bar[stage], sB + stage * L::B_TILE_BYTES, p.w_koff + kb * BLOCK_K,
-                               nt * BLOCK_N, bidx, 0);
-            } else {
-              // both CTAs' loads complete on the LEADER's barrier, which expects the bytes of the whole pair
-              const uint32_t fb = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
-              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-#pragma unroll
-              for (int mi = 0; mi < MT; ++mi)
-                ptx::tma_load_4d_2cta(tm, fb, sA + (stage * MT + mi) * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K,
-                                      w0[mi] + dx, h0[mi] + dy, b0[mi]);
-              ptx::tma_load_4d_2cta(&tmB, fb, sB + stage * L::B_TILE_BYTES, p.w_koff + kb * BLOCK_K,
-                                    nt * BLOCK_N + cta_rank * (BLOCK_N / CG), bidx, 0);
-              if (cta_rank != 0) ptx::mbar_arrive_cluster(fb);
-            }
+            for (int mi = 0; mi < MT; ++mi)
+              load(tm, fb, &full_bar[stage], slot + mi * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K, w0[mi] + dx, h0[mi] + dy,
+                   b0[mi]);
+            load(&tmB, fb, &full_bar[stage], slot + a_bytes, p.w_koff + kb * BLOCK_K, nrow0, bidx, 0);
+            if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_cluster(fb);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -355,23 +382,42 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * MT * BLOCK_N;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
-        ptx::tc_fence_after();
-        const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sB + stage * L::B_TILE_BYTES));
+      uint32_t accum = 0;                             // 0 for the first MMA of every accumulator of the tile
+      auto issue = [&](uint32_t a_addr, uint32_t b_addr, uint32_t acc_flag) {
+        const uint64_t b_desc = ptx::umma_desc_sw128(b_addr);
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
-          const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sA + (stage * MT + mi) * A_TILE_BYTES));
+          const uint64_t a_desc = ptx::umma_desc_sw128(a_addr + mi * A_TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             // advance 16 fp16 = 32 bytes inside the swizzle row: +2 in the 16-byte-granular address field
-            if (CG == 2) ptx::umma_f16_2cta(d_tmem + mi * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-            else ptx::umma_f16(d_tmem + mi * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            if (CG == 2) ptx::umma_f16_2cta(d_tmem + mi * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, acc_flag | k);
+            else ptx::umma_f16(d_tmem + mi * BLOCK_N, a_desc + 2 * k, b_desc + 2 * k, idesc, acc_flag | k);
           }
         }
-        // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-        if (CG == 2) ptx::umma_commit_2cta(&empty_bar[stage], 3); else ptx::umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      };
+      for (int s = 0; s < p.nseg; ++s) {
+        const bool halo_seg = HALO && p.taps[s] == 9;
+        const int slots = halo_seg ? 3 * p.kch[s] : p.taps[s] * p.kch[s];
+        for (int g = 0; g < slots; ++g) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t slot = ptx::smem_u32(smem + stage * stage_bytes);
+          if (halo_seg) {
+            // y-shift dyi = rows [dyi * W, dyi * W + 128 * MT) of the halo box
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              issue(slot + dyi * p.W * 128, slot + a_bytes + dyi * L::B_TILE_BYTES, accum);
+              accum = 1;
+            }
+          } else {
+            issue(slot, slot + a_bytes, accum);
+            accum = 1;
+          }
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if (CG == 2) ptx::umma_commit_2cta(&empty_bar[stage], 3); else ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
       // accumulator ready for the epilogue (of both CTAs)
       if (CG == 2) ptx::umma_commit_2cta(&tfull_bar[acc], 3); else ptx::umma_commit(&tfull_bar[acc]);
@@ -731,21 +777,45 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     GEMM_FAIL("conv_gemm: 256-row tiles need block_n 64/128, shared weights and the linear epilogue");
   op->m_tiles = int((M + (long long)BLOCK_M * op->m_sub - 1) / ((long long)BLOCK_M * op->m_sub));
   op->n_tiles = op->N / bn;
-  // CTA pairs (cta_group::2) for the two work-horse shapes: shared weights, linear epilogue, enough tiles for 74 pairs
+  // ---- CTA pairs (cta_group::2) and halo tiles ------------------------------------------------------------------
   {
-    static int no_pairs = -1;               // GDDIM_NO_CTA_PAIRS=1: A/B timing switch, not a product option
+    static int no_pairs = -1, no_halo = -1, halo128_cg = -1;   // A/B timing switches, not product options
     if (no_pairs < 0) { const char* e = getenv("GDDIM_NO_CTA_PAIRS"); no_pairs = (e && e[0] == '1') ? 1 : 0; }
-    // measured (profiles/): +8..11 % on the K >= 1152, N = 256 layers with at least two waves of tiles; nothing on the
-    // 256-row N = 128 tiles (the weight tile is a third of their traffic) and a loss on K = 256 GEMMs and single-wave
-    // layers, which therefore stay on single-CTA MMAs
-    const bool shape_ok = bn == 256 && op->m_sub == 1 && ktot / BLOCK_K >= 16 && op->m_tiles >= 256;
-    const bool can_pair = bn == 256 && op->m_sub == 1 && op->epi == EPI_LINEAR && op->w_batch_stride == 0 && op->n_store == 0;
+    if (no_halo < 0) { const char* e = getenv("GDDIM_NO_HALO"); no_halo = (e && e[0] == '1') ? 1 : 0; }
+    if (halo128_cg < 0) { const char* e = getenv("GDDIM_HALO128_CG"); halo128_cg = e ? atoi(e) : 2; }
+    static int halo256 = -1;               // GDDIM_HALO256=1: halo tiles for N = 256 too (measured slower: two ring slots)
+    if (halo256 < 0) { const char* e = getenv("GDDIM_HALO256"); halo256 = (e && e[0] == '1') ? 1 : 0; }
+    const bool plain = op->epi == EPI_LINEAR && op->w_batch_stride == 0 && op->n_store == 0;
+    const bool can_pair = plain && bn == 256 && op->m_sub == 1;
+    // halo tiles: 3x3 convolution whose CTA tile is a block of whole image rows of ONE image
+    const int tile_px = BLOCK_M * op->m_sub;
+    // (measured: 256-row N = 128 tiles 1.06 -> 1.29 PFLOP/s; N = 256 tiles lose, their ring shrinks to two slots)
+    const bool halo_ok = !no_halo && plain && ((bn == 128 && op->m_sub == 2) || (bn == 256 && op->m_sub == 1 && halo256)) &&
+                         op->seg[0].taps == 9 && (op->nseg == 1 || op->seg[1].taps == 1) && op->W >= 16 && op->W <= 128 &&
+                         tile_px % op->W == 0 && op->H % (tile_px / op->W) == 0;
+    // pairs, measured (profiles/): +8..11 % on the K >= 1152, N = 256 layers with at least two waves of tiles, a loss on
+    // K = 256 GEMMs and single-wave layers, which therefore stay on single-CTA MMAs
+    const bool shape_ok = ktot / BLOCK_K >= 16 && op->m_tiles >= 256;
     op->cg = (!no_pairs && shape_ok && can_pair) ? 2 : 1;
+    if (halo_ok && bn == 256 && op->m_tiles >= 2 && !no_pairs) op->cg = 2;   // three 32 KB weight tiles per slot do not fit
+    if (halo_ok && bn == 128 && op->m_tiles >= 2 && !no_pairs) op->cg = halo128_cg == 2 ? 2 : 1;
     if (force_cg == 1) op->cg = 1;
     if (force_cg == 2) {
-      if (!can_pair) GEMM_FAIL("conv_gemm: CTA pairs need block_n 256, 128-row tiles, shared weights and the linear epilogue");
+      if (!can_pair && !halo_ok) GEMM_FAIL("conv_gemm: CTA pairs need block_n 256 (or halo tiles), shared weights, linear epilogue");
       op->cg = 2;
     }
+    op->halo = 0;
+    if (halo_ok && !(bn == 256 && op->cg == 1)) {
+      using L0 = SmemLayout<32, 1, 1>;      // BAR / epilogue staging sizes do not depend on the tile shape ...
+      const int epi_bytes = L0::EPI_STAGE_BYTES + 2 * bn * 4;                 // ... except for the bias rows
+      const int b_tile = (bn / op->cg) * BLOCK_K * 2;
+      op->a_bytes = (tile_px + 2 * op->W) * BLOCK_K * 2;
+      op->stage_bytes = op->a_bytes + 3 * b_tile;
+      int st = (SMEM_BUDGET - L0::BAR_BYTES - epi_bytes) / op->stage_bytes;
+      if (st > 8) st = 8;
+      if (st >= 2) { op->halo = 1; op->stages = st; }
+    }
+    if (op->cg == 2 && !op->halo && !can_pair) op->cg = 1;
   }
   op->tiles_per_batch = 0;
   if (op->w_batch_stride != 0) {
@@ -764,6 +834,13 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     if (encode_4d(&op->tmA[s], g.ptr, dims, box)) return -1;
   }
   if (op->nseg == 1) op->tmA[1] = op->tmA[0];
+  op->tmH = op->tmA[0];
+  if (op->halo) {
+    const GemmSeg& g = op->seg[0];
+    const uint64_t dims[4] = {(uint64_t)g.c_total, (uint64_t)op->W, (uint64_t)op->H, (uint64_t)op->B};
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)op->W, (uint32_t)(BLOCK_M * op->m_sub / op->W + 2), 1};
+    if (encode_4d(&op->tmH, g.ptr, dims, box)) return -1;
+  }
   {
     uint64_t nb = 1, rows = op->N;
     if (op->w_batch_stride != 0) {
@@ -779,13 +856,14 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
   return 0;
 }
 
-template <int BN, int EPI, int MT, int CG = 1>
+template <int BN, int EPI, int MT, int CG = 1, bool HALO = false>
 static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
   using L = SmemLayout<BN, MT, CG>;
   static bool attr_set = false;
-  auto kern = conv_gemm_umma_kernel<BN, EPI, MT, CG>;
+  auto kern = conv_gemm_umma_kernel<BN, EPI, MT, CG, HALO>;
+  const int smem_total = HALO ? op->stages * op->stage_bytes + L::BAR_BYTES + L::EPI_BYTES : L::TOTAL;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO ? SMEM_BUDGET : L::TOTAL);
     if (e != cudaSuccess) GEMM_FAIL("cudaFuncSetAttribute(smem=%d): %s", L::TOTAL, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -805,18 +883,18 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
     const int units = ((a.m_tiles + 1) / 2) * a.n_tiles;
     const int pairs = units < num_sms_eff / 2 ? units : num_sms_eff / 2;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem_total; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, op->tmA[0], op->tmA[1], op->tmB, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, op->tmA[0], op->tmA[1], op->tmB, op->tmH, a);
     if (e != cudaSuccess) GEMM_FAIL("conv_gemm_umma pair launch: %s", cudaGetErrorString(e));
     return 0;
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms_eff ? tiles : num_sms_eff;
-  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(op->tmA[0], op->tmA[1], op->tmB, a);
+  kern<<<grid, NUM_THREADS, smem_total, st>>>(op->tmA[0], op->tmA[1], op->tmB, op->tmH, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) GEMM_FAIL("conv_gemm_umma launch: %s", cudaGetErrorString(e));
   return 0;
@@ -851,6 +929,13 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
       a.dbg = dbg;
     }
     if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX, 1>(op, a, st);
+    a.stages = op->stages; a.stage_bytes = op->stage_bytes; a.a_bytes = op->a_bytes;
+    if (op->halo) {
+      if (op->block_n == 256 && op->m_sub == 1 && op->cg == 2) return launch_umma<256, EPI_LINEAR, 1, 2, true>(op, a, st);
+      if (op->block_n == 128 && op->m_sub == 2 && op->cg == 1) return launch_umma<128, EPI_LINEAR, 2, 1, true>(op, a, st);
+      if (op->block_n == 128 && op->m_sub == 2 && op->cg == 2) return launch_umma<128, EPI_LINEAR, 2, 2, true>(op, a, st);
+      GEMM_FAIL("conv_gemm: no halo kernel for block_n %d, m_sub %d, cg %d", op->block_n, op->m_sub, op->cg);
+    }
     if (op->cg == 2) {
       if (op->block_n == 256 && op->m_sub == 1) return launch_umma<256, EPI_LINEAR, 1, 2>(op, a, st);
       GEMM_FAIL("conv_gemm: CTA pairs need block_n 256");

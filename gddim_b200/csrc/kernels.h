@@ -55,6 +55,9 @@ struct GemmOp {
   int block_n;
   int m_sub;                // 128-row sub-tiles per CTA tile (1 or 2)
   int cg;                   // CTAs per MMA (cta_group): 2 = cluster of two CTAs, each staging half the weight tile
+  int halo;                 // 3x3 conv with halo tiles: one (rows + 2)-row box per x-shift, y-shifts by descriptor offset
+  int stages, stage_bytes, a_bytes;   // halo: smem ring geometry
+  CUtensorMap tmH;          // halo box of segment 0
   int m_tiles, n_tiles, tiles_per_batch;
   int prepared;
 };

@@ -119,7 +119,39 @@ def test_umma_cta_pairs(B, two_seg):
   single, _ = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k, k1), 256, taps0=9, a1=None if a1 is None else a1.cuda(),
                             bias=bias.cuda(), residual=res.cuda(), scale=0.5, impl=0, force_block_n=256,
                             force_cta_pairs=1)
-  assert torch.equal(single, o32)          # same MMA order per output element: bit-identical to the single-CTA path
+  # same operands, fp32 accumulation; only the order of the taps differs (the pair path uses halo tiles here)
+  assert rel_l2(single.cpu().numpy(), o32.cpu().numpy()) < 1e-6
+
+
+HALO_CASES = [  # B, H, W, Cin, Cout, C1 (1x1 shortcut segment), block_n, m_sub, pairs
+    (2, 32, 32, 128, 128, 0, 128, 2, 1), (3, 32, 32, 128, 128, 256, 128, 2, 1), (3, 32, 32, 128, 128, 0, 128, 2, 2),
+    (2, 16, 16, 256, 256, 0, 256, 1, 2), (3, 16, 16, 256, 256, 128, 256, 1, 2), (1, 32, 32, 64, 256, 0, 256, 1, 2),
+    (2, 64, 64, 64, 128, 0, 128, 2, 1), (1, 16, 16, 128, 256, 0, 256, 1, 2)]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[f"b{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}+{c[5]}_bn{c[6]}x{c[7]}_cg{c[8]}" for c in HALO_CASES])
+def test_umma_halo_tiles(case):
+  """3x3 convolutions whose CTA tile is a block of whole image rows: one (rows + 2)-row TMA box per x-shift, the three
+  y-shifts are descriptor offsets into it (incl. CTA pairs, a 1x1 shortcut segment, odd tile counts, image borders)."""
+  B, H, W, Cin, Cout, C1, bn, ms, cg = case
+  g = torch.Generator().manual_seed(sum(case))
+  a = torch.randn(B, H, W, Cin, generator=g).to(torch.float16)
+  k = (torch.randn(3, 3, Cin, Cout, generator=g) / np.sqrt(9 * Cin)).numpy()
+  a1 = torch.randn(B, H, W, C1, generator=g).to(torch.float16) if C1 else None
+  k1 = (torch.randn(1, 1, C1, Cout, generator=g) / np.sqrt(C1)).numpy() if C1 else None
+  res = torch.randn(B, H, W, Cout, generator=g)
+  bias = torch.randn(Cout, generator=g)
+  want = _conv_ref(a, k, 9)
+  if C1:
+    want = want + _conv_ref(a1, k1, 1)
+  want = (want + bias.double() + res.double()) * 0.5
+  o32, o16 = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k, k1), Cout, taps0=9, a1=None if a1 is None else a1.cuda(),
+                           bias=bias.cuda(), residual=res.cuda(), scale=0.5, out_fp16=True, impl=0, force_block_n=bn,
+                           force_m_sub=ms, force_cta_pairs=cg)
+  e = rel_l2(o32.cpu().numpy(), want.numpy())
+  print(f"halo {case}: {e:.2e}")
+  assert e < 2e-5
+  assert rel_l2(o16.float().cpu().numpy(), want.numpy()) < 1e-3
 
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
