@@ -89,8 +89,8 @@ def main():
                  f"{(rd+wr)/max(n,1)/1e6:.1f} MB per launch; algorithmic minimum = operands + outputs (see DESIGN.md)\n")
     import shutil
     shutil.copy(p, os.path.join(OUT, f"{TAG}_gemm_traffic.csv"))
-  for rep, title in (("prof_gemm256.ncu-rep", "conv_gemm_umma_kernel<256,0,1> (six consecutive N=256 launches of the 16x16 level: 3x3 convs and the K=256 attention GEMMs; ncu --set full)"),
-                     ("prof_gemm128.ncu-rep", "conv_gemm_umma_kernel<128,0,2> (3x3 conv 128->128 @32x32, 256-row tiles; ncu --set full)"),
+  for rep, title in (("prof_gemm256.ncu-rep", "conv_gemm_umma_kernel<256,0,1,*> (six consecutive N=256 launches of the 16x16 level: 3x3 convs as CTA pairs and the K=256 attention GEMMs; ncu --set full)"),
+                     ("prof_gemm128.ncu-rep", "conv_gemm_umma_kernel<128,0,2,2,true> (3x3 conv 128->128 @32x32: 256-row halo tiles, CTA pairs; ncu --set full)"),
                      ("prof_gn.ncu-rep", "gn_apply_kernel (ncu --set full)")):
     p = os.path.join(SRC, rep)
     if os.path.exists(p):
