@@ -310,6 +310,8 @@ def run_ours(args):
 
 
 def main():
+  # NCCL prints its version banner (and NCCL_DEBUG output) on stdout; the contract is ONE JSON line there
+  os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
   args = parse()
   if args.impl == "reference":
     run_reference(args)
