@@ -4,11 +4,15 @@
 //   cld_jax/models/layers.py:66-107 (ddpm_conv1x1 / ddpm_conv3x3), layers.py:467-478 (NIN),
 //   cld_jax/models/layerspp.py:74-78 (attention einsums).
 //
-// Design: persistent CTAs (one per SM), 6 warps:
-//   warp 0   TMA producer  - one 4-D box load per (tap, 64-channel chunk) builds the im2col A tile
-//                            directly in shared memory (shifted box + hardware zero fill = SAME padding)
-//   warp 1   MMA issuer    - tcgen05.mma.kind::f16, 128 x BLOCK_N x 16, accumulators in TMEM (2 stages)
-//   warps 2-5 epilogue     - tcgen05.ld -> bias / temb / residual / scale (or row softmax) -> global
+// Design: persistent CTAs (one per SM), 10 warps:
+//   warps 0-7 epilogue     - tcgen05.ld -> swizzled smem transposition -> bias / temb / residual / scale / column
+//                            statistics (or row softmax) -> full-line global stores; two groups of four warps take
+//                            alternate 32-column chunks of every tile
+//   warp 8   TMA producer  - one 4-D box load per (tap, 64-channel chunk) builds the im2col A tile directly in
+//                            shared memory (shifted box + hardware zero fill = SAME padding); HALO kernels load one
+//                            (rows + 2)-row box per x-shift and take the y-shifts as descriptor offsets
+//   warp 9   MMA issuer    - tcgen05.mma.kind::f16, 128 x BLOCK_N x 16 (cta_group::2: 256 x BLOCK_N x 16 across a
+//                            CTA pair, each CTA staging half the weight tile), accumulators in TMEM (2 stages)
 // Operands are fp16 with fp32 accumulation; smem tiles use the 128-byte swizzle (K-major).
 #include <cstdio>
 #include <cstdlib>

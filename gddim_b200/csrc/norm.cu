@@ -5,13 +5,16 @@
 // ncsnpp.py:236.  Statistics: per (image, group) over (H, W, C/G), variance = E[x^2] - E[x]^2,
 // eps = 1e-6 (flax default), groups are contiguous channel blocks.
 //
-// Memory-bound, no tensor-core path.
-//   pass 1  gn_stats_kernel   reads the fp32 source once (float4, 4 loads in flight per thread), writes
-//                             per-slab partial sums; the last slab of an image (atomic ticket) folds them in a
-//                             fixed order into per-channel scale/shift  a = rstd*gamma, b = beta - mean*a
-//   pass 2  gn_apply_kernel   reads the source again, y = act(a*x + b) in registers (8 channels per thread,
-//                             coefficients held in registers across pixels), optional 4x4 / 2x2 FIR gather,
-//                             16-byte fp16 stores.  Also emits the raw (resampled) fp16 copy for shortcut convs.
+// Memory-bound, no tensor-core path.  Three routes, chosen per op in norm_launch:
+//   producer was a GEMM   gn_coef_kernel folds the column statistics the GEMM epilogue wrote (per 32-row slab) into
+//                         per-channel scale/shift  a = rstd*gamma, b = beta - mean*a  (no pass over the tensor), then
+//                         gn_apply_kernel: y = act(a*x + b) in registers (8 channels per thread, coefficients held in
+//                         registers across pixels), optional 4x4 / 2x2 FIR gather, 16-byte fp16 stores; also emits
+//                         the raw (resampled) fp16 copy for shortcut convs
+//   other producers       gn_stats_kernel reads the fp32 source once (float4, 4 loads in flight per thread), writes
+//                         per-slab partial sums; the last slab of an image (integer ticket) folds them in a fixed
+//                         order into a / b; then gn_apply_kernel
+//   images <= 64 pixels   gn_small_kernel: one CTA per image, the image in registers, statistics + apply in one launch
 #include <cstdlib>
 #include <cstdio>
 

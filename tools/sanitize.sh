@@ -12,3 +12,6 @@ x = np.random.default_rng(0).standard_normal((2,32,32,6)).astype(np.float32)
 print(float(np.abs(model.forward(x, 0.5)).max()))
 " > gpurun_out/sanitize_racecheck.log 2>&1
 tail -6 gpurun_out/sanitize_racecheck.log
+# CTA pairs (cta_group::2, remote mbarriers) and halo tiles at kernel level
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "halo or pairs" > gpurun_out/sanitize_pairs_halo.log 2>&1
+tail -6 gpurun_out/sanitize_pairs_halo.log
