@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
               ("bias", C.c_void_p), ("bias2", C.c_void_p), ("residual", C.c_void_p), ("rowscale", C.c_void_p),
               ("scale", C.c_float), ("out32", C.c_void_p), ("out16", C.c_void_p), ("row_out", C.c_void_p),
               ("ldo", C.c_int), ("epi", C.c_int), ("impl", C.c_int), ("force_block_n", C.c_int),
-              ("force_m_sub", C.c_int), ("n_store", C.c_int), ("force_cta_pairs", C.c_int)]
+              ("force_m_sub", C.c_int), ("n_store", C.c_int), ("force_cta_pairs", C.c_int), ("reverse", C.c_int)]
 
 
 class NormDesc(C.Structure):
@@ -43,7 +43,7 @@ class NormDesc(C.Structure):
               ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int),
               ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
               ("silu", C.c_int), ("resample", C.c_int), ("dst16", C.c_void_p), ("raw16", C.c_void_p),
-              ("raw_scale", C.c_float)]
+              ("raw_scale", C.c_float), ("reverse", C.c_int)]
 
 
 class Step(C.Structure):

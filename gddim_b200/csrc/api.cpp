@@ -312,6 +312,7 @@ int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream) {
   g.w_batch_stride = d->w_batch_stride; g.w_rows_per_batch = d->w_rows_per_batch;
   g.bias = d->bias; g.bias2 = d->bias2; g.residual = d->residual; g.rowscale = d->rowscale; g.scale = d->scale;
   g.out32 = d->out32; g.out16 = (__half*)d->out16; g.row_out = d->row_out; g.ldo = d->ldo; g.epi = d->epi; g.n_store = d->n_store;
+  g.reverse = d->reverse;
   if (d->impl == 0 && gemm_prepare(&g, d->force_block_n, d->force_m_sub, d->force_cta_pairs)) return set_err(std::string("gddim_conv_gemm: ") + gemm_last_error());
   if (gemm_launch(&g, d->impl, (cudaStream_t)stream)) return set_err(std::string("gddim_conv_gemm: ") + gemm_last_error());
   return 0;
@@ -327,6 +328,7 @@ int gddim_group_norm(const gddim_norm_desc* d, void* stream) {
   n.B = d->B; n.H = d->H; n.W = d->W; n.groups = d->groups; n.gamma = d->gamma; n.beta = d->beta; n.eps = d->eps;
   n.silu = d->silu; n.resample = d->resample; n.dst16 = (__half*)d->dst16; n.raw16 = (__half*)d->raw16;
   n.raw_scale = d->raw_scale;
+  n.reverse = d->reverse;
   n.splits = norm_splits(d->B, d->H, d->W);
   char* scratch = nullptr;
   const size_t nb_part = (size_t)d->B * n.splits * (d->groups > 0 ? d->groups : 1) * 2 * sizeof(float);

@@ -20,6 +20,7 @@
 #include <mutex>
 
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace gddim {
@@ -67,6 +68,7 @@ struct GemmArgs {
   int n_store;
   float* colstats;
   int stages, stage_bytes, a_bytes;   // HALO kernels: smem ring geometry (depends on W)
+  int reverse;   // tiles in descending order (the consumer of a tensor starts with what its producer wrote last: L2 hits)
   int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };
 
@@ -252,6 +254,7 @@ template <int BLOCK_N, int EPI, int MT, int CG, bool HALO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmH, const GemmArgs p) {
+  pdl_launch_dependents();   // the wait is after the prologue
   using L = SmemLayout<BLOCK_N, MT, CG>;
   static_assert(CG == 1 || (EPI == EPI_LINEAR && (BLOCK_N / CG) % 16 == 0), "CTA pairs: linear epilogue only");
   static_assert(!HALO || EPI == EPI_LINEAR, "halo tiles: linear epilogue only");
@@ -297,6 +300,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     if (CG == 2) { ptx::tmem_alloc_2cta(tmem_slot, TMEM_COLS); ptx::tmem_relinquish_2cta(); }
     else { ptx::tmem_alloc(tmem_slot, TMEM_COLS); ptx::tmem_relinquish(); }
   }
+  // everything above touched only this CTA's shared memory / TMEM; from here on global memory is read and written
+  pdl_wait();
   ptx::tc_fence_before();
   if (CG == 2) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
@@ -322,7 +327,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       if (CG == 1) ptx::tma_load_4d(tm, own_bar, dst, c0, c1, c2, c3);
       else ptx::tma_load_4d_2cta(tm, fb, dst, c0, c1, c2, c3);
     };
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    for (int tile_i = tile0; tile_i < num_tiles; tile_i += tile_step) {
+      const int tile = p.reverse ? num_tiles - 1 - tile_i : tile_i;
       const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
       int w0[MT], h0[MT], b0[MT];
 #pragma unroll
@@ -435,7 +441,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     int bias_buf = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, bias_buf ^= 1) {
+    for (int tile_i = tile0; tile_i < num_tiles; tile_i += tile_step, bias_buf ^= 1) {
+      const int tile = p.reverse ? num_tiles - 1 - tile_i : tile_i;
       const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
       const long long m = (long long)mt * MT * BLOCK_M + row;
       const bool valid = m < p.M;
@@ -569,6 +576,7 @@ struct RefArgs {
 };
 
 __global__ void __launch_bounds__(256) conv_gemm_ref_kernel(const RefArgs p) {
+  pdl_entry();
   __shared__ float sA[16][64 + 1];
   __shared__ float sW[16][64 + 1];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -654,6 +662,7 @@ __global__ void __launch_bounds__(256) conv_gemm_ref_kernel(const RefArgs p) {
 
 // column statistics of the reference path's fp32 output (same layout as the fused epilogue's)
 __global__ void colstats_ref_kernel(const float* out32, float* colstats, int M, int N, int ldo) {
+  pdl_entry();
   const int n = blockIdx.y * blockDim.x + threadIdx.x;
   const long long slab = blockIdx.x;
   if (n >= N) return;
@@ -669,6 +678,7 @@ __global__ void colstats_ref_kernel(const float* out32, float* colstats, int M, 
 }
 
 __global__ void softmax_ref_kernel(const float* s, __half* out16, float* row_out, int M, int N, int ldo) {
+  pdl_entry();
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float mx = -INFINITY;
@@ -888,17 +898,17 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
     const int pairs = units < num_sms_eff / 2 ? units : num_sms_eff / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem_total; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_attr(at, 1);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, op->tmA[0], op->tmA[1], op->tmB, op->tmH, a);
     if (e != cudaSuccess) GEMM_FAIL("conv_gemm_umma pair launch: %s", cudaGetErrorString(e));
     return 0;
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms_eff ? tiles : num_sms_eff;
-  kern<<<grid, NUM_THREADS, smem_total, st>>>(op->tmA[0], op->tmA[1], op->tmB, op->tmH, a);
+  launch_k(kern, dim3(grid), dim3(NUM_THREADS), smem_total, st, op->tmA[0], op->tmA[1], op->tmB, op->tmH, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) GEMM_FAIL("conv_gemm_umma launch: %s", cudaGetErrorString(e));
   return 0;
@@ -927,6 +937,7 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     a.scale = op->scale; a.out32 = op->out32; a.out16 = op->out16; a.row_out = op->row_out; a.ldo = op->ldo;
     a.colstats = op->colstats;
     a.n_store = op->n_store;
+    a.reverse = op->reverse;
     {
       static int dbg = -1;
       if (dbg < 0) { const char* e = getenv("GDDIM_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
@@ -984,13 +995,13 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     r.softmax_tmp = g_softmax_tmp;
   }
   dim3 grid((unsigned)((M + 63) / 64), (unsigned)((op->N + 63) / 64));
-  conv_gemm_ref_kernel<<<grid, 256, 0, st>>>(r);
+  launch_k(conv_gemm_ref_kernel, dim3(grid), dim3(256), 0, st, r);
   if (op->colstats != nullptr && op->out32 != nullptr) {
     dim3 g2((unsigned)((M + 31) / 32), (unsigned)((op->N + 127) / 128));
-    colstats_ref_kernel<<<g2, 128, 0, st>>>(op->out32, op->colstats, (int)M, op->N, op->ldo);
+    launch_k(colstats_ref_kernel, dim3(g2), dim3(128), 0, st, op->out32, op->colstats, (int)M, op->N, op->ldo);
   }
   if (op->epi == EPI_SOFTMAX)
-    softmax_ref_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(g_softmax_tmp, op->out16, op->row_out, (int)M, op->N, op->ldo);
+    launch_k(softmax_ref_kernel, dim3((unsigned)((M + 127) / 128)), dim3(128), 0, st, g_softmax_tmp, op->out16, op->row_out, (int)M, op->N, op->ldo);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) GEMM_FAIL("conv_gemm_ref launch: %s", cudaGetErrorString(e));
   return 0;

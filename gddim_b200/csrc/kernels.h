@@ -49,6 +49,10 @@ struct GemmOp {
   // optional GroupNorm statistics of the output, fused into the epilogue: per 32-row slab and column,
   // colstats[slab][0][n] = sum, colstats[slab][1][n] = sum of squares (slab = m / 32; rows >= M excluded)
   float* colstats;
+  // tiles in descending order.  A consumer that starts with what its producer wrote last finds it still in L2 (the
+  // 32x32-level tensors are larger than the 126 MB L2, so same-direction sweeps get no hits at all); unet.cpp
+  // alternates the direction along every producer -> consumer chain.  Results do not depend on it.
+  int reverse;
   // ---- filled by gemm_prepare ----
   CUtensorMap tmA[2];
   CUtensorMap tmB;
@@ -89,6 +93,7 @@ struct NormOp {
   __half* dst16;                 // normalised (+act, +resample) output  [B,H',W',C]; may be null
   __half* raw16;                 // raw (resampled) copy of the input in fp16; may be null
   float raw_scale;               // raw16 = x * raw_scale (power of two: headroom against fp16 overflow)
+  int reverse;                   // apply pass walks images / pixel chunks in descending order (see GemmOp::reverse)
 };
 int norm_launch(const NormOp* op, cudaStream_t st);
 int norm_num_launches(const NormOp* op);   // kernels norm_launch issues for this op (1 or 2)

@@ -19,6 +19,7 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace gddim {
 
@@ -42,6 +43,7 @@ struct StatsArgs {
 };
 
 __global__ void __launch_bounds__(1024) gn_stats_kernel(const StatsArgs p) {
+  pdl_entry();
   extern __shared__ float sm[];   // [threads][8]: per-channel sum[4], sumsq[4]
   __shared__ int s_last;
   const int C = p.c1 + p.c2;
@@ -137,6 +139,7 @@ struct CoefArgs {
 // up every lanes-th 32-row slab of its channel, the lanes are folded in a fixed order: deterministic, and the
 // dependent chain is slabs / lanes long (2048 slabs per image at 256x256, hence up to 1024 threads).
 __global__ void __launch_bounds__(1024) gn_coef_kernel(const CoefArgs p) {
+  pdl_entry();
   __shared__ float sm_s[1024], sm_q[1024];
   const int C = p.c1 + p.c2;
   const int cpg = C / p.groups;
@@ -191,6 +194,7 @@ struct ApplyArgs {
   int rows;                // pixel rows handled concurrently by a CTA (blockDim.x = rows * C/8)
   int pix_per_cta;
   __half* dst16; __half* raw16;
+  int reverse;   // walk images / pixel chunks in descending order (NormOp::reverse)
 };
 
 __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
@@ -227,9 +231,11 @@ __device__ __forceinline__ void tap_table(int oy, int ox, int& ny, int& nx, int&
 
 template <int RS>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
+  pdl_entry();
   const int C = p.c1 + p.c2;
   const int nv = C / 8;
-  const int b = blockIdx.y;
+  const int b = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int chunk = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int vi = threadIdx.x % nv, row = threadIdx.x / nv;
   const int c = vi * 8;
   const float* base; int cs;
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
     bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
   }
   const int Pout = p.Ho * p.Wo;
-  const int pbeg = blockIdx.x * p.pix_per_cta;
+  const int pbeg = chunk * p.pix_per_cta;
   const int pend = min(pbeg + p.pix_per_cta, Pout);
   __half* dst = p.dst16 ? p.dst16 + (long long)b * Pout * C + c : nullptr;
   __half* raw = p.raw16 ? p.raw16 + (long long)b * Pout * C + c : nullptr;
@@ -351,14 +357,16 @@ struct SmallArgs {
   int silu;
   float raw_scale;
   __half* dst16; __half* raw16;
+  int reverse;
 };
 
 template <int PPT>
 __global__ void __launch_bounds__(512) gn_small_kernel(const SmallArgs p) {
+  pdl_entry();
   extern __shared__ float sm[];            // [threads][2] partial (sum, sumsq) of each thread's 4 channels, then [groups][2]
   const int C = p.c1 + p.c2;
   const int nv = C / 4;
-  const int b = blockIdx.x;
+  const int b = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int vi = threadIdx.x % nv, row = threadIdx.x / nv;
   const int c = vi * 4;
   const float* base;
@@ -461,14 +469,15 @@ static int small_launch(const NormOp* op, cudaStream_t st) {
   a.inv_n = 1.0f / ((float)P * (float)cpg);
   a.eps = op->eps; a.gamma = op->gamma; a.beta = op->beta; a.silu = op->silu; a.raw_scale = op->raw_scale;
   a.dst16 = op->dst16; a.raw16 = op->raw16;
+  a.reverse = op->reverse;
   const int threads = rows * nv;
   const size_t smem = (size_t)threads * 2 * sizeof(float);
   switch (ppt) {
-    case 1: gn_small_kernel<1><<<op->B, threads, smem, st>>>(a); break;
-    case 2: gn_small_kernel<2><<<op->B, threads, smem, st>>>(a); break;
-    case 4: gn_small_kernel<4><<<op->B, threads, smem, st>>>(a); break;
-    case 8: gn_small_kernel<8><<<op->B, threads, smem, st>>>(a); break;
-    case 16: gn_small_kernel<16><<<op->B, threads, smem, st>>>(a); break;
+    case 1: launch_k(gn_small_kernel<1>, dim3(op->B), dim3(threads), smem, st, a); break;
+    case 2: launch_k(gn_small_kernel<2>, dim3(op->B), dim3(threads), smem, st, a); break;
+    case 4: launch_k(gn_small_kernel<4>, dim3(op->B), dim3(threads), smem, st, a); break;
+    case 8: launch_k(gn_small_kernel<8>, dim3(op->B), dim3(threads), smem, st, a); break;
+    case 16: launch_k(gn_small_kernel<16>, dim3(op->B), dim3(threads), smem, st, a); break;
     default: return 1;
   }
   return 0;
@@ -501,7 +510,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     int lanes = 1;                                      // ~4 slabs per thread, at most 1024 threads
     while (lanes * 2 * nch <= 1024 && lanes * 2 * 4 <= slabs) lanes *= 2;
     dim3 cgrid(op->B, op->groups / gpc);
-    gn_coef_kernel<<<cgrid, lanes * nch, 0, st>>>(c);
+    launch_k(gn_coef_kernel, dim3(cgrid), dim3(lanes * nch), 0, st, c);
   } else if (do_norm) {
     if (C % op->groups != 0) return -2;
     if (!op->partial || !op->coef || !op->ticket) return -5;
@@ -519,7 +528,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     s.eps = op->eps; s.gamma = op->gamma; s.beta = op->beta;
     s.partial = op->partial; s.coef = op->coef; s.ticket = op->ticket;
     dim3 grid(op->splits, op->B);
-    gn_stats_kernel<<<grid, threads, threads * 8 * sizeof(float), st>>>(s);
+    launch_k(gn_stats_kernel, dim3(grid), dim3(threads), threads * 8 * sizeof(float), st, s);
   }
   ApplyArgs a;
   a.src1 = op->src1; a.c1 = op->c1; a.src2 = op->src2; a.c2 = op->c2;
@@ -531,6 +540,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
   }
   a.coef = op->coef; a.silu = op->silu; a.do_norm = do_norm; a.raw_scale = op->raw_scale;
   a.dst16 = op->dst16; a.raw16 = op->raw16;
+  a.reverse = op->reverse;
   const int nv8 = C / 8;
   int rows = 256 / nv8;
   if (rows < 1) rows = 1;
@@ -544,11 +554,11 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
   dim3 grid((Pout + ppc - 1) / ppc, op->B);
   const int threads = rows * nv8;
   switch (op->resample) {
-    case RS_NONE: gn_apply_kernel<RS_NONE><<<grid, threads, 0, st>>>(a); break;
-    case RS_FIR_DOWN: gn_apply_kernel<RS_FIR_DOWN><<<grid, threads, 0, st>>>(a); break;
-    case RS_FIR_UP: gn_apply_kernel<RS_FIR_UP><<<grid, threads, 0, st>>>(a); break;
-    case RS_NAIVE_DOWN: gn_apply_kernel<RS_NAIVE_DOWN><<<grid, threads, 0, st>>>(a); break;
-    case RS_NAIVE_UP: gn_apply_kernel<RS_NAIVE_UP><<<grid, threads, 0, st>>>(a); break;
+    case RS_NONE: launch_k(gn_apply_kernel<RS_NONE>, dim3(grid), dim3(threads), 0, st, a); break;
+    case RS_FIR_DOWN: launch_k(gn_apply_kernel<RS_FIR_DOWN>, dim3(grid), dim3(threads), 0, st, a); break;
+    case RS_FIR_UP: launch_k(gn_apply_kernel<RS_FIR_UP>, dim3(grid), dim3(threads), 0, st, a); break;
+    case RS_NAIVE_DOWN: launch_k(gn_apply_kernel<RS_NAIVE_DOWN>, dim3(grid), dim3(threads), 0, st, a); break;
+    case RS_NAIVE_UP: launch_k(gn_apply_kernel<RS_NAIVE_UP>, dim3(grid), dim3(threads), 0, st, a); break;
     default: return -6;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -4;

@@ -9,6 +9,7 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace gddim {
 
@@ -18,6 +19,7 @@ static int ceil_div_ll(long long a, long long b) { return int((a + b - 1) / b); 
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ out, int H,
                                                        int W, int cin, int cout) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* sw = sm;                              // [9*cin][cout]
   float* sin_ = sm + 9 * cin * cout;           // [(rows+2)][W+2][cin]
@@ -62,7 +64,7 @@ int stem_conv_launch(const float* in, const float* w, const float* bias, float* 
     attr = smem;
   }
   dim3 grid((H + 3) / 4, B);
-  stem_conv_kernel<<<grid, 256, smem, st>>>(in, w, bias, out32, H, W, cin, cout);
+  launch_k(stem_conv_kernel, dim3(grid), dim3(256), smem, st, in, w, bias, out32, H, W, cin, cout);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -71,6 +73,7 @@ template <int COUT>
 __global__ void __launch_bounds__(256) head_conv_kernel(const __half* __restrict__ in, const float* __restrict__ w,
                                                        const float* __restrict__ bias, float* __restrict__ out, int B,
                                                        int H, int W, int cin) {
+  pdl_entry();
   extern __shared__ float sw[];                // [9*cin][COUT]
   for (int i = threadIdx.x; i < 9 * cin * COUT; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -119,10 +122,10 @@ int head_conv_launch(const __half* in, const float* w, const float* bias, float*
   int grid = ceil_div_ll(npix, 8);
   if (grid > 148 * 16) grid = 148 * 16;
   switch (cout) {
-    case 3: head_conv_kernel<3><<<grid, 256, smem, st>>>(in, w, bias, out32, B, H, W, cin); break;
-    case 6: head_conv_kernel<6><<<grid, 256, smem, st>>>(in, w, bias, out32, B, H, W, cin); break;
-    case 1: head_conv_kernel<1><<<grid, 256, smem, st>>>(in, w, bias, out32, B, H, W, cin); break;
-    case 2: head_conv_kernel<2><<<grid, 256, smem, st>>>(in, w, bias, out32, B, H, W, cin); break;
+    case 3: launch_k(head_conv_kernel<3>, dim3(grid), dim3(256), smem, st, in, w, bias, out32, B, H, W, cin); break;
+    case 6: launch_k(head_conv_kernel<6>, dim3(grid), dim3(256), smem, st, in, w, bias, out32, B, H, W, cin); break;
+    case 1: launch_k(head_conv_kernel<1>, dim3(grid), dim3(256), smem, st, in, w, bias, out32, B, H, W, cin); break;
+    case 2: launch_k(head_conv_kernel<2>, dim3(grid), dim3(256), smem, st, in, w, bias, out32, B, H, W, cin); break;
     default: return -3;
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
@@ -132,6 +135,7 @@ int head_conv_launch(const __half* in, const float* w, const float* bias, float*
 __global__ void __launch_bounds__(256) im2col_fir_down_kernel(const float* __restrict__ in, __half* __restrict__ a16,
                                                              int B, int H, int W, int c, int kpad, int use_fir,
                                                              float out_scale) {
+  pdl_entry();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * Wo * kpad;
   const float kf[4] = {0.125f, 0.375f, 0.375f, 0.125f};
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(256) im2col_fir_down_kernel(const float* __res
 // 8 channels per thread (c % 8 == 0, kpad == 9*c): float4 loads, one 16-byte store
 __global__ void __launch_bounds__(256) im2col_fir_down_vec8_kernel(const float* __restrict__ in, __half* __restrict__ a16,
                                                                   int B, int H, int W, int c, float out_scale) {
+  pdl_entry();
   const int Ho = H / 2, Wo = W / 2;
   const int cv = c / 8;
   const long long total = (long long)B * Ho * Wo * 9 * cv;
@@ -212,13 +217,13 @@ int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, in
     const long long total = (long long)B * (H / 2) * (W / 2) * 9 * (c / 8);
     int grid = ceil_div_ll(total, 256);
     if (grid > 148 * 32) grid = 148 * 32;
-    im2col_fir_down_vec8_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, out_scale);
+    launch_k(im2col_fir_down_vec8_kernel, dim3(grid), dim3(256), 0, st, in, a16, B, H, W, c, out_scale);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
   const long long total = (long long)B * (H / 2) * (W / 2) * kpad;
   int grid = ceil_div_ll(total, 256);
   if (grid > 148 * 32) grid = 148 * 32;
-  im2col_fir_down_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, kpad, use_fir, out_scale);
+  launch_k(im2col_fir_down_kernel, dim3(grid), dim3(256), 0, st, in, a16, B, H, W, c, kpad, use_fir, out_scale);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -226,6 +231,7 @@ int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, in
 __global__ void __launch_bounds__(256) im2col_same3x3_kernel(const float* __restrict__ in, __half* __restrict__ a16,
                                                             int B, int H, int W, int c, int kpad, float out_scale,
                                                             int split, int kseg) {
+  pdl_entry();
   // one thread per (pixel, 8 consecutive k): 16-byte stores
   const int kv = kpad / 8;
   const long long total = (long long)B * H * W * kv;
@@ -260,6 +266,7 @@ __global__ void __launch_bounds__(256) im2col_same3x3_kernel(const float* __rest
 template <int C>
 __global__ void __launch_bounds__(128) im2col_stem_split_kernel(const float* __restrict__ in, __half* __restrict__ a16,
                                                                int B, int H, int W, float out_scale) {
+  pdl_entry();
   const long long npix = (long long)B * H * W;
   const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
@@ -294,21 +301,22 @@ int im2col_same3x3_launch(const float* in, __half* a16, int B, int H, int W, int
   if (split && kpad == 192 && (c == 6 || c == 3)) {
     const long long npix = (long long)B * H * W;
     const int grid = ceil_div_ll(npix, 128);
-    if (c == 6) im2col_stem_split_kernel<6><<<grid, 128, 0, st>>>(in, a16, B, H, W, out_scale);
-    else im2col_stem_split_kernel<3><<<grid, 128, 0, st>>>(in, a16, B, H, W, out_scale);
+    if (c == 6) launch_k(im2col_stem_split_kernel<6>, dim3(grid), dim3(128), 0, st, in, a16, B, H, W, out_scale);
+    else launch_k(im2col_stem_split_kernel<3>, dim3(grid), dim3(128), 0, st, in, a16, B, H, W, out_scale);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
   const int kseg = split ? kpad / 3 : kpad;
   const long long total = (long long)B * H * W * (kpad / 8);
   int grid = ceil_div_ll(total, 256);
   if (grid > 148 * 32) grid = 148 * 32;
-  im2col_same3x3_kernel<<<grid, 256, 0, st>>>(in, a16, B, H, W, c, kpad, out_scale, split, kseg);
+  launch_k(im2col_same3x3_kernel, dim3(grid), dim3(256), 0, st, in, a16, B, H, W, c, kpad, out_scale, split, kseg);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 // ---- V^T: qkv16 [B,T,ld] (V at voff) -> vT [B,C,T]; 32x32 tiles through shared memory ------------------------
 __global__ void __launch_bounds__(256) transpose_v_kernel(const __half* __restrict__ qkv, __half* __restrict__ vT, int T,
                                                          int C, int ld, int voff) {
+  pdl_entry();
   __shared__ __half tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -327,6 +335,7 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const __half* __restri
 // 64x64 tiles, 16-byte global accesses on both sides (T, C, ld, voff multiples of 8; T, C multiples of 64)
 __global__ void __launch_bounds__(256) transpose_v64_kernel(const __half* __restrict__ qkv, __half* __restrict__ vT, int T,
                                                            int C, int ld, int voff) {
+  pdl_entry();
   __shared__ __align__(16) __half tile[64][72];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
@@ -352,17 +361,18 @@ __global__ void __launch_bounds__(256) transpose_v64_kernel(const __half* __rest
 int transpose_v_launch(const __half* qkv, __half* vT, int B, int T, int C, int ld, int voff, cudaStream_t st) {
   if (T % 64 == 0 && C % 64 == 0 && ld % 8 == 0 && voff % 8 == 0) {
     dim3 grid(T / 64, C / 64, B);
-    transpose_v64_kernel<<<grid, 256, 0, st>>>(qkv, vT, T, C, ld, voff);
+    launch_k(transpose_v64_kernel, dim3(grid), dim3(256), 0, st, qkv, vT, T, C, ld, voff);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
   }
   dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-  transpose_v_kernel<<<grid, 256, 0, st>>>(qkv, vT, T, C, ld, voff);
+  launch_k(transpose_v_kernel, dim3(grid), dim3(256), 0, st, qkv, vT, T, C, ld, voff);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 // ---- attention for very short sequences (the 4x4 middle block: T = 16) ---------------------------------------
 __global__ void __launch_bounds__(256) small_attn_kernel(const __half* __restrict__ qkv, __half* __restrict__ o16, int T,
                                                         int C, float scale) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* sq = sm;                 // [T][C]
   float* sk = sq + T * C;
@@ -413,7 +423,7 @@ int small_attn_launch(const __half* qkv, __half* o16, int B, int T, int C, float
     cudaFuncSetAttribute(small_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr = smem;
   }
-  small_attn_kernel<<<B, 256, smem, st>>>(qkv, o16, T, C, scale);
+  launch_k(small_attn_kernel, dim3(B), dim3(256), smem, st, qkv, o16, T, C, scale);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -422,6 +432,7 @@ int small_attn_launch(const __half* qkv, __half* o16, int B, int T, int C, float
 // will actually add up), same convention as the fused N = 256 epilogue.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s32, __half* __restrict__ p16,
                                                           float* __restrict__ rowinv, long long rows, int T) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -454,7 +465,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 int softmax_rows_launch(const float* s32, __half* p16, float* rowinv, long long rows, int T, cudaStream_t st) {
   if (T % 4 != 0 || rows <= 0) return -1;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  softmax_rows_kernel<<<grid, 256, 0, st>>>(s32, p16, rowinv, rows, T);
+  launch_k(softmax_rows_kernel, dim3(grid), dim3(256), 0, st, s32, p16, rowinv, rows, T);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -462,6 +473,7 @@ int softmax_rows_launch(const float* s32, __half* p16, float* rowinv, long long 
 __global__ void __launch_bounds__(256) dense_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ y, int rows, int K,
                                                    int N, int silu_in) {
+  pdl_entry();
   const long long total = (long long)rows * N;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -482,16 +494,17 @@ int dense_launch(const float* x, const float* w, const float* bias, float* y, in
   const long long total = (long long)rows * N;
   int grid = ceil_div_ll(total, 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  dense_kernel<<<grid, 256, 0, st>>>(x, w, bias, y, rows, K, N, silu_in);
+  launch_k(dense_kernel, dim3(grid), dim3(256), 0, st, x, w, bias, y, rows, K, N, silu_in);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 __global__ void add_vec_kernel(const float* a, const float* b, float* y, int n) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = a[i] + b[i];
 }
 int add_vec_launch(const float* a, const float* b, float* y, int n, cudaStream_t st) {
-  add_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, y, n);
+  launch_k(add_vec_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a, b, y, n);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

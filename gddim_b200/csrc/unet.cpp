@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace gddim {
@@ -776,6 +777,31 @@ int UNet::finalize() {
   if (arena_top_ > arena_peak_) return fail("internal: workspace plan mismatch");
   host_params_.clear();
   proj_w_host_.clear(); proj_w_host_.shrink_to_fit();
+  {
+    // Sweep directions: every GEMM / GroupNorm-apply pass starts at the end its main input was written LAST, so
+    // the tail of the producer's output is still in L2 when it is read (the 32x32-level tensors exceed the L2;
+    // same-direction sweeps get no hits).  GDDIM_ZIGZAG=0 keeps every pass ascending (A/B measurements).
+    const char* e = getenv("GDDIM_ZIGZAG");
+    const bool zigzag = !(e && e[0] == '0');
+    std::map<const void*, int> wdir;                 // buffer -> 1 if its last writer ran in descending order
+    auto dir_of = [&](const void* p) { auto it = wdir.find(p); return it == wdir.end() ? 0 : it->second; };
+    for (auto& op : ops_) {
+      if (op.kind == OP_GEMM) {
+        GemmOp& g = op.gemm;
+        g.reverse = zigzag ? !dir_of(g.seg[0].ptr) : 0;
+        if (g.out32) wdir[g.out32] = g.reverse;
+        if (g.out16) wdir[g.out16] = g.reverse;
+      } else if (op.kind == OP_NORM) {
+        NormOp& n = op.norm;
+        n.reverse = zigzag ? !dir_of(n.src1) : 0;
+        if (n.dst16) wdir[n.dst16] = n.reverse;
+        if (n.raw16) wdir[n.raw16] = n.reverse;
+      } else {
+        if (op.f_out) wdir[op.f_out] = 0;
+        if (op.h_out) wdir[op.h_out] = 0;
+      }
+    }
+  }
   for (auto& op : ops_) {
     if (op.kind == OP_GEMM) {
       if (gemm_prepare(&op.gemm, 0) != 0) return fail(std::string("gemm_prepare(") + op.tag + "): " + gemm_last_error());

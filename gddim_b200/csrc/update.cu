@@ -12,6 +12,7 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace gddim {
 
@@ -65,6 +66,7 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long idx, unsigne
 
 // Specialisation for C = 3 (pixel = 6 floats): a thread owns 2 pixels = 3 float4 per array.
 __global__ void __launch_bounds__(256) cld_step_c3_kernel(const CldStepDev p) {
+  pdl_entry();
   const long long npair = p.n_pix / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair;
        i += (long long)gridDim.x * blockDim.x) {
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(256) cld_step_c3_kernel(const CldStepDev p) {
 
 // Generic channel count: one thread per (pixel, d) pair.
 __global__ void __launch_bounds__(256) cld_step_generic_kernel(const CldStepDev p) {
+  pdl_entry();
   const long long n = p.n_pix * p.C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / p.C;
@@ -189,15 +192,16 @@ int cld_step_launch(const CldStepArgs* a, cudaStream_t st) {
   for (int k = 0; k < 4; ++k) d.nfac[k] = a->nfac[k];
   if (a->n_eps < 0 || a->n_eps > 6) return -1;
   if (a->C == 3 && a->n_pix % 2 == 0) {
-    cld_step_c3_kernel<<<grid_for(a->n_pix / 2, 256), 256, 0, st>>>(d);
+    launch_k(cld_step_c3_kernel, dim3(grid_for(a->n_pix / 2, 256)), dim3(256), 0, st, d);
   } else {
-    cld_step_generic_kernel<<<grid_for(a->n_pix * a->C, 256), 256, 0, st>>>(d);
+    launch_k(cld_step_generic_kernel, dim3(grid_for(a->n_pix * a->C, 256)), dim3(256), 0, st, d);
   }
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 __global__ void cld_split_kernel(const float* __restrict__ u, float* __restrict__ x, float* __restrict__ v,
                                  long long n_pix, int C, float mul, float add) {
+  pdl_entry();
   const long long n = n_pix * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / C;
@@ -208,13 +212,14 @@ __global__ void cld_split_kernel(const float* __restrict__ u, float* __restrict_
   }
 }
 int cld_split_launch(const float* u, float* x, float* v, long long n_pix, int C, float mul, float add, cudaStream_t st) {
-  cld_split_kernel<<<grid_for(n_pix * C, 256), 256, 0, st>>>(u, x, v, n_pix, C, mul, add);
+  launch_k(cld_split_kernel, dim3(grid_for(n_pix * C, 256)), dim3(256), 0, st, u, x, v, n_pix, C, mul, add);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 // reference layout [pix, d, g] <-> net layout [pix, g*C + d]
 __global__ void relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n_pix, int C,
                                 int to_net) {
+  pdl_entry();
   const long long n = n_pix * 2 * C;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / (2 * C);
@@ -229,7 +234,7 @@ __global__ void relayout_kernel(const float* __restrict__ src, float* __restrict
   }
 }
 int relayout_launch(const float* src, float* dst, long long n_pix, int C, int to_net, cudaStream_t st) {
-  relayout_kernel<<<grid_for(n_pix * 2 * C, 256), 256, 0, st>>>(src, dst, n_pix, C, to_net);
+  launch_k(relayout_kernel, dim3(grid_for(n_pix * 2 * C, 256)), dim3(256), 0, st, src, dst, n_pix, C, to_net);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(256) ab_step_ref_kernel(const float* __restric
                                                          const float* __restrict__ new_eps,
                                                          const float* __restrict__ hist, float* __restrict__ x_out,
                                                          float* __restrict__ hist_out, int order, long long n_pairs) {
+  pdl_entry();
   __shared__ float sc[8 * 4];
   if (threadIdx.x < (order + 3) * 4) sc[threadIdx.x] = coef[threadIdx.x];
   __syncthreads();
@@ -262,7 +268,7 @@ __global__ void __launch_bounds__(256) ab_step_ref_kernel(const float* __restric
 int ab_step_ref_layout_launch(const float* x, const float* coef, const float* new_eps, const float* hist, float* x_out,
                               float* hist_out, int order, long long n_pairs, cudaStream_t st) {
   if (order < 0 || order > 5) return -1;
-  ab_step_ref_kernel<<<grid_for(n_pairs, 256), 256, 0, st>>>(x, coef, new_eps, hist, x_out, hist_out, order, n_pairs);
+  launch_k(ab_step_ref_kernel, dim3(grid_for(n_pairs, 256)), dim3(256), 0, st, x, coef, new_eps, hist, x_out, hist_out, order, n_pairs);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -314,6 +320,7 @@ __device__ void dct_planes(float* img, float* tmp, const float* sD, int C, int f
 }
 
 __global__ void __launch_bounds__(256) dct32_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int fwd) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* sD = sm;
   float* img = sm + 1024;
@@ -332,7 +339,7 @@ int dct32_launch(const float* in, float* out, int B, int C, int fwd, cudaStream_
   if (ensure_dct_matrix()) return -1;
   const size_t smem = (size_t)(1024 + 2 * 1024 * C) * sizeof(float);
   if (smem > 48 * 1024) return -3;
-  dct32_kernel<<<B, 256, smem, st>>>(in, out, C, fwd);
+  launch_k(dct32_kernel, dim3(B), dim3(256), smem, st, in, out, C, fwd);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -340,6 +347,7 @@ int dct32_launch(const float* in, float* out, int B, int C, int fwd, cudaStream_
 __global__ void __launch_bounds__(256) blur_step_kernel(const float* __restrict__ y, const float* __restrict__ eps_x,
                                                        const float* __restrict__ a, const float* __restrict__ bcoef,
                                                        float* __restrict__ y_out, float* __restrict__ x_next, int C) {
+  pdl_entry();
   extern __shared__ float sm[];
   float* sD = sm;
   float* img = sm + 1024;
@@ -368,23 +376,25 @@ int blur_step_launch(const float* y, const float* eps_x, const float* a, const f
   if (ensure_dct_matrix()) return -1;
   const size_t smem = (size_t)(1024 + 2 * 1024 * C) * sizeof(float);
   if (smem > 48 * 1024) return -3;
-  blur_step_kernel<<<B, 256, smem, st>>>(y, eps_x, a, b, y_out, x_next, C);
+  launch_k(blur_step_kernel, dim3(B), dim3(256), smem, st, y, eps_x, a, b, y_out, x_next, C);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 __global__ void scale_shift_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float mul,
                                    float add) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = in[i] * mul + add;
 }
 int scale_shift_launch(const float* in, float* out, long long n, float mul, float add, cudaStream_t st) {
-  scale_shift_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, out, n, mul, add);
+  launch_k(scale_shift_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, in, out, n, mul, add);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 __global__ void scalar_ab_step_kernel(const float* __restrict__ x, const float* __restrict__ coef,
                                       const float* __restrict__ new_eps, const float* __restrict__ hist,
                                       float* __restrict__ x_out, float* __restrict__ hist_out, int n_hist, long long n) {
+  pdl_entry();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float e0 = new_eps[i];
     float acc = coef[0] * x[i] + coef[1] * e0;
@@ -399,7 +409,7 @@ __global__ void scalar_ab_step_kernel(const float* __restrict__ x, const float* 
 }
 int scalar_ab_step_launch(const float* x, const float* coef, const float* new_eps, const float* hist, float* x_out,
                           float* hist_out, int n_hist, long long n, cudaStream_t st) {
-  scalar_ab_step_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, coef, new_eps, hist, x_out, hist_out, n_hist, n);
+  launch_k(scalar_ab_step_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, x, coef, new_eps, hist, x_out, hist_out, n_hist, n);
   return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

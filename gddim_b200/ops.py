@@ -32,7 +32,7 @@ def pack_conv_weight(kernel_hwio, extra_1x1=None):
 
 def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residual=None, rowscale=None, scale=1.0,
               out_fp32=True, out_fp16=False, impl=0, force_block_n=0, force_m_sub=0, force_cta_pairs=0, epi=0, n_store=0, a0_coff=0, a0_c=None, w_ld=None,
-              w_koff=0, w_batch_stride=0, w_rows_per_batch=0):
+              w_koff=0, w_batch_stride=0, w_rows_per_batch=0, reverse=0):
   """a0 (and a1): fp16 [B,H,W,C]; w: fp16 K-major.  Returns (out32 or None, out16 or None[, row_out])."""
   import torch
   _lib.require_cuda("conv_gemm")
@@ -54,6 +54,7 @@ def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residu
   d.n_store = n_store
   d.epi, d.impl, d.force_block_n, d.force_m_sub = epi, impl, force_block_n, force_m_sub
   d.force_cta_pairs = force_cta_pairs
+  d.reverse = reverse
   st = torch.cuda.current_stream().cuda_stream
   _lib.check(_lib.lib().gddim_conv_gemm(C.byref(d), st), "gddim_conv_gemm")
   if epi == 1:
@@ -62,7 +63,7 @@ def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residu
 
 
 def group_norm(x, gamma, beta, groups=None, silu=True, resample=0, x2=None, want_raw=False, want_norm=True,
-               eps=1e-6, raw_scale=1.0):
+               eps=1e-6, raw_scale=1.0, reverse=0):
   """x (and x2): fp32 [B,H,W,C].  Returns (dst16 or None, raw16 or None)."""
   import torch
   _lib.require_cuda("group_norm")
@@ -80,6 +81,7 @@ def group_norm(x, gamma, beta, groups=None, silu=True, resample=0, x2=None, want
   raw = torch.empty((B, Ho, Wo, Ct), dtype=torch.float16, device="cuda") if want_raw else None
   d.dst16, d.raw16 = _ptr(dst), _ptr(raw)
   d.raw_scale = raw_scale
+  d.reverse = reverse
   st = torch.cuda.current_stream().cuda_stream
   _lib.check(_lib.lib().gddim_group_norm(C.byref(d), st), "gddim_group_norm")
   return dst, raw

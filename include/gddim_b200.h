@@ -146,6 +146,7 @@ typedef struct {
   int force_m_sub;                                          /* with force_block_n: 2 = 256-row CTA tiles */
   int n_store;                                              /* 0 = all N; else store only columns < n_store (fp32) */
   int force_cta_pairs;                                      /* 0 = heuristic, 1 = single-CTA MMA, 2 = cta_group::2 pairs (block_n 256) */
+  int reverse;                                              /* 1 = tiles in descending order (L2 reuse along producer -> consumer chains); same results */
 } gddim_gemm_desc;
 int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream);
 
@@ -158,6 +159,7 @@ typedef struct {
   int silu; int resample;
   void* dst16; void* raw16;
   float raw_scale;            /* raw16 = x * raw_scale */
+  int reverse;                /* 1 = apply pass walks the batch in descending order; same results */
 } gddim_norm_desc;
 int gddim_group_norm(const gddim_norm_desc* d, void* stream);
 

@@ -209,6 +209,42 @@ def test_group_norm_swish_resample(case, silu):
   assert rel_l2(raw.float().cpu().numpy(), want_r.numpy()) < 6e-4
 
 
+REV_CASES = [  # B, H, W, Cin, Cout, block_n, m_sub, pairs
+    (3, 32, 32, 128, 128, 128, 2, 2), (5, 16, 16, 256, 256, 256, 1, 2), (3, 16, 16, 128, 256, 256, 1, 1),
+    (7, 8, 8, 64, 64, 64, 1, 1), (9, 8, 16, 128, 128, 128, 2, 1)]
+
+
+@pytest.mark.parametrize("case", REV_CASES, ids=[f"b{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}_bn{c[5]}x{c[6]}_cg{c[7]}" for c in REV_CASES])
+def test_umma_reverse_tile_order_is_bit_identical(case):
+  """`reverse` only changes the order in which a CTA visits its tiles (L2 reuse along producer -> consumer chains,
+  unet.cpp finalize): the outputs must be bit-identical, including ragged last tiles, pairs and halo tiles."""
+  B, H, W, Cin, Cout, bn, ms, cg = case
+  g = torch.Generator().manual_seed(7 + sum(case))
+  a = torch.randn(B, H, W, Cin, generator=g).to(torch.float16).cuda()
+  k = (torch.randn(3, 3, Cin, Cout, generator=g) / np.sqrt(9 * Cin)).numpy()
+  res = torch.randn(B, H, W, Cout, generator=g).cuda()
+  bias = torch.randn(Cout, generator=g).cuda()
+  w = ops.pack_conv_weight(k)
+  outs = [ops.conv_gemm(a, w, Cout, taps0=9, bias=bias, residual=res, scale=0.5, out_fp16=True, impl=0,
+                        force_block_n=bn, force_m_sub=ms, force_cta_pairs=cg, reverse=r) for r in (0, 1)]
+  assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+  want = (_conv_ref(a.cpu(), k, 9) + bias.cpu().double() + res.cpu().double()) * 0.5
+  assert rel_l2(outs[1][0].cpu().numpy(), want.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(5, 32, 32, 128, 0, 0), (3, 16, 16, 256, 128, 1), (4, 8, 8, 256, 0, 0), (3, 16, 16, 64, 0, 2)],
+                         ids=lambda c: f"b{c[0]}_{c[1]}_{c[3]}+{c[4]}_rs{c[5]}")
+def test_group_norm_reverse_sweep_is_bit_identical(case):
+  B, H, W, C1, C2, rs = case
+  g = torch.Generator().manual_seed(11 + sum(case))
+  x1 = (torch.randn(B, H, W, C1, generator=g) * 2 + 0.3).cuda()
+  x2 = torch.randn(B, H, W, C2, generator=g).cuda() if C2 else None
+  Ct = C1 + C2
+  gamma, beta = (1 + 0.1 * torch.randn(Ct, generator=g)).cuda(), (0.1 * torch.randn(Ct, generator=g)).cuda()
+  outs = [ops.group_norm(x1, gamma, beta, silu=True, resample=rs, x2=x2, want_raw=True, reverse=r) for r in (0, 1)]
+  assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("order", [0, 1, 2, 3])
 @pytest.mark.parametrize("as_numpy", [True, False])
 def test_multistep_ab_step(order, as_numpy):
