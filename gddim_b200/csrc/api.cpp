@@ -318,6 +318,26 @@ int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream) {
   return 0;
 }
 
+int gddim_attention(const void* qkv16_dev, void* out16_dev, int B, int T, int C, float scale, int reverse, void* stream) {
+  if (need_cuda("gddim_attention")) return -1;
+  if (!qkv16_dev || !out16_dev || B < 1) return set_err("gddim_attention: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (attn_fused_supported(T, C)) {
+    AttnOp a;
+    memset(&a, 0, sizeof(a));
+    a.qkv = (const __half*)qkv16_dev; a.out16 = (__half*)out16_dev; a.B = B; a.T = T; a.C = C; a.scale = scale;
+    a.reverse = reverse;
+    if (attn_fused_prepare(&a)) return set_err(std::string("gddim_attention: ") + gemm_last_error());
+    if (attn_fused_launch(&a, B, st)) return set_err("gddim_attention: launch failed");
+    return 0;
+  }
+  if (T <= 64) {
+    if (small_attn_launch((const __half*)qkv16_dev, (__half*)out16_dev, B, T, C, scale, st)) return set_err("gddim_attention: launch failed");
+    return 0;
+  }
+  return set_err("gddim_attention: unsupported shape (T = 256 with C = 256, or T <= 64)");
+}
+
 int gddim_group_norm(const gddim_norm_desc* d, void* stream) {
   if (need_cuda("gddim_group_norm")) return -1;
   if (!d || !d->src1) return set_err("gddim_group_norm: bad arguments");

@@ -1,0 +1,278 @@
+// K2: fused single-head self-attention for the 16x16 level (T = 256 tokens, C = 256 channels) on tcgen05.
+//
+// Replaces, per attention block, the chain  QK^T GEMM (+ row softmax epilogue, P to HBM) -> V transpose -> P.V GEMM
+// that stands in for the two einsums of cld_jax/models/layerspp.py:74-78:
+//     w = softmax_(hw)( einsum('bhwc,bHWc->bhwHW', q, k) * C^-0.5 ),   h = einsum('bhwHW,bHWc->bhwc', w, v)
+// One CTA per (image, 128-query half), 9 warps:
+//   warps 0-7  softmax + epilogue: thread = (query row = TMEM lane, half of the 256 columns; warps w and w + 4 share a
+//              lane quadrant).  S is read from TMEM twice (row max, then exp -> fp16 P written into shared memory in
+//              the K-major 128B-swizzle layout of a UMMA A operand); the two column halves exchange row max / row sum
+//              through shared memory.  O is read from TMEM, scaled by 1/rowsum and transposed through swizzled shared
+//              memory so that every global store covers full 128-byte lines
+//   warp 8     one thread: TMA loads (Q, K per 64-channel block, each with its own barrier so that the first MMAs
+//              start while the rest is still in flight; later V into the shared memory K occupied) and both MMA
+//              sequences
+//              S = Q K^T (K-major B) and O = P V, where V is consumed as it lies in the qkv tensor, [key][channel]:
+//              an MN-major B operand (instruction-descriptor bit 16), so the V^T pass of the unfused chain disappears
+// TMEM: S in columns [0,256), O in [256,512).  Scores and probabilities never leave the SM.
+// Numerics are those of the unfused chain: P = exp2(s*scale*log2e - max) rounded to fp16, row sum taken over the
+// ROUNDED values, O = (P V) / sum in fp32, fp16 output.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.h"
+#include "launch.cuh"
+#include "ptx.cuh"
+
+namespace gddim {
+
+namespace {
+constexpr int AT_T = 256;            // tokens (keys) per image
+constexpr int AT_C = 256;            // channels
+constexpr int AT_Q = 128;            // query rows per CTA
+constexpr int AT_THREADS = 288;
+constexpr int AT_CTRL = 256;         // the TMA + MMA thread
+constexpr int AT_QBLK = AT_Q * 128;  // one 64-channel K-block of Q (or 64-key block of P): 128 rows x 128 B
+constexpr int AT_KBLK = AT_T * 128;  // one 64-channel block of K (K-major) or of V (MN-major): 256 rows x 128 B
+constexpr int AT_OFF_K = 4 * AT_QBLK;
+constexpr int AT_OFF_BAR = AT_OFF_K + 4 * AT_KBLK;
+constexpr int AT_OFF_XCH = AT_OFF_BAR + 128;        // [2 halves][128 rows] row max, then the same for row sums
+constexpr int AT_SMEM = AT_OFF_XCH + 2048 + 1024;   // + alignment slack
+
+// MN-major B operand (V: rows = keys, 128 B = 64 channels per row, 128B swizzle): 8-key groups 1024 B apart (SBO),
+// 64-channel blocks AT_KBLK apart (LBO)
+__device__ __forceinline__ uint64_t desc_v_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(AT_KBLK >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* smem, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(ptx::smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+}  // namespace
+
+struct AttnArgs {
+  __half* out16;     // [B, T, C]
+  float sc;          // C^-0.5 * log2(e)
+  int reverse;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnArgs p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t at_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                  // Q (4 x [128 x 64]), later P (4 x [128 x 64 keys]), later the output staging
+  uint8_t* sK = smem + AT_OFF_K;       // K (4 x [256 x 64]), later V (4 x [256 keys x 64 channels])
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
+  uint64_t* bar_qk = bars;             // [4] Q and K of one 64-channel block landed
+  uint64_t* bar_s = bars + 4;          // S = Q K^T complete (also: Q / K shared memory free)
+  uint64_t* bar_v = bars + 5;          // V landed
+  uint64_t* bar_p = bars + 6;          // P written by the 256 softmax threads
+  uint64_t* bar_o = bars + 7;          // O = P V complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* xch_max = reinterpret_cast<float*>(smem + AT_OFF_XCH);
+  float* xch_sum = xch_max + 2 * AT_Q;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int b = unit >> 1, half = unit & 1;
+
+  if (threadIdx.x == AT_CTRL) {
+    ptx::prefetch_tmap(&tm_qkv);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&bar_qk[i], 1);
+    ptx::mbar_init(bar_s, 1);
+    ptx::mbar_init(bar_v, 1);
+    ptx::mbar_init(bar_p, 256);
+    ptx::mbar_init(bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 8) { __syncwarp(); ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  pdl_wait();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == AT_CTRL) {
+    // ---- Q (this CTA's 128 rows) and K (all 256 keys), one 64-channel block per barrier ----
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      ptx::mbar_arrive_expect_tx(&bar_qk[kb], AT_QBLK + AT_KBLK);
+      tma_load_3d(&tm_qkv, &bar_qk[kb], sQ + kb * AT_QBLK, kb * 64, half * AT_Q, b);
+      tma_load_3d(&tm_qkv, &bar_qk[kb], sK + kb * AT_KBLK, AT_C + kb * 64, 0, b);
+      tma_load_3d(&tm_qkv, &bar_qk[kb], sK + kb * AT_KBLK + AT_QBLK, AT_C + kb * 64, 128, b);
+    }
+    // ---- S[128, 256] = Q K^T ----
+    {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(128, 256);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        ptx::mbar_wait(&bar_qk[kb], 0);
+        ptx::tc_fence_after();
+        const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sQ + kb * AT_QBLK));
+        const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sK + kb * AT_KBLK));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+      }
+      ptx::umma_commit(bar_s);
+    }
+    // ---- V into the shared memory K occupied (free once S is complete) ----
+    ptx::mbar_wait(bar_s, 0);
+    ptx::mbar_arrive_expect_tx(bar_v, 4 * AT_KBLK);
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      tma_load_3d(&tm_qkv, bar_v, sK + nb * AT_KBLK, 2 * AT_C + nb * 64, 0, b);
+      tma_load_3d(&tm_qkv, bar_v, sK + nb * AT_KBLK + AT_QBLK, 2 * AT_C + nb * 64, 128, b);
+    }
+    ptx::mbar_wait(bar_v, 0);
+    ptx::mbar_wait(bar_p, 0);
+    ptx::tc_fence_after();
+    // ---- O[128, 256] = P V : A = P (K-major, 64-key blocks), B = V (MN-major), K = 256 keys in 16 steps ----
+    {
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(128, 256) | (1u << 16);
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sQ + (s >> 2) * AT_QBLK)) + 2 * (s & 3);
+        const uint64_t b_desc = desc_v_mn(ptx::smem_u32(sK + s * 16 * 128));
+        ptx::umma_f16(tmem_base + 256, a_desc, b_desc, idesc, s != 0);
+      }
+      ptx::umma_commit(bar_o);
+    }
+  } else if (warp < 8) {
+    const int quad = warp & 3, ch = warp >> 2;                // TMEM lane quadrant, column half
+    const int row = quad * 32 + lane;                         // query row inside the CTA tile = TMEM lane
+    const uint32_t t_s = tmem_base + (uint32_t(quad * 32) << 16) + ch * 128;
+    uint32_t r[32];
+    ptx::mbar_wait(bar_s, 0);
+    ptx::tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      ptx::tmem_ld_32x32b_x32(t_s + c0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) * p.sc);
+    }
+    xch_max[ch * AT_Q + row] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(mx, xch_max[(ch ^ 1) * AT_Q + row]);
+    float sum = 0.f;
+    const uint32_t p_row = ptx::smem_u32(sQ) + row * 128;
+    const uint32_t sw = row & 7;
+#pragma unroll 1
+    for (int c0 = ch * 128; c0 < ch * 128 + 128; c0 += 32) {
+      ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(quad * 32) << 16) + c0, r);
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        // round to fp16 first so that the row sum matches what the P.V MMA actually consumes
+        v[j] = __half2float(__float2half_rn(exp2f(__uint_as_float(r[j]) * p.sc - mx)));
+        sum += v[j];
+      }
+      // keys c0 .. c0+31 -> 64-key block c0 / 64, 16-byte units (c0 % 64) / 8 .. + 3 of this row (128B swizzle)
+      const uint32_t blk = p_row + (c0 >> 6) * AT_QBLK;
+      const uint32_t u0 = (c0 & 63) >> 3;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t a = blk + (((u0 + u) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_h2(v[8 * u], v[8 * u + 1])),
+                     "r"(pack_h2(v[8 * u + 2], v[8 * u + 3])), "r"(pack_h2(v[8 * u + 4], v[8 * u + 5])),
+                     "r"(pack_h2(v[8 * u + 6], v[8 * u + 7]))
+                     : "memory");
+      }
+    }
+    xch_sum[ch * AT_Q + row] = sum;
+    ptx::fence_proxy_async();          // generic-proxy writes of P -> visible to the tensor core (async proxy)
+    ptx::mbar_arrive(bar_p);
+
+    // ---- epilogue: O / sum -> fp16 -> swizzled staging (this warp: 32 rows x 128 columns) -> full-line stores ----
+    ptx::mbar_wait(bar_o, 0);
+    ptx::tc_fence_after();
+    asm volatile("bar.sync 1, 256;" ::: "memory");            // the other half's row sums are written
+    // fixed order (half 0 + half 1) in both threads of a row: identical scale factors
+    const float inv = 1.0f / (xch_sum[row] + xch_sum[AT_Q + row]);
+    const uint32_t stg = ptx::smem_u32(sQ) + warp * (32 * 256);
+    const uint32_t t_o = tmem_base + (uint32_t(quad * 32) << 16) + 256 + ch * 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      ptx::tmem_ld_32x32b_x32(t_o + c0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t unit16 = (c0 >> 3) + u;                 // 16-byte unit of the 256-byte staging row
+        const uint32_t a = stg + lane * 256 + ((unit16 ^ (lane & 15)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                     "r"(pack_h2(__uint_as_float(r[8 * u]) * inv, __uint_as_float(r[8 * u + 1]) * inv)),
+                     "r"(pack_h2(__uint_as_float(r[8 * u + 2]) * inv, __uint_as_float(r[8 * u + 3]) * inv)),
+                     "r"(pack_h2(__uint_as_float(r[8 * u + 4]) * inv, __uint_as_float(r[8 * u + 5]) * inv)),
+                     "r"(pack_h2(__uint_as_float(r[8 * u + 6]) * inv, __uint_as_float(r[8 * u + 7]) * inv))
+                     : "memory");
+      }
+    }
+    __syncwarp();
+    // two rows per instruction: lanes 0-15 row 2i, lanes 16-31 row 2i + 1, 16 bytes each = 256 contiguous bytes per row
+    __half* obase = p.out16 + ((long long)b * AT_T + half * AT_Q + quad * 32) * AT_C + ch * 128;
+    const int rsel = lane >> 4, unit = lane & 15;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int rr = 2 * i + rsel;
+      uint4 val;
+      const uint32_t a = stg + rr * 256 + ((unit ^ (rr & 15)) << 4);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(a));
+      *reinterpret_cast<uint4*>(obase + (long long)rr * AT_C + unit * 8) = val;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+int attn_fused_supported(int T, int C) { return T == AT_T && C == AT_C; }
+
+int attn_fused_prepare(AttnOp* op) {
+  op->prepared = 0;
+  if (!attn_fused_supported(op->T, op->C)) return -1;
+  const uint64_t dims[3] = {(uint64_t)3 * op->C, (uint64_t)op->T, (uint64_t)op->B};
+  const uint32_t box[3] = {64, (uint32_t)AT_Q, 1};
+  if (tmap_encode_f16(&op->tm_qkv, op->qkv, 3, dims, box)) return -2;
+  op->prepared = 1;
+  return 0;
+}
+
+int attn_fused_launch(const AttnOp* op, int batch, cudaStream_t st) {
+  if (!op->prepared || batch < 1 || batch > op->B) return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(attn256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
+    attr_set = true;
+  }
+  AttnArgs a;
+  a.out16 = op->out16;
+  a.sc = op->scale * 1.4426950408889634f;
+  a.reverse = op->reverse;
+  if (launch_k(attn256_kernel, dim3(2 * batch), dim3(AT_THREADS), (size_t)AT_SMEM, st, op->tm_qkv, a) != cudaSuccess) return -3;
+  return 0;
+}
+
+}  // namespace gddim

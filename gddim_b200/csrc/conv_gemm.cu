@@ -729,6 +729,25 @@ static int encode_4d(CUtensorMap* tm, const void* base, const uint64_t dims[4], 
   return 0;
 }
 
+int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) GEMM_FAIL("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  if (rank < 2 || rank > 4) GEMM_FAIL("tmap_encode_f16: rank %d", rank);
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  cuuint64_t stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i]; bx[i] = box[i];
+    stride *= dims[i];
+    if (i < rank - 1) gstr[i] = stride;
+  }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GEMM_FAIL("cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
+  return 0;
+}
+
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {

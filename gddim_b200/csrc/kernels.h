@@ -72,6 +72,24 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub = 0, int force_c
 int gemm_launch(const GemmOp* op, int impl, cudaStream_t st);
 const char* gemm_last_error();
 
+// 128B-swizzled fp16 tensor map of rank 2..4 over a dense tensor (dims innermost first, box in elements)
+int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box);
+
+// ---- fused attention for T = 256 tokens, C = 256 channels (attn.cu) ------------------------------------------------
+// out16[b, t, :] = softmax_s( q[b,t,:] . k[b,s,:] * scale ) v[b,s,:]   with q, k, v = channel thirds of qkv16 [B, T, 3C]
+struct AttnOp {
+  const __half* qkv;   // [B, T, 3C]
+  __half* out16;       // [B, T, C]
+  int B, T, C;
+  float scale;
+  int reverse;         // CTAs walk the batch in descending order (see GemmOp::reverse)
+  CUtensorMap tm_qkv;  // filled by attn_fused_prepare
+  int prepared;
+};
+int attn_fused_supported(int T, int C);
+int attn_fused_prepare(AttnOp* op);
+int attn_fused_launch(const AttnOp* op, int batch, cudaStream_t st);
+
 // ---- GroupNorm (+SiLU) (+FIR / naive resampling) (norm.cu) ---------------------------------------
 enum { RS_NONE = 0, RS_FIR_DOWN = 1, RS_FIR_UP = 2, RS_NAIVE_DOWN = 3, RS_NAIVE_UP = 4 };
 

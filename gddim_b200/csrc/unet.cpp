@@ -399,7 +399,16 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
   rel(h16);
   T16 o16 = new16(C, H, W);
   const float sm_scale = 1.0f / std::sqrt((float)C);
-  if (T == 256 && C % 64 == 0) {
+  static const bool no_fused_attn = [] { const char* e = getenv("GDDIM_NO_FUSED_ATTN"); return e && e[0] == '1'; }();
+  if (attn_fused_supported(T, C) && !no_fused_attn) {
+    // QK^T -> softmax -> P.V in one kernel (attn.cu): scores / probabilities stay in TMEM / shared memory
+    Op op; op.kind = OP_ATTN_FUSED; op.tag = s.prefix + "attn_fused";
+    op.H = H; op.W = W; op.cout = C; op.T = T;
+    memset(&op.attn, 0, sizeof(op.attn));
+    op.attn.qkv = qkv.p; op.attn.out16 = o16.p; op.attn.B = max_batch_; op.attn.T = T; op.attn.C = C;
+    op.attn.scale = sm_scale;
+    ops_.push_back(op);
+  } else if (T == 256 && C % 64 == 0) {
     T16 p16 = new16(T, H, W);
     T16 vT; vT.C = T; vT.H = C; vT.W = 1; vT.bytes = (size_t)max_batch_ * C * T * 2; vT.p = (__half*)a_alloc(vT.bytes);
     float* rowinv = (float*)a_alloc((size_t)max_batch_ * T * 4);
@@ -796,6 +805,9 @@ int UNet::finalize() {
         n.reverse = zigzag ? !dir_of(n.src1) : 0;
         if (n.dst16) wdir[n.dst16] = n.reverse;
         if (n.raw16) wdir[n.raw16] = n.reverse;
+      } else if (op.kind == OP_ATTN_FUSED) {
+        op.attn.reverse = zigzag ? !dir_of(op.attn.qkv) : 0;
+        wdir[op.attn.out16] = op.attn.reverse;
       } else {
         if (op.f_out) wdir[op.f_out] = 0;
         if (op.h_out) wdir[op.h_out] = 0;
@@ -805,6 +817,8 @@ int UNet::finalize() {
   for (auto& op : ops_) {
     if (op.kind == OP_GEMM) {
       if (gemm_prepare(&op.gemm, 0) != 0) return fail(std::string("gemm_prepare(") + op.tag + "): " + gemm_last_error());
+    } else if (op.kind == OP_ATTN_FUSED) {
+      if (attn_fused_prepare(&op.attn) != 0) return fail(std::string("attn_fused_prepare(") + op.tag + "): " + gemm_last_error());
     }
   }
   if (cudaDeviceSynchronize() != cudaSuccess) return fail("device error during finalize");
@@ -904,6 +918,10 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         rc = softmax_rows_launch(op.f_in, op.h_out, op.f_out, (long long)batch * op.T, op.T, st);
         launches_ += 1;
         break;
+      case OP_ATTN_FUSED:
+        rc = attn_fused_launch(&op.attn, batch, st);
+        launches_ += 1;
+        break;
       case OP_SMALL_ATTN:
         rc = small_attn_launch(op.h_in, op.h_out, batch, op.T, op.cin, op.scale, st);
         launches_ += 1;
@@ -919,6 +937,8 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
       float ms = 0.f;
       cudaEventElapsedTime(&ms, prof_ev_[i], prof_ev_[i + 1]);
       prof_op_ms_[i] += ms;
+      if (ops_[i].kind == OP_ATTN_FUSED)
+        prof_op_flops_[i] = 4.0 * batch * (double)ops_[i].attn.T * ops_[i].attn.T * ops_[i].attn.C;   // QK^T + P.V
       if (ops_[i].kind == OP_GEMM) {
         const GemmOp& g = ops_[i].gemm;
         double k = 0;
@@ -942,7 +962,7 @@ void UNet::get_profile(double ms_by_kind[8], double* gemm_flops, long long* gemm
   double fl = 0;
   long long nl = 0;
   for (size_t i = 0; i < prof_op_ms_.size(); ++i) {
-    ms_by_kind[(int)ops_[i].kind] += prof_op_ms_[i];
+    ms_by_kind[ops_[i].kind == OP_ATTN_FUSED ? (int)OP_SMALL_ATTN : (int)ops_[i].kind] += prof_op_ms_[i];   // one attention family
     if (ops_[i].kind == OP_GEMM) { fl += prof_op_flops_[i] * prof_forwards_; nl += prof_forwards_; }
   }
   if (gemm_flops) *gemm_flops = fl;

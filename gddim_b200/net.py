@@ -168,7 +168,7 @@ class ScoreNet:
     ms = (C.c_double * 8)()
     fl, nl = C.c_double(), C.c_longlong()
     _lib.check(_lib.lib().gddim_ctx_get_profile(self._ctx, ms, C.byref(fl), C.byref(nl)))
-    names = ["stem", "groupnorm", "conv_gemm", "head", "im2col", "transpose_v", "small_attn"]
+    names = ["stem", "groupnorm", "conv_gemm", "head", "im2col", "transpose_v", "attention", "softmax_rows"]
     return {n: ms[i] for i, n in enumerate(names)}, fl.value, nl.value
 
   def dump_profile(self, path):

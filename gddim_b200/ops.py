@@ -85,3 +85,17 @@ def group_norm(x, gamma, beta, groups=None, silu=True, resample=0, x2=None, want
   st = torch.cuda.current_stream().cuda_stream
   _lib.check(_lib.lib().gddim_group_norm(C.byref(d), st), "gddim_group_norm")
   return dst, raw
+
+
+def attention(qkv, scale=None, reverse=0):
+  """qkv: fp16 [B,H,W,3C] (q, k, v channel thirds).  Returns softmax(q k^T * scale) v as fp16 [B,H,W,C]
+  (layerspp.py:74-78).  scale defaults to C^-0.5."""
+  import torch
+  _lib.require_cuda("attention")
+  B, H, W, C3 = qkv.shape
+  Cc = C3 // 3
+  out = torch.empty((B, H, W, Cc), dtype=torch.float16, device="cuda")
+  st = torch.cuda.current_stream().cuda_stream
+  _lib.check(_lib.lib().gddim_attention(_ptr(qkv), _ptr(out), B, H * W, Cc, float(Cc) ** -0.5 if scale is None else scale,
+                                        reverse, st), "gddim_attention")
+  return out

@@ -163,6 +163,12 @@ typedef struct {
 } gddim_norm_desc;
 int gddim_group_norm(const gddim_norm_desc* d, void* stream);
 
+/* Single-head self-attention of AttnBlockpp (cld_jax/models/layerspp.py:74-78: the two einsums around the softmax):
+ * out16[b,t,:] = softmax_s(q[b,t,:] . k[b,s,:] * scale) v[b,s,:], with q, k, v the channel thirds of qkv16 [B,T,3C]
+ * (fp16, device).  T = 256, C = 256: one fused tcgen05 kernel (scores never leave the SM); T <= 64: CUDA-core
+ * kernel; other shapes return an error (the network composes them from gddim_conv_gemm calls). */
+int gddim_attention(const void* qkv16_dev, void* out16_dev, int B, int T, int C, float scale, int reverse, void* stream);
+
 /* ---- samplers ----
  * kind 0: CLD deis (sampling.py:204-253 _impl_deis_sampler / get_deis_sampler)
  * kind 1: CLD order0 (sampling.py:156-202 get_order0_sampler, is_em = 0)

@@ -178,6 +178,42 @@ def test_attention_chain(impl):
   assert rel_l2(o16.float().reshape(B, T, Cc).cpu().numpy(), o_want.numpy()) < 3e-3
 
 
+@pytest.mark.parametrize("B", [1, 3, 8])
+@pytest.mark.parametrize("reverse", [0, 1])
+def test_fused_attention_256(B, reverse):
+  """attn256_kernel (QK^T -> softmax -> P.V, V as an MN-major operand) == softmax(q k^T / sqrt(C)) v, and agrees with
+  the unfused GEMM chain it replaces."""
+  H = W = 16; Cc = 256; T = H * W
+  g = torch.Generator().manual_seed(23 + B)
+  qkv = (torch.randn(B, H, W, 3 * Cc, generator=g) * 0.5).to(torch.float16)
+  qkv[..., :Cc] *= 2.0                                      # peaked rows as well as flat ones
+  qd = qkv.cuda()
+  o = ops.attention(qd, reverse=reverse)
+  q, k, v = [qkv[..., i * Cc:(i + 1) * Cc].double().reshape(B, T, Cc) for i in range(3)]
+  want = torch.einsum("bts,bsc->btc", torch.softmax(torch.einsum("btc,bsc->bts", q, k) * Cc ** -0.5, dim=-1), v)
+  e = rel_l2(o.float().reshape(B, T, Cc).cpu().numpy(), want.numpy())
+  print(f"fused attention B={B}: {e:.2e}")
+  assert e < 2e-3
+  scale = float(Cc) ** -0.5
+  _, p16, rowinv = ops.conv_gemm(qd, qd, T, taps0=1, a0_coff=0, a0_c=Cc, w_ld=3 * Cc, w_koff=Cc,
+                                 w_batch_stride=T * 3 * Cc, w_rows_per_batch=T, scale=scale, epi=1, impl=0)
+  vT = qd[..., 2 * Cc:].reshape(B, T, Cc).transpose(1, 2).contiguous()
+  _, o_chain = ops.conv_gemm(p16, vT, Cc, taps0=1, w_ld=T, w_batch_stride=Cc * T, w_rows_per_batch=Cc,
+                             rowscale=rowinv, out_fp32=False, out_fp16=True, impl=0)
+  assert rel_l2(o.float().cpu().numpy(), o_chain.float().cpu().numpy()) < 5e-4
+
+
+def test_attention_small_and_unsupported():
+  g = torch.Generator().manual_seed(5)
+  qkv = (torch.randn(2, 4, 4, 3 * 256, generator=g) * 0.5).to(torch.float16)
+  o = ops.attention(qkv.cuda())
+  q, k, v = [qkv[..., i * 256:(i + 1) * 256].double().reshape(2, 16, 256) for i in range(3)]
+  want = torch.einsum("bts,bsc->btc", torch.softmax(torch.einsum("btc,bsc->bts", q, k) / 16.0, dim=-1), v)
+  assert rel_l2(o.float().reshape(2, 16, 256).cpu().numpy(), want.numpy()) < 2e-3
+  with pytest.raises(RuntimeError):
+    ops.attention(torch.zeros(1, 16, 8, 3 * 256, dtype=torch.float16, device="cuda"))
+
+
 NORM_CASES = [(2, 32, 32, 128, 0, 0), (2, 16, 16, 256, 128, 0), (2, 16, 16, 128, 64, 0), (3, 8, 8, 256, 0, 1),
               (3, 8, 8, 256, 0, 2), (2, 16, 16, 128, 0, 3), (2, 4, 4, 256, 0, 4), (5, 4, 4, 256, 256, 0),
               (2, 32, 32, 64, 0, 1),
