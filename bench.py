@@ -261,7 +261,7 @@ def run_ours(args):
       traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
       pass
-    roof = {"bound": "tensor", "kernel": "conv_gemm_umma_kernel (all conv3x3 / 1x1 / attention GEMM launches)",
+    roof = {"bound": "tensor", "kernel": "conv_gemm_umma_kernel (all conv3x3 / 1x1 / NIN GEMM launches; the fused QK^T-softmax-PV kernel is the separate 'attention' family)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
             "flop_per_launch": gemm_flops / max(gemm_launches, 1),

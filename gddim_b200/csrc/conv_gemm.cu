@@ -22,6 +22,7 @@
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace gddim {
 
@@ -33,219 +34,6 @@ const char* gemm_last_error() { return g_gemm_err; }
     return -1;                                                  \
   } while (0)
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                       // 64 fp16 = 128 bytes = one swizzle row
-constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int SMEM_BUDGET = 227 * 1024;
-constexpr int NUM_THREADS = 320;
-// Warp roles.  The scheduler prefers the highest warp id among eligible warps of a sub-partition, so the two
-// single-thread roles that must never wait for an issue slot get the highest ids: warps 0-7 epilogue (TMEM lane
-// quadrant = warp id & 3; the two groups of four take alternate 32-column chunks of every tile, so each scheduler
-// has two epilogue warps to hide TMEM / smem / store latency behind each other and a tile drains in half the
-// time), warp 8 TMA producer, warp 9 MMA issuer + TMEM owner.
-constexpr int EPI_WARPS = 8;
-constexpr int EPI_GROUPS = 2;
-constexpr int PRODUCER_THREAD = 256;
-constexpr int MMA_WARP = 9;
-constexpr int MMA_THREAD = 288;
-
-struct GemmArgs {
-  int taps[2], kch[2], coff[2];
-  int nseg;
-  int H, W;
-  int M, N;
-  int m_tiles, n_tiles, tiles_per_batch;
-  int w_koff;
-  const float* bias;
-  const float* bias2;
-  const float* residual;
-  const float* rowscale;
-  float scale;
-  float* out32;
-  __half* out16;
-  float* row_out;
-  int ldo;
-  int n_store;
-  float* colstats;
-  int stages, stage_bytes, a_bytes;   // HALO kernels: smem ring geometry (depends on W)
-  int reverse;   // tiles in descending order (the consumer of a tensor starts with what its producer wrote last: L2 hits)
-  int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
-};
-
-// MT = number of 128-row M sub-tiles a CTA tile covers (2 for narrow N: the weight tile is then shared by 256
-// output rows, which halves the L2->smem operand traffic per FLOP of the N <= 128 layers)
-// CG = CTAs cooperating on one MMA (cta_group): with CG = 2 a cluster of two CTAs computes 256 x BLOCK_N per MMA, each
-// CTA staging its own 128 A rows and HALF of the weight tile -- a third less L2->smem traffic on the N = 256 layers
-template <int BLOCK_N, int MT, int CG = 1>
-struct SmemLayout {
-  static constexpr int B_TILE_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = MT * A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int BAR_BYTES = 256;
-  // epilogue staging: 8 warps x 32 rows x 32 fp32, XOR-swizzled in 16-byte units -- conflict-free 128-bit
-  // transposition without padding (the BLOCK_N = 256 layout has < 1 KB to spare next to four 48 KB stages)
-  static constexpr int EPI_ROW_FLOATS = 32;
-  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_ROW_FLOATS * 4;
-  static constexpr int EPI_BYTES = EPI_STAGE_BYTES + 2 * BLOCK_N * 4;   // + double-buffered (bias + bias2) row
-  static constexpr int AVAIL = SMEM_BUDGET - BAR_BYTES - EPI_BYTES;
-  static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES;   // dynamic smem is declared 1024-aligned
-};
-
-
-// ---- linear epilogue --------------------------------------------------------------------------------------------
-// TMEM -> registers (thread = row) -> swizzled smem -> registers (8 lanes = one 32-column row segment), so that
-// every global access is a full 128-byte line.  Two warps per scheduler run this, so it is written for a low
-// instruction count: the variant (residual / fp32 out / fp16 out / column statistics / row scale / full tile) is a
-// template parameter, and everything that does not depend on the accumulator (bias row, first residual chunk) is
-// fetched before waiting for the MMAs; the residual of chunk q+1 is in flight while chunk q is processed.
-template <int BLOCK_N, int MT>
-struct EpiCtx {
-  const GemmArgs& p;
-  float* stg;
-  float* bias_s;
-  uint64_t* tfull;
-  uint32_t tfull_phase;
-  uint32_t taddr;          // TMEM address of this warp's lane quadrant, first column of the accumulator stage
-  long long m0;            // first row of this warp in sub-tile 0
-  int n_tile0;             // first output column of the tile
-  int lane;
-  int group;               // epilogue group: takes the 32-column chunks q = group, group + 2, ...
-};
-
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-
-template <int BLOCK_N, int MT, bool RES_, bool O32_, bool O16_, bool STATS_, bool RSCALE_, bool FULL, bool GENERIC,
-          bool NARROW = false>
-__device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
-  constexpr int RS = SmemLayout<BLOCK_N, MT>::EPI_ROW_FLOATS;
-  constexpr int NCH = BLOCK_N / 32;
-  constexpr int NQ = MT * NCH;
-  const GemmArgs& p = cx.p;
-  // specialised variants know their features at compile time; the generic one tests the pointers
-  const bool RES = GENERIC ? (p.residual != nullptr) : RES_;
-  const bool O32 = GENERIC ? (p.out32 != nullptr) : O32_;
-  const bool O16 = GENERIC ? (p.out16 != nullptr) : O16_;
-  const bool STATS = GENERIC ? (p.colstats != nullptr) : STATS_;
-  const bool RSCALE = GENERIC ? (p.rowscale != nullptr) : RSCALE_;
-  const int lane = cx.lane;
-  const int rsub = lane >> 3;
-  const int c4 = (lane & 7) * 4;
-  // staging rows are 128 bytes; the 16-byte unit u of row r lives at unit (u ^ (r & 7))
-  const uint32_t stg_w = ptx::smem_u32(cx.stg) + lane * RS * 4;                 // this thread's row (write side)
-  const uint32_t wx = lane & 7;
-  // read side: rows rsub + 4 i, unit lane & 7; (row & 7) alternates between rsub and rsub + 4 with the parity of i
-  const uint32_t stg_r0 = ptx::smem_u32(cx.stg) + rsub * RS * 4 + (((lane & 7) ^ rsub) << 4);
-  const uint32_t stg_r1 = ptx::smem_u32(cx.stg) + (rsub + 4) * RS * 4 + (((lane & 7) ^ (rsub + 4)) << 4);
-  const uint32_t bias_a = ptx::smem_u32(cx.bias_s) + c4 * 4;
-  const long long ldo = p.ldo;
-  const float scale = p.scale;
-
-  auto load_res = [&](int q, float4 (&res)[8]) {
-    const long long mb = cx.m0 + (long long)(q / NCH) * BLOCK_M + rsub;
-    const float* base = p.residual + mb * ldo + cx.n_tile0 + (q % NCH) * 32 + c4;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (FULL || mb + i * 4 < p.M) res[i] = __ldg(reinterpret_cast<const float4*>(base + (long long)(i * 4) * ldo));
-      else res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  float4 res[8];
-  if (RES && cx.group < NQ) load_res(cx.group, res);
-  __syncwarp();
-  ptx::mbar_wait(cx.tfull, cx.tfull_phase);
-  ptx::tc_fence_after();
-  uint32_t r[32];
-  if (p.dbg == 3) return;
-#pragma unroll 1
-  for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
-    const int mi = q / NCH, c0 = (q % NCH) * 32;
-    ptx::tmem_ld_32x32b_x32(cx.taddr + mi * BLOCK_N + c0, r);
-    // residual of this group's next chunk: each float4 is re-loaded in place right after it has been consumed
-    const bool res_more = RES && (q + EPI_GROUPS < NQ);
-    const float* res_nbase = nullptr;
-    long long res_nmb = 0;
-    if (res_more) {
-      const int qn = q + EPI_GROUPS;
-      res_nmb = cx.m0 + (long long)(qn / NCH) * BLOCK_M + rsub;
-      res_nbase = p.residual + res_nmb * ldo + cx.n_tile0 + (qn % NCH) * 32 + c4;
-    }
-    ptx::tmem_ld_wait();
-    if (p.dbg == 1) continue;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ wx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-    __syncwarp();
-    const long long mb = cx.m0 + (long long)mi * BLOCK_M + rsub;                 // this lane's first row
-    const int n0 = cx.n_tile0 + c0 + c4;
-    float4 bsum = lds128(bias_a + c0 * 4);
-    bsum.x *= scale; bsum.y *= scale; bsum.z *= scale; bsum.w *= scale;
-    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
-    float* o32 = O32 ? p.out32 + mb * ldo + n0 : nullptr;
-    __half* o16 = O16 ? p.out16 + mb * ldo + n0 : nullptr;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 v = lds128(((i & 1) ? stg_r1 : stg_r0) + (i >> 1) * 8 * RS * 4);
-      const bool ok = FULL || (mb + i * 4 < p.M);
-      if (RSCALE) {
-        const float rsc = ok ? __ldg(p.rowscale + mb + i * 4) : 1.0f;
-        v.x *= rsc; v.y *= rsc; v.z *= rsc; v.w *= rsc;
-      }
-      if (RES) {
-        v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w;
-        if (res_more) {
-          if (FULL || res_nmb + i * 4 < p.M) res[i] = __ldg(reinterpret_cast<const float4*>(res_nbase + (long long)(i * 4) * ldo));
-          else res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      v.x = fmaf(v.x, scale, bsum.x); v.y = fmaf(v.y, scale, bsum.y);
-      v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
-      if (ok && p.dbg != 2) {
-        if (STATS) {
-          cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-          cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y); cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
-        }
-        if (NARROW) {
-          float* q = o32 + (long long)(i * 4) * ldo;
-          if (n0 + 0 < p.n_store) q[0] = v.x;
-          if (n0 + 1 < p.n_store) q[1] = v.y;
-          if (n0 + 2 < p.n_store) q[2] = v.z;
-          if (n0 + 3 < p.n_store) q[3] = v.w;
-        } else if (O32) *reinterpret_cast<float4*>(o32 + (long long)(i * 4) * ldo) = v;
-        if (O16) {
-          __half2 h0 = __floats2half2_rn(v.x, v.y);
-          __half2 h1 = __floats2half2_rn(v.z, v.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&h0);
-          pk.y = *reinterpret_cast<uint32_t*>(&h1);
-          *reinterpret_cast<uint2*>(o16 + (long long)(i * 4) * ldo) = pk;
-        }
-      }
-    }
-    if (STATS) {
-      // fold the 4 row sub-groups (lanes l, l+8, l+16, l+24): lanes 0..7 then own 32 rows x 4 columns
-#pragma unroll
-      for (int o = 8; o <= 16; o <<= 1) {
-        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
-        cq.x += __shfl_xor_sync(0xffffffffu, cq.x, o); cq.y += __shfl_xor_sync(0xffffffffu, cq.y, o);
-        cq.z += __shfl_xor_sync(0xffffffffu, cq.z, o); cq.w += __shfl_xor_sync(0xffffffffu, cq.w, o);
-      }
-      const long long mrow0 = cx.m0 + (long long)mi * BLOCK_M;
-      if (lane < 8 && (FULL || mrow0 < p.M)) {
-        float* cp = p.colstats + ((mrow0 >> 5) * 2) * ldo + n0;
-        *reinterpret_cast<float4*>(cp) = cs;
-        *reinterpret_cast<float4*>(cp + ldo) = cq;
-      }
-    }
-    __syncwarp();
-  }
-}
 
 // HALO (3x3 convolutions whose CTA tile is a block of whole image rows): one TMA box of (tile rows + 2) image rows is
 // loaded per x-shift and channel block, and the three y-shifted operands are just descriptor start addresses W rows

@@ -19,4 +19,6 @@ ncu --set full --clock-control none --import-source on --kernel-name-base mangle
     -s 45 -c 3 -f -o gpurun_out/prof_gemm128 python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:gn_apply_kernelILi0E \
     -s 160 -c 3 -f -o gpurun_out/prof_gn python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attn256_kernel \
+    -s 11 -c 2 -f -o gpurun_out/prof_attn python tools/prof_forward.py 256 >> gpurun_out/prof.log 2>&1
 tail -3 gpurun_out/prof.log

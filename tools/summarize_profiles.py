@@ -91,7 +91,8 @@ def main():
     shutil.copy(p, os.path.join(OUT, f"{TAG}_gemm_traffic.csv"))
   for rep, title in (("prof_gemm256.ncu-rep", "conv_gemm_umma_kernel<256,0,1,*> (six consecutive N=256 launches of the 16x16 level: 3x3 convs as CTA pairs and the K=256 attention GEMMs; ncu --set full)"),
                      ("prof_gemm128.ncu-rep", "conv_gemm_umma_kernel<128,0,2,2,true> (3x3 conv 128->128 @32x32: 256-row halo tiles, CTA pairs; ncu --set full)"),
-                     ("prof_gn.ncu-rep", "gn_apply_kernel (ncu --set full)")):
+                     ("prof_gn.ncu-rep", "gn_apply_kernel (ncu --set full)"),
+                     ("prof_attn.ncu-rep", "attn256_kernel (fused QK^T -> softmax -> P.V of one 16x16 attention block; ncu --set full)")):
     p = os.path.join(SRC, rep)
     if os.path.exists(p):
       lines.append(f"## {title}\n")
@@ -107,7 +108,7 @@ def main():
       agg[k][0] += 1; agg[k][1] += float(r["ms_per_forward"]); agg[k][2] += float(r["gflop"])
     tot = sum(v[1] for v in agg.values())
     lines.append(f"## per-op CUDA-event timing of one evaluation inside bench.py (eager launches): {tot:.2f} ms\n")
-    lines.append("kind: 0 stem, 1 groupnorm(stats+apply), 2 conv_gemm (tcgen05), 3 head, 4 im2col, 5 transpose_v, 6 small attention\n")
+    lines.append("kind: 0 stem, 1 groupnorm(stats+apply), 2 conv_gemm (tcgen05), 3 head, 4 im2col, 5 transpose_v, 6 small attention, 8 fused attention (tcgen05)\n")
     lines.append("| kind | H=W | N (C_out) | K | block_n | launches | ms | share | TFLOP/s |\n|---|---|---|---|---|---|---|---|---|")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
       tf = f"{v[2]/v[1]:.0f}" if v[2] > 0 and v[1] > 0 else ""
