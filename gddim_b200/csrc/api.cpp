@@ -338,6 +338,23 @@ int gddim_attention(const void* qkv16_dev, void* out16_dev, int B, int T, int C,
   return set_err("gddim_attention: unsupported shape (T = 256 with C = 256, or T <= 64)");
 }
 
+int gddim_attention_proj(const void* qkv16_dev, const void* w3_16_dev, const float* bias3_dev, const float* residual_dev,
+                         float* out32_dev, float* colstats_dev, int B, int T, int C, float scale, float out_scale,
+                         int reverse, void* stream) {
+  if (need_cuda("gddim_attention_proj")) return -1;
+  if (!qkv16_dev || !w3_16_dev || !bias3_dev || !residual_dev || !out32_dev || !colstats_dev || B < 1)
+    return set_err("gddim_attention_proj: bad arguments");
+  if (!attn_fused_supported(T, C)) return set_err("gddim_attention_proj: unsupported shape (T = 256 with C = 256)");
+  AttnOp a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = (const __half*)qkv16_dev; a.B = B; a.T = T; a.C = C; a.scale = scale; a.reverse = reverse;
+  a.w3 = (const __half*)w3_16_dev; a.bias3 = bias3_dev; a.residual = residual_dev; a.out32 = out32_dev;
+  a.colstats = colstats_dev; a.out_scale = out_scale;
+  if (attn_fused_prepare(&a)) return set_err(std::string("gddim_attention_proj: ") + gemm_last_error());
+  if (attn_fused_launch(&a, B, (cudaStream_t)stream)) return set_err("gddim_attention_proj: launch failed");
+  return 0;
+}
+
 int gddim_group_norm(const gddim_norm_desc* d, void* stream) {
   if (need_cuda("gddim_group_norm")) return -1;
   if (!d || !d->src1) return set_err("gddim_group_norm: bad arguments");

@@ -15,6 +15,11 @@
 //              S = Q K^T (K-major B) and O = P V, where V is consumed as it lies in the qkv tensor, [key][channel]:
 //              an MN-major B operand (instruction-descriptor bit 16), so the V^T pass of the unfused chain disappears
 // TMEM: S in columns [0,256), O in [256,512).  Scores and probabilities never leave the SM.
+// PROJ variant (the network path): the block's output projection NIN_3 and the residual (layerspp.py:79-83) run in
+// the same CTA -- O / rowsum is written as the fp16 A operand into the shared memory P occupied, the 256 x 256
+// projection weights stream into the shared memory V occupied, Y = O W3^T accumulates in TMEM columns [0,256) and
+// leaves through the GEMM kernels' own linear epilogue (gemm_epilogue.cuh: bias, residual, 1/sqrt(2), fp32 output,
+// column statistics for the next GroupNorm) -- bit-identical to the separate projection GEMM it replaces.
 // Numerics are those of the unfused chain: P = exp2(s*scale*log2e - max) rounded to fp16, row sum taken over the
 // ROUNDED values, O = (P V) / sum in fp32, fp16 output.
 #include <cstdio>
@@ -24,6 +29,7 @@
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace gddim {
 
@@ -38,7 +44,8 @@ constexpr int AT_KBLK = AT_T * 128;  // one 64-channel block of K (K-major) or o
 constexpr int AT_OFF_K = 4 * AT_QBLK;
 constexpr int AT_OFF_BAR = AT_OFF_K + 4 * AT_KBLK;
 constexpr int AT_OFF_XCH = AT_OFF_BAR + 128;        // [2 halves][128 rows] row max, then the same for row sums
-constexpr int AT_SMEM = AT_OFF_XCH + 2048 + 1024;   // + alignment slack
+constexpr int AT_OFF_BIAS = AT_OFF_XCH + 2048;      // [256] projection bias row (PROJ)
+constexpr int AT_SMEM = AT_OFF_BIAS + 1024 + 1024;  // + alignment slack
 
 // MN-major B operand (V: rows = keys, 128 B = 64 channels per row, 128B swizzle): 8-key groups 1024 B apart (SBO),
 // 64-channel blocks AT_KBLK apart (LBO)
@@ -59,6 +66,9 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, voi
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_(const void* tmap, uint64_t* bar, void* smem, int c0, int c1) {
+  ptx::tma_load_2d(tmap, bar, smem, c0, c1);
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -69,10 +79,13 @@ struct AttnArgs {
   __half* out16;     // [B, T, C]
   float sc;          // C^-0.5 * log2(e)
   int reverse;
+  const float* bias3;   // PROJ: projection bias [C]
+  GemmArgs g;           // PROJ: residual / out32 / colstats / ldo / scale / M of the projection epilogue
 };
 
+template <bool PROJ>
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnArgs p) {
+attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_w3, const AttnArgs p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t at_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -84,7 +97,11 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnArgs p) {
   uint64_t* bar_v = bars + 5;          // V landed
   uint64_t* bar_p = bars + 6;          // P written by the 256 softmax threads
   uint64_t* bar_o = bars + 7;          // O = P V complete
+  uint64_t* bar_w = bars + 9;          // PROJ: projection weights landed
+  uint64_t* bar_o16 = bars + 10;       // PROJ: O / rowsum written as an fp16 A operand by the 256 epilogue threads
+  uint64_t* bar_y = bars + 11;         // PROJ: Y = O W3^T complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* bias_s = reinterpret_cast<float*>(smem + AT_OFF_BIAS);
   float* xch_max = reinterpret_cast<float*>(smem + AT_OFF_XCH);
   float* xch_sum = xch_max + 2 * AT_Q;
 
@@ -99,6 +116,7 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnArgs p) {
     ptx::mbar_init(bar_v, 1);
     ptx::mbar_init(bar_p, 256);
     ptx::mbar_init(bar_o, 1);
+    if (PROJ) { ptx::prefetch_tmap(&tm_w3); ptx::mbar_init(bar_w, 1); ptx::mbar_init(bar_o16, 256); ptx::mbar_init(bar_y, 1); }
     ptx::fence_mbar_init();
   }
   if (warp == 8) { __syncwarp(); ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -152,6 +170,29 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnArgs p) {
         ptx::umma_f16(tmem_base + 256, a_desc, b_desc, idesc, s != 0);
       }
       ptx::umma_commit(bar_o);
+    }
+    if (PROJ) {
+      // ---- projection weights [256 out, 256 in] (K-major, 64-channel blocks) into the shared memory V occupied ----
+      ptx::mbar_wait(bar_o, 0);
+      ptx::mbar_arrive_expect_tx(bar_w, 4 * AT_KBLK);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        tma_load_2d_(&tm_w3, bar_w, sK + kb * AT_KBLK, kb * 64, 0);
+        tma_load_2d_(&tm_w3, bar_w, sK + kb * AT_KBLK + AT_QBLK, kb * 64, 128);
+      }
+      ptx::mbar_wait(bar_w, 0);
+      ptx::mbar_wait(bar_o16, 0);
+      ptx::tc_fence_after();
+      // ---- Y[128, 256] = O W3^T into the TMEM columns S occupied ----
+      constexpr uint32_t idesc = ptx::umma_idesc_f16(128, 256);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const uint64_t a_desc = ptx::umma_desc_sw128(ptx::smem_u32(sQ + kb * AT_QBLK));
+        const uint64_t b_desc = ptx::umma_desc_sw128(ptx::smem_u32(sK + kb * AT_KBLK));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+      }
+      ptx::umma_commit(bar_y);
     }
   } else if (warp < 8) {
     const int quad = warp & 3, ch = warp >> 2;                // TMEM lane quadrant, column half
@@ -207,8 +248,39 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnArgs p) {
     asm volatile("bar.sync 1, 256;" ::: "memory");            // the other half's row sums are written
     // fixed order (half 0 + half 1) in both threads of a row: identical scale factors
     const float inv = 1.0f / (xch_sum[row] + xch_sum[AT_Q + row]);
-    const uint32_t stg = ptx::smem_u32(sQ) + warp * (32 * 256);
     const uint32_t t_o = tmem_base + (uint32_t(quad * 32) << 16) + 256 + ch * 128;
+    if (PROJ) {
+      // O / rowsum -> fp16 A operand of the projection, in the layout P had (64-channel blocks, 128B swizzle)
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        ptx::tmem_ld_32x32b_x32(t_o + c0, r);
+        ptx::tmem_ld_wait();
+        const int cc = ch * 128 + c0;
+        const uint32_t blk = p_row + (cc >> 6) * AT_QBLK;
+        const uint32_t u0 = (cc & 63) >> 3;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t a = blk + (((u0 + u) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                       "r"(pack_h2(__uint_as_float(r[8 * u]) * inv, __uint_as_float(r[8 * u + 1]) * inv)),
+                       "r"(pack_h2(__uint_as_float(r[8 * u + 2]) * inv, __uint_as_float(r[8 * u + 3]) * inv)),
+                       "r"(pack_h2(__uint_as_float(r[8 * u + 4]) * inv, __uint_as_float(r[8 * u + 5]) * inv)),
+                       "r"(pack_h2(__uint_as_float(r[8 * u + 6]) * inv, __uint_as_float(r[8 * u + 7]) * inv))
+                       : "memory");
+        }
+      }
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(bar_o16);
+      bias_s[threadIdx.x] = __ldg(p.bias3 + threadIdx.x);                  // 256 epilogue threads = 256 output columns
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // the GEMM kernels' linear epilogue on this warp's lane quadrant and alternate 32-column chunks; its staging
+      // (4 KB per warp) reuses the A-operand memory, which it touches only after Y is complete
+      float* stg_f = reinterpret_cast<float*>(sQ) + warp * 32 * SmemLayout<256, 1>::EPI_ROW_FLOATS;
+      EpiCtx<256, 1> cx{p.g, stg_f, bias_s, bar_y, 0u, tmem_base + (uint32_t(quad * 32) << 16),
+                        (long long)b * AT_T + half * AT_Q + quad * 32, 0, lane, ch};
+      epi_tile<256, 1, true, true, false, true, false, true, false>(cx);
+    } else {
+    const uint32_t stg = ptx::smem_u32(sQ) + warp * (32 * 256);
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 32) {
       ptx::tmem_ld_32x32b_x32(t_o + c0, r);
@@ -237,6 +309,7 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnArgs p) {
       asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(a));
       *reinterpret_cast<uint4*>(obase + (long long)rr * AT_C + unit * 8) = val;
     }
+    }
   }
 
   ptx::tc_fence_before();
@@ -256,6 +329,13 @@ int attn_fused_prepare(AttnOp* op) {
   const uint64_t dims[3] = {(uint64_t)3 * op->C, (uint64_t)op->T, (uint64_t)op->B};
   const uint32_t box[3] = {64, (uint32_t)AT_Q, 1};
   if (tmap_encode_f16(&op->tm_qkv, op->qkv, 3, dims, box)) return -2;
+  op->tm_w3 = op->tm_qkv;
+  if (op->w3) {
+    if (!op->bias3 || !op->residual || !op->out32 || !op->colstats) return -3;
+    const uint64_t wd[2] = {(uint64_t)op->C, (uint64_t)op->C};          // [C_out rows][C_in] fp16, K-major
+    const uint32_t wb[2] = {64, 128};
+    if (tmap_encode_f16(&op->tm_w3, op->w3, 2, wd, wb)) return -2;
+  }
   op->prepared = 1;
   return 0;
 }
@@ -264,14 +344,23 @@ int attn_fused_launch(const AttnOp* op, int batch, cudaStream_t st) {
   if (!op->prepared || batch < 1 || batch > op->B) return -1;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(attn256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(attn256_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
+    if (cudaFuncSetAttribute(attn256_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
     attr_set = true;
   }
   AttnArgs a;
+  memset(&a, 0, sizeof(a));
   a.out16 = op->out16;
   a.sc = op->scale * 1.4426950408889634f;
   a.reverse = op->reverse;
-  if (launch_k(attn256_kernel, dim3(2 * batch), dim3(AT_THREADS), (size_t)AT_SMEM, st, op->tm_qkv, a) != cudaSuccess) return -3;
+  if (op->w3) {
+    a.bias3 = op->bias3;
+    a.g.residual = op->residual; a.g.out32 = op->out32; a.g.colstats = op->colstats;
+    a.g.ldo = op->C; a.g.scale = op->out_scale; a.g.M = batch * op->T; a.g.N = op->C;
+    if (launch_k(attn256_kernel<true>, dim3(2 * batch), dim3(AT_THREADS), (size_t)AT_SMEM, st, op->tm_qkv, op->tm_w3, a) != cudaSuccess) return -3;
+    return 0;
+  }
+  if (launch_k(attn256_kernel<false>, dim3(2 * batch), dim3(AT_THREADS), (size_t)AT_SMEM, st, op->tm_qkv, op->tm_w3, a) != cudaSuccess) return -3;
   return 0;
 }
 

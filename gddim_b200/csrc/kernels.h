@@ -83,7 +83,15 @@ struct AttnOp {
   int B, T, C;
   float scale;
   int reverse;         // CTAs walk the batch in descending order (see GemmOp::reverse)
-  CUtensorMap tm_qkv;  // filled by attn_fused_prepare
+  // optional fused output projection + residual (AttnBlockpp NIN_3, layerspp.py:79-83):
+  //   out32 = (out @ w3^T + residual) * out_scale + bias3 * out_scale, plus the column statistics of out32
+  const __half* w3;    // [C, C] fp16 K-major ([C_out][C_in]); null = attention only (out16)
+  const float* bias3;  // [C]
+  const float* residual;   // [B, T, C] fp32
+  float* out32;        // [B, T, C]
+  float* colstats;     // [B*T/32][2][C]
+  float out_scale;
+  CUtensorMap tm_qkv, tm_w3;  // filled by attn_fused_prepare
   int prepared;
 };
 int attn_fused_supported(int T, int C);

@@ -400,7 +400,29 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
   T16 o16 = new16(C, H, W);
   const float sm_scale = 1.0f / std::sqrt((float)C);
   static const bool no_fused_attn = [] { const char* e = getenv("GDDIM_NO_FUSED_ATTN"); return e && e[0] == '1'; }();
-  if (attn_fused_supported(T, C) && !no_fused_attn) {
+  static const bool no_fused_proj = [] { const char* e = getenv("GDDIM_NO_FUSED_PROJ"); return e && e[0] == '1'; }();
+  bool proj_fused = false;
+  T32 out_fused{nullptr, 0, 0, 0, 0};
+  if (attn_fused_supported(T, C) && !no_fused_attn && !no_fused_proj) {
+    // ... and the output projection + residual as well: one kernel from qkv to the block output
+    out_fused = new32(C, H, W);
+    Op op; op.kind = OP_ATTN_FUSED; op.tag = s.prefix + "attn_proj_fused";
+    op.H = H; op.W = W; op.cout = C; op.T = T;
+    memset(&op.attn, 0, sizeof(op.attn));
+    op.attn.qkv = qkv.p; op.attn.out16 = nullptr; op.attn.B = max_batch_; op.attn.T = T; op.attn.C = C;
+    op.attn.scale = sm_scale;
+    op.attn.w3 = w3; op.attn.bias3 = b3; op.attn.residual = x.p; op.attn.out32 = out_fused.p;
+    op.attn.colstats = out_fused.stats; op.attn.out_scale = out_scale;
+    if (out_fused.stats != nullptr || dry_) {
+      out_fused.stats_valid = out_fused.stats != nullptr;
+      ops_.push_back(op);
+      proj_fused = true;
+    } else {
+      rel(out_fused);
+    }
+  }
+  if (proj_fused) {
+  } else if (attn_fused_supported(T, C) && !no_fused_attn) {
     // QK^T -> softmax -> P.V in one kernel (attn.cu): scores / probabilities stay in TMEM / shared memory
     Op op; op.kind = OP_ATTN_FUSED; op.tag = s.prefix + "attn_fused";
     op.H = H; op.W = W; op.cout = C; op.T = T;
@@ -492,6 +514,10 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
     return T32{nullptr, 0, 0, 0, 0};
   }
   rel(qkv);
+  if (proj_fused) {
+    rel(o16);
+    return out_fused;
+  }
   T32 out = new32(C, H, W);
   {
     Op op; op.kind = OP_GEMM; op.tag = s.prefix + "proj";
@@ -807,7 +833,8 @@ int UNet::finalize() {
         if (n.raw16) wdir[n.raw16] = n.reverse;
       } else if (op.kind == OP_ATTN_FUSED) {
         op.attn.reverse = zigzag ? !dir_of(op.attn.qkv) : 0;
-        wdir[op.attn.out16] = op.attn.reverse;
+        if (op.attn.out16) wdir[op.attn.out16] = op.attn.reverse;
+        if (op.attn.out32) wdir[op.attn.out32] = op.attn.reverse;
       } else {
         if (op.f_out) wdir[op.f_out] = 0;
         if (op.h_out) wdir[op.h_out] = 0;
@@ -938,7 +965,8 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
       cudaEventElapsedTime(&ms, prof_ev_[i], prof_ev_[i + 1]);
       prof_op_ms_[i] += ms;
       if (ops_[i].kind == OP_ATTN_FUSED)
-        prof_op_flops_[i] = 4.0 * batch * (double)ops_[i].attn.T * ops_[i].attn.T * ops_[i].attn.C;   // QK^T + P.V
+        prof_op_flops_[i] = 4.0 * batch * (double)ops_[i].attn.T * ops_[i].attn.T * ops_[i].attn.C +   // QK^T + P.V
+                            (ops_[i].attn.w3 ? 2.0 * batch * (double)ops_[i].attn.T * ops_[i].attn.C * ops_[i].attn.C : 0.0);
       if (ops_[i].kind == OP_GEMM) {
         const GemmOp& g = ops_[i].gemm;
         double k = 0;

@@ -99,3 +99,20 @@ def attention(qkv, scale=None, reverse=0):
   _lib.check(_lib.lib().gddim_attention(_ptr(qkv), _ptr(out), B, H * W, Cc, float(Cc) ** -0.5 if scale is None else scale,
                                         reverse, st), "gddim_attention")
   return out
+
+
+def attention_proj(qkv, w3, bias3, residual, out_scale=1.0, scale=None, reverse=0):
+  """AttnBlockpp from qkv to the block output in one kernel (T = 256, C = 256): returns (out32 [B,H,W,C],
+  colstats [B*H*W/32, 2, C]) with out32 = (attention(qkv) @ w3^T + residual) * out_scale + bias3 * out_scale.
+  w3: fp16 [C_out, C_in]."""
+  import torch
+  _lib.require_cuda("attention_proj")
+  B, H, W, C3 = qkv.shape
+  Cc = C3 // 3
+  out = torch.empty((B, H, W, Cc), dtype=torch.float32, device="cuda")
+  stats = torch.empty((B * H * W // 32, 2, Cc), dtype=torch.float32, device="cuda")
+  st = torch.cuda.current_stream().cuda_stream
+  _lib.check(_lib.lib().gddim_attention_proj(_ptr(qkv), _ptr(w3), _ptr(bias3), _ptr(residual), _ptr(out), _ptr(stats), B,
+                                             H * W, Cc, float(Cc) ** -0.5 if scale is None else scale, out_scale, reverse, st),
+             "gddim_attention_proj")
+  return out, stats

@@ -168,6 +168,13 @@ int gddim_group_norm(const gddim_norm_desc* d, void* stream);
  * (fp16, device).  T = 256, C = 256: one fused tcgen05 kernel (scores never leave the SM); T <= 64: CUDA-core
  * kernel; other shapes return an error (the network composes them from gddim_conv_gemm calls). */
 int gddim_attention(const void* qkv16_dev, void* out16_dev, int B, int T, int C, float scale, int reverse, void* stream);
+/* The same plus the block's output projection and residual (NIN_3 and `x + h`, layerspp.py:79-83) in one kernel
+ * (T = 256, C = 256 only): out32 = (attention(qkv) @ w3^T + residual) * out_scale + bias3 * out_scale, and the
+ * per-32-row column statistics of out32 (colstats [B*T/32][2][C]: sums, sums of squares) for the next GroupNorm.
+ * w3: fp16 [C_out][C_in] (K-major), bias3 [C], residual / out32 fp32 [B,T,C]; all device pointers. */
+int gddim_attention_proj(const void* qkv16_dev, const void* w3_16_dev, const float* bias3_dev, const float* residual_dev,
+                         float* out32_dev, float* colstats_dev, int B, int T, int C, float scale, float out_scale,
+                         int reverse, void* stream);
 
 /* ---- samplers ----
  * kind 0: CLD deis (sampling.py:204-253 _impl_deis_sampler / get_deis_sampler)

@@ -203,6 +203,32 @@ def test_fused_attention_256(B, reverse):
   assert rel_l2(o.float().cpu().numpy(), o_chain.float().cpu().numpy()) < 5e-4
 
 
+@pytest.mark.parametrize("B,reverse", [(2, 0), (5, 1)])
+def test_fused_attention_projection(B, reverse):
+  """attn256_kernel<PROJ>: attention + NIN_3 + residual + 1/sqrt(2) + column statistics in one kernel == the fused
+  attention kernel followed by the projection GEMM, bit for bit (it runs the same epilogue code)."""
+  H = W = 16; Cc = 256; T = H * W
+  g = torch.Generator().manual_seed(31 + B)
+  qkv = (torch.randn(B, H, W, 3 * Cc, generator=g) * 0.5).to(torch.float16).cuda()
+  k3 = (torch.randn(1, 1, Cc, Cc, generator=g) / np.sqrt(Cc)).numpy()
+  w3 = ops.pack_conv_weight(k3)                               # fp16 [C_out, C_in]
+  b3 = torch.randn(Cc, generator=g).cuda()
+  x = torch.randn(B, H, W, Cc, generator=g).cuda()
+  sc = float(1.0 / np.sqrt(2.0))
+  out, stats = ops.attention_proj(qkv, w3, b3, x, out_scale=sc, reverse=reverse)
+  o16 = ops.attention(qkv)
+  want, _ = ops.conv_gemm(o16, w3, Cc, taps0=1, bias=b3, residual=x, scale=sc, impl=0)
+  assert torch.equal(out, want)
+  slabs = out.reshape(B * T // 32, 32, Cc).double()
+  assert rel_l2(stats[:, 0].cpu().numpy(), slabs.sum(1).cpu().numpy()) < 1e-6
+  assert rel_l2(stats[:, 1].cpu().numpy(), (slabs * slabs).sum(1).cpu().numpy()) < 1e-6
+  # and against the definition
+  q, k, v = [qkv[..., i * Cc:(i + 1) * Cc].double().reshape(B, T, Cc).cpu() for i in range(3)]
+  h = torch.einsum("bts,bsc->btc", torch.softmax(torch.einsum("btc,bsc->bts", q, k) * Cc ** -0.5, dim=-1), v)
+  ref = (h @ torch.as_tensor(k3[0, 0]).to(torch.float16).double() + b3.cpu().double() + x.reshape(B, T, Cc).cpu().double()) * sc
+  assert rel_l2(out.reshape(B, T, Cc).cpu().numpy(), ref.numpy()) < 1e-3
+
+
 def test_attention_small_and_unsupported():
   g = torch.Generator().manual_seed(5)
   qkv = (torch.randn(2, 4, 4, 3 * 256, generator=g) * 0.5).to(torch.float16)
