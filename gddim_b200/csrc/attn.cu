@@ -66,12 +66,18 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, voi
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_(const void* tmap, uint64_t* bar, void* smem, int c0, int c1) {
-  ptx::tma_load_2d(tmap, bar, smem, c0, c1);
-}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+// eight fp32 accumulator values r[0..7] * s -> eight fp16 -> one 16-byte shared-memory store
+__device__ __forceinline__ void sts_scaled8(uint32_t addr, const uint32_t* r, float s) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+               "r"(pack_h2(__uint_as_float(r[0]) * s, __uint_as_float(r[1]) * s)),
+               "r"(pack_h2(__uint_as_float(r[2]) * s, __uint_as_float(r[3]) * s)),
+               "r"(pack_h2(__uint_as_float(r[4]) * s, __uint_as_float(r[5]) * s)),
+               "r"(pack_h2(__uint_as_float(r[6]) * s, __uint_as_float(r[7]) * s))
+               : "memory");
 }
 }  // namespace
 
@@ -177,8 +183,8 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
       ptx::mbar_arrive_expect_tx(bar_w, 4 * AT_KBLK);
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
-        tma_load_2d_(&tm_w3, bar_w, sK + kb * AT_KBLK, kb * 64, 0);
-        tma_load_2d_(&tm_w3, bar_w, sK + kb * AT_KBLK + AT_QBLK, kb * 64, 128);
+        ptx::tma_load_2d(&tm_w3, bar_w, sK + kb * AT_KBLK, kb * 64, 0);
+        ptx::tma_load_2d(&tm_w3, bar_w, sK + kb * AT_KBLK + AT_QBLK, kb * 64, 128);
       }
       ptx::mbar_wait(bar_w, 0);
       ptx::mbar_wait(bar_o16, 0);
@@ -242,7 +248,7 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
     ptx::fence_proxy_async();          // generic-proxy writes of P -> visible to the tensor core (async proxy)
     ptx::mbar_arrive(bar_p);
 
-    // ---- epilogue: O / sum -> fp16 -> swizzled staging (this warp: 32 rows x 128 columns) -> full-line stores ----
+    // ---- epilogue ----
     ptx::mbar_wait(bar_o, 0);
     ptx::tc_fence_after();
     asm volatile("bar.sync 1, 256;" ::: "memory");            // the other half's row sums are written
@@ -259,15 +265,7 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
         const uint32_t blk = p_row + (cc >> 6) * AT_QBLK;
         const uint32_t u0 = (cc & 63) >> 3;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t a = blk + (((u0 + u) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
-                       "r"(pack_h2(__uint_as_float(r[8 * u]) * inv, __uint_as_float(r[8 * u + 1]) * inv)),
-                       "r"(pack_h2(__uint_as_float(r[8 * u + 2]) * inv, __uint_as_float(r[8 * u + 3]) * inv)),
-                       "r"(pack_h2(__uint_as_float(r[8 * u + 4]) * inv, __uint_as_float(r[8 * u + 5]) * inv)),
-                       "r"(pack_h2(__uint_as_float(r[8 * u + 6]) * inv, __uint_as_float(r[8 * u + 7]) * inv))
-                       : "memory");
-        }
+        for (int u = 0; u < 4; ++u) sts_scaled8(blk + (((u0 + u) ^ sw) << 4), r + 8 * u, inv);
       }
       ptx::fence_proxy_async();
       ptx::mbar_arrive(bar_o16);
@@ -280,35 +278,28 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
                         (long long)b * AT_T + half * AT_Q + quad * 32, 0, lane, ch};
       epi_tile<256, 1, true, true, false, true, false, true, false>(cx);
     } else {
-    const uint32_t stg = ptx::smem_u32(sQ) + warp * (32 * 256);
+      // O / rowsum -> fp16 -> swizzled staging (this warp: 32 rows x 128 columns) -> full-line global stores
+      const uint32_t stg = ptx::smem_u32(sQ) + warp * (32 * 256);
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-      ptx::tmem_ld_32x32b_x32(t_o + c0, r);
-      ptx::tmem_ld_wait();
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        ptx::tmem_ld_32x32b_x32(t_o + c0, r);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t unit16 = (c0 >> 3) + u;                 // 16-byte unit of the 256-byte staging row
-        const uint32_t a = stg + lane * 256 + ((unit16 ^ (lane & 15)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
-                     "r"(pack_h2(__uint_as_float(r[8 * u]) * inv, __uint_as_float(r[8 * u + 1]) * inv)),
-                     "r"(pack_h2(__uint_as_float(r[8 * u + 2]) * inv, __uint_as_float(r[8 * u + 3]) * inv)),
-                     "r"(pack_h2(__uint_as_float(r[8 * u + 4]) * inv, __uint_as_float(r[8 * u + 5]) * inv)),
-                     "r"(pack_h2(__uint_as_float(r[8 * u + 6]) * inv, __uint_as_float(r[8 * u + 7]) * inv))
-                     : "memory");
+        for (int u = 0; u < 4; ++u)       // 16-byte unit (c0 / 8 + u) of the 256-byte staging row
+          sts_scaled8(stg + lane * 256 + ((((c0 >> 3) + u) ^ (lane & 15)) << 4), r + 8 * u, inv);
       }
-    }
-    __syncwarp();
-    // two rows per instruction: lanes 0-15 row 2i, lanes 16-31 row 2i + 1, 16 bytes each = 256 contiguous bytes per row
-    __half* obase = p.out16 + ((long long)b * AT_T + half * AT_Q + quad * 32) * AT_C + ch * 128;
-    const int rsel = lane >> 4, unit = lane & 15;
+      __syncwarp();
+      // two rows per instruction: lanes 0-15 row 2i, lanes 16-31 row 2i + 1, 16 bytes each = 256 contiguous bytes per row
+      __half* obase = p.out16 + ((long long)b * AT_T + half * AT_Q + quad * 32) * AT_C + ch * 128;
+      const int rsel = lane >> 4, unit = lane & 15;
 #pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const int rr = 2 * i + rsel;
-      uint4 val;
-      const uint32_t a = stg + rr * 256 + ((unit ^ (rr & 15)) << 4);
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(a));
-      *reinterpret_cast<uint4*>(obase + (long long)rr * AT_C + unit * 8) = val;
-    }
+      for (int i = 0; i < 16; ++i) {
+        const int rr = 2 * i + rsel;
+        uint4 val;
+        const uint32_t a = stg + rr * 256 + ((unit ^ (rr & 15)) << 4);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(a));
+        *reinterpret_cast<uint4*>(obase + (long long)rr * AT_C + unit * 8) = val;
+      }
     }
   }
 
