@@ -101,6 +101,7 @@ SIGNATURES = {
     "gddim_conv_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "gddim_group_norm": (C.c_int, [C.POINTER(NormDesc), _P]),
     "gddim_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
+    "gddim_gn_qkv": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "gddim_attention_proj": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _P]),
     "gddim_sampler_create": (C.c_int, [_P, C.POINTER(SamplerCfg), _P, _P, C.POINTER(_P)]),
     "gddim_sampler_create_ts": (C.c_int, [_P, C.POINTER(SamplerCfg), _P, _P, _P, C.c_int, C.POINTER(_P)]),

@@ -355,6 +355,40 @@ int gddim_attention_proj(const void* qkv16_dev, const void* w3_16_dev, const flo
   return 0;
 }
 
+int gddim_gn_qkv(const float* x_dev, const float* gamma_dev, const float* beta_dev, int groups, float eps,
+                 const void* w16_dev, const float* bias_dev, void* out16_dev, int B, int T, int C, int N, int reverse,
+                 void* stream) {
+  if (need_cuda("gddim_gn_qkv")) return -1;
+  if (!x_dev || !gamma_dev || !beta_dev || !w16_dev || !bias_dev || !out16_dev || B < 1 || groups < 1)
+    return set_err("gddim_gn_qkv: bad arguments");
+  if (!gn_qkv_supported(T, C, N)) return set_err("gddim_gn_qkv: unsupported shape (C = 256, N = 768, T % 128 == 0)");
+  cudaStream_t st = (cudaStream_t)stream;
+  NormOp n;
+  memset(&n, 0, sizeof(n));
+  n.src1 = x_dev; n.c1 = C; n.B = B; n.H = T; n.W = 1; n.groups = groups; n.gamma = gamma_dev; n.beta = beta_dev; n.eps = eps;
+  n.coef_only = 1;
+  n.splits = norm_splits(B, T, 1);
+  char* scratch = nullptr;
+  const size_t nb_part = (size_t)B * n.splits * groups * 2 * sizeof(float);
+  const size_t nb_coef = (size_t)B * 2 * C * sizeof(float);
+  const size_t nb_tick = (size_t)B * sizeof(unsigned int);
+  if (cudaMallocAsync(&scratch, nb_part + nb_coef + nb_tick, st) != cudaSuccess) return set_err("gddim_gn_qkv: scratch allocation failed");
+  n.partial = (float*)scratch;
+  n.coef = (float*)(scratch + nb_part);
+  n.ticket = (unsigned int*)(scratch + nb_part + nb_coef);
+  cudaMemsetAsync(n.ticket, 0, nb_tick, st);
+  int rc = norm_launch(&n, st);
+  GnQkvOp q;
+  memset(&q, 0, sizeof(q));
+  q.x = x_dev; q.coef = n.coef; q.w = (const __half*)w16_dev; q.bias = bias_dev; q.out16 = (__half*)out16_dev;
+  q.B = B; q.T = T; q.C = C; q.N = N; q.reverse = reverse;
+  if (!rc) rc = gn_qkv_prepare(&q) ? -100 : 0;
+  if (!rc) rc = gn_qkv_launch(&q, B, st) ? -101 : 0;
+  cudaFreeAsync(scratch, st);
+  if (rc) return set_err("gddim_gn_qkv: launch failure (rc=" + std::to_string(rc) + ")");
+  return 0;
+}
+
 int gddim_group_norm(const gddim_norm_desc* d, void* stream) {
   if (need_cuda("gddim_group_norm")) return -1;
   if (!d || !d->src1) return set_err("gddim_group_norm: bad arguments");

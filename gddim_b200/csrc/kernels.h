@@ -98,6 +98,23 @@ int attn_fused_supported(int T, int C);
 int attn_fused_prepare(AttnOp* op);
 int attn_fused_launch(const AttnOp* op, int batch, cudaStream_t st);
 
+// ---- GroupNorm apply fused into the q/k/v projection (gn_qkv.cu; C = 256, N = 768, T % 128 == 0) ----------------------
+// out16[m, :] = fp16(x[m, :] * coef_a[b(m), :] + coef_b[b(m), :]) @ w^T + bias, with coef from a coef_only NormOp
+struct GnQkvOp {
+  const float* x;      // [B, T, C] fp32
+  const float* coef;   // [B, 2, C]
+  const __half* w;     // [N, C] fp16 K-major
+  const float* bias;   // [N]
+  __half* out16;       // [B, T, N]
+  int B, T, C, N;
+  int reverse;
+  CUtensorMap tm_w;    // filled by gn_qkv_prepare
+  int prepared;
+};
+int gn_qkv_supported(int T, int C, int N);
+int gn_qkv_prepare(GnQkvOp* op);
+int gn_qkv_launch(const GnQkvOp* op, int batch, cudaStream_t st);
+
 // ---- GroupNorm (+SiLU) (+FIR / naive resampling) (norm.cu) ---------------------------------------
 enum { RS_NONE = 0, RS_FIR_DOWN = 1, RS_FIR_UP = 2, RS_NAIVE_DOWN = 3, RS_NAIVE_UP = 4 };
 
@@ -120,6 +137,7 @@ struct NormOp {
   __half* raw16;                 // raw (resampled) copy of the input in fp16; may be null
   float raw_scale;               // raw16 = x * raw_scale (power of two: headroom against fp16 overflow)
   int reverse;                   // apply pass walks images / pixel chunks in descending order (see GemmOp::reverse)
+  int coef_only;                 // compute the scale / shift table `coef` only; the consumer applies it (gn_qkv.cu)
 };
 int norm_launch(const NormOp* op, cudaStream_t st);
 int norm_num_launches(const NormOp* op);   // kernels norm_launch issues for this op (1 or 2)

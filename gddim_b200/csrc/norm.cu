@@ -451,6 +451,7 @@ static int small_rows(const NormOp* op) {
 }
 
 int norm_num_launches(const NormOp* op) {
+  if (op->coef_only) return 1;
   if (small_rows(op) > 0) return 1;
   return op->dst16 ? 2 : 1;
 }
@@ -485,7 +486,7 @@ static int small_launch(const NormOp* op, cudaStream_t st) {
 
 int norm_launch(const NormOp* op, cudaStream_t st) {
   const int C = op->c1 + op->c2;
-  const int do_norm = op->dst16 != nullptr;
+  const int do_norm = op->dst16 != nullptr || op->coef_only;
   if (C % 8 != 0 || op->c1 % 8 != 0 || C > 2048) return -1;
   const int P = op->H * op->W;
   if (small_launch(op, st) == 0) return cudaGetLastError() == cudaSuccess ? 0 : -4;
@@ -530,6 +531,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     dim3 grid(op->splits, op->B);
     launch_k(gn_stats_kernel, dim3(grid), dim3(threads), threads * 8 * sizeof(float), st, s);
   }
+  if (op->coef_only) return cudaGetLastError() == cudaSuccess ? 0 : -4;
   ApplyArgs a;
   a.src1 = op->src1; a.c1 = op->c1; a.src2 = op->src2; a.c2 = op->c2;
   a.H = op->H; a.W = op->W;

@@ -354,8 +354,17 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
   const int C = x.C, H = x.H, W = x.W, T = H * W;
   const float out_scale = cfg_.skip_rescale ? (float)(1.0 / std::sqrt(2.0)) : 1.f;
   auto gn = gn_params(s, C);
-  T16 h16 = new16(C, H, W);
-  add_norm(x, nullptr, gn.first, gn.second, false, RS_NONE, &h16, nullptr, s.prefix + "gn");
+  // GroupNorm apply fused into the q/k/v projection (gn_qkv.cu): only the coefficient table is computed here
+  static const bool no_gnqkv = [] { const char* e = getenv("GDDIM_NO_FUSED_GNQKV"); return e && e[0] == '1'; }();
+  const bool gnqkv = gn_qkv_supported(T, C, 3 * C) && x.stats_valid && !no_gnqkv;
+  T16 h16{nullptr, 0, 0, 0, 0};
+  if (gnqkv) {
+    add_norm(x, nullptr, gn.first, gn.second, false, RS_NONE, nullptr, nullptr, s.prefix + "gn_coef");
+    ops_.back().norm.coef_only = 1;
+  } else {
+    h16 = new16(C, H, W);
+    add_norm(x, nullptr, gn.first, gn.second, false, RS_NONE, &h16, nullptr, s.prefix + "gn");
+  }
 
   const std::vector<float>* nw[4];
   const std::vector<float>* nb[4];
@@ -387,7 +396,14 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
     b3 = upload_f32(*nb[3]);
   }
   T16 qkv = new16(3 * C, H, W);
-  {
+  if (gnqkv) {
+    Op op; op.kind = OP_GN_QKV; op.tag = s.prefix + "gn_qkv";
+    op.H = H; op.W = W; op.cout = 3 * C; op.T = T;
+    memset(&op.gq, 0, sizeof(op.gq));
+    op.gq.x = x.p; op.gq.coef = gn_coef_; op.gq.w = wqkv; op.gq.bias = bqkv; op.gq.out16 = qkv.p;
+    op.gq.B = max_batch_; op.gq.T = T; op.gq.C = C; op.gq.N = 3 * C;
+    ops_.push_back(op);
+  } else {
     Op op; op.kind = OP_GEMM; op.tag = s.prefix + "qkv";
     op.gemm = make_gemm(max_batch_, H, W);
     GemmOp& g = op.gemm;
@@ -831,6 +847,9 @@ int UNet::finalize() {
         n.reverse = zigzag ? !dir_of(n.src1) : 0;
         if (n.dst16) wdir[n.dst16] = n.reverse;
         if (n.raw16) wdir[n.raw16] = n.reverse;
+      } else if (op.kind == OP_GN_QKV) {
+        op.gq.reverse = zigzag ? !dir_of(op.gq.x) : 0;
+        wdir[op.gq.out16] = op.gq.reverse;
       } else if (op.kind == OP_ATTN_FUSED) {
         op.attn.reverse = zigzag ? !dir_of(op.attn.qkv) : 0;
         if (op.attn.out16) wdir[op.attn.out16] = op.attn.reverse;
@@ -844,6 +863,8 @@ int UNet::finalize() {
   for (auto& op : ops_) {
     if (op.kind == OP_GEMM) {
       if (gemm_prepare(&op.gemm, 0) != 0) return fail(std::string("gemm_prepare(") + op.tag + "): " + gemm_last_error());
+    } else if (op.kind == OP_GN_QKV) {
+      if (gn_qkv_prepare(&op.gq) != 0) return fail(std::string("gn_qkv_prepare(") + op.tag + "): " + gemm_last_error());
     } else if (op.kind == OP_ATTN_FUSED) {
       if (attn_fused_prepare(&op.attn) != 0) return fail(std::string("attn_fused_prepare(") + op.tag + "): " + gemm_last_error());
     }
@@ -945,6 +966,10 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         rc = softmax_rows_launch(op.f_in, op.h_out, op.f_out, (long long)batch * op.T, op.T, st);
         launches_ += 1;
         break;
+      case OP_GN_QKV:
+        rc = gn_qkv_launch(&op.gq, batch, st);
+        launches_ += 1;
+        break;
       case OP_ATTN_FUSED:
         rc = attn_fused_launch(&op.attn, batch, st);
         launches_ += 1;
@@ -964,6 +989,8 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
       float ms = 0.f;
       cudaEventElapsedTime(&ms, prof_ev_[i], prof_ev_[i + 1]);
       prof_op_ms_[i] += ms;
+      if (ops_[i].kind == OP_GN_QKV)
+        prof_op_flops_[i] = 2.0 * batch * (double)ops_[i].gq.T * ops_[i].gq.C * ops_[i].gq.N;
       if (ops_[i].kind == OP_ATTN_FUSED)
         prof_op_flops_[i] = 4.0 * batch * (double)ops_[i].attn.T * ops_[i].attn.T * ops_[i].attn.C +   // QK^T + P.V
                             (ops_[i].attn.w3 ? 2.0 * batch * (double)ops_[i].attn.T * ops_[i].attn.C * ops_[i].attn.C : 0.0);
@@ -990,7 +1017,9 @@ void UNet::get_profile(double ms_by_kind[8], double* gemm_flops, long long* gemm
   double fl = 0;
   long long nl = 0;
   for (size_t i = 0; i < prof_op_ms_.size(); ++i) {
-    ms_by_kind[ops_[i].kind == OP_ATTN_FUSED ? (int)OP_SMALL_ATTN : (int)ops_[i].kind] += prof_op_ms_[i];   // one attention family
+    const OpKind k = ops_[i].kind;       // one attention family; the GroupNorm-fused projection counts as a GEMM
+    ms_by_kind[k == OP_ATTN_FUSED ? (int)OP_SMALL_ATTN : (k == OP_GN_QKV ? (int)OP_GEMM : (int)k)] += prof_op_ms_[i];
+    if (k == OP_GN_QKV) { fl += prof_op_flops_[i] * prof_forwards_; nl += prof_forwards_; }
     if (ops_[i].kind == OP_GEMM) { fl += prof_op_flops_[i] * prof_forwards_; nl += prof_forwards_; }
   }
   if (gemm_flops) *gemm_flops = fl;

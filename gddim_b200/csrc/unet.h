@@ -19,13 +19,14 @@ struct ParamSpec {
   float scale;
 };
 
-enum OpKind { OP_STEM, OP_NORM, OP_GEMM, OP_HEAD, OP_IM2COL, OP_TRANSPOSE_V, OP_SMALL_ATTN, OP_SOFTMAX_ROWS, OP_ATTN_FUSED };
+enum OpKind { OP_STEM, OP_NORM, OP_GEMM, OP_HEAD, OP_IM2COL, OP_TRANSPOSE_V, OP_SMALL_ATTN, OP_SOFTMAX_ROWS, OP_ATTN_FUSED, OP_GN_QKV };
 
 struct Op {
   OpKind kind;
   NormOp norm;
   GemmOp gemm;
   AttnOp attn;
+  GnQkvOp gq;
   // generic fields for the small kernels
   const float* f_in = nullptr;
   const __half* h_in = nullptr;

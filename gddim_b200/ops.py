@@ -116,3 +116,16 @@ def attention_proj(qkv, w3, bias3, residual, out_scale=1.0, scale=None, reverse=
                                              H * W, Cc, float(Cc) ** -0.5 if scale is None else scale, out_scale, reverse, st),
              "gddim_attention_proj")
   return out, stats
+
+
+def gn_qkv(x, gamma, beta, w, bias, groups=None, eps=1e-6, reverse=0):
+  """fp16(GroupNorm(x)) @ w^T + bias in one kernel (layerspp.py:69-72).  x fp32 [B,H,W,256], w fp16 [768,256]."""
+  import torch
+  _lib.require_cuda("gn_qkv")
+  B, H, W, Cc = x.shape
+  N = w.shape[0]
+  out = torch.empty((B, H, W, N), dtype=torch.float16, device="cuda")
+  st = torch.cuda.current_stream().cuda_stream
+  _lib.check(_lib.lib().gddim_gn_qkv(_ptr(x), _ptr(gamma), _ptr(beta), min(Cc // 4, 32) if groups is None else groups, eps,
+                                     _ptr(w), _ptr(bias), _ptr(out), B, H * W, Cc, N, reverse, st), "gddim_gn_qkv")
+  return out

@@ -176,6 +176,13 @@ int gddim_attention_proj(const void* qkv16_dev, const void* w3_16_dev, const flo
                          float* out32_dev, float* colstats_dev, int B, int T, int C, float scale, float out_scale,
                          int reverse, void* stream);
 
+/* GroupNorm (no activation) fused into a following pointwise projection, the head of AttnBlockpp (layerspp.py:69-72):
+ * out16 = fp16(GroupNorm(x)) @ w^T + bias, x fp32 [B,T,C], w fp16 [N][C] (K-major), out16 fp16 [B,T,N].
+ * C = 256, N = 768, T a multiple of 128; the normalised tensor never reaches HBM. */
+int gddim_gn_qkv(const float* x_dev, const float* gamma_dev, const float* beta_dev, int groups, float eps,
+                 const void* w16_dev, const float* bias_dev, void* out16_dev, int B, int T, int C, int N, int reverse,
+                 void* stream);
+
 /* ---- samplers ----
  * kind 0: CLD deis (sampling.py:204-253 _impl_deis_sampler / get_deis_sampler)
  * kind 1: CLD order0 (sampling.py:156-202 get_order0_sampler, is_em = 0)

@@ -229,6 +229,26 @@ def test_fused_attention_projection(B, reverse):
   assert rel_l2(out.reshape(B, T, Cc).cpu().numpy(), ref.numpy()) < 1e-3
 
 
+@pytest.mark.parametrize("B,reverse", [(1, 0), (3, 1), (8, 0)])
+def test_gn_fused_into_qkv_projection(B, reverse):
+  """gn_qkv_kernel: GroupNorm apply in the A-operand path of the q/k/v projection == gn_apply followed by the N = 768
+  GEMM, bit for bit (same x*a+b, same fp16 rounding, same accumulation order, same epilogue)."""
+  H = W = 16; Cc = 256
+  g = torch.Generator().manual_seed(41 + B)
+  x = (torch.randn(B, H, W, Cc, generator=g) * 1.7 + 0.2).cuda()
+  gamma, beta = (1 + 0.1 * torch.randn(Cc, generator=g)).cuda(), (0.1 * torch.randn(Cc, generator=g)).cuda()
+  k = (torch.randn(1, 1, Cc, 3 * Cc, generator=g) / np.sqrt(Cc)).numpy()
+  w = ops.pack_conv_weight(k)
+  bias = torch.randn(3 * Cc, generator=g).cuda()
+  got = ops.gn_qkv(x, gamma, beta, w, bias, reverse=reverse)
+  h16, _ = ops.group_norm(x, gamma, beta, silu=False)
+  _, want = ops.conv_gemm(h16, w, 3 * Cc, taps0=1, bias=bias, out_fp32=False, out_fp16=True, impl=0)
+  assert torch.equal(got, want)
+  hn = F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), eps=1e-6).permute(0, 2, 3, 1)
+  ref = hn.cpu() @ torch.as_tensor(k[0, 0]).double() + bias.cpu().double()
+  assert rel_l2(got.float().cpu().numpy(), ref.numpy()) < 1e-3
+
+
 def test_attention_small_and_unsupported():
   g = torch.Generator().manual_seed(5)
   qkv = (torch.randn(2, 4, 4, 3 * 256, generator=g) * 0.5).to(torch.float16)
