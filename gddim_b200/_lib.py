@@ -72,6 +72,8 @@ SIGNATURES = {
     "gddim_ctx_set_gemm_impl": (C.c_int, [_P, C.c_int]),
     "gddim_ctx_workspace_bytes": (C.c_size_t, [_P]),
     "gddim_ctx_launch_count": (C.c_longlong, [_P]),
+    "gddim_ctx_plan_size": (C.c_int, [_P]),
+    "gddim_ctx_plan_op": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
     "gddim_ctx_set_profile": (C.c_int, [_P, C.c_int]),
     "gddim_ctx_get_profile": (C.c_int, [_P, _P, _P, _P]),
     "gddim_ctx_dump_profile": (C.c_int, [_P, C.c_char_p]),

@@ -116,6 +116,17 @@ int gddim_ctx_set_gemm_impl(gddim_ctx* ctx, int impl) {
   return 0;
 }
 size_t gddim_ctx_workspace_bytes(const gddim_ctx* ctx) { return ctx ? ctx->net->workspace_bytes() : 0; }
+int gddim_ctx_plan_size(const gddim_ctx* ctx) { return ctx ? ctx->net->num_ops() : -1; }
+int gddim_ctx_plan_op(const gddim_ctx* ctx, int index, char* tag_buf, int tag_buf_len, int* kind) {
+  if (!ctx || index < 0 || index >= ctx->net->num_ops()) return set_err("gddim_ctx_plan_op: bad index");
+  const Op& op = ctx->net->op_at(index);
+  if (tag_buf && tag_buf_len > 0) {
+    strncpy(tag_buf, op.tag.c_str(), tag_buf_len - 1);
+    tag_buf[tag_buf_len - 1] = 0;
+  }
+  if (kind) *kind = (int)op.kind;
+  return 0;
+}
 long long gddim_ctx_launch_count(const gddim_ctx* ctx) { return ctx ? ctx->net->launch_count() : -1; }
 
 int gddim_ctx_set_profile(gddim_ctx* ctx, int on) {

@@ -65,6 +65,7 @@ class UNet {
   const std::string& error() const { return err_; }
   const gddim_model_cfg& cfg() const { return cfg_; }
   int num_ops() const { return (int)ops_.size(); }
+  const Op& op_at(int i) const { return ops_[i]; }
   // per-op CUDA-event timing of forward() (eager launches only); accumulates until reset
   void set_profile(bool on);
   bool profiling() const { return profile_; }

@@ -88,6 +88,21 @@ class ScoreNet:
         L.gddim_ctx_destroy(ctx)
     return self._specs
 
+  def plan(self, batch=1):
+    """[(tag, kind)] of the static launch plan for `batch` images per call (host-side walk only: works without a GPU)."""
+    L = _lib.lib()
+    ctx = C.c_void_p()
+    _lib.check(L.gddim_ctx_create(0, C.byref(self._cfg), int(batch), C.byref(ctx)), "gddim_ctx_create")
+    try:
+      out = []
+      buf, kind = C.create_string_buffer(256), C.c_int()
+      for i in range(L.gddim_ctx_plan_size(ctx)):
+        _lib.check(L.gddim_ctx_plan_op(ctx, i, buf, 256, C.byref(kind)), "gddim_ctx_plan_op")
+        out.append((buf.value.decode(), kind.value))
+      return out
+    finally:
+      L.gddim_ctx_destroy(ctx)
+
   def set_params(self, params):
     """params: flat or nested mapping of float arrays in Flax layout (e.g. state.params_ema)."""
     flat = flatten_params(params) if any(hasattr(v, "items") for v in params.values()) else \

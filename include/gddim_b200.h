@@ -67,6 +67,11 @@ int gddim_ctx_finalize(gddim_ctx* ctx);
 /* 0 = tcgen05/TMA kernels (default), 1 = CUDA-core reference kernels (on-GPU validation only) */
 int gddim_ctx_set_gemm_impl(gddim_ctx* ctx, int impl);
 size_t gddim_ctx_workspace_bytes(const gddim_ctx* ctx);
+/* Static launch plan of the network (available right after gddim_ctx_create, no GPU needed): number of planned ops, and
+ * for op `index` its tag ("ResnetBlockBigGANpp_3/conv1", "AttnBlockpp_0/gn_qkv", ...) and kind (0 stem, 1 groupnorm,
+ * 2 conv/GEMM, 3 head, 4 im2col, 5 V transpose, 6 small attention, 7 row softmax, 8 fused attention, 9 GroupNorm+qkv). */
+int gddim_ctx_plan_size(const gddim_ctx* ctx);
+int gddim_ctx_plan_op(const gddim_ctx* ctx, int index, char* tag_buf, int tag_buf_len, int* kind);
 long long gddim_ctx_launch_count(const gddim_ctx* ctx);   /* kernels launched by this ctx so far */
 
 /* per-op CUDA-event timing of the network evaluation (eager launches; CUDA graphs are bypassed while on).

@@ -229,11 +229,12 @@ def test_fused_attention_projection(B, reverse):
   assert rel_l2(out.reshape(B, T, Cc).cpu().numpy(), ref.numpy()) < 1e-3
 
 
-@pytest.mark.parametrize("B,reverse", [(1, 0), (3, 1), (8, 0)])
-def test_gn_fused_into_qkv_projection(B, reverse):
+@pytest.mark.parametrize("B,reverse,H", [(1, 0, 16), (3, 1, 16), (8, 0, 16), (2, 1, 32)])
+def test_gn_fused_into_qkv_projection(B, reverse, H):
   """gn_qkv_kernel: GroupNorm apply in the A-operand path of the q/k/v projection == gn_apply followed by the N = 768
-  GEMM, bit for bit (same x*a+b, same fp16 rounding, same accumulation order, same epilogue)."""
-  H = W = 16; Cc = 256
+  GEMM, bit for bit (same x*a+b, same fp16 rounding, same accumulation order, same epilogue).  H = 32: the 1024-token
+  attention of the 256x256 configuration."""
+  W = H; Cc = 256
   g = torch.Generator().manual_seed(41 + B)
   x = (torch.randn(B, H, W, Cc, generator=g) * 1.7 + 0.2).cuda()
   gamma, beta = (1 + 0.1 * torch.randn(Cc, generator=g)).cuda(), (0.1 * torch.randn(Cc, generator=g)).cuda()

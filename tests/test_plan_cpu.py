@@ -1,0 +1,55 @@
+"""Host-side launch plan of the score network (csrc/unet.cpp walk), inspected through the C ABI without a GPU:
+which kernels an NCSNpp.__call__ (cld_jax/models/ncsnpp.py:41-243) turns into for the BASELINE configurations."""
+import collections
+
+import pytest
+
+from gddim_b200 import configs, net
+
+KIND = {0: "stem", 1: "groupnorm", 2: "gemm", 3: "head", 4: "im2col", 5: "transpose_v", 6: "small_attn",
+        7: "softmax_rows", 8: "attn_fused", 9: "gn_qkv"}
+
+
+def _plan(cfg, cld=True, batch=4):
+  return net.ScoreNet(cfg, cld=cld).plan(batch)
+
+
+def test_deep_cifar_plan_uses_the_fused_attention_block():
+  plan = _plan(configs.cld_accr_dcifar10(), batch=256)
+  kinds = collections.Counter(KIND[k] for _, k in plan)
+  # attention blocks in creation order (ncsnpp.py:150-226): eight in the encoder at 16x16 (one per res-block), the
+  # middle block at 4x4, one in the decoder at 16x16.  16x16: GroupNorm coefficients -> gn_qkv -> attention + projection,
+  # nothing of the unfused chain; 4x4 (16 tokens): the CUDA-core attention kernel between plain GEMMs
+  for i in range(10):
+    tags = [t.split("/", 1)[1] for t, _ in plan if t.startswith(f"AttnBlockpp_{i}/")]
+    assert tags == (["gn", "qkv", "attn_small", "proj"] if i == 8 else ["gn_coef", "gn_qkv", "attn_proj_fused"]), (i, tags)
+  assert kinds["gn_qkv"] == 9 and kinds["attn_fused"] == 9 and kinds["transpose_v"] == 0 and kinds["softmax_rows"] == 0
+  assert kinds["small_attn"] == 1
+  # every convolution / NIN is a tcgen05 GEMM op; stem and head are GEMM ops too (no CUDA-core conv kernels in the plan)
+  assert kinds["stem"] == 0 and kinds["head"] == 0 and kinds["gemm"] > 150
+  # the plan is a property of the architecture, not of the batch
+  assert [t for t, _ in _plan(configs.cld_accr_dcifar10(), batch=8)] == [t for t, _ in plan]
+
+
+def test_blur_and_ddpmpp_plans():
+  blur = _plan(configs.blur_ddpm_deep_cifar10(1.0), cld=False)
+  assert sum(1 for _, k in blur if KIND[k] == "attn_fused") == 9
+  ddpmpp = _plan(configs.cld_ddpmpp_cifar10())
+  kinds = collections.Counter(KIND[k] for _, k in ddpmpp)
+  assert kinds["attn_fused"] == kinds["gn_qkv"] and kinds["attn_fused"] >= 1
+
+
+def test_256_geometry_keeps_the_long_sequence_attention_path():
+  cfg = configs.cld_accr_dcifar10()
+  cfg.data.image_size = 256
+  plan = _plan(cfg, batch=2)
+  tags = [t.split("/", 1)[1] for t, _ in plan if t.startswith("AttnBlockpp_0/")]
+  # 32x32 = 1024 tokens: scores through HBM in fp32, row softmax kernel, V transpose, P.V, projection
+  assert tags == ["gn_coef", "gn_qkv", "qk", "softmax", "vT", "pv", "proj"], tags
+
+
+def test_unsupported_width_is_rejected_at_context_creation():
+  cfg = configs.cld_accr_dcifar10()
+  cfg.model.nf = 32                                   # simple_cifar10: nf must be a multiple of 64
+  with pytest.raises(RuntimeError):
+    net.ScoreNet(cfg, cld=True).plan(1)
