@@ -5,7 +5,7 @@ NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -c
 SRC := gddim_b200/csrc
 OBJ := build/obj
 LIB := gddim_b200/libgddim_b200.so
-CU := $(SRC)/conv_gemm.cu $(SRC)/attn.cu $(SRC)/gn_qkv.cu $(SRC)/norm.cu $(SRC)/small.cu $(SRC)/update.cu
+CU := $(SRC)/conv_gemm.cu $(SRC)/conv_xf.cu $(SRC)/attn.cu $(SRC)/gn_qkv.cu $(SRC)/norm.cu $(SRC)/small.cu $(SRC)/update.cu
 CPP := $(SRC)/tables.cpp $(SRC)/unet.cpp $(SRC)/api.cpp
 OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU)) $(patsubst $(SRC)/%.cpp,$(OBJ)/%.o,$(CPP))
 HDRS := $(wildcard $(SRC)/*.h $(SRC)/*.cuh include/*.h)

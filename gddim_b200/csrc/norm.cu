@@ -451,7 +451,7 @@ static int small_rows(const NormOp* op) {
 }
 
 int norm_num_launches(const NormOp* op) {
-  if (op->coef_only) return 1;
+  if (op->coef_only) return op->raw16 ? 2 : 1;
   if (small_rows(op) > 0) return 1;
   return op->dst16 ? 2 : 1;
 }
@@ -531,7 +531,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     dim3 grid(op->splits, op->B);
     launch_k(gn_stats_kernel, dim3(grid), dim3(threads), threads * 8 * sizeof(float), st, s);
   }
-  if (op->coef_only) return cudaGetLastError() == cudaSuccess ? 0 : -4;
+  if (op->coef_only && op->raw16 == nullptr) return cudaGetLastError() == cudaSuccess ? 0 : -4;
   ApplyArgs a;
   a.src1 = op->src1; a.c1 = op->c1; a.src2 = op->src2; a.c2 = op->c2;
   a.H = op->H; a.W = op->W;
@@ -540,7 +540,7 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     case RS_FIR_UP: case RS_NAIVE_UP: a.Ho = op->H * 2; a.Wo = op->W * 2; break;
     default: a.Ho = op->H; a.Wo = op->W; break;
   }
-  a.coef = op->coef; a.silu = op->silu; a.do_norm = do_norm; a.raw_scale = op->raw_scale;
+  a.coef = op->coef; a.silu = op->silu; a.do_norm = op->dst16 != nullptr; a.raw_scale = op->raw_scale;
   a.dst16 = op->dst16; a.raw16 = op->raw16;
   a.reverse = op->reverse;
   const int nv8 = C / 8;
