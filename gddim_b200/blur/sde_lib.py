@@ -27,7 +27,7 @@ class SDE:
     _lib.check(_lib.lib().gddim_blur_create(float(sigma_blur_max), float(sampling_eps), C.byref(h)))
     self._h = h
     self.T = 1.0
-    self.alpha_start = self.t2alpha_fn(0.0)
+    self.alpha_start = float(_lib.lib().gddim_blur_t2alpha(self._h, 0.0))      # fp64: rho2t / sampling_T derive from it
 
   def __del__(self):
     try:

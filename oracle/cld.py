@@ -195,6 +195,14 @@ class CLD:
     eps = np.stack([_riemann(self, s, e, None, 0, num_item) for s, e in zip(rev_ts[:-1], rev_ts[1:])])
     return mean, eps
 
+  def prepare_naive_coef(self, rev_ts):
+    """sde_lib.py:276-287: Euler step matrices I + F(t) dt and 0.5 G G R^{-T} dt."""
+    rev_ts = np.asarray(rev_ts, dtype=np.float64)
+    dts = rev_ts[1:] - rev_ts[:-1]
+    mean = np.stack([np.eye(2) + self.s_F(t) * dt for t, dt in zip(rev_ts[:-1], dts)])
+    eps = self.eps_integrand(rev_ts[:-1]) * dts[:, None, None]
+    return mean, eps
+
   def get_deis_coef(self, order, rev_ts):
     """sde_lib.py:308-319 -> [N, order+3, 2, 2]."""
     rev_ts = np.asarray(rev_ts, dtype=np.float64)

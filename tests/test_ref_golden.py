@@ -1,0 +1,419 @@
+"""Parity against the REFERENCE ITSELF: tests/golden/ref_*.npz are outputs of the reference's own source files
+(cld_jax/{deis,sde_lib,sampling}.py, models/*.py, blur_jax/{sde_lib,blur,fft,sampling,multistep}.py) executed unmodified
+under tests/refshim in fp64 (tests/golden/make_ref_golden.py).  CPU tests pin the oracle and the library's host tables
+to them; `-m gpu` tests pin the CUDA path (update operator, DCT, FIR resamplers, network forward, every sampler)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from gddim_b200 import _lib, net
+from gddim_b200.blur import sde_lib as bsde
+from gddim_b200.cld import sde_lib
+from helpers import small_cfg
+from oracle import blur as ob
+from oracle import cld as oc
+from oracle import ncsnpp as on
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+inv = lambda x: (x + 1.) / 2.   # noqa: E731
+
+
+def ref(name):
+  return np.load(os.path.join(G, name))
+
+
+CLD_CASES = {"rk": dict(is_R_rk=True, R_dt=1e-3), "euler": dict(is_R_rk=False, R_dt=1e-3),
+             "b1": dict(is_R_rk=True, R_dt=1e-3, beta_0=0.5, beta_1=3.0, m_inv=2.0, vv_gamma=0.02)}
+
+
+# ---- CLD tables: cld_jax/sde_lib.py:45-319, deis.py:19-95 ---------------------------------------------------------------
+@pytest.mark.parametrize("tag", list(CLD_CASES))
+def test_oracle_cld_tables_match_reference(tag):
+  g = ref("ref_cld_tables.npz")
+  o = oc.CLD(**CLD_CASES[tag])
+  t = g["t_at"]
+  np.testing.assert_allclose(o.R(t), g[f"{tag}_R"], rtol=1e-9, atol=1e-13)
+  np.testing.assert_allclose(o.psi(t[1:], t[:-1]), g[f"{tag}_psi"], rtol=1e-12)
+  np.testing.assert_allclose(np.stack([o.s_F(s) for s in t]), g[f"{tag}_F"], rtol=1e-14)
+  np.testing.assert_allclose(np.stack([o.s_G(s) for s in t]), g[f"{tag}_G"], rtol=1e-14)
+  np.testing.assert_allclose(o.eps_integrand(t), g[f"{tag}_integrand"], rtol=1e-8, atol=1e-12)
+  rev = oc.get_rev_ts(1.0, 1e-3, 2, 9)
+  np.testing.assert_allclose(rev, g[f"{tag}_rev_ts"], rtol=1e-14)
+  for order in ((0, 1, 2, 3) if tag == "rk" else (2,)):
+    want = g[f"{tag}_deis_o{order}"]
+    assert want.shape == (9, order + 3, 2, 2) and np.all(want[:, -1] == 0)          # trailing padding matrix, deis.py:53
+    np.testing.assert_allclose(o.get_deis_coef(order, rev), want, rtol=1e-8, atol=1e-12)
+  m, e = o.prepare_order0_coef(rev)
+  np.testing.assert_allclose(m, g[f"{tag}_order0_mean"], rtol=1e-12)
+  np.testing.assert_allclose(e, g[f"{tag}_order0_eps"], rtol=1e-8, atol=1e-12)
+  m, e = o.prepare_naive_coef(rev)
+  np.testing.assert_allclose(m, g[f"{tag}_naive_mean"], rtol=1e-12)
+  np.testing.assert_allclose(e, g[f"{tag}_naive_eps"], rtol=1e-8, atol=1e-12)
+  if tag == "rk":
+    got = np.stack([o.eps2score(g["rk_eps2score_in"][b], tt) for b, tt in enumerate((0.3, 0.7))])
+    np.testing.assert_allclose(got, g["rk_eps2score"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("tag", list(CLD_CASES))
+def test_library_cld_tables_match_reference(tag):
+  """csrc/tables.cpp through the C ABI (gddim_cld_*), fp64 out (x64=True)."""
+  g = ref("ref_cld_tables.npz")
+  s = sde_lib.CLD(x64=True, **CLD_CASES[tag])
+  t = g["t_at"]
+  np.testing.assert_allclose(s.v_R(t), g[f"{tag}_R"], rtol=1e-9, atol=1e-13)
+  np.testing.assert_allclose(s.vv_psi(t[1:], t[:-1]), g[f"{tag}_psi"], rtol=1e-12)
+  np.testing.assert_allclose(np.stack([s.s_F(x) for x in t]), g[f"{tag}_F"], rtol=1e-14)
+  np.testing.assert_allclose(np.stack([s.s_G(x) for x in t]), g[f"{tag}_G"], rtol=1e-14)
+  np.testing.assert_allclose(s.v_eps_integrand(t), g[f"{tag}_integrand"], rtol=1e-8, atol=1e-12)
+  rev = g[f"{tag}_rev_ts"]
+  out = np.empty(10)
+  _lib.check(_lib.lib().gddim_rev_ts(1.0, 1e-3, 2, 9, out.ctypes.data))
+  np.testing.assert_allclose(out, rev, rtol=1e-14)
+  for order in ((0, 1, 2, 3) if tag == "rk" else (2,)):
+    np.testing.assert_allclose(s.get_deis_coef(order, rev), g[f"{tag}_deis_o{order}"], rtol=2e-6, atol=1e-9)
+  m, e = s.prepare_order0_coef(rev)
+  np.testing.assert_allclose(m, g[f"{tag}_order0_mean"], rtol=1e-12)
+  np.testing.assert_allclose(e, g[f"{tag}_order0_eps"], rtol=2e-6, atol=1e-9)
+  m, e = s.prepare_naive_coef(rev)
+  np.testing.assert_allclose(m, g[f"{tag}_naive_mean"], rtol=1e-12)
+  np.testing.assert_allclose(e, g[f"{tag}_naive_eps"], rtol=1e-8, atol=1e-12)
+  if tag == "rk":
+    np.testing.assert_allclose(s.eps2score(g["rk_eps2score_in"], [0.3, 0.7]), g["rk_eps2score"], rtol=1e-9)
+
+
+# ---- LambdaSDE / LSDE / MLCLD: sde_lib.py:334-519, sampling.py:272-325 -------------------------------------------------
+def test_oracle_variant_tables_match_reference():
+  g = ref("ref_cld_variants.npz")
+  o = oc.CLD(is_R_rk=False, R_dt=1e-4)
+  lam = oc.LambdaSDE(o, 0.5, True)
+  rev = g["rev_ts"]
+  np.testing.assert_allclose(np.stack([lam.s_hat_psi(s, t) for s, t in zip(rev[:-1], rev[1:])]), g["lambda05_hat_psi"], rtol=1e-8)
+  d0 = lam.get_deis_coef(0, rev)
+  np.testing.assert_allclose(d0, g["lambda05_deis_o0"], rtol=1e-7, atol=1e-11)
+  np.testing.assert_allclose(d0[:, [0, 1, 3]], g["lambda05_order0_coef"], rtol=1e-7, atol=1e-11)
+  np.testing.assert_allclose(lam.get_deis_coef(1, rev), g["lambda05_deis_o1"], rtol=1e-7, atol=1e-11)
+  ls = oc.LSDE(o)
+  np.testing.assert_allclose(ls.get_deis_coef(2, g["rev_ts6"]), g["lsde_deis_o2"], rtol=1e-8, atol=1e-12)
+  np.testing.assert_allclose(np.stack([ls.s_L(t) for t in g["rev_ts6"]]), g["lsde_L"], rtol=1e-10)
+  np.testing.assert_allclose(np.einsum("ij,...j->...i", ls.epsR2epsL_matrix(0.4), g["lsde_epsR2epsL_in"]), g["lsde_epsR2epsL"], rtol=1e-9)
+  ml = oc.MLCLD(o)
+  np.testing.assert_allclose(np.stack([ml.psi2(t) for t in g["rev_ts5"]]), g["mlcld_psi2"], rtol=1e-9)
+  np.testing.assert_allclose(ml.get_deis_coef(1, g["rev_ts5"]), g["mlcld_deis_o1"], rtol=1e-7, atol=1e-11)
+
+
+def test_library_variant_tables_match_reference():
+  g = ref("ref_cld_variants.npz")
+  s = sde_lib.CLD(x64=True, is_R_rk=False, R_dt=1e-4)
+  lam = sde_lib.LambdaSDE(s, 0.5, True)
+  rev = g["rev_ts"]
+  np.testing.assert_allclose(lam.get_deis_coef(0, rev), g["lambda05_deis_o0"], rtol=2e-6, atol=1e-9)
+  np.testing.assert_allclose(lam.get_order0_coef(rev), g["lambda05_order0_coef"], rtol=2e-6, atol=1e-9)
+  np.testing.assert_allclose(lam.get_deis_coef(1, rev), g["lambda05_deis_o1"], rtol=2e-6, atol=1e-9)
+  ls = sde_lib.LSDE(s)
+  np.testing.assert_allclose(ls.get_deis_coef(2, g["rev_ts6"]), g["lsde_deis_o2"], rtol=2e-6, atol=1e-9)
+  np.testing.assert_allclose(np.stack([ls.s_L(t) for t in g["rev_ts6"]]), g["lsde_L"], rtol=1e-9)
+  np.testing.assert_allclose(ls.epsR2epsL(0.4, g["lsde_epsR2epsL_in"]), g["lsde_epsR2epsL"], rtol=1e-8)
+  rev5 = np.ascontiguousarray(g["rev_ts5"])
+  out = np.empty((rev5.size - 1, 4, 2, 2))
+  _lib.check(_lib.lib().gddim_cld_mldeis_coef(s._h, 1, rev5.ctypes.data, rev5.size, out.ctypes.data), "gddim_cld_mldeis_coef")
+  np.testing.assert_allclose(out, g["mlcld_deis_o1"], rtol=2e-6, atol=1e-9)
+
+
+# ---- update operator and resamplers: deis.py:141-151, up_or_down_sampling.py:76-86,168-411 ---------------------------
+def test_oracle_ops_match_reference():
+  g = ref("ref_ops.npz")
+  for order in range(4):
+    x, h = oc.multistep_ab_step(g[f"ab{order}_x"], g[f"ab{order}_coef"], g[f"ab{order}_new_eps"], g[f"ab{order}_hist"])
+    np.testing.assert_allclose(x, g[f"ab{order}_x_next"], rtol=1e-13, atol=1e-14)
+    np.testing.assert_array_equal(h, g[f"ab{order}_hist_next"])
+  x = torch.from_numpy(g["fir_in"]).permute(0, 3, 1, 2)
+  nhwc = lambda t: t.permute(0, 2, 3, 1).numpy()   # noqa: E731
+  np.testing.assert_allclose(nhwc(on.upsample_2d(x, (1, 3, 3, 1))), g["fir_up"], rtol=1e-12, atol=1e-14)
+  np.testing.assert_allclose(nhwc(on.downsample_2d(x, (1, 3, 3, 1))), g["fir_down"], rtol=1e-12, atol=1e-14)
+  np.testing.assert_allclose(nhwc(on.naive_upsample_2d(x)), g["naive_up"], rtol=0, atol=0)
+  np.testing.assert_allclose(nhwc(on.naive_downsample_2d(x)), g["naive_down"], rtol=1e-14, atol=1e-15)
+  store = on._Store({"Conv2d_0/weight": g["fir_w"], "Conv2d_0/bias": np.zeros(4)}, torch.float64)
+  got = on._conv2d_down(on._Scope(store), x, 4, (1, 3, 3, 1))
+  np.testing.assert_allclose(nhwc(got), g["fir_conv_down"], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_gpu_multistep_ab_step_matches_reference():
+  from gddim_b200.cld import deis as gdeis
+  g = ref("ref_ops.npz")
+  for order in range(4):
+    a = [g[f"ab{order}_{k}"].astype(np.float32) for k in ("x", "coef", "new_eps", "hist")]
+    x, h = gdeis.multistep_ab_step(*a)
+    np.testing.assert_allclose(x, g[f"ab{order}_x_next"], rtol=0, atol=2e-5)
+    np.testing.assert_array_equal(h, g[f"ab{order}_hist_next"].astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rs,key", [(1, "fir_down"), (2, "fir_up"), (3, "naive_down"), (4, "naive_up")])
+def test_gpu_resamplers_match_reference(rs, key):
+  """gddim_group_norm(resample=1..4): the raw (un-normalised) output is the reference resampler applied to x."""
+  from gddim_b200 import ops
+  g = ref("ref_ops.npz")
+  x = torch.from_numpy(g["fir_in"].astype(np.float32)).cuda()
+  C_ = x.shape[-1]
+  _, raw = ops.group_norm(x, torch.ones(C_).cuda(), torch.zeros(C_).cuda(), silu=False, resample=rs, want_raw=True)
+  assert rel_l2(raw.float().cpu().numpy(), g[key]) < 6e-4          # fp16 output rounding
+
+
+# ---- network: models/ncsnpp.py:41-243 + layer files ---------------------------------------------------------------------
+def _ref_specs(g, kind):
+  return {str(n): (tuple(int(d) for d in str(s).split("x")), str(k), float(sc))
+          for n, s, k, sc in zip(g[f"{kind}_spec_names"], g[f"{kind}_spec_shapes"], g[f"{kind}_spec_kinds"], g[f"{kind}_spec_scales"])}
+
+
+@pytest.mark.parametrize("kind,npz", [("cld_deep", "ref_net.npz"), ("cld_ddpmpp", "ref_net.npz"), ("blur_deep", "ref_blur_sampler.npz")])
+def test_parameter_names_shapes_and_inits_match_reference_modules(kind, npz):
+  """The (name, shape, initializer) list the reference's flax modules create, in creation order, equals the oracle's
+  walk and the library's own walk (csrc/unet.cpp via gddim_param_spec) -- this is what a real checkpoint is keyed by."""
+  want = _ref_specs(ref(npz), kind)
+  cld = not kind.startswith("blur")
+  cfg = small_cfg(kind)
+  osp = on.collect_specs(cfg, cld=cld)
+  assert list(osp.keys()) == list(want.keys())
+  lsp = net.ScoreNet(cfg, cld=cld).specs()
+  assert list(lsp.keys()) == list(want.keys())
+  for k, (shape, kd, sc) in want.items():
+    for sp in (osp, lsp):
+      # (the library reports the initializer scale through a C float)
+      assert tuple(sp[k][0]) == shape and sp[k][1] == kd and abs(sp[k][2] - sc) <= 1e-7 * max(1.0, sc), (k, sp[k], want[k])
+
+
+def _params(kind):
+  from gddim_b200 import params
+  cfg = small_cfg(kind)
+  return cfg, params.generate(on.collect_specs(cfg, cld=not kind.startswith("blur")), seed=1234, nondegenerate=True)
+
+
+@pytest.mark.parametrize("kind,tol", [("cld_deep", 1e-10), ("cld_ddpmpp", 1e-5)])
+def test_oracle_forward_matches_reference(kind, tol):
+  """fp64 oracle vs the reference NCSNpp.__call__.  DDPM++ tolerance: the reference builds the positional-embedding
+  frequencies with an explicit float32 arange/exp (layers.py:456), which stays float32 under x64."""
+  g = ref("ref_net.npz")
+  cfg, p = _params(kind)
+  for j in (0, 1):
+    y = on.forward(p, cfg, g[f"{kind}_x"], 999.0 * float(g[f"{kind}_t{j}"]), dtype=torch.float64)
+    assert rel_l2(y, g[f"{kind}_y{j}"]) < tol
+  y32 = on.forward(p, cfg, g[f"{kind}_x"], 999.0 * float(g[f"{kind}_t0"]), dtype=torch.float32)
+  assert rel_l2(y32, g[f"{kind}_y0"]) < 1e-4          # the fp32 oracle the GPU tests compare with
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["cld_deep", "cld_ddpmpp"])
+def test_gpu_forward_matches_reference(kind):
+  from helpers import build
+  g = ref("ref_net.npz")
+  _, model, _ = build(kind)
+  for j in (0, 1):
+    y = model.forward(g[f"{kind}_x"], float(g[f"{kind}_t{j}"]))
+    e = rel_l2(y, g[f"{kind}_y{j}"])
+    print(f"{kind} forward t={float(g[f'{kind}_t{j}']):.3f}: rel_l2 vs reference {e:.2e}")
+    assert e < 2e-3
+
+
+# ---- samplers: cld_jax/sampling.py:41-669 ---------------------------------------------------------------------------------
+def _oracle_pair(kind="cld_mixed", mixed=False):
+  cfg, p = _params("cld_deep" if kind == "cld_mixed" else kind)
+  cfg = small_cfg(kind)
+  cfg.model.mixed_score = mixed
+  if kind == "cld_ddpmpp":
+    cfg.model.R_dt = 1e-4
+  o = oc.from_config(cfg)
+  return cfg, o, oc.make_eps_fn(o, on.make_net_fn(p, cfg, dtype=torch.float64))
+
+
+ORACLE_SAMPLERS = {
+    "deis_o2": lambda o, f, g: oc.deis_sampler(o, f, g["deis_o2_u"], 6, 2, denoising=True),
+    "deis_o3": lambda o, f, g: oc.deis_sampler(o, f, g["deis_o3_u"], 8, 3, denoising=True),
+    "deis_o0_nodenoise": lambda o, f, g: oc.deis_sampler(o, f, g["deis_o0_nodenoise_u"], 5, 0, denoising=False),
+    "order0": lambda o, f, g: oc.order0_sampler(o, f, g["order0_u"], 6, denoising=True),
+    "hybdeis": lambda o, f, g: oc.deis_sampler(o, f, g["hybdeis_u"], 9, 1, denoising=True, rev_ts=oc.hyd_rev_ts(o, 9, 0.3, 0.3, 2, True)),
+    "sdeis": lambda o, f, g: oc.sdeis_sampler(oc.LambdaSDE(o, 0.5, True), f, g["sdeis_u"], 5, 1, g["sdeis_z"].astype(np.float64), denoising=True),
+    "ldeis": lambda o, f, g: oc.ldeis_sampler(o, f, g["ldeis_u"], 6, 2, denoising=False),
+    "em": lambda o, f, g: oc.em_sampler(o, f, g["em_u"], 6, g["em_z"].astype(np.float64), lambda_coef=0.7, denoising=True),
+    "sscs": lambda o, f, g: oc.sscs_sampler(o, f, g["sscs_u"], 5, g["sscs_z"].astype(np.float64).reshape((5, 2) + g["sscs_u"].shape), denoising=False),
+    "mldeis": lambda o, f, g: oc.mldeis_sampler(o, f, g["mldeis_u"], 6, 1, denoising=True),
+}
+
+
+@pytest.mark.parametrize("name", list(ORACLE_SAMPLERS))
+def test_oracle_samplers_match_reference(name):
+  """Every CLD sampler factory of the reference, end to end on the small NCSN++ (fp64 both sides)."""
+  g = ref("ref_cld_samplers.npz")
+  _, o, eps_fn = _oracle_pair()
+  x, v, nfe = ORACLE_SAMPLERS[name](o, eps_fn, g)
+  want_x = g[f"{name}_x"][0] if name == "hybdeis" else g[f"{name}_x"]          # psampler: leading device axis
+  want_v = g[f"{name}_v"][0] if name == "hybdeis" else g[f"{name}_v"]
+  assert nfe == int(g[f"{name}_nfe"])
+  assert rel_l2(x, want_x) < 1e-7 and rel_l2(v, want_v) < 1e-7, (rel_l2(x, want_x), rel_l2(v, want_v))
+
+
+def test_oracle_mixed_score_and_ddpmpp_samplers_match_reference():
+  g = ref("ref_cld_samplers.npz")
+  _, o, eps_fn = _oracle_pair(mixed=True)
+  x, v, _ = oc.deis_sampler(o, eps_fn, g["mixed_deis_o2_u"], 6, 2, denoising=True)
+  assert rel_l2(x, g["mixed_deis_o2_x"]) < 1e-7 and rel_l2(v, g["mixed_deis_o2_v"]) < 1e-7
+  _, o, eps_fn = _oracle_pair("cld_ddpmpp")
+  x, v, _ = oc.deis_sampler(o, eps_fn, g["ddpmpp_deis_o1_u"], 6, 1, denoising=True)
+  assert rel_l2(x, g["ddpmpp_deis_o1_x"]) < 1e-4 and rel_l2(v, g["ddpmpp_deis_o1_v"]) < 1e-4       # fp32 embedding table, see above
+
+
+def test_oracle_order0_em_matches_reference():
+  g = ref("ref_cld_samplers.npz")
+  _, o, eps_fn = _oracle_pair()
+  rev = oc.get_rev_ts(1.0, 1e-3, 2, 5)
+  mean, em = o.prepare_naive_coef(rev)
+  w = g["order0_em_u"].astype(np.float64)
+  for i in range(5):
+    w = np.einsum("ij,...j->...i", mean[i], w) + np.einsum("ij,...j->...i", em[i], eps_fn(w, rev[i]))
+  w = oc.denoise_step(o, eps_fn, w)
+  assert rel_l2((w[..., 0] + 1) / 2, g["order0_em_x"]) < 1e-7 and rel_l2(w[..., 1], g["order0_em_v"]) < 1e-7
+
+
+def _gpu_pair(kind="cld_mixed", mixed=False):
+  from helpers import build
+  cfg, model, _ = build(kind)
+  cfg.model.mixed_score = mixed
+  if kind == "cld_ddpmpp":
+    cfg.model.R_dt = 1e-4
+  sde = sde_lib.from_config(cfg)
+  if kind == "cld_mixed":
+    cfg.model.mixed_score = True
+  return sde, model
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["deis_o2", "deis_o3", "deis_o0_nodenoise", "order0", "order0_em", "hybdeis", "sdeis", "ldeis", "em",
+                                  "sscs", "mldeis", "mixed_deis_o2", "ddpmpp_deis_o1"])
+def test_gpu_samplers_match_reference(name):
+  """The CUDA path against samples produced by the reference's own sampler code on the same prior noise, parameters and
+  (for the stochastic samplers) the same standard normals.  Tolerance 1e-3 relative L2 (north star); the mixed-score,
+  em and sscs variants amplify operand rounding slightly (see test_gpu_sampler.py) and use 1.5e-3."""
+  from gddim_b200.cld import sampling
+  g = ref("ref_cld_samplers.npz")
+  u = g[f"{name}_u"]
+  B = u.shape[0]
+  shape = (32, 32, 3)
+  if name == "mixed_deis_o2":
+    sde, model = _gpu_pair(mixed=True)
+  elif name == "ddpmpp_deis_o1":
+    sde, model = _gpu_pair("cld_ddpmpp")
+  else:
+    sde, model = _gpu_pair()
+  z = g[f"{name}_z"] if f"{name}_z" in g.files else None
+  if name.startswith("deis_o") or name in ("mixed_deis_o2", "ddpmpp_deis_o1"):
+    nfe, order, den = {"deis_o2": (6, 2, True), "deis_o3": (8, 3, True), "deis_o0_nodenoise": (5, 0, False),
+                       "mixed_deis_o2": (6, 2, True), "ddpmpp_deis_o1": (6, 1, True)}[name]
+    x, v, n = sampling.get_deis_sampler(sde, model, shape, nfe, inv, order, ts_order=2, denoising=den)(0, model, B, u=u)
+  elif name == "order0":
+    x, v, n = sampling.get_order0_sampler(sde, model, shape, 6, inv, is_em=False, denoising=True)(0, model, B, u=u)
+  elif name == "order0_em":
+    x, v, n = sampling.get_order0_sampler(sde, model, shape, 6, inv, is_em=True, denoising=True)(0, model, B, u=u)
+  elif name == "hybdeis":
+    cfg = small_cfg("cld_mixed")
+    cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "hybdeis", 9, 1
+    xs, vs, n = sampling.get_sampling_fn(cfg, sde, model, None, inv)(None, model, B, u=u[None])
+    assert xs.shape == g["hybdeis_x"].shape                                    # (n_dev = 1, B, 32, 32, 3) like pmap
+    x, v = xs[0], vs[0]
+  elif name == "sdeis":
+    x, v, n = sampling.get_sdeis_sampler(sde, model, shape, 5, inv, 1, lambda_coef=0.5, use_order0=True, ts_order=2,
+                                         denoising=True)(0, model, B, u=u, noise=z)
+  elif name == "ldeis":
+    x, v, n = sampling.get_L_deis_sampler(sde, model, shape, 6, inv, 2, ts_order=2, denoising=False)(0, model, B, u=u)
+  elif name == "em":
+    x, v, n = sampling.get_em_sampler(sde, model, shape, 6, inv, lambda_coef=0.7, ts_order=2, denoising=True)(0, model, B, u=u, noise=z)
+  elif name == "sscs":
+    x, v, n = sampling.get_sscs_sampler(sde, model, shape, 5, inv, ts_order=2, denoising=False)(0, model, B, u=u, noise=z)
+  elif name == "mldeis":
+    x, v, n = sampling.get_mldeis_sampler(sde, model, shape, 6, inv, 1, ts_order=2, denoising=True)(0, model, B, u=u)
+  want_x = g[f"{name}_x"][0] if name == "hybdeis" else g[f"{name}_x"]
+  want_v = g[f"{name}_v"][0] if name == "hybdeis" else g[f"{name}_v"]
+  ex, ev = rel_l2(x, want_x), rel_l2(v, want_v)
+  print(f"{name}: rel_l2 vs reference x {ex:.2e} v {ev:.2e}")
+  tol = 1.5e-3 if name in ("mixed_deis_o2", "em", "sscs", "order0_em", "sdeis", "ldeis", "mldeis") else 1e-3
+  assert n == int(g[f"{name}_nfe"]) and ex < tol and ev < tol
+
+
+# ---- blur: blur_jax/sde_lib.py:18-163, blur.py:11-107, sampling.py:42-90, multistep.py:94-98 ----------------------------
+@pytest.mark.parametrize("smax", [1.0, 10.0])
+def test_oracle_and_library_blur_tables_match_reference(smax):
+  g = ref("ref_blur_tables.npz")
+  tag = f"s{int(smax)}"
+  o, s = ob.SDE(sigma_blur_max=smax), bsde.SDE(sigma_blur_max=smax)
+  ts = g[f"{tag}_ts"]
+  np.testing.assert_allclose(ob.get_rev_ts(o, 2, 50), g[f"{tag}_rev_ts"], rtol=1e-13)
+  assert abs(o.sampling_T - float(g[f"{tag}_sampling_T"])) < 1e-14 and abs(s.sampling_T - float(g[f"{tag}_sampling_T"])) < 1e-14
+  np.testing.assert_allclose(np.stack([o.y_mean_coef(t) for t in ts]), g[f"{tag}_y_mean_coef"], rtol=1e-12)
+  np.testing.assert_allclose(np.array([o.y_std_coef(t) for t in ts]), g[f"{tag}_y_std_coef"], rtol=1e-12)
+  np.testing.assert_allclose([o.rho2t(r) for r in (0.5, 7.0, 80.0)], g[f"{tag}_rho2t"], rtol=1e-13)
+  np.testing.assert_allclose(s.y_mean_coef(ts), g[f"{tag}_y_mean_coef"], rtol=2e-6)
+  np.testing.assert_allclose(s.get_frequency_scaling(ts), g[f"{tag}_freq_scaling"], rtol=2e-6)
+  np.testing.assert_allclose(s.y_std_coef(ts), g[f"{tag}_y_std_coef"], rtol=2e-6)
+  np.testing.assert_allclose(s.t2alpha_fn(ts), g[f"{tag}_alpha"], rtol=2e-6, atol=1e-12)
+  np.testing.assert_allclose([s.rho2t(r) for r in (0.5, 7.0, 80.0)], g[f"{tag}_rho2t"], rtol=1e-6)
+  rev = np.empty(51)
+  _lib.check(_lib.lib().gddim_rev_ts(s.sampling_T, 1e-5, 2, 50, rev.ctypes.data))
+  np.testing.assert_allclose(rev, g[f"{tag}_rev_ts"], rtol=1e-13)
+
+
+def test_oracle_dct_and_scalar_ab_step_match_reference():
+  g = ref("ref_blur_tables.npz")
+  np.testing.assert_allclose(ob.batch_img_dct(g["dct_in"]), g["dct"], rtol=1e-11, atol=1e-13)
+  np.testing.assert_allclose(ob.batch_img_idct(g["dct_in"]), g["idct"], rtol=1e-11, atol=1e-13)
+  for order in range(3):
+    x, h = ob.ab_step(g[f"sab{order}_x"], g[f"sab{order}_coef"], g[f"sab{order}_new_eps"], g[f"sab{order}_hist"])
+    np.testing.assert_allclose(x, g[f"sab{order}_x_next"], rtol=1e-13, atol=1e-14)
+    np.testing.assert_array_equal(h, g[f"sab{order}_hist_next"])
+
+
+def test_oracle_blur_net_and_sampler_match_reference():
+  g = ref("ref_blur_sampler.npz")
+  cfg, p = _params("blur_deep")
+  y = on.forward(p, cfg, g["net_x"], 999.0 * float(g["net_t"]), dtype=torch.float64)
+  assert rel_l2(y, g["net_y"]) < 1e-10
+  net_fn = on.make_net_fn(p, cfg, dtype=torch.float64)
+  x, n = ob.order0_sampler(ob.from_config(cfg), net_fn, g["order0_y"].astype(np.float64), 6, ts_order=2)
+  assert n == int(g["order0_nfe"]) and rel_l2(x, g["order0_x"]) < 1e-8
+  x, n = ob.order0_sampler(ob.from_config(cfg), net_fn, g["order0_y"].astype(np.float64), 5, ts_order=2)
+  assert n == int(g["p_order0_nfe"]) == 5 and rel_l2(x, g["p_order0_x"][0]) < 1e-8
+
+
+@pytest.mark.gpu
+def test_gpu_dct_and_scalar_ab_step_match_reference():
+  from gddim_b200.blur import blur as gblur
+  from gddim_b200.blur import multistep as gms
+  g = ref("ref_blur_tables.npz")
+  x = g["dct_in"].astype(np.float32)
+  np.testing.assert_allclose(gblur.batch_img_dct(x), g["dct"], atol=2e-5)
+  np.testing.assert_allclose(gblur.batch_img_idct(x), g["idct"], atol=2e-5)
+  for order in range(3):
+    a = [g[f"sab{order}_{k}"].astype(np.float32) for k in ("x", "coef", "new_eps", "hist")]
+    xn, hn = gms.ab_step(*a)
+    np.testing.assert_allclose(xn, g[f"sab{order}_x_next"], atol=2e-5)
+    np.testing.assert_array_equal(hn, g[f"sab{order}_hist_next"].astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_gpu_blur_net_and_sampler_match_reference():
+  from helpers import build
+  from gddim_b200.blur import sampling as bs
+  g = ref("ref_blur_sampler.npz")
+  cfg, model, _ = build("blur_deep")
+  y = model.forward(g["net_x"], float(g["net_t"]))
+  assert rel_l2(y, g["net_y"]) < 2e-3
+  s = bsde.from_config(cfg)
+  x, n = bs.get_order0_sampler(s, model, (32, 32, 3), 2, 6, inv)(0, model, 2, u=g["order0_y"])
+  print(f"blur order0: rel_l2 vs reference {rel_l2(x, g['order0_x']):.2e}")
+  assert n == 6 and rel_l2(x, g["order0_x"]) < 1e-3
+  cfg.sampling.nfe = 5
+  xs, n = bs.get_sampling_fn(cfg, s, model, None, inv)(None, model, 2, u=g["order0_y"][None])
+  cfg.sampling.nfe = 50
+  assert n == 5 and xs.shape == g["p_order0_x"].shape and rel_l2(xs[0], g["p_order0_x"][0]) < 1e-3

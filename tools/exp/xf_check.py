@@ -28,7 +28,7 @@ np.save(sys.argv[3], y.cpu().numpy())
 def run(xf, B):
   out = tempfile.mktemp(suffix=".npy")
   env = dict(os.environ, GDDIM_XF="1" if xf else "0")
-  r = subprocess.run([sys.executable, "-c", CHILD, ROOT, str(B), out], env=env, capture_output=True, text=True, timeout=600)
+  r = subprocess.run([sys.executable, "-c", CHILD, ROOT, str(B), out], env=env, capture_output=True, text=True, timeout=150)
   print(f"--- GDDIM_XF={int(xf)} batch {B}: rc={r.returncode}\n{r.stdout[-400:]}{r.stderr[-800:]}")
   return np.load(out) if r.returncode == 0 and os.path.exists(out) else None
 
