@@ -12,6 +12,7 @@ The reference's own JAX/XLA path cannot run in this image (jax/flax absent, SURV
 and `cpu_baseline` time the torch-CPU fp32 restatement of the same sampler ("port"), never labelled JAX.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -27,6 +28,7 @@ if ROOT not in sys.path:
 
 METRIC = "CIFAR10 32x32 images/sec @ 50 NFE deis_order=2 (CLD, deep NCSN++)"
 GFLOP_PER_IMG_EVAL = {"deep": 37.168, "ddpmpp": 21.707}
+TRAFFIC_FILE = "r02_gemm_traffic.json"                         # ncu DRAM pass of the GEMM family (tools/profile.sh)
 
 
 def parse():
@@ -45,7 +47,18 @@ def parse():
                   help="cld = BASELINE configs 2/4/5 (default: config 2); blur = config 3 (order-0 DDIM in DCT space)")
   ap.add_argument("--image-size", type=int, default=32, help="256 = BASELINE config 5 geometry (use --batch 8)")
   ap.add_argument("--profile-csv", default="", help="write the per-op timing table of one profiled step here")
-  return ap.parse_args()
+  ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4, 5],
+                  help="BASELINE.json configs[k-1] preset (per-GPU sizes; 2 = the default the driver runs): "
+                       "1 = deep CLD, batch 4, NFE 10, order 0; 2 = deep CLD, batch 256, NFE 50, order 2; "
+                       "3 = blur, batch 256, NFE 50; 4 = deep CLD, order 3, 256 per GPU (global 2048 on 8 GPUs); "
+                       "5 = deep CLD at 256x256, order 2, 8 per GPU (global 64 on 8 GPUs)")
+  args = ap.parse_args()
+  preset = {1: dict(batch=4, nfe=10, order=0), 2: dict(batch=256, nfe=50, order=2),
+            3: dict(workload="blur", batch=256, nfe=50), 4: dict(batch=256, nfe=50, order=3),
+            5: dict(image_size=256, batch=8, nfe=50, order=2)}.get(args.config, {})
+  for k, v in preset.items():
+    setattr(args, k, v)
+  return args
 
 
 def make_cfg(name, workload="cld", image_size=32):
@@ -120,12 +133,14 @@ def run_reference(args):
   rank = int(os.environ.get("RANK", 0))
   if rank != 0:
     return
-  from gddim_b200 import net
+  # parameter inventory from the ORACLE's own walk (oracle.ncsnpp.collect_specs) and the plain-python generator: this arm
+  # never loads libgddim_b200.so (gddim_b200.configs / params are data-only modules)
+  from gddim_b200 import params as gparams
+  from oracle import ncsnpp as on
   cfg = make_cfg(args.net)
-  model = net.ScoreNet(cfg, cld=True)
-  params = model.init_params(seed=1234, nondegenerate=True)
+  params = gparams.generate(on.collect_specs(cfg, cld=True), seed=1234, nondegenerate=True)
   threads = os.cpu_count() or 1
-  batch = args.cpu_batch or 2
+  batch = args.cpu_batch or 8
   for _ in range(max(args.warmup, 0)):
     cpu_port_sample(cfg, params, batch, min(args.nfe, 4), args.order, threads)     # short warm-up (thread pools, caches)
   t = 0.0
@@ -237,7 +252,7 @@ def run_ours(args):
   d2h = sum(o.nbytes for o in outs[:-1])           # (xs, vs) for CLD, (xs,) for blur; the last item is nfe
 
   # ---- roofline of the dominant kernel (conv_gemm_umma) from one profiled step ------------------------------
-  roof = None
+  roof, roof_hbm = None, None
   if rank == 0:
     model.set_profile(True)
     core.run(model, B, u_dev)
@@ -258,14 +273,37 @@ def run_ours(args):
     # DRAM bytes per launch of the same kernel family from the committed ncu pass (profiles/, tools/profile.sh)
     traffic = None
     try:
-      traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))["dram_bytes_per_launch"]
+      tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
+      traffic, traffic_commit = tj["dram_bytes_per_launch"], tj.get("commit", "unrecorded")
     except Exception:
-      pass
+      traffic_commit = None
+    # ---- HBM-bound kernel families against the measured copy bandwidth ---------------------------------------------
+    hbm_peak = peaks.get("hbm_gbs", 6500.0)
+    norm_bytes = model.get_profile_norm_bytes()
+    gn_ms = ms_kind["groupnorm"]
+    upd_ms, upd_bytes = C.c_double(), C.c_double()
+    from gddim_b200 import _lib as glib
+    glib.check(glib.lib().gddim_sampler_time_update(core.handle(model, B), B, 50, C.byref(upd_ms), C.byref(upd_bytes),
+                                                    stream.cuda_stream), "gddim_sampler_time_update")
+    torch.cuda.synchronize()
+    roof_hbm = {
+        "peak": hbm_peak, "unit": "GB/s",
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, read+write)" if peaks else "fallback 6.5 TB/s",
+        "groupnorm": {"kernels": "gn_coef / gn_apply<*> / gn_small / gn_stats (all OP_NORM launches of one step)",
+                      "bytes": norm_bytes, "ms": gn_ms, "achieved": norm_bytes / (gn_ms * 1e-3) * 1e-9 if gn_ms > 0 else 0.0,
+                      "frac": (norm_bytes / (gn_ms * 1e-3) * 1e-9) / hbm_peak if gn_ms > 0 else 0.0,
+                      "bytes_def": "fp32 source read once (+ once more where the statistics are not produced by the GEMM epilogue), fp16 outputs written once"},
+        "update": {"kernel": "blur_step_kernel" if blur else "cld_step_c3_kernel",
+                   "bytes_per_launch": upd_bytes.value, "avg_launch_ms": upd_ms.value,
+                   "achieved": upd_bytes.value / (upd_ms.value * 1e-3) * 1e-9 if upd_ms.value > 0 else 0.0,
+                   "frac": (upd_bytes.value / (upd_ms.value * 1e-3) * 1e-9) / hbm_peak if upd_ms.value > 0 else 0.0,
+                   "bytes_def": "(order+3) x 24576 B per image (CLD) / 4 x 12288 B per image (blur), SURVEY.md 8d; 50 launches timed one by one, L2 flushed (256 MB memset) before each"}}
     roof = {"bound": "tensor", "kernel": "conv_gemm_umma_kernel (all conv3x3 / 1x1 / NIN GEMM launches; the fused QK^T-softmax-PV kernel is the separate 'attention' family)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
             "flop_per_launch": gemm_flops / max(gemm_launches, 1),
-            "traffic": traffic, "launches": gemm_launches, "avg_launch_ms": ms_kind["conv_gemm"] / max(gemm_launches, 1),
+            "traffic": traffic, "traffic_source": f"profiles/{TRAFFIC_FILE} (ncu dram bytes, measured at commit {traffic_commit})",
+            "launches": gemm_launches, "avg_launch_ms": ms_kind["conv_gemm"] / max(gemm_launches, 1),
             "share_of_step": ms_kind["conv_gemm"] / tot if tot else None,
             "ms_by_kernel_family": {k: round(v_, 3) for k, v_ in ms_kind.items()}}
 
@@ -276,7 +314,7 @@ def run_ours(args):
   cpu = None
   if world == 1 and not args.no_cpu_baseline and default_workload:
     threads = os.cpu_count() or 1
-    cb = args.cpu_batch or 2
+    cb = args.cpu_batch or 8
     v_cpu, dt = cpu_port_sample(cfg, model.params, cb, nfe, order, threads)
     cpu = {"value": v_cpu, "unit": "images/s", "cores": threads, "kind": "port",
            "sample": f"{cb} image(s) x {nfe} NFE, same net/sampler, torch-CPU fp32 restatement of the reference "
@@ -303,7 +341,7 @@ def run_ours(args):
                      "l2": f"working set >> L2: {model.workspace_bytes() / 2**30:.2f} GiB of activations+weights per evaluation"},
           "tensor_frac_end_to_end": value * flop_img / (world * 1e12 * (roof["peak"] if roof else 1400.0)),
           "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-          "gpu_launches": int(launches), "clocks": clk, "roofline": roof}
+          "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_hbm": roof_hbm}
   if cpu is not None:
     line["cpu_baseline"] = cpu
   print(json.dumps(line), flush=True)

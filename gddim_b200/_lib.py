@@ -77,6 +77,7 @@ SIGNATURES = {
     "gddim_ctx_set_profile": (C.c_int, [_P, C.c_int]),
     "gddim_ctx_get_profile": (C.c_int, [_P, _P, _P, _P]),
     "gddim_ctx_dump_profile": (C.c_int, [_P, C.c_char_p]),
+    "gddim_ctx_get_profile_hbm": (C.c_int, [_P, _P]),
     "gddim_unet_forward": (C.c_int, [_P, _P, C.c_float, _P, C.c_int, _P]),
     "gddim_cld_create": (C.c_int, [C.c_double] * 6 + [C.c_int, C.POINTER(_P)]),
     "gddim_cld_destroy": (None, [_P]),
@@ -112,12 +113,15 @@ SIGNATURES = {
     "gddim_cld_mldeis_coef": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
     "gddim_cld_psi1": (C.c_int, [_P, C.c_double, C.c_int, _P]),
     "gddim_sampler_destroy": (None, [_P]),
+    "gddim_sampler_alive": (C.c_int, [_P]),
+    "gddim_sampler_set_seed": (C.c_int, [_P, C.c_ulonglong]),
     "gddim_sampler_coef": (C.c_longlong, [_P, _P, C.c_longlong]),
     "gddim_sampler_num_steps": (C.c_int, [_P]),
     "gddim_sampler_rev_ts": (C.c_int, [_P, _P, C.c_int]),
     "gddim_sample": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "gddim_sample_noise": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "gddim_sampler_launch_count": (C.c_longlong, [_P]),
+    "gddim_sampler_time_update": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
 }
 
 _lib = None

@@ -36,12 +36,13 @@ class _Sampler:
     self.inverse_scaler = inverse_scaler
     self.mul, self.add, self.affine = _affine_of(inverse_scaler)
     self.use_graph = use_graph
-    self._h, self._ctx_id, self._net = None, None, None
+    self._h, self._gen, self._net = None, None, None
 
   def _destroy(self):
     if self._h is not None:
       _lib.lib().gddim_sampler_destroy(self._h)
       self._h = None
+    self._gen = None
 
   def __del__(self):
     try:
@@ -51,7 +52,8 @@ class _Sampler:
 
   def handle(self, net, batch):
     ctx = net.ensure(batch)
-    if self._h is not None and self._ctx_id == ctx.value and self._net is net:
+    # tied to ONE network context: reused only while that context lives (see cld/sampling.py _Sampler._current)
+    if self._h is not None and self._net is net and self._gen == net.generation and _lib.lib().gddim_sampler_alive(self._h):
       return self._h
     self._destroy()
     cfg = _lib.SamplerCfg(kind=_lib.BLUR_ORDER0, nfe=self.nfe, deis_order=0, ts_order=self.ts_order, denoising=0,
@@ -60,7 +62,8 @@ class _Sampler:
     h = C.c_void_p()
     _lib.check(_lib.lib().gddim_sampler_create(ctx, C.byref(cfg), None, self.sde._h, C.byref(h)),
                "gddim_sampler_create")
-    self._h, self._ctx_id, self._net = h, ctx.value, net
+    self._h, self._gen, self._net = h, net.generation, net
+    net.register_sampler(self)
     return h
 
   def launch_count(self):

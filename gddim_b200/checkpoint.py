@@ -41,9 +41,12 @@ def _ext_hook(code, data):
 def _unchunk(tree):
   if isinstance(tree, dict):
     if tree.get(_CHUNK_KEY):
-      shape = tuple(tree["shape"])
+      # flax.serialization._chunk: 'shape' and 'chunks' are _tuple_to_dict(...) = {'0': v0, '1': v1, ...}
+      sh = tree["shape"]
+      shape = tuple(int(sh[k]) for k in sorted(sh, key=int)) if isinstance(sh, dict) else tuple(int(v) for v in sh)
       chunks = tree["chunks"]
-      parts = [np.asarray(chunks[k]).ravel() for k in sorted(chunks, key=int)]
+      seq = [chunks[k] for k in sorted(chunks, key=int)] if isinstance(chunks, dict) else list(chunks)
+      parts = [np.asarray(c).ravel() for c in seq]
       return np.concatenate(parts).reshape(shape)
     return {k: _unchunk(v) for k, v in tree.items()}
   return tree
@@ -61,8 +64,27 @@ def restore_bytes(data):
   return _unchunk(_decode_keys(tree))
 
 
-def load_flax_checkpoint(path):
-  with open(path, "rb") as f:
+def _natural_key(name):
+  import re
+  return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", name)]
+
+
+def resolve_checkpoint_path(ckpt_dir, step=None, prefix="checkpoint_"):
+  """flax.training.checkpoints.restore_checkpoint path rules: a file is taken as is; a directory yields
+  `<dir>/<prefix><step>` or, without `step`, the latest `<prefix>*` file in natural order (tmp files skipped)."""
+  import os
+  if not os.path.isdir(ckpt_dir):
+    return ckpt_dir
+  if step is not None:
+    return os.path.join(ckpt_dir, f"{prefix}{step}")
+  names = sorted((n for n in os.listdir(ckpt_dir) if n.startswith(prefix) and not n.endswith("tmp")), key=_natural_key)
+  if not names:
+    raise FileNotFoundError(f"no '{prefix}*' checkpoint in {ckpt_dir}")
+  return os.path.join(ckpt_dir, names[-1])
+
+
+def load_flax_checkpoint(path, step=None, prefix="checkpoint_"):
+  with open(resolve_checkpoint_path(path, step, prefix), "rb") as f:
     return restore_bytes(f.read())
 
 

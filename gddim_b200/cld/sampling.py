@@ -5,9 +5,11 @@
 process drives one GPU; multi-GPU runs launch one process per GPU and shard the batch axis).
 The whole loop (network evaluations + multistep updates + denoising step) runs inside libgddim_b200.so.
 
-Implemented: 'deis' (204-253), 'order0' (156-202, is_em=False), 'hybdeis' (255-269) and the stochastic 'sdeis'
-(380-427, on LambdaSDE).  'ldeis', 'mldeis', 'ode', 'sscs', 'em' are SURVEY.md 8(f) "next" rows and raise
-NotImplementedError; unknown names raise a bare RuntimeError exactly like sampling.py:152-153.
+All nine method names of sampling.py:57-151 dispatch: 'deis' (204-253), 'order0' (156-202, incl. is_em), 'hybdeis'
+(255-269), 'sdeis' (380-427, on LambdaSDE), 'ldeis' (497-540), 'mldeis' (272-378), 'em' (624-669), 'sscs' (542-622) as
+step programs executed by the library; 'ode' (432-495) drives gddim_unet_forward from scipy's RK45 on the host like the
+reference (only the network evaluation is native there: the 2x2 algebra runs as torch ops with one host round trip per
+RK45 stage).  Unknown names raise a bare RuntimeError exactly like sampling.py:152-153.
 """
 import ctypes as C
 
@@ -15,8 +17,6 @@ import numpy as np
 
 from .. import _lib
 from .. import net as _net
-
-_NEXT = ()
 
 
 def get_data_shape(config):
@@ -91,8 +91,6 @@ def get_sampling_fn(config, sde, model, shape, inverse_scaler):
                                 noise_nfe_ratio=config.sampling.noise_nfe_ratio,
                                 img_t_ratio=config.sampling.img_t_ratio, ts_order=config.sampling.ts_order,
                                 denoising=config.sampling.noise_removal, is_p=True)
-  if name in _NEXT:
-    raise NotImplementedError(f"sampler '{name}' is not part of the round-1 hot path (SURVEY.md 8f)")
   raise RuntimeError
 
 
@@ -109,12 +107,36 @@ class _Sampler:
     self.use_graph = use_graph
     self.rev_ts = None if rev_ts is None else np.ascontiguousarray(np.asarray(rev_ts, np.float64))
     self.lambda_coef, self.use_order0, self.seed = float(lambda_coef), bool(use_order0), 0
-    self._h, self._ctx_id, self._net = None, None, None
+    self._h, self._gen, self._net = None, None, None
 
   def _destroy(self):
     if self._h is not None:
       _lib.lib().gddim_sampler_destroy(self._h)
       self._h = None
+    self._gen = None
+
+  def _current(self, net, batch):
+    """The C sampler is tied to ONE network context (weights, workspace, captured graphs): it is reused only while
+    that context lives (ScoreNet.generation counts re-creations -- a freed-and-reallocated ctx can have the same
+    address) and the library still reports it attached."""
+    ctx = net.ensure(batch)
+    if self._h is not None and self._net is net and self._gen == net.generation and \
+        _lib.lib().gddim_sampler_alive(self._h):
+      return ctx, True
+    self._destroy()
+    return ctx, False
+
+  def _adopt(self, h, net):
+    self._h, self._gen, self._net = h, net.generation, net
+    net.register_sampler(self)
+    _lib.check(_lib.lib().gddim_sampler_set_seed(h, int(self.seed)), "gddim_sampler_set_seed")
+    return h
+
+  def set_seed(self, seed):
+    """Key of the internally drawn noise for the following calls (no rebuild; cf. gddim_sampler_set_seed)."""
+    self.seed = int(seed) % (2 ** 64)
+    if self._h is not None and _lib.lib().gddim_sampler_alive(self._h):
+      _lib.check(_lib.lib().gddim_sampler_set_seed(self._h, self.seed), "gddim_sampler_set_seed")
 
   def __del__(self):
     try:
@@ -123,10 +145,9 @@ class _Sampler:
       pass
 
   def handle(self, net, batch):
-    ctx = net.ensure(batch)
-    if self._h is not None and self._ctx_id == ctx.value and self._net is net:
+    ctx, ok = self._current(net, batch)
+    if ok:
       return self._h
-    self._destroy()
     cfg = _lib.SamplerCfg(kind=self.kind, nfe=self.nfe, deis_order=self.order, ts_order=self.ts_order,
                           denoising=int(self.denoising), mixed_score=int(bool(self.sde.mixed_score)),
                           use_graph=int(self.use_graph), x_mul=self.mul if self.affine else 1.0,
@@ -139,8 +160,7 @@ class _Sampler:
       rc = _lib.lib().gddim_sampler_create_ts(ctx, C.byref(cfg), self.sde._h, None, self.rev_ts.ctypes.data,
                                                self.rev_ts.size, C.byref(h))
     _lib.check(rc, "gddim_sampler_create")
-    self._h, self._ctx_id, self._net = h, ctx.value, net
-    return h
+    return self._adopt(h, net)
 
   # -- introspection used by parity tests --------------------------------------------------------------
   def coef_table(self, net, batch):
@@ -197,37 +217,54 @@ class _Sampler:
     return x, v, self.nfe
 
 
-def _seed_of(rng):
+def _seed_of(rng, rank=None):
+  """64-bit Philox key from whatever the caller passes as `rng` (jax PRNGKey uint32[2], int, None), with the process
+  rank folded in: under one-process-per-GPU every rank must draw different noise, like the per-device keys the
+  reference hands to pmap(sampler) (run_lib.py:718-722)."""
   if rng is None:
-    return 0
-  return int(np.asarray(rng).astype(np.uint64).ravel().sum() % (2 ** 63))
+    base = 0
+  else:
+    a = np.asarray(rng).astype(np.uint64).ravel()
+    base = 0
+    for w in a:                                    # order-sensitive mix (the old sum mapped (0,7) and (7,0) together)
+      base = (base * 0x9E3779B97F4A7C15 + int(w) + 0x7F4A7C15) % (2 ** 64)
+  if rank is None:
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+  return (base ^ ((rank * 0xD1B54A32D192ED03) % (2 ** 64))) % (2 ** 64)
 
 
 def _wrap(core, sde, data_shape, is_p):
+  stochastic = core.kind == _lib.CLD_SDEIS        # sdeis, and the em / sscs programs with a noise term
+
   def sampler(rng, state, batch_size, u=None, trace=False, noise=None):
     """sampling.py:212-230 (non-pmapped): u (B,H,W,C,2) -> (x, v, nfe)."""
     if u is None:
       from . import sde_lib as _sl
+      prior_rng = rng
       if _sl._is_jax_key(rng):                         # rng, step_rng = random.split(rng)   (sampling.py:213)
         from .. import jax_random
-        rng = jax_random.split(rng)[1]
-      u = sde.prior_sampling(rng, (batch_size,) + tuple(data_shape))
-    if core.kind == _lib.CLD_SDEIS and noise is None and _seed_of(rng) != core.seed:
-      core.seed = _seed_of(rng)          # a new key re-seeds the Philox stream (sampler object is rebuilt)
-      core._destroy()
+        prior_rng = jax_random.split(rng)[1]
+      u = sde.prior_sampling(prior_rng, (batch_size,) + tuple(data_shape))
+    if stochastic and noise is None:
+      core.set_seed(_seed_of(rng))                     # a new key = a new noise field; no rebuild
     return core.run(state, batch_size, u, trace=trace, noise=noise)
 
   def psampler(prng, pstate, batch_size, u=None):
-    """sampling.py:232-237: leading axis = local devices driven by this process (1)."""
+    """sampling.py:232-237: leading axis = local devices driven by this process (1).  `prng` carries one key per local
+    device ([1, 2] uint32); key 0 draws the prior when u is None and -- as in pmap(sampler)(prng, ...) -- seeds the
+    noise this device injects (stochastic samplers)."""
     import torch
+    rng = prng
+    if isinstance(prng, np.ndarray) and prng.dtype == np.uint32 and prng.ndim == 2 and prng.shape[1] == 2:
+      rng = prng[0]                                     # flax.jax_utils.unreplicate(prng)   (sampling.py:233)
     if u is None:
-      rng = prng                                        # flax.jax_utils.unreplicate(prng)   (sampling.py:233)
-      if isinstance(prng, np.ndarray) and prng.dtype == np.uint32 and prng.ndim == 2 and prng.shape[1] == 2:
-        rng = prng[0]
       u = sde.prior_sampling(rng, (1, batch_size) + tuple(data_shape))
     if u.shape[0] != 1:
       raise ValueError("this process drives one GPU: the leading device axis of u must be 1 "
                        "(launch one process per GPU and shard the batch, see bench.py)")
+    if stochastic:
+      core.set_seed(_seed_of(rng))
     x, v, nfe = core.run(pstate, batch_size, u[0])
     if torch.is_tensor(x):
       return x[None], v[None], nfe
@@ -266,13 +303,6 @@ def get_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, ts
   core = _Sampler(_lib.CLD_DEIS, sde, model, data_shape, nfe, inverse_scaler, deis_order, int(ts_order), denoising,
                   is_p)
   return _wrap(core, sde, data_shape, is_p)
-
-
-def _next(name):
-  def f(*a, **k):
-    raise NotImplementedError(f"{name} is not part of the round-1 hot path (SURVEY.md 8f)")
-  f.__name__ = name
-  return f
 
 
 def _impl_deis_sampler(sde, model, data_shape, nfe, inverse_scaler, deis_order, rev_ts, denoising=False, is_p=False):
@@ -323,10 +353,9 @@ class _ProgramSampler(_Sampler):
     self.n_noise = sum(1 for st in steps if any(st.F))
 
   def handle(self, net, batch):
-    ctx = net.ensure(batch)
-    if self._h is not None and self._ctx_id == ctx.value and self._net is net:
+    ctx, ok = self._current(net, batch)
+    if ok:
       return self._h
-    self._destroy()
     cfg = _lib.SamplerCfg(kind=_lib.CLD_PROGRAM, nfe=self.nfe, deis_order=0, ts_order=2, denoising=int(self.denoising),
                           mixed_score=int(bool(self.sde.mixed_score)), use_graph=int(self.use_graph),
                           x_mul=self.mul if self.affine else 1.0, x_add=self.add if self.affine else 0.0,
@@ -335,8 +364,7 @@ class _ProgramSampler(_Sampler):
     h = C.c_void_p()
     _lib.check(_lib.lib().gddim_sampler_create_program(ctx, C.byref(cfg), arr, len(self.steps), self.history, C.byref(h)),
                "gddim_sampler_create_program")
-    self._h, self._ctx_id, self._net = h, ctx.value, net
-    return h
+    return self._adopt(h, net)
 
 
 def _step(t=-1.0, A=None, Cs=(), F=None, M=None, first_eps=0, trace=0, P=None):

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -21,9 +22,11 @@ using namespace gddim;
 static thread_local std::string g_err;
 static int set_err(const std::string& m) { g_err = m; return -1; }
 
+struct gddim_sampler;
 struct gddim_ctx {
   int device;
   std::unique_ptr<UNet> net;
+  std::vector<gddim_sampler*> samplers;   // samplers built on this context: orphaned (not freed) by gddim_ctx_destroy
 };
 struct gddim_cld { std::unique_ptr<CldTables> t; };
 struct gddim_blur { std::unique_ptr<BlurTables> t; };
@@ -37,7 +40,7 @@ struct gddim_sampler {
   std::vector<float> coef;            // CLD: [n_steps][per][4], per = order+3 (deis/order0) or order+4 (sdeis)
   int per = 0;
   std::vector<float> nfac;            // sdeis: [n_steps][4] factor applied to the standard normals
-  unsigned long long calls = 0;       // sample calls so far
+  int capacity = 0;                   // images the sampler's own buffers were sized for (= the context's max_batch then)
   std::vector<gddim_step> program;    // GDDIM_CLD_PROGRAM: explicit step list
   int history = 1;
   float den_A[4], den_C[4];
@@ -77,9 +80,15 @@ int gddim_ctx_create(int device, const gddim_model_cfg* cfg, int max_batch, gddi
   *out = c.release();
   return 0;
 }
+static void free_sampler_buffers(gddim_sampler* s);
+static void orphan_sampler(gddim_sampler* s);
 void gddim_ctx_destroy(gddim_ctx* ctx) {
   if (!ctx) return;
   if (ctx->net && ctx->net->finalized()) cudaSetDevice(ctx->device);
+  // samplers hold a raw ctx*, buffers sized for this context's max_batch and CUDA graphs with its weight / workspace
+  // pointers baked in: release their device state now and orphan them, so that a stale handle fails loudly in
+  // gddim_sample* instead of replaying freed memory (the handle itself stays valid until gddim_sampler_destroy)
+  for (gddim_sampler* s : ctx->samplers) orphan_sampler(s);
   delete ctx;
 }
 int gddim_param_count(const gddim_ctx* ctx) { return ctx ? (int)ctx->net->specs().size() : -1; }
@@ -137,6 +146,11 @@ int gddim_ctx_set_profile(gddim_ctx* ctx, int on) {
 int gddim_ctx_get_profile(const gddim_ctx* ctx, double* ms_by_kind, double* gemm_flops, long long* gemm_launches) {
   if (!ctx || !ms_by_kind) return set_err("gddim_ctx_get_profile: bad arguments");
   ctx->net->get_profile(ms_by_kind, gemm_flops, gemm_launches);
+  return 0;
+}
+int gddim_ctx_get_profile_hbm(const gddim_ctx* ctx, double* norm_bytes) {
+  if (!ctx || !norm_bytes) return set_err("gddim_ctx_get_profile_hbm: bad arguments");
+  *norm_bytes = ctx->net->profile_norm_bytes();
   return 0;
 }
 int gddim_ctx_dump_profile(const gddim_ctx* ctx, const char* path) {
@@ -434,12 +448,22 @@ static void free_sampler_buffers(gddim_sampler* s) {
   s->graphs.clear();
   cudaFree(s->d_temb_all); cudaFree(s->d_u); cudaFree(s->d_xin); cudaFree(s->d_stage); cudaFree(s->d_x);
   cudaFree(s->d_v); cudaFree(s->d_blur_a); cudaFree(s->d_blur_b);
+  s->d_temb_all = s->d_u = s->d_xin = s->d_stage = s->d_x = s->d_v = s->d_blur_a = s->d_blur_b = nullptr;
   for (auto p : s->d_eps) cudaFree(p);
   s->d_eps.clear();
   if (s->own_stream) cudaStreamDestroy(s->own_stream);
   if (s->ev_in) cudaEventDestroy(s->ev_in);
   if (s->ev_out) cudaEventDestroy(s->ev_out);
   s->own_stream = nullptr; s->ev_in = s->ev_out = nullptr;
+}
+static void orphan_sampler(gddim_sampler* s) {
+  free_sampler_buffers(s);
+  s->ctx = nullptr;
+  s->capacity = 0;
+}
+static void attach_sampler(gddim_ctx* ctx, gddim_sampler* s) {
+  s->capacity = ctx->net->max_batch();
+  ctx->samplers.push_back(s);
 }
 
 int gddim_sampler_create(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const gddim_cld* cld, const gddim_blur* blur,
@@ -567,6 +591,7 @@ int gddim_sampler_create_ts(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, const 
     free_sampler_buffers(s.get());
     return set_err(std::string("gddim_sampler_create: device allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
   }
+  attach_sampler(ctx, s.get());
   *out = s.release();
   return 0;
 }
@@ -621,15 +646,28 @@ int gddim_sampler_create_program(gddim_ctx* ctx, const gddim_sampler_cfg* cfg, c
     free_sampler_buffers(s.get());
     return set_err("gddim_sampler_create_program: device allocation failed");
   }
+  attach_sampler(ctx, s.get());
   *out = s.release();
   return 0;
 }
 
 void gddim_sampler_destroy(gddim_sampler* s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->device);
-  free_sampler_buffers(s);
+  if (s->ctx) {                                  // still attached: detach from the context, then free
+    cudaSetDevice(s->ctx->device);
+    auto& v = s->ctx->samplers;
+    v.erase(std::remove(v.begin(), v.end(), s), v.end());
+    free_sampler_buffers(s);
+  }
   delete s;
+}
+
+int gddim_sampler_alive(const gddim_sampler* s) { return (s && s->ctx) ? 1 : 0; }
+
+int gddim_sampler_set_seed(gddim_sampler* s, unsigned long long seed) {
+  if (!s) return set_err("gddim_sampler_set_seed: bad arguments");
+  s->cfg.seed = seed;                            // read at launch time: no rebuild, graphs stay valid
+  return 0;
 }
 
 long long gddim_sampler_coef(const gddim_sampler* s, float* out, long long cap) {
@@ -694,9 +732,10 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
   if (!s || !u || !x) return set_err("gddim_sample: bad arguments");
   if (noise_dev != nullptr && s->cfg.kind != GDDIM_CLD_SDEIS && s->cfg.kind != GDDIM_CLD_PROGRAM)
     return set_err("gddim_sample_noise: explicit noise is for the stochastic samplers");
-  s->calls += 1;
+  if (!s->ctx) return set_err("gddim_sample: the network context this sampler was built on has been destroyed");
   UNet& net = *s->ctx->net;
-  if (batch < 1 || batch > net.max_batch()) return set_err("gddim_sample: batch exceeds the context's max_batch");
+  if (batch < 1 || batch > s->capacity || batch > net.max_batch())
+    return set_err("gddim_sample: batch exceeds the capacity the sampler was created with");
   if (cudaSetDevice(s->ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
   cudaStream_t caller = (cudaStream_t)stream;
   cudaStream_t st = caller;
@@ -861,5 +900,61 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
 }
 
 long long gddim_sampler_launch_count(const gddim_sampler* s) { return s ? s->launches : -1; }
+
+// Measurement hook (bench.py's HBM roofline leg): the sampler's own per-step update kernel -- cld_step at full order
+// (reads u and order+1 ring slots, writes u) or blur_step (reads y and eps, writes y and the next network input) --
+// launched `iters` times on the sampler's buffers, each from a flushed L2, timed one by one with CUDA events on `stream`.
+int gddim_sampler_time_update(gddim_sampler* s, int batch, int iters, double* ms_per_launch, double* bytes_per_launch,
+                              void* stream) {
+  if (!s || !s->ctx || iters < 1 || !ms_per_launch || !bytes_per_launch) return set_err("gddim_sampler_time_update: bad arguments");
+  if (batch < 1 || batch > s->capacity) return set_err("gddim_sampler_time_update: batch exceeds the sampler's capacity");
+  if (s->cfg.kind == GDDIM_CLD_PROGRAM) return set_err("gddim_sampler_time_update: not available for step programs");
+  if (cudaSetDevice(s->ctx->device) != cudaSuccess) return set_err("cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  UNet& net = *s->ctx->net;
+  const long long n_pix = (long long)batch * s->S * s->S;
+  const size_t state_bytes = (size_t)n_pix * net.net_channels() * 4;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = 0;
+  auto one = [&]() -> int {
+    if (s->is_blur)
+      return blur_step_launch(s->d_u, s->d_eps[0], s->d_blur_a, s->d_blur_b, s->d_u, s->d_xin, batch, s->C, st);
+    CldStepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u = s->d_u; a.u_out = s->d_u; a.n_pix = n_pix; a.C = s->C;
+    a.n_eps = s->order + 1;
+    const float ident[4] = {1.f, 0.f, 0.f, 1.f};
+    memcpy(a.coef[0], ident, 16);                       // identity: the state stays finite over many launches
+    for (int j = 0; j <= s->order; ++j) a.eps[j] = s->d_eps[j];
+    return cld_step_launch(&a, st);
+  };
+  // every timed launch starts from a flushed L2 (a 256 MB memset in between), as in the sampler where a whole network
+  // evaluation runs between two updates; launches are timed one by one
+  void* flush = nullptr;
+  const size_t flush_bytes = (size_t)256 << 20;
+  if (cudaMalloc(&flush, flush_bytes) != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return set_err("gddim_sampler_time_update: cudaMalloc failed"); }
+  for (int i = 0; i < 3 && !rc; ++i) rc = one();
+  double total = 0.0;
+  for (int i = 0; i < iters && !rc; ++i) {
+    cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
+    cudaEventRecord(e0, st);
+    rc = one();
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms1 = 0.f;
+    cudaEventElapsedTime(&ms1, e0, e1);
+    total += ms1;
+  }
+  cudaFree(flush);
+  const float ms = (float)total;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc) return set_err("gddim_sampler_time_update: launch failed");
+  *ms_per_launch = ms / iters;
+  // algorithmic bytes: CLD reads u + (order+1) eps, writes u' = (order+3) state arrays;
+  // blur reads y and eps, writes y' and the next network input = 4 arrays
+  *bytes_per_launch = s->is_blur ? 4.0 * (double)state_bytes : (double)(s->order + 3) * (double)state_bytes;
+  return 0;
+}
 
 }  // extern "C"

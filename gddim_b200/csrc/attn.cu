@@ -333,11 +333,11 @@ int attn_fused_prepare(AttnOp* op) {
 
 int attn_fused_launch(const AttnOp* op, int batch, cudaStream_t st) {
   if (!op->prepared || batch < 1 || batch > op->B) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     if (cudaFuncSetAttribute(attn256_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
     if (cudaFuncSetAttribute(attn256_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM) != cudaSuccess) return -2;
-    attr_set = true;
+    attr_set.done();
   }
   AttnArgs a;
   memset(&a, 0, sizeof(a));

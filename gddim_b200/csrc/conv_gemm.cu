@@ -680,20 +680,15 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
 template <int BN, int EPI, int MT, int CG = 1, bool HALO = false>
 static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
   using L = SmemLayout<BN, MT, CG>;
-  static bool attr_set = false;
+  static DeviceOnce attr_set;
   auto kern = conv_gemm_umma_kernel<BN, EPI, MT, CG, HALO>;
   const int smem_total = HALO ? op->stages * op->stage_bytes + L::BAR_BYTES + L::EPI_BYTES : L::TOTAL;
-  if (!attr_set) {
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO ? SMEM_BUDGET : L::TOTAL);
     if (e != cudaSuccess) GEMM_FAIL("cudaFuncSetAttribute(smem=%d): %s", L::TOTAL, cudaGetErrorString(e));
-    attr_set = true;
+    attr_set.done();
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int num_sms = device_sm_count();
   int num_sms_eff = num_sms;
   {
     static int cap = -1;                      // GDDIM_GEMM_MAX_CTAS: SM-partitioning experiments only
@@ -745,11 +740,13 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     a.colstats = op->colstats;
     a.n_store = op->n_store;
     a.reverse = op->reverse;
+#ifdef GDDIM_ABLATE      // timing-only epilogue ablations (results INVALID): compile with -DGDDIM_ABLATE, never in the product build
     {
       static int dbg = -1;
       if (dbg < 0) { const char* e = getenv("GDDIM_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
       a.dbg = dbg;
     }
+#endif
     if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX, 1>(op, a, st);
     a.stages = op->stages; a.stage_bytes = op->stage_bytes; a.a_bytes = op->a_bytes;
     if (op->halo) {

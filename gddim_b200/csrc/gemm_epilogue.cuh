@@ -7,6 +7,12 @@
 
 #include "ptx.cuh"
 
+#ifdef GDDIM_ABLATE
+#define GDDIM_DBG_STORE(p) ((p).dbg != 2)
+#else
+#define GDDIM_DBG_STORE(p) true
+#endif
+
 namespace gddim {
 
 constexpr int BLOCK_M = 128;
@@ -138,7 +144,9 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
   ptx::mbar_wait(cx.tfull, cx.tfull_phase);
   ptx::tc_fence_after();
   uint32_t r[32];
+#ifdef GDDIM_ABLATE
   if (p.dbg == 3) return;
+#endif
 #pragma unroll 1
   for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
     const int mi = q / NCH, c0 = (q % NCH) * 32;
@@ -153,7 +161,9 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
       res_nbase = p.residual + res_nmb * ldo + cx.n_tile0 + (qn % NCH) * 32 + c4;
     }
     ptx::tmem_ld_wait();
+#ifdef GDDIM_ABLATE
     if (p.dbg == 1) continue;
+#endif
 #pragma unroll
     for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ wx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
     __syncwarp();
@@ -181,7 +191,7 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
       }
       v.x = fmaf(v.x, scale, bsum.x); v.y = fmaf(v.y, scale, bsum.y);
       v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
-      if (ok && p.dbg != 2) {
+      if (ok && GDDIM_DBG_STORE(p)) {
         if (STATS) {
           cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
           cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y); cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);

@@ -199,10 +199,10 @@ int gn_qkv_prepare(GnQkvOp* op) {
 
 int gn_qkv_launch(const GnQkvOp* op, int batch, cudaStream_t st) {
   if (!op->prepared || batch < 1 || batch > op->B) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.need()) {
     if (cudaFuncSetAttribute(gn_qkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GQ_SMEM) != cudaSuccess) return -2;
-    attr_set = true;
+    attr_set.done();
   }
   GnQkvArgs a;
   memset(&a, 0, sizeof(a));

@@ -152,13 +152,7 @@ int norm_launch(const NormOp* op, cudaStream_t st);
 int norm_num_launches(const NormOp* op);   // kernels norm_launch issues for this op (1 or 2)
 int norm_splits(int B, int H, int W);
 
-// ---- small direct convolutions and data movement (small.cu) ---------------------------------------
-// 3x3 SAME conv with few input channels (stem): in fp32 [B,H,W,cin] -> out32 [B,H,W,cout]
-int stem_conv_launch(const float* in, const float* w /*[3,3,cin,cout]*/, const float* bias, float* out32, int B,
-                     int H, int W, int cin, int cout, cudaStream_t st);
-// 3x3 SAME conv with few output channels (head): in fp16 [B,H,W,cin] -> out32 [B,H,W,cout]
-int head_conv_launch(const __half* in, const float* w /*[3,3,cin,cout]*/, const float* bias, float* out32, int B,
-                     int H, int W, int cin, int cout, cudaStream_t st);
+// ---- gathers and data movement (small.cu) ---------------------------------------------------------
 // FIR (pad 2, [1,3,3,1]x[1,3,3,1]/64) followed by the 3x3 stride-2 VALID window gather:
 // in fp32 [B,H,W,c] -> A16 [B,H/2,W/2,kpad] with k = tap*c + ch (zero padded to kpad)
 int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,

@@ -32,6 +32,22 @@ inline int pdl_attr(cudaLaunchAttribute* at, int n) {
   return n + 1;
 }
 
+// cudaFuncSetAttribute (max dynamic shared memory) and the SM count are PER DEVICE: one process may drive several
+// devices through several contexts, so "done once" flags are kept per (kernel, device), not per process.
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  static int dev() { int d = 0; cudaGetDevice(&d); return d; }
+  bool need() const { const int d = dev(); return d >= 64 || !((mask >> d) & 1ull); }
+  void done() { const int d = dev(); if (d < 64) mask |= 1ull << d; }
+};
+inline int device_sm_count() {
+  static int n[64] = {0};
+  const int d = DeviceOnce::dev();
+  if (d >= 64) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v; }
+  if (n[d] == 0) cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d);
+  return n[d];
+}
+
 template <typename... P, typename... A>
 inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -15,122 +15,6 @@ namespace gddim {
 
 static int ceil_div_ll(long long a, long long b) { return int((a + b - 1) / b); }
 
-// ---- stem: fp32 in [B,H,W,cin<=8] -> out32 [B,H,W,cout]; block = 4 image rows x all couts ------------------
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, float* __restrict__ out, int H,
-                                                       int W, int cin, int cout) {
-  pdl_entry();
-  extern __shared__ float sm[];
-  float* sw = sm;                              // [9*cin][cout]
-  float* sin_ = sm + 9 * cin * cout;           // [(rows+2)][W+2][cin]
-  const int rows = 4;
-  const int b = blockIdx.y;
-  const int y0 = blockIdx.x * rows;
-  for (int i = threadIdx.x; i < 9 * cin * cout; i += blockDim.x) sw[i] = w[i];
-  const int tw = W + 2;
-  for (int i = threadIdx.x; i < (rows + 2) * tw * cin; i += blockDim.x) {
-    const int ci = i % cin;
-    const int x = (i / cin) % tw - 1;
-    const int y = y0 + i / (cin * tw) - 1;
-    float v = 0.f;
-    if (x >= 0 && x < W && y >= 0 && y < H) v = in[(((long long)b * H + y) * W + x) * cin + ci];
-    sin_[i] = v;
-  }
-  __syncthreads();
-  const int total = rows * W * cout;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int co = i % cout;
-    const int x = (i / cout) % W;
-    const int r = i / (cout * W);
-    if (y0 + r >= H) continue;
-    float acc = bias ? bias[co] : 0.f;
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {
-        const float* ip = sin_ + ((r + ky) * tw + (x + kx)) * cin;
-        const float* wp = sw + ((ky * 3 + kx) * cin) * cout + co;
-        for (int ci = 0; ci < cin; ++ci) acc += ip[ci] * wp[ci * cout];
-      }
-    out[(((long long)b * H + y0 + r) * W + x) * cout + co] = acc;
-  }
-}
-
-int stem_conv_launch(const float* in, const float* w, const float* bias, float* out32, int B, int H, int W, int cin,
-                     int cout, cudaStream_t st) {
-  const size_t smem = (size_t)(9 * cin * cout + 6 * (W + 2) * cin) * sizeof(float);
-  if (smem > 200 * 1024) return -1;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = smem;
-  }
-  dim3 grid((H + 3) / 4, B);
-  launch_k(stem_conv_kernel, dim3(grid), dim3(256), smem, st, in, w, bias, out32, H, W, cin, cout);
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-
-// ---- head: fp16 in [B,H,W,cin] -> out32 [B,H,W,cout<=8]; one warp per output pixel ---------------------------
-template <int COUT>
-__global__ void __launch_bounds__(256) head_conv_kernel(const __half* __restrict__ in, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, float* __restrict__ out, int B,
-                                                       int H, int W, int cin) {
-  pdl_entry();
-  extern __shared__ float sw[];                // [9*cin][COUT]
-  for (int i = threadIdx.x; i < 9 * cin * COUT; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long npix = (long long)B * H * W;
-  for (long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); pix < npix; pix += (long long)gridDim.x * 8) {
-    const int x = int(pix % W), y = int((pix / W) % H);
-    const long long b = pix / ((long long)W * H);
-    float acc[COUT];
-#pragma unroll
-    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = y + ky - 1;
-      if (yy < 0 || yy >= H) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = x + kx - 1;
-        if (xx < 0 || xx >= W) continue;
-        const __half* ip = in + ((b * H + yy) * W + xx) * cin;
-        const float* wp = sw + (ky * 3 + kx) * cin * COUT;
-        for (int ci = lane * 2; ci < cin; ci += 64) {
-          const float2 v = __half22float2(*reinterpret_cast<const __half2*>(ip + ci));
-#pragma unroll
-          for (int j = 0; j < COUT; ++j) acc[j] += v.x * wp[ci * COUT + j] + v.y * wp[(ci + 1) * COUT + j];
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < COUT; ++j) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-    }
-    if (lane < COUT) {
-      float v = 0.f;
-#pragma unroll
-      for (int j = 0; j < COUT; ++j) if (lane == j) v = acc[j];
-      out[pix * COUT + lane] = v + (bias ? bias[lane] : 0.f);
-    }
-  }
-}
-
-int head_conv_launch(const __half* in, const float* w, const float* bias, float* out32, int B, int H, int W, int cin,
-                     int cout, cudaStream_t st) {
-  const size_t smem = (size_t)9 * cin * cout * sizeof(float);
-  if (smem > 48 * 1024 || cin % 2 != 0) return -1;
-  const long long npix = (long long)B * H * W;
-  int grid = ceil_div_ll(npix, 8);
-  if (grid > 148 * 16) grid = 148 * 16;
-  switch (cout) {
-    case 3: launch_k(head_conv_kernel<3>, dim3(grid), dim3(256), smem, st, in, w, bias, out32, B, H, W, cin); break;
-    case 6: launch_k(head_conv_kernel<6>, dim3(grid), dim3(256), smem, st, in, w, bias, out32, B, H, W, cin); break;
-    case 1: launch_k(head_conv_kernel<1>, dim3(grid), dim3(256), smem, st, in, w, bias, out32, B, H, W, cin); break;
-    case 2: launch_k(head_conv_kernel<2>, dim3(grid), dim3(256), smem, st, in, w, bias, out32, B, H, W, cin); break;
-    default: return -3;
-  }
-  return cudaGetLastError() == cudaSuccess ? 0 : -2;
-}
-
 // ---- input pyramid: FIR (pad 2) then 3x3 stride-2 VALID window gather -> GEMM A operand ---------------------
 __global__ void __launch_bounds__(256) im2col_fir_down_kernel(const float* __restrict__ in, __half* __restrict__ a16,
                                                              int B, int H, int W, int c, int kpad, int use_fir,

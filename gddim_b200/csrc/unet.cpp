@@ -869,6 +869,7 @@ int UNet::finalize() {
       if (attn_fused_prepare(&op.attn) != 0) return fail(std::string("attn_fused_prepare(") + op.tag + "): " + gemm_last_error());
     }
   }
+#ifdef GDDIM_WITH_XF       // experimental kernel: only in builds made with `make XF=1`, never in the default library
   {
     // EXPERIMENTAL (GDDIM_XF=1, not validated on hardware yet): GroupNorm + swish applied on load inside the following
     // 3x3 convolution (conv_xf.cu).  Pattern: a non-resampling NormOp whose normalised output feeds only the next op, a
@@ -894,6 +895,7 @@ int UNet::finalize() {
       fprintf(stderr, "gddim: GDDIM_XF=1: %d convolutions take their A operand through the normalise-on-load kernel\n", n_xf);
     }
   }
+#endif
   if (cudaDeviceSynchronize() != cudaSuccess) return fail("device error during finalize");
   finalized_ = true;
   return 0;
@@ -944,16 +946,13 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
     for (auto& e : prof_ev_) cudaEventCreate(&e);
     prof_op_ms_.assign(ops_.size(), 0.0);
     prof_op_flops_.assign(ops_.size(), 0.0);
+    prof_op_bytes_.assign(ops_.size(), 0.0);
   }
   size_t op_idx = 0;
   if (prof) cudaEventRecord(prof_ev_[0], st);
   for (auto& op : ops_) {
     int rc = 0;
     switch (op.kind) {
-      case OP_STEM:
-        rc = stem_conv_launch(x_dev, op.w, op.bias, op.f_out, batch, op.H, op.W, op.cin, op.cout, st);
-        launches_ += 1;
-        break;
       case OP_NORM: {
         NormOp n = op.norm;
         n.B = batch;
@@ -966,16 +965,15 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         g.B = batch;
         if (op.out_is_external) g.out32 = out_dev;
         g.m_tiles = (int)(((long long)batch * g.H * g.W + 128 * g.m_sub - 1) / (128 * g.m_sub));
+#ifdef GDDIM_WITH_XF
         if (g.xf) rc = conv_xf_launch(&g, st);     // (the A operand tensor does not exist for these layers)
-        else rc = gemm_launch(&g, gemm_impl, st);
+        else
+#endif
+        rc = gemm_launch(&g, gemm_impl, st);
         if (rc) return fail(std::string("gemm_launch(") + op.tag + "): " + gemm_last_error());
         launches_ += (gemm_impl == 1 && g.epi == EPI_SOFTMAX) ? 2 : 1;
         break;
       }
-      case OP_HEAD:
-        rc = head_conv_launch(op.h_in, op.w, op.bias, out_dev, batch, op.H, op.W, op.cin, op.cout, st);
-        launches_ += 1;
-        break;
       case OP_IM2COL:
         if (op.use_fir == 2)
           rc = im2col_same3x3_launch(x_dev, op.h_out, batch, op.H, op.W, op.cin, op.kpad, kRawScale, 1, st);
@@ -1026,6 +1024,20 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         for (int s2 = 0; s2 < g.nseg; ++s2) k += (double)g.seg[s2].taps * g.seg[s2].c;
         prof_op_flops_[i] = 2.0 * batch * g.H * g.W * (double)g.N * k;
       }
+      if (ops_[i].kind == OP_NORM) {
+        // algorithmic HBM bytes of the GroupNorm(+swish, +resample) pass: fp32 source read once (twice when the
+        // statistics do not come from the producer's epilogue), fp16 outputs written once
+        const NormOp& n = ops_[i].norm;
+        const double in_el = (double)batch * n.H * n.W * (n.c1 + n.c2);
+        const double f = (n.resample == RS_FIR_DOWN || n.resample == RS_NAIVE_DOWN) ? 0.25
+                       : ((n.resample == RS_FIR_UP || n.resample == RS_NAIVE_UP) ? 4.0 : 1.0);
+        const bool stats_pass = n.colstats1 == nullptr || (n.src2 != nullptr && n.colstats2 == nullptr);
+        double b = 0;
+        if (!n.coef_only || stats_pass) b += 4.0 * in_el * ((stats_pass && !n.coef_only) ? 2.0 : 1.0);
+        if (n.dst16) b += 2.0 * in_el * f;
+        if (n.raw16) b += 2.0 * in_el * f;
+        prof_op_bytes_[i] = b;
+      }
     }
     ++prof_forwards_;
   }
@@ -1052,10 +1064,17 @@ void UNet::get_profile(double ms_by_kind[8], double* gemm_flops, long long* gemm
   if (gemm_launches) *gemm_launches = nl;
 }
 
+double UNet::profile_norm_bytes() const {
+  double b = 0;
+  for (size_t i = 0; i < prof_op_bytes_.size(); ++i)
+    if (ops_[i].kind == OP_NORM) b += prof_op_bytes_[i] * prof_forwards_;
+  return b;
+}
+
 int UNet::dump_profile(const char* path) const {
   FILE* f = fopen(path, "w");
   if (!f) return -1;
-  fprintf(f, "op,kind,H,W,N,K,block_n,ms_per_forward,gflop,tflops\n");
+  fprintf(f, "op,kind,H,W,N,K,block_n,ms_per_forward,gflop,tflops,mbytes,gbs\n");
   for (size_t i = 0; i < prof_op_ms_.size(); ++i) {
     const Op& op = ops_[i];
     const double ms = prof_forwards_ ? prof_op_ms_[i] / prof_forwards_ : 0.0;
@@ -1067,8 +1086,10 @@ int UNet::dump_profile(const char* path) const {
     } else if (op.kind == OP_NORM) {
       H = op.norm.H; W = op.norm.W; N = op.norm.c1 + op.norm.c2;
     }
-    fprintf(f, "%s,%d,%d,%d,%d,%.0f,%d,%.5f,%.4f,%.2f\n", op.tag.c_str(), (int)op.kind, H, W, N, k, bn, ms,
-            prof_op_flops_[i] * 1e-9, ms > 0 ? prof_op_flops_[i] / (ms * 1e-3) * 1e-12 : 0.0);
+    const double by = i < prof_op_bytes_.size() ? prof_op_bytes_[i] : 0.0;
+    fprintf(f, "%s,%d,%d,%d,%d,%.0f,%d,%.5f,%.4f,%.2f,%.3f,%.1f\n", op.tag.c_str(), (int)op.kind, H, W, N, k, bn, ms,
+            prof_op_flops_[i] * 1e-9, ms > 0 ? prof_op_flops_[i] / (ms * 1e-3) * 1e-12 : 0.0, by * 1e-6,
+            ms > 0 ? by / (ms * 1e-3) * 1e-9 : 0.0);
   }
   fclose(f);
   return 0;

@@ -19,6 +19,7 @@ struct ParamSpec {
   float scale;
 };
 
+// (OP_STEM / OP_HEAD are never planned -- stem and head run as GEMM ops; the names keep the numbering of gddim_ctx_plan_op stable)
 enum OpKind { OP_STEM, OP_NORM, OP_GEMM, OP_HEAD, OP_IM2COL, OP_TRANSPOSE_V, OP_SMALL_ATTN, OP_SOFTMAX_ROWS, OP_ATTN_FUSED, OP_GN_QKV };
 
 struct Op {
@@ -71,6 +72,7 @@ class UNet {
   bool profiling() const { return profile_; }
   void get_profile(double ms_by_kind[8], double* gemm_flops, long long* gemm_launches) const;
   int dump_profile(const char* path) const;
+  double profile_norm_bytes() const;      // algorithmic HBM bytes of all GroupNorm ops over the profiled forwards
 
  private:
   struct T32 { float* p; int C, H, W; size_t bytes; float* stats; size_t stats_bytes; bool stats_valid; };
@@ -89,6 +91,7 @@ class UNet {
   std::vector<cudaEvent_t> prof_ev_;
   std::vector<double> prof_op_ms_;        // per op, accumulated
   std::vector<double> prof_op_flops_;     // per op per forward (GEMMs)
+  std::vector<double> prof_op_bytes_;     // per op per forward (GroupNorm family: algorithmic HBM bytes)
   long long prof_forwards_ = 0;
 
   // workspace arena (activations) with a first-fit free list, offsets assigned during the walk

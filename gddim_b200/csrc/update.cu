@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) cld_step_c3_kernel(const CldStepDev p) {
     float u[12], acc[12];
     {
       const float4* q = reinterpret_cast<const float4*>(p.u) + i * 3;
-      const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+      const float4 a = q[0], b = q[1], c = q[2];     // plain loads: u is updated in place by this launch
       u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = b.x; u[5] = b.y; u[6] = b.z; u[7] = b.w;
       u[8] = c.x; u[9] = c.y; u[10] = c.z; u[11] = c.w;
     }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) cld_step_c3_kernel(const CldStepDev p) {
     for (int j = 0; j < p.n_eps; ++j) {
       float e[12];
       const float4* q = reinterpret_cast<const float4*>(p.eps[j]) + i * 3;
-      const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+      const float4 a = q[0], b = q[1], c = q[2];     // plain loads: eps[0] may be eps_store (mixed score)
       e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
       e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w;
       if (j == 0 && p.mixed) {

@@ -74,6 +74,8 @@ class ScoreNet:
     self._gemm_impl = 0
     self._specs = None
     self._src = None          # the pstate.params_ema object the current parameters came from
+    self.generation = 0       # bumped whenever the device context is (re)created: samplers compare it, not the ctx address
+    self._samplers = []       # weak references to the Python samplers built on the current context
 
   # -- parameters -----------------------------------------------------------------------------------
   def specs(self):
@@ -125,8 +127,18 @@ class ScoreNet:
       _lib.check(_lib.lib().gddim_ctx_set_gemm_impl(self._ctx, self._gemm_impl))
 
   # -- context ------------------------------------------------------------------------------------------
+  def register_sampler(self, sampler):
+    import weakref
+    self._samplers = [r for r in self._samplers if r() is not None and r() is not sampler] + [weakref.ref(sampler)]
+
   def _destroy(self):
     if self._ctx is not None:
+      # samplers built on this context go first (the library would orphan them anyway, gddim_ctx_destroy)
+      for r in self._samplers:
+        smp = r()
+        if smp is not None:
+          smp._destroy()
+      self._samplers = []
       _lib.lib().gddim_ctx_destroy(self._ctx)
       self._ctx = None
       self._max_batch = 0
@@ -162,6 +174,7 @@ class ScoreNet:
       L.gddim_ctx_destroy(ctx)
       raise
     self._ctx, self._max_batch = ctx, int(batch)
+    self.generation += 1
     return ctx
 
   @property
@@ -185,6 +198,12 @@ class ScoreNet:
     _lib.check(_lib.lib().gddim_ctx_get_profile(self._ctx, ms, C.byref(fl), C.byref(nl)))
     names = ["stem", "groupnorm", "conv_gemm", "head", "im2col", "transpose_v", "attention", "softmax_rows"]
     return {n: ms[i] for i, n in enumerate(names)}, fl.value, nl.value
+
+  def get_profile_norm_bytes(self):
+    """Algorithmic HBM bytes of every GroupNorm op over the profiled forwards (gddim_ctx_get_profile_hbm)."""
+    b = C.c_double()
+    _lib.check(_lib.lib().gddim_ctx_get_profile_hbm(self._ctx, C.byref(b)))
+    return b.value
 
   def dump_profile(self, path):
     _lib.check(_lib.lib().gddim_ctx_dump_profile(self._ctx, str(path).encode()))

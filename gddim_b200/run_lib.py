@@ -36,18 +36,31 @@ def sample_data(config, ckpt_file, result_folder, is_continue=False, params=None
   sde = sde_lib.from_config(config)
   sampling_fn = sampling.get_sampling_fn(config, sde, score_model, None, inverse_scaler)
   num_sampling_rounds = config.eval.num_samples // config.eval.batch_size + 1  # :704
-  n_dev = 1                                                                    # one process drives one GPU
+  # The reference drives jax.local_device_count() GPUs from one process; here one process drives one GPU and the
+  # launcher (torchrun) starts WORLD_SIZE of them.  The key handling is that of a WORLD_SIZE-device pmap: the round's
+  # keys are split n_dev + 1 ways, key 1 draws the prior of ALL devices in one call (sampling.py:233-235) and this rank
+  # keeps its slice, so the samples do not depend on how the devices are spread over processes; rank k gets
+  # sample_rng[k] for its noise.  Every rank writes its own file (no collective on the path).
+  n_dev = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+  rank = int(os.environ.get("RANK", "0"))
+  if not 0 <= rank < n_dev:
+    raise RuntimeError(f"RANK={rank} outside WORLD_SIZE={n_dev}")
+  data_shape = sampling.get_data_shape(config)
   written = []
   for r in range(num_sampling_rounds):
     keys = jax_random.split(rng, n_dev + 1)                                    # :715
     rng, sample_rng = keys[0], keys[1:]
-    f_sample = os.path.join(result_folder, f"samples_{r}.npz")
+    f_sample = os.path.join(result_folder, f"samples_{r}.npz" if n_dev == 1 else f"samples_{r}_rank{rank}.npz")
     if os.path.exists(f_sample) and is_continue:
       logging.critical(f"SKIP!!! Already exists {f_sample}")
       continue
     if max_rounds is not None and len(written) >= max_rounds:
       break
-    samples_org_x, samples_v, nfe_cnt = sampling_fn(sample_rng, score_model, config.eval.batch_size // n_dev)
+    per_dev = config.eval.batch_size // n_dev
+    u = None
+    if n_dev > 1:
+      u = sde.prior_sampling(sample_rng[0], (n_dev, per_dev) + tuple(data_shape))[rank:rank + 1]
+    samples_org_x, samples_v, nfe_cnt = sampling_fn(sample_rng[rank:rank + 1], score_model, per_dev, u)
     samples_org_x, samples_v = np.asarray(samples_org_x), np.asarray(samples_v)
     samples_x = np.clip(samples_org_x * 255., 0, 255).astype(np.uint8)         # :723
     samples_x = samples_x.reshape((-1, config.data.image_size, config.data.image_size, config.data.num_channels))

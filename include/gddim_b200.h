@@ -80,6 +80,8 @@ long long gddim_ctx_launch_count(const gddim_ctx* ctx);   /* kernels launched by
 int gddim_ctx_set_profile(gddim_ctx* ctx, int on);
 int gddim_ctx_get_profile(const gddim_ctx* ctx, double* ms_by_kind, double* gemm_flops, long long* gemm_launches);
 int gddim_ctx_dump_profile(const gddim_ctx* ctx, const char* path);   /* per-op CSV */
+/* algorithmic HBM bytes of all GroupNorm(+swish, +resample) ops over the profiled forwards (fp32 in, fp16 out) */
+int gddim_ctx_get_profile_hbm(const gddim_ctx* ctx, double* norm_bytes);
 
 /* ---- score network: NCSNpp.apply / get_eps_fn's model call (models/utils.py:128-166; ncsnpp.py:41-243) ----
  * x_dev, out_dev: fp32 [batch, S, S, data_channels*state_mult] in net layout; t = diffusion time (labels = 999 t
@@ -242,7 +244,15 @@ int gddim_cld_ldeis_coef(const gddim_cld* cld, int order, const double* rev_ts, 
  * (inverse = 1: expm(int_t^0 F_1)), sde_lib.py:120-156 */
 int gddim_cld_mldeis_coef(const gddim_cld* cld, int order, const double* rev_ts, int n_ts, double* out);
 int gddim_cld_psi1(const gddim_cld* cld, double t, int inverse, double* out /*[2,2]*/);
+/* Lifetime: a sampler is built on one gddim_ctx (weights, workspace and CUDA graphs are baked in).  gddim_ctx_destroy
+ * releases the device state of every sampler still attached to it and orphans them: an orphaned handle stays valid for
+ * gddim_sampler_destroy / gddim_sampler_alive, every gddim_sample* call on it fails with an error.  Destroy order is
+ * therefore free (the reference has no such notion: JAX closures keep their arrays alive). */
 void gddim_sampler_destroy(gddim_sampler* s);
+int gddim_sampler_alive(const gddim_sampler* s);   /* 1 while the context the sampler was built on exists */
+/* Philox key of the internally drawn noise (sdeis / em / sscs) for the following gddim_sample* calls -- the role of the
+ * `rng` argument of the reference's sampler(rng, state, ...) (cld_jax/sampling.py:380-427).  No rebuild, graphs stay. */
+int gddim_sampler_set_seed(gddim_sampler* s, unsigned long long seed);
 /* The table the sampler steps through (for index-exact parity checks): fp32 [n_steps, order+3, 2, 2] for CLD
  * deis.  Returns the number of floats written (or needed when out == NULL). */
 long long gddim_sampler_coef(const gddim_sampler* s, float* out, long long cap);
@@ -264,6 +274,11 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
                        float* trace_dev, const float* noise_dev, void* stream);
 /* kernels launched (or replayed through CUDA graphs) by this sampler so far */
 long long gddim_sampler_launch_count(const gddim_sampler* s);
+/* measurement hook: the sampler's per-step update kernel (deis.multistep_ab_step at full order / the blur DCT-update-IDCT
+ * step) launched `iters` times on the sampler's own buffers; average launch time (CUDA events on `stream`) and the
+ * algorithmic bytes of one launch, (order+3) state arrays for CLD, 4 for blur */
+int gddim_sampler_time_update(gddim_sampler* s, int batch, int iters, double* ms_per_launch, double* bytes_per_launch,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,8 +1,10 @@
 """ORACLE (test infrastructure, NOT product code) -- blurring-diffusion SDE, DCT and order-0 sampler, numpy fp64.
 
-Parity status: **parity unpinned** by the reference (blur_jax has no tests).  Pinned in
-tests/test_oracle_blur.py by scipy.fft.dctn(type=2, norm='ortho'), IDCT(DCT)=id, sampling_T =
-rho2t(80) ~ 0.99598 and grid endpoints.
+Parity status: PINNED to outputs of the reference itself (blur_jax/{sde_lib,blur,fft,sampling,multistep}.py run
+unmodified under tests/refshim; fixtures tests/golden/ref_blur_*.npz; tests/test_ref_golden.py): schedule tables
+for sigma_blur_max 1 and 10 (1e-12), the 51-point time grid, rho2t, batch_img_dct / idct (1e-11), ab_step (1e-13),
+the network forward (1e-10) and the order-0 sampler end to end, with and without pmap (1e-8).  scipy.fft.dctn,
+IDCT(DCT) = id and the grid endpoints stay in tests/test_oracle_blur.py.
 
 Restates (file:line relative to /root/reference/blur_jax):
   blur.py:11-107          Makhoul-FFT DCT-II / DCT-III, batch_img_dct / batch_img_idct

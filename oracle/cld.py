@@ -1,9 +1,13 @@
 """ORACLE (test infrastructure, NOT product code) -- CLD SDE tables + DEIS sampler, numpy fp64.
 
-Parity status: **parity unpinned** by the reference (its tests assert nothing); this
-restatement is pinned by the analytic known-answer identities of SURVEY.md 8(c) in
-tests/test_oracle_cld.py.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs may import this package.
+Parity status: PINNED to outputs of the reference itself.  The reference ships no golden vectors and its tests
+assert nothing, but its own source files run unmodified under tests/refshim (numpy stand-in for
+jax/flax); tests/golden/make_ref_golden.py wrote their outputs to tests/golden/ref_cld_*.npz and
+tests/test_ref_golden.py holds every function below to them in fp64: R(t)/Psi/F/G/integrand tables (RK4 and
+Euler scans, beta_1 != 0), get_deis_coef orders 0-3, prepare_order0/naive_coef, LambdaSDE / LSDE / MLCLD
+tables (<= 1e-7), multistep_ab_step (1e-13), and all ten sampler factories end to end on a small NCSN++
+(<= 1e-7 relative L2).  The analytic known-answer identities of SURVEY.md 8(c) stay in tests/test_oracle_cld.py.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this package.
 
 Follows (file:line relative to /root/reference):
   cld_jax/sde_lib.py:17-43     inv_2x2, get_interp_fn

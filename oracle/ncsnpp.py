@@ -1,9 +1,13 @@
 """ORACLE (test infrastructure, NOT product code) -- NCSN++/DDPM++ forward, torch CPU (fp32 or fp64).
 
-Parity status: **parity unpinned** by the reference (no golden activations shipped, flax/jax not
-installable here).  Pinned by tests/test_oracle_net.py: parameter counts of SURVEY.md 8(c)(8)
-(107,597,446 / 107,587,075 / 61,811,334 / 3,883,686), the literal upfirdn_2d restatement below vs
-its closed forms, and per-layer numpy cross-checks.
+Parity status: PINNED to outputs of the reference itself: models/ncsnpp.py + layerspp.py + layers.py +
+up_or_down_sampling.py run unmodified under tests/refshim (flax.linen stand-in with compact-module auto-naming);
+tests/test_ref_golden.py checks against tests/golden/ref_net.npz / ref_ops.npz / ref_blur_sampler.npz that
+(i) the parameter names, shapes, initialisers and creation order of this walk equal what the reference's modules
+create, (ii) the fp64 forward equals the reference's NCSNpp.__call__ to 1e-10 (FIR + pyramid + Fourier net) /
+1e-5 (DDPM++: the reference builds its positional table in explicit float32), (iii) upsample_2d / downsample_2d /
+conv_downsample_2d / naive_* equal the reference functions to 1e-12.  tests/test_oracle_net.py keeps the
+parameter counts of SURVEY.md 8(c)(8) (107,597,446 / 107,587,075 / 61,811,334 / 3,883,686) and closed forms.
 
 Restates (file:line relative to /root/reference/cld_jax/models):
   ncsnpp.py:41-243              NCSNpp.__call__ (control flow, skip stack, input pyramid)
@@ -14,8 +18,9 @@ Restates (file:line relative to /root/reference/cld_jax/models):
   layers.py:30-42,60-107        get_act, default_init, ddpm_conv1x1/3x3
   layers.py:450-478             get_timestep_embedding, NIN
   up_or_down_sampling.py:40-86,168-411  Conv2d, naive_*sample_2d, conv_downsample_2d, upfirdn_2d, upsample_2d, downsample_2d
-Flax behaviour assumed (flax 0.3.1 not available): nn.GroupNorm(epsilon=1e-6, contiguous channel
-groups, stats over H,W,C/G), nn.Conv padding SAME, auto-naming <Class>_<k> per parent scope.
+Third-party behaviour restated from the published flax 0.3.x API (the package itself is not installable here; the
+same statement lives once more, independently, in tests/refshim/shim.py): nn.GroupNorm(epsilon=1e-6, contiguous
+channel groups, stats over H,W,C/G), nn.Conv padding SAME, auto-naming <Class>_<k> per parent scope.
 
 Parameters are a flat dict  "ResnetBlockBigGANpp_3/Conv_0/kernel" -> array in Flax layout
 (conv HWIO, dense (in,out)).  `collect_specs` runs the same walk and records

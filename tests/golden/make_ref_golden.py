@@ -223,7 +223,8 @@ def gen_cld_net_samplers(refshim, jax, jnp, mutils, sde_lib, sampling, prior_u, 
   r = fn(jax.random.PRNGKey(0)[None], sys.modules["flax.jax_utils"].replicate(st), 2, jnp.asarray(u[None].astype(np.float64)))
   out["hybdeis_u"], out["hybdeis_x"], out["hybdeis_v"], out["hybdeis_nfe"] = u, np.asarray(r[0]), np.asarray(r[1]), int(r[2])
   print(f"[cld] sampler hybdeis (psampler) t={time.time() - t00:.0f}s", flush=True)
-  run("sdeis", sampling.get_sdeis_sampler(sde, model, shape, 5, inv, 1, lambda_coef=0.5, use_order0=True, ts_order=2, denoising=True),
+  # (denoising=True raises AttributeError in the reference: LambdaSDE has no sampling_eps / s_F, sampling.py:383)
+  run("sdeis", sampling.get_sdeis_sampler(sde, model, shape, 5, inv, 1, lambda_coef=0.5, use_order0=True, ts_order=2, denoising=False),
       st, prior_u(2, seed=41), 2)
   run("ldeis", sampling.get_L_deis_sampler(sde, model, shape, 6, inv, 2, ts_order=2, denoising=False), st, prior_u(2, seed=61), 2)
   run("em", sampling.get_em_sampler(sde, model, shape, 6, inv, lambda_coef=0.7, ts_order=2, denoising=True), st, prior_u(2, seed=62), 2)

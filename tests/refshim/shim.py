@@ -696,6 +696,9 @@ def install(tree):
   for stub in ("tensorflow", "wandb", "matplotlib", "matplotlib.pyplot", "tensorflow_gan", "tensorflow_hub", "tensorflow_datasets"):
     _stub_module(stub)
   sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+  # einops probes every framework found in sys.modules with isinstance(x, (tf.Tensor, tf.Variable)): give it real types
+  sys.modules["tensorflow"].Tensor = type("Tensor", (), {})
+  sys.modules["tensorflow"].Variable = type("Variable", (), {})
 
   sys.path.insert(0, os.path.join(REF_ROOT, tree))
   return jax

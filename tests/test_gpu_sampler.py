@@ -455,3 +455,86 @@ def test_order0_is_em_matches_oracle():
     w = (np.einsum("ij,...j->...i", mean, w) + np.einsum("ij,...j->...i", em, eps_fn(w, cur))).astype(np.float32)
   w = oc.denoise_step(o, eps_fn, w).astype(np.float32)
   assert n == 6 and rel_l2(x, (w[..., 0] + 1) / 2) < TOL_MIXED and rel_l2(v, w[..., 1]) < TOL_MIXED
+
+
+def test_sampler_survives_context_recreation():
+  """A cached C sampler must not outlive the network context it was built on: growing the batch or installing new
+  parameters re-creates the context (gddim_b200/net.py ensure / set_params); the sampler is rebuilt, never replayed
+  against freed weights, and results stay those of a fresh sampler."""
+  from gddim_b200 import _lib, net as gnet
+  cfg, model0, _ = build("cld_deep")
+  model = gnet.ScoreNet(cfg, cld=True)
+  model.set_params(dict(model0.params))
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_deis_sampler(sde, model, (32, 32, 3), 4, inv, 1, ts_order=2, denoising=True)
+  u2, u5 = prior_u(2, seed=90), prior_u(5, seed=91)
+  a2 = fn(0, model, 2, u=u2)[0]
+  gen = model.generation
+  h_old = fn.core._h
+  a5 = fn(0, model, 5, u=u5)[0]                       # batch grows: context re-created, sampler rebuilt
+  assert model.generation == gen + 1 and fn.core._gen == model.generation
+  b2 = fn(0, model, 2, u=u2)[0]                       # fits the new context: same sampler, same result
+  np.testing.assert_array_equal(a2, b2)
+  fresh = sampling.get_deis_sampler(sde, model, (32, 32, 3), 4, inv, 1, ts_order=2, denoising=True)
+  np.testing.assert_array_equal(fresh(0, model, 5, u=u5)[0], a5)
+  # new parameters: context destroyed; both Python samplers drop their handles, results follow the new weights
+  p2 = {k: (v * 1.01).astype(np.float32) for k, v in model.params.items()}
+  model.set_params(p2)
+  assert fn.core._h is None and fresh.core._h is None
+  c2 = fn(0, model, 2, u=u2)[0]
+  assert np.isfinite(c2).all() and not np.array_equal(c2, a2)
+  # C level: a handle whose context was destroyed reports dead and refuses to sample
+  L = _lib.lib()
+  h = fn.core._h
+  assert L.gddim_sampler_alive(h) == 1
+  fn.core._h = None                                   # keep the raw handle out of the Python owner for this check
+  model._samplers = []
+  model._destroy()
+  assert L.gddim_sampler_alive(h) == 0
+  x = np.empty((2, 32, 32, 3), np.float32)
+  rc = L.gddim_sample(h, u2.ctypes.data, x.ctypes.data, x.ctypes.data, 2, 1, None, None)
+  assert rc != 0 and "destroyed" in _lib.last_error()
+  L.gddim_sampler_destroy(h)
+  del h_old
+
+
+def test_psampler_noise_follows_the_key():
+  """the pmapped stochastic samplers must draw their noise from the key they are given (per call, per
+  rank), like pmap(sampler)(prng, ...) in the reference -- not from a constant seed."""
+  cfg, model, _ = build("cld_deep")
+  sde = sde_lib.from_config(cfg)
+  cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order, cfg.sampling.lambda_coef = "sdeis", 3, 0, 1.0
+  fn = sampling.get_sampling_fn(cfg, sde, model, None, inv)
+  cfg.sampling.method = "deis"
+  u = prior_u(2, seed=92)[None]
+  k1, k2 = np.array([[0, 7]], np.uint32), np.array([[7, 0]], np.uint32)
+  a = fn(k1, model, 2, u=u)[0]
+  h = fn.core._h.value
+  b = fn(k2, model, 2, u=u)[0]
+  c = fn(k1, model, 2, u=u)[0]
+  assert fn.core._h.value == h                          # re-keyed without rebuilding the sampler or its graphs
+  assert not np.array_equal(a, b) and np.array_equal(a, c)
+  assert sampling._seed_of(k1[0], rank=0) != sampling._seed_of(k1[0], rank=1)      # ranks draw different noise
+
+
+def test_sample_data_from_independent_flax_checkpoint_matches_oracle(tmp_path):
+  """N2: a State blob hand-packed with raw msgpack in tests/test_checkpoint.py (chunked leaves, optimizer subtree; not
+  the repo's writer) -> run_lib.sample_data -> samples equal the oracle's on the same jax-keyed prior."""
+  from gddim_b200 import jax_random, run_lib
+  from test_checkpoint import _write_independent_checkpoint
+  cfg, model, net_fn = build("cld_deep")
+  cfg.sampling.method, cfg.sampling.nfe, cfg.sampling.deis_order = "deis", 4, 1
+  cfg.eval.batch_size, cfg.eval.num_samples = 2, 1
+  d = tmp_path / "checkpoints"
+  d.mkdir()
+  _write_independent_checkpoint(d / "checkpoint_26", model.params)
+  files = run_lib.sample_data(cfg, str(d / "checkpoint_26"), str(tmp_path / "res"), max_rounds=1)
+  got = np.load(files[0])
+  rng = jax_random.PRNGKey(cfg.seed + 1)
+  rng, _ = jax_random.split(rng)
+  keys = jax_random.split(rng, 2)
+  sde = sde_lib.from_config(cfg)
+  u = sde.prior_sampling(keys[1], (1, 2, 32, 32, 3))[0]
+  ox, ov, _ = oracle_cld_sample(cfg, net_fn, u, 4, 1, denoising=True)
+  assert rel_l2(got["samples_x"][0], ox) < TOL and rel_l2(got["samples_v"][0], ov) < TOL
+  assert np.abs(got["samples"].astype(np.int32) - np.clip(ox * 255., 0, 255).astype(np.uint8).astype(np.int32)).max() <= 1

@@ -236,7 +236,7 @@ ORACLE_SAMPLERS = {
     "deis_o0_nodenoise": lambda o, f, g: oc.deis_sampler(o, f, g["deis_o0_nodenoise_u"], 5, 0, denoising=False),
     "order0": lambda o, f, g: oc.order0_sampler(o, f, g["order0_u"], 6, denoising=True),
     "hybdeis": lambda o, f, g: oc.deis_sampler(o, f, g["hybdeis_u"], 9, 1, denoising=True, rev_ts=oc.hyd_rev_ts(o, 9, 0.3, 0.3, 2, True)),
-    "sdeis": lambda o, f, g: oc.sdeis_sampler(oc.LambdaSDE(o, 0.5, True), f, g["sdeis_u"], 5, 1, g["sdeis_z"].astype(np.float64), denoising=True),
+    "sdeis": lambda o, f, g: oc.sdeis_sampler(oc.LambdaSDE(o, 0.5, True), f, g["sdeis_u"], 5, 1, g["sdeis_z"].astype(np.float64), denoising=False),
     "ldeis": lambda o, f, g: oc.ldeis_sampler(o, f, g["ldeis_u"], 6, 2, denoising=False),
     "em": lambda o, f, g: oc.em_sampler(o, f, g["em_u"], 6, g["em_z"].astype(np.float64), lambda_coef=0.7, denoising=True),
     "sscs": lambda o, f, g: oc.sscs_sampler(o, f, g["sscs_u"], 5, g["sscs_z"].astype(np.float64).reshape((5, 2) + g["sscs_u"].shape), denoising=False),
@@ -324,8 +324,9 @@ def test_gpu_samplers_match_reference(name):
     assert xs.shape == g["hybdeis_x"].shape                                    # (n_dev = 1, B, 32, 32, 3) like pmap
     x, v = xs[0], vs[0]
   elif name == "sdeis":
+    # (the reference's sdeis only runs with noise_removal=False: LambdaSDE lacks sampling_eps / s_F, sampling.py:383)
     x, v, n = sampling.get_sdeis_sampler(sde, model, shape, 5, inv, 1, lambda_coef=0.5, use_order0=True, ts_order=2,
-                                         denoising=True)(0, model, B, u=u, noise=z)
+                                         denoising=False)(0, model, B, u=u, noise=z)
   elif name == "ldeis":
     x, v, n = sampling.get_L_deis_sampler(sde, model, shape, 6, inv, 2, ts_order=2, denoising=False)(0, model, B, u=u)
   elif name == "em":
