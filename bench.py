@@ -258,6 +258,7 @@ def run_ours(args):
     core.run(model, B, u_dev)
     torch.cuda.synchronize()
     ms_kind, gemm_flops, gemm_launches = model.get_profile()
+    norm_bytes = model.get_profile_norm_bytes()
     if args.profile_csv:
       os.makedirs(os.path.dirname(os.path.abspath(args.profile_csv)), exist_ok=True)
       model.dump_profile(args.profile_csv)
@@ -279,7 +280,6 @@ def run_ours(args):
       traffic_commit = None
     # ---- HBM-bound kernel families against the measured copy bandwidth ---------------------------------------------
     hbm_peak = peaks.get("hbm_gbs", 6500.0)
-    norm_bytes = model.get_profile_norm_bytes()
     gn_ms = ms_kind["groupnorm"]
     upd_ms, upd_bytes = C.c_double(), C.c_double()
     from gddim_b200 import _lib as glib

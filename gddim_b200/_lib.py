@@ -35,7 +35,9 @@ class GemmDesc(C.Structure):
               ("bias", C.c_void_p), ("bias2", C.c_void_p), ("residual", C.c_void_p), ("rowscale", C.c_void_p),
               ("scale", C.c_float), ("out32", C.c_void_p), ("out16", C.c_void_p), ("row_out", C.c_void_p),
               ("ldo", C.c_int), ("epi", C.c_int), ("impl", C.c_int), ("force_block_n", C.c_int),
-              ("force_m_sub", C.c_int), ("n_store", C.c_int), ("force_cta_pairs", C.c_int), ("reverse", C.c_int)]
+              ("force_m_sub", C.c_int), ("n_store", C.c_int), ("force_cta_pairs", C.c_int), ("reverse", C.c_int),
+              ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p), ("gn_eps", C.c_float), ("gn_groups", C.c_int),
+              ("gn_silu", C.c_int), ("pad_", C.c_int)]
 
 
 class NormDesc(C.Structure):
@@ -102,6 +104,7 @@ SIGNATURES = {
     "gddim_relayout": (C.c_int, [_P, _P, C.c_longlong, C.c_int, C.c_int, _P]),
     "gddim_dct2d_32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "gddim_conv_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
+    "gddim_gemm_gnf_supported": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gddim_group_norm": (C.c_int, [C.POINTER(NormDesc), _P]),
     "gddim_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "gddim_gn_qkv": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -338,10 +338,13 @@ int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream) {
   g.bias = d->bias; g.bias2 = d->bias2; g.residual = d->residual; g.rowscale = d->rowscale; g.scale = d->scale;
   g.out32 = d->out32; g.out16 = (__half*)d->out16; g.row_out = d->row_out; g.ldo = d->ldo; g.epi = d->epi; g.n_store = d->n_store;
   g.reverse = d->reverse;
+  g.gn_gamma = d->gn_gamma; g.gn_beta = d->gn_beta; g.gn_eps = d->gn_eps; g.gn_groups = d->gn_groups; g.gn_silu = d->gn_silu;
   if (d->impl == 0 && gemm_prepare(&g, d->force_block_n, d->force_m_sub, d->force_cta_pairs)) return set_err(std::string("gddim_conv_gemm: ") + gemm_last_error());
   if (gemm_launch(&g, d->impl, (cudaStream_t)stream)) return set_err(std::string("gddim_conv_gemm: ") + gemm_last_error());
   return 0;
 }
+
+int gddim_gemm_gnf_supported(int H, int W, int N, int groups) { return gemm_gnf_supported(H, W, N, groups); }
 
 int gddim_attention(const void* qkv16_dev, void* out16_dev, int B, int T, int C, float scale, int reverse, void* stream) {
   if (need_cuda("gddim_attention")) return -1;

@@ -43,10 +43,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmH, const GemmArgs p) {
   pdl_launch_dependents();   // the wait is after the prologue
-  using L = SmemLayout<BLOCK_N, MT, CG>;
-  static_assert(CG == 1 || (EPI == EPI_LINEAR && (BLOCK_N / CG) % 16 == 0), "CTA pairs: linear epilogue only");
-  static_assert(!HALO || EPI == EPI_LINEAR, "halo tiles: linear epilogue only");
+  constexpr bool GNF = EPI == EPI_GNF;
+  using L = SmemLayout<BLOCK_N, MT, CG, GNF ? GnfSmem<BLOCK_N>::BYTES : 0>;
+  static_assert(CG == 1 || (EPI != EPI_SOFTMAX && (BLOCK_N / CG) % 16 == 0), "CTA pairs: linear / GNF epilogue only");
+  static_assert(!HALO || EPI != EPI_SOFTMAX, "halo tiles: linear / GNF epilogue only");
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // rank 0 = leader: issues the MMAs
+  // GNF with images spanning several CTAs: the launch is a cluster of gn_xc CTAs (CG == 2: the MMA pair itself)
+  const bool clustered = CG == 2 || (GNF && p.gn_xc > 1);
   constexpr int MAX_STAGES = 8;
   const int STAGES = HALO ? p.stages : L::STAGES;
   const int stage_bytes = HALO ? p.stage_bytes : L::STAGE_BYTES;
@@ -65,6 +68,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * stage_bytes + L::BAR_BYTES);
   float* epi_bias = reinterpret_cast<float*>(smem + STAGES * stage_bytes + L::BAR_BYTES + L::EPI_STAGE_BYTES);
+  uint8_t* gnf_smem = smem + STAGES * stage_bytes + L::BAR_BYTES + L::EPI_STAGE_BYTES + 2 * BLOCK_N * 4;   // GNF only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,6 +86,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       ptx::mbar_init(&tfull_bar[s], 1);
       ptx::mbar_init(&tempty_bar[s], (EPI == EPI_SOFTMAX ? 4 : EPI_WARPS) * CG);   // both CTAs' epilogues (leader's barrier)
     }
+    if (GNF)      // statistics exchange: one arrival per (CTA of the cluster, group of the N tile) and tile
+      ptx::mbar_init(reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR), p.gn_xc * (BLOCK_N / p.gn_cpg));
     ptx::fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -91,7 +97,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   // everything above touched only this CTA's shared memory / TMEM; from here on global memory is read and written
   pdl_wait();
   ptx::tc_fence_before();
-  if (CG == 2) ptx::cluster_sync(); else __syncthreads();
+  if (clustered) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -235,7 +241,28 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       const long long m = (long long)mt * MT * BLOCK_M + row;
       const bool valid = m < p.M;
       uint32_t r[32];
-      if (EPI == EPI_LINEAR) {
+      if (GNF) {
+        constexpr int RS = L::EPI_ROW_FLOATS;
+        float* stg = epi_stage + warp * 32 * RS;
+        float* bias_s = epi_bias + bias_buf * BLOCK_N;
+        float* gb = reinterpret_cast<float*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_GB) + bias_buf * 2 * BLOCK_N;
+        for (int j = threadIdx.x; j < BLOCK_N; j += EPI_WARPS * 32) {
+          float b = 0.f;
+          if (p.bias != nullptr) b += __ldg(p.bias + nt * BLOCK_N + j);
+          if (p.bias2 != nullptr) b += __ldg(p.bias2 + nt * BLOCK_N + j);
+          bias_s[j] = b;
+          gb[j] = __ldg(p.gn_gamma + nt * BLOCK_N + j);
+          gb[BLOCK_N + j] = __ldg(p.gn_beta + nt * BLOCK_N + j);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        EpiCtx<BLOCK_N, MT> cx{p, stg, bias_s, &tfull_bar[acc], acc_phase, tmem_base + (uint32_t(quad * 32) << 16) + acc * MT * BLOCK_N,
+                               (long long)mt * MT * BLOCK_M + quad * 32, nt * BLOCK_N, lane, group};
+        GnfCtx gx{reinterpret_cast<float2*>(gnf_smem), reinterpret_cast<float2*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_GSTAT),
+                  reinterpret_cast<float2*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_XCHG), gb, gb + BLOCK_N,
+                  reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR), (uint32_t)bias_buf,
+                  clustered ? ptx::cluster_ctarank() : 0u, warp};
+        epi_tile_gnf<BLOCK_N, MT>(cx, gx);
+      } else if (EPI == EPI_LINEAR) {
         // TMEM -> registers (thread = row) -> padded smem -> registers (8 lanes = one 32-column row segment),
         // so that every global access of the epilogue is a full 128-byte line.  Everything that does not depend
         // on the accumulator (bias row, first residual chunk) is fetched before waiting for the MMAs, and the
@@ -328,7 +355,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   }
 
   ptx::tc_fence_before();
-  if (CG == 2) ptx::cluster_sync(); else __syncthreads();     // pair: neither CTA may retire while its peer still works
+  if (clustered) ptx::cluster_sync(); else __syncthreads();     // pair / cluster: no CTA may retire while a peer still works
   if (warp == MMA_WARP) {
     ptx::tc_fence_after();
     if (CG == 2) ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -538,6 +565,34 @@ int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t*
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
+// EPI_GNF tile rule: with a CTA tile of `tr` rows and `bn` columns, an image of `rpi` rows must either fit the tile a
+// whole number of times (>= 16 rows each, <= GNF_IMGS images) or span 2 / 4 CTAs of one cluster, which then must own all
+// N columns (bn == N); a group's channels never straddle N tiles and a tile holds at most GNF_GMAX groups.
+static int gnf_cluster(int rpi, int tr, int bn, int N, int cpg) {
+  if (bn % cpg != 0 || bn / cpg > GNF_GMAX) return 0;
+  if (rpi >= tr) {
+    const int xc = rpi / tr;
+    if (xc == 1) return 1;
+    return ((xc == 2 || xc == 4) && bn == N) ? xc : 0;
+  }
+  if (rpi < 16 || tr % rpi != 0 || tr / rpi > GNF_IMGS) return 0;
+  return 1;
+}
+
+int gemm_gnf_supported(int H, int W, int N, int groups) {
+  if (groups <= 0 || N % groups != 0 || N % 32 != 0 || !is_pow2(H) || !is_pow2(W)) return 0;
+  const int cpg = N / groups, rpi = H * W;
+  if (cpg != 4 && cpg != 8) return 0;
+  for (int bn = 256; bn >= 32; bn >>= 1) {
+    if (N % bn != 0) continue;
+    for (int ms = 1; ms <= 2; ++ms) {
+      if (ms == 2 && bn != 128 && bn != 64) continue;
+      if (gnf_cluster(rpi, BLOCK_M * ms, bn, N, cpg)) return 1;
+    }
+  }
+  return 0;
+}
+
 int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
   op->prepared = 0;
   op->m_sub = 1;
@@ -553,6 +608,17 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     ktot += g.taps * g.c;
   }
   if (op->w_koff + ktot > op->w_ld) GEMM_FAIL("conv_gemm: K range exceeds weight row stride");
+  const bool gnf = op->epi == EPI_GNF;
+  const int rpi = op->H * op->W;
+  int cpg = 0;
+  if (gnf) {
+    if (!op->gn_gamma || !op->gn_beta || !op->out16 || op->out32 || op->colstats || op->residual || op->rowscale ||
+        op->n_store != 0 || op->w_batch_stride != 0)
+      GEMM_FAIL("conv_gemm: the GroupNorm epilogue writes out16 only (no out32 / colstats / residual / rowscale / n_store / batched B)");
+    if (!gemm_gnf_supported(op->H, op->W, op->N, op->gn_groups))
+      GEMM_FAIL("conv_gemm: GroupNorm epilogue not available for %dx%d, N=%d, groups=%d", op->H, op->W, op->N, op->gn_groups);
+    cpg = op->N / op->gn_groups;
+  }
   int bn = force_block_n;
   if (bn == 0) {
     if (op->epi == EPI_SOFTMAX) bn = op->N;
@@ -573,6 +639,7 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
         if (op->N % cand != 0) continue;
         for (int ms = 1; ms <= 2; ++ms) {
           if (ms == 2 && (cand > 128 || cand < 64 || op->w_batch_stride != 0)) continue;
+          if (gnf && !gnf_cluster(rpi, BLOCK_M * ms, cand, op->N, cpg)) continue;
           const long long tiles = ((mt + ms - 1) / ms) * (op->N / cand);
           const long long waves = (tiles + 147) / 148;
           const double width = (double)cand * ms;         // output columns x row-tiles sharing one operand load
@@ -594,7 +661,12 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     GEMM_FAIL("conv_gemm: n_store supports bias + scale + fp32 output only");
   op->block_n = bn;
   if (force_block_n != 0) op->m_sub = (force_m_sub == 2) ? 2 : 1;
-  if (op->m_sub == 2 && ((bn != 128 && bn != 64) || op->w_batch_stride != 0 || op->epi != EPI_LINEAR))
+  op->gn_xc = 0;
+  if (gnf) {
+    op->gn_xc = gnf_cluster(rpi, BLOCK_M * op->m_sub, bn, op->N, cpg);
+    if (op->gn_xc == 0) GEMM_FAIL("conv_gemm: GroupNorm epilogue: no valid tile for block_n %d, m_sub %d at %dx%d", bn, op->m_sub, op->H, op->W);
+  }
+  if (op->m_sub == 2 && ((bn != 128 && bn != 64) || op->w_batch_stride != 0 || op->epi == EPI_SOFTMAX))
     GEMM_FAIL("conv_gemm: 256-row tiles need block_n 64/128, shared weights and the linear epilogue");
   op->m_tiles = int((M + (long long)BLOCK_M * op->m_sub - 1) / ((long long)BLOCK_M * op->m_sub));
   op->n_tiles = op->N / bn;
@@ -606,8 +678,9 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     if (halo128_cg < 0) { const char* e = getenv("GDDIM_HALO128_CG"); halo128_cg = e ? atoi(e) : 2; }
     static int halo256 = -1;               // GDDIM_HALO256=1: halo tiles for N = 256 too (measured slower: two ring slots)
     if (halo256 < 0) { const char* e = getenv("GDDIM_HALO256"); halo256 = (e && e[0] == '1') ? 1 : 0; }
-    const bool plain = op->epi == EPI_LINEAR && op->w_batch_stride == 0 && op->n_store == 0;
-    const bool can_pair = plain && bn == 256 && op->m_sub == 1;
+    const bool plain = op->epi != EPI_SOFTMAX && op->w_batch_stride == 0 && op->n_store == 0;
+    // (GroupNorm epilogue: a pair must be exactly one image; images spanning 4 CTAs run as clusters of single-CTA MMAs)
+    const bool can_pair = plain && bn == 256 && op->m_sub == 1 && (!gnf || op->gn_xc == 2);
     // halo tiles: 3x3 convolution whose CTA tile is a block of whole image rows of ONE image
     const int tile_px = BLOCK_M * op->m_sub;
     // (measured: 256-row N = 128 tiles 1.06 -> 1.29 PFLOP/s; N = 256 tiles lose, their ring shrinks to two slots)
@@ -620,15 +693,18 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     op->cg = (!no_pairs && shape_ok && can_pair) ? 2 : 1;
     if (halo_ok && bn == 256 && op->m_tiles >= 2 && !no_pairs) op->cg = 2;   // three 32 KB weight tiles per slot do not fit
     if (halo_ok && bn == 128 && op->m_tiles >= 2 && !no_pairs) op->cg = halo128_cg == 2 ? 2 : 1;
+    if (gnf && op->gn_xc != 2) op->cg = 1;
     if (force_cg == 1) op->cg = 1;
     if (force_cg == 2) {
-      if (!can_pair && !halo_ok) GEMM_FAIL("conv_gemm: CTA pairs need block_n 256 (or halo tiles), shared weights, linear epilogue");
+      if ((!can_pair && !halo_ok) || (gnf && op->gn_xc != 2))
+        GEMM_FAIL("conv_gemm: CTA pairs need block_n 256 (or halo tiles), shared weights, linear epilogue");
       op->cg = 2;
     }
     op->halo = 0;
     if (halo_ok && !(bn == 256 && op->cg == 1)) {
       using L0 = SmemLayout<32, 1, 1>;      // BAR / epilogue staging sizes do not depend on the tile shape ...
-      const int epi_bytes = L0::EPI_STAGE_BYTES + 2 * bn * 4;                 // ... except for the bias rows
+      const int epi_bytes = L0::EPI_STAGE_BYTES + 2 * bn * 4 +                // ... except for the bias rows
+                            (gnf ? (bn == 128 ? GnfSmem<128>::BYTES : GnfSmem<256>::BYTES) : 0);
       const int b_tile = (bn / op->cg) * BLOCK_K * 2;
       op->a_bytes = (tile_px + 2 * op->W) * BLOCK_K * 2;
       op->stage_bytes = op->a_bytes + 3 * b_tile;
@@ -679,7 +755,7 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
 
 template <int BN, int EPI, int MT, int CG = 1, bool HALO = false>
 static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
-  using L = SmemLayout<BN, MT, CG>;
+  using L = SmemLayout<BN, MT, CG, EPI == EPI_GNF ? GnfSmem<BN>::BYTES : 0>;
   static DeviceOnce attr_set;
   auto kern = conv_gemm_umma_kernel<BN, EPI, MT, CG, HALO>;
   const int smem_total = HALO ? op->stages * op->stage_bytes + L::BAR_BYTES + L::EPI_BYTES : L::TOTAL;
@@ -709,6 +785,35 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
     return 0;
   }
   const int tiles = a.m_tiles * a.n_tiles;
+  if (EPI == EPI_GNF && a.gn_xc > 1) {
+    // images span gn_xc CTAs: clusters of gn_xc single-CTA MMAs, CTA r of a cluster owns tile (k * gn_xc + r) = part r of
+    // image k.  The grid is what can be co-resident (a persistent cluster that had to wait for a free GPC slot would
+    // run its whole share after everyone else): cudaOccupancyMaxActiveClusters, cached per device.
+    const int xc = a.gn_xc;
+    if (tiles % xc != 0) GEMM_FAIL("conv_gemm: GroupNorm epilogue needs whole images (tiles %d, cluster %d)", tiles, xc);
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem_total; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = xc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    static int max_clusters[64][5] = {};
+    const int dev = DeviceOnce::dev() & 63;
+    if (max_clusters[dev][xc] == 0) {
+      cfg.gridDim = dim3(num_sms / xc * xc); cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms / xc / 2 > 0 ? num_sms / xc / 2 : 1; }
+      max_clusters[dev][xc] = n;
+    }
+    int clusters = tiles / xc;
+    if (clusters > max_clusters[dev][xc]) clusters = max_clusters[dev][xc];
+    if (clusters > num_sms_eff / xc) clusters = num_sms_eff / xc;
+    cfg.gridDim = dim3(clusters * xc);
+    cfg.numAttrs = pdl_attr(at, 1);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, op->tmA[0], op->tmA[1], op->tmB, op->tmH, a);
+    if (e != cudaSuccess) GEMM_FAIL("conv_gemm_umma cluster launch (x%d): %s", xc, cudaGetErrorString(e));
+    return 0;
+  }
   const int grid = tiles < num_sms_eff ? tiles : num_sms_eff;
   launch_k(kern, dim3(grid), dim3(NUM_THREADS), smem_total, st, op->tmA[0], op->tmA[1], op->tmB, op->tmH, a);
   cudaError_t e = cudaGetLastError();
@@ -718,6 +823,38 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
 
 static float* g_softmax_tmp = nullptr;
 static size_t g_softmax_tmp_bytes = 0;
+
+// reference path of EPI_GNF: GroupNorm (+ swish) of the fp32 GEMM result, one block per (image, group)
+__global__ void __launch_bounds__(256) gnf_ref_kernel(const float* __restrict__ v, __half* __restrict__ out16, int rpi, int N,
+                                                      int cpg, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float eps, int silu, int ldo) {
+  pdl_entry();
+  const long long row0 = (long long)blockIdx.x * rpi;
+  const int c0 = blockIdx.y * cpg;
+  const int n = rpi * cpg;
+  __shared__ double sh[2][256];
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float x = v[(row0 + i / cpg) * N + c0 + i % cpg];
+    s += x; q += (double)x * x;
+  }
+  sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  const float mean = (float)(sh[0][0] / n);
+  const float var = fmaxf((float)(sh[1][0] / n - (sh[0][0] / n) * (sh[0][0] / n)), 0.f);
+  const float rstd = rsqrtf(var + eps);
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int c = c0 + i % cpg;
+    const long long m = row0 + i / cpg;
+    float y = (v[m * N + c] - mean) * rstd * gamma[c] + beta[c];
+    if (silu) y = y / (1.0f + expf(-y));
+    out16[m * ldo + c] = __float2half_rn(y);
+  }
+}
 
 int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
   const long long M = (long long)op->B * op->H * op->W;
@@ -749,6 +886,32 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
 #endif
     if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX, 1>(op, a, st);
     a.stages = op->stages; a.stage_bytes = op->stage_bytes; a.a_bytes = op->a_bytes;
+    if (op->epi == EPI_GNF) {
+      a.gn_gamma = op->gn_gamma; a.gn_beta = op->gn_beta; a.gn_eps = op->gn_eps; a.gn_cpg = op->N / op->gn_groups;
+      a.gn_silu = op->gn_silu; a.gn_rpi = op->H * op->W; a.gn_xc = op->gn_xc;
+      if (op->halo) {
+        if (op->block_n == 128 && op->m_sub == 2 && op->cg == 1) return launch_umma<128, EPI_GNF, 2, 1, true>(op, a, st);
+        GEMM_FAIL("conv_gemm: no GroupNorm-epilogue halo kernel for block_n %d, m_sub %d, cg %d", op->block_n, op->m_sub, op->cg);
+      }
+      if (op->cg == 2) {
+        if (op->block_n == 256 && op->m_sub == 1) return launch_umma<256, EPI_GNF, 1, 2>(op, a, st);
+        GEMM_FAIL("conv_gemm: CTA pairs need block_n 256");
+      }
+      if (op->m_sub == 2) {
+        switch (op->block_n) {
+          case 128: return launch_umma<128, EPI_GNF, 2>(op, a, st);
+          case 64: return launch_umma<64, EPI_GNF, 2>(op, a, st);
+          default: GEMM_FAIL("conv_gemm: m_sub=2 needs block_n 64 or 128 (got %d)", op->block_n);
+        }
+      }
+      switch (op->block_n) {
+        case 256: return launch_umma<256, EPI_GNF, 1>(op, a, st);
+        case 128: return launch_umma<128, EPI_GNF, 1>(op, a, st);
+        case 64: return launch_umma<64, EPI_GNF, 1>(op, a, st);
+        case 32: return launch_umma<32, EPI_GNF, 1>(op, a, st);
+        default: GEMM_FAIL("conv_gemm: unsupported block_n %d", op->block_n);
+      }
+    }
     if (op->halo) {
       if (op->block_n == 256 && op->m_sub == 1 && op->cg == 2) return launch_umma<256, EPI_LINEAR, 1, 2, true>(op, a, st);
       if (op->block_n == 128 && op->m_sub == 2 && op->cg == 1) return launch_umma<128, EPI_LINEAR, 2, 1, true>(op, a, st);
@@ -788,6 +951,24 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
   r.scale = op->scale; r.out32 = op->out32; r.out16 = op->out16; r.row_out = op->row_out; r.ldo = op->ldo;
   r.epi = op->epi;
   r.n_store = op->n_store;
+  if (op->epi == EPI_GNF) {
+    if (!op->gn_gamma || !op->gn_beta || !op->out16 || op->gn_groups <= 0 || op->N % op->gn_groups != 0)
+      GEMM_FAIL("conv_gemm ref: bad GroupNorm epilogue arguments");
+    const size_t need = (size_t)M * op->N * sizeof(float);
+    if (need > g_softmax_tmp_bytes) {
+      if (g_softmax_tmp) cudaFree(g_softmax_tmp);
+      if (cudaMalloc(&g_softmax_tmp, need) != cudaSuccess) GEMM_FAIL("conv_gemm ref: scratch alloc failed");
+      g_softmax_tmp_bytes = need;
+    }
+    r.epi = EPI_LINEAR; r.out32 = g_softmax_tmp; r.out16 = nullptr; r.ldo = op->N;
+    dim3 grid0((unsigned)((M + 63) / 64), (unsigned)((op->N + 63) / 64));
+    launch_k(conv_gemm_ref_kernel, dim3(grid0), dim3(256), 0, st, r);
+    launch_k(gnf_ref_kernel, dim3((unsigned)op->B, (unsigned)op->gn_groups), dim3(256), 0, st, (const float*)g_softmax_tmp, op->out16,
+             op->H * op->W, op->N, op->N / op->gn_groups, op->gn_gamma, op->gn_beta, op->gn_eps, op->gn_silu, op->ldo);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) GEMM_FAIL("conv_gemm_ref (GroupNorm epilogue) launch: %s", cudaGetErrorString(e));
+    return 0;
+  }
   if (op->w_batch_stride != 0 && (op->H * op->W) % 64 != 0) GEMM_FAIL("conv_gemm ref: batched B needs H*W %% 64 == 0");
   if (op->epi == EPI_SOFTMAX) {
     const size_t need = (size_t)M * op->N * sizeof(float);

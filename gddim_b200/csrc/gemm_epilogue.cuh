@@ -51,6 +51,14 @@ struct GemmArgs {
   float* colstats;
   int stages, stage_bytes, a_bytes;   // HALO kernels: smem ring geometry (depends on W)
   int reverse;   // tiles in descending order (the consumer of a tensor starts with what its producer wrote last: L2 hits)
+  // EPI_GNF: GroupNorm (+ swish) of the OUTPUT fused into the epilogue (see epi_tile_gnf): out16 = act(GN(v))
+  const float* gn_gamma;   // [N]
+  const float* gn_beta;    // [N]
+  float gn_eps;
+  int gn_cpg;              // channels per group (4 or 8)
+  int gn_silu;
+  int gn_rpi;              // rows (pixels) per image = H * W
+  int gn_xc;               // CTAs an image spans = cluster size of the launch (1, 2 or 4)
   int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };
 
@@ -58,7 +66,24 @@ struct GemmArgs {
 // output rows, which halves the L2->smem operand traffic per FLOP of the N <= 128 layers)
 // CG = CTAs cooperating on one MMA (cta_group): with CG = 2 a cluster of two CTAs computes 256 x BLOCK_N per MMA, each
 // CTA staging its own 128 A rows and HALF of the weight tile -- a third less L2->smem traffic on the N = 256 layers
-template <int BLOCK_N, int MT, int CG = 1>
+// GNF epilogue scratch (see epi_tile_gnf): per-warp group partials, per-(image, group) mean / rstd, double-buffered
+// gamma / beta rows, the cluster exchange buffer
+constexpr int GNF_GMAX = 32;                                   // groups per N tile (BLOCK_N / cpg <= 32 ... 64 for cpg 4, N 256: rejected)
+constexpr int GNF_IMGS = 16;                                   // images per CTA tile (256 rows of 4x4 images)
+constexpr int GNF_PSTAT_BYTES = 2 * 4 * 2 * GNF_GMAX * 8;      // [MT<=2][quad][seg][group] float2
+constexpr int GNF_GSTAT_BYTES = GNF_IMGS * GNF_GMAX * 8;       // [image][group] (mean, rstd)
+constexpr int GNF_XCHG_BYTES = 2 * 4 * GNF_GMAX * 8;           // [tile parity][cluster rank][group] (sum, sumsq)
+template <int BLOCK_N>
+struct GnfSmem {
+  static constexpr int GB_BYTES = 2 * 2 * BLOCK_N * 4;         // [buf][gamma | beta][BLOCK_N]
+  static constexpr int OFF_GSTAT = GNF_PSTAT_BYTES;
+  static constexpr int OFF_XCHG = OFF_GSTAT + GNF_GSTAT_BYTES;
+  static constexpr int OFF_GB = OFF_XCHG + GNF_XCHG_BYTES;
+  static constexpr int OFF_BAR = OFF_GB + GB_BYTES;
+  static constexpr int BYTES = OFF_BAR + 16;
+};
+
+template <int BLOCK_N, int MT, int CG = 1, int EXTRA = 0>
 struct SmemLayout {
   static constexpr int B_TILE_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = MT * A_TILE_BYTES + B_TILE_BYTES;
@@ -67,7 +92,7 @@ struct SmemLayout {
   // transposition without padding (the BLOCK_N = 256 layout has < 1 KB to spare next to four 48 KB stages)
   static constexpr int EPI_ROW_FLOATS = 32;
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * EPI_ROW_FLOATS * 4;
-  static constexpr int EPI_BYTES = EPI_STAGE_BYTES + 2 * BLOCK_N * 4;   // + double-buffered (bias + bias2) row
+  static constexpr int EPI_BYTES = EPI_STAGE_BYTES + 2 * BLOCK_N * 4 + EXTRA;   // + double-buffered (bias + bias2) row (+ GNF scratch)
   static constexpr int AVAIL = SMEM_BUDGET - BAR_BYTES - EPI_BYTES;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES;   // dynamic smem is declared 1024-aligned
@@ -231,6 +256,221 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
     }
     __syncwarp();
   }
+}
+
+// ---- GroupNorm-fused epilogue (EPI_GNF) ----------------------------------------------------------------------------
+// out16 = act(GroupNorm(v)), v = acc * scale + (bias + bias2) * scale: the normalisation that FOLLOWS a convolution
+// (layerspp.py:218: h = act(GroupNorm_1(conv1(...) + Dense_0(act(temb))))) is applied by the convolution's own epilogue,
+// so v never exists in HBM and the separate GroupNorm pass (one fp32 read + one fp16 write per element, the HBM-bound
+// third of an evaluation) disappears for these layers.  GroupNorm statistics are per (image, group of cpg channels):
+//   * pass 1 reads the accumulator from TMEM, forms v and reduces it to per-warp (32-row, group) partial sums;
+//   * the eight epilogue warps meet on a named barrier and fold the partials of every image in the tile in a fixed order;
+//     when an image spans several CTAs (gn_xc = 2 or 4: the CTAs of one cluster own the tiles of one image) the per-CTA
+//     sums are exchanged through distributed shared memory (st.shared::cluster + mbarrier release / acquire at cluster
+//     scope) and added in rank order -- deterministic, no atomics;
+//   * pass 2 reads the accumulator AGAIN (it stays resident in its TMEM stage), normalises, applies swish and writes
+//     fp16 rows through the usual swizzled staging buffer as full 64-byte row segments.
+// Tiles may hold several whole images (8x8: two per 128-row tile, 4x4: eight; then a warp's 32 rows split into two
+// 16-row segments).  Rows >= M (ragged last tile of a small batch) are excluded from the sums and not stored.
+struct GnfCtx {
+  float2* pstat;          // [MT][4][2][GNF_GMAX]
+  float2* gstat;          // [GNF_IMGS][GNF_GMAX]
+  float2* xchg;           // [2][4][GNF_GMAX]
+  const float* gam;       // this tile's gamma / beta rows in shared memory
+  const float* bet;
+  uint64_t* xbar;         // cluster exchange barrier (count = gn_xc * groups per tile)
+  uint32_t xparity;       // parity of this tile's exchange phase
+  uint32_t xrank;         // rank of this CTA in the cluster
+  int warp;               // epilogue warp 0..7 (quad = warp & 3, group = warp >> 2)
+};
+
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "GNF_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra GNF_DONE;\n\t"
+      "bra GNF_WAIT_LOOP;\n\t"
+      "GNF_DONE:\n\t"
+      "}\n" ::"r"(ptx::smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ float gnf_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+template <int BLOCK_N, int MT>
+__device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, const GnfCtx& gx) {
+  constexpr int RS = 32;
+  constexpr int NCH = BLOCK_N / 32;
+  constexpr int NQ = MT * NCH;
+  constexpr int TR = MT * BLOCK_M;
+  const GemmArgs& p = cx.p;
+  const int lane = cx.lane;
+  const int rsub = lane >> 3;
+  const int c4 = (lane & 7) * 4;
+  const int quad = gx.warp & 3;
+  const uint32_t stg_w = ptx::smem_u32(cx.stg) + lane * RS * 4;
+  const uint32_t wx = lane & 7;
+  const uint32_t stg_r0 = ptx::smem_u32(cx.stg) + rsub * RS * 4 + (((lane & 7) ^ rsub) << 4);
+  const uint32_t stg_r1 = ptx::smem_u32(cx.stg) + (rsub + 4) * RS * 4 + (((lane & 7) ^ (rsub + 4)) << 4);
+  const uint32_t bias_a = ptx::smem_u32(cx.bias_s) + c4 * 4;
+  const float scale = p.scale;
+  const int cpg = p.gn_cpg;
+  const int rpi = p.gn_rpi;
+  const bool split = rpi < 32;                       // 4x4 images: rows 0-15 and 16-31 of a warp are different images
+  const int G = BLOCK_N / cpg;                       // groups per N tile
+  const long long mwarp = cx.m0;                     // first row of this warp in sub-tile 0 (tile row0 + quad * 32)
+  const long long mtile = cx.m0 - quad * 32;
+
+  ptx::mbar_wait(cx.tfull, cx.tfull_phase);
+  ptx::tc_fence_after();
+  uint32_t r[32];
+  // ---------------- pass 1: per-warp (segment, group) sums of v and v^2 ----------------
+#pragma unroll 1
+  for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
+    const int mi = q / NCH, c0 = (q % NCH) * 32;
+    ptx::tmem_ld_32x32b_x32(cx.taddr + mi * BLOCK_N + c0, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ wx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    const long long mb = mwarp + (long long)mi * BLOCK_M + rsub;
+    float4 bsum = lds128(bias_a + c0 * 4);
+    bsum.x *= scale; bsum.y *= scale; bsum.z *= scale; bsum.w *= scale;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = lds128(((i & 1) ? stg_r1 : stg_r0) + (i >> 1) * 8 * RS * 4);
+      v.x = fmaf(v.x, scale, bsum.x); v.y = fmaf(v.y, scale, bsum.y);
+      v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
+      if (mb + i * 4 < p.M) {
+        const float s = (v.x + v.y) + (v.z + v.w);
+        const float qq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+        if (split && i >= 4) { s1 += s; q1 += qq; } else { s0 += s; q0 += qq; }
+      }
+    }
+    // fold the 4 row sub-groups (lanes l, l+8, l+16, l+24), then the lanes of one group (cpg = 8: lane pairs)
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    }
+    if (cpg == 8) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+    }
+    if (lane < 8 && (cpg == 4 || (lane & 1) == 0)) {
+      const int gi = (c0 + c4) / cpg;
+      float2* dst = gx.pstat + ((mi * 4 + quad) * 2) * GNF_GMAX + gi;
+      dst[0] = make_float2(s0, q0);
+      dst[GNF_GMAX] = make_float2(s1, q1);
+    }
+    __syncwarp();
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  // ---------------- fold: (image, group) -> mean, rstd ----------------
+  const int tid = gx.warp * 32 + lane;
+  const float inv_n = 1.0f / ((float)rpi * (float)cpg);
+  if (p.gn_xc > 1) {
+    // one image spans the gn_xc CTAs of this cluster: this CTA's tile is part of image 0
+    if (tid < G) {
+      float S = 0.f, Q = 0.f;
+      for (int sl = 0; sl < MT * 4; ++sl) {
+        const float2 a = gx.pstat[(sl * 2) * GNF_GMAX + tid];
+        S += a.x; Q += a.y;
+      }
+      float2* mine = gx.xchg + (gx.xparity * 4 + gx.xrank) * GNF_GMAX + tid;
+      const uint32_t my_addr = ptx::smem_u32(mine), bar_addr = ptx::smem_u32(gx.xbar);
+      for (int rk = 0; rk < p.gn_xc; ++rk) {
+        st_cluster_f32x2(ptx::mapa(my_addr, rk), S, Q);
+        mbar_arrive_release_cluster(ptx::mapa(bar_addr, rk));
+      }
+      mbar_wait_acquire_cluster(gx.xbar, gx.xparity);
+      S = 0.f; Q = 0.f;
+      for (int rk = 0; rk < p.gn_xc; ++rk) {
+        const float2 a = gx.xchg[(gx.xparity * 4 + rk) * GNF_GMAX + tid];
+        S += a.x; Q += a.y;
+      }
+      const float mean = S * inv_n;
+      const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+      gx.gstat[tid] = make_float2(mean, rsqrtf(var + p.gn_eps));
+    }
+  } else {
+    const int n_img = rpi >= TR ? 1 : TR / rpi;
+    for (int t = tid; t < n_img * G; t += EPI_WARPS * 32) {
+      const int img = t / G, g = t - img * G;
+      float S = 0.f, Q = 0.f;
+      if (split) {
+        const float2 a = gx.pstat[((img >> 1) * 2 + (img & 1)) * GNF_GMAX + g];
+        S = a.x; Q = a.y;
+      } else {
+        const int per = rpi >= TR ? MT * 4 : rpi / 32;      // 32-row slabs per image
+        for (int k = 0; k < per; ++k) {
+          const float2 a = gx.pstat[((img * per + k) * 2) * GNF_GMAX + g];
+          S += a.x; Q += a.y;
+        }
+      }
+      const float mean = S * inv_n;
+      const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+      gx.gstat[img * GNF_GMAX + g] = make_float2(mean, rsqrtf(var + p.gn_eps));
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  // ---------------- pass 2: normalise, activate, store fp16 ----------------
+  const long long ldo = p.ldo;
+#pragma unroll 1
+  for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
+    const int mi = q / NCH, c0 = (q % NCH) * 32;
+    ptx::tmem_ld_32x32b_x32(cx.taddr + mi * BLOCK_N + c0, r);
+    const float4 g4 = *reinterpret_cast<const float4*>(gx.gam + c0 + c4);
+    const float4 b4 = *reinterpret_cast<const float4*>(gx.bet + c0 + c4);
+    const int gi = (c0 + c4) / cpg;
+    // image of this warp's rows inside the tile: row offset (mi * 128 + quad * 32 [+ 16]) / rpi
+    const int row_off = mi * BLOCK_M + quad * 32;
+    const int img0 = (p.gn_xc > 1 || rpi >= TR) ? 0 : row_off / rpi;
+    const float2 st0 = gx.gstat[img0 * GNF_GMAX + gi];
+    const float2 st1 = split ? gx.gstat[(img0 + 1) * GNF_GMAX + gi] : st0;
+    float4 a0, o0, a1, o1;
+    a0.x = st0.y * g4.x; a0.y = st0.y * g4.y; a0.z = st0.y * g4.z; a0.w = st0.y * g4.w;
+    o0.x = b4.x - st0.x * a0.x; o0.y = b4.y - st0.x * a0.y; o0.z = b4.z - st0.x * a0.z; o0.w = b4.w - st0.x * a0.w;
+    a1.x = st1.y * g4.x; a1.y = st1.y * g4.y; a1.z = st1.y * g4.z; a1.w = st1.y * g4.w;
+    o1.x = b4.x - st1.x * a1.x; o1.y = b4.y - st1.x * a1.y; o1.z = b4.z - st1.x * a1.z; o1.w = b4.w - st1.x * a1.w;
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ wx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    const long long mb = mwarp + (long long)mi * BLOCK_M + rsub;
+    const int n0 = cx.n_tile0 + c0 + c4;
+    float4 bsum = lds128(bias_a + c0 * 4);
+    bsum.x *= scale; bsum.y *= scale; bsum.z *= scale; bsum.w *= scale;
+    __half* o16 = p.out16 + mb * ldo + n0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 v = lds128(((i & 1) ? stg_r1 : stg_r0) + (i >> 1) * 8 * RS * 4);
+      v.x = fmaf(v.x, scale, bsum.x); v.y = fmaf(v.y, scale, bsum.y);
+      v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
+      const float4 aa = (i >= 4) ? a1 : a0, oo = (i >= 4) ? o1 : o0;
+      v.x = fmaf(v.x, aa.x, oo.x); v.y = fmaf(v.y, aa.y, oo.y); v.z = fmaf(v.z, aa.z, oo.z); v.w = fmaf(v.w, aa.w, oo.w);
+      if (p.gn_silu) { v.x = gnf_silu(v.x); v.y = gnf_silu(v.y); v.z = gnf_silu(v.z); v.w = gnf_silu(v.w); }
+      if (mb + i * 4 < p.M) {
+        __half2 h0 = __floats2half2_rn(v.x, v.y);
+        __half2 h1 = __floats2half2_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(o16 + (long long)(i * 4) * ldo) = pk;
+      }
+    }
+    __syncwarp();
+  }
+  (void)mtile;
 }
 
 }  // namespace gddim

@@ -22,7 +22,7 @@ struct GemmSeg {
   int taps;            // 1 or 9
 };
 
-enum { EPI_LINEAR = 0, EPI_SOFTMAX = 1 };
+enum { EPI_LINEAR = 0, EPI_SOFTMAX = 1, EPI_GNF = 2 };
 
 struct GemmOp {
   GemmSeg seg[2];
@@ -53,6 +53,14 @@ struct GemmOp {
   // 32x32-level tensors are larger than the 126 MB L2, so same-direction sweeps get no hits at all); unet.cpp
   // alternates the direction along every producer -> consumer chain.  Results do not depend on it.
   int reverse;
+  // EPI_GNF: out16 = act(GroupNorm(linear epilogue value)) -- the GroupNorm that follows the convolution is applied by
+  // its own epilogue (two passes over the TMEM accumulator, statistics exchanged inside the CTA / across the cluster);
+  // out32, colstats, residual and rowscale must be null.  gemm_gnf_supported() tells which geometries qualify.
+  const float* gn_gamma;    // [N]
+  const float* gn_beta;     // [N]
+  float gn_eps;
+  int gn_groups;            // groups over the N output channels (channels per group must be 4 or 8)
+  int gn_silu;
   // EXPERIMENTAL (GDDIM_XF=1, conv_xf.cu): A operand = swish(GroupNorm(source)) produced on load from the fp32 source(s)
   int xf;
   const float* xf_src1; int xf_c1;
@@ -69,8 +77,13 @@ struct GemmOp {
   int stages, stage_bytes, a_bytes;   // halo: smem ring geometry
   CUtensorMap tmH;          // halo box of segment 0
   int m_tiles, n_tiles, tiles_per_batch;
+  int gn_xc;                // EPI_GNF: CTAs per image = cluster size (1, 2, 4)
   int prepared;
 };
+
+// EPI_GNF is available for H*W in {16, 64, 256} (any N that is a multiple of 32) and for H*W = 1024 with N in {64, 128};
+// channels per group 4 or 8
+int gemm_gnf_supported(int H, int W, int N, int groups);
 
 // Encodes the TMA descriptors (needs the final device addresses). Returns 0 or a negative error.
 int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub = 0, int force_cg = 0);

@@ -137,7 +137,10 @@ int gddim_dct2d_32(const float* in_dev, float* out_dev, int batch, int C, int fo
  *      flax nn.GroupNorm + swish + up_or_down_sampling resamplers, layerspp.py:196-213) ----
  * out[m,n] = (sum_seg sum_tap sum_c A_seg[pixel(m)+tap, c] Wt[n, k] * rowscale[m] + bias[n] + bias2[n]
  *             + residual[m,n]) * scale, m over the [B,H,W] pixel grid.  A*, w, out16: fp16; K-major weights
- * Wt [N, w_ld] with k = w_koff + seg-major, tap-major, channel-minor.  epi = 1: row softmax (N == 256). */
+ * Wt [N, w_ld] with k = w_koff + seg-major, tap-major, channel-minor.  epi = 1: row softmax (N == 256).
+ * epi = 2: the GroupNorm (+ swish) that FOLLOWS the convolution (layerspp.py:218 h = act(GroupNorm_1(h))) applied by
+ * the epilogue itself: out16 = act(GN(out)) with flax semantics (eps, contiguous groups, statistics per image);
+ * gn_gamma / gn_beta [N], out32 / residual / rowscale must be NULL; geometries: gddim_gemm_gnf_supported. */
 typedef struct {
   const void* a0; int a0_ctot, a0_coff, a0_c, a0_taps;
   const void* a1; int a1_ctot, a1_coff, a1_c, a1_taps;      /* a1 = NULL: single segment */
@@ -147,15 +150,18 @@ typedef struct {
   const float* bias; const float* bias2; const float* residual; const float* rowscale;
   float scale;
   float* out32; void* out16; float* row_out; int ldo;
-  int epi;                                                  /* 0 linear, 1 softmax */
+  int epi;                                                  /* 0 linear, 1 softmax, 2 linear + GroupNorm(+swish) of the output */
   int impl;                                                 /* 0 tcgen05, 1 CUDA-core reference */
   int force_block_n;                                        /* 0 = heuristic */
   int force_m_sub;                                          /* with force_block_n: 2 = 256-row CTA tiles */
   int n_store;                                              /* 0 = all N; else store only columns < n_store (fp32) */
   int force_cta_pairs;                                      /* 0 = heuristic, 1 = single-CTA MMA, 2 = cta_group::2 pairs (block_n 256) */
   int reverse;                                              /* 1 = tiles in descending order (L2 reuse along producer -> consumer chains); same results */
+  const float* gn_gamma; const float* gn_beta;              /* epi = 2 */
+  float gn_eps; int gn_groups; int gn_silu; int pad_;
 } gddim_gemm_desc;
 int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream);
+int gddim_gemm_gnf_supported(int H, int W, int N, int groups);   /* 1 if epi = 2 is available for this output geometry */
 
 /* resample: 0 none, 1 FIR down, 2 FIR up, 3 naive (mean) down, 4 naive (repeat) up.  dst16 = act(GN(x)) resampled,
  * raw16 = x resampled (either may be NULL).  Sources are fp32 NHWC, channel-concatenated (src2 optional). */

@@ -380,3 +380,64 @@ def test_few_channel_output_umma_or_ref(impl):
   o32, _ = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(kp), 32, taps0=9, bias=bp.cuda(), impl=impl, n_store=6)
   assert o32.shape == (3, 32, 32, 6)
   assert rel_l2(o32.cpu().numpy(), want.numpy()) < 2e-5
+
+
+GNF_CASES = [  # B, H, W, Cin, N, taps, force_block_n, force_m_sub, force_pairs     (what it exercises)
+    (3, 16, 16, 128, 256, 9, 0, 0, 0),      # image = 2 CTAs: cluster of two single-CTA MMAs (DSMEM exchange)
+    (4, 16, 16, 128, 256, 9, 256, 1, 2),    # image = one cta_group::2 pair
+    (2, 32, 32, 64, 128, 9, 0, 0, 0),       # image = 4 CTAs, 256-row halo tiles
+    (3, 32, 32, 64, 64, 9, 0, 0, 0),        # image = 4 CTAs, plain 256-row tiles, 4 channels per group
+    (5, 8, 8, 128, 256, 9, 0, 0, 0),        # two images per tile, ragged last tile
+    (3, 4, 4, 256, 256, 9, 0, 0, 0),        # 16-row images: a warp's 32 rows split in two, M = 48 < one tile
+    (9, 4, 4, 128, 128, 9, 128, 2, 0),      # 256-row tiles of 16 images, 4 channels per group
+    (2, 16, 16, 64, 128, 9, 128, 2, 0),     # tile = exactly one image
+    (2, 16, 16, 64, 128, 1, 128, 1, 0),     # 1x1 convolution, image = 2 CTAs
+    (6, 8, 8, 256, 256, 9, 64, 1, 0),       # narrow N tiles: groups never straddle tiles
+    (40, 16, 16, 128, 256, 9, 0, 0, 0),     # more tiles than SMs: persistent loop, exchange parity alternates
+    (37, 32, 32, 128, 128, 9, 0, 0, 0),     # more 4-clusters than fit at once
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
+@pytest.mark.parametrize("silu", [True, False])
+@pytest.mark.parametrize("case", GNF_CASES, ids=[f"b{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}_t{c[5]}_bn{c[6]}x{c[7]}_cg{c[8]}" for c in GNF_CASES])
+def test_conv_with_groupnorm_epilogue(impl, silu, case):
+  """epi = 2: out16 = act(GroupNorm(conv(a) + bias + bias2)) in ONE kernel == the reference order conv -> GroupNorm_1 ->
+  swish of layerspp.py:214-219 (torch fp64 on the same fp16 operands; flax eps 1e-6, min(C/4, 32) groups)."""
+  B, H, W, Cin, N, taps, bn, ms, pairs = case
+  if impl == 1 and (bn or B > 9):
+    pytest.skip("tile variants do not exist on the CUDA-core path")
+  g = torch.Generator().manual_seed(B * 131 + H + N)
+  a = torch.randn(B, H, W, Cin, generator=g).to(torch.float16)
+  kk = 3 if taps == 9 else 1
+  k = (torch.randn(kk, kk, Cin, N, generator=g) / np.sqrt(taps * Cin)).numpy()
+  bias, bias2 = torch.randn(N, generator=g), 0.5 * torch.randn(N, generator=g)
+  gamma, beta = 1 + 0.2 * torch.randn(N, generator=g), 0.3 * torch.randn(N, generator=g)
+  groups = min(N // 4, 32)
+  assert ops._lib.lib().gddim_gemm_gnf_supported(H, W, N, groups) == 1
+  v = _conv_ref(a, k, taps) + (bias + bias2).double()
+  # per-image offsets so that the statistics really differ between the images of one tile
+  want = F.group_norm(v.permute(0, 3, 1, 2), groups, gamma.double(), beta.double(), eps=1e-6)
+  if silu:
+    want = on.swish(want)
+  want = want.permute(0, 2, 3, 1)
+  _, o16 = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k), N, taps0=taps, bias=bias.cuda(), bias2=bias2.cuda(), impl=impl,
+                         force_block_n=bn, force_m_sub=ms, force_cta_pairs=pairs, gn=(gamma.cuda(), beta.cuda(), groups, silu))
+  torch.cuda.synchronize()
+  e = rel_l2(o16.float().cpu().numpy(), want.numpy())
+  print(f"gnf {case} impl={impl} silu={silu}: rel_l2={e:.2e}")
+  assert e < 6e-4                                    # fp16 output rounding ~ 2^-11 / sqrt(3)
+  # per image: a wrong statistic (mixed-up images inside a tile) shows up as a per-image error, not in the global norm
+  per = [rel_l2(o16[b].float().cpu().numpy(), want[b].numpy()) for b in range(B)]
+  assert max(per) < 8e-4, per
+
+
+def test_groupnorm_epilogue_is_deterministic_and_reverse_invariant():
+  B, H, W, Cin, N = 6, 16, 16, 128, 256
+  g = torch.Generator().manual_seed(7)
+  a = torch.randn(B, H, W, Cin, generator=g).to(torch.float16).cuda()
+  w = ops.pack_conv_weight((torch.randn(3, 3, Cin, N, generator=g) / np.sqrt(9 * Cin)).numpy())
+  gamma, beta = (1 + 0.2 * torch.randn(N, generator=g)).cuda(), (0.3 * torch.randn(N, generator=g)).cuda()
+  outs = [ops.conv_gemm(a, w, N, gn=(gamma, beta, 32, True), reverse=r)[1] for r in (0, 1, 0)]
+  torch.cuda.synchronize()
+  assert torch.equal(outs[0], outs[2]) and torch.equal(outs[0], outs[1])
