@@ -86,8 +86,10 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       ptx::mbar_init(&tfull_bar[s], 1);
       ptx::mbar_init(&tempty_bar[s], (EPI == EPI_SOFTMAX ? 4 : EPI_WARPS) * CG);   // both CTAs' epilogues (leader's barrier)
     }
-    if (GNF)      // statistics exchange: one arrival per (CTA of the cluster, group of the N tile) and tile
-      ptx::mbar_init(reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR), p.gn_xc * (BLOCK_N / p.gn_cpg));
+    if (GNF) {    // statistics exchange: one local arrival (expect_tx) + the bytes of every CTA of the cluster per tile
+      ptx::mbar_init(reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR), 1);
+      ptx::mbar_init(reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR) + 1, 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -182,9 +184,12 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    int mma_seq = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++mma_seq) {
+      GDDIM_STAMP(p, true, mma_seq, 8);
       ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
+      GDDIM_STAMP(p, true, mma_seq, 9);
       const uint32_t d_tmem = tmem_base + acc * MT * BLOCK_N;
       uint32_t accum = 0;                             // 0 for the first MMA of every accumulator of the tile
       auto issue = [&](uint32_t a_addr, uint32_t b_addr, uint32_t acc_flag) {
@@ -224,6 +229,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         }
       }
       // accumulator ready for the epilogue (of both CTAs)
+      GDDIM_STAMP(p, true, mma_seq, 10);
       if (CG == 2) ptx::umma_commit_2cta(&tfull_bar[acc], 3); else ptx::umma_commit(&tfull_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -235,7 +241,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     int bias_buf = 0;
-    for (int tile_i = tile0; tile_i < num_tiles; tile_i += tile_step, bias_buf ^= 1) {
+    int tile_seq = 0;
+    for (int tile_i = tile0; tile_i < num_tiles; tile_i += tile_step, bias_buf ^= 1, ++tile_seq) {
       const int tile = p.reverse ? num_tiles - 1 - tile_i : tile_i;
       const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
       const long long m = (long long)mt * MT * BLOCK_M + row;
@@ -259,8 +266,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
                                (long long)mt * MT * BLOCK_M + quad * 32, nt * BLOCK_N, lane, group};
         GnfCtx gx{reinterpret_cast<float2*>(gnf_smem), reinterpret_cast<float2*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_GSTAT),
                   reinterpret_cast<float2*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_XCHG), gb, gb + BLOCK_N,
-                  reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR), (uint32_t)bias_buf,
-                  clustered ? ptx::cluster_ctarank() : 0u, warp};
+                  reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR), (uint32_t)(tile_seq & 1),
+                  (uint32_t)((tile_seq >> 1) & 1), clustered ? ptx::cluster_ctarank() : 0u, warp, tile_seq};
         epi_tile_gnf<BLOCK_N, MT>(cx, gx);
       } else if (EPI == EPI_LINEAR) {
         // TMEM -> registers (thread = row) -> padded smem -> registers (8 lanes = one 32-column row segment),
@@ -291,7 +298,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         const unsigned mode = (p.residual ? 1u : 0u) | (p.out32 ? 2u : 0u) | (p.out16 ? 4u : 0u) |
                               (p.colstats ? 8u : 0u) | (p.rowscale ? 16u : 0u);
         EpiCtx<BLOCK_N, MT> cx{p, stg, bias_s, &tfull_bar[acc], acc_phase, tmem_base + (uint32_t(quad * 32) << 16) + acc * MT * BLOCK_N,
-                               (long long)mt * MT * BLOCK_M + quad * 32, nt * BLOCK_N, lane, group};
+                               (long long)mt * MT * BLOCK_M + quad * 32, nt * BLOCK_N, lane, group, tile_seq, warp};
         if (p.n_store > 0) epi_tile<BLOCK_N, MT, false, true, false, false, false, false, false, true>(cx);   // few-channel output
         else if (!full) epi_tile<BLOCK_N, MT, true, true, true, true, true, false, true>(cx);     // ragged last tile: generic path
         else if (mode == (2u | 8u)) epi_tile<BLOCK_N, MT, false, true, false, true, false, true, false>(cx);           // conv1, shortcut conv2, stem
@@ -804,6 +811,7 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
       int n = 0;
       if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms / xc / 2 > 0 ? num_sms / xc / 2 : 1; }
       max_clusters[dev][xc] = n;
+      if (getenv("GDDIM_VERBOSE")) fprintf(stderr, "gddim: conv_gemm<%d,GNF,%d,%d,%d>: %d co-resident clusters of %d CTAs (%d SMs)\n", BN, MT, CG, (int)HALO, n, xc, num_sms);
     }
     int clusters = tiles / xc;
     if (clusters > max_clusters[dev][xc]) clusters = max_clusters[dev][xc];
@@ -882,7 +890,30 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
       static int dbg = -1;
       if (dbg < 0) { const char* e = getenv("GDDIM_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
       a.dbg = dbg;
+      static long long* clk = nullptr;
+      if (getenv("GDDIM_CLK")) {
+        if (!clk) cudaMalloc(&clk, 16 * 16 * sizeof(long long));
+        cudaMemsetAsync(clk, 0, 16 * 16 * sizeof(long long), st);
+        a.dbg_clk = clk;
+      }
     }
+    struct ClkDump {
+      long long* clk; cudaStream_t st;
+      ~ClkDump() {
+        if (!clk) return;
+        long long h[256];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+        long long t0 = h[8];
+        fprintf(stderr, "CLK timeline CTA 0 (cycles since the MMA thread first waited):\n");
+        for (int t = 0; t < 10; ++t) {
+          if (h[t * 16 + 8] == 0) break;
+          fprintf(stderr, " tile %d  mma: wait %lld..%lld issue_done %lld | epi: wait %lld..%lld p1 %lld bar %lld fold %lld bar %lld p2 %lld\n", t,
+                  h[t * 16 + 8] - t0, h[t * 16 + 9] - t0, h[t * 16 + 10] - t0, h[t * 16 + 0] - t0, h[t * 16 + 1] - t0,
+                  h[t * 16 + 2] - t0, h[t * 16 + 3] - t0, h[t * 16 + 4] - t0, h[t * 16 + 5] - t0, h[t * 16 + 6] - t0);
+        }
+      }
+    } clk_dump{a.dbg_clk, st};
 #endif
     if (op->epi == EPI_SOFTMAX) return launch_umma<256, EPI_SOFTMAX, 1>(op, a, st);
     a.stages = op->stages; a.stage_bytes = op->stage_bytes; a.a_bytes = op->a_bytes;

@@ -9,8 +9,11 @@
 
 #ifdef GDDIM_ABLATE
 #define GDDIM_DBG_STORE(p) ((p).dbg != 2)
+// clock64 stamp `slot` of tile `t` (CTA 0, one lane): timeline experiments only
+#define GDDIM_STAMP(p, cond, t, slot) do { if ((p).dbg_clk && blockIdx.x == 0 && (cond) && (t) < 16) (p).dbg_clk[(t) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define GDDIM_DBG_STORE(p) true
+#define GDDIM_STAMP(p, cond, t, slot) do { } while (0)
 #endif
 
 namespace gddim {
@@ -59,6 +62,7 @@ struct GemmArgs {
   int gn_silu;
   int gn_rpi;              // rows (pixels) per image = H * W
   int gn_xc;               // CTAs an image spans = cluster size of the launch (1, 2 or 4)
+  long long* dbg_clk;   // GDDIM_ABLATE builds: clock64 timeline of CTA 0 ([tile < 16][16 stamps]), else null
   int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };
 
@@ -80,7 +84,7 @@ struct GnfSmem {
   static constexpr int OFF_XCHG = OFF_GSTAT + GNF_GSTAT_BYTES;
   static constexpr int OFF_GB = OFF_XCHG + GNF_XCHG_BYTES;
   static constexpr int OFF_BAR = OFF_GB + GB_BYTES;
-  static constexpr int BYTES = OFF_BAR + 16;
+  static constexpr int BYTES = OFF_BAR + 16;                    // two mbarriers
 };
 
 template <int BLOCK_N, int MT, int CG = 1, int EXTRA = 0>
@@ -117,6 +121,8 @@ struct EpiCtx {
   int n_tile0;             // first output column of the tile
   int lane;
   int group;               // epilogue group: takes the 32-column chunks q = group, group + 2, ...
+  int tile_seq = 0;        // tiles this CTA has processed before (timeline stamps)
+  int warp_id = -1;
 };
 
 __device__ __forceinline__ float4 lds128(uint32_t a) {
@@ -166,8 +172,10 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
   float4 res[8];
   if (RES && cx.group < NQ) load_res(cx.group, res);
   __syncwarp();
+  GDDIM_STAMP(p, cx.warp_id == 0 && lane == 0, cx.tile_seq, 0);
   ptx::mbar_wait(cx.tfull, cx.tfull_phase);
   ptx::tc_fence_after();
+  GDDIM_STAMP(p, cx.warp_id == 0 && lane == 0, cx.tile_seq, 1);
   uint32_t r[32];
 #ifdef GDDIM_ABLATE
   if (p.dbg == 3) return;
@@ -256,6 +264,7 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
     }
     __syncwarp();
   }
+  GDDIM_STAMP(p, cx.warp_id == 0 && lane == 0, cx.tile_seq, 6);
 }
 
 // ---- GroupNorm-fused epilogue (EPI_GNF) ----------------------------------------------------------------------------
@@ -278,10 +287,12 @@ struct GnfCtx {
   float2* xchg;           // [2][4][GNF_GMAX]
   const float* gam;       // this tile's gamma / beta rows in shared memory
   const float* bet;
-  uint64_t* xbar;         // cluster exchange barrier (count = gn_xc * groups per tile)
-  uint32_t xparity;       // parity of this tile's exchange phase
+  uint64_t* xbar;         // two cluster exchange barriers (count 1 + transaction bytes), alternating by tile parity
+  uint32_t xparity;       // which barrier / exchange buffer this tile uses (tile_seq & 1)
+  uint32_t xphase;        // phase parity of that barrier ((tile_seq >> 1) & 1)
   uint32_t xrank;         // rank of this CTA in the cluster
   int warp;               // epilogue warp 0..7 (quad = warp & 3, group = warp >> 2)
+  int tile_seq;           // how many tiles this CTA has processed before (timeline stamps)
 };
 
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
@@ -304,6 +315,81 @@ __device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_
       : "memory");
 }
 __device__ __forceinline__ float gnf_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// asynchronous remote store that completes `8` bytes on the destination CTA's mbarrier (no fence on the sender side:
+// a release at cluster scope would first drain this thread's outstanding global stores, measured ~5 k cycles per tile)
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
+               "f"(a), "f"(b), "r"(cluster_bar)
+               : "memory");
+}
+// Recursive-halving all-to-one reduction over the lanes of a warp (or of each 16-lane half when HALF): every lane enters
+// with NV partial values; after log2(NV) exchange steps lane L holds the total of value gnf_holder_index(L) over all
+// participating lanes -- NV shuffles in total instead of NV * log2(lanes).
+template <int N>
+__device__ __forceinline__ void gnf_halve(float (&a)[16], int mask, int lane) {
+  const bool upper = (lane & mask) != 0;
+#pragma unroll
+  for (int k = 0; k < N / 2; ++k) {
+    const float send = upper ? a[k] : a[k + N / 2];
+    const float keep = upper ? a[k + N / 2] : a[k];
+    a[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+  }
+}
+template <int NV, bool HALF>
+__device__ __forceinline__ float gnf_reduce(float (&a)[16], int lane) {
+  // halving steps use the highest lane bits; the remaining low bits are folded with plain butterfly adds
+  if (HALF) {
+    if (NV == 16) { gnf_halve<16>(a, 8, lane); gnf_halve<8>(a, 4, lane); gnf_halve<4>(a, 2, lane); gnf_halve<2>(a, 1, lane); }
+    else { gnf_halve<8>(a, 8, lane); gnf_halve<4>(a, 4, lane); gnf_halve<2>(a, 2, lane); a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1); }
+  } else {
+    if (NV == 16) { gnf_halve<16>(a, 16, lane); gnf_halve<8>(a, 8, lane); gnf_halve<4>(a, 4, lane); gnf_halve<2>(a, 2, lane);
+                    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1); }
+    else { gnf_halve<8>(a, 16, lane); gnf_halve<4>(a, 8, lane); gnf_halve<2>(a, 4, lane);
+           a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2); a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1); }
+  }
+  return a[0];
+}
+// which value a lane holds after gnf_reduce, and whether it is the lane that publishes it
+template <int NV, bool HALF>
+__device__ __forceinline__ int gnf_holder_index(int lane, bool* writer) {
+  if (HALF) {
+    if (NV == 16) { *writer = true; return lane & 15; }
+    *writer = (lane & 1) == 0; return (lane >> 1) & 7;
+  }
+  if (NV == 16) { *writer = (lane & 1) == 0; return (lane >> 1) & 15; }
+  *writer = (lane & 3) == 0; return (lane >> 2) & 7;
+}
+
+// pass 1 of one 32 x 32 chunk held as thread = row: v = acc * scale + bias, per-(group, stat) partials (gnf_chunk_partials),
+// then the lane reduction (gnf_chunk_reduce) -- split in two so that the TMEM load of the next chunk can be issued in between
+template <int NV>
+__device__ __forceinline__ void gnf_chunk_partials(const uint32_t (&r)[32], uint32_t bias_base, float scale, bool row_ok,
+                                                   float (&a)[16]) {
+  constexpr int CPG = 64 / NV;                        // NV = 2 * groups per 32-column chunk
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = 0.f;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float4 b = lds128(bias_base + j4 * 16);
+    const float v0 = row_ok ? fmaf(__uint_as_float(r[4 * j4 + 0]), scale, b.x * scale) : 0.f;
+    const float v1 = row_ok ? fmaf(__uint_as_float(r[4 * j4 + 1]), scale, b.y * scale) : 0.f;
+    const float v2 = row_ok ? fmaf(__uint_as_float(r[4 * j4 + 2]), scale, b.z * scale) : 0.f;
+    const float v3 = row_ok ? fmaf(__uint_as_float(r[4 * j4 + 3]), scale, b.w * scale) : 0.f;
+    const int g = (4 * j4) / CPG;                     // compile-time after unrolling
+    a[2 * g] += (v0 + v1) + (v2 + v3);
+    a[2 * g + 1] = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, a[2 * g + 1]))));
+  }
+}
+template <int NV, bool HALF>
+__device__ __forceinline__ void gnf_chunk_reduce(float (&a)[16], int lane, float2* dst_seg0, int gi0) {
+  const float tot = gnf_reduce<NV, HALF>(a, lane);
+  bool writer;
+  const int idx = gnf_holder_index<NV, HALF>(lane, &writer);
+  if (writer) {
+    float* d = reinterpret_cast<float*>(dst_seg0 + (HALF && lane >= 16 ? GNF_GMAX : 0) + gi0 + (idx >> 1)) + (idx & 1);
+    *d = tot;
+  }
+}
 
 template <int BLOCK_N, int MT>
 __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, const GnfCtx& gx) {
@@ -329,57 +415,51 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
   const long long mwarp = cx.m0;                     // first row of this warp in sub-tile 0 (tile row0 + quad * 32)
   const long long mtile = cx.m0 - quad * 32;
 
+  const bool stamp = gx.warp == 0 && lane == 0;
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 0);
   ptx::mbar_wait(cx.tfull, cx.tfull_phase);
   ptx::tc_fence_after();
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 1);
   uint32_t r[32];
   // ---------------- pass 1: per-warp (segment, group) sums of v and v^2 ----------------
+  // thread = accumulator row: no staging through shared memory, the lanes are reduced with recursive-halving shuffles;
+  // the TMEM load of chunk q + 1 is in flight while the partials of chunk q are reduced
+  {
+    const long long mrow = mwarp + lane;                         // this thread's row in sub-tile 0
+    const uint32_t bias_row = ptx::smem_u32(cx.bias_s);
+    if (cx.group < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (cx.group / NCH) * BLOCK_N + (cx.group % NCH) * 32, r);
 #pragma unroll 1
-  for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
-    const int mi = q / NCH, c0 = (q % NCH) * 32;
-    ptx::tmem_ld_32x32b_x32(cx.taddr + mi * BLOCK_N + c0, r);
-    ptx::tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ wx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-    __syncwarp();
-    const long long mb = mwarp + (long long)mi * BLOCK_M + rsub;
-    float4 bsum = lds128(bias_a + c0 * 4);
-    bsum.x *= scale; bsum.y *= scale; bsum.z *= scale; bsum.w *= scale;
-    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 v = lds128(((i & 1) ? stg_r1 : stg_r0) + (i >> 1) * 8 * RS * 4);
-      v.x = fmaf(v.x, scale, bsum.x); v.y = fmaf(v.y, scale, bsum.y);
-      v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
-      if (mb + i * 4 < p.M) {
-        const float s = (v.x + v.y) + (v.z + v.w);
-        const float qq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-        if (split && i >= 4) { s1 += s; q1 += qq; } else { s0 += s; q0 += qq; }
+    for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
+      const int mi = q / NCH, c0 = (q % NCH) * 32;
+      const bool row_ok = mrow + (long long)mi * BLOCK_M < p.M;
+      float2* dst = gx.pstat + ((mi * 4 + quad) * 2) * GNF_GMAX;
+      const int gi0 = c0 / cpg;
+      float a[16];
+      ptx::tmem_ld_wait();
+      if (cpg == 4) gnf_chunk_partials<16>(r, bias_row + c0 * 4, scale, row_ok, a);
+      else gnf_chunk_partials<8>(r, bias_row + c0 * 4, scale, row_ok, a);
+      const int qn = q + EPI_GROUPS;
+      if (qn < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (qn / NCH) * BLOCK_N + (qn % NCH) * 32, r);
+      if (cpg == 4) {
+        if (split) gnf_chunk_reduce<16, true>(a, lane, dst, gi0); else gnf_chunk_reduce<16, false>(a, lane, dst, gi0);
+      } else {
+        if (split) gnf_chunk_reduce<8, true>(a, lane, dst, gi0); else gnf_chunk_reduce<8, false>(a, lane, dst, gi0);
       }
     }
-    // fold the 4 row sub-groups (lanes l, l+8, l+16, l+24), then the lanes of one group (cpg = 8: lane pairs)
-#pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-    }
-    if (cpg == 8) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
-    }
-    if (lane < 8 && (cpg == 4 || (lane & 1) == 0)) {
-      const int gi = (c0 + c4) / cpg;
-      float2* dst = gx.pstat + ((mi * 4 + quad) * 2) * GNF_GMAX + gi;
-      dst[0] = make_float2(s0, q0);
-      dst[GNF_GMAX] = make_float2(s1, q1);
-    }
-    __syncwarp();
   }
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 2);
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 3);
   // ---------------- fold: (image, group) -> mean, rstd ----------------
   const int tid = gx.warp * 32 + lane;
   const float inv_n = 1.0f / ((float)rpi * (float)cpg);
   if (p.gn_xc > 1) {
-    // one image spans the gn_xc CTAs of this cluster: this CTA's tile is part of image 0
+    // one image spans the gn_xc CTAs of this cluster: this CTA's tile is part of image 0.  Exchange: every CTA sends its
+    // G (sum, sumsq) pairs to all CTAs of the cluster with asynchronous remote stores that complete bytes on the
+    // receiver's mbarrier (armed below with the expected byte count); two barriers / buffers alternate by tile parity,
+    // so data of tile i + 1 can never be counted into the phase of tile i.
+    uint64_t* xb = gx.xbar + gx.xparity;
+    if (tid == 0) ptx::mbar_arrive_expect_tx(xb, (uint32_t)(p.gn_xc * G * 8));
     if (tid < G) {
       float S = 0.f, Q = 0.f;
       for (int sl = 0; sl < MT * 4; ++sl) {
@@ -387,12 +467,9 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
         S += a.x; Q += a.y;
       }
       float2* mine = gx.xchg + (gx.xparity * 4 + gx.xrank) * GNF_GMAX + tid;
-      const uint32_t my_addr = ptx::smem_u32(mine), bar_addr = ptx::smem_u32(gx.xbar);
-      for (int rk = 0; rk < p.gn_xc; ++rk) {
-        st_cluster_f32x2(ptx::mapa(my_addr, rk), S, Q);
-        mbar_arrive_release_cluster(ptx::mapa(bar_addr, rk));
-      }
-      mbar_wait_acquire_cluster(gx.xbar, gx.xparity);
+      const uint32_t my_addr = ptx::smem_u32(mine), bar_addr = ptx::smem_u32(xb);
+      for (int rk = 0; rk < p.gn_xc; ++rk) st_async_f32x2(ptx::mapa(my_addr, rk), S, Q, ptx::mapa(bar_addr, rk));
+      ptx::mbar_wait(xb, gx.xphase);
       S = 0.f; Q = 0.f;
       for (int rk = 0; rk < p.gn_xc; ++rk) {
         const float2 a = gx.xchg[(gx.xparity * 4 + rk) * GNF_GMAX + tid];
@@ -422,13 +499,15 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
       gx.gstat[img * GNF_GMAX + g] = make_float2(mean, rsqrtf(var + p.gn_eps));
     }
   }
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 4);
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 5);
   // ---------------- pass 2: normalise, activate, store fp16 ----------------
   const long long ldo = p.ldo;
+  if (cx.group < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (cx.group / NCH) * BLOCK_N + (cx.group % NCH) * 32, r);
 #pragma unroll 1
   for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
     const int mi = q / NCH, c0 = (q % NCH) * 32;
-    ptx::tmem_ld_32x32b_x32(cx.taddr + mi * BLOCK_N + c0, r);
     const float4 g4 = *reinterpret_cast<const float4*>(gx.gam + c0 + c4);
     const float4 b4 = *reinterpret_cast<const float4*>(gx.bet + c0 + c4);
     const int gi = (c0 + c4) / cpg;
@@ -445,6 +524,11 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ wx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    // the registers are free again: the TMEM load of the next chunk overlaps the normalise / swish / store work below
+    {
+      const int qn = q + EPI_GROUPS;
+      if (qn < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (qn / NCH) * BLOCK_N + (qn % NCH) * 32, r);
+    }
     __syncwarp();
     const long long mb = mwarp + (long long)mi * BLOCK_M + rsub;
     const int n0 = cx.n_tile0 + c0 + c4;
@@ -470,6 +554,7 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
     }
     __syncwarp();
   }
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 6);
   (void)mtile;
 }
 

@@ -280,9 +280,18 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
       w1 = upload_f16(pk);
     }
   }
-  T32 h2 = new32(out_ch, Ho, Wo);
+  // GroupNorm_1 + swish applied by conv1's own epilogue (EPI_GNF, conv_gemm.cu): h = conv1(...) + Dense_0(act(temb)) is
+  // never written; conv1 emits conv2's fp16 A operand directly.  Geometries the epilogue does not cover (images spanning
+  // more than four CTAs) keep the separate pass.  GDDIM_NO_GNF=1: A/B switch.
+  static const bool no_gnf = [] { const char* e = getenv("GDDIM_NO_GNF"); return e && e[0] == '1'; }();
+  auto gn1 = gn_params(s, out_ch);
+  const int groups1 = std::min(out_ch / 4, 32);
+  const bool fuse1 = !no_gnf && gemm_gnf_supported(Ho, Wo, out_ch, groups1);
+  T16 a2 = new16(out_ch, Ho, Wo);
+  T32 h2{nullptr, 0, 0, 0, 0};
+  if (!fuse1) h2 = new32(out_ch, Ho, Wo);
   {
-    Op op; op.kind = OP_GEMM; op.tag = s.prefix + "conv1";
+    Op op; op.kind = OP_GEMM; op.tag = s.prefix + (fuse1 ? "conv1_gn1" : "conv1");
     op.gemm = make_gemm(max_batch_, Ho, Wo);
     GemmOp& g = op.gemm;
     g.nseg = 1;
@@ -290,16 +299,22 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     g.w = w1; g.N = out_ch; g.w_ld = 9 * Cin;
     g.bias = bias1;
     g.bias2 = temb_off >= 0 ? temb_cur_ + temb_off : nullptr;
-    g.out32 = h2.p; g.ldo = out_ch;
-    g.colstats = h2.stats; h2.stats_valid = h2.stats != nullptr;
+    g.ldo = out_ch;
+    if (fuse1) {
+      g.epi = EPI_GNF;
+      g.out16 = a2.p;
+      g.gn_gamma = gn1.first; g.gn_beta = gn1.second; g.gn_eps = 1e-6f; g.gn_groups = groups1; g.gn_silu = 1;
+    } else {
+      g.out32 = h2.p;
+      g.colstats = h2.stats; h2.stats_valid = h2.stats != nullptr;
+    }
     ops_.push_back(op);
   }
   rel(a1);
-
-  auto gn1 = gn_params(s, out_ch);
-  T16 a2 = new16(out_ch, Ho, Wo);
-  add_norm(h2, nullptr, gn1.first, gn1.second, true, RS_NONE, &a2, nullptr, s.prefix + "gn1");
-  rel(h2);
+  if (!fuse1) {
+    add_norm(h2, nullptr, gn1.first, gn1.second, true, RS_NONE, &a2, nullptr, s.prefix + "gn1");
+    rel(h2);
+  }
 
   Scope c1 = s.child("Conv");
   const auto* k1 = param(c1, "kernel", {3, 3, out_ch, out_ch}, 0, scale0(0.f));   // init_scale = config.model.init_scale
