@@ -248,6 +248,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       const long long m = (long long)mt * MT * BLOCK_M + row;
       const bool valid = m < p.M;
       uint32_t r[32];
+      bool tmem_released = false;
       if (GNF) {
         constexpr int RS = L::EPI_ROW_FLOATS;
         float* stg = epi_stage + warp * 32 * RS;
@@ -268,7 +269,25 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
                   reinterpret_cast<float2*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_XCHG), gb, gb + BLOCK_N,
                   reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR), (uint32_t)(tile_seq & 1),
                   (uint32_t)((tile_seq >> 1) & 1), clustered ? ptx::cluster_ctarank() : 0u, warp, tile_seq};
-        epi_tile_gnf<BLOCK_N, MT>(cx, gx);
+        if (p.out32 != nullptr) {
+          // dual mode: pass 1 = the plain linear epilogue (fp32 result + column statistics) with the group-partials hook;
+          // the accumulator is free afterwards, pass 2 re-reads the fp32 result
+          const bool full = ((long long)(mt + 1) * MT * BLOCK_M <= (long long)p.M);
+          if (!full) epi_tile<BLOCK_N, MT, true, true, false, true, false, false, true, false, true>(cx, gx.pstat, quad);
+          else if (p.residual != nullptr) epi_tile<BLOCK_N, MT, true, true, false, true, false, true, false, false, true>(cx, gx.pstat, quad);
+          else epi_tile<BLOCK_N, MT, false, true, false, true, false, true, false, false, true>(cx, gx.pstat, quad);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty_bar[acc]), 0));
+            else ptx::mbar_arrive(&tempty_bar[acc]);
+          }
+          tmem_released = true;
+          gnf_fold<BLOCK_N, MT>(p, gx, lane);
+          epi_tile_gnf_dual_pass2<BLOCK_N, MT>(cx, gx);
+        } else {
+          epi_tile_gnf<BLOCK_N, MT>(cx, gx);
+        }
       } else if (EPI == EPI_LINEAR) {
         // TMEM -> registers (thread = row) -> padded smem -> registers (8 lanes = one 32-column row segment),
         // so that every global access of the epilogue is a full 128-byte line.  Everything that does not depend
@@ -353,7 +372,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !tmem_released) {
         if (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty_bar[acc]), 0));   // the leader's barrier
         else ptx::mbar_arrive(&tempty_bar[acc]);
       }
@@ -619,9 +638,10 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
   const int rpi = op->H * op->W;
   int cpg = 0;
   if (gnf) {
-    if (!op->gn_gamma || !op->gn_beta || !op->out16 || op->out32 || op->colstats || op->residual || op->rowscale ||
-        op->n_store != 0 || op->w_batch_stride != 0)
-      GEMM_FAIL("conv_gemm: the GroupNorm epilogue writes out16 only (no out32 / colstats / residual / rowscale / n_store / batched B)");
+    if (!op->gn_gamma || !op->gn_beta || !op->out16 || op->rowscale || op->n_store != 0 || op->w_batch_stride != 0)
+      GEMM_FAIL("conv_gemm: the GroupNorm epilogue needs gamma / beta / out16 and excludes rowscale / n_store / batched B");
+    if (!op->out32 && (op->colstats || op->residual))
+      GEMM_FAIL("conv_gemm: GroupNorm epilogue: colstats / residual belong to the dual mode (out32 + out16)");
     if (!gemm_gnf_supported(op->H, op->W, op->N, op->gn_groups))
       GEMM_FAIL("conv_gemm: GroupNorm epilogue not available for %dx%d, N=%d, groups=%d", op->H, op->W, op->N, op->gn_groups);
     cpg = op->N / op->gn_groups;
@@ -991,11 +1011,18 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
       if (cudaMalloc(&g_softmax_tmp, need) != cudaSuccess) GEMM_FAIL("conv_gemm ref: scratch alloc failed");
       g_softmax_tmp_bytes = need;
     }
-    r.epi = EPI_LINEAR; r.out32 = g_softmax_tmp; r.out16 = nullptr; r.ldo = op->N;
+    r.epi = EPI_LINEAR; r.out16 = nullptr;
+    const float* vsrc = op->out32;
+    int vld = op->ldo;
+    if (op->out32 == nullptr) { r.out32 = g_softmax_tmp; r.ldo = op->N; vsrc = g_softmax_tmp; vld = op->N; }   // out16 only
     dim3 grid0((unsigned)((M + 63) / 64), (unsigned)((op->N + 63) / 64));
     launch_k(conv_gemm_ref_kernel, dim3(grid0), dim3(256), 0, st, r);
-    launch_k(gnf_ref_kernel, dim3((unsigned)op->B, (unsigned)op->gn_groups), dim3(256), 0, st, (const float*)g_softmax_tmp, op->out16,
-             op->H * op->W, op->N, op->N / op->gn_groups, op->gn_gamma, op->gn_beta, op->gn_eps, op->gn_silu, op->ldo);
+    if (op->colstats != nullptr && op->out32 != nullptr) {
+      dim3 g2((unsigned)((M + 31) / 32), (unsigned)((op->N + 127) / 128));
+      launch_k(colstats_ref_kernel, dim3(g2), dim3(128), 0, st, op->out32, op->colstats, (int)M, op->N, op->ldo);
+    }
+    launch_k(gnf_ref_kernel, dim3((unsigned)op->B, (unsigned)op->gn_groups), dim3(256), 0, st, vsrc, op->out16,
+             op->H * op->W, vld, op->N / op->gn_groups, op->gn_gamma, op->gn_beta, op->gn_eps, op->gn_silu, op->ldo);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) GEMM_FAIL("conv_gemm_ref (GroupNorm epilogue) launch: %s", cudaGetErrorString(e));
     return 0;

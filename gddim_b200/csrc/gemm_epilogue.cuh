@@ -134,9 +134,11 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
+// GNP: additionally reduce the column sums to GroupNorm (segment, group) partials in shared memory (gnp_pstat, layout of
+// GnfCtx::pstat) -- pass 1 of the dual GroupNorm epilogue, see epi_tile_gnf_dual
 template <int BLOCK_N, int MT, bool RES_, bool O32_, bool O16_, bool STATS_, bool RSCALE_, bool FULL, bool GENERIC,
-          bool NARROW = false>
-__device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
+          bool NARROW = false, bool GNP = false>
+__device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx, float2* gnp_pstat = nullptr, int gnp_quad = 0) {
   constexpr int RS = SmemLayout<BLOCK_N, MT>::EPI_ROW_FLOATS;
   constexpr int NCH = BLOCK_N / 32;
   constexpr int NQ = MT * NCH;
@@ -144,8 +146,9 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
   // specialised variants know their features at compile time; the generic one tests the pointers
   const bool RES = GENERIC ? (p.residual != nullptr) : RES_;
   const bool O32 = GENERIC ? (p.out32 != nullptr) : O32_;
-  const bool O16 = GENERIC ? (p.out16 != nullptr) : O16_;
-  const bool STATS = GENERIC ? (p.colstats != nullptr) : STATS_;
+  const bool O16 = GNP ? false : (GENERIC ? (p.out16 != nullptr) : O16_);     // (GNP: out16 is the normalised output of pass 2)
+  const bool STATS = GNP || (GENERIC ? (p.colstats != nullptr) : STATS_);
+  const bool gnp_split = GNP && p.gn_rpi < 32;
   const bool RSCALE = GENERIC ? (p.rowscale != nullptr) : RSCALE_;
   const int lane = cx.lane;
   const int rsub = lane >> 3;
@@ -205,6 +208,7 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
     float4 bsum = lds128(bias_a + c0 * 4);
     bsum.x *= scale; bsum.y *= scale; bsum.z *= scale; bsum.w *= scale;
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gs0 = 0.f, gq0 = 0.f, gs1 = 0.f, gq1 = 0.f;            // GNP, 16-row images: rows 0..15 / 16..31 of the slab
     float* o32 = O32 ? p.out32 + mb * ldo + n0 : nullptr;
     __half* o16 = O16 ? p.out16 + mb * ldo + n0 : nullptr;
 #pragma unroll
@@ -228,6 +232,11 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
         if (STATS) {
           cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
           cq.x = fmaf(v.x, v.x, cq.x); cq.y = fmaf(v.y, v.y, cq.y); cq.z = fmaf(v.z, v.z, cq.z); cq.w = fmaf(v.w, v.w, cq.w);
+          if (GNP && gnp_split) {
+            const float s4 = (v.x + v.y) + (v.z + v.w);
+            if (i >= 4) { gs1 += s4; gq1 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, gq1)))); }
+            else { gs0 += s4; gq0 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, gq0)))); }
+          }
         }
         if (NARROW) {
           float* q = o32 + (long long)(i * 4) * ldo;
@@ -256,10 +265,29 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx) {
         cq.z += __shfl_xor_sync(0xffffffffu, cq.z, o); cq.w += __shfl_xor_sync(0xffffffffu, cq.w, o);
       }
       const long long mrow0 = cx.m0 + (long long)mi * BLOCK_M;
-      if (lane < 8 && (FULL || mrow0 < p.M)) {
+      if (lane < 8 && (FULL || mrow0 < p.M) && (!GNP || p.colstats != nullptr)) {
         float* cp = p.colstats + ((mrow0 >> 5) * 2) * ldo + n0;
         *reinterpret_cast<float4*>(cp) = cs;
         *reinterpret_cast<float4*>(cp + ldo) = cq;
+      }
+      if (GNP) {
+        // (segment, group) partials of this warp's 32-row slab: 4 columns per lane -> one group (cpg 4) or half of one
+        float s0 = (cs.x + cs.y) + (cs.z + cs.w), q0 = (cq.x + cq.y) + (cq.z + cq.w);
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gq0 += __shfl_xor_sync(0xffffffffu, gq0, o);
+          gs1 += __shfl_xor_sync(0xffffffffu, gs1, o); gq1 += __shfl_xor_sync(0xffffffffu, gq1, o);
+        }
+        if (p.gn_cpg == 8) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
+          gs0 += __shfl_xor_sync(0xffffffffu, gs0, 1); gq0 += __shfl_xor_sync(0xffffffffu, gq0, 1);
+          gs1 += __shfl_xor_sync(0xffffffffu, gs1, 1); gq1 += __shfl_xor_sync(0xffffffffu, gq1, 1);
+        }
+        if (lane < 8 && (p.gn_cpg == 4 || (lane & 1) == 0)) {
+          float2* dst = gnp_pstat + ((mi * 4 + gnp_quad) * 2) * GNF_GMAX + (c0 + c4) / p.gn_cpg;
+          dst[0] = gnp_split ? make_float2(gs0, gq0) : make_float2(s0, q0);
+          dst[GNF_GMAX] = make_float2(gs1, gq1);
+        }
       }
     }
     __syncwarp();
@@ -391,6 +419,72 @@ __device__ __forceinline__ void gnf_chunk_reduce(float (&a)[16], int lane, float
   }
 }
 
+// fold of the per-warp partials into per-(image, group) mean / rstd (with the cluster exchange when an image spans
+// several CTAs), bracketed by the two named barriers of the eight epilogue warps
+template <int BLOCK_N, int MT>
+__device__ __forceinline__ void gnf_fold(const GemmArgs& p, const GnfCtx& gx, int lane) {
+  constexpr int TR = MT * BLOCK_M;
+  const int cpg = p.gn_cpg, rpi = p.gn_rpi;
+  const bool split = rpi < 32;
+  const int G = BLOCK_N / cpg;
+  const bool stamp = gx.warp == 0 && lane == 0;
+  (void)stamp;
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 3);
+  // ---------------- fold: (image, group) -> mean, rstd ----------------
+  const int tid = gx.warp * 32 + lane;
+  const float inv_n = 1.0f / ((float)rpi * (float)cpg);
+  if (p.gn_xc > 1) {
+    // one image spans the gn_xc CTAs of this cluster: this CTA's tile is part of image 0.  Exchange: every CTA sends its
+    // G (sum, sumsq) pairs to all CTAs of the cluster with asynchronous remote stores that complete bytes on the
+    // receiver's mbarrier (armed below with the expected byte count); two barriers / buffers alternate by tile parity,
+    // so data of tile i + 1 can never be counted into the phase of tile i.
+    uint64_t* xb = gx.xbar + gx.xparity;
+    if (tid == 0) ptx::mbar_arrive_expect_tx(xb, (uint32_t)(p.gn_xc * G * 8));
+    if (tid < G) {
+      float S = 0.f, Q = 0.f;
+      for (int sl = 0; sl < MT * 4; ++sl) {
+        const float2 a = gx.pstat[(sl * 2) * GNF_GMAX + tid];
+        S += a.x; Q += a.y;
+      }
+      float2* mine = gx.xchg + (gx.xparity * 4 + gx.xrank) * GNF_GMAX + tid;
+      const uint32_t my_addr = ptx::smem_u32(mine), bar_addr = ptx::smem_u32(xb);
+      for (int rk = 0; rk < p.gn_xc; ++rk) st_async_f32x2(ptx::mapa(my_addr, rk), S, Q, ptx::mapa(bar_addr, rk));
+      ptx::mbar_wait(xb, gx.xphase);
+      S = 0.f; Q = 0.f;
+      for (int rk = 0; rk < p.gn_xc; ++rk) {
+        const float2 a = gx.xchg[(gx.xparity * 4 + rk) * GNF_GMAX + tid];
+        S += a.x; Q += a.y;
+      }
+      const float mean = S * inv_n;
+      const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+      gx.gstat[tid] = make_float2(mean, rsqrtf(var + p.gn_eps));
+    }
+  } else {
+    const int n_img = rpi >= TR ? 1 : TR / rpi;
+    for (int t = tid; t < n_img * G; t += EPI_WARPS * 32) {
+      const int img = t / G, g = t - img * G;
+      float S = 0.f, Q = 0.f;
+      if (split) {
+        const float2 a = gx.pstat[((img >> 1) * 2 + (img & 1)) * GNF_GMAX + g];
+        S = a.x; Q = a.y;
+      } else {
+        const int per = rpi >= TR ? MT * 4 : rpi / 32;      // 32-row slabs per image
+        for (int k = 0; k < per; ++k) {
+          const float2 a = gx.pstat[((img * per + k) * 2) * GNF_GMAX + g];
+          S += a.x; Q += a.y;
+        }
+      }
+      const float mean = S * inv_n;
+      const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
+      gx.gstat[img * GNF_GMAX + g] = make_float2(mean, rsqrtf(var + p.gn_eps));
+    }
+  }
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 4);
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+  GDDIM_STAMP(p, stamp, gx.tile_seq, 5);
+}
+
 template <int BLOCK_N, int MT>
 __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, const GnfCtx& gx) {
   constexpr int RS = 32;
@@ -448,60 +542,7 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
     }
   }
   GDDIM_STAMP(p, stamp, gx.tile_seq, 2);
-  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-  GDDIM_STAMP(p, stamp, gx.tile_seq, 3);
-  // ---------------- fold: (image, group) -> mean, rstd ----------------
-  const int tid = gx.warp * 32 + lane;
-  const float inv_n = 1.0f / ((float)rpi * (float)cpg);
-  if (p.gn_xc > 1) {
-    // one image spans the gn_xc CTAs of this cluster: this CTA's tile is part of image 0.  Exchange: every CTA sends its
-    // G (sum, sumsq) pairs to all CTAs of the cluster with asynchronous remote stores that complete bytes on the
-    // receiver's mbarrier (armed below with the expected byte count); two barriers / buffers alternate by tile parity,
-    // so data of tile i + 1 can never be counted into the phase of tile i.
-    uint64_t* xb = gx.xbar + gx.xparity;
-    if (tid == 0) ptx::mbar_arrive_expect_tx(xb, (uint32_t)(p.gn_xc * G * 8));
-    if (tid < G) {
-      float S = 0.f, Q = 0.f;
-      for (int sl = 0; sl < MT * 4; ++sl) {
-        const float2 a = gx.pstat[(sl * 2) * GNF_GMAX + tid];
-        S += a.x; Q += a.y;
-      }
-      float2* mine = gx.xchg + (gx.xparity * 4 + gx.xrank) * GNF_GMAX + tid;
-      const uint32_t my_addr = ptx::smem_u32(mine), bar_addr = ptx::smem_u32(xb);
-      for (int rk = 0; rk < p.gn_xc; ++rk) st_async_f32x2(ptx::mapa(my_addr, rk), S, Q, ptx::mapa(bar_addr, rk));
-      ptx::mbar_wait(xb, gx.xphase);
-      S = 0.f; Q = 0.f;
-      for (int rk = 0; rk < p.gn_xc; ++rk) {
-        const float2 a = gx.xchg[(gx.xparity * 4 + rk) * GNF_GMAX + tid];
-        S += a.x; Q += a.y;
-      }
-      const float mean = S * inv_n;
-      const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
-      gx.gstat[tid] = make_float2(mean, rsqrtf(var + p.gn_eps));
-    }
-  } else {
-    const int n_img = rpi >= TR ? 1 : TR / rpi;
-    for (int t = tid; t < n_img * G; t += EPI_WARPS * 32) {
-      const int img = t / G, g = t - img * G;
-      float S = 0.f, Q = 0.f;
-      if (split) {
-        const float2 a = gx.pstat[((img >> 1) * 2 + (img & 1)) * GNF_GMAX + g];
-        S = a.x; Q = a.y;
-      } else {
-        const int per = rpi >= TR ? MT * 4 : rpi / 32;      // 32-row slabs per image
-        for (int k = 0; k < per; ++k) {
-          const float2 a = gx.pstat[((img * per + k) * 2) * GNF_GMAX + g];
-          S += a.x; Q += a.y;
-        }
-      }
-      const float mean = S * inv_n;
-      const float var = fmaxf(Q * inv_n - mean * mean, 0.f);
-      gx.gstat[img * GNF_GMAX + g] = make_float2(mean, rsqrtf(var + p.gn_eps));
-    }
-  }
-  GDDIM_STAMP(p, stamp, gx.tile_seq, 4);
-  asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-  GDDIM_STAMP(p, stamp, gx.tile_seq, 5);
+  gnf_fold<BLOCK_N, MT>(p, gx, lane);
   // ---------------- pass 2: normalise, activate, store fp16 ----------------
   const long long ldo = p.ldo;
   if (cx.group < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (cx.group / NCH) * BLOCK_N + (cx.group % NCH) * 32, r);
@@ -556,6 +597,65 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
   }
   GDDIM_STAMP(p, stamp, gx.tile_seq, 6);
   (void)mtile;
+}
+
+// Dual GroupNorm epilogue: the convolution ALSO keeps its plain result.  out32 (+ colstats) = the linear epilogue value v
+// (bias, residual, scale: the (x + h)/sqrt(2) trunk of layerspp.py:224-227) and out16 = act(GroupNorm(v)) with the
+// parameters of the NEXT block's GroupNorm_0 (layerspp.py:196) -- the consumer's normalisation pass disappears.
+// Pass 1 is the ordinary linear epilogue (epi_tile with the GNP hook); the accumulator is not needed afterwards, pass 2
+// re-reads v from out32: every lane reads back exactly the elements it stored itself (program order, L2 hits).
+template <int BLOCK_N, int MT>
+__device__ __forceinline__ void epi_tile_gnf_dual_pass2(const EpiCtx<BLOCK_N, MT>& cx, const GnfCtx& gx) {
+  constexpr int NCH = BLOCK_N / 32;
+  constexpr int NQ = MT * NCH;
+  constexpr int TR = MT * BLOCK_M;
+  const GemmArgs& p = cx.p;
+  const int lane = cx.lane;
+  const int rsub = lane >> 3;
+  const int c4 = (lane & 7) * 4;
+  const int quad = gx.warp & 3;
+  const int cpg = p.gn_cpg, rpi = p.gn_rpi;
+  const bool split = rpi < 32;
+  const long long ldo = p.ldo;
+#pragma unroll 1
+  for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
+    const int mi = q / NCH, c0 = (q % NCH) * 32;
+    const long long mb = cx.m0 + (long long)mi * BLOCK_M + rsub;
+    const int n0 = cx.n_tile0 + c0 + c4;
+    const float* src = p.out32 + mb * ldo + n0;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      v[i] = (mb + i * 4 < p.M) ? __ldcg(reinterpret_cast<const float4*>(src + (long long)(i * 4) * ldo)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 g4 = *reinterpret_cast<const float4*>(gx.gam + c0 + c4);
+    const float4 b4 = *reinterpret_cast<const float4*>(gx.bet + c0 + c4);
+    const int gi = (c0 + c4) / cpg;
+    const int row_off = mi * BLOCK_M + quad * 32;
+    const int img0 = (p.gn_xc > 1 || rpi >= TR) ? 0 : row_off / rpi;
+    const float2 st0 = gx.gstat[img0 * GNF_GMAX + gi];
+    const float2 st1 = split ? gx.gstat[(img0 + 1) * GNF_GMAX + gi] : st0;
+    float4 a0, o0, a1, o1;
+    a0.x = st0.y * g4.x; a0.y = st0.y * g4.y; a0.z = st0.y * g4.z; a0.w = st0.y * g4.w;
+    o0.x = b4.x - st0.x * a0.x; o0.y = b4.y - st0.x * a0.y; o0.z = b4.z - st0.x * a0.z; o0.w = b4.w - st0.x * a0.w;
+    a1.x = st1.y * g4.x; a1.y = st1.y * g4.y; a1.z = st1.y * g4.z; a1.w = st1.y * g4.w;
+    o1.x = b4.x - st1.x * a1.x; o1.y = b4.y - st1.x * a1.y; o1.z = b4.z - st1.x * a1.z; o1.w = b4.w - st1.x * a1.w;
+    __half* o16 = p.out16 + mb * ldo + n0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 aa = (i >= 4) ? a1 : a0, oo = (i >= 4) ? o1 : o0;
+      float4 y;
+      y.x = fmaf(v[i].x, aa.x, oo.x); y.y = fmaf(v[i].y, aa.y, oo.y); y.z = fmaf(v[i].z, aa.z, oo.z); y.w = fmaf(v[i].w, aa.w, oo.w);
+      if (p.gn_silu) { y.x = gnf_silu(y.x); y.y = gnf_silu(y.y); y.z = gnf_silu(y.z); y.w = gnf_silu(y.w); }
+      if (mb + i * 4 < p.M) {
+        __half2 h0 = __floats2half2_rn(y.x, y.y);
+        __half2 h1 = __floats2half2_rn(y.z, y.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(o16 + (long long)(i * 4) * ldo) = pk;
+      }
+    }
+  }
 }
 
 }  // namespace gddim

@@ -51,8 +51,30 @@ UNet::~UNet() {
 }
 
 // ---- arenas -------------------------------------------------------------------------------------------
+void UNet::flush_pending() {
+  if (pending_free_.empty()) return;
+  last_flush_at_ = ops_.size();
+  for (auto& pf : pending_free_) {
+    size_t bytes = pf.second;
+    size_t off = (char*)pf.first - arena_;
+    size_t i = 0;
+    while (i < free_.size() && free_[i].first < off) ++i;
+    free_.insert(free_.begin() + i, {off, bytes});
+    if (i + 1 < free_.size() && free_[i].first + free_[i].second == free_[i + 1].first) {
+      free_[i].second += free_[i + 1].second;
+      free_.erase(free_.begin() + i + 1);
+    }
+    if (i > 0 && free_[i - 1].first + free_[i - 1].second == free_[i].first) {
+      free_[i - 1].second += free_[i].second;
+      free_.erase(free_.begin() + i);
+    }
+  }
+  pending_free_.clear();
+}
+
 void* UNet::a_alloc(size_t bytes) {
   bytes = align_up(bytes, 1024);
+  if (!hold_pending_) flush_pending();
   for (size_t i = 0; i < free_.size(); ++i) {
     if (free_[i].second >= bytes) {
       const size_t off = free_[i].first;
@@ -67,19 +89,7 @@ void* UNet::a_alloc(size_t bytes) {
 }
 
 void UNet::a_free(void* p, size_t bytes) {
-  bytes = align_up(bytes, 1024);
-  size_t off = (char*)p - arena_;
-  size_t i = 0;
-  while (i < free_.size() && free_[i].first < off) ++i;
-  free_.insert(free_.begin() + i, {off, bytes});
-  if (i + 1 < free_.size() && free_[i].first + free_[i].second == free_[i + 1].first) {
-    free_[i].second += free_[i + 1].second;
-    free_.erase(free_.begin() + i + 1);
-  }
-  if (i > 0 && free_[i - 1].first + free_[i - 1].second == free_[i].first) {
-    free_[i - 1].second += free_[i].second;
-    free_.erase(free_.begin() + i);
-  }
+  pending_free_.push_back({p, align_up(bytes, 1024)});      // see flush_pending()
 }
 
 void* UNet::w_alloc(size_t bytes) {
@@ -248,10 +258,37 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
   const float out_scale = cfg_.skip_rescale ? (float)(1.0 / std::sqrt(2.0)) : 1.f;
 
   auto gn0 = gn_params(s, Cin);
+  // GroupNorm_0 + swish of THIS block applied by the epilogue of the GEMM that produced the input (dual GroupNorm
+  // epilogue, conv_gemm.cu): possible when that GEMM is the op pushed last (nothing ran in between), the input is a single
+  // un-resampled tensor consumed without a raw shortcut copy, and the geometry qualifies.  The producer then writes its
+  // fp32 result (trunk / residual / skip) AND this block's fp16 A operand; the separate pass disappears.
+  static const bool no_gnf0 = [] { const char* e = getenv("GDDIM_NO_GNF0"); const char* e1 = getenv("GDDIM_NO_GNF");
+                                   return (e && e[0] == '1') || (e1 && e1[0] == '1'); }();
+  const int groups0 = std::min(Cin / 4, 32);
+  bool fuse0 = false;
+  if (!no_gnf0 && in2 == nullptr && rs == RS_NONE && !need_sc && in1.prod_op >= 0 && in1.prod_op == (int)ops_.size() - 1 &&
+      last_flush_at_ < ops_.size() && gemm_gnf_supported(H, W, Cin, groups0)) {
+    const Op& po = ops_[in1.prod_op];
+    const GemmOp& pg = po.gemm;
+    fuse0 = po.kind == OP_GEMM && pg.epi == EPI_LINEAR && pg.out32 == in1.p && pg.out16 == nullptr && pg.rowscale == nullptr &&
+            pg.n_store == 0 && pg.w_batch_stride == 0 && pg.N == Cin && pg.ldo == Cin && pg.H == H && pg.W == W &&
+            !po.out_is_external;
+  }
+  hold_pending_ = fuse0;                 // a1 becomes an output of the producer: it must not reuse what that op still reads
   T16 a1 = new16(Cin, Ho, Wo);
+  hold_pending_ = false;
   T16 x16; x16.p = nullptr;
   if (need_sc) x16 = new16(Cin, Ho, Wo);
-  add_norm(in1, in2, gn0.first, gn0.second, true, rs, &a1, need_sc ? &x16 : nullptr, s.prefix + "gn0");
+  if (fuse0) {
+    Op& po = ops_[in1.prod_op];
+    GemmOp& pg = po.gemm;
+    pg.epi = EPI_GNF;
+    pg.out16 = a1.p;
+    pg.gn_gamma = gn0.first; pg.gn_beta = gn0.second; pg.gn_eps = 1e-6f; pg.gn_groups = groups0; pg.gn_silu = 1;
+    po.tag += "+gn0";
+  } else {
+    add_norm(in1, in2, gn0.first, gn0.second, true, rs, &a1, need_sc ? &x16 : nullptr, s.prefix + "gn0");
+  }
 
   // conv1 (Conv_0) + Dense_0(act(temb))
   Scope c0 = s.child("Conv");
@@ -356,6 +393,7 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     g.scale = out_scale;
     g.out32 = out.p; g.ldo = out_ch;
     g.colstats = out.stats; out.stats_valid = out.stats != nullptr;
+    out.prod_op = (int)ops_.size();
     ops_.push_back(op);
   }
   rel(a2);
@@ -569,6 +607,9 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
 int UNet::walk() {
   ops_.clear();
   free_.clear();
+  pending_free_.clear();
+  hold_pending_ = false;
+  last_flush_at_ = 0;
   arena_top_ = 0;
   weight_top_ = 0;
   temb_total_ = 0;
@@ -658,6 +699,7 @@ int UNet::walk() {
       g.w = wp; g.N = nf; g.w_ld = kpad; g.bias = bp;
       g.out32 = h0.p; g.ldo = nf;
       g.colstats = h0.stats; h0.stats_valid = h0.stats != nullptr;
+      h0.prod_op = (int)ops_.size();
       ops_.push_back(op);
     }
     rel(a16);
@@ -718,6 +760,7 @@ int UNet::walk() {
           g.residual = h.p; g.scale = m.skip_rescale ? (float)(1.0 / std::sqrt(2.0)) : 1.f;
           g.out32 = np.p; g.ldo = cout;
           g.colstats = np.stats; np.stats_valid = np.stats != nullptr;
+          np.prod_op = (int)ops_.size();
           ops_.push_back(op);
         }
         rel(a16);

@@ -75,7 +75,9 @@ class UNet {
   double profile_norm_bytes() const;      // algorithmic HBM bytes of all GroupNorm ops over the profiled forwards
 
  private:
-  struct T32 { float* p; int C, H, W; size_t bytes; float* stats; size_t stats_bytes; bool stats_valid; };
+  // prod_op: index in ops_ of the GEMM whose linear epilogue wrote this tensor (-1: other producers) -- lets the next
+  // block attach its GroupNorm_0 to that epilogue (dual GroupNorm epilogue, resblock())
+  struct T32 { float* p; int C, H, W; size_t bytes; float* stats; size_t stats_bytes; bool stats_valid; int prod_op = -1; };
   struct T16 { __half* p; int C, H, W; size_t bytes; };
   struct Scope;
   gddim_model_cfg cfg_;
@@ -86,6 +88,12 @@ class UNet {
   std::vector<ParamSpec> specs_;
   std::map<std::string, std::vector<float>> host_params_;
   std::vector<Op> ops_;
+  // buffers released since the last allocation: returned to the free list by the next ordinary allocation, but kept out of
+  // it for an allocation that becomes an extra OUTPUT of the op pushed last (it must not alias that op's inputs)
+  std::vector<std::pair<void*, size_t>> pending_free_;
+  bool hold_pending_ = false;
+  size_t last_flush_at_ = 0;            // ops_.size() when released buffers last went back to the free list
+  void flush_pending();
   long long launches_ = 0;
   bool profile_ = false;
   std::vector<cudaEvent_t> prof_ev_;

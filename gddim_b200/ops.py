@@ -34,7 +34,8 @@ def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residu
               out_fp32=True, out_fp16=False, impl=0, force_block_n=0, force_m_sub=0, force_cta_pairs=0, epi=0, n_store=0, a0_coff=0, a0_c=None, w_ld=None,
               w_koff=0, w_batch_stride=0, w_rows_per_batch=0, reverse=0, gn=None):
   """a0 (and a1): fp16 [B,H,W,C]; w: fp16 K-major.  Returns (out32 or None, out16 or None[, row_out]).
-  gn = (gamma, beta, groups, silu[, eps]): epi 2, the GroupNorm (+ swish) of the output applied by the epilogue -> out16."""
+  gn = (gamma, beta, groups, silu[, eps[, dual]]): epi 2, the GroupNorm (+ swish) of the output applied by the epilogue
+  -> out16; dual = True also returns the un-normalised fp32 result (bias / residual / scale as usual) in out32."""
   import torch
   _lib.require_cuda("conv_gemm")
   B, H, W, C0 = a0.shape
@@ -48,11 +49,12 @@ def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residu
   d.bias, d.bias2, d.residual, d.rowscale = _ptr(bias), _ptr(bias2), _ptr(residual), _ptr(rowscale)
   d.scale = scale
   No = n_store or N
+  gn_dual = gn is not None and len(gn) > 5 and bool(gn[5])     # dual mode: fp32 linear result AND its normalised fp16 copy
   if gn is not None:
-    epi, out_fp32, out_fp16 = 2, False, True
+    epi, out_fp32, out_fp16 = 2, gn_dual, True
     d.gn_gamma, d.gn_beta, d.gn_groups, d.gn_silu = gn[0].data_ptr(), gn[1].data_ptr(), int(gn[2]), int(bool(gn[3]))
     d.gn_eps = float(gn[4]) if len(gn) > 4 else 1e-6
-  o32 = torch.empty((B, H, W, No), dtype=torch.float32, device="cuda") if (out_fp32 and epi == 0) else None
+  o32 = torch.empty((B, H, W, No), dtype=torch.float32, device="cuda") if (out_fp32 and (epi == 0 or gn_dual)) else None
   o16 = torch.empty((B, H, W, N), dtype=torch.float16, device="cuda") if (out_fp16 or epi == 1) else None
   row = torch.empty((B, H, W), dtype=torch.float32, device="cuda") if epi == 1 else None
   d.out32, d.out16, d.row_out, d.ldo = _ptr(o32), _ptr(o16), _ptr(row), No

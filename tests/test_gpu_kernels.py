@@ -441,3 +441,46 @@ def test_groupnorm_epilogue_is_deterministic_and_reverse_invariant():
   outs = [ops.conv_gemm(a, w, N, gn=(gamma, beta, 32, True), reverse=r)[1] for r in (0, 1, 0)]
   torch.cuda.synchronize()
   assert torch.equal(outs[0], outs[2]) and torch.equal(outs[0], outs[1])
+
+
+DUAL_CASES = [  # B, H, W, C (= Cin = N), residual, force_block_n, force_m_sub, force_pairs
+    (2, 32, 32, 128, True, 0, 0, 0),        # 4-CTA cluster, halo tiles
+    (3, 16, 16, 256, True, 0, 0, 0),        # 2-CTA cluster
+    (4, 16, 16, 256, True, 256, 1, 2),      # cta_group::2 pair = one image
+    (5, 8, 8, 256, True, 0, 0, 0),          # two images per tile, ragged
+    (3, 4, 4, 256, False, 0, 0, 0),         # 16-row images, no residual (shortcut-conv blocks, pyramid)
+    (9, 4, 4, 128, True, 128, 2, 0),
+    (38, 32, 32, 128, True, 0, 0, 0),
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
+@pytest.mark.parametrize("case", DUAL_CASES, ids=[f"b{c[0]}_{c[1]}x{c[2]}_{c[3]}{'_res' if c[4] else ''}_bn{c[5]}x{c[6]}_cg{c[7]}" for c in DUAL_CASES])
+def test_conv_with_dual_groupnorm_epilogue(impl, case):
+  """epi = 2 with out32: the conv2 of a ResBlock keeps its trunk result (x + h)/sqrt(2) in fp32 (+ column statistics for
+  other consumers) and ALSO emits act(GroupNorm_0(.)) of the next block (layerspp.py:196) as fp16."""
+  B, H, W, Cc, with_res, bn, ms, pairs = case
+  if impl == 1 and (bn or B > 9):
+    pytest.skip("tile variants do not exist on the CUDA-core path")
+  g = torch.Generator().manual_seed(B * 17 + H)
+  a = torch.randn(B, H, W, Cc, generator=g).to(torch.float16)
+  k = (torch.randn(3, 3, Cc, Cc, generator=g) / np.sqrt(9 * Cc)).numpy()
+  bias = torch.randn(Cc, generator=g)
+  res = 2.0 * torch.randn(B, H, W, Cc, generator=g) if with_res else None
+  gamma, beta = 1 + 0.2 * torch.randn(Cc, generator=g), 0.3 * torch.randn(Cc, generator=g)
+  groups = min(Cc // 4, 32)
+  sc = float(1 / np.sqrt(2.0))
+  v = _conv_ref(a, k, 9) + bias.double()
+  if with_res:
+    v = v + res.double()
+  v = v * sc
+  want = on.swish(F.group_norm(v.permute(0, 3, 1, 2), groups, gamma.double(), beta.double(), eps=1e-6)).permute(0, 2, 3, 1)
+  o32, o16 = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k), Cc, bias=bias.cuda(), residual=None if res is None else res.cuda(),
+                           scale=sc, impl=impl, force_block_n=bn, force_m_sub=ms, force_cta_pairs=pairs,
+                           gn=(gamma.cuda(), beta.cuda(), groups, True, 1e-6, True))
+  torch.cuda.synchronize()
+  e32, e16 = rel_l2(o32.cpu().numpy(), v.numpy()), rel_l2(o16.float().cpu().numpy(), want.numpy())
+  print(f"dual gnf {case} impl={impl}: out32 {e32:.2e} out16 {e16:.2e}")
+  assert e32 < 2e-5 and e16 < 6e-4
+  per = [rel_l2(o16[b].float().cpu().numpy(), want[b].numpy()) for b in range(B)]
+  assert max(per) < 8e-4, per
