@@ -49,7 +49,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   static_assert(!HALO || EPI != EPI_SOFTMAX, "halo tiles: linear / GNF epilogue only");
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;     // rank 0 = leader: issues the MMAs
   // GNF with images spanning several CTAs: the launch is a cluster of gn_xc CTAs (CG == 2: the MMA pair itself)
-  const bool clustered = CG == 2 || (GNF && p.gn_xc > 1);
+  const bool clustered = CG == 2 || (GNF && p.gn_xc > 1 && p.gn_xg == nullptr);
   constexpr int MAX_STAGES = 8;
   const int STAGES = HALO ? p.stages : L::STAGES;
   const int stage_bytes = HALO ? p.stage_bytes : L::STAGE_BYTES;
@@ -608,7 +608,7 @@ static int gnf_cluster(int rpi, int tr, int bn, int N, int cpg) {
 int gemm_gnf_supported(int H, int W, int N, int groups) {
   if (groups <= 0 || N % groups != 0 || N % 32 != 0 || !is_pow2(H) || !is_pow2(W)) return 0;
   const int cpg = N / groups, rpi = H * W;
-  if (cpg != 4 && cpg != 8) return 0;
+  if (cpg != 4 && cpg != 8 && cpg != 16) return 0;
   for (int bn = 256; bn >= 32; bn >>= 1) {
     if (N % bn != 0) continue;
     for (int ms = 1; ms <= 2; ++ms) {
@@ -708,6 +708,10 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     const bool plain = op->epi != EPI_SOFTMAX && op->w_batch_stride == 0 && op->n_store == 0;
     // (GroupNorm epilogue: a pair must be exactly one image; images spanning 4 CTAs run as clusters of single-CTA MMAs)
     const bool can_pair = plain && bn == 256 && op->m_sub == 1 && (!gnf || op->gn_xc == 2);
+    // images spanning four CTAs: two cta_group::2 pairs with the statistics exchanged through global memory (all SMs
+    // busy) when the halo pair kernel applies, else a cluster of four single-CTA MMAs (DSMEM exchange, 132 SMs)
+    static int gnf_pairs4 = -1;              // GDDIM_GNF_PAIRS4=0: A/B switch back to 4-CTA clusters
+    if (gnf_pairs4 < 0) { const char* e = getenv("GDDIM_GNF_PAIRS4"); gnf_pairs4 = (e && e[0] == '0') ? 0 : 1; }
     // halo tiles: 3x3 convolution whose CTA tile is a block of whole image rows of ONE image
     const int tile_px = BLOCK_M * op->m_sub;
     // (measured: 256-row N = 128 tiles 1.06 -> 1.29 PFLOP/s; N = 256 tiles lose, their ring shrinks to two slots)
@@ -720,10 +724,10 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     op->cg = (!no_pairs && shape_ok && can_pair) ? 2 : 1;
     if (halo_ok && bn == 256 && op->m_tiles >= 2 && !no_pairs) op->cg = 2;   // three 32 KB weight tiles per slot do not fit
     if (halo_ok && bn == 128 && op->m_tiles >= 2 && !no_pairs) op->cg = halo128_cg == 2 ? 2 : 1;
-    if (gnf && op->gn_xc != 2) op->cg = 1;
+    if (gnf && op->gn_xc != 2 && !(op->gn_xc == 4 && gnf_pairs4 && halo_ok && bn == 128 && op->cg == 2)) op->cg = 1;
     if (force_cg == 1) op->cg = 1;
     if (force_cg == 2) {
-      if ((!can_pair && !halo_ok) || (gnf && op->gn_xc != 2))
+      if ((!can_pair && !halo_ok) || (gnf && op->gn_xc != 2 && !(op->gn_xc == 4 && halo_ok && bn == 128)))
         GEMM_FAIL("conv_gemm: CTA pairs need block_n 256 (or halo tiles), shared weights, linear epilogue");
       op->cg = 2;
     }
@@ -800,7 +804,13 @@ static int launch_umma(const GemmOp* op, const GemmArgs& a, cudaStream_t st) {
   }
   if (CG == 2) {
     const int units = ((a.m_tiles + 1) / 2) * a.n_tiles;
-    const int pairs = units < num_sms_eff / 2 ? units : num_sms_eff / 2;
+    int pairs = units < num_sms_eff / 2 ? units : num_sms_eff / 2;
+    if (EPI == EPI_GNF && a.gn_xg != nullptr) {
+      // the two pairs of an image must work on it in the same round: an even number of pairs, whole images
+      if (units % 2 != 0) GEMM_FAIL("conv_gemm: GroupNorm epilogue needs whole images (%d pair tiles)", units);
+      pairs &= ~1;
+      if (pairs < 2) GEMM_FAIL("conv_gemm: GroupNorm epilogue over two pairs needs at least four SMs");
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem_total; cfg.stream = st;
     cudaLaunchAttribute at[2];
@@ -941,6 +951,21 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
       a.gn_gamma = op->gn_gamma; a.gn_beta = op->gn_beta; a.gn_eps = op->gn_eps; a.gn_cpg = op->N / op->gn_groups;
       a.gn_silu = op->gn_silu; a.gn_rpi = op->H * op->W; a.gn_xc = op->gn_xc;
       if (op->halo) {
+        if (op->block_n == 128 && op->m_sub == 2 && op->cg == 2) {
+          // two pairs per image, exchange through global memory: [4-CTA group][round parity][rank][group][2] tagged words
+          static unsigned long long* xg[64] = {};
+          const int dev = DeviceOnce::dev() & 63;
+          if (!xg[dev]) {
+            const size_t bytes = (size_t)(device_sm_count() / 4 + 1) * 2 * 4 * GNF_GMAX * 2 * sizeof(unsigned long long);
+            if (cudaMalloc(&xg[dev], bytes) != cudaSuccess) GEMM_FAIL("conv_gemm: GroupNorm exchange buffer allocation failed");
+            cudaMemset(xg[dev], 0, bytes);
+          }
+          a.gn_xg = xg[dev];
+          // tags restart at 1 in every launch (a captured graph replays the same arguments): clear the words first
+          const size_t used = (size_t)(device_sm_count() / 4 + 1) * 2 * 4 * GNF_GMAX * 2 * sizeof(unsigned long long);
+          if (cudaMemsetAsync(xg[dev], 0, used, st) != cudaSuccess) GEMM_FAIL("conv_gemm: clearing the GroupNorm exchange buffer failed");
+          return launch_umma<128, EPI_GNF, 2, 2, true>(op, a, st);
+        }
         if (op->block_n == 128 && op->m_sub == 2 && op->cg == 1) return launch_umma<128, EPI_GNF, 2, 1, true>(op, a, st);
         GEMM_FAIL("conv_gemm: no GroupNorm-epilogue halo kernel for block_n %d, m_sub %d, cg %d", op->block_n, op->m_sub, op->cg);
       }

@@ -58,10 +58,13 @@ struct GemmArgs {
   const float* gn_gamma;   // [N]
   const float* gn_beta;    // [N]
   float gn_eps;
-  int gn_cpg;              // channels per group (4 or 8)
+  int gn_cpg;              // channels per group (4, 8 or 16)
   int gn_silu;
   int gn_rpi;              // rows (pixels) per image = H * W
-  int gn_xc;               // CTAs an image spans = cluster size of the launch (1, 2 or 4)
+  int gn_xc;               // CTAs an image spans (1, 2 or 4)
+  // gn_xg != null: the gn_xc CTAs of an image are `gn_xc` CONSECUTIVE CTAs of the grid (not one cluster) and exchange
+  // their statistics through this global buffer of tagged 64-bit words (see gnf_fold); null: one cluster, DSMEM exchange
+  unsigned long long* gn_xg;
   long long* dbg_clk;   // GDDIM_ABLATE builds: clock64 timeline of CTA 0 ([tile < 16][16 stamps]), else null
   int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };
@@ -278,12 +281,12 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx, float2* 
           gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gq0 += __shfl_xor_sync(0xffffffffu, gq0, o);
           gs1 += __shfl_xor_sync(0xffffffffu, gs1, o); gq1 += __shfl_xor_sync(0xffffffffu, gq1, o);
         }
-        if (p.gn_cpg == 8) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
-          gs0 += __shfl_xor_sync(0xffffffffu, gs0, 1); gq0 += __shfl_xor_sync(0xffffffffu, gq0, 1);
-          gs1 += __shfl_xor_sync(0xffffffffu, gs1, 1); gq1 += __shfl_xor_sync(0xffffffffu, gq1, 1);
+        for (int o = 1; o * 4 < p.gn_cpg; o <<= 1) {          // lanes of one group: 2 (cpg 8) or 4 (cpg 16)
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+          gs0 += __shfl_xor_sync(0xffffffffu, gs0, o); gq0 += __shfl_xor_sync(0xffffffffu, gq0, o);
+          gs1 += __shfl_xor_sync(0xffffffffu, gs1, o); gq1 += __shfl_xor_sync(0xffffffffu, gq1, o);
         }
-        if (lane < 8 && (p.gn_cpg == 4 || (lane & 1) == 0)) {
+        if (lane < 8 && ((lane * 4) % p.gn_cpg) == 0) {
           float2* dst = gnp_pstat + ((mi * 4 + gnp_quad) * 2) * GNF_GMAX + (c0 + c4) / p.gn_cpg;
           dst[0] = gnp_split ? make_float2(gs0, gq0) : make_float2(s0, q0);
           dst[GNF_GMAX] = make_float2(gs1, gq1);
@@ -343,6 +346,19 @@ __device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_
       : "memory");
 }
 __device__ __forceinline__ float gnf_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// swish of four values with ONE reciprocal: 1/d_i = (1 / (d0 d1 d2 d3)) * (product of the other three).  The epilogue is
+// bound by the special-function pipe (16 results per clock and SM: ex2 + rcp per element = 4096 cycles per 256 x 128
+// tile); sharing the reciprocal cuts it to 1.25 per element.  x is clamped at -20 (swish(-20) = -4e-8 rounds to zero in
+// fp16) so that the product of four (1 + e^-x) <= 4.9e8 stays far below the fp32 range.
+__device__ __forceinline__ void gnf_silu4(float4& v) {
+  const float x0 = fmaxf(v.x, -20.f), x1 = fmaxf(v.y, -20.f), x2 = fmaxf(v.z, -20.f), x3 = fmaxf(v.w, -20.f);
+  const float d0 = 1.0f + __expf(-x0), d1 = 1.0f + __expf(-x1), d2 = 1.0f + __expf(-x2), d3 = 1.0f + __expf(-x3);
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+  const float r01 = r * p23, r23 = r * p01;
+  v.x = x0 * (r01 * d1); v.y = x1 * (r01 * d0); v.z = x2 * (r23 * d3); v.w = x3 * (r23 * d2);
+}
 // asynchronous remote store that completes `8` bytes on the destination CTA's mbarrier (no fence on the sender side:
 // a release at cluster scope would first drain this thread's outstanding global stores, measured ~5 k cycles per tile)
 __device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar) {
@@ -366,6 +382,13 @@ __device__ __forceinline__ void gnf_halve(float (&a)[16], int mask, int lane) {
 template <int NV, bool HALF>
 __device__ __forceinline__ float gnf_reduce(float (&a)[16], int lane) {
   // halving steps use the highest lane bits; the remaining low bits are folded with plain butterfly adds
+  if (NV == 4) {                                  // 16 channels per group: two groups per 32-column chunk
+    if (HALF) { gnf_halve<4>(a, 8, lane); gnf_halve<2>(a, 4, lane); }
+    else { gnf_halve<4>(a, 16, lane); gnf_halve<2>(a, 8, lane); a[0] += __shfl_xor_sync(0xffffffffu, a[0], 4); }
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+    return a[0];
+  }
   if (HALF) {
     if (NV == 16) { gnf_halve<16>(a, 8, lane); gnf_halve<8>(a, 4, lane); gnf_halve<4>(a, 2, lane); gnf_halve<2>(a, 1, lane); }
     else { gnf_halve<8>(a, 8, lane); gnf_halve<4>(a, 4, lane); gnf_halve<2>(a, 2, lane); a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1); }
@@ -380,6 +403,10 @@ __device__ __forceinline__ float gnf_reduce(float (&a)[16], int lane) {
 // which value a lane holds after gnf_reduce, and whether it is the lane that publishes it
 template <int NV, bool HALF>
 __device__ __forceinline__ int gnf_holder_index(int lane, bool* writer) {
+  if (NV == 4) {
+    if (HALF) { *writer = (lane & 3) == 0; return (lane >> 2) & 3; }
+    *writer = (lane & 7) == 0; return (lane >> 3) & 3;
+  }
   if (HALF) {
     if (NV == 16) { *writer = true; return lane & 15; }
     *writer = (lane & 1) == 0; return (lane >> 1) & 7;
@@ -434,11 +461,53 @@ __device__ __forceinline__ void gnf_fold(const GemmArgs& p, const GnfCtx& gx, in
   // ---------------- fold: (image, group) -> mean, rstd ----------------
   const int tid = gx.warp * 32 + lane;
   const float inv_n = 1.0f / ((float)rpi * (float)cpg);
-  if (p.gn_xc > 1) {
-    // one image spans the gn_xc CTAs of this cluster: this CTA's tile is part of image 0.  Exchange: every CTA sends its
-    // G (sum, sumsq) pairs to all CTAs of the cluster with asynchronous remote stores that complete bytes on the
-    // receiver's mbarrier (armed below with the expected byte count); two barriers / buffers alternate by tile parity,
-    // so data of tile i + 1 can never be counted into the phase of tile i.
+  if (p.gn_xc > 1 && p.gn_xg != nullptr) {
+    // one image spans gn_xc consecutive CTAs of the grid that are NOT one cluster (32x32 images on cta_group::2 pairs: two
+    // pairs per image, all 148 SMs busy -- clusters of four only fit 132).  Exchange through global memory without any
+    // fence: every (sum, sumsq) travels in two 64-bit words {value, sequence tag} written with relaxed gpu-scope stores
+    // (64-bit accesses are single-copy atomic), the readers poll until the tag of this round shows up.  Two buffers
+    // alternate by round; nobody can be two rounds ahead (round r + 1 needs every peer's data of round r + 1, which a
+    // peer only writes after it has read round r).  All CTAs of the persistent grid are co-resident (one per SM).
+    if (tid < G) {
+      float S = 0.f, Q = 0.f;
+      for (int sl = 0; sl < MT * 4; ++sl) {
+        const float2 a = gx.pstat[(sl * 2) * GNF_GMAX + tid];
+        S += a.x; Q += a.y;
+      }
+      const unsigned int seq = (unsigned int)gx.tile_seq + 1u;
+      const int xc = p.gn_xc;
+      const int grp = blockIdx.x / xc, me = blockIdx.x % xc;
+      unsigned long long* base = p.gn_xg + ((size_t)(grp * 2 + (int)gx.xparity) * 4) * (GNF_GMAX * 2);
+      unsigned long long* mine = base + (size_t)me * (GNF_GMAX * 2) + tid * 2;
+      const unsigned long long w0 = ((unsigned long long)seq << 32) | __float_as_uint(S);
+      const unsigned long long w1 = ((unsigned long long)seq << 32) | __float_as_uint(Q);
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mine), "l"(w0) : "memory");
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(mine + 1), "l"(w1) : "memory");
+      float St = 0.f, Qt = 0.f;
+      for (int rk = 0; rk < xc; ++rk) {
+        float s_r = S, q_r = Q;
+        if (rk != me) {
+          const unsigned long long* src = base + (size_t)rk * (GNF_GMAX * 2) + tid * 2;
+          unsigned long long a0, a1;
+          unsigned int spins = 0;
+          do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a0) : "l"(src) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a1) : "l"(src + 1) : "memory");
+            if (++spins > (1u << 26)) __trap();          // a peer CTA never showed up: fail loudly instead of hanging
+          } while ((unsigned int)(a0 >> 32) != seq || (unsigned int)(a1 >> 32) != seq);
+          s_r = __uint_as_float((unsigned int)a0);
+          q_r = __uint_as_float((unsigned int)a1);
+        }
+        St += s_r; Qt += q_r;
+      }
+      const float mean = St * inv_n;
+      const float var = fmaxf(Qt * inv_n - mean * mean, 0.f);
+      gx.gstat[tid] = make_float2(mean, rsqrtf(var + p.gn_eps));
+    }
+  } else if (p.gn_xc > 1) {
+    // one image spans the gn_xc CTAs of this cluster: every CTA sends its G (sum, sumsq) pairs to all CTAs of the cluster
+    // with asynchronous remote stores that complete bytes on the receiver's mbarrier (armed with the expected byte count);
+    // two barriers / buffers alternate by tile parity, so data of tile i + 1 can never be counted into the phase of tile i
     uint64_t* xb = gx.xbar + gx.xparity;
     if (tid == 0) ptx::mbar_arrive_expect_tx(xb, (uint32_t)(p.gn_xc * G * 8));
     if (tid < G) {
@@ -531,13 +600,16 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
       float a[16];
       ptx::tmem_ld_wait();
       if (cpg == 4) gnf_chunk_partials<16>(r, bias_row + c0 * 4, scale, row_ok, a);
-      else gnf_chunk_partials<8>(r, bias_row + c0 * 4, scale, row_ok, a);
+      else if (cpg == 8) gnf_chunk_partials<8>(r, bias_row + c0 * 4, scale, row_ok, a);
+      else gnf_chunk_partials<4>(r, bias_row + c0 * 4, scale, row_ok, a);
       const int qn = q + EPI_GROUPS;
       if (qn < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (qn / NCH) * BLOCK_N + (qn % NCH) * 32, r);
       if (cpg == 4) {
         if (split) gnf_chunk_reduce<16, true>(a, lane, dst, gi0); else gnf_chunk_reduce<16, false>(a, lane, dst, gi0);
-      } else {
+      } else if (cpg == 8) {
         if (split) gnf_chunk_reduce<8, true>(a, lane, dst, gi0); else gnf_chunk_reduce<8, false>(a, lane, dst, gi0);
+      } else {
+        if (split) gnf_chunk_reduce<4, true>(a, lane, dst, gi0); else gnf_chunk_reduce<4, false>(a, lane, dst, gi0);
       }
     }
   }
@@ -583,7 +655,7 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
       v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
       const float4 aa = (i >= 4) ? a1 : a0, oo = (i >= 4) ? o1 : o0;
       v.x = fmaf(v.x, aa.x, oo.x); v.y = fmaf(v.y, aa.y, oo.y); v.z = fmaf(v.z, aa.z, oo.z); v.w = fmaf(v.w, aa.w, oo.w);
-      if (p.gn_silu) { v.x = gnf_silu(v.x); v.y = gnf_silu(v.y); v.z = gnf_silu(v.z); v.w = gnf_silu(v.w); }
+      if (p.gn_silu) gnf_silu4(v);
       if (mb + i * 4 < p.M) {
         __half2 h0 = __floats2half2_rn(v.x, v.y);
         __half2 h1 = __floats2half2_rn(v.z, v.w);
@@ -645,7 +717,7 @@ __device__ __forceinline__ void epi_tile_gnf_dual_pass2(const EpiCtx<BLOCK_N, MT
       const float4 aa = (i >= 4) ? a1 : a0, oo = (i >= 4) ? o1 : o0;
       float4 y;
       y.x = fmaf(v[i].x, aa.x, oo.x); y.y = fmaf(v[i].y, aa.y, oo.y); y.z = fmaf(v[i].z, aa.z, oo.z); y.w = fmaf(v[i].w, aa.w, oo.w);
-      if (p.gn_silu) { y.x = gnf_silu(y.x); y.y = gnf_silu(y.y); y.z = gnf_silu(y.z); y.w = gnf_silu(y.w); }
+      if (p.gn_silu) gnf_silu4(y);
       if (mb + i * 4 < p.M) {
         __half2 h0 = __floats2half2_rn(y.x, y.y);
         __half2 h1 = __floats2half2_rn(y.z, y.w);

@@ -59,7 +59,7 @@ struct GemmOp {
   const float* gn_gamma;    // [N]
   const float* gn_beta;     // [N]
   float gn_eps;
-  int gn_groups;            // groups over the N output channels (channels per group must be 4 or 8)
+  int gn_groups;            // groups over the N output channels (channels per group must be 4, 8 or 16)
   int gn_silu;
   // EXPERIMENTAL (GDDIM_XF=1, conv_xf.cu): A operand = swish(GroupNorm(source)) produced on load from the fp32 source(s)
   int xf;
@@ -82,7 +82,7 @@ struct GemmOp {
 };
 
 // EPI_GNF is available for H*W in {16, 64, 256} (any N that is a multiple of 32) and for H*W = 1024 with N in {64, 128};
-// channels per group 4 or 8
+// channels per group 4, 8 or 16
 int gemm_gnf_supported(int H, int W, int N, int groups);
 
 // Encodes the TMA descriptors (needs the final device addresses). Returns 0 or a negative error.

@@ -244,6 +244,20 @@ static GemmOp make_gemm(int B, int H, int W) {
   return g;
 }
 
+// Where the GroupNorm-fused epilogue pays (measured per layer on B200 at batch 256, profiles/r02_gnf_per_op.txt): the
+// epilogue gets two passes and a swish, which is free while the main loop is longer than the epilogue (K >= 2304 at
+// 32x32, everything at 16x16 where a CTA pair owns an image) and costs more than the removed GroupNorm pass where the
+// epilogue is already the bottleneck (K = 1152 at 32x32: 256 x 128 tiles with a 9 k-cycle main loop; K = 4608 at 8x8).
+// GDDIM_GNF_ALL=1 fuses wherever the geometry allows (A/B).
+static bool gnf_pays(int H, int W, int K, bool dual) {
+  static const bool all = [] { const char* e = getenv("GDDIM_GNF_ALL"); return e && e[0] == '1'; }();
+  if (all) return true;
+  const int rpi = H * W;
+  if (rpi >= 1024) return !dual && K >= 2304;
+  if (rpi == 64) return dual || K <= 2304;
+  return true;
+}
+
 // ---- ResnetBlockBigGANpp (layerspp.py:180-227) ------------------------------------------------------------
 UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch, bool up, bool down) {
   Scope s = top.child("ResnetBlockBigGANpp");
@@ -270,9 +284,11 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
       last_flush_at_ < ops_.size() && gemm_gnf_supported(H, W, Cin, groups0)) {
     const Op& po = ops_[in1.prod_op];
     const GemmOp& pg = po.gemm;
+    int pk = 0;
+    for (int sgi = 0; sgi < pg.nseg; ++sgi) pk += pg.seg[sgi].taps * pg.seg[sgi].c;
     fuse0 = po.kind == OP_GEMM && pg.epi == EPI_LINEAR && pg.out32 == in1.p && pg.out16 == nullptr && pg.rowscale == nullptr &&
             pg.n_store == 0 && pg.w_batch_stride == 0 && pg.N == Cin && pg.ldo == Cin && pg.H == H && pg.W == W &&
-            !po.out_is_external;
+            !po.out_is_external && gnf_pays(H, W, pk, true);
   }
   hold_pending_ = fuse0;                 // a1 becomes an output of the producer: it must not reuse what that op still reads
   T16 a1 = new16(Cin, Ho, Wo);
@@ -323,7 +339,7 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
   static const bool no_gnf = [] { const char* e = getenv("GDDIM_NO_GNF"); return e && e[0] == '1'; }();
   auto gn1 = gn_params(s, out_ch);
   const int groups1 = std::min(out_ch / 4, 32);
-  const bool fuse1 = !no_gnf && gemm_gnf_supported(Ho, Wo, out_ch, groups1);
+  const bool fuse1 = !no_gnf && gemm_gnf_supported(Ho, Wo, out_ch, groups1) && gnf_pays(Ho, Wo, 9 * Cin, false);
   T16 a2 = new16(out_ch, Ho, Wo);
   T32 h2{nullptr, 0, 0, 0, 0};
   if (!fuse1) h2 = new32(out_ch, Ho, Wo);

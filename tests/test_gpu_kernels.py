@@ -484,3 +484,55 @@ def test_conv_with_dual_groupnorm_epilogue(impl, case):
   assert e32 < 2e-5 and e16 < 6e-4
   per = [rel_l2(o16[b].float().cpu().numpy(), want[b].numpy()) for b in range(B)]
   assert max(per) < 8e-4, per
+
+
+@pytest.mark.parametrize("dual", [False, True])
+@pytest.mark.parametrize("shape", [(3, 16, 16), (5, 8, 8), (3, 4, 4), (2, 32, 32)])
+def test_groupnorm_epilogue_16_channels_per_group(shape, dual):
+  """The h half of a concatenated [h, skip] GroupNorm input (512 channels, 32 groups: 16 channels per group) normalised
+  by the producer: N = 256 with 16 groups (N = 128 with 8 groups at 32x32)."""
+  B, H, W = shape
+  N = 128 if H == 32 else 256
+  groups = N // 16
+  g = torch.Generator().manual_seed(B + H)
+  a = torch.randn(B, H, W, 128, generator=g).to(torch.float16)
+  k = (torch.randn(3, 3, 128, N, generator=g) / np.sqrt(9 * 128)).numpy()
+  bias = torch.randn(N, generator=g)
+  gamma, beta = 1 + 0.2 * torch.randn(N, generator=g), 0.3 * torch.randn(N, generator=g)
+  v = _conv_ref(a, k, 9) + bias.double()
+  want = on.swish(F.group_norm(v.permute(0, 3, 1, 2), groups, gamma.double(), beta.double(), eps=1e-6)).permute(0, 2, 3, 1)
+  o32, o16 = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k), N, bias=bias.cuda(), gn=(gamma.cuda(), beta.cuda(), groups, True, 1e-6, dual))
+  torch.cuda.synchronize()
+  assert rel_l2(o16.float().cpu().numpy(), want.numpy()) < 6e-4
+  if dual:
+    assert rel_l2(o32.cpu().numpy(), v.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("B", [2, 37, 75, 150])
+@pytest.mark.parametrize("dual", [False, True])
+def test_groupnorm_epilogue_two_pairs_per_image(B, dual):
+  """32x32 images on cta_group::2 pairs: two pairs per image, statistics exchanged through tagged global words
+  (all SMs busy; clusters of four only fit 132).  Several rounds, repeated launches (tags restart), odd / even counts."""
+  H = W = 32
+  C_ = 128
+  g = torch.Generator().manual_seed(B)
+  a = torch.randn(B, H, W, C_, generator=g).to(torch.float16)
+  k = (torch.randn(3, 3, C_, C_, generator=g) / np.sqrt(9 * C_)).numpy()
+  bias = torch.randn(C_, generator=g)
+  res = torch.randn(B, H, W, C_, generator=g) if dual else None
+  gamma, beta = 1 + 0.2 * torch.randn(C_, generator=g), 0.3 * torch.randn(C_, generator=g)
+  v = _conv_ref(a, k, 9) + bias.double()
+  if dual:
+    v = v + res.double()
+  want = on.swish(F.group_norm(v.permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), eps=1e-6)).permute(0, 2, 3, 1)
+  ad, wd, bd, gd, bed = a.cuda(), ops.pack_conv_weight(k), bias.cuda(), gamma.cuda(), beta.cuda()
+  rd = None if res is None else res.cuda()
+  outs = []
+  for rep in range(3):
+    o32, o16 = ops.conv_gemm(ad, wd, C_, bias=bd, residual=rd, force_block_n=128, force_m_sub=2, force_cta_pairs=2,
+                             gn=(gd, bed, 32, True, 1e-6, dual))
+    outs.append(o16)
+  torch.cuda.synchronize()
+  per = [rel_l2(outs[0][b].float().cpu().numpy(), want[b].numpy()) for b in range(B)]
+  assert max(per) < 8e-4, (max(per), int(np.argmax(per)))
+  assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
