@@ -37,7 +37,7 @@ class GemmDesc(C.Structure):
               ("ldo", C.c_int), ("epi", C.c_int), ("impl", C.c_int), ("force_block_n", C.c_int),
               ("force_m_sub", C.c_int), ("n_store", C.c_int), ("force_cta_pairs", C.c_int), ("reverse", C.c_int),
               ("gn_gamma", C.c_void_p), ("gn_beta", C.c_void_p), ("gn_eps", C.c_float), ("gn_groups", C.c_int),
-              ("gn_silu", C.c_int), ("pad_", C.c_int)]
+              ("gn_silu", C.c_int), ("wsplit", C.c_int)]
 
 
 class NormDesc(C.Structure):
@@ -54,6 +54,7 @@ class Step(C.Structure):
               ("has_P", C.c_int), ("P", C.c_float * 4)]
 
 
+CTX_PRECISE_WEIGHTS = 1
 CLD_DEIS, CLD_ORDER0, BLUR_ORDER0, CLD_SDEIS, CLD_PROGRAM = 0, 1, 2, 3, 4
 
 _P = C.c_void_p
@@ -65,6 +66,7 @@ SIGNATURES = {
     "gddim_abi_version": (C.c_int, []),
     "gddim_cuda_available": (C.c_int, []),
     "gddim_ctx_create": (C.c_int, [C.c_int, C.POINTER(ModelCfg), C.c_int, C.POINTER(_P)]),
+    "gddim_ctx_create_ex": (C.c_int, [C.c_int, C.POINTER(ModelCfg), C.c_int, C.c_uint, C.POINTER(_P)]),
     "gddim_ctx_destroy": (None, [_P]),
     "gddim_param_count": (C.c_int, [_P]),
     "gddim_param_spec": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int * 4), C.POINTER(C.c_int),

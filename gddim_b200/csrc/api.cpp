@@ -72,10 +72,13 @@ int gddim_cuda_available(void) {
 
 // ---- context ------------------------------------------------------------------------------------------------
 int gddim_ctx_create(int device, const gddim_model_cfg* cfg, int max_batch, gddim_ctx** out) {
+  return gddim_ctx_create_ex(device, cfg, max_batch, 0, out);
+}
+int gddim_ctx_create_ex(int device, const gddim_model_cfg* cfg, int max_batch, unsigned flags, gddim_ctx** out) {
   if (!cfg || !out || max_batch < 1) return set_err("gddim_ctx_create: bad arguments");
   std::unique_ptr<gddim_ctx> c(new gddim_ctx);
   c->device = device;
-  c->net.reset(new UNet(*cfg, max_batch));
+  c->net.reset(new UNet(*cfg, max_batch, (flags & GDDIM_CTX_PRECISE_WEIGHTS) != 0));
   if (!c->net->error().empty()) return set_err("gddim_ctx_create: " + c->net->error());
   *out = c.release();
   return 0;
@@ -338,6 +341,7 @@ int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream) {
   g.bias = d->bias; g.bias2 = d->bias2; g.residual = d->residual; g.rowscale = d->rowscale; g.scale = d->scale;
   g.out32 = d->out32; g.out16 = (__half*)d->out16; g.row_out = d->row_out; g.ldo = d->ldo; g.epi = d->epi; g.n_store = d->n_store;
   g.reverse = d->reverse;
+  g.wsplit = d->wsplit;
   g.gn_gamma = d->gn_gamma; g.gn_beta = d->gn_beta; g.gn_eps = d->gn_eps; g.gn_groups = d->gn_groups; g.gn_silu = d->gn_silu;
   if (d->impl == 0 && gemm_prepare(&g, d->force_block_n, d->force_m_sub, d->force_cta_pairs)) return set_err(std::string("gddim_conv_gemm: ") + gemm_last_error());
   if (gemm_launch(&g, d->impl, (cudaStream_t)stream)) return set_err(std::string("gddim_conv_gemm: ") + gemm_last_error());

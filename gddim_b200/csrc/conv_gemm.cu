@@ -136,6 +136,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       }
       const int bidx = p.tiles_per_batch > 0 ? mt / p.tiles_per_batch : 0;
       const int nrow0 = nt * BLOCK_N + cta_rank * (BLOCK_N / CG);
+      for (int ws = 0; ws < p.wsplit; ++ws) {          // precise mode: A against W_hi, then A again against W_lo
+      const int wk0 = p.w_koff + ws * p.ktot;
       int kb = 0;
       for (int s = 0; s < p.nseg; ++s) {
         const CUtensorMap* tm = (s == 0) ? &tmA0 : &tmA1;
@@ -151,7 +153,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 #pragma unroll
               for (int dyi = 0; dyi < 3; ++dyi)
                 load(&tmB, fb, &full_bar[stage], slot + a_bytes + dyi * L::B_TILE_BYTES,
-                     p.w_koff + kb * BLOCK_K + (dyi * 3 + dxi) * cseg + kc * BLOCK_K, nrow0, bidx, 0);
+                     wk0 + kb * BLOCK_K + (dyi * 3 + dxi) * cseg + kc * BLOCK_K, nrow0, bidx, 0);
               if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_cluster(fb);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -170,11 +172,12 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
             for (int mi = 0; mi < MT; ++mi)
               load(tm, fb, &full_bar[stage], slot + mi * A_TILE_BYTES, p.coff[s] + kc * BLOCK_K, w0[mi] + dx, h0[mi] + dy,
                    b0[mi]);
-            load(&tmB, fb, &full_bar[stage], slot + a_bytes, p.w_koff + kb * BLOCK_K, nrow0, bidx, 0);
+            load(&tmB, fb, &full_bar[stage], slot + a_bytes, wk0 + kb * BLOCK_K, nrow0, bidx, 0);
             if (CG == 2 && cta_rank != 0) ptx::mbar_arrive_cluster(fb);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
+      }
       }
     }
   } else if (threadIdx.x == MMA_THREAD && cta_rank == 0) {
@@ -205,7 +208,8 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           }
         }
       };
-      for (int s = 0; s < p.nseg; ++s) {
+      for (int sw = 0; sw < p.nseg * p.wsplit; ++sw) {
+        const int s = sw % p.nseg;
         const bool halo_seg = HALO && p.taps[s] == 9;
         const int slots = halo_seg ? 3 * p.kch[s] : p.taps[s] * p.kch[s];
         for (int g = 0; g < slots; ++g) {
@@ -399,6 +403,7 @@ struct RefArgs {
   int B, H, W, M, N;
   const __half* w;
   int w_ld, w_koff;
+  int w_lo_off;                  // > 0: second weight half (W = W_hi + W_lo) this many columns further
   long long w_batch_stride;
   int tiles_per_batch_rows;      // rows of M per batch matrix (0 = shared)
   const float* bias;
@@ -457,6 +462,7 @@ __global__ void __launch_bounds__(256) conv_gemm_ref_kernel(const RefArgs p) {
             long long boff = 0;
             if (p.w_batch_stride != 0) boff = (m0 / p.tiles_per_batch_rows) * p.w_batch_stride;
             v = __half2float(p.w[boff + (long long)n * p.w_ld + p.w_koff + kglobal + kk]);
+            if (p.w_lo_off > 0) v += __half2float(p.w[boff + (long long)n * p.w_ld + p.w_koff + p.w_lo_off + kglobal + kk]);
           }
           sW[kk][r] = v;
         }
@@ -633,7 +639,9 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     if (g.taps != 1 && g.taps != 9) GEMM_FAIL("conv_gemm: taps must be 1 or 9");
     ktot += g.taps * g.c;
   }
-  if (op->w_koff + ktot > op->w_ld) GEMM_FAIL("conv_gemm: K range exceeds weight row stride");
+  if (op->wsplit != 0 && op->wsplit != 1 && op->wsplit != 2) GEMM_FAIL("conv_gemm: wsplit must be 1 or 2");
+  if (op->w_koff + ktot * (op->wsplit == 2 ? 2 : 1) > op->w_ld) GEMM_FAIL("conv_gemm: K range exceeds weight row stride");
+  if (op->wsplit == 2 && (op->w_batch_stride != 0 || op->epi == EPI_SOFTMAX)) GEMM_FAIL("conv_gemm: split weights need a shared weight matrix");
   const bool gnf = op->epi == EPI_GNF;
   const int rpi = op->H * op->W;
   int cpg = 0;
@@ -910,6 +918,9 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     a.M = (int)M; a.N = op->N;
     a.m_tiles = op->m_tiles; a.n_tiles = op->n_tiles; a.tiles_per_batch = op->tiles_per_batch;
     a.w_koff = op->w_koff;
+    a.wsplit = op->wsplit == 2 ? 2 : 1;
+    a.ktot = 0;
+    for (int s = 0; s < op->nseg; ++s) a.ktot += op->seg[s].taps * op->seg[s].c;
     a.bias = op->bias; a.bias2 = op->bias2; a.residual = op->residual; a.rowscale = op->rowscale;
     a.scale = op->scale; a.out32 = op->out32; a.out16 = op->out16; a.row_out = op->row_out; a.ldo = op->ldo;
     a.colstats = op->colstats;
@@ -1022,6 +1033,8 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
   }
   r.nseg = op->nseg; r.B = op->B; r.H = op->H; r.W = op->W; r.M = (int)M; r.N = op->N;
   r.w = op->w; r.w_ld = op->w_ld; r.w_koff = op->w_koff; r.w_batch_stride = op->w_batch_stride;
+  r.w_lo_off = 0;
+  if (op->wsplit == 2) for (int s = 0; s < op->nseg; ++s) r.w_lo_off += op->seg[s].taps * op->seg[s].c;
   r.tiles_per_batch_rows = op->H * op->W;
   r.bias = op->bias; r.bias2 = op->bias2; r.residual = op->residual; r.rowscale = op->rowscale;
   r.scale = op->scale; r.out32 = op->out32; r.out16 = op->out16; r.row_out = op->row_out; r.ldo = op->ldo;

@@ -41,6 +41,8 @@ struct GemmArgs {
   int M, N;
   int m_tiles, n_tiles, tiles_per_batch;
   int w_koff;
+  int wsplit;        // 1, or 2: the K loop runs twice, the second time against the weight columns shifted by ktot (W = W_hi + W_lo)
+  int ktot;          // K of one pass in elements
   const float* bias;
   const float* bias2;
   const float* residual;

@@ -32,6 +32,7 @@ struct GemmOp {
   int N;                    // output columns
   int w_ld;                 // row stride of w in elements (>= Ktot)
   int w_koff;               // first K column used in w
+  int wsplit;               // 0 / 1: one pass; 2: W = W_hi + W_lo, columns [w_koff, +K) and [w_koff + K, +2K) (precise mode)
   long long w_batch_stride; // elements between per-image B matrices; 0 = shared weights
   int w_rows_per_batch;     // rows (N) per batch matrix when batched
   const float* bias;

@@ -35,7 +35,7 @@ struct UNet::Scope {
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-UNet::UNet(const gddim_model_cfg& cfg, int max_batch) : cfg_(cfg), max_batch_(max_batch) {
+UNet::UNet(const gddim_model_cfg& cfg, int max_batch, bool precise) : cfg_(cfg), max_batch_(max_batch), precise_(precise) {
   dry_ = true;
   arena_ = reinterpret_cast<char*>(uintptr_t(1) << 20);   // fake non-null base for the dry planning pass
   wts_ = reinterpret_cast<char*>(uintptr_t(1) << 20);
@@ -175,12 +175,19 @@ static float scale0(float s) { return s == 0.f ? 1e-10f : s; }   // layers.py:62
 constexpr float kRawScale = 1.0f / 64.0f;
 
 // conv kernel HWIO (kh,kw,cin,cout) -> K-major [cout][koff + tap*cin + ci] inside rows of length ld
+// lo_off > 0 (precise mode): the rounding remainder w - fp16(w) goes, again as fp16, lo_off columns further -- the GEMM
+// then runs its K loop twice (A x W_hi + A x W_lo): the weights enter with ~22 significant bits
 static void pack_conv(const std::vector<float>& k, int taps, int cin, int cout, std::vector<__half>& dst, int ld,
-                      int koff, float mul = 1.f) {
+                      int koff, float mul = 1.f, int lo_off = 0) {
   for (int tap = 0; tap < taps; ++tap)
     for (int ci = 0; ci < cin; ++ci) {
       const float* src = k.data() + ((size_t)tap * cin + ci) * cout;
-      for (int co = 0; co < cout; ++co) dst[(size_t)co * ld + koff + tap * cin + ci] = __float2half_rn(src[co] * mul);
+      for (int co = 0; co < cout; ++co) {
+        const float w = src[co] * mul;
+        const __half hi = __float2half_rn(w);
+        dst[(size_t)co * ld + koff + tap * cin + ci] = hi;
+        if (lo_off > 0) dst[(size_t)co * ld + lo_off + koff + tap * cin + ci] = __float2half_rn(w - __half2float(hi));
+      }
     }
 }
 
@@ -324,12 +331,13 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
   }
   __half* w1 = nullptr;
   {
-    const size_t n = (size_t)out_ch * 9 * Cin;
+    const int wmul = precise_ ? 2 : 1;
+    const size_t n = (size_t)out_ch * 9 * Cin * wmul;
     if (dry_) w1 = (__half*)w_alloc(n * 2);
     else {
       if (!k0) return T32{nullptr, 0, 0, 0, 0};
       std::vector<__half> pk(n);
-      pack_conv(*k0, 9, Cin, out_ch, pk, 9 * Cin, 0);
+      pack_conv(*k0, 9, Cin, out_ch, pk, 9 * Cin * wmul, 0, 1.f, precise_ ? 9 * Cin : 0);
       w1 = upload_f16(pk);
     }
   }
@@ -349,7 +357,7 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     GemmOp& g = op.gemm;
     g.nseg = 1;
     g.seg[0] = {a1.p, Cin, 0, Cin, 9};
-    g.w = w1; g.N = out_ch; g.w_ld = 9 * Cin;
+    g.w = w1; g.N = out_ch; g.w_ld = 9 * Cin * (precise_ ? 2 : 1); g.wsplit = precise_ ? 2 : 1;
     g.bias = bias1;
     g.bias2 = temb_off >= 0 ? temb_cur_ + temb_off : nullptr;
     g.ldo = out_ch;
@@ -382,14 +390,15 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
   const int ktot = 9 * out_ch + (need_sc ? Cin : 0);
   __half* w2 = nullptr;
   const float* bias2v = nullptr;
-  if (dry_) { w2 = (__half*)w_alloc((size_t)out_ch * ktot * 2); w_alloc(out_ch * 4); }
+  const int wld2 = ktot * (precise_ ? 2 : 1), lo2 = precise_ ? ktot : 0;
+  if (dry_) { w2 = (__half*)w_alloc((size_t)out_ch * wld2 * 2); w_alloc(out_ch * 4); }
   else {
     if (!k1 || !b1 || (need_sc && (!k2 || !b2))) return T32{nullptr, 0, 0, 0, 0};
-    std::vector<__half> pk((size_t)out_ch * ktot);
-    pack_conv(*k1, 9, out_ch, out_ch, pk, ktot, 0);
+    std::vector<__half> pk((size_t)out_ch * wld2);
+    pack_conv(*k1, 9, out_ch, out_ch, pk, wld2, 0, 1.f, lo2);
     std::vector<float> bsum(*b1);
     if (need_sc) {
-      pack_conv(*k2, 1, Cin, out_ch, pk, ktot, 9 * out_ch, 1.0f / kRawScale);
+      pack_conv(*k2, 1, Cin, out_ch, pk, wld2, 9 * out_ch, 1.0f / kRawScale, lo2);
       for (int i = 0; i < out_ch; ++i) bsum[i] += (*b2)[i];
     }
     w2 = upload_f16(pk);
@@ -403,7 +412,7 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     g.nseg = need_sc ? 2 : 1;
     g.seg[0] = {a2.p, out_ch, 0, out_ch, 9};
     if (need_sc) g.seg[1] = {x16.p, Cin, 0, Cin, 1};
-    g.w = w2; g.N = out_ch; g.w_ld = ktot;
+    g.w = w2; g.N = out_ch; g.w_ld = wld2; g.wsplit = precise_ ? 2 : 1;
     g.bias = bias2v;
     g.residual = need_sc ? nullptr : in1.p;
     g.scale = out_scale;

@@ -44,7 +44,8 @@ struct Op {
 
 class UNet {
  public:
-  UNet(const gddim_model_cfg& cfg, int max_batch);
+  // precise: conv weights as fp16 hi + lo pairs (two K passes per convolution; parity mode, ~2x slower convolutions)
+  UNet(const gddim_model_cfg& cfg, int max_batch, bool precise = false);
   ~UNet();
   const std::vector<ParamSpec>& specs() const { return specs_; }
   int set_param(const std::string& name, const float* host, size_t n);
@@ -83,6 +84,7 @@ class UNet {
   gddim_model_cfg cfg_;
   int max_batch_;
   bool dry_ = true;
+  bool precise_ = false;
   bool finalized_ = false;
   std::string err_;
   std::vector<ParamSpec> specs_;

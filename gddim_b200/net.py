@@ -64,8 +64,9 @@ def flatten_params(tree, prefix=""):
 class ScoreNet:
   """Handle of one NCSN++/DDPM++ network on one GPU (the `model` / `pstate` stand-in)."""
 
-  def __init__(self, config, cld=True, device=None):
-    self.config, self.cld = config, cld
+  def __init__(self, config, cld=True, device=None, precise=False):
+    """precise=True: convolution weights as fp16 (hi, lo) pairs, two K passes per convolution (parity mode)."""
+    self.config, self.cld, self.precise = config, cld, bool(precise)
     self.device = device
     self._cfg = model_cfg_from_config(config, cld)
     self._ctx = None
@@ -161,7 +162,8 @@ class ScoreNet:
     L = _lib.lib()
     dev = torch.cuda.current_device() if self.device is None else int(self.device)
     ctx = C.c_void_p()
-    _lib.check(L.gddim_ctx_create(dev, C.byref(self._cfg), int(batch), C.byref(ctx)), "gddim_ctx_create")
+    _lib.check(L.gddim_ctx_create_ex(dev, C.byref(self._cfg), int(batch), 1 if self.precise else 0, C.byref(ctx)),
+               "gddim_ctx_create")
     try:
       for name in _read_specs(ctx):
         if name not in self._params:

@@ -17,9 +17,10 @@ def _ptr(t):
   return None if t is None else t.data_ptr()
 
 
-def pack_conv_weight(kernel_hwio, extra_1x1=None):
+def pack_conv_weight(kernel_hwio, extra_1x1=None, split=False):
   """Flax HWIO kernel (kh,kw,cin,cout) [+ optional 1x1 shortcut kernel (1,1,cin2,cout)] -> K-major fp16
-  [cout, kh*kw*cin (+ cin2)] with k = tap*cin + ci  (the layout csrc/unet.cpp packs)."""
+  [cout, kh*kw*cin (+ cin2)] with k = tap*cin + ci  (the layout csrc/unet.cpp packs).  split=True: [cout, 2K] =
+  [fp16(w) | fp16(w - fp16(w))] for conv_gemm(..., wsplit=2) (precise mode)."""
   import torch
   k = torch.as_tensor(np.asarray(kernel_hwio, np.float32))
   kh, kw, cin, cout = k.shape
@@ -27,12 +28,16 @@ def pack_conv_weight(kernel_hwio, extra_1x1=None):
   if extra_1x1 is not None:
     e = torch.as_tensor(np.asarray(extra_1x1, np.float32))
     w = torch.cat([w, e.reshape(-1, cout).t().contiguous()], dim=1)
-  return w.to(torch.float16).contiguous().cuda()
+  hi = w.to(torch.float16)
+  if split:
+    lo = (w - hi.float()).to(torch.float16)
+    return torch.cat([hi, lo], dim=1).contiguous().cuda()
+  return hi.contiguous().cuda()
 
 
 def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residual=None, rowscale=None, scale=1.0,
               out_fp32=True, out_fp16=False, impl=0, force_block_n=0, force_m_sub=0, force_cta_pairs=0, epi=0, n_store=0, a0_coff=0, a0_c=None, w_ld=None,
-              w_koff=0, w_batch_stride=0, w_rows_per_batch=0, reverse=0, gn=None):
+              w_koff=0, w_batch_stride=0, w_rows_per_batch=0, reverse=0, gn=None, wsplit=0):
   """a0 (and a1): fp16 [B,H,W,C]; w: fp16 K-major.  Returns (out32 or None, out16 or None[, row_out]).
   gn = (gamma, beta, groups, silu[, eps[, dual]]): epi 2, the GroupNorm (+ swish) of the output applied by the epilogue
   -> out16; dual = True also returns the un-normalised fp32 result (bias / residual / scale as usual) in out32."""
@@ -62,6 +67,7 @@ def conv_gemm(a0, w, N, taps0=9, a1=None, taps1=1, bias=None, bias2=None, residu
   d.epi, d.impl, d.force_block_n, d.force_m_sub = epi, impl, force_block_n, force_m_sub
   d.force_cta_pairs = force_cta_pairs
   d.reverse = reverse
+  d.wsplit = wsplit
   st = torch.cuda.current_stream().cuda_stream
   _lib.check(_lib.lib().gddim_conv_gemm(C.byref(d), st), "gddim_conv_gemm")
   if epi == 1:

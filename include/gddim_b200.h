@@ -55,6 +55,11 @@ int gddim_cuda_available(void);
 
 /* ---- context / parameters: models/utils.py:109-125 init_model, run_lib.py:707-711 restore + replicate ---- */
 int gddim_ctx_create(int device, const gddim_model_cfg* cfg, int max_batch, gddim_ctx** out);
+/* flags: GDDIM_CTX_PRECISE_WEIGHTS = every 3x3 / shortcut convolution keeps its weights as an fp16 (hi, lo) pair and runs
+ * its K loop twice (A x W_hi + A x W_lo): removes the weight half of the operand rounding (parity mode; the reference
+ * computes in fp32).  Twice the weight memory and tensor work of those layers. */
+#define GDDIM_CTX_PRECISE_WEIGHTS 1u
+int gddim_ctx_create_ex(int device, const gddim_model_cfg* cfg, int max_batch, unsigned flags, gddim_ctx** out);
 void gddim_ctx_destroy(gddim_ctx* ctx);
 /* parameter inventory in Flax naming (e.g. "ResnetBlockBigGANpp_3/Conv_0/kernel"), Flax layouts
  * (conv HWIO, dense (in,out)).  kind: 0 variance_scaling(fan_avg, uniform), 1 zeros, 2 ones, 3 normal */
@@ -158,7 +163,8 @@ typedef struct {
   int force_cta_pairs;                                      /* 0 = heuristic, 1 = single-CTA MMA, 2 = cta_group::2 pairs (block_n 256) */
   int reverse;                                              /* 1 = tiles in descending order (L2 reuse along producer -> consumer chains); same results */
   const float* gn_gamma; const float* gn_beta;              /* epi = 2 */
-  float gn_eps; int gn_groups; int gn_silu; int pad_;
+  float gn_eps; int gn_groups; int gn_silu;
+  int wsplit;                                               /* 0 / 1: plain; 2: w rows hold W_hi then W_lo (K columns apart, W = W_hi + W_lo): two K passes */
 } gddim_gemm_desc;
 int gddim_conv_gemm(const gddim_gemm_desc* d, void* stream);
 int gddim_gemm_gnf_supported(int H, int W, int N, int groups);   /* 1 if epi = 2 is available for this output geometry */

@@ -31,13 +31,14 @@ def small_cfg(kind):
 _cache = {}
 
 
-def build(kind, nondegenerate=True, seed=1234):
-  """-> (cfg, ScoreNet with parameters, oracle net_fn(x, labels) in fp32)."""
-  key = (kind, nondegenerate, seed)
+def build(kind, nondegenerate=True, seed=1234, precise=False):
+  """-> (cfg, ScoreNet with parameters, oracle net_fn(x, labels) in fp32).  precise: convolution weights as fp16 (hi, lo)
+  pairs (the library's parity mode)."""
+  key = (kind, nondegenerate, seed, precise)
   if key not in _cache:
     cfg = small_cfg(kind)
     cld = not kind.startswith("blur")
-    model = net.ScoreNet(cfg, cld=cld)
+    model = net.ScoreNet(cfg, cld=cld, precise=precise)
     p = model.init_params(seed=seed, nondegenerate=nondegenerate)
     _cache[key] = (cfg, model, on.make_net_fn(p, cfg))
   return _cache[key]

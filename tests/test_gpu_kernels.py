@@ -536,3 +536,23 @@ def test_groupnorm_epilogue_two_pairs_per_image(B, dual):
   per = [rel_l2(outs[0][b].float().cpu().numpy(), want[b].numpy()) for b in range(B)]
   assert max(per) < 8e-4, (max(per), int(np.argmax(per)))
   assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["ref", "umma"])
+@pytest.mark.parametrize("case", [(2, 32, 32, 128, 128), (3, 16, 16, 256, 256), (3, 4, 4, 256, 256), (2, 16, 16, 64, 128)],
+                         ids=lambda c: f"b{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}")
+def test_conv_split_weights_removes_weight_rounding(impl, case):
+  """wsplit = 2 (precise mode): W = fp16(W) + fp16(W - fp16(W)), two K passes.  Against a conv with the SAME fp16
+  activations but the full fp32 weights the error drops from ~2e-4 (weight rounding) to accumulation-order level."""
+  B, H, W, Cin, Cout = case
+  g = torch.Generator().manual_seed(Cin + H)
+  a = torch.randn(B, H, W, Cin, generator=g).to(torch.float16)
+  k = (torch.randn(3, 3, Cin, Cout, generator=g) / np.sqrt(9 * Cin)).numpy()
+  x = a.double().permute(0, 3, 1, 2)
+  want = F.conv2d(x, torch.as_tensor(k).double().permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)     # fp32 weights, not rounded
+  o_split, _ = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k, split=True), Cout, impl=impl, wsplit=2, w_ld=2 * 9 * Cin)
+  o_plain, _ = ops.conv_gemm(a.cuda(), ops.pack_conv_weight(k), Cout, impl=impl)
+  torch.cuda.synchronize()
+  e_split, e_plain = rel_l2(o_split.cpu().numpy(), want.numpy()), rel_l2(o_plain.cpu().numpy(), want.numpy())
+  print(f"split weights {case} impl={impl}: plain {e_plain:.2e} -> split {e_split:.2e}")
+  assert e_split < 2e-6 and e_plain > 5e-5

@@ -103,3 +103,36 @@ def test_256x256_forward_matches_oracle():
   err = rel_l2(got, want)
   print(f"256x256 forward: rel-L2 {err:.3e}")
   assert err < FWD_TOL
+
+
+def test_256x256_full_width_forward_matches_oracle():
+  """BASELINE config 5 at FULL width (accr_dcifar10 with data.image_size=256: nf=128, 8 res-blocks per level, 107.6 M
+  parameters, 2.26 TFLOP per image and evaluation), batch 1: the network the config-5 bench line runs, not a narrowed
+  stand-in.  One oracle evaluation takes tens of seconds on the host."""
+  from gddim_b200 import configs, net
+  from oracle import ncsnpp as on
+  cfg = configs.cld_accr_dcifar10()
+  cfg.data.image_size = 256
+  model = net.ScoreNet(cfg, cld=True)
+  p = model.init_params(seed=12, nondegenerate=True)
+  x = np.random.default_rng(4).standard_normal((1, 256, 256, 6)).astype(np.float32)
+  got = model.forward(x, 0.6)
+  want = on.forward(p, cfg, x, 999 * 0.6)
+  err = rel_l2(got, want)
+  print(f"256x256 full-width forward: rel-L2 {err:.3e}")
+  assert np.isfinite(got).all() and err < FWD_TOL
+
+
+@pytest.mark.parametrize("kind", ["cld_deep", "cld_ddpmpp", "blur_deep"])
+def test_precise_weights_mode_shows_the_residual_is_operand_rounding(kind):
+  """GDDIM_CTX_PRECISE_WEIGHTS: convolution weights as fp16 (hi, lo) pairs, two K passes.  Activations still enter the
+  tensor cores as fp16, so this removes exactly the weight half of the operand rounding: the distance to the fp32 oracle
+  must drop by about 1/sqrt(2) (two independent, equally large rounding sources) -- the evidence that the ~1.3e-3 of one
+  evaluation is operand rounding and not a kernel defect."""
+  cfg, fast, net_fn = build(kind)
+  _, prec, _ = build(kind, precise=True)
+  x = np.random.default_rng(3).standard_normal((3, 32, 32, fast.net_channels)).astype(np.float32)
+  want = net_fn(x, 999.0 * 0.3)
+  e_fast, e_prec = rel_l2(fast.forward(x, 0.3), want), rel_l2(prec.forward(x, 0.3), want)
+  print(f"{kind}: one evaluation vs fp32 oracle: fp16 weights {e_fast:.2e}, (hi, lo) weights {e_prec:.2e}, ratio {e_prec / e_fast:.2f}")
+  assert e_prec < 0.85 * e_fast and e_prec < 1.2e-3

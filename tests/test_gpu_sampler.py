@@ -540,3 +540,25 @@ def test_sample_data_from_independent_flax_checkpoint_matches_oracle(tmp_path):
   # uint8 quantisation as run_lib.py:723 (random weights drive most pixels into saturation; compare away from the edges)
   mine = np.clip(got["samples_x"] * 255., 0, 255).astype(np.uint8).reshape(got["samples"].shape)
   np.testing.assert_array_equal(got["samples"], mine)
+
+
+def test_loosened_cases_meet_1e3_in_precise_weights_mode():
+  """the cases whose fast-mode error sits at 1.0-1.15e-3 (mixed score, Euler-Maruyama) against the
+  north-star figure 1e-3 -- in the precise-weights mode (fp16 (hi, lo) weight pairs) they pass at TOL = 1e-3."""
+  from oracle import cld as oc
+  cfg, model, net_fn = build("cld_mixed", precise=True)
+  sde = sde_lib.from_config(cfg)
+  u = prior_u(2, seed=7)
+  x, v, _ = sampling.get_deis_sampler(sde, model, (32, 32, 3), 8, inv, 2, ts_order=2, denoising=True)(0, model, 2, u=u)
+  ox, ov, _ = oracle_cld_sample(cfg, net_fn, u, 8, 2, denoising=True)
+  e_mixed = max(rel_l2(x, ox), rel_l2(v, ov))
+  cfg.model.mixed_score = False
+  sde2, o = sde_lib.from_config(cfg), oc.from_config(cfg)
+  cfg.model.mixed_score = True
+  z = np.random.default_rng(63).standard_normal((5,) + u.shape).astype(np.float32)
+  u2 = prior_u(2, seed=62)
+  x, v, _ = sampling.get_em_sampler(sde2, model, (32, 32, 3), 6, inv, lambda_coef=0.7, ts_order=2, denoising=True)(0, model, 2, u=u2, noise=z)
+  ox, ov, _ = oc.em_sampler(o, oc.make_eps_fn(o, net_fn), u2, 6, z, lambda_coef=0.7, denoising=True, dtype=np.float32)
+  e_em = max(rel_l2(x, ox), rel_l2(v, ov))
+  print(f"precise weights: mixed-score deis {e_mixed:.2e}, em {e_em:.2e}")
+  assert e_mixed < TOL and e_em < TOL
