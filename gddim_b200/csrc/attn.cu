@@ -45,7 +45,8 @@ constexpr int AT_OFF_K = 4 * AT_QBLK;
 constexpr int AT_OFF_BAR = AT_OFF_K + 4 * AT_KBLK;
 constexpr int AT_OFF_XCH = AT_OFF_BAR + 128;        // [2 halves][128 rows] row max, then the same for row sums
 constexpr int AT_OFF_BIAS = AT_OFF_XCH + 2048;      // [256] projection bias row (PROJ)
-constexpr int AT_SMEM = AT_OFF_BIAS + 1024 + 1024;  // + alignment slack
+constexpr int AT_OFF_GNF = AT_OFF_BIAS + 1024;      // PROJ + GroupNorm of the output: gemm_epilogue.cuh GnfSmem<256>
+constexpr int AT_SMEM = AT_OFF_GNF + GnfSmem<256>::BYTES + 1024;  // + alignment slack
 
 // MN-major B operand (V: rows = keys, 128 B = 64 channels per row, 128B swizzle): 8-key groups 1024 B apart (SBO),
 // 64-channel blocks AT_KBLK apart (LBO)
@@ -123,12 +124,17 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
     ptx::mbar_init(bar_p, 256);
     ptx::mbar_init(bar_o, 1);
     if (PROJ) { ptx::prefetch_tmap(&tm_w3); ptx::mbar_init(bar_w, 1); ptx::mbar_init(bar_o16, 256); ptx::mbar_init(bar_y, 1); }
+    if (PROJ && p.g.gn_gamma != nullptr) {       // statistics exchange with the CTA that owns the image's other half
+      ptx::mbar_init(reinterpret_cast<uint64_t*>(smem + AT_OFF_GNF + GnfSmem<256>::OFF_BAR), 1);
+      ptx::mbar_init(reinterpret_cast<uint64_t*>(smem + AT_OFF_GNF + GnfSmem<256>::OFF_BAR) + 1, 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 8) { __syncwarp(); ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   pdl_wait();
   ptx::tc_fence_before();
-  __syncthreads();
+  // (GroupNorm epilogue: launched as clusters of two CTAs = one image; the peer's barrier must exist before data is sent)
+  if (PROJ && p.g.gn_gamma != nullptr) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -270,13 +276,29 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
       ptx::fence_proxy_async();
       ptx::mbar_arrive(bar_o16);
       bias_s[threadIdx.x] = __ldg(p.bias3 + threadIdx.x);                  // 256 epilogue threads = 256 output columns
+      const bool gn = p.g.gn_gamma != nullptr;
+      uint8_t* gnf = smem + AT_OFF_GNF;
+      float* gb = reinterpret_cast<float*>(gnf + GnfSmem<256>::OFF_GB);
+      if (gn) { gb[threadIdx.x] = __ldg(p.g.gn_gamma + threadIdx.x); gb[256 + threadIdx.x] = __ldg(p.g.gn_beta + threadIdx.x); }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // the GEMM kernels' linear epilogue on this warp's lane quadrant and alternate 32-column chunks; its staging
       // (4 KB per warp) reuses the A-operand memory, which it touches only after Y is complete
       float* stg_f = reinterpret_cast<float*>(sQ) + warp * 32 * SmemLayout<256, 1>::EPI_ROW_FLOATS;
       EpiCtx<256, 1> cx{p.g, stg_f, bias_s, bar_y, 0u, tmem_base + (uint32_t(quad * 32) << 16),
                         (long long)b * AT_T + half * AT_Q + quad * 32, 0, lane, ch};
-      epi_tile<256, 1, true, true, false, true, false, true, false>(cx);
+      if (gn) {
+        // the NEXT block's GroupNorm_0 + swish applied here (dual GroupNorm epilogue, gemm_epilogue.cuh): pass 1 = the
+        // linear epilogue with group partials, statistics exchanged with the peer CTA through DSMEM, pass 2 re-reads
+        // the fp32 result and writes the consumer's fp16 A operand
+        GnfCtx gx{reinterpret_cast<float2*>(gnf), reinterpret_cast<float2*>(gnf + GnfSmem<256>::OFF_GSTAT),
+                  reinterpret_cast<float2*>(gnf + GnfSmem<256>::OFF_XCHG), gb, gb + 256,
+                  reinterpret_cast<uint64_t*>(gnf + GnfSmem<256>::OFF_BAR), 0u, 0u, ptx::cluster_ctarank(), warp, 0};
+        epi_tile<256, 1, true, true, false, true, false, true, false, false, true>(cx, gx.pstat, quad);
+        gnf_fold<256, 1>(p.g, gx, lane);
+        epi_tile_gnf_dual_pass2<256, 1>(cx, gx);
+      } else {
+        epi_tile<256, 1, true, true, false, true, false, true, false>(cx);
+      }
     } else {
       // O / rowsum -> fp16 -> swizzled staging (this warp: 32 rows x 128 columns) -> full-line global stores
       const uint32_t stg = ptx::smem_u32(sQ) + warp * (32 * 256);
@@ -348,6 +370,21 @@ int attn_fused_launch(const AttnOp* op, int batch, cudaStream_t st) {
     a.bias3 = op->bias3;
     a.g.residual = op->residual; a.g.out32 = op->out32; a.g.colstats = op->colstats;
     a.g.ldo = op->C; a.g.scale = op->out_scale; a.g.M = batch * op->T; a.g.N = op->C;
+    if (op->gn_gamma != nullptr) {
+      // + act(GroupNorm(out32)) for the next block: the two CTAs of an image form a cluster and exchange their statistics
+      if (!op->gn_beta || !op->gn_out16 || op->gn_groups <= 0 || (op->C / op->gn_groups != 8 && op->C / op->gn_groups != 4 && op->C / op->gn_groups != 16))
+        return -4;
+      a.g.gn_gamma = op->gn_gamma; a.g.gn_beta = op->gn_beta; a.g.gn_eps = op->gn_eps; a.g.gn_cpg = op->C / op->gn_groups;
+      a.g.gn_silu = op->gn_silu; a.g.gn_rpi = op->T; a.g.gn_xc = 2; a.g.gn_xg = nullptr; a.g.out16 = op->gn_out16;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * batch); cfg.blockDim = dim3(AT_THREADS); cfg.dynamicSmemBytes = AT_SMEM; cfg.stream = st;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = pdl_attr(at, 1);
+      if (cudaLaunchKernelEx(&cfg, attn256_kernel<true>, op->tm_qkv, op->tm_w3, a) != cudaSuccess) return -3;
+      return 0;
+    }
     if (launch_k(attn256_kernel<true>, dim3(2 * batch), dim3(AT_THREADS), (size_t)AT_SMEM, st, op->tm_qkv, op->tm_w3, a) != cudaSuccess) return -3;
     return 0;
   }

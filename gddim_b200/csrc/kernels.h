@@ -114,6 +114,10 @@ struct AttnOp {
   float* out32;        // [B, T, C]
   float* colstats;     // [B*T/32][2][C]
   float out_scale;
+  // optional (with w3): out16n = act(GroupNorm(out32)) -- the GroupNorm_0 of the ResBlock that consumes the attention
+  // block's output (layerspp.py:196), applied by this kernel's epilogue (dual GroupNorm epilogue, gemm_epilogue.cuh)
+  const float* gn_gamma; const float* gn_beta; float gn_eps; int gn_groups; int gn_silu;
+  __half* gn_out16;    // [B, T, C]
   CUtensorMap tm_qkv, tm_w3;  // filled by attn_fused_prepare
   int prepared;
 };

@@ -286,18 +286,25 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
   static const bool no_gnf0 = [] { const char* e = getenv("GDDIM_NO_GNF0"); const char* e1 = getenv("GDDIM_NO_GNF");
                                    return (e && e[0] == '1') || (e1 && e1[0] == '1'); }();
   const int groups0 = std::min(Cin / 4, 32);
-  bool fuse0 = false;
+  bool fuse0 = false, fuse_attn = false;
   if (!no_gnf0 && in2 == nullptr && rs == RS_NONE && !need_sc && in1.prod_op >= 0 && in1.prod_op == (int)ops_.size() - 1 &&
       last_flush_at_ < ops_.size() && gemm_gnf_supported(H, W, Cin, groups0)) {
     const Op& po = ops_[in1.prod_op];
     const GemmOp& pg = po.gemm;
+    if (po.kind == OP_ATTN_FUSED) {
+      // producer = the fused attention + projection kernel (one image = a cluster of two CTAs)
+      const AttnOp& pa = po.attn;
+      fuse_attn = pa.w3 != nullptr && pa.out32 == in1.p && pa.gn_gamma == nullptr && pa.C == Cin && pa.T == H * W &&
+                  (Cin / groups0 == 4 || Cin / groups0 == 8 || Cin / groups0 == 16);
+    }
     int pk = 0;
-    for (int sgi = 0; sgi < pg.nseg; ++sgi) pk += pg.seg[sgi].taps * pg.seg[sgi].c;
+    if (po.kind == OP_GEMM)
+      for (int sgi = 0; sgi < pg.nseg && sgi < 2; ++sgi) pk += pg.seg[sgi].taps * pg.seg[sgi].c;
     fuse0 = po.kind == OP_GEMM && pg.epi == EPI_LINEAR && pg.out32 == in1.p && pg.out16 == nullptr && pg.rowscale == nullptr &&
             pg.n_store == 0 && pg.w_batch_stride == 0 && pg.N == Cin && pg.ldo == Cin && pg.H == H && pg.W == W &&
             !po.out_is_external && gnf_pays(H, W, pk, true);
   }
-  hold_pending_ = fuse0;                 // a1 becomes an output of the producer: it must not reuse what that op still reads
+  hold_pending_ = fuse0 || fuse_attn;    // a1 becomes an output of the producer: it must not reuse what that op still reads
   T16 a1 = new16(Cin, Ho, Wo);
   hold_pending_ = false;
   T16 x16; x16.p = nullptr;
@@ -308,6 +315,11 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     pg.epi = EPI_GNF;
     pg.out16 = a1.p;
     pg.gn_gamma = gn0.first; pg.gn_beta = gn0.second; pg.gn_eps = 1e-6f; pg.gn_groups = groups0; pg.gn_silu = 1;
+    po.tag += "+gn0";
+  } else if (fuse_attn) {
+    Op& po = ops_[in1.prod_op];
+    po.attn.gn_gamma = gn0.first; po.attn.gn_beta = gn0.second; po.attn.gn_eps = 1e-6f; po.attn.gn_groups = groups0;
+    po.attn.gn_silu = 1; po.attn.gn_out16 = a1.p;
     po.tag += "+gn0";
   } else {
     add_norm(in1, in2, gn0.first, gn0.second, true, rs, &a1, need_sc ? &x16 : nullptr, s.prefix + "gn0");
@@ -509,6 +521,7 @@ UNet::T32 UNet::attnblock(Scope& top, const T32& x) {
     op.attn.colstats = out_fused.stats; op.attn.out_scale = out_scale;
     if (out_fused.stats != nullptr || dry_) {
       out_fused.stats_valid = out_fused.stats != nullptr;
+      out_fused.prod_op = (int)ops_.size();
       ops_.push_back(op);
       proj_fused = true;
     } else {
@@ -936,6 +949,7 @@ int UNet::finalize() {
       } else if (op.kind == OP_ATTN_FUSED) {
         op.attn.reverse = zigzag ? !dir_of(op.attn.qkv) : 0;
         if (op.attn.out16) wdir[op.attn.out16] = op.attn.reverse;
+        if (op.attn.gn_out16) wdir[op.attn.gn_out16] = op.attn.reverse;
         if (op.attn.out32) wdir[op.attn.out32] = op.attn.reverse;
       } else {
         if (op.f_out) wdir[op.f_out] = 0;
