@@ -3,7 +3,8 @@
 Mirrors `CLD` (sde_lib.py:45-319) and `from_config` (321-331).  Returned arrays are numpy float32 unless
 x64=True (the reference runs with jax_enable_x64 = config.model.x64 = False).  The pickle cache of the
 reference (`used_cache`) is not reproduced: tables are recomputed (sub-second).
-`LambdaSDE` / `LSDE` (334-519) are SURVEY.md 8(f) "next" rows and raise NotImplementedError.
+`LambdaSDE` (334-404) and `LSDE` (407-519) are host-table classes over the same library (stochastic gDDIM and
+the L-parameterised score); both are pinned to the reference's own classes in tests/test_ref_golden.py.
 """
 import ctypes as C
 

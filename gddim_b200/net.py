@@ -250,10 +250,10 @@ class State:
     self.params_ema, self.model_state, self.step = params_ema, model_state, step
 
 
-def init_model(rng, config, cld=True, nondegenerate=False):
+def init_model(rng, config, cld=True, nondegenerate=False, precise=False):
   """models/utils.py:109-125: returns (model, init_model_state, initial_params).  `rng` is an int seed or
-  None (JAX's threefry stream is not reproduced; see gddim_b200/params.py)."""
-  model = ScoreNet(config, cld=cld)
+  None (JAX's threefry stream is not reproduced; see gddim_b200/params.py).  precise: see ScoreNet."""
+  model = ScoreNet(config, cld=cld, precise=precise)
   seed = 1234 if rng is None else int(np.asarray(rng).ravel()[-1])
   params = model.init_params(seed=seed, nondegenerate=nondegenerate)
   return model, None, params

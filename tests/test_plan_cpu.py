@@ -22,11 +22,18 @@ def test_deep_cifar_plan_uses_the_fused_attention_block():
   # nothing of the unfused chain; 4x4 (16 tokens): the CUDA-core attention kernel between plain GEMMs
   for i in range(10):
     tags = [t.split("/", 1)[1] for t, _ in plan if t.startswith(f"AttnBlockpp_{i}/")]
-    assert tags == (["gn", "qkv", "attn_small", "proj"] if i == 8 else ["gn_coef", "gn_qkv", "attn_proj_fused"]), (i, tags)
+    # blocks 0..6 are followed by a ResBlock at the same resolution: the fused kernel also emits that block's
+    # act(GroupNorm_0(.)) ("+gn0"); block 7 feeds the FIR-downsampling block, block 9 the upsampling block
+    fused = "attn_proj_fused+gn0" if i < 7 else "attn_proj_fused"
+    assert tags == (["gn", "qkv", "attn_small", "proj"] if i == 8 else ["gn_coef", "gn_qkv", fused]), (i, tags)
   assert kinds["gn_qkv"] == 9 and kinds["attn_fused"] == 9 and kinds["transpose_v"] == 0 and kinds["softmax_rows"] == 0
   assert kinds["small_attn"] == 1
   # every convolution / NIN is a tcgen05 GEMM op; stem and head are GEMM ops too (no CUDA-core conv kernels in the plan)
   assert kinds["stem"] == 0 and kinds["head"] == 0 and kinds["gemm"] > 150
+  # GroupNorm + swish between conv1 and conv2 of a ResBlock is applied by conv1's epilogue wherever the measured
+  # per-layer rule (unet.cpp gnf_pays) allows; GroupNorm_0 of 24 blocks comes from the producer of their input
+  tags = collections.Counter(t.split("/", 1)[1] for t, _ in plan if "/" in t)
+  assert tags["conv1_gn1"] == 58 and tags["gn1"] == 18 and tags["conv2+gn0"] + tags["conv+gn0"] + tags["attn_proj_fused+gn0"] == 24
   # the plan is a property of the architecture, not of the batch
   assert [t for t, _ in _plan(configs.cld_accr_dcifar10(), batch=8)] == [t for t, _ in plan]
 
