@@ -26,6 +26,8 @@ for (H, cin, cout) in [(32, 128, 128), (32, 256, 128), (16, 256, 256), (16, 512,
   res["linear_f16out"] = timeit(lambda: ops.conv_gemm(a, w, cout, bias=bias, out_fp32=False, out_fp16=True))
   res["gnf"] = timeit(lambda: ops.conv_gemm(a, w, cout, bias=bias, gn=(gamma, beta, 32, True)))
   res["gnf_nosilu"] = timeit(lambda: ops.conv_gemm(a, w, cout, bias=bias, gn=(gamma, beta, 32, False)))
+  res["linear_res"] = timeit(lambda: ops.conv_gemm(a, w, cout, bias=bias, residual=x32, scale=0.7071))
+  res["gnf_dual"] = timeit(lambda: ops.conv_gemm(a, w, cout, bias=bias, residual=x32, scale=0.7071, gn=(gamma, beta, 32, True, 1e-6, True)))
   res["gn_pass"] = timeit(lambda: ops.group_norm(x32, gamma, beta, silu=True))
   print(f"H={H:2d} {cin}->{cout} K={9*cin}: " + "  ".join(f"{k}={v:6.1f}us" for k, v in res.items()) +
         f"   linear {fl/res['linear']*1e-6:6.0f} TF/s  gnf {fl/res['gnf']*1e-6:6.0f} TF/s", flush=True)
