@@ -295,7 +295,7 @@ attn256_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant
                   reinterpret_cast<uint64_t*>(gnf + GnfSmem<256>::OFF_BAR), 0u, 0u, ptx::cluster_ctarank(), warp, 0};
         epi_tile<256, 1, true, true, false, true, false, true, false, false, true>(cx, gx.pstat, quad);
         gnf_fold<256, 1>(p.g, gx, lane);
-        epi_tile_gnf_dual_pass2<256, 1>(cx, gx);
+        epi_tile_gnf_dual_pass2<256, 1, true>(cx, gx);
       } else {
         epi_tile<256, 1, true, true, false, true, false, true, false>(cx);
       }

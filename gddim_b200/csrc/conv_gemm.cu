@@ -262,7 +262,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           float b = 0.f;
           if (p.bias != nullptr) b += __ldg(p.bias + nt * BLOCK_N + j);
           if (p.bias2 != nullptr) b += __ldg(p.bias2 + nt * BLOCK_N + j);
-          bias_s[j] = b;
+          bias_s[j] = p.out32 != nullptr ? b : b * p.scale;      // (dual mode: the linear epilogue of pass 1 scales it itself)
           gb[j] = __ldg(p.gn_gamma + nt * BLOCK_N + j);
           gb[BLOCK_N + j] = __ldg(p.gn_beta + nt * BLOCK_N + j);
         }
@@ -288,9 +288,11 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
           }
           tmem_released = true;
           gnf_fold<BLOCK_N, MT>(p, gx, lane);
-          epi_tile_gnf_dual_pass2<BLOCK_N, MT>(cx, gx);
+          if (full) epi_tile_gnf_dual_pass2<BLOCK_N, MT, true>(cx, gx); else epi_tile_gnf_dual_pass2<BLOCK_N, MT, false>(cx, gx);
+        } else if ((long long)(mt + 1) * MT * BLOCK_M <= (long long)p.M) {
+          epi_tile_gnf<BLOCK_N, MT, true>(cx, gx);
         } else {
-          epi_tile_gnf<BLOCK_N, MT>(cx, gx);
+          epi_tile_gnf<BLOCK_N, MT, false>(cx, gx);
         }
       } else if (EPI == EPI_LINEAR) {
         // TMEM -> registers (thread = row) -> padded smem -> registers (8 lanes = one 32-column row segment),

@@ -9,10 +9,12 @@
 
 #ifdef GDDIM_ABLATE
 #define GDDIM_DBG_STORE(p) ((p).dbg != 2)
+#define GDDIM_DBG_IS(p, k) ((p).dbg == (k))
 // clock64 stamp `slot` of tile `t` (CTA 0, one lane): timeline experiments only
 #define GDDIM_STAMP(p, cond, t, slot) do { if ((p).dbg_clk && blockIdx.x == 0 && (cond) && (t) < 16) (p).dbg_clk[(t) * 16 + (slot)] = clock64(); } while (0)
 #else
 #define GDDIM_DBG_STORE(p) true
+#define GDDIM_DBG_IS(p, k) false
 #define GDDIM_STAMP(p, cond, t, slot) do { } while (0)
 #endif
 
@@ -347,19 +349,16 @@ __device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ float gnf_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// swish of four values with ONE reciprocal: 1/d_i = (1 / (d0 d1 d2 d3)) * (product of the other three).  The epilogue is
-// bound by the special-function pipe (16 results per clock and SM: ex2 + rcp per element = 4096 cycles per 256 x 128
-// tile); sharing the reciprocal cuts it to 1.25 per element.  x is clamped at -20 (swish(-20) = -4e-8 rounds to zero in
-// fp16) so that the product of four (1 + e^-x) <= 4.9e8 stays far below the fp32 range.
-__device__ __forceinline__ void gnf_silu4(float4& v) {
-  const float x0 = fmaxf(v.x, -20.f), x1 = fmaxf(v.y, -20.f), x2 = fmaxf(v.z, -20.f), x3 = fmaxf(v.w, -20.f);
-  const float d0 = 1.0f + __expf(-x0), d1 = 1.0f + __expf(-x1), d2 = 1.0f + __expf(-x2), d3 = 1.0f + __expf(-x3);
-  const float p01 = d0 * d1, p23 = d2 * d3;
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
-  const float r01 = r * p23, r23 = r * p01;
-  v.x = x0 * (r01 * d1); v.y = x1 * (r01 * d0); v.z = x2 * (r23 * d3); v.w = x3 * (r23 * d2);
+// y * sigmoid(y) from y and t = -log2(e) * y (both formed by independent FMAs off the accumulator): ex2, add, rcp, mul --
+// four issue slots per value, two of them on the special-function pipe.  (A variant sharing one reciprocal between four
+// values -- 1.25 special-function results but 7.5 issue slots per value -- measured 2 - 3 % slower: the epilogue is bound
+// by instruction issue, not by the special-function pipe.)  No clamp is
+// needed: t -> +inf gives ex2 = inf, rcp = 0, y * 0 = 0.
+__device__ __forceinline__ float gnf_silu_t(float y, float t) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return y * r;
 }
 // asynchronous remote store that completes `8` bytes on the destination CTA's mbarrier (no fence on the sender side:
 // a release at cluster scope would first drain this thread's outstanding global stores, measured ~5 k cycles per tile)
@@ -419,7 +418,8 @@ __device__ __forceinline__ int gnf_holder_index(int lane, bool* writer) {
 
 // pass 1 of one 32 x 32 chunk held as thread = row: v = acc * scale + bias, per-(group, stat) partials (gnf_chunk_partials),
 // then the lane reduction (gnf_chunk_reduce) -- split in two so that the TMEM load of the next chunk can be issued in between
-template <int NV>
+// (the bias row in shared memory is already multiplied by `scale`; FULL: every row of the tile exists)
+template <int NV, bool FULL>
 __device__ __forceinline__ void gnf_chunk_partials(const uint32_t (&r)[32], uint32_t bias_base, float scale, bool row_ok,
                                                    float (&a)[16]) {
   constexpr int CPG = 64 / NV;                        // NV = 2 * groups per 32-column chunk
@@ -428,10 +428,10 @@ __device__ __forceinline__ void gnf_chunk_partials(const uint32_t (&r)[32], uint
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     float4 b = lds128(bias_base + j4 * 16);
-    const float v0 = row_ok ? fmaf(__uint_as_float(r[4 * j4 + 0]), scale, b.x * scale) : 0.f;
-    const float v1 = row_ok ? fmaf(__uint_as_float(r[4 * j4 + 1]), scale, b.y * scale) : 0.f;
-    const float v2 = row_ok ? fmaf(__uint_as_float(r[4 * j4 + 2]), scale, b.z * scale) : 0.f;
-    const float v3 = row_ok ? fmaf(__uint_as_float(r[4 * j4 + 3]), scale, b.w * scale) : 0.f;
+    const float v0 = (FULL || row_ok) ? fmaf(__uint_as_float(r[4 * j4 + 0]), scale, b.x) : 0.f;
+    const float v1 = (FULL || row_ok) ? fmaf(__uint_as_float(r[4 * j4 + 1]), scale, b.y) : 0.f;
+    const float v2 = (FULL || row_ok) ? fmaf(__uint_as_float(r[4 * j4 + 2]), scale, b.z) : 0.f;
+    const float v3 = (FULL || row_ok) ? fmaf(__uint_as_float(r[4 * j4 + 3]), scale, b.w) : 0.f;
     const int g = (4 * j4) / CPG;                     // compile-time after unrolling
     a[2 * g] += (v0 + v1) + (v2 + v3);
     a[2 * g + 1] = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, a[2 * g + 1]))));
@@ -556,7 +556,7 @@ __device__ __forceinline__ void gnf_fold(const GemmArgs& p, const GnfCtx& gx, in
   GDDIM_STAMP(p, stamp, gx.tile_seq, 5);
 }
 
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, bool FULL>
 __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, const GnfCtx& gx) {
   constexpr int RS = 32;
   constexpr int NCH = BLOCK_N / 32;
@@ -589,7 +589,7 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
   // ---------------- pass 1: per-warp (segment, group) sums of v and v^2 ----------------
   // thread = accumulator row: no staging through shared memory, the lanes are reduced with recursive-halving shuffles;
   // the TMEM load of chunk q + 1 is in flight while the partials of chunk q are reduced
-  {
+  if (!GDDIM_DBG_IS(p, 6)) {
     const long long mrow = mwarp + lane;                         // this thread's row in sub-tile 0
     const uint32_t bias_row = ptx::smem_u32(cx.bias_s);
     if (cx.group < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (cx.group / NCH) * BLOCK_N + (cx.group % NCH) * 32, r);
@@ -601,9 +601,9 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
       const int gi0 = c0 / cpg;
       float a[16];
       ptx::tmem_ld_wait();
-      if (cpg == 4) gnf_chunk_partials<16>(r, bias_row + c0 * 4, scale, row_ok, a);
-      else if (cpg == 8) gnf_chunk_partials<8>(r, bias_row + c0 * 4, scale, row_ok, a);
-      else gnf_chunk_partials<4>(r, bias_row + c0 * 4, scale, row_ok, a);
+      if (cpg == 4) gnf_chunk_partials<16, FULL>(r, bias_row + c0 * 4, scale, row_ok, a);
+      else if (cpg == 8) gnf_chunk_partials<8, FULL>(r, bias_row + c0 * 4, scale, row_ok, a);
+      else gnf_chunk_partials<4, FULL>(r, bias_row + c0 * 4, scale, row_ok, a);
       const int qn = q + EPI_GROUPS;
       if (qn < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (qn / NCH) * BLOCK_N + (qn % NCH) * 32, r);
       if (cpg == 4) {
@@ -619,7 +619,8 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
   gnf_fold<BLOCK_N, MT>(p, gx, lane);
   // ---------------- pass 2: normalise, activate, store fp16 ----------------
   const long long ldo = p.ldo;
-  if (cx.group < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (cx.group / NCH) * BLOCK_N + (cx.group % NCH) * 32, r);
+  if (GDDIM_DBG_IS(p, 8)) return;
+  if (cx.group < NQ && !GDDIM_DBG_IS(p, 4)) ptx::tmem_ld_32x32b_x32(cx.taddr + (cx.group / NCH) * BLOCK_N + (cx.group % NCH) * 32, r);
 #pragma unroll 1
   for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
     const int mi = q / NCH, c0 = (q % NCH) * 32;
@@ -631,34 +632,46 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
     const int img0 = (p.gn_xc > 1 || rpi >= TR) ? 0 : row_off / rpi;
     const float2 st0 = gx.gstat[img0 * GNF_GMAX + gi];
     const float2 st1 = split ? gx.gstat[(img0 + 1) * GNF_GMAX + gi] : st0;
+    // y = (acc * scale + bias * scale) * A + O = acc * (scale * A) + (bias_s * A + O) with A = rstd * gamma, O = beta - mean * A
+    // (bias_s holds bias * scale); t = -log2(e) * y comes from a second FMA off the accumulator
+    constexpr float NL2E = -1.4426950408889634f;
+    float4 bsum = lds128(bias_a + c0 * 4);
     float4 a0, o0, a1, o1;
     a0.x = st0.y * g4.x; a0.y = st0.y * g4.y; a0.z = st0.y * g4.z; a0.w = st0.y * g4.w;
-    o0.x = b4.x - st0.x * a0.x; o0.y = b4.y - st0.x * a0.y; o0.z = b4.z - st0.x * a0.z; o0.w = b4.w - st0.x * a0.w;
-    a1.x = st1.y * g4.x; a1.y = st1.y * g4.y; a1.z = st1.y * g4.z; a1.w = st1.y * g4.w;
-    o1.x = b4.x - st1.x * a1.x; o1.y = b4.y - st1.x * a1.y; o1.z = b4.z - st1.x * a1.z; o1.w = b4.w - st1.x * a1.w;
+    o0.x = fmaf(bsum.x - st0.x, a0.x, b4.x); o0.y = fmaf(bsum.y - st0.x, a0.y, b4.y);
+    o0.z = fmaf(bsum.z - st0.x, a0.z, b4.z); o0.w = fmaf(bsum.w - st0.x, a0.w, b4.w);
+    a0.x *= scale; a0.y *= scale; a0.z *= scale; a0.w *= scale;
+    a1 = a0; o1 = o0;
+    if (split) {
+      a1.x = st1.y * g4.x; a1.y = st1.y * g4.y; a1.z = st1.y * g4.z; a1.w = st1.y * g4.w;
+      o1.x = fmaf(bsum.x - st1.x, a1.x, b4.x); o1.y = fmaf(bsum.y - st1.x, a1.y, b4.y);
+      o1.z = fmaf(bsum.z - st1.x, a1.z, b4.z); o1.w = fmaf(bsum.w - st1.x, a1.w, b4.w);
+      a1.x *= scale; a1.y *= scale; a1.z *= scale; a1.w *= scale;
+    }
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j) sts128(stg_w + ((j ^ wx) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
     // the registers are free again: the TMEM load of the next chunk overlaps the normalise / swish / store work below
     {
       const int qn = q + EPI_GROUPS;
-      if (qn < NQ) ptx::tmem_ld_32x32b_x32(cx.taddr + (qn / NCH) * BLOCK_N + (qn % NCH) * 32, r);
+      if (qn < NQ && !GDDIM_DBG_IS(p, 4)) ptx::tmem_ld_32x32b_x32(cx.taddr + (qn / NCH) * BLOCK_N + (qn % NCH) * 32, r);
     }
     __syncwarp();
     const long long mb = mwarp + (long long)mi * BLOCK_M + rsub;
     const int n0 = cx.n_tile0 + c0 + c4;
-    float4 bsum = lds128(bias_a + c0 * 4);
-    bsum.x *= scale; bsum.y *= scale; bsum.z *= scale; bsum.w *= scale;
     __half* o16 = p.out16 + mb * ldo + n0;
+    const bool silu = p.gn_silu != 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 v = lds128(((i & 1) ? stg_r1 : stg_r0) + (i >> 1) * 8 * RS * 4);
-      v.x = fmaf(v.x, scale, bsum.x); v.y = fmaf(v.y, scale, bsum.y);
-      v.z = fmaf(v.z, scale, bsum.z); v.w = fmaf(v.w, scale, bsum.w);
+      const float4 acc = lds128(((i & 1) ? stg_r1 : stg_r0) + (i >> 1) * 8 * RS * 4);
       const float4 aa = (i >= 4) ? a1 : a0, oo = (i >= 4) ? o1 : o0;
-      v.x = fmaf(v.x, aa.x, oo.x); v.y = fmaf(v.y, aa.y, oo.y); v.z = fmaf(v.z, aa.z, oo.z); v.w = fmaf(v.w, aa.w, oo.w);
-      if (p.gn_silu) gnf_silu4(v);
-      if (mb + i * 4 < p.M) {
+      float4 v;
+      v.x = fmaf(acc.x, aa.x, oo.x); v.y = fmaf(acc.y, aa.y, oo.y); v.z = fmaf(acc.z, aa.z, oo.z); v.w = fmaf(acc.w, aa.w, oo.w);
+      if (silu && !GDDIM_DBG_IS(p, 5)) {
+        v.x = gnf_silu_t(v.x, fmaf(acc.x, aa.x * NL2E, oo.x * NL2E)); v.y = gnf_silu_t(v.y, fmaf(acc.y, aa.y * NL2E, oo.y * NL2E));
+        v.z = gnf_silu_t(v.z, fmaf(acc.z, aa.z * NL2E, oo.z * NL2E)); v.w = gnf_silu_t(v.w, fmaf(acc.w, aa.w * NL2E, oo.w * NL2E));
+      }
+      if ((FULL || mb + i * 4 < p.M) && !GDDIM_DBG_IS(p, 7)) {
         __half2 h0 = __floats2half2_rn(v.x, v.y);
         __half2 h1 = __floats2half2_rn(v.z, v.w);
         uint2 pk;
@@ -678,11 +691,12 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
 // parameters of the NEXT block's GroupNorm_0 (layerspp.py:196) -- the consumer's normalisation pass disappears.
 // Pass 1 is the ordinary linear epilogue (epi_tile with the GNP hook); the accumulator is not needed afterwards, pass 2
 // re-reads v from out32: every lane reads back exactly the elements it stored itself (program order, L2 hits).
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, bool FULL>
 __device__ __forceinline__ void epi_tile_gnf_dual_pass2(const EpiCtx<BLOCK_N, MT>& cx, const GnfCtx& gx) {
   constexpr int NCH = BLOCK_N / 32;
   constexpr int NQ = MT * NCH;
   constexpr int TR = MT * BLOCK_M;
+  constexpr float NL2E = -1.4426950408889634f;
   const GemmArgs& p = cx.p;
   const int lane = cx.lane;
   const int rsub = lane >> 3;
@@ -690,6 +704,7 @@ __device__ __forceinline__ void epi_tile_gnf_dual_pass2(const EpiCtx<BLOCK_N, MT
   const int quad = gx.warp & 3;
   const int cpg = p.gn_cpg, rpi = p.gn_rpi;
   const bool split = rpi < 32;
+  const bool silu = p.gn_silu != 0;
   const long long ldo = p.ldo;
 #pragma unroll 1
   for (int q = cx.group; q < NQ; q += EPI_GROUPS) {
@@ -700,27 +715,33 @@ __device__ __forceinline__ void epi_tile_gnf_dual_pass2(const EpiCtx<BLOCK_N, MT
     float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      v[i] = (mb + i * 4 < p.M) ? __ldcg(reinterpret_cast<const float4*>(src + (long long)(i * 4) * ldo)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i] = (FULL || mb + i * 4 < p.M) ? __ldcg(reinterpret_cast<const float4*>(src + (long long)(i * 4) * ldo)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 g4 = *reinterpret_cast<const float4*>(gx.gam + c0 + c4);
     const float4 b4 = *reinterpret_cast<const float4*>(gx.bet + c0 + c4);
     const int gi = (c0 + c4) / cpg;
     const int row_off = mi * BLOCK_M + quad * 32;
     const int img0 = (p.gn_xc > 1 || rpi >= TR) ? 0 : row_off / rpi;
     const float2 st0 = gx.gstat[img0 * GNF_GMAX + gi];
-    const float2 st1 = split ? gx.gstat[(img0 + 1) * GNF_GMAX + gi] : st0;
     float4 a0, o0, a1, o1;
     a0.x = st0.y * g4.x; a0.y = st0.y * g4.y; a0.z = st0.y * g4.z; a0.w = st0.y * g4.w;
     o0.x = b4.x - st0.x * a0.x; o0.y = b4.y - st0.x * a0.y; o0.z = b4.z - st0.x * a0.z; o0.w = b4.w - st0.x * a0.w;
-    a1.x = st1.y * g4.x; a1.y = st1.y * g4.y; a1.z = st1.y * g4.z; a1.w = st1.y * g4.w;
-    o1.x = b4.x - st1.x * a1.x; o1.y = b4.y - st1.x * a1.y; o1.z = b4.z - st1.x * a1.z; o1.w = b4.w - st1.x * a1.w;
+    a1 = a0; o1 = o0;
+    if (split) {
+      const float2 st1 = gx.gstat[(img0 + 1) * GNF_GMAX + gi];
+      a1.x = st1.y * g4.x; a1.y = st1.y * g4.y; a1.z = st1.y * g4.z; a1.w = st1.y * g4.w;
+      o1.x = b4.x - st1.x * a1.x; o1.y = b4.y - st1.x * a1.y; o1.z = b4.z - st1.x * a1.z; o1.w = b4.w - st1.x * a1.w;
+    }
     __half* o16 = p.out16 + mb * ldo + n0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 aa = (i >= 4) ? a1 : a0, oo = (i >= 4) ? o1 : o0;
       float4 y;
       y.x = fmaf(v[i].x, aa.x, oo.x); y.y = fmaf(v[i].y, aa.y, oo.y); y.z = fmaf(v[i].z, aa.z, oo.z); y.w = fmaf(v[i].w, aa.w, oo.w);
-      if (p.gn_silu) gnf_silu4(y);
-      if (mb + i * 4 < p.M) {
+      if (silu) {
+        y.x = gnf_silu_t(y.x, fmaf(v[i].x, aa.x * NL2E, oo.x * NL2E)); y.y = gnf_silu_t(y.y, fmaf(v[i].y, aa.y * NL2E, oo.y * NL2E));
+        y.z = gnf_silu_t(y.z, fmaf(v[i].z, aa.z * NL2E, oo.z * NL2E)); y.w = gnf_silu_t(y.w, fmaf(v[i].w, aa.w * NL2E, oo.w * NL2E));
+      }
+      if (FULL || mb + i * 4 < p.M) {
         __half2 h0 = __floats2half2_rn(y.x, y.y);
         __half2 h1 = __floats2half2_rn(y.z, y.w);
         uint2 pk;

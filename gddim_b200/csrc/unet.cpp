@@ -252,17 +252,14 @@ static GemmOp make_gemm(int B, int H, int W) {
 }
 
 // Where the GroupNorm-fused epilogue pays (measured per layer on B200 at batch 256, profiles/r02_gnf_per_op.txt): the
-// epilogue gets two passes and a swish, which is free while the main loop is longer than the epilogue (K >= 2304 at
-// 32x32, everything at 16x16 where a CTA pair owns an image) and costs more than the removed GroupNorm pass where the
-// epilogue is already the bottleneck (K = 1152 at 32x32: 256 x 128 tiles with a 9 k-cycle main loop; K = 4608 at 8x8).
-// GDDIM_GNF_ALL=1 fuses wherever the geometry allows (A/B).
+// epilogue gets two passes and a swish.  That is hidden behind the next tile's main loop where a CTA runs several tiles
+// (+3 us on a 64 us convolution at 16x16, +17 .. +19 us at 32x32) and always cheaper than the 45 - 53 us GroupNorm pass
+// it removes; the single-wave 8x8 layers (one tile per CTA: the epilogue is fully exposed) gain 4 us at K = 2304 and lose
+// 2 us at K = 4608, which therefore keep the separate 12 us pass.  GDDIM_GNF_ALL=1 fuses wherever the geometry allows.
 static bool gnf_pays(int H, int W, int K, bool dual) {
   static const bool all = [] { const char* e = getenv("GDDIM_GNF_ALL"); return e && e[0] == '1'; }();
   if (all) return true;
-  const int rpi = H * W;
-  if (rpi >= 1024) return !dual && K >= 2304;
-  if (rpi == 64) return dual || K <= 2304;
-  return true;
+  return !(H * W == 64 && !dual && K >= 4608);
 }
 
 // ---- ResnetBlockBigGANpp (layerspp.py:180-227) ------------------------------------------------------------
