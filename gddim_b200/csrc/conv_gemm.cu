@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmH, const GemmArgs p) {
   pdl_launch_dependents();   // the wait is after the prologue
+  GDDIM_STAMP(p, threadIdx.x == 0, 0, 11);
   constexpr bool GNF = EPI == EPI_GNF;
   using L = SmemLayout<BLOCK_N, MT, CG, GNF ? GnfSmem<BLOCK_N>::BYTES : 0>;
   static_assert(CG == 1 || (EPI != EPI_SOFTMAX && (BLOCK_N / CG) % 16 == 0), "CTA pairs: linear / GNF epilogue only");
@@ -91,6 +92,13 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
       ptx::mbar_init(reinterpret_cast<uint64_t*>(gnf_smem + GnfSmem<BLOCK_N>::OFF_BAR) + 1, 1);
     }
     ptx::fence_mbar_init();
+    if (p.pf_bytes > 0) {
+      const long long per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 127) & ~127LL;
+      long long off = (long long)blockIdx.x * per;
+      const long long end = off + per < p.pf_bytes ? off + per : p.pf_bytes;
+      for (; off < end; off += 8192)
+        ptx::prefetch_l2_bulk(static_cast<const char*>(p.pf_ptr) + off, (uint32_t)(end - off < 8192 ? end - off : 8192));
+    }
   }
   if (warp == MMA_WARP) {
     if (CG == 2) { ptx::tmem_alloc_2cta(tmem_slot, TMEM_COLS); ptx::tmem_relinquish_2cta(); }
@@ -102,6 +110,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
   if (clustered) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GDDIM_STAMP(p, threadIdx.x == 0, 0, 12);
 
   // work unit = CG vertically adjacent CTA tiles x one N tile; CTA `cta_rank` of the pair owns M tile unit_m * CG + rank
   const int unit_m = (p.m_tiles + CG - 1) / CG;
@@ -215,6 +224,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
         for (int g = 0; g < slots; ++g) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
+          GDDIM_STAMP(p, sw == 0 && g == 0, mma_seq, 15);
           const uint32_t slot = ptx::smem_u32(smem + stage * stage_bytes);
           if (halo_seg) {
             // y-shift dyi = rows [dyi * W, dyi * W + 128 * MT) of the halo box
@@ -388,6 +398,7 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
 
   ptx::tc_fence_before();
   if (clustered) ptx::cluster_sync(); else __syncthreads();     // pair / cluster: no CTA may retire while a peer still works
+  GDDIM_STAMP(p, threadIdx.x == 0, 0, 13);
   if (warp == MMA_WARP) {
     ptx::tc_fence_after();
     if (CG == 2) ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS); else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -928,6 +939,11 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     a.colstats = op->colstats;
     a.n_store = op->n_store;
     a.reverse = op->reverse;
+    {
+      static int wpf = -1;                    // GDDIM_NO_WPF=1: A/B switch for the weight prefetch
+      if (wpf < 0) { const char* e = getenv("GDDIM_NO_WPF"); wpf = (e && e[0] == '1') ? 0 : 1; }
+      if (wpf && op->w_batch_stride == 0) { a.pf_ptr = op->w; a.pf_bytes = (long long)op->N * op->w_ld * 2; }
+    }
 #ifdef GDDIM_ABLATE      // timing-only epilogue ablations (results INVALID): compile with -DGDDIM_ABLATE, never in the product build
     {
       static int dbg = -1;
@@ -947,12 +963,12 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
         long long h[256];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
-        long long t0 = h[8];
-        fprintf(stderr, "CLK timeline CTA 0 (cycles since the MMA thread first waited):\n");
+        long long t0 = h[11] ? h[11] : h[8];
+        fprintf(stderr, "CLK timeline CTA 0 (cycles since kernel entry): prologue done %lld, kernel end %lld\n", h[12] - t0, h[13] - t0);
         for (int t = 0; t < 10; ++t) {
           if (h[t * 16 + 8] == 0) break;
-          fprintf(stderr, " tile %d  mma: wait %lld..%lld issue_done %lld | epi: wait %lld..%lld p1 %lld bar %lld fold %lld bar %lld p2 %lld\n", t,
-                  h[t * 16 + 8] - t0, h[t * 16 + 9] - t0, h[t * 16 + 10] - t0, h[t * 16 + 0] - t0, h[t * 16 + 1] - t0,
+          fprintf(stderr, " tile %d  mma: first operands %lld wait %lld..%lld issue_done %lld | epi: wait %lld..%lld p1 %lld bar %lld fold %lld bar %lld p2 %lld\n", t,
+                  h[t * 16 + 15] - t0, h[t * 16 + 8] - t0, h[t * 16 + 9] - t0, h[t * 16 + 10] - t0, h[t * 16 + 0] - t0, h[t * 16 + 1] - t0,
                   h[t * 16 + 2] - t0, h[t * 16 + 3] - t0, h[t * 16 + 4] - t0, h[t * 16 + 5] - t0, h[t * 16 + 6] - t0);
         }
       }

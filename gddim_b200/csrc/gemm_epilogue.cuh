@@ -69,6 +69,10 @@ struct GemmArgs {
   // gn_xg != null: the gn_xc CTAs of an image are `gn_xc` CONSECUTIVE CTAs of the grid (not one cluster) and exchange
   // their statistics through this global buffer of tagged 64-bit words (see gnf_fold); null: one cluster, DSMEM exchange
   unsigned long long* gn_xg;
+  // weights of this launch (contiguous [N, w_ld] fp16): every CTA asks L2 for its slice at kernel entry, so that the whole
+  // matrix streams in from HBM as ONE parallel burst instead of k-block by k-block behind the ring's HBM round trips
+  const void* pf_ptr;
+  long long pf_bytes;
   long long* dbg_clk;   // GDDIM_ABLATE builds: clock64 timeline of CTA 0 ([tile < 16][16 stamps]), else null
   int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };

@@ -55,6 +55,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }
 
 // ---- TMA ------------------------------------------------------------------------------------------
+// bulk prefetch of `bytes` (multiple of 16) of global memory into L2, no shared-memory destination
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

@@ -161,6 +161,14 @@ def test_config2_sampler_deep_nfe50_order2_small_batch(deep):
   print(f"config2 deep nfe50 o2: trace rel_l2 {['%.1e' % e for e in errs]}; x {rel_l2(x, ox):.2e} v {rel_l2(v, ov):.2e}")
   assert n == 50 and np.isfinite(x).all()
   assert max(errs) < TOL and rel_l2(x, ox) < TOL and rel_l2(v, ov) < TOL
+  # the same two priors as rows 37, 38 of BASELINE's FULL batch (256: other tile shapes, CTA pairs, all SMs busy): images
+  # are independent, so the oracle's two samples are the reference for those rows of the full-batch run
+  ub = prior_u(256, seed=12)
+  ub[37:39] = u
+  xb, vb, _ = fn(0, model, 256, u=ub)
+  eb = (rel_l2(xb[37:39], ox), rel_l2(vb[37:39], ov))
+  print(f"config2 deep nfe50 o2, batch 256 rows 37-38 vs oracle: x {eb[0]:.2e} v {eb[1]:.2e}")
+  assert np.isfinite(xb).all() and max(eb) < TOL
 
 
 def test_full_batch_properties_config2(deep):
