@@ -345,6 +345,122 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
   }
 }
 
+// ---- FIR resampling through shared memory ----------------------------------------------------------------------------
+// gn_apply_kernel<RS_FIR_*> evaluates act(a*x + b) once per TAP: 16 swish evaluations per output element when
+// downsampling and 4 per output (16 per input element) when upsampling -- the special-function pipe, not HBM, bounded those
+// launches (128 us for the 32x32x128 FIR-down pass whose bytes take 26 us).  Here a CTA stages the input rows its output
+// rows need (one image, CC channels, all columns + a zero column on either side), normalised + activated ONCE, next to
+// the raw values for the shortcut operand, and the 4x4 / 2x2 taps then read shared memory.  Same tap order and weights
+// as tap_table, so results are identical to the direct kernel.
+template <int RS>
+__global__ void __launch_bounds__(256) gn_fir_tiled_kernel(const ApplyArgs p, int cc, int ro, int ri) {
+  pdl_entry();
+  extern __shared__ __align__(16) float fsm[];
+  const int C = p.c1 + p.c2;
+  const int Wp = p.W + 2;
+  float* T = fsm;                                        // [ri][W + 2][cc]  act(norm(x))   (only when dst16)
+  float* X = fsm + (p.dst16 ? (size_t)ri * Wp * cc : 0);   // [ri][W + 2][cc]  x              (only when raw16)
+  const int b = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
+  const int ct = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int rt = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int c0 = ct * cc;
+  const int oy0 = rt * ro;
+  const int iy0 = RS == RS_FIR_DOWN ? 2 * oy0 - 1 : oy0 / 2 - 1;
+  const float* base; int cs;
+  if (c0 < p.c1) { base = p.src1 + (long long)b * p.H * p.W * p.c1 + c0; cs = p.c1; }
+  else { base = p.src2 + (long long)b * p.H * p.W * p.c2 + (c0 - p.c1); cs = p.c2; }
+  // ---- stage the rows: thread = (4-channel vector, pixel) ----
+  const int nv4 = cc / 4;
+  {
+    const int v = threadIdx.x % nv4, pr = threadIdx.x / nv4, prs = blockDim.x / nv4;
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
+    if (p.dst16) {
+      a4 = *reinterpret_cast<const float4*>(p.coef + ((long long)b * 2) * C + c0 + v * 4);
+      b4 = *reinterpret_cast<const float4*>(p.coef + ((long long)b * 2 + 1) * C + c0 + v * 4);
+    }
+    const int n = ri * Wp;
+    for (int e0 = pr; e0 < n; e0 += 4 * prs) {           // four loads in flight per thread
+      float4 x[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * prs;
+        const int r = e / Wp, xc = e - r * Wp;
+        const int iy = iy0 + r, ix = xc - 1;
+        x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+          x[k] = __ldg(reinterpret_cast<const float4*>(base + ((long long)iy * p.W + ix) * cs + v * 4));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * prs;
+        if (e >= n) break;
+        const int r = e / Wp, xc = e - r * Wp;
+        const int iy = iy0 + r, ix = xc - 1;
+        const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        if (p.dst16) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (in) {
+            t.x = x[k].x * a4.x + b4.x; t.y = x[k].y * a4.y + b4.y; t.z = x[k].z * a4.z + b4.z; t.w = x[k].w * a4.w + b4.w;
+            if (p.silu) { t.x = silu_f(t.x); t.y = silu_f(t.y); t.z = silu_f(t.z); t.w = silu_f(t.w); }
+          }
+          *reinterpret_cast<float4*>(T + (size_t)e * cc + v * 4) = t;
+        }
+        if (p.raw16) *reinterpret_cast<float4*>(X + (size_t)e * cc + v * 4) = x[k];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- taps from shared memory: thread = (4-channel vector, output pixel); the 8 threads of one pixel read 128 contiguous
+  //      bytes = one pass over the 32 banks, whatever the pixel stride of the taps ----
+  const int v4 = threadIdx.x % nv4, pr = threadIdx.x / nv4, prs = blockDim.x / nv4;
+  const int Pout = p.Ho * p.Wo;
+  for (int e = pr; e < ro * p.Wo; e += prs) {
+    const int orow = e / p.Wo, ox = e - orow * p.Wo;
+    const int oy = oy0 + orow;
+    if (oy >= p.Ho) break;
+    int ny, nx, y0, x0;
+    float wy[4], wx[4];
+    tap_table<RS>(oy, ox, ny, nx, y0, x0, wy, wx);
+    float4 an = make_float4(0.f, 0.f, 0.f, 0.f), ar = an;
+#pragma unroll
+    for (int i = 0; i < (RS == RS_FIR_DOWN ? 4 : 2); ++i) {
+      const int iy = y0 + i;
+      if (iy < 0 || iy >= p.H) continue;
+#pragma unroll
+      for (int j = 0; j < (RS == RS_FIR_DOWN ? 4 : 2); ++j) {
+        const int ix = x0 + j;
+        if (ix < 0 || ix >= p.W) continue;
+        const float w = wy[i] * wx[j];
+        const size_t so = ((size_t)(iy - iy0) * Wp + (ix + 1)) * cc + v4 * 4;
+        if (p.dst16) {
+          const float4 t = *reinterpret_cast<const float4*>(T + so);
+          an.x += w * t.x; an.y += w * t.y; an.z += w * t.z; an.w += w * t.w;
+        }
+        if (p.raw16) {
+          const float4 x = *reinterpret_cast<const float4*>(X + so);
+          ar.x += w * x.x; ar.y += w * x.y; ar.z += w * x.z; ar.w += w * x.w;
+        }
+      }
+    }
+    const long long o = ((long long)b * Pout + (long long)oy * p.Wo + ox) * C + c0 + v4 * 4;
+    if (p.dst16) {
+      const __half2 h0 = __floats2half2_rn(an.x, an.y), h1 = __floats2half2_rn(an.z, an.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.dst16 + o) = pk;
+    }
+    if (p.raw16) {
+      const __half2 h0 = __floats2half2_rn(ar.x * p.raw_scale, ar.y * p.raw_scale);
+      const __half2 h1 = __floats2half2_rn(ar.z * p.raw_scale, ar.w * p.raw_scale);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(p.raw16 + o) = pk;
+    }
+  }
+}
+
 // ---- small images (H*W <= 64: the 8x8 and 4x4 levels): statistics + apply in ONE kernel, one CTA per image ----------
 // The whole image (<= 64 pixels x C channels) sits in registers: thread = (pixel row, 4-channel vector), PPT pixels per
 // thread.  Replaces coef/stats + apply launches whose cost at these sizes is launch latency, not bytes.
@@ -543,6 +659,29 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
   a.coef = op->coef; a.silu = op->silu; a.do_norm = op->dst16 != nullptr; a.raw_scale = op->raw_scale;
   a.dst16 = op->dst16; a.raw16 = op->raw16;
   a.reverse = op->reverse;
+  if ((op->resample == RS_FIR_DOWN || op->resample == RS_FIR_UP) && C % 32 == 0 && op->c1 % 32 == 0 && op->W % 2 == 0) {
+    static int tiled = -1;                        // GDDIM_NO_FIR_TILED=1: A/B switch back to the direct kernel
+    if (tiled < 0) { const char* e = getenv("GDDIM_NO_FIR_TILED"); tiled = (e && e[0] == '1') ? 0 : 1; }
+    const int cc = 32;
+    const bool down = op->resample == RS_FIR_DOWN;
+    int ro = down ? 2 : 8;
+    if (ro > a.Ho) ro = a.Ho;
+    const int ri = down ? 2 * ro + 2 : ro / 2 + 2;
+    const size_t smem = (size_t)((a.dst16 ? 1 : 0) + (a.raw16 ? 1 : 0)) * ri * (op->W + 2) * cc * sizeof(float);
+    if (tiled && a.Ho % ro == 0 && smem <= 96 * 1024 && (a.dst16 || a.raw16)) {
+      static DeviceOnce attr_set;
+      if (attr_set.need()) {
+        cudaFuncSetAttribute(gn_fir_tiled_kernel<RS_FIR_DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(gn_fir_tiled_kernel<RS_FIR_UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set.done();
+      }
+      dim3 grid(a.Ho / ro, C / cc, op->B);
+      a.rows = 0; a.pix_per_cta = 0;
+      if (down) launch_k(gn_fir_tiled_kernel<RS_FIR_DOWN>, dim3(grid), dim3(256), smem, st, a, cc, ro, ri);
+      else launch_k(gn_fir_tiled_kernel<RS_FIR_UP>, dim3(grid), dim3(256), smem, st, a, cc, ro, ri);
+      return cudaGetLastError() == cudaSuccess ? 0 : -4;
+    }
+  }
   const int nv8 = C / 8;
   int rows = 256 / nv8;
   if (rows < 1) rows = 1;
