@@ -347,116 +347,139 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
 
 // ---- FIR resampling through shared memory ----------------------------------------------------------------------------
 // gn_apply_kernel<RS_FIR_*> evaluates act(a*x + b) once per TAP: 16 swish evaluations per output element when
-// downsampling and 4 per output (16 per input element) when upsampling -- the special-function pipe, not HBM, bounded those
-// launches (128 us for the 32x32x128 FIR-down pass whose bytes take 26 us).  Here a CTA stages the input rows its output
-// rows need (one image, CC channels, all columns + a zero column on either side), normalised + activated ONCE, next to
-// the raw values for the shortcut operand, and the 4x4 / 2x2 taps then read shared memory.  Same tap order and weights
-// as tap_table, so results are identical to the direct kernel.
+// downsampling and 4 per output (16 per input element) when upsampling -- instruction issue, not HBM, bounds those
+// launches.  Here a CTA stages the input rows its output rows need (one image, 32 channels, all columns + a zero column on
+// either side, rows outside the image as zeros), normalised + activated ONCE, next to the raw values for the shortcut
+// operand; the taps then read shared memory with compile-time weights and no bounds tests.  Same tap order and weight
+// products as tap_table (a skipped out-of-range tap and an added zero are the same number): results are identical to
+// the direct kernel.  W must be a power of two (index arithmetic by shifts).
+__device__ __forceinline__ void fir_store4(__half* p, const float4& v, float s) {
+  const __half2 h0 = __floats2half2_rn(v.x * s, v.y * s), h1 = __floats2half2_rn(v.z * s, v.w * s);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+__device__ __forceinline__ void fir_acc(float4& a, float w, const float4& t) {
+  a.x += w * t.x; a.y += w * t.y; a.z += w * t.z; a.w += w * t.w;
+}
+
 template <int RS>
-__global__ void __launch_bounds__(256) gn_fir_tiled_kernel(const ApplyArgs p, int cc, int ro, int ri) {
+__global__ void __launch_bounds__(256) gn_fir_tiled_kernel(const ApplyArgs p, int ro, int ri, int lw) {
   pdl_entry();
+  constexpr int CC = 32;                                 // channels per CTA: the 8 threads of a pixel cover 128 bytes
   extern __shared__ __align__(16) float fsm[];
   const int C = p.c1 + p.c2;
-  const int Wp = p.W + 2;
-  float* T = fsm;                                        // [ri][W + 2][cc]  act(norm(x))   (only when dst16)
-  float* X = fsm + (p.dst16 ? (size_t)ri * Wp * cc : 0);   // [ri][W + 2][cc]  x              (only when raw16)
+  const int W = p.W, Wp = W + 2;
+  float* T = fsm;                                          // [ri][W + 2][CC]  act(norm(x))   (only when dst16)
+  float* X = fsm + (p.dst16 ? (size_t)ri * Wp * CC : 0);   // [ri][W + 2][CC]  x              (only when raw16)
   const int b = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const int ct = p.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
   const int rt = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
-  const int c0 = ct * cc;
+  const int c0 = ct * CC;
   const int oy0 = rt * ro;
   const int iy0 = RS == RS_FIR_DOWN ? 2 * oy0 - 1 : oy0 / 2 - 1;
   const float* base; int cs;
-  if (c0 < p.c1) { base = p.src1 + (long long)b * p.H * p.W * p.c1 + c0; cs = p.c1; }
-  else { base = p.src2 + (long long)b * p.H * p.W * p.c2 + (c0 - p.c1); cs = p.c2; }
-  // ---- stage the rows: thread = (4-channel vector, pixel) ----
-  const int nv4 = cc / 4;
+  if (c0 < p.c1) { base = p.src1 + (long long)b * p.H * W * p.c1 + c0; cs = p.c1; }
+  else { base = p.src2 + (long long)b * p.H * W * p.c2 + (c0 - p.c1); cs = p.c2; }
+  const int v = threadIdx.x & 7, pr = threadIdx.x >> 3;      // 4-channel vector, pixel slot (32 per pass)
+  const bool norm = p.dst16 != nullptr, rawo = p.raw16 != nullptr;
+  // ---- stage the rows ----
   {
-    const int v = threadIdx.x % nv4, pr = threadIdx.x / nv4, prs = blockDim.x / nv4;
     float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
-    if (p.dst16) {
+    if (norm) {
       a4 = *reinterpret_cast<const float4*>(p.coef + ((long long)b * 2) * C + c0 + v * 4);
       b4 = *reinterpret_cast<const float4*>(p.coef + ((long long)b * 2 + 1) * C + c0 + v * 4);
     }
-    const int n = ri * Wp;
-    for (int e0 = pr; e0 < n; e0 += 4 * prs) {           // four loads in flight per thread
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = pr; e < 2 * ri; e += 32) {                 // the two zero columns
+      const size_t so = ((size_t)(e >> 1) * Wp + ((e & 1) ? W + 1 : 0)) * CC + v * 4;
+      if (norm) *reinterpret_cast<float4*>(T + so) = z4;
+      if (rawo) *reinterpret_cast<float4*>(X + so) = z4;
+    }
+    const int n = ri << lw;
+    for (int e0 = pr; e0 < n; e0 += 4 * 32) {              // four loads in flight per thread
       float4 x[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int e = e0 + k * prs;
-        const int r = e / Wp, xc = e - r * Wp;
-        const int iy = iy0 + r, ix = xc - 1;
-        x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < n && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-          x[k] = __ldg(reinterpret_cast<const float4*>(base + ((long long)iy * p.W + ix) * cs + v * 4));
+        const int e = e0 + k * 32;
+        const int iy = iy0 + (e >> lw), ix = e & (W - 1);
+        x[k] = z4;
+        if (e < n && iy >= 0 && iy < p.H) x[k] = __ldg(reinterpret_cast<const float4*>(base + ((long long)iy * W + ix) * cs + v * 4));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int e = e0 + k * prs;
+        const int e = e0 + k * 32;
         if (e >= n) break;
-        const int r = e / Wp, xc = e - r * Wp;
-        const int iy = iy0 + r, ix = xc - 1;
-        const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-        if (p.dst16) {
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (in) {
+        const int r = e >> lw, ix = e & (W - 1);
+        const int iy = iy0 + r;
+        const size_t so = ((size_t)r * Wp + ix + 1) * CC + v * 4;
+        if (norm) {
+          float4 t = z4;
+          if (iy >= 0 && iy < p.H) {
             t.x = x[k].x * a4.x + b4.x; t.y = x[k].y * a4.y + b4.y; t.z = x[k].z * a4.z + b4.z; t.w = x[k].w * a4.w + b4.w;
             if (p.silu) { t.x = silu_f(t.x); t.y = silu_f(t.y); t.z = silu_f(t.z); t.w = silu_f(t.w); }
           }
-          *reinterpret_cast<float4*>(T + (size_t)e * cc + v * 4) = t;
+          *reinterpret_cast<float4*>(T + so) = t;
         }
-        if (p.raw16) *reinterpret_cast<float4*>(X + (size_t)e * cc + v * 4) = x[k];
+        if (rawo) *reinterpret_cast<float4*>(X + so) = x[k];
       }
     }
   }
   __syncthreads();
-  // ---- taps from shared memory: thread = (4-channel vector, output pixel); the 8 threads of one pixel read 128 contiguous
-  //      bytes = one pass over the 32 banks, whatever the pixel stride of the taps ----
-  const int v4 = threadIdx.x % nv4, pr = threadIdx.x / nv4, prs = blockDim.x / nv4;
-  const int Pout = p.Ho * p.Wo;
-  for (int e = pr; e < ro * p.Wo; e += prs) {
-    const int orow = e / p.Wo, ox = e - orow * p.Wo;
-    const int oy = oy0 + orow;
-    if (oy >= p.Ho) break;
-    int ny, nx, y0, x0;
-    float wy[4], wx[4];
-    tap_table<RS>(oy, ox, ny, nx, y0, x0, wy, wx);
-    float4 an = make_float4(0.f, 0.f, 0.f, 0.f), ar = an;
+  const int Wo = p.Wo;
+  const long long obase = (long long)b * p.Ho * Wo;
+  if (RS == RS_FIR_DOWN) {
+    // out(oy, ox) = sum_{i, j < 4} k[i] k[j] t[2 oy - 1 + i][2 ox - 1 + j]: local row 2 (oy - oy0) + i, column 2 ox + j
+    const float kf[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+    const int lwo = lw - 1;
+    for (int e = pr; e < (ro << lwo); e += 32) {
+      const int orow = e >> lwo, ox = e & (Wo - 1);
+      float4 an = make_float4(0.f, 0.f, 0.f, 0.f), ar = an;
+      const size_t s0 = ((size_t)(2 * orow) * Wp + 2 * ox) * CC + v * 4;
 #pragma unroll
-    for (int i = 0; i < (RS == RS_FIR_DOWN ? 4 : 2); ++i) {
-      const int iy = y0 + i;
-      if (iy < 0 || iy >= p.H) continue;
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < (RS == RS_FIR_DOWN ? 4 : 2); ++j) {
-        const int ix = x0 + j;
-        if (ix < 0 || ix >= p.W) continue;
-        const float w = wy[i] * wx[j];
-        const size_t so = ((size_t)(iy - iy0) * Wp + (ix + 1)) * cc + v4 * 4;
-        if (p.dst16) {
-          const float4 t = *reinterpret_cast<const float4*>(T + so);
-          an.x += w * t.x; an.y += w * t.y; an.z += w * t.z; an.w += w * t.w;
+        for (int j = 0; j < 4; ++j) {
+          const float w = kf[i] * kf[j];
+          const size_t so = s0 + ((size_t)i * Wp + j) * CC;
+          if (norm) fir_acc(an, w, *reinterpret_cast<const float4*>(T + so));
+          if (rawo) fir_acc(ar, w, *reinterpret_cast<const float4*>(X + so));
         }
-        if (p.raw16) {
-          const float4 x = *reinterpret_cast<const float4*>(X + so);
-          ar.x += w * x.x; ar.y += w * x.y; ar.z += w * x.z; ar.w += w * x.w;
-        }
+      const long long o = (obase + (long long)(oy0 + orow) * Wo + ox) * C + c0 + v * 4;
+      if (norm) fir_store4(p.dst16 + o, an, 1.0f);
+      if (rawo) fir_store4(p.raw16 + o, ar, p.raw_scale);
+    }
+  } else {
+    // a thread owns the 2 x 2 outputs of input pixel (y, x): the 3 x 3 neighbourhood n[a][b] = t[y - 1 + a][x - 1 + b] is
+    // read once; weights as tap_table: even output rows take rows (y - 1, y) with (0.25, 0.75), odd ones (y, y + 1) with
+    // (0.75, 0.25), columns alike; accumulation in tap order (i, j)
+    const float q = 0.25f, h = 0.75f;
+    for (int e = pr; e < ((ro >> 1) << lw); e += 32) {
+      const int ly = e >> lw, x = e & (W - 1);
+      const size_t s0 = ((size_t)ly * Wp + x) * CC + v * 4;      // n[0][0]: local row ly, column (x - 1) + 1
+      const long long o00 = (obase + (long long)(oy0 + 2 * ly) * Wo + 2 * x) * C + c0 + v * 4;
+#pragma unroll
+      for (int arr = 0; arr < 2; ++arr) {
+        if (arr == 0 ? !norm : !rawo) continue;
+        const float* S = arr == 0 ? T : X;
+        float4 n[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) n[a][bb] = *reinterpret_cast<const float4*>(S + s0 + ((size_t)a * Wp + bb) * CC);
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+        fir_acc(o0, q * q, n[0][0]); fir_acc(o0, q * h, n[0][1]); fir_acc(o0, h * q, n[1][0]); fir_acc(o0, h * h, n[1][1]);
+        fir_acc(o1, q * h, n[0][1]); fir_acc(o1, q * q, n[0][2]); fir_acc(o1, h * h, n[1][1]); fir_acc(o1, h * q, n[1][2]);
+        fir_acc(o2, h * q, n[1][0]); fir_acc(o2, h * h, n[1][1]); fir_acc(o2, q * q, n[2][0]); fir_acc(o2, q * h, n[2][1]);
+        fir_acc(o3, h * h, n[1][1]); fir_acc(o3, h * q, n[1][2]); fir_acc(o3, q * h, n[2][1]); fir_acc(o3, q * q, n[2][2]);
+        __half* d = arr == 0 ? p.dst16 : p.raw16;
+        const float sc = arr == 0 ? 1.0f : p.raw_scale;
+        fir_store4(d + o00, o0, sc);
+        fir_store4(d + o00 + C, o1, sc);
+        fir_store4(d + o00 + (long long)Wo * C, o2, sc);
+        fir_store4(d + o00 + (long long)Wo * C + C, o3, sc);
       }
-    }
-    const long long o = ((long long)b * Pout + (long long)oy * p.Wo + ox) * C + c0 + v4 * 4;
-    if (p.dst16) {
-      const __half2 h0 = __floats2half2_rn(an.x, an.y), h1 = __floats2half2_rn(an.z, an.w);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(p.dst16 + o) = pk;
-    }
-    if (p.raw16) {
-      const __half2 h0 = __floats2half2_rn(ar.x * p.raw_scale, ar.y * p.raw_scale);
-      const __half2 h1 = __floats2half2_rn(ar.z * p.raw_scale, ar.w * p.raw_scale);
-      uint2 pk;
-      pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(p.raw16 + o) = pk;
     }
   }
 }
@@ -663,12 +686,14 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
     static int tiled = -1;                        // GDDIM_NO_FIR_TILED=1: A/B switch back to the direct kernel
     if (tiled < 0) { const char* e = getenv("GDDIM_NO_FIR_TILED"); tiled = (e && e[0] == '1') ? 0 : 1; }
     const int cc = 32;
+    int lw = 0;
+    while ((1 << lw) < op->W) ++lw;
     const bool down = op->resample == RS_FIR_DOWN;
     int ro = down ? 2 : 8;
     if (ro > a.Ho) ro = a.Ho;
     const int ri = down ? 2 * ro + 2 : ro / 2 + 2;
     const size_t smem = (size_t)((a.dst16 ? 1 : 0) + (a.raw16 ? 1 : 0)) * ri * (op->W + 2) * cc * sizeof(float);
-    if (tiled && a.Ho % ro == 0 && smem <= 96 * 1024 && (a.dst16 || a.raw16)) {
+    if (tiled && (1 << lw) == op->W && a.Ho % ro == 0 && ro % 2 == 0 && smem <= 96 * 1024 && (a.dst16 || a.raw16)) {
       static DeviceOnce attr_set;
       if (attr_set.need()) {
         cudaFuncSetAttribute(gn_fir_tiled_kernel<RS_FIR_DOWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -677,8 +702,8 @@ int norm_launch(const NormOp* op, cudaStream_t st) {
       }
       dim3 grid(a.Ho / ro, C / cc, op->B);
       a.rows = 0; a.pix_per_cta = 0;
-      if (down) launch_k(gn_fir_tiled_kernel<RS_FIR_DOWN>, dim3(grid), dim3(256), smem, st, a, cc, ro, ri);
-      else launch_k(gn_fir_tiled_kernel<RS_FIR_UP>, dim3(grid), dim3(256), smem, st, a, cc, ro, ri);
+      if (down) launch_k(gn_fir_tiled_kernel<RS_FIR_DOWN>, dim3(grid), dim3(256), smem, st, a, ro, ri, lw);
+      else launch_k(gn_fir_tiled_kernel<RS_FIR_UP>, dim3(grid), dim3(256), smem, st, a, ro, ri, lw);
       return cudaGetLastError() == cudaSuccess ? 0 : -4;
     }
   }
