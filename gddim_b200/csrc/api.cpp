@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <algorithm>
@@ -52,8 +53,15 @@ struct gddim_sampler {
   float* d_stage = nullptr;           // host-buffer staging / reference-layout scratch
   float *d_x = nullptr, *d_v = nullptr;
   float *d_blur_a = nullptr, *d_blur_b = nullptr;
-  std::vector<cudaGraphExec_t> graphs;   // per ring slot
+  std::vector<cudaGraphExec_t> graphs;   // per ring slot (trace / explicit-noise / stochastic calls)
   int graph_batch = 0;
+  // deterministic samplers: ONE graph per sample call -- every network evaluation, time-embedding copy, update kernel,
+  // the layout changes at both ends -- over the sampler's own buffers (inputs staged in d_stage, results in d_x / d_v)
+  cudaGraphExec_t whole_graph = nullptr;
+  int whole_batch = 0;                   // batch the graph was captured for
+  int warm_batch = 0;                    // batch that has run once eagerly (lazy initialisations done: capturable)
+  long long launches_per_sample = 0;
+  bool in_whole = false;                 // inside the body of a whole-sample run: no per-slot graphs, no re-entry
   long long kernels_per_forward = 0;
   long long launches = 0;
   cudaStream_t own_stream = nullptr;   // used when the caller passes the legacy default stream (not capturable)
@@ -453,6 +461,8 @@ int gddim_group_norm(const gddim_norm_desc* d, void* stream) {
 static void free_sampler_buffers(gddim_sampler* s) {
   for (auto g : s->graphs) if (g) cudaGraphExecDestroy(g);
   s->graphs.clear();
+  if (s->whole_graph) cudaGraphExecDestroy(s->whole_graph);
+  s->whole_graph = nullptr; s->whole_batch = s->warm_batch = 0;
   cudaFree(s->d_temb_all); cudaFree(s->d_u); cudaFree(s->d_xin); cudaFree(s->d_stage); cudaFree(s->d_x);
   cudaFree(s->d_v); cudaFree(s->d_blur_a); cudaFree(s->d_blur_b);
   s->d_temb_all = s->d_u = s->d_xin = s->d_stage = s->d_x = s->d_v = s->d_blur_a = s->d_blur_b = nullptr;
@@ -691,6 +701,19 @@ int gddim_sampler_rev_ts(const gddim_sampler* s, double* out, int cap) {
   return n;
 }
 
+static bool whole_graph_enabled() {
+  static int on = -1;                       // GDDIM_NO_WHOLE_GRAPH=1: A/B switch back to one graph per network evaluation
+  if (on < 0) { const char* e = getenv("GDDIM_NO_WHOLE_GRAPH"); on = (e && e[0] == '1') ? 0 : 1; }
+  return on == 1;
+}
+// does a call draw per-step noise (a key / explicit normals: arguments of the call, not properties of the sampler)?
+static bool sampler_draws_noise(const gddim_sampler* s) {
+  if (s->cfg.kind == GDDIM_CLD_SDEIS) return true;
+  for (const gddim_step& ps : s->program)
+    if (ps.F[0] != 0.f || ps.F[1] != 0.f || ps.F[2] != 0.f || ps.F[3] != 0.f) return true;
+  return false;
+}
+
 // one network evaluation #e (time index e) reading s->d_u / d_xin and writing ring slot `slot`
 static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t st) {
   UNet& net = *s->ctx->net;
@@ -698,7 +721,7 @@ static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t s
   if (tt > 0)
     cudaMemcpyAsync(net.temb_cur(), s->d_temb_all + (size_t)e * tt, (size_t)tt * 4, cudaMemcpyDeviceToDevice, st);
   const float* in = (s->is_blur || s->cfg.kind == GDDIM_CLD_PROGRAM) ? s->d_xin : s->d_u;
-  if (s->cfg.use_graph && !net.profiling()) {
+  if (s->cfg.use_graph && !net.profiling() && !s->in_whole) {
     if (s->graph_batch != batch) {
       for (auto g : s->graphs) if (g) cudaGraphExecDestroy(g);
       s->graphs.assign(s->d_eps.size(), nullptr);
@@ -761,6 +784,61 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
   const long long n_pix = (long long)batch * s->S * s->S;
   const size_t state_elems = (size_t)n_pix * net.net_channels();
   const size_t img_elems = (size_t)n_pix * s->C;
+
+  // ---- deterministic samplers: the whole call as one CUDA graph ----------------------------------------------------
+  // (per-step noise keys, explicit noise and traces are arguments of the call and would be baked into the graph: those
+  // calls keep one graph per network evaluation with the update kernels launched in between)
+  if (whole_graph_enabled() && s->cfg.use_graph && !net.profiling() && !s->in_whole && !trace_dev && !noise_dev &&
+      !sampler_draws_noise(s)) {
+    if (!s->is_blur && !v) return set_err("gddim_sample: CLD sampler needs a v output");
+    if (cudaMemcpyAsync(s->d_stage, u, state_elems * 4, host_buffers ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return set_err("gddim_sample: input copy failed");
+    int rc = 0;
+    s->in_whole = true;
+    if (s->whole_graph && s->whole_batch == batch) {
+      if (cudaGraphLaunch(s->whole_graph, st) != cudaSuccess) rc = set_err("cudaGraphLaunch failed");
+      s->launches += s->launches_per_sample;
+    } else if (s->warm_batch != batch) {
+      // first call at this batch: eager (function attributes, exchange buffers, the DCT matrix are set up lazily)
+      if (s->whole_graph) { cudaGraphExecDestroy(s->whole_graph); s->whole_graph = nullptr; s->whole_batch = 0; }
+      rc = gddim_sample_noise(s, s->d_stage, s->d_x, s->d_v, batch, 0, nullptr, nullptr, st);
+      if (!rc) s->warm_batch = batch;
+    } else {
+      const long long before = s->launches;
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        s->in_whole = false;
+        return set_err("cudaStreamBeginCapture failed");
+      }
+      rc = gddim_sample_noise(s, s->d_stage, s->d_x, s->d_v, batch, 0, nullptr, nullptr, st);
+      const cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (!rc && ce != cudaSuccess) rc = set_err(std::string("graph capture failed: ") + cudaGetErrorString(ce));
+      if (!rc) {
+        s->launches_per_sample = s->launches - before;
+        const cudaError_t ci = cudaGraphInstantiate(&s->whole_graph, g, 0);
+        if (ci != cudaSuccess) rc = set_err(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ci));
+        else s->whole_batch = batch;
+      }
+      if (g) cudaGraphDestroy(g);
+      if (!rc && cudaGraphLaunch(s->whole_graph, st) != cudaSuccess) rc = set_err("cudaGraphLaunch failed");
+    }
+    s->in_whole = false;
+    if (rc) return rc;
+    const cudaMemcpyKind back = host_buffers ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    cudaMemcpyAsync(x, s->d_x, img_elems * 4, back, st);
+    if (!s->is_blur) cudaMemcpyAsync(v, s->d_v, img_elems * 4, back, st);
+    if (host_buffers) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return set_err(std::string("gddim_sample: ") + cudaGetErrorString(e));
+    }
+    if (legacy) {
+      cudaEventRecord(s->ev_out, st);
+      cudaStreamWaitEvent(caller, s->ev_out, 0);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(std::string("gddim_sample: ") + cudaGetErrorString(e));
+    return 0;
+  }
 
   if (!s->is_blur) {
     if (!v) return set_err("gddim_sample: CLD sampler needs a v output");

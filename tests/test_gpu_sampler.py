@@ -92,8 +92,18 @@ def test_graph_replay_equals_eager_launches():
   xb, vb, _ = b(0, model, 2, u=u)
   assert np.array_equal(xa, xb) and np.array_equal(va, vb)
   assert a.core.launch_count() == b.core.launch_count() > 0
-  xa2, _, _ = a(0, model, 2, u=u)            # second call replays the captured graphs
-  assert np.array_equal(xa, xa2)
+  n1 = a.core.launch_count()
+  xa2, va2, _ = a(0, model, 2, u=u)          # second call: the whole sample is captured into one graph and launched
+  xa3, va3, _ = a(0, model, 2, u=u)          # third call: replay
+  assert np.array_equal(xa, xa2) and np.array_equal(va, va2) and np.array_equal(xa, xa3) and np.array_equal(va, va3)
+  assert a.core.launch_count() == 3 * n1     # the graph holds every kernel of the call
+  u2 = prior_u(2, seed=6)                    # the graph reads the sampler's own staging buffer: new inputs, same graph
+  xc, _, _ = a(0, model, 2, u=u2)
+  xd, _, _ = b(0, model, 2, u=u2)
+  assert np.array_equal(xc, xd) and not np.array_equal(xc, xa)
+  ud = torch.as_tensor(u2).cuda()            # device-resident caller buffers go through the same graph
+  xe, ve, _ = a(0, model, 2, u=ud)
+  assert np.array_equal(xe.cpu().numpy(), xc)
 
 
 def test_blur_order0_matches_oracle():
