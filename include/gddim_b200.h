@@ -218,7 +218,8 @@ typedef struct {
   int ts_order;
   int denoising;     /* config.sampling.noise_removal */
   int mixed_score;   /* config.model.mixed_score (CLD) */
-  int use_graph;     /* capture the network evaluation in a CUDA graph */
+  int use_graph;     /* CUDA graphs: deterministic samplers capture the WHOLE sample call (second call at a batch size onwards),
+                        calls with per-step noise / traces one graph per network evaluation */
   float x_mul, x_add; /* inverse_scaler as an affine map: x_out = x * x_mul + x_add  ((x+1)/2 -> 0.5, 0.5) */
   float lambda_coef;  /* sdeis: config.sampling.lambda_coef */
   int sdeis_use_order0; /* sdeis: config.sampling.sdeis_use_order0 */
