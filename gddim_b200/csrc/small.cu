@@ -7,6 +7,7 @@
 // layerspp.py:115-143 + up_or_down_sampling.py:168-209 (Downsample fir+with_conv = conv_downsample_2d),
 // layerspp.py:61-83 (AttnBlockpp), ncsnpp.py:87-89 + layerspp.py:216 (Dense).
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 #include "launch.cuh"
@@ -95,8 +96,136 @@ __global__ void __launch_bounds__(256) im2col_fir_down_vec8_kernel(const float* 
   }
 }
 
+// Same result through shared memory: the FIR output grid f (H + 1) x (W + 1) of the rows a CTA needs is computed ONCE
+// (the direct kernels recompute the 16-tap FIR for each of the 9 window positions it belongs to and are bound by
+// instruction issue: 72 us for the 16x16x128 level whose bytes take 11 us), then the nine stride-2 windows are copied
+// out.  CTA = (output-row pair, 32-channel chunk, image); staged input rows carry two zero columns on either side and
+// zero rows outside the image, so no tap needs a bounds test.  Tap order and weights as in the direct kernels.
+__global__ void __launch_bounds__(256) im2col_fir_down_tiled_kernel(const float* __restrict__ in, __half* __restrict__ a16,
+                                                                   int H, int W, int c, int ro, float out_scale) {
+  pdl_entry();
+  extern __shared__ __align__(16) float ism[];
+  constexpr int CC = 32;
+  const int Ho = H / 2, Wo = W / 2;
+  const int nxr = 2 * ro + 4, nfr = 2 * ro + 1;         // staged input rows, FIR rows
+  const int Wx = W + 4, Wf = W + 1;
+  float* X = ism;                                         // [nxr][Wx][CC]
+  float* F = ism + (size_t)nxr * Wx * CC;                 // [nfr][Wf][CC]
+  const int oy0 = blockIdx.x * ro, c0 = blockIdx.y * CC;
+  const long long b = blockIdx.z;
+  const int v = threadIdx.x & 7, pr = threadIdx.x >> 3;   // 4-channel vector, pixel slot
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // input row r <-> image row 2 oy0 - 2 + r, column x <-> image column x - 2
+  for (int e = pr; e < nxr * Wx; e += 32) {
+    const int r = e / Wx, x = e - r * Wx;
+    const int iy = 2 * oy0 - 2 + r, ix = x - 2;
+    float4 t = z4;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) t = __ldg(reinterpret_cast<const float4*>(in + ((b * H + iy) * W + ix) * c + c0 + v * 4));
+    *reinterpret_cast<float4*>(X + (size_t)e * CC + v * 4) = t;
+  }
+  __syncthreads();
+  // f[py][px] = sum_{i, j} k[i] k[j] in[py + i - 2][px + j - 2]; FIR row q <-> py = 2 oy0 + q: input rows q + i, columns px + j
+  const float kf[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (int e = pr; e < nfr * Wf; e += 32) {
+    const int q = e / Wf, px = e - q * Wf;
+    float4 acc = z4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float w = kf[i] * kf[j];
+        const float4 t = *reinterpret_cast<const float4*>(X + ((size_t)(q + i) * Wx + px + j) * CC + v * 4);
+        acc.x += w * t.x; acc.y += w * t.y; acc.z += w * t.z; acc.w += w * t.w;
+      }
+    *reinterpret_cast<float4*>(F + (size_t)e * CC + v * 4) = acc;
+  }
+  __syncthreads();
+  // windows: a16[opix][tap * c + ch] = f[2 oy + ky][2 ox + kx][ch] * out_scale
+  for (int e = pr; e < ro * Wo * 9; e += 32) {
+    const int tap = e % 9, op = e / 9;
+    const int orow = op / Wo, ox = op - orow * Wo;
+    if (oy0 + orow >= Ho) break;
+    const int ky = tap / 3, kx = tap - ky * 3;
+    const float4 t = *reinterpret_cast<const float4*>(F + ((size_t)(2 * orow + ky) * Wf + 2 * ox + kx) * CC + v * 4);
+    const __half2 h0 = __floats2half2_rn(t.x * out_scale, t.y * out_scale), h1 = __floats2half2_rn(t.z * out_scale, t.w * out_scale);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+    const long long opix = (b * Ho + oy0 + orow) * Wo + ox;
+    *reinterpret_cast<uint2*>(a16 + opix * (9 * c) + tap * c + c0 + v * 4) = pk;
+  }
+}
+
+// few channels (the c = 6 input of the first pyramid level, kpad = 64): one CTA per image, the whole image and its FIR grid
+// in shared memory, then one thread per output element of the [Ho * Wo][kpad] operand (zero beyond 9 c)
+__global__ void __launch_bounds__(256) im2col_fir_down_image_kernel(const float* __restrict__ in, __half* __restrict__ a16,
+                                                                   int H, int W, int c, int kpad, float out_scale) {
+  pdl_entry();
+  extern __shared__ __align__(16) float ism[];
+  const int Wx = W + 4, Hx = H + 4, Wf = W + 1, Hf = H + 1;
+  float* X = ism;                                   // [Hx][Wx][c], image at offset (2, 2), zeros around
+  float* F = ism + (size_t)Hx * Wx * c;             // [Hf][Wf][c]
+  const long long b = blockIdx.x;
+  for (int e = threadIdx.x; e < Hx * Wx * c; e += blockDim.x) {
+    const int ch = e % c, x = (e / c) % Wx, y = e / (c * Wx);
+    const int iy = y - 2, ix = x - 2;
+    X[e] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(in + ((b * H + iy) * W + ix) * c + ch) : 0.f;
+  }
+  __syncthreads();
+  const float kf[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (int e = threadIdx.x; e < Hf * Wf * c; e += blockDim.x) {
+    const int ch = e % c, px = (e / c) % Wf, py = e / (c * Wf);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc += kf[i] * kf[j] * X[((py + i) * Wx + px + j) * c + ch];
+    F[e] = acc;
+  }
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  for (int e = threadIdx.x; e < Ho * Wo * kpad; e += blockDim.x) {
+    const int k = e % kpad, op = e / kpad;
+    float vv = 0.f;
+    if (k < 9 * c) {
+      const int ch = k % c, tap = k / c;
+      const int ky = tap / 3, kx = tap - ky * 3;
+      const int oy = op / Wo, ox = op - oy * Wo;
+      vv = F[((2 * oy + ky) * Wf + 2 * ox + kx) * c + ch];
+    }
+    a16[(b * Ho * Wo + op) * kpad + k] = __float2half_rn(vv * out_scale);
+  }
+}
+
 int im2col_fir_down_launch(const float* in, __half* a16, int B, int H, int W, int c, int kpad, int use_fir,
                            float out_scale, cudaStream_t st) {
+  static int tiled = -1;                        // GDDIM_NO_IM2COL_TILED=1: A/B switch back to the direct kernels
+  if (tiled < 0) { const char* e = getenv("GDDIM_NO_IM2COL_TILED"); tiled = (e && e[0] == '1') ? 0 : 1; }
+  if (tiled && use_fir && c % 32 == 0 && kpad == 9 * c && H % 4 == 0 && W % 2 == 0) {
+    const int ro = 2;
+    const size_t smem = ((size_t)(2 * ro + 4) * (W + 4) + (size_t)(2 * ro + 1) * (W + 1)) * 32 * sizeof(float);
+    if (smem <= 96 * 1024) {
+      static DeviceOnce attr_set;
+      if (attr_set.need()) {
+        cudaFuncSetAttribute(im2col_fir_down_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set.done();
+      }
+      launch_k(im2col_fir_down_tiled_kernel, dim3(H / 2 / ro, c / 32, B), dim3(256), smem, st, in, a16, H, W, c, ro, out_scale);
+      return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    }
+  }
+  if (tiled && use_fir && c <= 8 && H % 2 == 0 && W % 2 == 0) {
+    const size_t smem = ((size_t)(H + 4) * (W + 4) + (size_t)(H + 1) * (W + 1)) * c * sizeof(float);
+    if (smem <= 96 * 1024) {
+      static DeviceOnce attr_set2;
+      if (attr_set2.need()) {
+        cudaFuncSetAttribute(im2col_fir_down_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set2.done();
+      }
+      launch_k(im2col_fir_down_image_kernel, dim3(B), dim3(256), smem, st, in, a16, H, W, c, kpad, out_scale);
+      return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    }
+  }
   if (use_fir && c % 8 == 0 && kpad == 9 * c) {
     const long long total = (long long)B * (H / 2) * (W / 2) * 9 * (c / 8);
     int grid = ceil_div_ll(total, 256);
