@@ -6,13 +6,8 @@ SRC := gddim_b200/csrc
 OBJ := build/obj
 LIB := gddim_b200/libgddim_b200.so
 CU := $(SRC)/conv_gemm.cu $(SRC)/attn.cu $(SRC)/gn_qkv.cu $(SRC)/norm.cu $(SRC)/small.cu $(SRC)/update.cu
-# `make XF=1` adds the EXPERIMENTAL normalise-on-load convolution (csrc/conv_xf.cu, selected at run time by GDDIM_XF=1);
-# `make ABLATE=1` compiles the timing-only epilogue ablations (GDDIM_GEMM_DBG, results invalid).  Neither is in the
-# default library.
-ifeq ($(XF),1)
-CU += $(SRC)/conv_xf.cu
-NVFLAGS += -DGDDIM_WITH_XF
-endif
+# `make ABLATE=1` compiles the timing-only epilogue ablations (GDDIM_GEMM_DBG, results invalid) and the clock64 timeline;
+# never in the default library.
 ifeq ($(ABLATE),1)
 NVFLAGS += -DGDDIM_ABLATE
 endif

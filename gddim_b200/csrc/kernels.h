@@ -62,12 +62,6 @@ struct GemmOp {
   float gn_eps;
   int gn_groups;            // groups over the N output channels (channels per group must be 4, 8 or 16)
   int gn_silu;
-  // EXPERIMENTAL (GDDIM_XF=1, conv_xf.cu): A operand = swish(GroupNorm(source)) produced on load from the fp32 source(s)
-  int xf;
-  const float* xf_src1; int xf_c1;
-  const float* xf_src2; int xf_c2;
-  const float* xf_coef;     // [B, 2, C] scale / shift table of the preceding coef_only NormOp
-  int xf_silu;
   // ---- filled by gemm_prepare ----
   CUtensorMap tmA[2];
   CUtensorMap tmB;
@@ -91,9 +85,6 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub = 0, int force_c
 // impl: 0 = tcgen05/TMA kernel, 1 = CUDA-core reference kernel (validation only)
 int gemm_launch(const GemmOp* op, int impl, cudaStream_t st);
 const char* gemm_last_error();
-// EXPERIMENTAL: normalise-on-load variant of a prepared halo / CTA-pair layer (conv_xf.cu)
-int conv_xf_supported(const GemmOp* op);
-int conv_xf_launch(const GemmOp* op, cudaStream_t st);
 
 // 128B-swizzled fp16 tensor map of rank 2..4 over a dense tensor (dims innermost first, box in elements)
 int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint32_t* box);

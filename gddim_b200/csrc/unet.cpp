@@ -963,33 +963,6 @@ int UNet::finalize() {
       if (attn_fused_prepare(&op.attn) != 0) return fail(std::string("attn_fused_prepare(") + op.tag + "): " + gemm_last_error());
     }
   }
-#ifdef GDDIM_WITH_XF       // experimental kernel: only in builds made with `make XF=1`, never in the default library
-  {
-    // EXPERIMENTAL (GDDIM_XF=1, not validated on hardware yet): GroupNorm + swish applied on load inside the following
-    // 3x3 convolution (conv_xf.cu).  Pattern: a non-resampling NormOp whose normalised output feeds only the next op, a
-    // single-segment halo / CTA-pair GEMM.  The NormOp then only computes the coefficient table (and the raw copy, if any).
-    const char* e = getenv("GDDIM_XF");
-    if (e && e[0] == '1') {
-      int n_xf = 0;
-      for (size_t i = 0; i + 1 < ops_.size(); ++i) {
-        Op& a = ops_[i];
-        Op& b = ops_[i + 1];
-        if (a.kind != OP_NORM || b.kind != OP_GEMM) continue;
-        NormOp& n = a.norm;
-        GemmOp& g = b.gemm;
-        if (n.resample != RS_NONE || n.dst16 == nullptr || n.coef_only || g.seg[0].ptr != n.dst16 || g.nseg != 1) continue;
-        if (n.colstats1 == nullptr || (n.src2 != nullptr && n.colstats2 == nullptr)) continue;
-        g.xf_src1 = n.src1; g.xf_c1 = n.c1; g.xf_src2 = n.src2; g.xf_c2 = n.c2; g.xf_coef = n.coef; g.xf_silu = n.silu;
-        if (!conv_xf_supported(&g)) { g.xf_src1 = nullptr; continue; }
-        g.xf = 1;
-        n.coef_only = 1;
-        n.dst16 = nullptr;
-        ++n_xf;
-      }
-      fprintf(stderr, "gddim: GDDIM_XF=1: %d convolutions take their A operand through the normalise-on-load kernel\n", n_xf);
-    }
-  }
-#endif
   if (cudaDeviceSynchronize() != cudaSuccess) return fail("device error during finalize");
   finalized_ = true;
   return 0;
@@ -1059,10 +1032,6 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         g.B = batch;
         if (op.out_is_external) g.out32 = out_dev;
         g.m_tiles = (int)(((long long)batch * g.H * g.W + 128 * g.m_sub - 1) / (128 * g.m_sub));
-#ifdef GDDIM_WITH_XF
-        if (g.xf) rc = conv_xf_launch(&g, st);     // (the A operand tensor does not exist for these layers)
-        else
-#endif
         rc = gemm_launch(&g, gemm_impl, st);
         if (rc) return fail(std::string("gemm_launch(") + op.tag + "): " + gemm_last_error());
         launches_ += (gemm_impl == 1 && g.epi == EPI_SOFTMAX) ? 2 : 1;

@@ -15,9 +15,3 @@ if [ "$1" = "bench" ]; then
   timeout 1200 python bench.py --steps 2 --warmup 3 --profile-csv gpurun_out/profile_ops.csv > gpurun_out/bench.json 2> gpurun_out/bench.err
   tail -c 3000 gpurun_out/bench.json | tee -a gpurun_out/ci.log; tail -5 gpurun_out/bench.err | tee -a gpurun_out/ci.log
 fi
-if [ "$1" = "xf" ] || [ "$2" = "xf" ]; then
-  echo "== experimental: normalise-on-load convolution (GDDIM_XF=1) ==" | tee -a gpurun_out/ci.log
-  timeout 600 python tools/exp/xf_check.py 2>&1 | tail -20 | tee -a gpurun_out/ci.log
-  GDDIM_XF=1 timeout 600 python -m pytest tests/test_gpu_net.py -m gpu -q -x 2>&1 | tail -5 | tee -a gpurun_out/ci.log
-  for t in 0 1 0 1; do GDDIM_XF=$t timeout 300 python tools/ab.py 256 3 2>&1 | grep -E "^AB|rror" | tee -a gpurun_out/ci.log; done
-fi
