@@ -645,12 +645,23 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
   if (!is_pow2(op->W) || !is_pow2(op->H)) GEMM_FAIL("conv_gemm: H and W must be powers of two (got %d x %d)", op->H, op->W);
   if (op->nseg < 1 || op->nseg > 2) GEMM_FAIL("conv_gemm: 1 or 2 A segments");
   int ktot = 0;
+  op->cuda_core = 0;
   for (int s = 0; s < op->nseg; ++s) {
     const GemmSeg& g = op->seg[s];
-    if (g.c % BLOCK_K != 0 || g.c_off % 8 != 0 || g.c_total % 8 != 0)
-      GEMM_FAIL("conv_gemm: segment %d channels (%d of %d at %d) must be a multiple of %d", s, g.c, g.c_total, g.c_off, BLOCK_K);
+    if (g.c % 16 != 0 || g.c_off % 8 != 0 || g.c_total % 8 != 0)
+      GEMM_FAIL("conv_gemm: segment %d channels (%d of %d at %d) must be a multiple of 16", s, g.c, g.c_total, g.c_off);
+    if (g.c % BLOCK_K != 0) op->cuda_core = 1;       // narrow layers (nf = 32 networks): no 64-wide K block to feed the UMMA
     if (g.taps != 1 && g.taps != 9) GEMM_FAIL("conv_gemm: taps must be 1 or 9");
     ktot += g.taps * g.c;
+  }
+  if (op->cuda_core) {
+    // CUDA-core kernel (conv_gemm_ref_kernel): any N, linear epilogue with every option but the fused GroupNorm / softmax
+    if (op->epi != EPI_LINEAR) GEMM_FAIL("conv_gemm: channel counts that are not multiples of %d support the linear epilogue only", BLOCK_K);
+    if (op->w_koff + ktot * (op->wsplit == 2 ? 2 : 1) > op->w_ld) GEMM_FAIL("conv_gemm: K range exceeds weight row stride");
+    if (op->w_batch_stride != 0) GEMM_FAIL("conv_gemm: batched B operand needs channel counts that are multiples of %d", BLOCK_K);
+    op->block_n = 0; op->cg = 1; op->halo = 0; op->gn_xc = 0; op->m_tiles = op->n_tiles = op->tiles_per_batch = 0;
+    op->prepared = 1;
+    return 0;
   }
   if (op->wsplit != 0 && op->wsplit != 1 && op->wsplit != 2) GEMM_FAIL("conv_gemm: wsplit must be 1 or 2");
   if (op->w_koff + ktot * (op->wsplit == 2 ? 2 : 1) > op->w_ld) GEMM_FAIL("conv_gemm: K range exceeds weight row stride");
@@ -917,7 +928,7 @@ __global__ void __launch_bounds__(256) gnf_ref_kernel(const float* __restrict__ 
 
 int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
   const long long M = (long long)op->B * op->H * op->W;
-  if (impl == 0) {
+  if (impl == 0 && !(op->prepared && op->cuda_core)) {
     if (!op->prepared) GEMM_FAIL("conv_gemm: op not prepared");
     GemmArgs a;
     memset(&a, 0, sizeof(a));

@@ -18,7 +18,7 @@ struct GemmSeg {
   const __half* ptr;   // [B,H,W,c_total]
   int c_total;         // channel count of the tensor
   int c_off;           // first channel used
-  int c;               // channels used (multiple of 64)
+  int c;               // channels used (multiple of 64 for the tcgen05 kernel; multiples of 16 run on CUDA cores)
   int taps;            // 1 or 9
 };
 
@@ -73,6 +73,8 @@ struct GemmOp {
   CUtensorMap tmH;          // halo box of segment 0
   int m_tiles, n_tiles, tiles_per_batch;
   int gn_xc;                // EPI_GNF: CTAs per image = cluster size (1, 2, 4)
+  int cuda_core;            // a segment's channel count is not a multiple of 64 (nf = 32 networks): the layer runs on the
+                            // CUDA-core kernel whatever `impl` says; linear epilogue only
   int prepared;
 };
 

@@ -295,9 +295,10 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
                   (Cin / groups0 == 4 || Cin / groups0 == 8 || Cin / groups0 == 16);
     }
     int pk = 0;
+    bool ptc = true;                         // the producer runs on the tcgen05 kernel (64-wide K blocks)
     if (po.kind == OP_GEMM)
-      for (int sgi = 0; sgi < pg.nseg && sgi < 2; ++sgi) pk += pg.seg[sgi].taps * pg.seg[sgi].c;
-    fuse0 = po.kind == OP_GEMM && pg.epi == EPI_LINEAR && pg.out32 == in1.p && pg.out16 == nullptr && pg.rowscale == nullptr &&
+      for (int sgi = 0; sgi < pg.nseg && sgi < 2; ++sgi) { pk += pg.seg[sgi].taps * pg.seg[sgi].c; ptc = ptc && pg.seg[sgi].c % 64 == 0; }
+    fuse0 = po.kind == OP_GEMM && ptc && pg.epi == EPI_LINEAR && pg.out32 == in1.p && pg.out16 == nullptr && pg.rowscale == nullptr &&
             pg.n_store == 0 && pg.w_batch_stride == 0 && pg.N == Cin && pg.ldo == Cin && pg.H == H && pg.W == W &&
             !po.out_is_external && gnf_pays(H, W, pk, true);
   }
@@ -356,7 +357,7 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
   static const bool no_gnf = [] { const char* e = getenv("GDDIM_NO_GNF"); return e && e[0] == '1'; }();
   auto gn1 = gn_params(s, out_ch);
   const int groups1 = std::min(out_ch / 4, 32);
-  const bool fuse1 = !no_gnf && gemm_gnf_supported(Ho, Wo, out_ch, groups1) && gnf_pays(Ho, Wo, 9 * Cin, false);
+  const bool fuse1 = !no_gnf && Cin % 64 == 0 && gemm_gnf_supported(Ho, Wo, out_ch, groups1) && gnf_pays(Ho, Wo, 9 * Cin, false);
   T16 a2 = new16(out_ch, Ho, Wo);
   T32 h2{nullptr, 0, 0, 0, 0};
   if (!fuse1) h2 = new32(out_ch, Ho, Wo);
@@ -651,7 +652,8 @@ int UNet::walk() {
   const gddim_model_cfg& m = cfg_;
   if (m.n_levels < 1 || m.n_levels > 8) return fail("n_levels out of range");
   if (!m.centered) return fail("config.data.centered = False is not supported");
-  if (m.nf % 64 != 0) return fail("nf must be a multiple of 64 for the tcgen05 GEMM path (got " + std::to_string(m.nf) + ")");
+  // nf = 32 (simple_cifar10): layers with 32 / 96 input channels have no 64-wide K block and run on the CUDA-core GEMM
+  if (m.nf % 32 != 0) return fail("nf must be a multiple of 32 (got " + std::to_string(m.nf) + ")");
   const int nf = m.nf, S = m.image_size, Cnet = net_channels();
   Scope top;
   temb_dim_ = nf * 4;
@@ -1034,7 +1036,10 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         g.m_tiles = (int)(((long long)batch * g.H * g.W + 128 * g.m_sub - 1) / (128 * g.m_sub));
         rc = gemm_launch(&g, gemm_impl, st);
         if (rc) return fail(std::string("gemm_launch(") + op.tag + "): " + gemm_last_error());
-        launches_ += (gemm_impl == 1 && g.epi == EPI_SOFTMAX) ? 2 : 1;
+        if (gemm_impl == 1 || g.cuda_core)     // CUDA-core path: column statistics / softmax are separate kernels
+          launches_ += 1 + ((g.colstats && g.out32) ? 1 : 0) + (g.epi == EPI_SOFTMAX ? 1 : 0) + (g.epi == EPI_GNF ? 1 : 0);
+        else
+          launches_ += 1;
         break;
       }
       case OP_IM2COL:

@@ -34,6 +34,10 @@ CASES = [  # B, H, W, Cin, Cout, two_seg
     (3, 4, 4, 256, 256, False),        # M = 48 < one tile: tail rows masked
     (1, 32, 32, 384, 128, True),
     (5, 16, 16, 64, 64, False),
+    # nf = 32 networks (simple_cifar10): 32 / 96 channels have no 64-wide K block -> CUDA-core kernel on both `impl`s
+    (3, 32, 32, 32, 32, False),
+    (2, 32, 32, 96, 32, True),
+    (3, 16, 16, 96, 64, True),
 ]
 
 
@@ -266,7 +270,10 @@ NORM_CASES = [(2, 32, 32, 128, 0, 0), (2, 16, 16, 256, 128, 0), (2, 16, 16, 128,
               (2, 32, 32, 64, 0, 1),
               # single-kernel path for images of <= 64 pixels (8x8 / 4x4 levels), incl. concatenated sources
               (3, 8, 8, 256, 0, 0), (2, 8, 8, 256, 256, 0), (3, 4, 4, 256, 0, 0), (2, 8, 8, 128, 0, 0), (2, 4, 4, 64, 64, 0),
-              (2, 8, 8, 192, 64, 0), (2, 2, 2, 256, 0, 0)]
+              (2, 8, 8, 192, 64, 0), (2, 2, 2, 256, 0, 0),
+              # nf = 32 networks: 8 / 16 / 24 groups of four channels
+              (2, 32, 32, 32, 0, 0), (2, 32, 32, 32, 32, 0), (3, 32, 32, 64, 32, 0), (2, 32, 32, 32, 0, 3), (2, 16, 16, 64, 0, 4),
+              (2, 16, 16, 64, 64, 0), (3, 8, 8, 64, 0, 0), (2, 4, 4, 64, 64, 0)]
 
 
 @pytest.mark.parametrize("case", NORM_CASES, ids=[f"b{c[0]}_{c[1]}_{c[3]}+{c[4]}_rs{c[5]}" for c in NORM_CASES])

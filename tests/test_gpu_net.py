@@ -86,6 +86,29 @@ def test_attention_block_matches_oracle_in_isolation():
     assert err < FWD_TOL
 
 
+def test_simple_cifar10_nf32_forward_matches_oracle():
+  """simple_cifar10 (cld_jax/configs/simple_cifar10_config.py: nf = 32, four res-blocks per level, naive resampling,
+  positional embedding) at its shipped size: 3 883 686 parameters.  Its 32- and 96-channel convolutions have no 64-wide K
+  block and run on the CUDA-core GEMM, the 64- / 128-channel ones on tcgen05; C = 64 attention through the unfused
+  QK^T-softmax / P.V GEMMs."""
+  from gddim_b200 import configs, net
+  from oracle import ncsnpp as on
+  cfg = configs.cld_simple_cifar10()
+  model = net.ScoreNet(cfg, cld=True)
+  p = model.init_params(seed=21, nondegenerate=True)
+  assert sum(v.size for v in p.values()) == 3_883_686
+  x = np.random.default_rng(5).standard_normal((3, 32, 32, 6)).astype(np.float32)
+  for t in (0.7, 0.05):
+    got = model.forward(x, t)
+    want = on.forward(p, cfg, x, 999 * t)
+    err = rel_l2(got, want)
+    print(f"simple_cifar10 (nf=32) forward t={t}: rel-L2 {err:.3e}")
+    assert np.isfinite(got).all() and err < FWD_TOL
+  a = model.forward(x, 0.7)
+  b = model.forward(x[:1].copy(), 0.7)
+  assert rel_l2(b, a[:1]) < 1e-5                              # an image does not depend on its batch mates
+
+
 def test_256x256_forward_matches_oracle():
   """BASELINE config 5: accr_dcifar10 with data.image_size=256 -> 256/128/64/32 pyramid, conv tiles
   that cover half an image row, one 1024-token attention in the middle.  Narrowed (nf=64, 1 res-block) so the

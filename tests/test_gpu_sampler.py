@@ -52,6 +52,27 @@ def test_cld_deis_matches_oracle(kind, order, nfe, denoise):
   np.testing.assert_allclose(tab, want, rtol=2e-6, atol=1e-9)
 
 
+def test_simple_cifar10_nf32_sampler_matches_oracle():
+  """gDDIM (deis, order 2) on the shipped simple_cifar10 network (nf = 32): CUDA-core GEMMs for the 32- / 96-channel
+  layers inside the same sampler graph."""
+  from gddim_b200 import configs
+  from oracle import ncsnpp as on
+  cfg = configs.cld_simple_cifar10()
+  model = net.ScoreNet(cfg, cld=True)
+  p = model.init_params(seed=22, nondegenerate=True)
+  net_fn = on.make_net_fn(p, cfg)
+  sde = sde_lib.from_config(cfg)
+  fn = sampling.get_deis_sampler(sde, model, (32, 32, 3), 6, inv, 2, ts_order=2, denoising=True, is_p=False)
+  u = prior_u(2, seed=12)
+  x, v, n = fn(0, model, 2, u=u)
+  ox, ov, _ = oracle_cld_sample(cfg, net_fn, u, 6, 2, denoising=True)
+  print(f"simple_cifar10 (nf=32) deis o2 nfe6: x {rel_l2(x, ox):.2e} v {rel_l2(v, ov):.2e}")
+  assert n == 6 and rel_l2(x, ox) < TOL and rel_l2(v, ov) < TOL
+  x2, v2, _ = fn(0, model, 2, u=u)           # second call: whole-sample graph
+  x3, v3, _ = fn(0, model, 2, u=u)           # third call: replay
+  assert np.array_equal(x, x2) and np.array_equal(x, x3)
+
+
 def test_cld_order0_sampler_matches_oracle():
   cfg, model, net_fn = build("cld_deep")
   sde = sde_lib.from_config(cfg)

@@ -60,6 +60,22 @@ def test_256_geometry_keeps_the_long_sequence_attention_path():
 
 def test_unsupported_width_is_rejected_at_context_creation():
   cfg = configs.cld_accr_dcifar10()
-  cfg.model.nf = 32                                   # simple_cifar10: nf must be a multiple of 64
+  cfg.model.nf = 48                                   # nf must be a multiple of 32
   with pytest.raises(RuntimeError):
     net.ScoreNet(cfg, cld=True).plan(1)
+
+
+def test_simple_cifar10_nf32_plans():
+  """simple_cifar10 (cld_jax/configs/simple_cifar10_config.py:45: nf = 32, ch_mult (1, 2, 2, 2), four res-blocks, naive
+  resampling, positional embedding): 32 / 64 / 96 / 128-channel layers.  The 64- and 128-channel ones are tcgen05 GEMMs
+  (GroupNorm epilogue included); the 32- / 96-channel ones have no 64-wide K block and keep the separate GroupNorm pass in
+  front of a CUDA-core GEMM -- the planner must not attach a GroupNorm epilogue to them."""
+  model = net.ScoreNet(configs.cld_simple_cifar10(), cld=True)
+  plan = model.plan(8)
+  tags = collections.Counter(t.split("/", 1)[-1] for t, _ in plan)
+  kinds = collections.Counter(KIND[k] for _, k in plan)
+  assert kinds["gemm"] > 60 and kinds["gn_qkv"] == 0 and kinds["attn_fused"] == 0      # C = 64 attention: unfused chain
+  assert tags["qk_softmax"] == tags["pv"] == tags["vT"] and tags["qk_softmax"] >= 1
+  assert tags["conv1"] > 0 and tags["conv1_gn1"] > 0                                   # both kinds of conv1 are present
+  n_params = sum(int(__import__("numpy").prod(shape)) for shape, _, _ in model.specs().values())
+  assert n_params == 3_883_686                                                         # SURVEY.md 8(c)(8)
