@@ -715,7 +715,10 @@ static bool sampler_draws_noise(const gddim_sampler* s) {
 }
 
 // one network evaluation #e (time index e) reading s->d_u / d_xin and writing ring slot `slot`
-static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t st) {
+// upd: the CLD update that consumes this evaluation.  Where the evaluation is launched directly (eager calls and the body of
+// a whole-sample graph) it travels with the forward pass (the head convolution's epilogue applies it); per-slot graphs are
+// replayed for many steps and cannot hold per-step coefficients, so there the update kernel follows the graph launch.
+static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t st, const CldStepArgs* upd = nullptr) {
   UNet& net = *s->ctx->net;
   const int tt = net.temb_total();
   if (tt > 0)
@@ -744,9 +747,13 @@ static int eval_net(gddim_sampler* s, int e, int slot, int batch, cudaStream_t s
     }
     if (cudaGraphLaunch(s->graphs[slot], st) != cudaSuccess) return set_err("cudaGraphLaunch failed");
     s->launches += s->kernels_per_forward;
+    if (upd != nullptr) {
+      if (cld_step_launch(upd, st)) return set_err("cld_step launch failed");
+      s->launches += 1;
+    }
   } else {
     const long long before = net.launch_count();
-    if (net.forward(in, s->d_eps[slot], batch, st)) return set_err(net.error());
+    if (net.forward(in, s->d_eps[slot], batch, st, upd)) return set_err(net.error());
     s->launches += net.launch_count() - before;
   }
   return 0;
@@ -908,7 +915,6 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
     const int n_evals = s->cfg.kind == GDDIM_CLD_PROGRAM ? 0 : s->n_steps + (s->cfg.denoising ? 1 : 0);
     for (int e = 0; e < n_evals; ++e) {
       const int slot = e % ring;
-      if (eval_net(s, e, slot, batch, st)) return -1;
       CldStepArgs a;
       memset(&a, 0, sizeof(a));
       a.u = s->d_u; a.u_out = s->d_u;
@@ -935,8 +941,7 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
         memcpy(a.coef[1], s->den_C, 16);
         a.eps[0] = s->d_eps[slot];
       }
-      if (cld_step_launch(&a, st)) return set_err("cld_step launch failed");
-      s->launches += 1;
+      if (eval_net(s, e, slot, batch, st, &a)) return -1;       // network evaluation + the update that consumes it
       if (trace_dev && e < s->n_steps) {
         if (relayout_launch(s->d_u, trace_dev + (size_t)e * state_elems, n_pix, s->C, 0, st)) return set_err("trace relayout failed");
         s->launches += 1;

@@ -334,7 +334,13 @@ conv_gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_con
                               (p.colstats ? 8u : 0u) | (p.rowscale ? 16u : 0u);
         EpiCtx<BLOCK_N, MT> cx{p, stg, bias_s, &tfull_bar[acc], acc_phase, tmem_base + (uint32_t(quad * 32) << 16) + acc * MT * BLOCK_N,
                                (long long)mt * MT * BLOCK_M + quad * 32, nt * BLOCK_N, lane, group, tile_seq, warp};
-        if (p.n_store > 0) epi_tile<BLOCK_N, MT, false, true, false, false, false, false, false, true>(cx);   // few-channel output
+        if (p.n_store > 0) {                                                                                    // few-channel output
+          bool done = false;
+          if constexpr (BLOCK_N == 32 && MT == 1 && CG == 1 && !HALO) {
+            if (p.upd_on) { epi_head_update<BLOCK_N, MT>(cx); done = true; }      // head + gDDIM update
+          }
+          if (!done) epi_tile<BLOCK_N, MT, false, true, false, false, false, false, false, true>(cx);
+        }
         else if (!full) epi_tile<BLOCK_N, MT, true, true, true, true, true, false, true>(cx);     // ragged last tile: generic path
         else if (mode == (2u | 8u)) epi_tile<BLOCK_N, MT, false, true, false, true, false, true, false>(cx);           // conv1, shortcut conv2, stem
         else if (mode == (1u | 2u | 8u)) epi_tile<BLOCK_N, MT, true, true, false, true, false, true, false>(cx);       // conv2 / proj / pyramid
@@ -926,6 +932,15 @@ __global__ void __launch_bounds__(256) gnf_ref_kernel(const float* __restrict__ 
   }
 }
 
+// the epilogue of this (prepared) launch can apply the CLD update `u`: the six-column head convolution on the 128 x 32 tcgen05
+// tile, three data channels, no noise term, at most four eps terms, eps_0 = this launch's own output
+int gemm_head_update_supported(const GemmOp* op, const CldStepArgs* u) {
+  return op->prepared && !op->cuda_core && op->epi == EPI_LINEAR && op->n_store == 6 && op->ldo == 6 && op->block_n == 32 &&
+         op->m_sub == 1 && op->cg == 1 && !op->halo && op->out32 != nullptr && u != nullptr && u->C == 3 && u->noise_mode == 0 &&
+         u->n_eps >= 1 && u->n_eps <= 4 && u->eps[0] == op->out32 && (!u->mixed || u->eps_store == op->out32) &&
+         u->n_pix == (long long)op->B * op->H * op->W;
+}
+
 int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
   const long long M = (long long)op->B * op->H * op->W;
   if (impl == 0 && !(op->prepared && op->cuda_core)) {
@@ -950,6 +965,18 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
     a.colstats = op->colstats;
     a.n_store = op->n_store;
     a.reverse = op->reverse;
+    if (op->upd != nullptr) {
+      const CldStepArgs& u = *op->upd;
+      if (!gemm_head_update_supported(op, op->upd)) GEMM_FAIL("conv_gemm: head update: unsupported layer / step (see gemm_head_update_supported)");
+      a.upd_on = 1;
+      a.upd.u = u.u; a.upd.u_out = u.u_out;
+      // unused history slots read the oldest used one again (the loads are unconditional, the sums are not)
+      for (int j = 0; j < 4; ++j) a.upd.eps[j] = j < u.n_eps ? u.eps[j] : u.eps[u.n_eps - 1];
+      if (u.n_eps == 1) for (int j = 1; j < 4; ++j) a.upd.eps[j] = u.u;       // (eps[0] is being written by this launch)
+      a.upd.n_eps = u.n_eps; a.upd.mixed = u.mixed;
+      for (int j = 0; j < 5; ++j) for (int k = 0; k < 4; ++k) a.upd.coef[j][k] = u.coef[j][k];
+      for (int k = 0; k < 4; ++k) a.upd.mixm[k] = u.mixm[k];
+    }
     {
       static int wpf = -1;                    // GDDIM_NO_WPF=1: A/B switch for the weight prefetch
       if (wpf < 0) { const char* e = getenv("GDDIM_NO_WPF"); wpf = (e && e[0] == '1') ? 0 : 1; }

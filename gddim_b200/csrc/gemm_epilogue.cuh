@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 
 #include "ptx.cuh"
+#include "cld_update.cuh"
 
 #ifdef GDDIM_ABLATE
 #define GDDIM_DBG_STORE(p) ((p).dbg != 2)
@@ -73,6 +74,10 @@ struct GemmArgs {
   // matrix streams in from HBM as ONE parallel burst instead of k-block by k-block behind the ring's HBM round trips
   const void* pf_ptr;
   long long pf_bytes;
+  // head convolution of a CLD network inside a deterministic sampler: the gDDIM / DEIS update of the state is applied by
+  // this launch's epilogue (epi_head_update) to the eps values it holds in registers -- the update kernel disappears
+  int upd_on;
+  CldUpd upd;
   long long* dbg_clk;   // GDDIM_ABLATE builds: clock64 timeline of CTA 0 ([tile < 16][16 stamps]), else null
   int dbg;   // GDDIM_GEMM_DBG (timing experiments only): 1 = epilogue drains TMEM only, 2 = no global stores, 3 = no TMEM reads
 };
@@ -304,6 +309,59 @@ __device__ __forceinline__ void epi_tile(const EpiCtx<BLOCK_N, MT>& cx, float2* 
     __syncwarp();
   }
   GDDIM_STAMP(p, cx.warp_id == 0 && lane == 0, cx.tile_seq, 6);
+}
+
+// ---- head convolution + gDDIM update ---------------------------------------------------------------------------------
+// The head convolution (ncsnpp.py:237) produces eps = [eps_x | eps_v], six columns of one 32-wide N tile.  Thread = row =
+// pixel after the TMEM load, so a thread holds the complete eps of its pixel and can apply the sampler's update
+//   eps_0 (+= M u, mixed score) -> ring slot;   u' = A u + sum_j C_j eps_j      (cld_jax/deis.py:141-151, sampling.py:30-39)
+// right there: u (requested before the accumulator is waited for) and the earlier evaluations eps_1.. (24-byte rows) are read,
+// u' and eps_0 written, all as 8-byte accesses of consecutive rows by consecutive lanes.  Same arithmetic as
+// cld_step_c3_kernel (cld_update.cuh): the fused and the standalone update give bit-identical states.
+template <int BLOCK_N, int MT>
+__device__ __forceinline__ void epi_head_update(const EpiCtx<BLOCK_N, MT>& cx) {
+  static_assert(BLOCK_N == 32 && MT == 1, "head tile: one 32-column chunk");
+  const GemmArgs& p = cx.p;
+  const CldUpd& up = p.upd;
+  const long long m = cx.m0 + cx.lane;
+  const bool ok = m < p.M;                              // ragged last tile: such lanes compute on row 0 and store nothing
+  const long long mr = ok ? m : 0;
+  float u[6];
+  if (cx.group == 0) {
+    const float2* q = reinterpret_cast<const float2*>(up.u + mr * 6);
+    const float2 a = q[0], b = q[1], c = q[2];          // plain loads: u_out may be u
+    u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y; u[4] = c.x; u[5] = c.y;
+  }
+  ptx::mbar_wait(cx.tfull, cx.tfull_phase);
+  ptx::tc_fence_after();
+  if (cx.group != 0) return;                            // one 32-column chunk per tile: the second epilogue group only waits
+  uint32_t r[8];
+  ptx::tmem_ld_32x32b_x8(cx.taddr, r);                  // (warp-wide) the six real columns + 2 of the padding
+  float eh[3][6];
+#pragma unroll
+  for (int j = 1; j < 4; ++j) {         // (unused slots point at a valid row: unconditional loads, conditional sums)
+    const float2* h = reinterpret_cast<const float2*>(up.eps[j] + mr * 6);
+    const float2 ha = __ldg(h), hb = __ldg(h + 1), hc = __ldg(h + 2);
+    eh[j - 1][0] = ha.x; eh[j - 1][1] = ha.y; eh[j - 1][2] = hb.x; eh[j - 1][3] = hb.y; eh[j - 1][4] = hc.x; eh[j - 1][5] = hc.y;
+  }
+  ptx::tmem_ld_wait();
+  float e[6], acc[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) e[j] = fmaf(__uint_as_float(r[j]), p.scale, cx.bias_s[j] * p.scale);     // as epi_tile
+  if (up.mixed) cld_px_mix(e, u, up.mixm[0], up.mixm[1], up.mixm[2], up.mixm[3]);
+  if (ok) {
+    float2* o = reinterpret_cast<float2*>(p.out32 + m * 6);
+    o[0] = make_float2(e[0], e[1]); o[1] = make_float2(e[2], e[3]); o[2] = make_float2(e[4], e[5]);
+  }
+  cld_px_apply(acc, u, up.coef[0][0], up.coef[0][1], up.coef[0][2], up.coef[0][3]);
+  cld_px_acc(acc, e, up.coef[1][0], up.coef[1][1], up.coef[1][2], up.coef[1][3]);
+#pragma unroll
+  for (int j = 1; j < 4; ++j)
+    if (j < up.n_eps) cld_px_acc(acc, eh[j - 1], up.coef[1 + j][0], up.coef[1 + j][1], up.coef[1 + j][2], up.coef[1 + j][3]);
+  if (ok) {
+    float2* o = reinterpret_cast<float2*>(up.u_out + m * 6);
+    o[0] = make_float2(acc[0], acc[1]); o[1] = make_float2(acc[2], acc[3]); o[2] = make_float2(acc[4], acc[5]);
+  }
 }
 
 // ---- GroupNorm-fused epilogue (EPI_GNF) ----------------------------------------------------------------------------

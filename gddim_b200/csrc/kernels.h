@@ -8,6 +8,8 @@
 
 namespace gddim {
 
+struct CldStepArgs;
+
 // ---- implicit-GEMM convolution / GEMM (conv_gemm.cu) -------------------------------------------
 // out[m, n] = epilogue( sum_seg sum_tap sum_c A_seg[pixel(m)+tap, c] * Wt[n, k(seg,tap,c)] )
 //   m enumerates pixels of a [B,H,W] grid in NHW order; taps = 9 -> 3x3 SAME window, 1 -> pointwise.
@@ -73,6 +75,9 @@ struct GemmOp {
   CUtensorMap tmH;          // halo box of segment 0
   int m_tiles, n_tiles, tiles_per_batch;
   int gn_xc;                // EPI_GNF: CTAs per image = cluster size (1, 2, 4)
+  // optional: the CLD sampler's update applied by this launch's epilogue (head convolution only; see
+  // gemm_head_update_supported).  Host pointer, read at launch.
+  const CldStepArgs* upd;
   int cuda_core;            // a segment's channel count is not a multiple of 64 (nf = 32 networks): the layer runs on the
                             // CUDA-core kernel whatever `impl` says; linear epilogue only
   int prepared;
@@ -84,6 +89,7 @@ int gemm_gnf_supported(int H, int W, int N, int groups);
 
 // Encodes the TMA descriptors (needs the final device addresses). Returns 0 or a negative error.
 int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub = 0, int force_cg = 0);
+int gemm_head_update_supported(const GemmOp* op, const CldStepArgs* u);
 // impl: 0 = tcgen05/TMA kernel, 1 = CUDA-core reference kernel (validation only)
 int gemm_launch(const GemmOp* op, int impl, cudaStream_t st);
 const char* gemm_last_error();

@@ -129,6 +129,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
+// 32 lanes x 8 consecutive fp32 columns (few-column epilogues)
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 // ---- CTA pairs (cta_group::2): two CTAs of a cluster issue one M = 256 MMA; each loads its own A rows and half of B ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -1004,7 +1004,7 @@ int UNet::time_projections(double t, float* dst_dev, cudaStream_t st) {
   return 0;
 }
 
-int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st) {
+int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st, const CldStepArgs* head_update) {
   if (!finalized_) return fail("context not finalized");
   if (batch < 1 || batch > max_batch_) return fail("batch exceeds max_batch");
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -1034,8 +1034,18 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         g.B = batch;
         if (op.out_is_external) g.out32 = out_dev;
         g.m_tiles = (int)(((long long)batch * g.H * g.W + 128 * g.m_sub - 1) / (128 * g.m_sub));
+        bool update_behind = false;
+        if (op.out_is_external && head_update != nullptr) {
+          static const bool no_fuse = [] { const char* e = getenv("GDDIM_NO_HEAD_UPDATE"); return e && e[0] == '1'; }();   // A/B switch
+          if (!no_fuse && gemm_impl == 0 && gemm_head_update_supported(&g, head_update)) g.upd = head_update;
+          else update_behind = true;
+        }
         rc = gemm_launch(&g, gemm_impl, st);
         if (rc) return fail(std::string("gemm_launch(") + op.tag + "): " + gemm_last_error());
+        if (update_behind) {
+          if (cld_step_launch(head_update, st)) return fail("cld_step launch failed");
+          launches_ += 1;
+        }
         if (gemm_impl == 1 || g.cuda_core)     // CUDA-core path: column statistics / softmax are separate kernels
           launches_ += 1 + ((g.colstats && g.out32) ? 1 : 0) + (g.epi == EPI_SOFTMAX ? 1 : 0) + (g.epi == EPI_GNF ? 1 : 0);
         else

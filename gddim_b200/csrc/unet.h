@@ -57,7 +57,10 @@ class UNet {
   int temb_total() const { return temb_total_; }
   float* temb_cur() const { return temb_cur_; }     // the buffer the conv epilogues read
   // forward: uses whatever temb_cur() currently holds
-  int forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st);
+  // head_update (CLD samplers): the update u' = A u + sum_j C_j eps_j that consumes this evaluation (eps[0] = out_dev) runs
+  // as part of the forward pass -- inside the head convolution's epilogue where that layer qualifies
+  // (gemm_head_update_supported), else as the update kernel right behind it
+  int forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st, const CldStepArgs* head_update = nullptr);
   int net_channels() const { return cfg_.data_channels * cfg_.state_mult; }
   int image_size() const { return cfg_.image_size; }
   int max_batch() const { return max_batch_; }

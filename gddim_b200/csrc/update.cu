@@ -13,6 +13,7 @@
 
 #include "kernels.h"
 #include "launch.cuh"
+#include "cld_update.cuh"
 
 namespace gddim {
 
@@ -64,57 +65,43 @@ __device__ __forceinline__ float4 philox_normal4(unsigned long long idx, unsigne
   return make_float4(m0 * c0, m0 * s0, m1 * c1, m1 * s1);
 }
 
-// Specialisation for C = 3 (pixel = 6 floats): a thread owns 2 pixels = 3 float4 per array.
+// Specialisation for C = 3 (pixel = 6 floats): a thread owns 2 pixels = 3 float4 per array.  The per-pixel algebra is
+// cld_update.cuh's (shared with the head convolution's epilogue, which applies the same update in place of this kernel
+// for the deterministic samplers).
 __global__ void __launch_bounds__(256) cld_step_c3_kernel(const CldStepDev p) {
   pdl_entry();
   const long long npair = p.n_pix / 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair;
        i += (long long)gridDim.x * blockDim.x) {
-    float u[12], acc[12];
+    float u[2][6], accp[2][6];
     {
       const float4* q = reinterpret_cast<const float4*>(p.u) + i * 3;
       const float4 a = q[0], b = q[1], c = q[2];     // plain loads: u is updated in place by this launch
-      u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = b.x; u[5] = b.y; u[6] = b.z; u[7] = b.w;
-      u[8] = c.x; u[9] = c.y; u[10] = c.z; u[11] = c.w;
+      u[0][0] = a.x; u[0][1] = a.y; u[0][2] = a.z; u[0][3] = a.w; u[0][4] = b.x; u[0][5] = b.y;
+      u[1][0] = b.z; u[1][1] = b.w; u[1][2] = c.x; u[1][3] = c.y; u[1][4] = c.z; u[1][5] = c.w;
     }
-#pragma unroll
-    for (int px = 0; px < 2; ++px)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float x = u[px * 6 + d], v = u[px * 6 + 3 + d];
-        acc[px * 6 + d] = p.coef[0][0] * x + p.coef[0][1] * v;
-        acc[px * 6 + 3 + d] = p.coef[0][2] * x + p.coef[0][3] * v;
-      }
+    cld_px_apply(accp[0], u[0], p.coef[0][0], p.coef[0][1], p.coef[0][2], p.coef[0][3]);
+    cld_px_apply(accp[1], u[1], p.coef[0][0], p.coef[0][1], p.coef[0][2], p.coef[0][3]);
     for (int j = 0; j < p.n_eps; ++j) {
-      float e[12];
+      float e[2][6];
       const float4* q = reinterpret_cast<const float4*>(p.eps[j]) + i * 3;
       const float4 a = q[0], b = q[1], c = q[2];     // plain loads: eps[0] may be eps_store (mixed score)
-      e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
-      e[8] = c.x; e[9] = c.y; e[10] = c.z; e[11] = c.w;
+      e[0][0] = a.x; e[0][1] = a.y; e[0][2] = a.z; e[0][3] = a.w; e[0][4] = b.x; e[0][5] = b.y;
+      e[1][0] = b.z; e[1][1] = b.w; e[1][2] = c.x; e[1][3] = c.y; e[1][4] = c.z; e[1][5] = c.w;
       if (j == 0 && p.mixed) {
-#pragma unroll
-        for (int px = 0; px < 2; ++px)
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const float x = u[px * 6 + d], v = u[px * 6 + 3 + d];
-            e[px * 6 + d] += p.mixm[0] * x + p.mixm[1] * v;
-            e[px * 6 + 3 + d] += p.mixm[2] * x + p.mixm[3] * v;
-          }
+        cld_px_mix(e[0], u[0], p.mixm[0], p.mixm[1], p.mixm[2], p.mixm[3]);
+        cld_px_mix(e[1], u[1], p.mixm[0], p.mixm[1], p.mixm[2], p.mixm[3]);
         float4* s = reinterpret_cast<float4*>(p.eps_store) + i * 3;
-        s[0] = make_float4(e[0], e[1], e[2], e[3]);
-        s[1] = make_float4(e[4], e[5], e[6], e[7]);
-        s[2] = make_float4(e[8], e[9], e[10], e[11]);
+        s[0] = make_float4(e[0][0], e[0][1], e[0][2], e[0][3]);
+        s[1] = make_float4(e[0][4], e[0][5], e[1][0], e[1][1]);
+        s[2] = make_float4(e[1][2], e[1][3], e[1][4], e[1][5]);
       }
-      const float c00 = p.coef[1 + j][0], c01 = p.coef[1 + j][1], c10 = p.coef[1 + j][2], c11 = p.coef[1 + j][3];
-#pragma unroll
-      for (int px = 0; px < 2; ++px)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float ex = e[px * 6 + d], ev = e[px * 6 + 3 + d];
-          acc[px * 6 + d] += c00 * ex + c01 * ev;
-          acc[px * 6 + 3 + d] += c10 * ex + c11 * ev;
-        }
+      cld_px_acc(accp[0], e[0], p.coef[1 + j][0], p.coef[1 + j][1], p.coef[1 + j][2], p.coef[1 + j][3]);
+      cld_px_acc(accp[1], e[1], p.coef[1 + j][0], p.coef[1 + j][1], p.coef[1 + j][2], p.coef[1 + j][3]);
     }
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { acc[k] = accp[0][k]; acc[6 + k] = accp[1][k]; }
     if (p.noise_mode != 0) {
       float z[12];                 // reference layout of the two pixels: (px, d, g)
       if (p.noise_mode == 1) {

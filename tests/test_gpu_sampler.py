@@ -73,6 +73,27 @@ def test_simple_cifar10_nf32_sampler_matches_oracle():
   assert np.array_equal(x, x2) and np.array_equal(x, x3)
 
 
+@pytest.mark.parametrize("kind,order", [("cld_deep", 2), ("cld_deep", 3), ("cld_mixed", 1)])
+def test_update_fused_into_head_conv_equals_update_kernel(kind, order):
+  """Untraced deterministic calls apply the gDDIM update inside the head convolution's epilogue (epi_head_update); traced
+  calls replay one graph per ring slot and launch cld_step_c3_kernel behind it.  Same per-pixel arithmetic
+  (cld_update.cuh): the states must be bit-identical, and the fused call launches one kernel less per evaluation."""
+  cfg, model, _ = build(kind)
+  sde = sde_lib.from_config(cfg)
+  nfe = 7
+  a = sampling.get_deis_sampler(sde, model, (32, 32, 3), nfe, inv, order, ts_order=2, denoising=True, is_p=False)
+  b = sampling.get_deis_sampler(sde, model, (32, 32, 3), nfe, inv, order, ts_order=2, denoising=True, is_p=False)
+  u = prior_u(3, seed=31 + order)
+  xa, va, _ = a(0, model, 3, u=u)                       # eager first call: fused update
+  na = a.core.launch_count()
+  xb, vb, _, tr = b(0, model, 3, u=u, trace=True)       # per-slot graphs + update kernel
+  nb = b.core.launch_count()
+  assert np.array_equal(xa, xb) and np.array_equal(va, vb)
+  assert nb - na == nfe + (nfe - 1)                     # nfe update kernels + nfe - 1 trace relayouts
+  xa2, va2, _ = a(0, model, 3, u=u)                     # whole-sample graph capture + launch
+  assert np.array_equal(xa, xa2) and np.array_equal(va, va2)
+
+
 def test_cld_order0_sampler_matches_oracle():
   cfg, model, net_fn = build("cld_deep")
   sde = sde_lib.from_config(cfg)
