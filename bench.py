@@ -297,6 +297,11 @@ def run_ours(args):
                    "bytes_per_launch": upd_bytes.value, "avg_launch_ms": upd_ms.value,
                    "achieved": upd_bytes.value / (upd_ms.value * 1e-3) * 1e-9 if upd_ms.value > 0 else 0.0,
                    "frac": (upd_bytes.value / (upd_ms.value * 1e-3) * 1e-9) / hbm_peak if upd_ms.value > 0 else 0.0,
+                   "in_timed_step": bool(blur),
+                   "note": ("one launch per step behind the network evaluation" if blur else
+                            "the timed step applies this update inside the head convolution's epilogue (epi_head_update, same "
+                            "per-pixel arithmetic, no separate launch); the standalone kernel measured here serves stochastic "
+                            "and traced calls"),
                    "bytes_def": "(order+3) x 24576 B per image (CLD) / 4 x 12288 B per image (blur), SURVEY.md 8d; 200 launches back to back in one CUDA-event pair on rotating buffer sets (>= 400 MB in total, 3x the L2), so every launch reads from HBM"}}
     roof = {"bound": "tensor", "kernel": "conv_gemm_umma_kernel (all conv3x3 / 1x1 / NIN GEMM launches; the fused QK^T-softmax-PV kernel is the separate 'attention' family)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,

@@ -656,7 +656,7 @@ int gemm_prepare(GemmOp* op, int force_block_n, int force_m_sub, int force_cg) {
     const GemmSeg& g = op->seg[s];
     if (g.c % 16 != 0 || g.c_off % 8 != 0 || g.c_total % 8 != 0)
       GEMM_FAIL("conv_gemm: segment %d channels (%d of %d at %d) must be a multiple of 16", s, g.c, g.c_total, g.c_off);
-    if (g.c % BLOCK_K != 0) op->cuda_core = 1;       // narrow layers (nf = 32 networks): no 64-wide K block to feed the UMMA
+    if (g.c % BLOCK_K != 0) op->cuda_core = 1;       // no 64-wide K block to feed the UMMA (the network planner pairs pixels instead)
     if (g.taps != 1 && g.taps != 9) GEMM_FAIL("conv_gemm: taps must be 1 or 9");
     ktot += g.taps * g.c;
   }

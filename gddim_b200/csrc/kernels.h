@@ -78,8 +78,9 @@ struct GemmOp {
   // optional: the CLD sampler's update applied by this launch's epilogue (head convolution only; see
   // gemm_head_update_supported).  Host pointer, read at launch.
   const CldStepArgs* upd;
-  int cuda_core;            // a segment's channel count is not a multiple of 64 (nf = 32 networks): the layer runs on the
-                            // CUDA-core kernel whatever `impl` says; linear epilogue only
+  int cuda_core;            // a segment's channel count is not a multiple of 64: the op runs on the CUDA-core kernel
+                            // whatever `impl` says; linear epilogue only (operator ABI -- the network planner pairs pixels
+                            // instead, unet.cpp pack_conv_paired)
   int prepared;
 };
 

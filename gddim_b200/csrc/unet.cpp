@@ -191,6 +191,38 @@ static void pack_conv(const std::vector<float>& k, int taps, int cin, int cout, 
     }
 }
 
+// Pixel pairing for channel counts that are odd multiples of 32 (nf = 32 networks: 32 / 96 channels): a tcgen05 K block is
+// 64 fp16 = 128 bytes, and in NHWC two horizontally adjacent pixels of a 32-channel tensor ARE 64 contiguous channels.  A
+// [B, H, W, c] tensor is therefore read as [B, H, W/2, 2c] and the convolution becomes a 3x3 (or 1x1) convolution on the
+// half-width grid of "super-pixels" with 2c input and 2n output channels (the [B, H, W, n] result in the same memory):
+//   W'[dy, dX, (p_in, ci), (p_out, co)] = W[dy, dx, ci, co],  dx = 2 dX + p_in - p_out,  zero where |dx| > 1
+// SAME padding of the super-pixel grid is SAME padding of the pixel grid (whole super-pixels of zeros).  A third of the MMA
+// work multiplies structural zeros -- on layers that are a percent of a network's FLOPs, and in exchange every layer of the
+// network runs on the tensor cores through the one kernel.  Layout as pack_conv: K-major rows [p_out*cout + co][koff + ...].
+static void pack_conv_paired(const std::vector<float>& k, int taps, int cin, int cout, std::vector<__half>& dst, int ld,
+                             int koff, float mul = 1.f, int lo_off = 0) {
+  const int n3 = taps == 9 ? 3 : 1;
+  for (int dyi = 0; dyi < n3; ++dyi)
+    for (int dXi = 0; dXi < n3; ++dXi)
+      for (int pi = 0; pi < 2; ++pi)
+        for (int po = 0; po < 2; ++po) {
+          const int dx = taps == 9 ? 2 * (dXi - 1) + pi - po : (pi == po ? 0 : 2);
+          if (dx < -1 || dx > 1) continue;                                    // structural zero (dst is zero-initialised)
+          const int tap_src = taps == 9 ? dyi * 3 + dx + 1 : 0, tap_dst = taps == 9 ? dyi * 3 + dXi : 0;
+          for (int ci = 0; ci < cin; ++ci) {
+            const float* src = k.data() + ((size_t)tap_src * cin + ci) * cout;
+            for (int co = 0; co < cout; ++co) {
+              const float w = src[co] * mul;
+              const __half hi = __float2half_rn(w);
+              const size_t at = (size_t)(po * cout + co) * ld + koff + (size_t)tap_dst * 2 * cin + pi * cin + ci;
+              dst[at] = hi;
+              if (lo_off > 0) dst[at + lo_off] = __float2half_rn(w - __half2float(hi));
+            }
+          }
+        }
+}
+static bool needs_pairing(int c) { return c % 64 != 0; }       // (c % 32 == 0 is guaranteed by the nf check in walk())
+
 std::pair<const float*, const float*> UNet::gn_params(Scope& s, int C) {
   Scope g = s.child("GroupNorm");
   const auto* sc = param(g, "scale", {C}, 2, 1.f);
@@ -229,15 +261,17 @@ void UNet::add_norm(const T32& in1, const T32* in2, const float* gamma, const fl
 }
 
 int UNet::add_temb_proj(const std::vector<float>* w, const std::vector<float>* b, const std::vector<float>* conv_b,
-                        int out_ch) {
+                        int out_ch, int copies) {
   const int off = temb_total_;
-  temb_total_ += out_ch;
+  temb_total_ += out_ch * copies;
   if (!dry_) {
     // proj_w_host_ is [temb_dim][total] assembled column-block by column-block; total known from the dry pass
     const int total = (int)proj_b_host_.size();
-    for (int k = 0; k < temb_dim_; ++k)
-      for (int n = 0; n < out_ch; ++n) proj_w_host_[(size_t)k * total + off + n] = (*w)[(size_t)k * out_ch + n];
-    for (int n = 0; n < out_ch; ++n) proj_b_host_[off + n] = (*b)[n] + (*conv_b)[n];
+    for (int c = 0; c < copies; ++c) {
+      for (int k = 0; k < temb_dim_; ++k)
+        for (int n = 0; n < out_ch; ++n) proj_w_host_[(size_t)k * total + off + c * out_ch + n] = (*w)[(size_t)k * out_ch + n];
+      for (int n = 0; n < out_ch; ++n) proj_b_host_[off + c * out_ch + n] = (*b)[n] + (*conv_b)[n];
+    }
   }
   return off;
 }
@@ -323,7 +357,11 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     add_norm(in1, in2, gn0.first, gn0.second, true, rs, &a1, need_sc ? &x16 : nullptr, s.prefix + "gn0");
   }
 
-  // conv1 (Conv_0) + Dense_0(act(temb))
+  // conv1 (Conv_0) + Dense_0(act(temb)).  pf1 / pf2 = 2: pixel-paired (pack_conv_paired) -- half-width grid, twice the
+  // channels on both sides; such layers keep their GroupNorms as separate passes and leave the statistics to them
+  const int pf1 = needs_pairing(Cin) ? 2 : 1;
+  const int pf2 = (needs_pairing(out_ch) || (need_sc && needs_pairing(Cin))) ? 2 : 1;
+  if ((pf1 == 2 || pf2 == 2) && Wo % 2 != 0) { err_ = "pixel pairing needs an even width"; return T32{nullptr, 0, 0, 0, 0}; }
   Scope c0 = s.child("Conv");
   const auto* k0 = param(c0, "kernel", {3, 3, Cin, out_ch}, 0, 1.f);
   const auto* b0 = param(c0, "bias", {out_ch}, 1, 1.f);
@@ -334,20 +372,26 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     const auto* dw = param(d0, "kernel", {temb_dim_, out_ch}, 0, 1.f);
     const auto* db = param(d0, "bias", {out_ch}, 1, 1.f);
     if (!dry_ && (!dw || !db || !b0)) return T32{nullptr, 0, 0, 0, 0};
-    temb_off = add_temb_proj(dw, db, b0, out_ch);
+    temb_off = add_temb_proj(dw, db, b0, out_ch, pf1);
   } else {
-    if (dry_) w_alloc(out_ch * 4);
-    else { if (!b0) return T32{nullptr, 0, 0, 0, 0}; bias1 = upload_f32(*b0); }
+    if (dry_) w_alloc(out_ch * pf1 * 4);
+    else {
+      if (!b0) return T32{nullptr, 0, 0, 0, 0};
+      std::vector<float> bb;
+      for (int c = 0; c < pf1; ++c) bb.insert(bb.end(), b0->begin(), b0->end());
+      bias1 = upload_f32(bb);
+    }
   }
   __half* w1 = nullptr;
   {
     const int wmul = precise_ ? 2 : 1;
-    const size_t n = (size_t)out_ch * 9 * Cin * wmul;
+    const size_t n = (size_t)out_ch * pf1 * 9 * Cin * pf1 * wmul;
     if (dry_) w1 = (__half*)w_alloc(n * 2);
     else {
       if (!k0) return T32{nullptr, 0, 0, 0, 0};
-      std::vector<__half> pk(n);
-      pack_conv(*k0, 9, Cin, out_ch, pk, 9 * Cin * wmul, 0, 1.f, precise_ ? 9 * Cin : 0);
+      std::vector<__half> pk(n, __float2half(0.f));
+      if (pf1 == 2) pack_conv_paired(*k0, 9, Cin, out_ch, pk, 9 * 2 * Cin * wmul, 0, 1.f, precise_ ? 9 * 2 * Cin : 0);
+      else pack_conv(*k0, 9, Cin, out_ch, pk, 9 * Cin * wmul, 0, 1.f, precise_ ? 9 * Cin : 0);
       w1 = upload_f16(pk);
     }
   }
@@ -363,21 +407,21 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
   if (!fuse1) h2 = new32(out_ch, Ho, Wo);
   {
     Op op; op.kind = OP_GEMM; op.tag = s.prefix + (fuse1 ? "conv1_gn1" : "conv1");
-    op.gemm = make_gemm(max_batch_, Ho, Wo);
+    op.gemm = make_gemm(max_batch_, Ho, Wo / pf1);
     GemmOp& g = op.gemm;
     g.nseg = 1;
-    g.seg[0] = {a1.p, Cin, 0, Cin, 9};
-    g.w = w1; g.N = out_ch; g.w_ld = 9 * Cin * (precise_ ? 2 : 1); g.wsplit = precise_ ? 2 : 1;
+    g.seg[0] = {a1.p, Cin * pf1, 0, Cin * pf1, 9};
+    g.w = w1; g.N = out_ch * pf1; g.w_ld = 9 * Cin * pf1 * (precise_ ? 2 : 1); g.wsplit = precise_ ? 2 : 1;
     g.bias = bias1;
     g.bias2 = temb_off >= 0 ? temb_cur_ + temb_off : nullptr;
-    g.ldo = out_ch;
+    g.ldo = out_ch * pf1;
     if (fuse1) {
       g.epi = EPI_GNF;
       g.out16 = a2.p;
       g.gn_gamma = gn1.first; g.gn_beta = gn1.second; g.gn_eps = 1e-6f; g.gn_groups = groups1; g.gn_silu = 1;
     } else {
       g.out32 = h2.p;
-      g.colstats = h2.stats; h2.stats_valid = h2.stats != nullptr;
+      if (pf1 == 1) { g.colstats = h2.stats; h2.stats_valid = h2.stats != nullptr; }   // (paired: columns are (pixel, channel))
     }
     ops_.push_back(op);
   }
@@ -397,37 +441,40 @@ UNet::T32 UNet::resblock(Scope& top, const T32& in1, const T32* in2, int out_ch,
     k2 = param(c2, "kernel", {1, 1, Cin, out_ch}, 0, 1.f);
     b2 = param(c2, "bias", {out_ch}, 1, 1.f);
   }
-  const int ktot = 9 * out_ch + (need_sc ? Cin : 0);
+  const int ktot = (9 * out_ch + (need_sc ? Cin : 0)) * pf2;
   __half* w2 = nullptr;
   const float* bias2v = nullptr;
   const int wld2 = ktot * (precise_ ? 2 : 1), lo2 = precise_ ? ktot : 0;
-  if (dry_) { w2 = (__half*)w_alloc((size_t)out_ch * wld2 * 2); w_alloc(out_ch * 4); }
+  if (dry_) { w2 = (__half*)w_alloc((size_t)out_ch * pf2 * wld2 * 2); w_alloc(out_ch * pf2 * 4); }
   else {
     if (!k1 || !b1 || (need_sc && (!k2 || !b2))) return T32{nullptr, 0, 0, 0, 0};
-    std::vector<__half> pk((size_t)out_ch * wld2);
-    pack_conv(*k1, 9, out_ch, out_ch, pk, wld2, 0, 1.f, lo2);
+    std::vector<__half> pk((size_t)out_ch * pf2 * wld2, __float2half(0.f));
+    if (pf2 == 2) pack_conv_paired(*k1, 9, out_ch, out_ch, pk, wld2, 0, 1.f, lo2);
+    else pack_conv(*k1, 9, out_ch, out_ch, pk, wld2, 0, 1.f, lo2);
     std::vector<float> bsum(*b1);
     if (need_sc) {
-      pack_conv(*k2, 1, Cin, out_ch, pk, wld2, 9 * out_ch, 1.0f / kRawScale, lo2);
+      if (pf2 == 2) pack_conv_paired(*k2, 1, Cin, out_ch, pk, wld2, 9 * 2 * out_ch, 1.0f / kRawScale, lo2);
+      else pack_conv(*k2, 1, Cin, out_ch, pk, wld2, 9 * out_ch, 1.0f / kRawScale, lo2);
       for (int i = 0; i < out_ch; ++i) bsum[i] += (*b2)[i];
     }
+    if (pf2 == 2) bsum.insert(bsum.end(), bsum.begin(), bsum.begin() + out_ch);
     w2 = upload_f16(pk);
     bias2v = upload_f32(bsum);
   }
   T32 out = new32(out_ch, Ho, Wo);
   {
     Op op; op.kind = OP_GEMM; op.tag = s.prefix + "conv2";
-    op.gemm = make_gemm(max_batch_, Ho, Wo);
+    op.gemm = make_gemm(max_batch_, Ho, Wo / pf2);
     GemmOp& g = op.gemm;
     g.nseg = need_sc ? 2 : 1;
-    g.seg[0] = {a2.p, out_ch, 0, out_ch, 9};
-    if (need_sc) g.seg[1] = {x16.p, Cin, 0, Cin, 1};
-    g.w = w2; g.N = out_ch; g.w_ld = wld2; g.wsplit = precise_ ? 2 : 1;
+    g.seg[0] = {a2.p, out_ch * pf2, 0, out_ch * pf2, 9};
+    if (need_sc) g.seg[1] = {x16.p, Cin * pf2, 0, Cin * pf2, 1};
+    g.w = w2; g.N = out_ch * pf2; g.w_ld = wld2; g.wsplit = precise_ ? 2 : 1;
     g.bias = bias2v;
     g.residual = need_sc ? nullptr : in1.p;
     g.scale = out_scale;
-    g.out32 = out.p; g.ldo = out_ch;
-    g.colstats = out.stats; out.stats_valid = out.stats != nullptr;
+    g.out32 = out.p; g.ldo = out_ch * pf2;
+    if (pf2 == 1) { g.colstats = out.stats; out.stats_valid = out.stats != nullptr; }
     out.prod_op = (int)ops_.size();
     ops_.push_back(op);
   }
@@ -652,7 +699,7 @@ int UNet::walk() {
   const gddim_model_cfg& m = cfg_;
   if (m.n_levels < 1 || m.n_levels > 8) return fail("n_levels out of range");
   if (!m.centered) return fail("config.data.centered = False is not supported");
-  // nf = 32 (simple_cifar10): layers with 32 / 96 input channels have no 64-wide K block and run on the CUDA-core GEMM
+  // nf = 32 (simple_cifar10): layers with 32 / 96 input channels are planned pixel-paired (pack_conv_paired)
   if (m.nf % 32 != 0) return fail("nf must be a multiple of 32 (got " + std::to_string(m.nf) + ")");
   const int nf = m.nf, S = m.image_size, Cnet = net_channels();
   Scope top;
@@ -860,9 +907,11 @@ int UNet::walk() {
     const auto* hb = param(hc, "bias", {Cnet}, 1, 1.f);
     // C_out = 6 (or 3) is padded to one 32-wide N tile; only the real columns are stored (n_store)
     const int npad = 32;
+    const int pf = needs_pairing(a.C) ? 2 : 1;          // nf = 32: pixel-paired, 2 x C_out columns per super-pixel
+    if (pf == 2 && a.W % 2 != 0) return fail("pixel pairing needs an even width");
     float head_wscale = 1.f;
     __half* wp = nullptr; const float* bp = nullptr;
-    if (dry_) { wp = (__half*)w_alloc((size_t)npad * 9 * a.C * 2); w_alloc(npad * 4); }
+    if (dry_) { wp = (__half*)w_alloc((size_t)npad * 9 * a.C * pf * 2); w_alloc(npad * 4); }
     else {
       if (!hk || !hb) return -1;
       // The reference initialises this layer with scale 1e-10 (init_scale = 0): bring the weights into fp16's
@@ -872,24 +921,22 @@ int UNet::walk() {
       int e = 0;
       if (wmax > 0.f) std::frexp(wmax, &e);
       head_wscale = std::ldexp(1.0f, -e);                         // wmax * head_wscale in [0.5, 1)
-      std::vector<__half> pk((size_t)npad * 9 * a.C, __float2half(0.f));
-      for (int tap = 0; tap < 9; ++tap)
-        for (int ci = 0; ci < a.C; ++ci)
-          for (int co = 0; co < Cnet; ++co)
-            pk[(size_t)co * 9 * a.C + tap * a.C + ci] =
-                __float2half_rn((*hk)[((size_t)tap * a.C + ci) * Cnet + co] * head_wscale);
+      std::vector<__half> pk((size_t)npad * 9 * a.C * pf, __float2half(0.f));
+      if (pf == 2) pack_conv_paired(*hk, 9, a.C, Cnet, pk, 9 * a.C * pf, 0, head_wscale);
+      else pack_conv(*hk, 9, a.C, Cnet, pk, 9 * a.C, 0, head_wscale);
       std::vector<float> bb(npad, 0.f);
-      for (int co = 0; co < Cnet; ++co) bb[co] = (*hb)[co] * head_wscale;
+      for (int c = 0; c < pf; ++c)
+        for (int co = 0; co < Cnet; ++co) bb[c * Cnet + co] = (*hb)[co] * head_wscale;
       wp = upload_f16(pk); bp = upload_f32(bb);
     }
     Op op; op.kind = OP_GEMM; op.tag = "head";
     op.out_is_external = true;
-    op.gemm = make_gemm(max_batch_, a.H, a.W);
+    op.gemm = make_gemm(max_batch_, a.H, a.W / pf);
     GemmOp& g = op.gemm;
-    g.nseg = 1; g.seg[0] = {a.p, a.C, 0, a.C, 9};
-    g.w = wp; g.N = npad; g.w_ld = 9 * a.C; g.bias = bp;
+    g.nseg = 1; g.seg[0] = {a.p, a.C * pf, 0, a.C * pf, 9};
+    g.w = wp; g.N = npad; g.w_ld = 9 * a.C * pf; g.bias = bp;
     g.out32 = reinterpret_cast<float*>(uintptr_t(16));   // patched with the caller's output at launch
-    g.ldo = Cnet; g.n_store = Cnet;
+    g.ldo = Cnet * pf; g.n_store = Cnet * pf;
     g.scale = 1.0f / head_wscale;
     ops_.push_back(op);
     rel(a);
@@ -1080,6 +1127,8 @@ int UNet::forward(const float* x_dev, float* out_dev, int batch, cudaStream_t st
         rc = small_attn_launch(op.h_in, op.h_out, batch, op.T, op.cin, op.scale, st);
         launches_ += 1;
         break;
+      case OP_STEM: case OP_HEAD:       // never planned (unet.h): stem and head are OP_GEMM
+        return fail("internal: unplanned op kind in " + op.tag);
     }
     if (rc) return fail("launch failed in op " + op.tag + " (rc=" + std::to_string(rc) + ")");
     ++op_idx;

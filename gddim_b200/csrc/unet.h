@@ -146,7 +146,8 @@ class UNet {
   T32 attnblock(Scope& top, const T32& x);
   void add_norm(const T32& in1, const T32* in2, const float* gamma, const float* beta, bool silu, int resample,
                 T16* dst, T16* raw, const std::string& tag);
-  int add_temb_proj(const std::vector<float>* w, const std::vector<float>* b, const std::vector<float>* conv_b, int out_ch);
+  // copies > 1: the same projection again in the following column blocks (pixel-paired convolutions read [b | b])
+  int add_temb_proj(const std::vector<float>* w, const std::vector<float>* b, const std::vector<float>* conv_b, int out_ch, int copies = 1);
   std::pair<const float*, const float*> gn_params(Scope& s, int C);
   int fail(const std::string& m) { err_ = m; return -1; }
 };

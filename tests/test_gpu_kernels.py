@@ -34,7 +34,8 @@ CASES = [  # B, H, W, Cin, Cout, two_seg
     (3, 4, 4, 256, 256, False),        # M = 48 < one tile: tail rows masked
     (1, 32, 32, 384, 128, True),
     (5, 16, 16, 64, 64, False),
-    # nf = 32 networks (simple_cifar10): 32 / 96 channels have no 64-wide K block -> CUDA-core kernel on both `impl`s
+    # operator ABI with channel counts that are odd multiples of 32: no 64-wide K block -> CUDA-core kernel on both
+    # `impl`s (the network planner never gets here: it pairs pixels, unet.cpp pack_conv_paired)
     (3, 32, 32, 32, 32, False),
     (2, 32, 32, 96, 32, True),
     (3, 16, 16, 96, 64, True),

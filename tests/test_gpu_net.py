@@ -88,9 +88,9 @@ def test_attention_block_matches_oracle_in_isolation():
 
 def test_simple_cifar10_nf32_forward_matches_oracle():
   """simple_cifar10 (cld_jax/configs/simple_cifar10_config.py: nf = 32, four res-blocks per level, naive resampling,
-  positional embedding) at its shipped size: 3 883 686 parameters.  Its 32- and 96-channel convolutions have no 64-wide K
-  block and run on the CUDA-core GEMM, the 64- / 128-channel ones on tcgen05; C = 64 attention through the unfused
-  QK^T-softmax / P.V GEMMs."""
+  positional embedding) at its shipped size: 3 883 686 parameters.  Its 32- and 96-channel convolutions (and the head)
+  run pixel-paired on the tcgen05 kernel (unet.cpp pack_conv_paired: two adjacent pixels = one 64-channel K block);
+  C = 64 attention through the unfused QK^T-softmax / P.V GEMMs."""
   from gddim_b200 import configs, net
   from oracle import ncsnpp as on
   cfg = configs.cld_simple_cifar10()

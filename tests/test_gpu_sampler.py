@@ -53,8 +53,9 @@ def test_cld_deis_matches_oracle(kind, order, nfe, denoise):
 
 
 def test_simple_cifar10_nf32_sampler_matches_oracle():
-  """gDDIM (deis, order 2) on the shipped simple_cifar10 network (nf = 32): CUDA-core GEMMs for the 32- / 96-channel
-  layers inside the same sampler graph."""
+  """gDDIM (deis, order 2) on the shipped simple_cifar10 network (nf = 32): pixel-paired convolutions for the 32- /
+  96-channel layers and the head (whose 2 x 6 output columns keep the update as a kernel of its own) inside the same
+  sampler graph."""
   from gddim_b200 import configs
   from oracle import ncsnpp as on
   cfg = configs.cld_simple_cifar10()

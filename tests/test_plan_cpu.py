@@ -67,9 +67,9 @@ def test_unsupported_width_is_rejected_at_context_creation():
 
 def test_simple_cifar10_nf32_plans():
   """simple_cifar10 (cld_jax/configs/simple_cifar10_config.py:45: nf = 32, ch_mult (1, 2, 2, 2), four res-blocks, naive
-  resampling, positional embedding): 32 / 64 / 96 / 128-channel layers.  The 64- and 128-channel ones are tcgen05 GEMMs
-  (GroupNorm epilogue included); the 32- / 96-channel ones have no 64-wide K block and keep the separate GroupNorm pass in
-  front of a CUDA-core GEMM -- the planner must not attach a GroupNorm epilogue to them."""
+  resampling, positional embedding): 32 / 64 / 96 / 128-channel layers.  Layers whose input has 32 or 96 channels are
+  planned pixel-paired (unet.cpp pack_conv_paired: [B,H,W,c] read as [B,H,W/2,2c], so that a K block is 64 channels wide)
+  and keep their GroupNorms as separate passes; the 64- / 128-channel ones take the usual path, GroupNorm epilogue included."""
   model = net.ScoreNet(configs.cld_simple_cifar10(), cld=True)
   plan = model.plan(8)
   tags = collections.Counter(t.split("/", 1)[-1] for t, _ in plan)

@@ -1,4 +1,5 @@
-"""A short sampler call for ncu (update / DCT kernels): usage prof_sampler.py cld|blur [batch] [nfe]"""
+"""A short sampler call for ncu (update / DCT kernels): usage prof_sampler.py cld|blur [batch] [nfe] [deep]
+(`deep`: the full accr_dcifar10 network instead of the narrowed one -- for captures of the head convolution + update)"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -10,7 +11,9 @@ inv = lambda x: (x + 1.) / 2.
 rng = np.random.default_rng(0)
 if kind == "cld":
   from gddim_b200.cld import sampling, sde_lib
-  cfg = configs.cld_accr_dcifar10(); cfg.model.nf, cfg.model.num_res_blocks = 64, 1      # small net: the update kernels are what is profiled
+  cfg = configs.cld_accr_dcifar10()
+  if not (len(sys.argv) > 4 and sys.argv[4] == "deep"):
+    cfg.model.nf, cfg.model.num_res_blocks = 64, 1      # small net: the update kernels are what is profiled
   model = net.ScoreNet(cfg, cld=True); model.init_params(seed=1, nondegenerate=True)
   fn = sampling.get_deis_sampler(sde_lib.from_config(cfg), model, (32, 32, 3), nfe, inv, 2, ts_order=2, denoising=True)
   fn.core.use_graph = False

@@ -6,6 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC, OUT = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
 HBM = PEAKS.get("hbm_gbs", 6551.4)
+PFX = os.environ.get("PFX", "r02")     # PFX=r02f: the captures of tools/profile_r02_final.sh -> profiles/r02f_ncu_summary.md
 WANT = collections.OrderedDict([
     ("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
@@ -29,12 +30,12 @@ def to_us(v, unit):
 
 def main():
   commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-  lines = [f"# r02 ncu captures (commit {commit}; `tools/profile_r02.sh`, deep NCSN++ batch 256, `--set full --clock-control none`)", "",
+  lines = [f"# {PFX} ncu captures (commit {commit}; `tools/profile_r02.sh` / `tools/profile_r02_final.sh`, deep NCSN++ batch 256, `--set full --clock-control none`)", "",
            f"HBM peak for the fractions: {HBM} GB/s (MEASURED_PEAKS.json).  DRAM bytes are per launch; cold-cache, serialised launches.", "",
            "| capture | kernel | time us | DRAM rd MB | DRAM wr MB | DRAM GB/s | frac of HBM peak | tensor pipe % | XU pipe % | issue % | L2 hit % | regs | grid x cluster |",
            "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
   for f in sorted(os.listdir(SRC)):
-    if not (f.startswith("r02_") and f.endswith("_raw.csv")):
+    if not (f.startswith(PFX + "_") and f.endswith("_raw.csv")):
       continue
     rows = list(csv.reader(open(os.path.join(SRC, f))))
     if len(rows) < 3:
@@ -52,11 +53,11 @@ def main():
       gbs = (rd + wr) / (t * 1e-6) * 1e-9
       g = lambda k: d.get(k, ("", ""))[0]
       name = d.get("name", "?").split("(")[0][-70:]
-      lines.append(f"| {f[4:-8]} | `{name}` | {t:.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | {gbs:.0f} | {gbs / HBM:.2f} | {g('tensor_pipe_pct')} | "
+      lines.append(f"| {f[len(PFX) + 1:-8]} | `{name}` | {t:.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | {gbs:.0f} | {gbs / HBM:.2f} | {g('tensor_pipe_pct')} | "
                    f"{g('xu_pipe_pct')} | {g('issue_pct')} | {g('l2_hit_pct')} | {g('regs')} | {g('grid')} x {g('cluster')} |")
       os.makedirs(OUT, exist_ok=True)
   # launch list: per-kernel totals of one evaluation
-  p = os.path.join(SRC, "r02_launches.csv")
+  p = os.path.join(SRC, PFX + "_launches.csv")
   if os.path.exists(p):
     rows = [r for r in csv.reader(open(p)) if len(r) > 5 and r[0].strip('"').isdigit()]
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -72,9 +73,9 @@ def main():
               "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
       lines.append(f"| `{k[-90:]}` | {v[0]} | {v[1]:.0f} | {v[1] / tot:.3f} |")
-    with open(os.path.join(OUT, "r02_ncu_launches.csv"), "w") as o:
+    with open(os.path.join(OUT, PFX + "_ncu_launches.csv"), "w") as o:
       o.write(open(p).read())
-  p = os.path.join(SRC, "r02_gemm_traffic.csv")
+  p = os.path.join(SRC, PFX + "_gemm_traffic.csv")
   if os.path.exists(p):
     rows = list(csv.reader(open(p)))
     hdr = next(r for r in rows if "Metric Name" in r)
@@ -93,11 +94,11 @@ def main():
     if n:
       json.dump({"commit": commit, "launches": n, "dram_bytes_per_launch": tot_b / n, "dram_bytes_per_evaluation": tot_b,
                  "avg_launch_us_under_ncu": tot_t / n, "how": "ncu dram__bytes_read.sum + dram__bytes_write.sum over every conv_gemm_umma launch of one evaluation (tools/profile_r02.sh)"},
-                open(os.path.join(OUT, "r02_gemm_traffic.json"), "w"), indent=1)
-      lines += ["", f"## GEMM family DRAM traffic: {n} launches, {tot_b / 1e9:.2f} GB per evaluation, {tot_b / n / 1e6:.1f} MB per launch (profiles/r02_gemm_traffic.json)"]
-      with open(os.path.join(OUT, "r02_gemm_traffic.csv"), "w") as o:
+                open(os.path.join(OUT, PFX + "_gemm_traffic.json"), "w"), indent=1)
+      lines += ["", f"## GEMM family DRAM traffic: {n} launches, {tot_b / 1e9:.2f} GB per evaluation, {tot_b / n / 1e6:.1f} MB per launch (profiles/{PFX}_gemm_traffic.json)"]
+      with open(os.path.join(OUT, PFX + "_gemm_traffic.csv"), "w") as o:
         o.write(open(p).read())
-  open(os.path.join(OUT, "r02_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
+  open(os.path.join(OUT, PFX + "_ncu_summary.md"), "w").write("\n".join(lines) + "\n")
   print("\n".join(lines[:40]))
 
 
