@@ -145,7 +145,10 @@ int gddim_dct2d_32(const float* in_dev, float* out_dev, int batch, int C, int fo
  * Wt [N, w_ld] with k = w_koff + seg-major, tap-major, channel-minor.  epi = 1: row softmax (N == 256).
  * epi = 2: the GroupNorm (+ swish) that FOLLOWS the convolution (layerspp.py:218 h = act(GroupNorm_1(h))) applied by
  * the epilogue itself: out16 = act(GN(out)) with flax semantics (eps, contiguous groups, statistics per image);
- * gn_gamma / gn_beta [N], out32 / residual / rowscale must be NULL; geometries: gddim_gemm_gnf_supported. */
+ * gn_gamma / gn_beta [N], out32 / residual / rowscale must be NULL; geometries: gddim_gemm_gnf_supported.
+ * Channel counts (a*_c): multiples of 64 run on the tcgen05 kernel; other multiples of 16 run on the CUDA-core kernel
+ * whatever `impl` says (linear epilogue only).  The network itself never needs that: its 32- / 96-channel layers are
+ * planned pixel-paired. */
 typedef struct {
   const void* a0; int a0_ctot, a0_coff, a0_c, a0_taps;
   const void* a1; int a1_ctot, a1_coff, a1_c, a1_taps;      /* a1 = NULL: single segment */
@@ -287,8 +290,8 @@ int gddim_sample_noise(gddim_sampler* s, const float* u, float* x, float* v, int
                        float* trace_dev, const float* noise_dev, void* stream);
 /* kernels launched (or replayed through CUDA graphs) by this sampler so far */
 long long gddim_sampler_launch_count(const gddim_sampler* s);
-/* measurement hook: the sampler's per-step update kernel (deis.multistep_ab_step at full order / the blur DCT-update-IDCT
- * step) launched `iters` times on the sampler's own buffers; average launch time (CUDA events on `stream`) and the
+/* measurement hook: the sampler's per-step update KERNEL (deis.multistep_ab_step at full order / the blur DCT-update-IDCT
+ * step; deterministic CLD calls apply the same update inside the head convolution's epilogue instead) launched `iters` times on the sampler's own buffers; average launch time (CUDA events on `stream`) and the
  * algorithmic bytes of one launch, (order+3) state arrays for CLD, 4 for blur */
 int gddim_sampler_time_update(gddim_sampler* s, int batch, int iters, double* ms_per_launch, double* bytes_per_launch,
                               void* stream);

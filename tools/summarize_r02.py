@@ -69,7 +69,9 @@ def main():
         continue
       agg[name][0] += 1; agg[name][1] += us
     tot = sum(v[1] for v in agg.values())
-    lines += ["", f"## launch list of one evaluation ({len(rows)} launches, {tot / 1e3:.2f} ms serialised; shares are what to compare with bench.py)", "",
+    what = "launch list of one evaluation" if PFX == "r02" else \
+        "the first launches of `python bench.py --steps 2 --warmup 1` (150 time-embedding `dense_kernel` launches of sampler creation, then the first evaluations with the update inside the head convolution: no `cld_step` launches)"
+    lines += ["", f"## {what} ({len(rows)} launches, {tot / 1e3:.2f} ms serialised; shares are what to compare with bench.py)", "",
               "| kernel | launches | total us | share |", "|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
       lines.append(f"| `{k[-90:]}` | {v[0]} | {v[1]:.0f} | {v[1] / tot:.3f} |")
