@@ -234,7 +234,9 @@ def test_fused_attention_projection(B, reverse):
   assert rel_l2(out.reshape(B, T, Cc).cpu().numpy(), ref.numpy()) < 1e-3
 
 
-@pytest.mark.parametrize("B,reverse,H", [(1, 0, 16), (3, 1, 16), (8, 0, 16), (2, 1, 32)])
+@pytest.mark.parametrize("B,reverse,H", [(1, 0, 16), (3, 1, 16), (8, 0, 16), (2, 1, 32),
+                                         # more tiles than SMs: the persistent kernel's CTAs walk 2..5 tiles each
+                                         (150, 0, 16), (77, 1, 16), (45, 0, 32)])
 def test_gn_fused_into_qkv_projection(B, reverse, H):
   """gn_qkv_kernel: GroupNorm apply in the A-operand path of the q/k/v projection == gn_apply followed by the N = 768
   GEMM, bit for bit (same x*a+b, same fp16 rounding, same accumulation order, same epilogue).  H = 32: the 1024-token
