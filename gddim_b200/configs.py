@@ -72,6 +72,12 @@ def blur_ddpm_deep_cifar10(sigma_blur_max=10.0):
   return _blur_base(_common_model(sigma_blur_max=sigma_blur_max))
 
 
+def blur_simple_cifar10(sigma_blur_max=10.0):
+  """blur_jax/configs/simple_cifar10_config.py:36-63 (nf = 32, same model section as the CLD one)."""
+  return _blur_base(_common_model(nf=32, num_res_blocks=4, fir=False, progressive_input="none",
+                                  embedding_type="positional", ema_rate=0.999, sigma_blur_max=sigma_blur_max))
+
+
 def blur_ddpmpp_cifar10(sigma_blur_max=10.0):
   return _blur_base(_common_model(num_res_blocks=4, fir=False, progressive_input="none",
                                   embedding_type="positional", sigma_blur_max=sigma_blur_max))

@@ -107,6 +107,28 @@ def test_simple_cifar10_nf32_forward_matches_oracle():
   a = model.forward(x, 0.7)
   b = model.forward(x[:1].copy(), 0.7)
   assert rel_l2(b, a[:1]) < 1e-5                              # an image does not depend on its batch mates
+  # precise-weights mode through the paired packer ((hi, lo) pairs): the weight half of the operand rounding disappears
+  want = on.forward(p, cfg, x, 999 * 0.7)
+  pm = net.ScoreNet(cfg, cld=True, precise=True)
+  pm.set_params(p)
+  e_fast, e_prec = rel_l2(a, want), rel_l2(pm.forward(x, 0.7), want)
+  print(f"simple_cifar10 (nf=32): fp16 weights {e_fast:.2e}, (hi, lo) weights {e_prec:.2e}")
+  assert e_prec < 0.85 * e_fast
+
+
+def test_blur_simple_cifar10_nf32_forward_matches_oracle():
+  """blur_jax/configs/simple_cifar10_config.py: three data channels -- the pixel-paired head stores 2 x 3 columns."""
+  from gddim_b200 import configs, net
+  from oracle import ncsnpp as on
+  cfg = configs.blur_simple_cifar10(1.0)
+  model = net.ScoreNet(cfg, cld=False)
+  p = model.init_params(seed=23, nondegenerate=True)
+  x = np.random.default_rng(6).standard_normal((2, 32, 32, 3)).astype(np.float32)
+  got = model.forward(x, 0.4)
+  want = on.forward(p, cfg, x, 999 * 0.4)
+  err = rel_l2(got, want)
+  print(f"blur simple_cifar10 (nf=32) forward: rel-L2 {err:.3e}")
+  assert np.isfinite(got).all() and err < FWD_TOL
 
 
 def test_256x256_forward_matches_oracle():
