@@ -970,9 +970,9 @@ int gemm_launch(const GemmOp* op, int impl, cudaStream_t st) {
       if (!gemm_head_update_supported(op, op->upd)) GEMM_FAIL("conv_gemm: head update: unsupported layer / step (see gemm_head_update_supported)");
       a.upd_on = 1;
       a.upd.u = u.u; a.upd.u_out = u.u_out;
-      // unused history slots read the oldest used one again (the loads are unconditional, the sums are not)
-      for (int j = 0; j < 4; ++j) a.upd.eps[j] = j < u.n_eps ? u.eps[j] : u.eps[u.n_eps - 1];
-      if (u.n_eps == 1) for (int j = 1; j < 4; ++j) a.upd.eps[j] = u.u;       // (eps[0] is being written by this launch)
+      // the history loads are unconditional (registers), the sums are not: unused slots read rows of this launch's own A
+      // operand -- valid (>= 128 bytes per pixel), never written by this launch (the loads are ld.global.nc)
+      for (int j = 0; j < 4; ++j) a.upd.eps[j] = (j >= 1 && j < u.n_eps) ? u.eps[j] : reinterpret_cast<const float*>(op->seg[0].ptr);
       a.upd.n_eps = u.n_eps; a.upd.mixed = u.mixed;
       for (int j = 0; j < 5; ++j) for (int k = 0; k < 4; ++k) a.upd.coef[j][k] = u.coef[j][k];
       for (int k = 0; k < 4; ++k) a.upd.mixm[k] = u.mixm[k];
