@@ -158,7 +158,7 @@ def run_reference(args):
                                      "restatement of cld_jax sampler (JAX not installable offline)"},
           "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
           "gpu_launches": 0}
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def run_ours(args):
@@ -353,12 +353,30 @@ def run_ours(args):
           "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_hbm": roof_hbm}
   if cpu is not None:
     line["cpu_baseline"] = cpu
-  print(json.dumps(line), flush=True)
+  emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+  """The one JSON line of the contract, on the process's ORIGINAL stdout (see main)."""
+  data = (json.dumps(line) + "\n").encode()
+  if _JSON_FD is None:
+    sys.stdout.write(data.decode()); sys.stdout.flush()
+  else:
+    os.write(_JSON_FD, data)
 
 
 def main():
-  # NCCL prints its version banner (and NCCL_DEBUG output) on stdout; the contract is ONE JSON line there
+  # NCCL prints its version banner (and NCCL_DEBUG output) on stdout -- from C, behind Python's back; the contract is ONE
+  # JSON line there.  Everything this process (and the libraries it loads) writes to fd 1 goes to stderr instead; only
+  # emit() writes to the original stdout.
+  global _JSON_FD
   os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+  sys.stdout.flush()
+  _JSON_FD = os.dup(1)
+  os.dup2(2, 1)
   args = parse()
   if args.impl == "reference":
     run_reference(args)
