@@ -638,11 +638,10 @@ __device__ __forceinline__ void epi_tile_gnf(const EpiCtx<BLOCK_N, MT>& cx, cons
   const int cpg = p.gn_cpg;
   const int rpi = p.gn_rpi;
   const bool split = rpi < 32;                       // 4x4 images: rows 0-15 and 16-31 of a warp are different images
-  const int G = BLOCK_N / cpg;                       // groups per N tile
   const long long mwarp = cx.m0;                     // first row of this warp in sub-tile 0 (tile row0 + quad * 32)
   const long long mtile = cx.m0 - quad * 32;
 
-  const bool stamp = gx.warp == 0 && lane == 0;
+  [[maybe_unused]] const bool stamp = gx.warp == 0 && lane == 0;
   GDDIM_STAMP(p, stamp, gx.tile_seq, 0);
   ptx::mbar_wait(cx.tfull, cx.tfull_phase);
   ptx::tc_fence_after();

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
   __half* dst = p.dst16 ? p.dst16 + (long long)b * Pout * C + c : nullptr;
   __half* raw = p.raw16 ? p.raw16 + (long long)b * Pout * C + c : nullptr;
 
-  if (RS == RS_NONE) {
+  if constexpr (RS == RS_NONE) {
     // straight path: 4 pixels in flight per thread
     int pix = pbeg + row;
     for (; pix + 3 * p.rows < pend; pix += 4 * p.rows) {
@@ -303,44 +303,44 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyArgs p) {
       }
     }
     return;
-  }
-
-  for (int pix = pbeg + row; pix < pend; pix += p.rows) {
-    const int ox = pix % p.Wo, oy = pix / p.Wo;
-    int ny, nx, y0, x0;
-    float wy[4], wx[4];
-    tap_table<RS>(oy, ox, ny, nx, y0, x0, wy, wx);
-    float accn[8], accr[8];
+  } else {
+    for (int pix = pbeg + row; pix < pend; pix += p.rows) {
+      const int ox = pix % p.Wo, oy = pix / p.Wo;
+      int ny, nx, y0, x0;
+      float wy[4], wx[4];
+      tap_table<RS>(oy, ox, ny, nx, y0, x0, wy, wx);
+      float accn[8], accr[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { accn[j] = 0.f; accr[j] = 0.f; }
-    for (int i = 0; i < ny; ++i) {
-      const int iy = y0 + i;
-      if (iy < 0 || iy >= p.H) continue;
-      for (int j = 0; j < nx; ++j) {
-        const int ix = x0 + j;
-        if (ix < 0 || ix >= p.W) continue;
-        const float w = wy[i] * wx[j];
-        const float* q = base + ((long long)iy * p.W + ix) * cs;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(q));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(q + 4));
-        const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      for (int j = 0; j < 8; ++j) { accn[j] = 0.f; accr[j] = 0.f; }
+      for (int i = 0; i < ny; ++i) {
+        const int iy = y0 + i;
+        if (iy < 0 || iy >= p.H) continue;
+        for (int j = 0; j < nx; ++j) {
+          const int ix = x0 + j;
+          if (ix < 0 || ix >= p.W) continue;
+          const float w = wy[i] * wx[j];
+          const float* q = base + ((long long)iy * p.W + ix) * cs;
+          const float4 v0 = __ldg(reinterpret_cast<const float4*>(q));
+          const float4 v1 = __ldg(reinterpret_cast<const float4*>(q + 4));
+          const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          accr[k] += w * x[k];
-          if (p.do_norm) {
-            float t = x[k] * a[k] + bb[k];
-            if (p.silu) t = silu_f(t);
-            accn[k] += w * t;
+          for (int k = 0; k < 8; ++k) {
+            accr[k] += w * x[k];
+            if (p.do_norm) {
+              float t = x[k] * a[k] + bb[k];
+              if (p.silu) t = silu_f(t);
+              accn[k] += w * t;
+            }
           }
         }
       }
-    }
-    const long long o = (long long)pix * C;
-    if (dst) store8(dst + o, accn);
-    if (raw) {
+      const long long o = (long long)pix * C;
+      if (dst) store8(dst + o, accn);
+      if (raw) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) accr[k] *= p.raw_scale;
-      store8(raw + o, accr);
+        for (int k = 0; k < 8; ++k) accr[k] *= p.raw_scale;
+        store8(raw + o, accr);
+      }
     }
   }
 }
