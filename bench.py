@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 
 METRIC = "CIFAR10 32x32 images/sec @ 50 NFE deis_order=2 (CLD, deep NCSN++)"
 GFLOP_PER_IMG_EVAL = {"deep": 37.168, "ddpmpp": 21.707}
-TRAFFIC_FILE = "r02_gemm_traffic.json"                         # ncu DRAM pass of the GEMM family (tools/profile.sh)
+TRAFFIC_FILE = "r02f_gemm_traffic.json"                         # ncu DRAM pass of the GEMM family (tools/profile.sh)
 
 
 def parse():
