@@ -79,3 +79,11 @@ def test_simple_cifar10_nf32_plans():
   assert tags["conv1"] > 0 and tags["conv1_gn1"] > 0                                   # both kinds of conv1 are present
   n_params = sum(int(__import__("numpy").prod(shape)) for shape, _, _ in model.specs().values())
   assert n_params == 3_883_686
+
+
+def test_blur_simple_cifar10_nf32_plans_like_the_cld_one():
+  """blur_jax/configs/simple_cifar10_config.py: same model section, three data channels instead of six."""
+  cld = [t for t, _ in net.ScoreNet(configs.cld_simple_cifar10(), cld=True).plan(4)]
+  blur = [t for t, _ in net.ScoreNet(configs.blur_simple_cifar10(1.0), cld=False).plan(4)]
+  assert cld == blur and blur[0] == "stem_im2col" and blur[-1] == "head"
+
